@@ -1,0 +1,157 @@
+/* fokl_b200.h -- C ABI of the B200-native FoKL.fit hot path (libfokl_b200.so).
+ *
+ * The reference (ESMS-Group-Public/FoKL-GPy) is pure Python and has no FFI boundary of its own; every
+ * entry point below replaces a *stage* of `FoKL.fit` / its nested `gibbs` closure
+ * (src/FoKL/FoKLRoutines.py, "FR").  The Python host (fokl-gpy_b200/FoKL/_engine.py) binds these
+ * with ctypes; INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success and a negative FOKL_E* code on failure; nothing throws
+ *     across the ABI; fokl_last_error(ctx) returns a human-readable message for the last failure.
+ *   - pointers documented "dev" are device pointers owned by the caller (e.g. torch tensors'
+ *     data_ptr()); pointers documented "host" are plain host memory, read before the call returns.
+ *   - work is enqueued on the ctx stream and is asynchronous unless stated; one ctx per
+ *     (process, device); a ctx is not thread-safe.
+ *   - all floating point is IEEE float64; matrices are column-major unless stated.
+ */
+#ifndef FOKL_B200_H
+#define FOKL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FOKL_ABI_VERSION 1
+
+#define FOKL_OK 0
+#define FOKL_EINVAL (-1)   /* bad argument                                  */
+#define FOKL_ECUDA (-2)    /* CUDA runtime error (see fokl_last_error)      */
+#define FOKL_ENOMEM (-3)   /* workspace allocation failed                   */
+#define FOKL_ERANGE (-4)   /* inputs not normalised to [0, 1] (FR:590-591)  */
+#define FOKL_ESTATE (-5)   /* call sequence error (e.g. phis not set)       */
+
+#define FOKL_KERNEL_CUBIC 0      /* 'Cubic Splines'          (FR:834-836) */
+#define FOKL_KERNEL_BERNOULLI 1  /* 'Bernoulli Polynomials'  (FR:841-843) */
+
+#define FOKL_RNG_NONE 0      /* BIC / betahat only, no chain                                   */
+#define FOKL_RNG_INJECTED 1  /* variates supplied by the caller (numpy legacy stream, parity)  */
+#define FOKL_RNG_PHILOX 2    /* counter-based Philox4x32-10 on device (free-running)           */
+
+typedef struct fokl_ctx fokl_ctx;
+
+/* ---- context ------------------------------------------------------------------------------- */
+
+int fokl_abi_version(void);
+
+/* device: CUDA ordinal.  cuda_stream: a cudaStream_t to enqueue on, or NULL for a ctx-owned stream. */
+int fokl_ctx_create(fokl_ctx **out, int device, void *cuda_stream);
+int fokl_ctx_destroy(fokl_ctx *ctx);
+const char *fokl_last_error(fokl_ctx *ctx);
+/* blocks until all work enqueued on the ctx stream has finished; reports deferred range errors. */
+int fokl_ctx_synchronize(fokl_ctx *ctx);
+/* number of kernels this ctx has launched since creation (for bench.py's gpu_launches). */
+int64_t fokl_launch_count(fokl_ctx *ctx);
+
+/* ---- basis tables: replaces getKernels.sp500()/bernoulli() output consumed at FR:1480-1482 ----
+ * cubic:     tab (host) [n_orders][n_piece][4]  -- phis[s][k][piece] transposed to (s, piece, k)
+ * bernoulli: tab (host) [n_orders][row_len]     -- row n holds its n + 2 monomial coefficients      */
+int fokl_set_phis_cubic(fokl_ctx *ctx, const double *tab, int n_orders, int n_piece);
+int fokl_set_phis_bernoulli(fokl_ctx *ctx, const double *tab, int n_orders, int row_len);
+
+/* ---- K1: design-matrix columns, replaces the triple loop FR:1446-1485 (+ FR:570-589) -----------
+ * x      dev  normalised inputs, column-major N x M, column k at x + k*ldx
+ * terms  host C x M row-major; terms[j][k] = order of the basis function of input k in term j, 0 = absent
+ *             (one row of `discmtx`, FR:1473)
+ * Xnew   dev  output: column j written to Xnew + j*ld (N doubles each); ld % 2 == 0, Xnew 16B-aligned
+ * X[i][j] = prod_{k: terms[j][k] != 0} phi_{terms[j][k]}(x[i][k]), multiplied in increasing k.     */
+int fokl_basis_build(fokl_ctx *ctx, int kernel, const double *x, int64_t n, int64_t ldx, int m,
+                     const int16_t *terms, int c, double *Xnew, int64_t ld);
+
+/* fill a column with ones (X[:, 0], FR:1436). */
+int fokl_fill_ones(fokl_ctx *ctx, double *col, int64_t n);
+
+/* ---- K2: Gram / projection update, replaces XtX = X'X, Xty = X'y (FR:1492-1494) ----------------
+ * Computes only what is new when columns [p_old, p_old + c) were appended to X:
+ *   block[(i) * c + j] = sum_n A_i[n] * X[n][p_old + j],  i = 0 .. p_old + c   (row-major (p+1) x c)
+ * where A_i = column i of X for i < p_old + c and A_{p_old+c} = y.  Deterministic summation order.   */
+int fokl_gram_update(fokl_ctx *ctx, const double *X, int64_t ld, int64_t n, int p_old, int c,
+                     const double *y, double *block);
+
+/* moments of y: out (dev, 3 doubles) = { n, sum y, sum y^2 } (dtd, FR:1374). */
+int fokl_y_moments(fokl_ctx *ctx, const double *y, int64_t n, double *out);
+
+/* scatter a (reduced) block into the symmetric master Gram G (dev, row-major ldg x ldg) and Xty (dev):
+ * G[i][p_old+j] = G[p_old+j][i] = block[i][j]; Xty[p_old+j] = block[p_old+c][j]. */
+int fokl_gram_scatter(fokl_ctx *ctx, const double *block, int p_old, int c, double *G, int64_t ldg,
+                      double *Xty);
+
+/* keep (host, ascending, p_new entries): G_out[a][b] = G[keep[a]][keep[b]], Xty_out[a] = Xty[keep[a]]. */
+int fokl_gram_compact(fokl_ctx *ctx, const double *G, int64_t ldg, const double *Xty, const int32_t *keep,
+                      int p_new, double *G_out, int64_t ldg_out, double *Xty_out);
+
+/* move column keep[a] of X to position a (keep ascending, keep[a] >= a): the X <- xers step (FR:1695). */
+int fokl_columns_compact(fokl_ctx *ctx, double *X, int64_t ld, int64_t n, const int32_t *keep, int p_new);
+
+/* ---- K3/K4: per-candidate spectral factorisation, betahat, BIC, Gibbs chain ---------------------
+ * replaces, per `gibbs` invocation: eigh (FR:1499), betahat (FR:1502-1504), the draw loop
+ * (FR:1519-1548), BIC (FR:1551-1554) and the column statistics the selection loop derives from the
+ * draws (FR:1656-1658, 1671).                                                                        */
+typedef struct fokl_hypers {
+    double a, b, atau, btau;   /* inverse-gamma hyper-parameters (FR:1304-1307)           */
+    double sigsqd0, tausqd0;   /* chain start (FR:1371-1372)                              */
+    double yty, sum_y;         /* data moments (global over all ranks)                    */
+    int64_t n;                 /* number of data rows (global)                            */
+    int32_t draws;             /* chain length D = burnin + draws (FR:1309)               */
+    int32_t stat_from0;        /* ceil(D/2)      first row of the "mean0" window (FR:1658)*/
+    int32_t stat_from1;        /* ceil(D/2 + 1)  first row of mean1/std1 window (FR:1656) */
+    int32_t reserved;
+} fokl_hypers;
+
+/* Candidate c uses the p_c = set_offsets[c+1] - set_offsets[c] columns col_sets[set_offsets[c] ..] of G.
+ * Packed output offsets (both sides compute them the same way):
+ *   vec_off[c] = sum_{c' < c} p_c'          (betahat, lamb, stats/3)
+ *   mat_off[c] = sum_{c' < c} p_c'^2        (Q, column-major p x p, ascending eigenvalues like eigh)
+ *   betas for candidate c start at D * vec_off[c], row-major D x p_c; sigs/taus at D * c.
+ * run_chain (host, n_cand flags or NULL = all): 0 -> only eig/betahat/ev for that candidate.
+ * rng_mode FOKL_RNG_INJECTED: variates (dev) holds for candidate c, at D * (vec_off[c] + 2c), D rows of
+ *   [z_0 .. z_{p-1}, g1, g2] = normal(p), standard_gamma(astar), standard_gamma(atau_star) in the
+ *   order one reference `gibbs` call consumes them (FR:1527, 1541, 1547).
+ * rng_mode FOKL_RNG_PHILOX: stream_ids (host, n_cand) select independent Philox streams of `seed`.
+ * sign_fix (dev, packed like betahat, or NULL): z_j is multiplied by sign_fix[j] (parity harness only:
+ *   aligns eigenvector signs with another eigensolver).
+ * Outputs (dev; any of betahat/lamb/Q/betas/sigs/taus/stats may be NULL):
+ *   ev[c]        BIC (FR:1554), without the aic adjustment (FR:1654, host side)
+ *   stats        per candidate 3 x p_c: row 0 mean over rows [stat_from1, D), row 1 std (ddof 0) over the
+ *                same rows, row 2 mean over rows [stat_from0, D)
+ *   info[c]      bit 0: bstar < 0 seen (FR:1538); bits 8..: Jacobi sweeps used                      */
+int fokl_candidates_eval(fokl_ctx *ctx, const double *G, int64_t ldg, const double *Xty,
+                         const int32_t *col_sets, const int32_t *set_offsets, int n_cand,
+                         const fokl_hypers *hyp, const uint8_t *run_chain, int rng_mode, uint64_t seed,
+                         const uint64_t *stream_ids, const double *variates, const double *sign_fix,
+                         double *ev, double *betahat, double *lamb, double *Q, double *betas,
+                         double *sigs, double *taus, double *stats, int32_t *info);
+
+/* ---- checks / "next" rows ------------------------------------------------------------------- */
+
+/* residual moments of an explicit model: out (dev, 2 doubles) = { sum r, sum r^2 }, r = y - X[:, :p] beta
+ * (the N-length form of FR:1551; used to cross-check the Gram-only BIC at full size). */
+int fokl_residual_moments(fokl_ctx *ctx, const double *X, int64_t ld, int64_t n, int p,
+                          const double *beta, const double *y, double *out);
+
+/* evaluate (FR:966-969): out[i][d] = sum_j X[i][j] * betas[d][j]; X column-major (ld), betas row-major
+ * n_draws x p (dev), out row-major n x n_draws (dev). */
+int fokl_predict_draws(fokl_ctx *ctx, const double *X, int64_t ld, int64_t n, int p, const double *betas,
+                       int n_draws, double *out);
+
+/* clean/_normalize on device (FR:377, 436-437): minmax_out (dev, 2*m) = per-column min, max of x
+ * (column-major n x m, ldx); then fokl_normalize applies x = (x - min) / (max - min) in place with
+ * minmax (host, 2*m). */
+int fokl_column_minmax(fokl_ctx *ctx, const double *x, int64_t n, int64_t ldx, int m, double *minmax_out);
+int fokl_normalize(fokl_ctx *ctx, double *x, int64_t n, int64_t ldx, int m, const double *minmax);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FOKL_B200_H */

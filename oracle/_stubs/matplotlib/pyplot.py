@@ -1,0 +1,7 @@
+"""No-op pyplot stub (see package docstring)."""
+
+
+def __getattr__(name):
+    def _noop(*args, **kwargs):
+        return None
+    return _noop

@@ -1,0 +1,230 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (build container only).
+
+TEST INFRASTRUCTURE.  Run from the repo root:   python oracle/gen_golden.py [case ...]
+
+Each fixture stores the already-normalised inputs the reference trained on, the hyper-parameters, the
+numpy seed, and the reference's outputs (betas tail + column moments, mtx, evs, number of `gibbs`
+calls, a digest of the legacy-RNG end state, and the Gram / eigh results of selected calls).
+"""
+import hashlib
+import os
+import sys
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, _HERE)
+import ref_harness  # noqa: E402
+import spline_table  # noqa: E402
+
+REF = '/root/reference'
+GOLD = os.path.join(os.path.dirname(_HERE), 'tests', 'golden')
+
+
+def rng_digest():
+    st = np.random.get_state()
+    h = hashlib.sha256(st[1].tobytes() + bytes(str((st[2], st[3], repr(st[4]))), 'ascii')).hexdigest()
+    return h
+
+
+def cubic_phis():
+    tab = np.load(os.path.join(GOLD, 'phis_cubic_48.npy'))
+    return spline_table.to_phis(tab)
+
+
+def run_case(name, make_model, fit_args, fit_kwargs, seed, shim=False, keep_calls=(0, 1, -1)):
+    FR = ref_harness.load_reference(distinct_perms_shim=shim)
+    rec = []
+    real_eigh = FR.eigh
+
+    def eigh_hook(a, *args, **kw):
+        lam, q = real_eigh(a, *args, **kw)
+        rec.append((np.array(a), lam.copy(), q.copy()))
+        return lam, q
+
+    FR.eigh = eigh_hook
+    try:
+        np.random.seed(seed)
+        model = make_model(FR)
+        betas, mtx, evs = model.fit(*fit_args, **fit_kwargs)
+        digest = rng_digest()
+    finally:
+        FR.eigh = real_eigh
+    out = dict(
+        inputs=np.asarray(model.inputs, dtype=np.float64), data=np.asarray(model.data, dtype=np.float64),
+        seed=seed, kernel=model.kernel, a=float(model.a), b=float(model.b), atau=float(model.atau),
+        btau=float(model.btau), tolerance=int(model.tolerance), burnin=int(model.burnin),
+        draws=int(model.draws), way3=bool(model.way3), aic=bool(model.aic), gimmie=bool(model.gimmie),
+        threshav=float(model.threshav), threshstda=float(model.threshstda),
+        threshstdb=float(model.threshstdb),
+        betas_tail=betas[-50:], betas_mean=betas.mean(axis=0), betas_std=betas.std(axis=0),
+        betas_shape=np.array(betas.shape), mtx=np.asarray(mtx, dtype=np.float64), evs=np.asarray(evs),
+        n_gibbs=len(rec), rng_digest=digest, gram_sizes=np.array([r[0].shape[0] for r in rec]))
+    for tag, idx in zip(('first', 'second', 'last'), keep_calls):
+        if len(rec) > abs(idx):
+            out['xtx_' + tag] = rec[idx][0]
+            out['lamb_' + tag] = rec[idx][1]
+            out['q_' + tag] = rec[idx][2]
+    np.savez_compressed(os.path.join(GOLD, name + '.npz'), **out)
+    print(name, 'gibbs calls', len(rec), 'betas', betas.shape, 'evs', len(evs), 'min ev', float(np.min(evs)))
+    return model
+
+
+# ------------------------------------------------------------------------------------------------
+
+def isotherm_arrays():
+    """examples/isotherm/isotherm_benchmark.ipynb cells 1, 3, 5, 7, 9."""
+    d = os.path.join(REF, 'examples', 'isotherm', 'data')
+    M = 0.0440095
+    R = 8.31446261815324
+    data = np.loadtxt(os.path.join(d, 'data.txt'), skiprows=2)
+    T = data[:, 0]
+    p = data[:, 1] * 1e3
+    q = data[:, 2]
+    T_const = np.where(T[:-1] != T[1:])[0]
+    T_const = np.insert(T_const + 1, [0, len(T_const)], [0, len(T)])
+    n = len(T_const) - 1
+    nd = np.array(list(T_const[i + 1] - T_const[i] for i in range(n)))
+    toth = np.loadtxt(os.path.join(d, 'toth.txt'), skiprows=2)
+    qs = np.repeat(toth[:, 1], nd)
+    mu = p / np.sqrt(2 * np.pi * M * R * T)
+    sigma1 = q / mu / (qs - q)
+    Delta = np.log(sigma1)
+    return 1 / T, np.log(p), Delta, T[T_const[:-1]], qs[T_const[:-1]]
+
+
+def case_isotherm_gp():
+    inv_T, ln_p, Delta, _, _ = isotherm_arrays()
+    T_min, T_max, p_min, p_max = 273.15, 353.15, 67, 102100
+    run_case('isotherm_gp', lambda FR: FR.FoKL(kernel=1, UserWarnings=False, ConsoleOutput=False),
+             ([inv_T, ln_p], Delta),
+             dict(clean=True, minmax=[[1 / T_max, 1 / T_min], [np.log(p_min), np.log(p_max)]]), seed=11)
+
+
+def case_isotherm_qmax():
+    _, _, _, Tq, qmax = isotherm_arrays()
+    run_case('isotherm_qmax',
+             lambda FR: FR.FoKL(kernel=1, UserWarnings=False, ConsoleOutput=False, atau=1e-6),
+             (Tq, qmax), dict(clean=True, minmax=[[273.15, 353.15]]), seed=12)
+
+
+def case_cfg2(changed):
+    import pandas as pd
+    d = pd.read_csv(os.path.join(REF, 'test', 'testdatatest.csv'), dtype=float)
+    inputs = d[['x', 'y']]
+    data = d['data']
+    phis = cubic_phis()
+    if not changed:
+        run_case('cfg2_default', lambda FR: FR.FoKL(phis=phis, UserWarnings=False, ConsoleOutput=False),
+                 (inputs, data), dict(clean=True), seed=102823)
+    else:
+        run_case('cfg2_changed', lambda FR: FR.FoKL(phis=phis, UserWarnings=False, ConsoleOutput=False),
+                 (inputs, data), dict(aic=True, a=3, b=1.8, atau=17, btau=2100.5, tolerance=3, clean=True),
+                 seed=102923)
+
+
+def case_cfg1_sigmoid():
+    d = os.path.join(REF, 'examples', 'sigmoid')
+    xg = np.loadtxt(os.path.join(d, 'x.csv'), dtype=float, delimiter=',')
+    yg = np.loadtxt(os.path.join(d, 'y.csv'), dtype=float, delimiter=',')
+    zg = np.loadtxt(os.path.join(d, 'z.csv'), dtype=float, delimiter=',')
+    m, n = xg.shape
+    x = np.reshape(xg, (m * n, 1), order='F')
+    y = np.reshape(yg, (m * n, 1), order='F')
+    z = np.reshape(zg, (m * n, 1), order='F')
+    phis = cubic_phis()
+    run_case('cfg1_sigmoid',
+             lambda FR: FR.FoKL(phis=phis, a=9, b=0.01, atau=3, btau=4000, aic=True, UserWarnings=False,
+                                ConsoleOutput=False),
+             ([x, y], z), dict(clean=True), seed=0)
+
+
+def synth(n, m, seed):
+    rng = np.random.default_rng(seed)
+    x = rng.random((n, m))
+    y = np.sin(2 * np.pi * x[:, 0]) + 2 * (x[:, 1] - 0.5) ** 2
+    if m > 3:
+        y = y + x[:, 2] * x[:, 3]
+    elif m > 2:
+        y = y + x[:, 1] * x[:, 2]
+    y = y + 0.05 * rng.standard_normal(n)
+    return x, y
+
+
+def case_way3_bernoulli():
+    x, y = synth(400, 4, 21)
+    run_case('way3_bernoulli',
+             lambda FR: FR.FoKL(kernel=1, way3=True, draws=150, burnin=150, UserWarnings=False,
+                                ConsoleOutput=False),
+             (x, y), dict(clean=True), seed=21)
+
+
+def case_way3_cubic():
+    x, y = synth(300, 3, 22)
+    phis = cubic_phis()
+    run_case('way3_cubic',
+             lambda FR: FR.FoKL(phis=phis, way3=True, draws=120, burnin=130, UserWarnings=False,
+                                ConsoleOutput=False),
+             (x, y), dict(clean=True), seed=22)
+
+
+def case_two_way_cubic():
+    x, y = synth(500, 4, 23)
+    phis = cubic_phis()
+    run_case('two_way_cubic',
+             lambda FR: FR.FoKL(phis=phis, draws=100, burnin=100, UserWarnings=False, ConsoleOutput=False),
+             (x, y), dict(clean=True), seed=23)
+
+
+def case_m1():
+    rng = np.random.default_rng(24)
+    x = rng.random(60)
+    y = np.exp(-3 * x) + 0.01 * rng.standard_normal(60)
+    phis = cubic_phis()
+    run_case('m1_cubic',
+             lambda FR: FR.FoKL(phis=phis, draws=100, burnin=100, UserWarnings=False, ConsoleOutput=False),
+             (x, y), dict(clean=True), seed=24)
+
+
+def case_basis_values():
+    """Pin the scalar basis evaluation (FR:807-849) and _inputs_to_phind (FR:544-592)."""
+    FR = ref_harness.load_reference()
+    rng = np.random.default_rng(31)
+    x = np.concatenate([rng.random(300), [0.0, 1.0, 0.5, 1 / 499, 2 / 499, 1e-300, 1 - 2 ** -53]])
+    tab = np.load(os.path.join(GOLD, 'phis_cubic_48.npy'))
+    phis_c = spline_table.to_phis(tab)
+    mc = FR.FoKL(phis=phis_c, UserWarnings=False)
+    _, phind, xsm = mc._inputs_to_phind(x[:, None])
+    orders_c = np.arange(1, 49)
+    vals_c = np.zeros((len(x), len(orders_c)))
+    for i in range(len(x)):
+        for j, o in enumerate(orders_c):
+            c = [phis_c[o - 1][k][phind[i, 0]] for k in range(4)]
+            vals_c[i, j] = mc.evaluate_basis(c, xsm[i, 0])
+    mb = FR.FoKL(kernel=1, UserWarnings=False)
+    orders_b = np.arange(1, 21)
+    vals_b = np.zeros((len(x), len(orders_b)))
+    for i in range(len(x)):
+        for j, o in enumerate(orders_b):
+            vals_b[i, j] = mb.evaluate_basis(mb.phis[o - 1], x[i])
+    np.savez_compressed(os.path.join(GOLD, 'basis_values.npz'), x=x, phind=phind[:, 0], xsm=xsm[:, 0],
+                        cubic=vals_c, bernoulli=vals_b)
+    # the Bernoulli table itself (KAT 4 of SURVEY 8c), converted to a dense array
+    width = max(len(r) for r in mb.phis)
+    bt = np.zeros((len(mb.phis), width))
+    for n_, r in enumerate(mb.phis):
+        bt[n_, :len(r)] = r
+    np.save(os.path.join(GOLD, 'bernoulli_table.npy'), bt)
+    print('basis_values', vals_c.shape, vals_b.shape, bt.shape)
+
+
+CASES = dict(isotherm_gp=case_isotherm_gp, isotherm_qmax=case_isotherm_qmax,
+             cfg2_default=lambda: case_cfg2(False), cfg2_changed=lambda: case_cfg2(True),
+             cfg1_sigmoid=case_cfg1_sigmoid, way3_bernoulli=case_way3_bernoulli,
+             way3_cubic=case_way3_cubic, two_way_cubic=case_two_way_cubic, m1_cubic=case_m1,
+             basis_values=case_basis_values)
+
+if __name__ == '__main__':
+    todo = sys.argv[1:] or list(CASES)
+    for c in todo:
+        CASES[c]()

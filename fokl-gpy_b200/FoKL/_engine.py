@@ -1,0 +1,369 @@
+"""Device engine: owns the HBM-resident state of one `fit` and drives libfokl_b200.so through ctypes.
+
+PyTorch is used only as the carrier of device memory, the CUDA stream and (multi-GPU) the NCCL process
+group; every numerical stage is a hand-written sm_100a kernel behind the C ABI (include/fokl_b200.h).
+
+HBM layout (all float64):
+    x     [M][ldx]     normalised inputs, column-major (one input per row of the tensor), ldx = ceil16(N)
+    y     [ldx]        data
+    X     [Pcap][ld]   design matrix, column-major: X[j] is column j (N doubles), column 0 = ones
+    G     [Gcap][Gcap] master Gram X'X of the columns currently in X (symmetric), Xty [Gcap]
+Multi-GPU: every rank holds N/world rows of x, y, X; Gram blocks are summed with one NCCL allreduce per
+substage, after which every rank owns the full G (axis 1).
+"""
+import ctypes
+import math
+
+import numpy as np
+
+from . import _lib
+
+CUBIC = 'Cubic Splines'
+BERNOULLI = 'Bernoulli Polynomials'
+
+
+def _round_up(v, m):
+    return ((int(v) + m - 1) // m) * m
+
+
+def pack_phis(phis, kernel):
+    """Reference `phis` structure -> dense float64 table (cubic [n][n_piece][4]; Bernoulli [n][width])."""
+    n = len(phis)
+    if kernel == CUBIC:
+        n_piece = len(phis[0][0])
+        tab = np.empty((n, n_piece, 4), dtype=np.float64)
+        for s in range(n):
+            for k in range(4):
+                tab[s, :, k] = phis[s][k]
+        return tab
+    width = max(len(r) for r in phis)
+    tab = np.zeros((n, max(width, 2)), dtype=np.float64)
+    for s in range(n):
+        tab[s, :len(phis[s])] = phis[s]
+    return tab
+
+
+class DeviceDataset:
+    """Normalised inputs and data resident in HBM (this rank's row shard)."""
+
+    def __init__(self, x, y, n, m, ldx):
+        self.x, self.y, self.n, self.m, self.ldx = x, y, n, m, ldx
+
+
+class CandidateResult:
+    __slots__ = ('ev', 'info', 'stats', 'betas', 'sigs', 'taus', 'betahat', 'lamb', 'Q', 'p', 'vec_off', 'mat_off',
+                 'draws')
+
+    def betas_of(self, c):
+        o = self.draws * self.vec_off[c]
+        return self.betas[o:o + self.draws * self.p[c]].view(self.draws, self.p[c])
+
+    def stats_of(self, c):
+        o = 3 * self.vec_off[c]
+        return self.stats[o:o + 3 * self.p[c]].view(3, self.p[c])
+
+
+class Engine:
+    def __init__(self, device=None, group=None):
+        import torch
+        self.torch = torch
+        if not torch.cuda.is_available():
+            raise RuntimeError("FoKL (B200 build) needs a CUDA device: there is no CPU fallback for fit().")
+        self.lib = _lib.load()
+        if device is None:
+            device = torch.device('cuda', torch.cuda.current_device())
+        self.device = torch.device(device)
+        self.dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.group = group
+        self.dist = None
+        self.world = 1
+        self.rank = 0
+        if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()
+                                 and group is not False):
+            self.dist = torch.distributed
+            self.world = self.dist.get_world_size(group if group not in (None, False) else None)
+            self.rank = self.dist.get_rank(group if group not in (None, False) else None)
+            if self.world == 1:
+                self.dist = None
+        if group is False:
+            self.group = None
+        ctx = ctypes.c_void_p()
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        rc = self.lib.fokl_ctx_create(ctypes.byref(ctx), self.dev_index, ctypes.c_void_p(stream))
+        if rc != 0:
+            raise RuntimeError("fokl_ctx_create failed with code %d" % rc)
+        self.ctx = ctx
+        self._phis_key = None
+        self.kernel_id = None
+        self.n_orders = 0
+        self.ds = None
+        self.X = None
+        self.P = 0
+        self.G = self.Xty = self.G2 = self.Xty2 = None
+        self.block = None
+        self.n_global = 0
+        self.sum_y = self.yty = 0.0
+        self.gibbs_launch_batches = 0
+
+    # ------------------------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, 'ctx', None) is not None and self.ctx:
+            self.lib.fokl_ctx_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            msg = self.lib.fokl_last_error(self.ctx)
+            msg = msg.decode() if msg else ''
+            if rc == _lib.ERANGE:
+                raise ValueError(msg)
+            raise RuntimeError("libfokl_b200 error %d: %s" % (rc, msg))
+
+    def synchronize(self):
+        self._ck(self.lib.fokl_ctx_synchronize(self.ctx))
+
+    def launch_count(self):
+        return int(self.lib.fokl_launch_count(self.ctx))
+
+    def _allreduce(self, t):
+        if self.dist is not None:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+
+    # ------------------------------------------------------------------------------------------------
+    def set_phis(self, phis, kernel):
+        key = (id(phis), kernel, len(phis))
+        if key == self._phis_key:
+            return
+        tab = np.ascontiguousarray(pack_phis(phis, kernel))
+        if kernel == CUBIC:
+            self._ck(self.lib.fokl_set_phis_cubic(self.ctx, tab.ctypes.data, tab.shape[0], tab.shape[1]))
+            self.kernel_id = _lib.KERNEL_CUBIC
+        elif kernel == BERNOULLI:
+            self._ck(self.lib.fokl_set_phis_bernoulli(self.ctx, tab.ctypes.data, tab.shape[0], tab.shape[1]))
+            self.kernel_id = _lib.KERNEL_BERNOULLI
+        else:
+            raise ValueError("The kernel %r is not currently supported." % (kernel,))
+        self.n_orders = tab.shape[0]
+        self._phis_key = key
+        self._phis_ref = phis   # keep alive so id() stays unique
+
+    # ------------------------------------------------------------------------------------------------
+    def upload(self, inputs, data):
+        """Host numpy (N x M normalised inputs, N or N x 1 data) -> DeviceDataset.  H2D copies + one transpose."""
+        torch = self.torch
+        inputs = np.ascontiguousarray(inputs, dtype=np.float64)
+        if inputs.ndim == 1:
+            inputs = inputs[:, None]
+        data = np.ascontiguousarray(np.asarray(data, dtype=np.float64).reshape(-1))
+        n, m = inputs.shape
+        if data.shape[0] != n:
+            raise ValueError("inputs and data must have the same number of rows")
+        ldx = _round_up(max(n, 1), 16)
+        x = torch.zeros((m, ldx), dtype=torch.float64, device=self.device)
+        y = torch.zeros((ldx,), dtype=torch.float64, device=self.device)
+        xr = torch.from_numpy(inputs).to(self.device, non_blocking=False)
+        x[:, :n].copy_(xr.t())
+        y[:n].copy_(torch.from_numpy(data).to(self.device))
+        self.h2d_bytes = inputs.nbytes + data.nbytes
+        return DeviceDataset(x, y, n, m, ldx)
+
+    def begin_fit(self, ds):
+        """Bind a dataset; allocate X (ones column) and the Gram state; compute the data moments."""
+        torch = self.torch
+        self.ds = ds
+        n = ds.n
+        self.ld = ds.ldx
+        self.Pcap = 0
+        self.X = None
+        self._ensure_columns(64 if n * 64 * 8 < (4 << 30) else 16)
+        self._ck(self.lib.fokl_fill_ones(self.ctx, self.X.data_ptr(), n))
+        self.P = 0
+        mom = torch.zeros(3, dtype=torch.float64, device=self.device)
+        self._ck(self.lib.fokl_y_moments(self.ctx, ds.y.data_ptr(), n, mom.data_ptr()))
+        self._allreduce(mom)
+        momh = mom.cpu().numpy()
+        self.n_global = int(round(momh[0]))
+        self.sum_y = float(momh[1])
+        self.yty = float(momh[2])
+        self.Gcap = 0
+        self._ensure_gram(64)
+        self._append_built(1)      # Gram entries of the ones column: G00 = n, Xty0 = sum y
+        return self
+
+    def _ensure_columns(self, need):
+        torch = self.torch
+        if self.X is not None and need <= self.Pcap:
+            return
+        new_cap = max(need, int(self.Pcap * 1.5) + 8)
+        free, _ = torch.cuda.mem_get_info(self.device)
+        col_bytes = self.ld * 8
+        max_extra = int(free * 0.9) // col_bytes
+        if new_cap > max_extra:
+            new_cap = max(need, max_extra)
+        if new_cap > max_extra:
+            raise MemoryError("design matrix of %d columns x %d rows does not fit in device memory" % (need, self.ds.n))
+        Xn = torch.empty((new_cap, self.ld), dtype=torch.float64, device=self.device)
+        if self.X is not None and self.P > 0:
+            Xn[:self.P].copy_(self.X[:self.P])
+        self.X = Xn
+        self.Pcap = new_cap
+
+    def _ensure_gram(self, need):
+        torch = self.torch
+        if need <= self.Gcap:
+            return
+        cap = max(need, self.Gcap * 2, 64)
+        G = torch.zeros((cap, cap), dtype=torch.float64, device=self.device)
+        Xty = torch.zeros((cap,), dtype=torch.float64, device=self.device)
+        if self.G is not None and self.P > 0:
+            G[:self.P, :self.P].copy_(self.G[:self.P, :self.P])
+            Xty[:self.P].copy_(self.Xty[:self.P])
+        self.G, self.Xty = G, Xty
+        self.G2 = torch.zeros_like(G)
+        self.Xty2 = torch.zeros_like(Xty)
+        self.Gcap = cap
+
+    def _append_built(self, c):
+        """Columns [P, P + c) of X have just been written: update G and Xty (K2 + allreduce + scatter)."""
+        torch = self.torch
+        p_old = self.P
+        self._ensure_gram(p_old + c)
+        need = (p_old + c + 1) * c
+        if self.block is None or self.block.numel() < need:
+            self.block = torch.empty((int(need * 1.5) + 64,), dtype=torch.float64, device=self.device)
+        self._ck(self.lib.fokl_gram_update(self.ctx, self.X.data_ptr(), self.ld, self.ds.n, p_old, c,
+                                           self.ds.y.data_ptr(), self.block.data_ptr()))
+        if self.dist is not None:
+            self._allreduce(self.block[:need])
+        self._ck(self.lib.fokl_gram_scatter(self.ctx, self.block.data_ptr(), p_old, c, self.G.data_ptr(), self.Gcap,
+                                            self.Xty.data_ptr()))
+        self.P = p_old + c
+
+    def append_terms(self, terms):
+        """K1 + K2 for `terms` (C x M integer orders): appends C columns to X, extends G / Xty."""
+        terms = np.ascontiguousarray(terms, dtype=np.int16)
+        c, m = terms.shape
+        if m != self.ds.m:
+            raise ValueError("term width does not match the number of inputs")
+        if c == 0:
+            return
+        self._ensure_columns(self.P + c)
+        self._ck(self.lib.fokl_basis_build(self.ctx, self.kernel_id, self.ds.x.data_ptr(), self.ds.n, self.ds.ldx, m,
+                                           terms.ctypes.data, c, self.X[self.P].data_ptr(), self.ld))
+        self._append_built(c)
+
+    def compact(self, keep):
+        """Keep only columns `keep` (ascending, includes 0) of X / G / Xty: the X <- xers step (FR:1695)."""
+        keep = np.ascontiguousarray(keep, dtype=np.int32)
+        p_new = len(keep)
+        if p_new == self.P:
+            return
+        self._ck(self.lib.fokl_columns_compact(self.ctx, self.X.data_ptr(), self.ld, self.ds.n, keep.ctypes.data, p_new))
+        self._ck(self.lib.fokl_gram_compact(self.ctx, self.G.data_ptr(), self.Gcap, self.Xty.data_ptr(),
+                                            keep.ctypes.data, p_new, self.G2.data_ptr(), self.Gcap, self.Xty2.data_ptr()))
+        self.G, self.G2 = self.G2, self.G
+        self.Xty, self.Xty2 = self.Xty2, self.Xty
+        self.P = p_new
+
+    # ------------------------------------------------------------------------------------------------
+    def make_hypers(self, a, b, atau, btau, sigsqd0, tausqd0, draws):
+        h = _lib.Hypers()
+        h.a, h.b, h.atau, h.btau = float(a), float(b), float(atau), float(btau)
+        h.sigsqd0, h.tausqd0 = float(sigsqd0), float(tausqd0)
+        h.yty, h.sum_y = self.yty, self.sum_y
+        h.n = self.n_global
+        h.draws = int(draws)
+        h.stat_from0 = int(math.ceil(draws / 2))
+        h.stat_from1 = int(math.ceil(draws / 2 + 1))
+        h.reserved = 0
+        return h
+
+    def evaluate(self, col_sets, hyp, rng_mode=_lib.RNG_NONE, run_chain=None, seed=0, stream_ids=None,
+                 variates=None, sign_fix=None, want_betas=False, want_eig=False, refine_tol=1e-7):
+        """K3/K4 on a batch of candidate models (lists of column indices into the current X / G).
+
+        Returns a CandidateResult; `ev` is a host numpy array (this call synchronises)."""
+        torch = self.torch
+        n_cand = len(col_sets)
+        p = np.array([len(s) for s in col_sets], dtype=np.int64)
+        offs = np.zeros(n_cand + 1, dtype=np.int32)
+        offs[1:] = np.cumsum(p)
+        flat = np.ascontiguousarray(np.concatenate([np.asarray(s, dtype=np.int32) for s in col_sets]))
+        vec_off = np.concatenate([[0], np.cumsum(p)[:-1]]).astype(np.int64)
+        mat_off = np.concatenate([[0], np.cumsum(p * p)[:-1]]).astype(np.int64)
+        total_p = int(p.sum())
+        D = int(hyp.draws)
+        f64 = dict(dtype=torch.float64, device=self.device)
+        ev = torch.empty(n_cand, **f64)
+        info = torch.zeros(n_cand, dtype=torch.int32, device=self.device)
+        betahat = torch.empty(total_p, **f64)
+        chain_any = rng_mode != _lib.RNG_NONE and (run_chain is None or bool(np.any(run_chain)))
+        stats = torch.zeros(3 * total_p, **f64) if chain_any else None
+        betas = torch.empty(D * total_p, **f64) if (chain_any and want_betas) else None
+        sigs = torch.empty(D * n_cand, **f64) if (chain_any and want_betas) else None
+        taus = torch.empty(D * n_cand, **f64) if (chain_any and want_betas) else None
+        lamb = torch.empty(total_p, **f64) if want_eig else None
+        Q = torch.empty(int((p * p).sum()), **f64) if want_eig else None
+        rc_arr = None
+        if run_chain is not None:
+            rc_arr = np.ascontiguousarray(run_chain, dtype=np.uint8)
+        sid = None
+        if stream_ids is not None:
+            sid = np.ascontiguousarray(stream_ids, dtype=np.uint64)
+        var_t = None
+        if rng_mode == _lib.RNG_INJECTED:
+            var_t = variates if torch.is_tensor(variates) else torch.from_numpy(
+                np.ascontiguousarray(variates, dtype=np.float64)).to(self.device)
+        sf_t = None
+        if sign_fix is not None:
+            sf_t = sign_fix if torch.is_tensor(sign_fix) else torch.from_numpy(
+                np.ascontiguousarray(sign_fix, dtype=np.float64)).to(self.device)
+
+        def ptr(t):
+            return None if t is None else t.data_ptr()
+
+        self._ck(self.lib.fokl_candidates_eval(
+            self.ctx, self.G.data_ptr(), self.Gcap, self.Xty.data_ptr(), flat.ctypes.data, offs.ctypes.data, n_cand,
+            ctypes.byref(hyp), None if rc_arr is None else rc_arr.ctypes.data, rng_mode, ctypes.c_uint64(int(seed)),
+            None if sid is None else sid.ctypes.data, ptr(var_t), ptr(sf_t), ptr(ev), ptr(betahat), ptr(lamb), ptr(Q),
+            ptr(betas), ptr(sigs), ptr(taus), ptr(stats), ptr(info)))
+        self.gibbs_launch_batches += 1
+        res = CandidateResult()
+        res.p, res.vec_off, res.mat_off, res.draws = p, vec_off, mat_off, D
+        res.ev = ev.cpu().numpy()
+        res.info = info.cpu().numpy()
+        res.stats, res.betas, res.sigs, res.taus = stats, betas, sigs, taus
+        res.betahat, res.lamb, res.Q = betahat, lamb, Q
+        # ---- refine near-interpolating / degenerate fits with an N-length residual pass (FR:1551) --------
+        if refine_tol is not None and refine_tol > 0:
+            n = float(self.n_global)
+            var_y = self.yty / n - (self.sum_y / n) ** 2
+            with np.errstate(all='ignore'):
+                siglik = np.exp((res.ev - p * np.log(n) - (n - 1.0)) / n)
+            bad = ~np.isfinite(res.ev) | ~(siglik > refine_tol * var_y)
+            for c in np.nonzero(bad)[0]:
+                res.ev[c] = self.residual_bic(col_sets[c], betahat[vec_off[c]:vec_off[c] + p[c]])
+        return res
+
+    def residual_bic(self, cols, betahat_dev):
+        """BIC of FR:1551-1554 from an explicit N-length residual pass over X (used when the Gram-only
+        formula has lost too many digits to cancellation)."""
+        torch = self.torch
+        cols = np.ascontiguousarray(cols, dtype=np.int32)
+        out = torch.zeros(2, dtype=torch.float64, device=self.device)
+        self._ck(self.lib.fokl_residual_moments(self.ctx, self.X.data_ptr(), self.ld, self.ds.n, len(cols),
+                                                cols.ctypes.data, betahat_dev.data_ptr(), self.ds.y.data_ptr(),
+                                                out.data_ptr()))
+        self._allreduce(out)
+        sr, srr = out.cpu().numpy()
+        n = float(self.n_global)
+        siglik = srr / n - (sr / n) ** 2
+        with np.errstate(all='ignore'):
+            lik = -(n / 2) * np.log(siglik) - (n - 1) / 2
+        return len(cols) * np.log(n) - 2 * lik

@@ -1,0 +1,297 @@
+"""Host side of the forward-selection loop of `FoKL.fit` (reference: src/FoKL/FoKLRoutines.py:1561-1760).
+
+The loop is inherently sequential in its stages; what it asks of the device per substage is
+  (1) append the new terms' columns to X and extend the Gram (K1 + K2),
+  (2) evaluate the full model (eig + BIC + Gibbs chain + column statistics),
+  (3) evaluate kill proposals -- here as *batches* of independent candidate models (one CTA each) instead
+      of one `gibbs` call at a time -- and
+  (4) drop the accepted kills (column / Gram compaction).
+The batching is exact: a proposal's outcome depends only on the kill set accepted so far and on the
+draws of the last accepted model (FR:1670-1690), so all proposals that pass the threshold test under the
+current state are evaluated together, the first (in the reference's order) that lowers the BIC is
+accepted, and the remainder is re-batched under the new state.
+"""
+import math
+
+import numpy as np
+
+from . import _lib
+
+
+def distinct_permutations(v):
+    """All distinct orderings of the multiset v as integer rows in ascending lexicographic order --
+    what np.unique(perms(v), axis=0) returns at FR:1616, without enumerating len(v)! permutations."""
+    a = sorted(int(t) for t in v)
+    n = len(a)
+    rows = [tuple(a)]
+    while True:
+        i = n - 2
+        while i >= 0 and a[i] >= a[i + 1]:
+            i -= 1
+        if i < 0:
+            break
+        j = n - 1
+        while a[j] <= a[i]:
+            j -= 1
+        a[i], a[j] = a[j], a[i]
+        a[i + 1:] = reversed(a[i + 1:])
+        rows.append(tuple(a))
+    return np.array(rows, dtype=np.int64).reshape(len(rows), n)
+
+
+def first_partition(ind, m, sett):
+    """FR:1605-1613."""
+    v = [0] * m
+    left = ind
+    while left:
+        for j in range(sett):
+            v[j] += 1
+            left -= 1
+            if left == 0:
+                break
+    return v
+
+
+def next_partition(v, m, way3):
+    """FR:1722-1740; mutates v, returns False when this `ind` is exhausted."""
+    if m == 1:
+        return False
+    if way3:
+        if v[1] > v[2]:
+            v[0] += 1
+            v[1] -= 1
+            return True
+        if v[2]:
+            v[1] += 1
+            v[2] -= 1
+            if v[1] > v[0]:
+                v[0] += 1
+                v[1] -= 1
+            return True
+        return False
+    if v[1]:
+        v[0] += 1
+        v[1] -= 1
+        return True
+    return False
+
+
+class NumpyVariates:
+    """Parity RNG: consumes the global legacy numpy stream exactly like one reference `gibbs` call
+    (FR:1527, 1541, 1547): per draw normal(size=(p, 1)), gamma(astar, .), gamma(atau_star, .).
+    np.random.gamma(k, s) == s * standard_gamma(k) bitwise, so the stream does not depend on values."""
+    mode = _lib.RNG_INJECTED
+
+    def __init__(self, a, atau, n, draws):
+        self.a, self.atau, self.n, self.draws = a, atau, n, draws
+
+    def draw(self, p):
+        astar = self.a + 1 + self.n / 2 + p / 2
+        atau_star = self.atau + (p - 1) / 2
+        out = np.empty((self.draws, p + 2))
+        normal, sgamma = np.random.normal, np.random.standard_gamma
+        for k in range(self.draws):
+            out[k, :p] = normal(loc=0, scale=1, size=(p, 1))[:, 0]
+            out[k, p] = sgamma(astar)
+            out[k, p + 1] = sgamma(atau_star)
+        return out
+
+
+class PhiloxVariates:
+    """Free-running RNG on the device; one seed per fit drawn from the global numpy RNG (so np.random.seed
+    still makes a fit reproducible), one stream per `gibbs` call index."""
+    mode = _lib.RNG_PHILOX
+
+    def __init__(self):
+        self.seed = int(np.random.randint(0, 2 ** 31 - 1)) * (2 ** 31) + int(np.random.randint(0, 2 ** 31 - 1))
+
+
+def forward_select(engine, hy, m, n_phis, console=True, rng='philox', eager=False, on_substage=None,
+                   recorder=None):
+    """Run the selection loop on an Engine that has a dataset bound (engine.begin_fit).
+
+    hy: dict with a, b, atau, btau, tolerance, total_draws, gimmie, way3, threshav, threshstda, threshstdb, aic.
+    Returns dict(betas=(D x P) numpy of the chosen model, mtx, evs, n_gibbs, n_batches)."""
+    torch = engine.torch
+    n = engine.n_global
+    D = int(hy['total_draws'])
+    a, b, atau, btau = hy['a'], hy['b'], hy['atau'], hy['btau']
+    hyp = engine.make_hypers(a, b, atau, btau, b / (1 + a), btau / (1 + atau), D)
+    aic_adj = (2 - np.log(n)) if hy['aic'] else 0.0
+    if rng == 'numpy':
+        src = NumpyVariates(a, atau, n, D)
+        seed = 0
+    else:
+        src = PhiloxVariates()
+        seed = src.seed
+    mode = src.mode
+    sett = 1 if m == 1 else (3 if hy['way3'] else 2)
+    tolerance = hy['tolerance']
+
+    terms = np.zeros((0, m), dtype=np.int64)     # damtx: row j <-> column j + 1 of X
+    evs = []
+    best = None            # (betas tensor, mtx)
+    last = None
+    greater = 0
+    call_id = [0]
+    n_gibbs = 0
+    n_batches = 0
+
+    def run(col_sets, chains, ids):
+        nonlocal n_batches
+        n_batches += 1
+        sid = np.asarray(ids, dtype=np.uint64)
+        if mode == _lib.RNG_INJECTED:
+            # Parity mode.  Eigenvector signs are arbitrary and LAPACK's choice is what pairs each injected
+            # normal with a direction (S = Q diag(...), FR:1525-1528), so the signs of the device eigenvectors are
+            # aligned with scipy.linalg.eigh of the *same Gram bits* before the chain runs.  Only +-1 factors come
+            # from the host; every number in the result is computed on the device.
+            from scipy.linalg import eigh as _eigh
+            pre = engine.evaluate(col_sets, hyp, rng_mode=_lib.RNG_NONE, want_eig=True)
+            signs = []
+            for c, cols in enumerate(col_sets):
+                idx = torch.as_tensor(np.asarray(cols, dtype=np.int64), device=engine.device)
+                g_sub = engine.G.index_select(0, idx).index_select(1, idx).cpu().numpy()
+                if recorder is not None:
+                    xty_sub = engine.Xty.index_select(0, idx).cpu().numpy()
+                    recorder(tuple(map(tuple, terms[np.asarray(cols[1:], dtype=np.int64) - 1])), g_sub, xty_sub)
+                pc = len(cols)
+                q_dev = pre.Q[pre.mat_off[c]:pre.mat_off[c] + pc * pc].view(pc, pc).cpu().numpy().T
+                with np.errstate(all='ignore'):
+                    _, q_ref = _eigh(g_sub)
+                sg = np.sign(np.sum(q_dev * q_ref, axis=0))
+                sg[sg == 0] = 1.0
+                signs.append(sg)
+            variates = np.concatenate([
+                (v if v is not None else np.zeros((D, len(s_) + 2))).reshape(-1) for v, s_ in zip(chains, col_sets)])
+            flags = np.array([v is not None for v in chains], dtype=np.uint8)
+            return engine.evaluate(col_sets, hyp, rng_mode=mode, run_chain=flags, seed=seed, stream_ids=sid,
+                                   variates=variates, sign_fix=np.concatenate(signs), want_betas=True)
+        flags = np.array([bool(v) for v in chains], dtype=np.uint8)
+        any_chain = bool(flags.any())
+        return engine.evaluate(col_sets, hyp, rng_mode=mode if any_chain else _lib.RNG_NONE, run_chain=flags,
+                               seed=seed, stream_ids=sid, want_betas=any_chain)
+
+    ind = 1
+    finished = False
+    while True:
+        part = first_partition(ind, m, sett)
+        while True:
+            vecs = distinct_permutations(part)
+            vm = vecs.shape[0]
+            p_old = engine.P                     # columns of the model accepted so far (incl. intercept)
+            engine.append_terms(vecs)
+            terms = np.concatenate([terms, vecs], axis=0)
+            dam = terms.shape[0]
+            full = list(range(engine.P))
+
+            # ---- full model (FR:1650) -----------------------------------------------------------------------
+            call_id[0] += 1
+            n_gibbs += 1
+            chain_arg = src.draw(len(full)) if mode == _lib.RNG_INJECTED else True
+            res = run([full], [chain_arg], [call_id[0]])
+            ev = float(res.ev[0]) + aic_adj * (dam + 1)
+            st = res.stats_of(0).cpu().numpy()
+            cur_betas = res.betas_of(0)
+            new_cols = np.arange(p_old, p_old + vm)
+            with np.errstate(all='ignore'):
+                bv0 = np.abs(st[0, new_cols])                          # |mean| over rows h1.. (FR:1656)
+                bv1 = st[1, new_cols] / np.abs(st[2, new_cols])        # std / |mean over rows h0..| (FR:1657-58)
+            order = np.argsort(bv0, kind='quicksort')
+            bv0, bv1, cand_cols = bv0[order], bv1[order], new_cols[order]
+            icpt = abs(float(st[2, 0]))                                # |mean(beters[h0:, 0])| (FR:1671)
+
+            # ---- kill proposals (FR:1666-1692), batched --------------------------------------------------------
+            killed = []            # column indices (into current X) accepted for removal
+            evmin = ev
+            cur = 0
+            while cur < vm:
+                thr = hy['threshav'] * icpt
+                props = [i for i in range(cur, vm)
+                         if (bv1[i] > hy['threshstdb']) or (bv1[i] > hy['threshstda'] and bv0[i] < thr)]
+                if not props:
+                    break
+                sets, chains, ids = [], [], []
+                base = call_id[0]
+                for r, i in enumerate(props):
+                    drop = set(killed) | {int(cand_cols[i])}
+                    sets.append([c for c in full if c not in drop])
+                    ids.append(base + r + 1)
+                if mode == _lib.RNG_INJECTED:
+                    # stream parity: variates are consumed test by test, so run sequentially until one is accepted
+                    accepted = None
+                    for r, i in enumerate(props):
+                        call_id[0] += 1
+                        n_gibbs += 1
+                        v = src.draw(len(sets[r]))
+                        rr = run([sets[r]], [v], [ids[r]])
+                        evt = float(rr.ev[0]) + aic_adj * len(sets[r])
+                        if evt < evmin:
+                            accepted = (i, evt, rr, 0)
+                            break
+                else:
+                    rr = run(sets, [bool(eager)] * len(sets), ids)
+                    accepted = None
+                    for r, i in enumerate(props):
+                        evt = float(rr.ev[r]) + aic_adj * len(sets[r])
+                        if evt < evmin:
+                            accepted = (i, evt, rr, r)
+                            break
+                    tested = (props.index(accepted[0]) + 1) if accepted else len(props)
+                    call_id[0] += tested
+                    n_gibbs += tested
+                    if accepted and not eager:
+                        # the accepted model's draws are needed (FR:1690): run its chain with its own stream id
+                        i, evt, _, r = accepted
+                        rr1 = run([sets[r]], [True], [ids[r]])
+                        accepted = (i, evt, rr1, 0)
+                if accepted is None:
+                    break
+                i, evt, rr, slot = accepted
+                killed.append(int(cand_cols[i]))
+                evmin = evt
+                cur_betas = rr.betas_of(slot).clone()
+                icpt = abs(float(rr.stats_of(slot)[2, 0].item()))
+                cur = i + 1
+
+            # ---- drop accepted kills (FR:1691-1695) ---------------------------------------------------------------
+            if killed:
+                keep = [c for c in full if c not in set(killed)]
+                engine.compact(keep)
+                terms = np.delete(terms, [c - 1 for c in killed], axis=0)
+            ev = evmin
+            last = (cur_betas, terms.copy())
+            if console:
+                print([ind, float(ev)])
+            if on_substage is not None:
+                on_substage(ind, ev, terms)
+
+            # ---- bookkeeping (FR:1701-1721) -----------------------------------------------------------------------
+            if evs:
+                if ev < np.min(evs):
+                    best = last
+                    greater = 1
+                    evs.append(ev)
+                elif greater < tolerance:
+                    greater += 1
+                    evs.append(ev)
+                else:
+                    finished = True
+                    evs.append(ev)
+                    break
+            else:
+                greater += 1
+                best = last
+                evs.append(ev)
+            if not next_partition(part, m, hy['way3']):
+                break
+        if finished:
+            break
+        ind += 1
+        if ind > n_phis:
+            break
+
+    chosen = last if hy['gimmie'] else best
+    betas = chosen[0].cpu().numpy()
+    return dict(betas=betas, mtx=chosen[1].astype(np.float64), evs=np.array(evs, dtype=np.float64),
+                n_gibbs=n_gibbs, n_batches=n_batches)

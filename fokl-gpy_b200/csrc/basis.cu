@@ -1,0 +1,369 @@
+// basis.cu -- K1: fused BSS-ANOVA design-matrix builder (sm_100a).
+//
+// Replaces the Python triple loop of the reference, src/FoKL/FoKLRoutines.py:1446-1485, together with
+// _inputs_to_phind (FR:570-589) and evaluate_basis d = 0 (FR:834-836, 841-843).
+//
+// Per tile of ROWS consecutive data rows a CTA
+//   phase 1: evaluates every distinct (input k, order d) factor the term list needs, once per row, into
+//            shared memory F[factor][row] -- coefficient tables of the orders in use are staged in shared
+//            memory (cubic: [slot][piece][4], one 32-byte gather per factor; Bernoulli: whole table);
+//   phase 2: forms each term's product (increasing input index, like FR:1466-1483) from F and streams it to
+//            the column-major design matrix with coalesced 16-byte stores (2 adjacent rows per thread).
+// HBM traffic = read N*M inputs once + write N*C outputs: 8*N*(M + C) bytes -- the kernel's roofline.
+#include "fokl_ctx.cuh"
+#include "fokl_math.cuh"
+#include <algorithm>
+#include <string.h>
+#include <vector>
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kMaxTermFactors = 7;     // interacting inputs per term (fit uses <= 3)
+constexpr int kMaxFactors = 96;        // distinct (input, order) pairs per launch
+constexpr int kMaxTermsPerLaunch = 2048;
+
+struct FactorMeta {          // one distinct (input, order) pair
+    int16_t k;               // input column
+    int16_t d;               // order (1-based, phis[d-1])
+    int16_t slot;            // staged-table slot of this order (cubic), -1 = read global table
+    int16_t pad;
+};
+
+struct TermMeta {            // one output column
+    uint8_t cnt;             // number of factors (0 -> constant 1)
+    uint8_t f[kMaxTermFactors];
+};
+
+struct BasisParams {
+    const double *x;
+    int64_t n, ldx;
+    double *out;
+    int64_t ld;
+    const double *tab;       // global coefficient table
+    int n_piece;             // cubic: pieces per order; bernoulli: row length
+    int n_factors, n_terms, n_slots;
+    const FactorMeta *factors;
+    const TermMeta *terms;
+    const int16_t *slot_order;   // order (1-based) staged in each slot
+    int *flag;
+    int64_t n_tiles;
+};
+
+__device__ __forceinline__ double eval_factor_cubic(const double *cf, double xs, double x2, double x3)
+{
+    return fokl::cubic_basis(cf[0], cf[1], cf[2], cf[3], xs, x2, x3);
+}
+
+// Bernoulli with on-the-fly correctly rounded powers (no local array)
+__device__ __forceinline__ double eval_factor_bernoulli(const double *c, int n_coef, double x)
+{
+    double h = x, l = 0.0, s = 0.0;
+    for (int q = 1; q < n_coef; ++q) {
+        if (q > 1) {
+            double p = __dmul_rn(h, x);
+            double e = __fma_rn(h, x, -p);
+            double t = __fma_rn(l, x, e);
+            double nh = __dadd_rn(p, t);
+            l = __dsub_rn(t, __dsub_rn(nh, p));
+            h = nh;
+        }
+        s = __dadd_rn(s, __dmul_rn(c[q], h));
+    }
+    return __dadd_rn(c[0], s);
+}
+
+template <int KERNEL, int RPT>
+__global__ void __launch_bounds__(kThreads) basis_kernel(const BasisParams P)
+{
+    constexpr int ROWS = kThreads * RPT;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // layout: [staged table][F: n_factors * ROWS doubles][factors][terms]
+    double *s_tab = reinterpret_cast<double *>(smem_raw);
+    size_t tab_doubles = (KERNEL == FOKL_KERNEL_CUBIC) ? (size_t)P.n_slots * P.n_piece * 4
+                                                       : (size_t)P.n_slots * P.n_piece;
+    tab_doubles = (tab_doubles + 1) & ~(size_t)1;   // keep F 16-byte aligned
+    double *s_F = s_tab + tab_doubles;
+    FactorMeta *s_fac = reinterpret_cast<FactorMeta *>(s_F + (size_t)P.n_factors * ROWS);
+    TermMeta *s_term = reinterpret_cast<TermMeta *>(s_fac + P.n_factors);
+
+    const int tid = threadIdx.x;
+    // ---- stage coefficient tables and metadata ------------------------------------------------
+    if (KERNEL == FOKL_KERNEL_CUBIC) {
+        const int per = P.n_piece * 4;
+        for (int s = 0; s < P.n_slots; ++s) {
+            const double *src = P.tab + (size_t)(P.slot_order[s] - 1) * per;
+            for (int e = tid; e < per; e += kThreads) s_tab[(size_t)s * per + e] = __ldg(src + e);
+        }
+    } else {
+        const int per = P.n_piece;
+        for (int s = 0; s < P.n_slots; ++s) {
+            const double *src = P.tab + (size_t)(P.slot_order[s] - 1) * per;
+            for (int e = tid; e < per; e += kThreads) s_tab[(size_t)s * per + e] = __ldg(src + e);
+        }
+    }
+    for (int f = tid; f < P.n_factors; f += kThreads) s_fac[f] = P.factors[f];
+    for (int j = tid; j < P.n_terms; j += kThreads) s_term[j] = P.terms[j];
+    __syncthreads();
+
+    for (int64_t tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+        const int64_t row0 = tile * ROWS + (int64_t)tid * RPT;
+        // ---- phase 1: factor values -------------------------------------------------------------
+        {
+            double xv[RPT], xs[RPT], x2[RPT], x3[RPT];
+            int ph[RPT];
+            int cur_k = -1;
+            for (int f = 0; f < P.n_factors; ++f) {
+                const FactorMeta fm = s_fac[f];
+                if (fm.k != cur_k) {
+                    cur_k = fm.k;
+                    const double *xc = P.x + (int64_t)cur_k * P.ldx;
+                    if (RPT == 2 && row0 + 1 < P.n) {
+                        double2 t = *reinterpret_cast<const double2 *>(xc + row0);
+                        xv[0] = t.x;
+                        xv[RPT - 1] = t.y;
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < RPT; ++r) xv[r] = (row0 + r < P.n) ? xc[row0 + r] : 0.5;
+                    }
+                    if (KERNEL == FOKL_KERNEL_CUBIC) {
+#pragma unroll
+                        for (int r = 0; r < RPT; ++r) {
+                            bool ok = fokl::phind_xsm(xv[r], P.n_piece, ph[r], xs[r]);
+                            if (ph[r] > P.n_piece - 1) { ok = false; ph[r] = P.n_piece - 1; }
+                            if (!ok && row0 + r < P.n) atomicOr(P.flag, 1);
+                            fokl::square_cube(xs[r], x2[r], x3[r]);
+                        }
+                    }
+                }
+                double v[RPT];
+                if (KERNEL == FOKL_KERNEL_CUBIC) {
+#pragma unroll
+                    for (int r = 0; r < RPT; ++r) {
+                        if (fm.slot >= 0) {
+                            const double4 *cp = reinterpret_cast<const double4 *>(
+                                s_tab + ((size_t)fm.slot * P.n_piece + ph[r]) * 4);
+                            double4 c4 = *cp;
+                            v[r] = fokl::cubic_basis(c4.x, c4.y, c4.z, c4.w, xs[r], x2[r], x3[r]);
+                        } else {
+                            const double *cp = P.tab + ((size_t)(fm.d - 1) * P.n_piece + ph[r]) * 4;
+                            v[r] = fokl::cubic_basis(__ldg(cp), __ldg(cp + 1), __ldg(cp + 2), __ldg(cp + 3), xs[r],
+                                                     x2[r], x3[r]);
+                        }
+                    }
+                } else {
+                    const double *cp = (fm.slot >= 0) ? (s_tab + (size_t)fm.slot * P.n_piece)
+                                                      : (P.tab + (size_t)(fm.d - 1) * P.n_piece);
+#pragma unroll
+                    for (int r = 0; r < RPT; ++r) v[r] = eval_factor_bernoulli(cp, fm.d + 1, xv[r]);
+                }
+                if (RPT == 2) {
+                    *reinterpret_cast<double2 *>(s_F + (size_t)f * ROWS + tid * 2) = make_double2(v[0], v[RPT - 1]);
+                } else {
+                    s_F[(size_t)f * ROWS + tid] = v[0];
+                }
+            }
+        }
+        __syncthreads();
+        // ---- phase 2: products, streamed to HBM -----------------------------------------------------
+        {
+            double pre[RPT];
+#pragma unroll
+            for (int r = 0; r < RPT; ++r) pre[r] = 1.0;
+            int pf0 = -1, pf1 = -1;
+            const bool full = (row0 + RPT - 1 < P.n);
+            for (int j = 0; j < P.n_terms; ++j) {
+                const TermMeta tm = s_term[j];
+                double v[RPT];
+                if (tm.cnt == 0) {
+#pragma unroll
+                    for (int r = 0; r < RPT; ++r) v[r] = 1.0;
+                } else {
+                    int start;
+                    if (tm.cnt >= 3 && tm.f[0] == pf0 && tm.f[1] == pf1) {
+                        start = 2;   // reuse (b0 * b1) from the previous term: same rounding, fewer LDS
+                    } else {
+                        const double *a = s_F + (size_t)tm.f[0] * ROWS + tid * RPT;
+#pragma unroll
+                        for (int r = 0; r < RPT; ++r) pre[r] = a[r];
+                        start = 1;
+                        if (tm.cnt >= 3) {
+                            const double *b = s_F + (size_t)tm.f[1] * ROWS + tid * RPT;
+#pragma unroll
+                            for (int r = 0; r < RPT; ++r) pre[r] = __dmul_rn(pre[r], b[r]);
+                            start = 2;
+                            pf0 = tm.f[0];
+                            pf1 = tm.f[1];
+                        } else {
+                            pf0 = -1;
+                        }
+                    }
+#pragma unroll
+                    for (int r = 0; r < RPT; ++r) v[r] = pre[r];
+                    for (int q = start; q < tm.cnt; ++q) {
+                        const double *b = s_F + (size_t)tm.f[q] * ROWS + tid * RPT;
+#pragma unroll
+                        for (int r = 0; r < RPT; ++r) v[r] = __dmul_rn(v[r], b[r]);
+                    }
+                }
+                double *dst = P.out + (int64_t)j * P.ld + row0;
+                if (RPT == 2 && full) {
+                    __stcs(reinterpret_cast<double2 *>(dst), make_double2(v[0], v[RPT - 1]));
+                } else {
+#pragma unroll
+                    for (int r = 0; r < RPT; ++r)
+                        if (row0 + r < P.n) __stcs(dst + r, v[r]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+struct LaunchPlan {
+    std::vector<FactorMeta> factors;
+    std::vector<TermMeta> terms;
+    std::vector<int16_t> slot_order;
+    int first_term = 0;
+};
+
+}  // namespace
+
+extern "C" int fokl_basis_build(fokl_ctx *ctx, int kernel, const double *x, int64_t n, int64_t ldx, int m,
+                                const int16_t *terms, int c, double *Xnew, int64_t ld)
+{
+    FOKL_CHECK_CTX(ctx);
+    if (!x || !terms || !Xnew || n < 0 || m < 1 || c < 0 || ldx < n || ld < n)
+        FOKL_FAIL(ctx, FOKL_EINVAL, "basis_build: bad argument");
+    if (kernel != FOKL_KERNEL_CUBIC && kernel != FOKL_KERNEL_BERNOULLI)
+        FOKL_FAIL(ctx, FOKL_EINVAL, "basis_build: unknown kernel");
+    int rc = fokl_bind_device(ctx);
+    if (rc) return rc;
+    const double *tab = kernel == FOKL_KERNEL_CUBIC ? ctx->cubic_tab : ctx->bern_tab;
+    const int n_orders = kernel == FOKL_KERNEL_CUBIC ? ctx->cubic_orders : ctx->bern_orders;
+    const int row_len = kernel == FOKL_KERNEL_CUBIC ? ctx->cubic_pieces : ctx->bern_row;
+    if (!tab) FOKL_FAIL(ctx, FOKL_ESTATE, "basis_build: phis table for this kernel was not set");
+    if (n == 0 || c == 0) return FOKL_OK;
+
+    // ---- plan launches: distinct (input, order) factors per chunk of terms ----------------------------
+    std::vector<LaunchPlan> plans;
+    {
+        LaunchPlan cur;
+        std::vector<int> fac_index((size_t)m * (n_orders + 1), -1);
+        auto flush = [&]() {
+            if (!cur.terms.empty()) plans.push_back(cur);
+            int next = cur.first_term + (int)cur.terms.size();
+            cur = LaunchPlan();
+            cur.first_term = next;
+            std::fill(fac_index.begin(), fac_index.end(), -1);
+        };
+        for (int j = 0; j < c; ++j) {
+            const int16_t *row = terms + (size_t)j * m;
+            int need_new = 0, cnt = 0;
+            for (int k = 0; k < m; ++k) {
+                int d = row[k];
+                if (d == 0) continue;
+                if (d < 0 || d > n_orders) FOKL_FAIL(ctx, FOKL_EINVAL, "basis_build: term order outside len(phis)");
+                if (kernel == FOKL_KERNEL_BERNOULLI && d + 1 > row_len)
+                    FOKL_FAIL(ctx, FOKL_EINVAL, "basis_build: bernoulli row too short for order");
+                ++cnt;
+                if (fac_index[(size_t)k * (n_orders + 1) + d] < 0) ++need_new;
+            }
+            if (cnt > kMaxTermFactors) FOKL_FAIL(ctx, FOKL_EINVAL, "basis_build: more than 7 interacting inputs in a term");
+            if ((int)cur.factors.size() + need_new > kMaxFactors || (int)cur.terms.size() >= kMaxTermsPerLaunch) flush();
+            TermMeta tm;
+            tm.cnt = 0;
+            for (int q = 0; q < kMaxTermFactors; ++q) tm.f[q] = 0;
+            for (int k = 0; k < m; ++k) {
+                int d = row[k];
+                if (d == 0) continue;
+                int &fi = fac_index[(size_t)k * (n_orders + 1) + d];
+                if (fi < 0) {
+                    fi = (int)cur.factors.size();
+                    FactorMeta fm;
+                    fm.k = (int16_t)k; fm.d = (int16_t)d; fm.slot = -1; fm.pad = 0;
+                    cur.factors.push_back(fm);
+                }
+                tm.f[tm.cnt++] = (uint8_t)fi;
+            }
+            cur.terms.push_back(tm);
+        }
+        flush();
+    }
+
+    const bool aligned2 = ((ld % 2) == 0) && ((ldx % 2) == 0) && (((uintptr_t)Xnew % 16) == 0) && (((uintptr_t)x % 16) == 0);
+    const size_t smem_cap = ctx->smem_optin ? ctx->smem_optin : 48 * 1024;
+
+    for (LaunchPlan &pl : plans) {
+        // phase 1 walks factors grouped by input: sort by (k, d) and remap term indices
+        const int nf = (int)pl.factors.size();
+        std::vector<int> order(nf), inv(nf);
+        for (int i = 0; i < nf; ++i) order[i] = i;
+        std::sort(order.begin(), order.end(), [&](int a, int b) {
+            if (pl.factors[a].k != pl.factors[b].k) return pl.factors[a].k < pl.factors[b].k;
+            return pl.factors[a].d < pl.factors[b].d;
+        });
+        std::vector<FactorMeta> sorted(nf);
+        for (int i = 0; i < nf; ++i) { sorted[i] = pl.factors[order[i]]; inv[order[i]] = i; }
+        for (TermMeta &tm : pl.terms)
+            for (int q = 0; q < tm.cnt; ++q) tm.f[q] = (uint8_t)inv[tm.f[q]];
+        // staged-table slots: distinct orders, as many as fit next to F
+        std::vector<int16_t> orders;
+        for (const FactorMeta &fm : sorted)
+            if (std::find(orders.begin(), orders.end(), fm.d) == orders.end()) orders.push_back(fm.d);
+        std::sort(orders.begin(), orders.end());
+        const size_t per_slot = (kernel == FOKL_KERNEL_CUBIC ? (size_t)row_len * 4 : (size_t)row_len) * sizeof(double);
+        const int nt = (int)pl.terms.size();
+        auto smem_need = [&](int rpt, int nslots) {
+            size_t tab_bytes = ((nslots * per_slot / sizeof(double) + 1) & ~(size_t)1) * sizeof(double);
+            return tab_bytes + (size_t)nf * kThreads * rpt * sizeof(double) + (size_t)nf * sizeof(FactorMeta) +
+                   (size_t)nt * sizeof(TermMeta) + 16;
+        };
+        int rpt = aligned2 ? 2 : 1;
+        int nslots = (int)orders.size();
+        // prefer two resident CTAs per SM; otherwise shrink rows per thread, then staged slots
+        if (rpt == 2 && smem_need(2, nslots) > smem_cap / 2) rpt = 1;
+        while (nslots > 0 && smem_need(rpt, nslots) > smem_cap) --nslots;
+        if (smem_need(rpt, nslots) > smem_cap) FOKL_FAIL(ctx, FOKL_EINVAL, "basis_build: term list needs too much shared memory");
+        orders.resize(nslots);
+        for (FactorMeta &fm : sorted) {
+            auto it = std::find(orders.begin(), orders.end(), fm.d);
+            fm.slot = (it == orders.end()) ? (int16_t)-1 : (int16_t)(it - orders.begin());
+        }
+        // upload metadata
+        size_t off_fac = 0;
+        size_t off_term = off_fac + (size_t)nf * sizeof(FactorMeta);
+        size_t off_slot = (off_term + (size_t)nt * sizeof(TermMeta) + 15) & ~(size_t)15;
+        size_t meta_bytes = off_slot + (size_t)(nslots + 1) * sizeof(int16_t);
+        std::vector<unsigned char> host(meta_bytes, 0);
+        memcpy(host.data() + off_fac, sorted.data(), (size_t)nf * sizeof(FactorMeta));
+        memcpy(host.data() + off_term, pl.terms.data(), (size_t)nt * sizeof(TermMeta));
+        if (nslots) memcpy(host.data() + off_slot, orders.data(), (size_t)nslots * sizeof(int16_t));
+        // the copy is stream-ordered behind any kernel still reading the previous metadata
+        unsigned char *dmeta = (unsigned char *)fokl_scratch(ctx, fokl_ctx::B_BASIS, meta_bytes);
+        if (!dmeta) return FOKL_ENOMEM;
+        FOKL_CUDA(ctx, cudaMemcpyAsync(dmeta, host.data(), meta_bytes, cudaMemcpyHostToDevice, ctx->stream));
+
+        BasisParams P;
+        P.x = x; P.n = n; P.ldx = ldx;
+        P.out = Xnew + (int64_t)pl.first_term * ld; P.ld = ld;
+        P.tab = tab; P.n_piece = row_len;
+        P.n_factors = nf; P.n_terms = nt; P.n_slots = nslots;
+        P.factors = reinterpret_cast<const FactorMeta *>(dmeta + off_fac);
+        P.terms = reinterpret_cast<const TermMeta *>(dmeta + off_term);
+        P.slot_order = reinterpret_cast<const int16_t *>(dmeta + off_slot);
+        P.flag = ctx->d_flag;
+        const int rows = kThreads * rpt;
+        P.n_tiles = (n + rows - 1) / rows;
+        const size_t smem = smem_need(rpt, nslots);
+        const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, smem_cap / std::max<size_t>(smem, 1)));
+        int grid = (int)std::min<int64_t>(P.n_tiles, (int64_t)ctx->num_sms * ctas_per_sm);
+        void (*kern)(const BasisParams) = nullptr;
+        if (kernel == FOKL_KERNEL_CUBIC) kern = rpt == 2 ? basis_kernel<FOKL_KERNEL_CUBIC, 2> : basis_kernel<FOKL_KERNEL_CUBIC, 1>;
+        else kern = rpt == 2 ? basis_kernel<FOKL_KERNEL_BERNOULLI, 2> : basis_kernel<FOKL_KERNEL_BERNOULLI, 1>;
+        FOKL_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
+        kern<<<grid, kThreads, smem, ctx->stream>>>(P);
+        FOKL_LAUNCH_CHECK(ctx);
+    }
+    return FOKL_OK;
+}

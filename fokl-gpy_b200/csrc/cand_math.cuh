@@ -1,0 +1,286 @@
+// cand_math.cuh -- per-candidate spectral factorisation, betahat/BIC and the eigenbasis Gibbs chain.
+//
+// Written against a tiny "Team" abstraction (one CTA on the device; a single sequential thread in the
+// host emulation build, tests/host_emu) so the numerical logic can be checked against the CPU oracle
+// without a GPU.  Reference stages replaced (src/FoKL/FoKLRoutines.py):
+//   eigh(XtX)              FR:1499     -> jacobi_eigh   (one-sided cyclic Jacobi, round-robin pairs)
+//   betahat                FR:1502-04  -> ols_and_bic
+//   BIC                    FR:1551-54  -> ols_and_bic   (from Gram quantities, centred on mean(y))
+//   draw loop              FR:1519-48  -> gibbs_chain   (eigenbasis form, O(p) per draw)
+#pragma once
+#include "fokl_math.cuh"
+
+namespace fokl {
+
+struct Team {
+    int tid, nthr;    // thread in CTA
+    int lane, nlane;  // lane in warp (nlane = 1 in host emulation)
+    int warp, nwarp;
+    FOKL_HD void sync() const
+    {
+#if defined(__CUDA_ARCH__)
+        __syncthreads();
+#endif
+    }
+};
+
+FOKL_HD void warp_sum3(const Team &, double &a, double &b, double &c)
+{
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+        c += __shfl_xor_sync(0xffffffffu, c, o);
+    }
+#else
+    (void)a; (void)b; (void)c;
+#endif
+}
+
+FOKL_HD double warp_sum1(const Team &, double a)
+{
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+#endif
+    return a;
+}
+
+// CTA-wide sum of three values; every thread returns the same bits (fixed summation order).
+// red: shared scratch of 2 * 3 * nwarp doubles; parity alternates between calls.
+FOKL_HD void team_sum3(const Team &t, double &a, double &b, double &c, double *red, int parity)
+{
+    warp_sum3(t, a, b, c);
+    double *r = red + parity * 3 * t.nwarp;
+    if (t.lane == 0) {
+        r[3 * t.warp + 0] = a;
+        r[3 * t.warp + 1] = b;
+        r[3 * t.warp + 2] = c;
+    }
+    t.sync();
+    double sa = 0.0, sb = 0.0, sc = 0.0;
+    for (int w = 0; w < t.nwarp; ++w) {
+        sa += r[3 * w + 0];
+        sb += r[3 * w + 1];
+        sc += r[3 * w + 2];
+    }
+    a = sa; b = sb; c = sc;
+}
+
+// ---- one-sided Jacobi ---------------------------------------------------------------------------
+// Orthogonalise columns i, j of W (and apply the same rotation to V).  One warp per pair.
+FOKL_HD bool jacobi_pair(const Team &t, double *wi, double *wj, double *vi, double *vj, int p, double tol)
+{
+    double al = 0.0, be = 0.0, ga = 0.0;
+    for (int e = t.lane; e < p; e += t.nlane) {
+        double a = wi[e], b = wj[e];
+        al += a * a;
+        be += b * b;
+        ga += a * b;
+    }
+    warp_sum3(t, al, be, ga);
+    if (!(fabs(ga) > tol * sqrt(al * be))) return false;
+    double zeta = (be - al) / (2.0 * ga);
+    double tt = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+    double c = 1.0 / sqrt(1.0 + tt * tt);
+    double s = c * tt;
+    for (int e = t.lane; e < p; e += t.nlane) {
+        double a = wi[e], b = wj[e];
+        wi[e] = c * a - s * b;
+        wj[e] = s * a + c * b;
+        a = vi[e]; b = vj[e];
+        vi[e] = c * a - s * b;
+        vj[e] = s * a + c * b;
+    }
+    return true;
+}
+
+// W (in: symmetric matrix, column-major ld; out: W = G V with mutually orthogonal columns),
+// V (out: orthogonal).  flag: one shared int.  Returns the number of sweeps used.
+FOKL_HD int jacobi_eigh(const Team &t, double *W, double *V, int p, int ld, int max_sweeps, double tol,
+                        volatile int *flag)
+{
+    for (int j = t.warp; j < p; j += t.nwarp)
+        for (int e = t.lane; e < p; e += t.nlane) V[(int64_t)j * ld + e] = (e == j) ? 1.0 : 0.0;
+    t.sync();
+    if (p < 2) return 0;
+    const int n = p + (p & 1);
+    const int nm1 = n - 1;
+    int sweep = 0;
+    for (; sweep < max_sweeps; ++sweep) {
+        if (t.tid == 0) *flag = 0;
+        t.sync();
+        for (int r = 0; r < nm1; ++r) {
+            for (int k = t.warp; k < n / 2; k += t.nwarp) {
+                int i, j;
+                if (k == 0) { i = nm1; j = r; }
+                else { i = (r + k) % nm1; j = (r - k + nm1) % nm1; }
+                if (i > j) { int q = i; i = j; j = q; }
+                if (j >= p) continue;
+                bool rot = jacobi_pair(t, W + (int64_t)i * ld, W + (int64_t)j * ld, V + (int64_t)i * ld,
+                                       V + (int64_t)j * ld, p, tol);
+                if (rot && t.lane == 0) *flag = 1;
+            }
+            t.sync();
+        }
+        int any = *flag;
+        t.sync();
+        if (!any) { ++sweep; break; }
+    }
+    return sweep;
+}
+
+// After jacobi_eigh: Rayleigh quotients, ascending order (like scipy.linalg.eigh), eigenvectors.
+//   lam_raw (p scratch), perm (p ints scratch); outputs lamb[p] ascending, Q column-major p x p (ld = p).
+FOKL_HD void eig_finish(const Team &t, const double *W, const double *V, int p, int ld, double *lam_raw,
+                        int *perm, double *lamb, double *Q)
+{
+    for (int j = t.warp; j < p; j += t.nwarp) {
+        double s = 0.0;
+        for (int e = t.lane; e < p; e += t.nlane) s += V[(int64_t)j * ld + e] * W[(int64_t)j * ld + e];
+        s = warp_sum1(t, s);
+        if (t.lane == 0) lam_raw[j] = s;
+    }
+    t.sync();
+    for (int j = t.tid; j < p; j += t.nthr) {
+        double lj = lam_raw[j];
+        int rank = 0;
+        for (int i = 0; i < p; ++i) {
+            double li = lam_raw[i];
+            rank += (li < lj || (li == lj && i < j)) ? 1 : 0;
+        }
+        perm[rank] = j;
+    }
+    t.sync();
+    for (int r = t.warp; r < p; r += t.nwarp) {
+        int j = perm[r];
+        for (int e = t.lane; e < p; e += t.nlane) Q[(int64_t)r * p + e] = V[(int64_t)j * ld + e];
+        if (t.lane == 0) lamb[r] = lam_raw[j];
+    }
+    t.sync();
+}
+
+struct CandConst {
+    double a, b, atau, btau, sigsqd0, tausqd0, yty, sum_y;
+    double n;     // number of rows as double
+    int draws, from0, from1;
+};
+
+// betahat = Q diag(1/lamb) Q' Xty (FR:1502-1504, no clamp on tiny/negative eigenvalues) and the BIC of
+// FR:1551-1554 computed from Gram quantities.  G (row-major, ldg) is the master Gram, idx the candidate's
+// column list (idx[0] must be the intercept column).  ct[p] (out) = Q' Xty.  scratch: p doubles.
+// Returns ev in every thread.
+FOKL_HD double ols_and_bic(const Team &t, const double *G, int64_t ldg, const double *Xty, const int *idx,
+                           int p, const double *lamb, const double *Q, const CandConst &k, double *ct,
+                           double *betahat, double *scratch, double *red)
+{
+    for (int r = t.warp; r < p; r += t.nwarp) {
+        double s = 0.0;
+        for (int e = t.lane; e < p; e += t.nlane) s += Q[(int64_t)r * p + e] * Xty[idx[e]];
+        s = warp_sum1(t, s);
+        if (t.lane == 0) ct[r] = s;
+    }
+    t.sync();
+    for (int i = t.tid; i < p; i += t.nthr) {
+        double s = 0.0;
+        for (int r = 0; r < p; ++r) s += Q[(int64_t)r * p + i] * (ct[r] / lamb[r]);
+        betahat[i] = s;
+    }
+    t.sync();
+    // centred quantities: y_c = y - ybar, beta_c = betahat - ybar e_0, r = y_c - X beta_c
+    const double ybar = k.sum_y / k.n;
+    const int64_t row0 = (int64_t)idx[0] * ldg;    // G[0][*] = column sums
+    double d1 = 0.0, d2 = 0.0, d3 = 0.0;           // bc'xc, bc'G bc, g0'bc
+    for (int i = t.tid; i < p; i += t.nthr) {
+        double bi = betahat[i] - (i == 0 ? ybar : 0.0);
+        scratch[i] = bi;
+    }
+    t.sync();
+    for (int i = t.tid; i < p; i += t.nthr) {
+        const double *gi = G + (int64_t)idx[i] * ldg;
+        double s = 0.0;
+        for (int j = 0; j < p; ++j) s += gi[idx[j]] * scratch[j];
+        double g0 = G[row0 + idx[i]];
+        double xc = Xty[idx[i]] - ybar * g0;
+        d1 += scratch[i] * xc;
+        d2 += scratch[i] * s;
+        d3 += g0 * scratch[i];
+    }
+    team_sum3(t, d1, d2, d3, red, 0);
+    t.sync();
+    double yty_c = k.yty - k.n * ybar * ybar;
+    double srr = yty_c - 2.0 * d1 + d2;
+    double sr = -d3;
+    double siglik = srr / k.n - (sr / k.n) * (sr / k.n);
+    double lik = -(k.n / 2.0) * log(siglik) - (k.n - 1.0) / 2.0;
+    return (double)p * log(k.n) - 2.0 * lik;
+}
+
+struct ChainRng {
+    int mode;                 // FOKL_RNG_INJECTED = 1, FOKL_RNG_PHILOX = 2
+    const double *variates;   // injected: D rows of [z(p), g1, g2]
+    const double *sign_fix;   // optional p
+    Philox philox;
+    uint32_t stream_lo, stream_hi;
+    double *gg;               // philox: scratch D x 2 pre-generated standard gammas
+};
+
+// The draw loop of FR:1519-1548 in the eigenbasis (gamma = Q' beta):
+//   d_j = 1/(lamb_j + 1/tau^2);  gamma_j = d_j ct_j + sqrt(sig^2) sqrt(d_j) z_j
+//   bstar = b + 0.5 (sum lamb gamma^2 - 2 sum gamma ct + yty + sum gamma^2 / tau^2)
+//   sig^2 = 1 / ((1/bstar) G1);  btau* = (1/(2 sig^2)) sum gamma^2 + btau;  tau^2 = 1 / ((1/btau*) G2)
+// gam (out) D x p row-major, sigs/taus (out) D.  Returns 1 if bstar < 0 was seen.
+FOKL_HD int gibbs_chain(const Team &t, int p, const double *lamb, const double *ct, const CandConst &k,
+                        const ChainRng &rng, double *gam, double *sigs, double *taus, double *red)
+{
+    const int D = k.draws;
+    const double astar = k.a + 1.0 + k.n / 2.0 + (double)p / 2.0;
+    const double atau_star = k.atau + (double)(p - 1) / 2.0;
+    if (rng.mode == 2) {
+        for (int d = t.tid; d < D; d += t.nthr) {
+            rng.gg[2 * d + 0] = philox_gamma(rng.philox, rng.stream_lo, rng.stream_hi, (uint32_t)d, 0u, astar);
+            rng.gg[2 * d + 1] = philox_gamma(rng.philox, rng.stream_lo, rng.stream_hi, (uint32_t)d, 1024u,
+                                             atau_star);
+        }
+        t.sync();
+    }
+    double sig = k.sigsqd0, tau = k.tausqd0;
+    int bad = 0;
+    for (int d = 0; d < D; ++d) {
+        const double itau = 1.0 / tau;
+        const double ssig = sqrt(sig);
+        double s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        for (int e = t.tid; e < p; e += t.nthr) {
+            double z;
+            if (rng.mode == 1) z = rng.variates[(int64_t)d * (p + 2) + e];
+            else z = philox_normal(rng.philox, rng.stream_lo, rng.stream_hi, (uint32_t)d, (uint32_t)e);
+            if (rng.sign_fix) z *= rng.sign_fix[e];
+            double l = lamb[e], c = ct[e];
+            double dj = 1.0 / (l + itau);
+            double g = dj * c + ssig * sqrt(dj) * z;
+            gam[(int64_t)d * p + e] = g;
+            s1 += l * g * g;
+            s2 += g * c;
+            s3 += g * g;
+        }
+        team_sum3(t, s1, s2, s3, red, d & 1);
+        double g1, g2;
+        if (rng.mode == 1) {
+            g1 = rng.variates[(int64_t)d * (p + 2) + p];
+            g2 = rng.variates[(int64_t)d * (p + 2) + p + 1];
+        } else {
+            g1 = rng.gg[2 * d];
+            g2 = rng.gg[2 * d + 1];
+        }
+        double bstar = k.b + 0.5 * (s1 - 2.0 * s2 + k.yty + s3 / tau);
+        if (bstar < 0.0) { sig = nan(""); bad = 1; }
+        else sig = 1.0 / ((1.0 / bstar) * g1);
+        double btau_star = (1.0 / (2.0 * sig)) * s3 + k.btau;
+        tau = 1.0 / ((1.0 / btau_star) * g2);
+        if (t.tid == 0) { sigs[d] = sig; taus[d] = tau; }
+    }
+    return bad;
+}
+
+}  // namespace fokl

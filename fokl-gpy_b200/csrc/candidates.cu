@@ -1,0 +1,390 @@
+// candidates.cu -- K3/K4: per-candidate spectral factorisation, betahat, BIC, eigenbasis Gibbs chain,
+// betas = Gamma Q' and the column statistics the forward-selection loop reads (sm_100a).
+//
+// One CTA per candidate model.  Replaces, per `gibbs` invocation of the reference
+// (src/FoKL/FoKLRoutines.py): eigh FR:1499, betahat FR:1502-1504, draw loop FR:1519-1548,
+// BIC FR:1551-1554, and the reductions over the draws at FR:1656-1658, 1671.
+// The numerical core lives in cand_math.cuh (shared with the host emulation used by the CPU tests).
+#include "fokl_ctx.cuh"
+#include "cand_math.cuh"
+#include <algorithm>
+#include <math.h>
+#include <string.h>
+#include <vector>
+
+namespace {
+
+using fokl::CandConst;
+using fokl::ChainRng;
+using fokl::Team;
+
+constexpr int kEigThreads = 256;
+constexpr int kChainThreads = 128;
+constexpr int kSmemHeaderDoubles = 64;   // reduction scratch (2*3*8) + flag
+
+struct CandMeta {
+    int32_t p;
+    int32_t set_off;     // into col_sets
+    int32_t chain_idx;   // -1: no chain
+    int32_t pad;
+    int64_t vec_off;     // sum of p of previous candidates
+    int64_t mat_off;     // sum of p^2 of previous candidates
+    int64_t wv_off;      // offset (doubles) of this candidate's W|V pair in the global workspace
+    int64_t gam_off;     // sum of p of previous *chain* candidates
+    uint64_t stream_id;
+};
+
+struct EigParams {
+    const double *G;
+    int64_t ldg;
+    const double *Xty;
+    const int32_t *col_sets;
+    const CandMeta *meta;
+    CandConst k;
+    double *wv;          // global W|V workspace
+    double *lam_raw, *scratch, *ct;   // packed by vec_off
+    int32_t *perm;
+    double *lamb, *Q, *betahat, *ev;
+    int32_t *info;
+    int smem_doubles;    // dynamic shared memory available for W|V (after the header)
+};
+
+__device__ __forceinline__ Team make_team()
+{
+    Team t;
+    t.tid = threadIdx.x; t.nthr = blockDim.x;
+    t.lane = threadIdx.x & 31; t.nlane = 32;
+    t.warp = threadIdx.x >> 5; t.nwarp = blockDim.x >> 5;
+    return t;
+}
+
+__global__ void __launch_bounds__(kEigThreads) cand_eig_kernel(const EigParams P)
+{
+    extern __shared__ __align__(16) double sh[];
+    const Team t = make_team();
+    const CandMeta m = P.meta[blockIdx.x];
+    const int p = m.p;
+    const int32_t *idx = P.col_sets + m.set_off;
+    double *red = sh;
+    volatile int *flag = reinterpret_cast<volatile int *>(sh + 56);
+    const bool in_smem = (2 * p * p <= P.smem_doubles);
+    double *W = in_smem ? (sh + kSmemHeaderDoubles) : (P.wv + m.wv_off);
+    double *V = W + (size_t)p * p;
+
+    for (int e = t.tid; e < p * p; e += t.nthr) {
+        int col = e / p, row = e - col * p;
+        W[e] = P.G[(int64_t)idx[row] * P.ldg + idx[col]];
+    }
+    t.sync();
+    const double tol = 2.220446049250313e-16 * (2.0 * sqrt((double)p) + 6.0);
+    int sweeps = fokl::jacobi_eigh(t, W, V, p, p, 40, tol, flag);
+    double *lamb = P.lamb + m.vec_off;
+    double *Q = P.Q + m.mat_off;
+    fokl::eig_finish(t, W, V, p, p, P.lam_raw + m.vec_off, P.perm + m.vec_off, lamb, Q);
+    double ev = fokl::ols_and_bic(t, P.G, P.ldg, P.Xty, idx, p, lamb, Q, P.k, P.ct + m.vec_off,
+                                  P.betahat + m.vec_off, P.scratch + m.vec_off, red);
+    if (t.tid == 0) {
+        P.ev[blockIdx.x] = ev;
+        P.info[blockIdx.x] = sweeps << 8;
+    }
+}
+
+struct ChainParams {
+    const CandMeta *meta;
+    const int32_t *chain_list;
+    CandConst k;
+    const double *lamb, *ct;
+    int rng_mode;
+    uint64_t seed;
+    const double *variates, *sign_fix;
+    double *gg, *gam, *sigs, *taus;
+    int32_t *info;
+};
+
+__global__ void __launch_bounds__(kChainThreads) cand_chain_kernel(const ChainParams P)
+{
+    __shared__ double red[2 * 3 * (kChainThreads / 32)];
+    const Team t = make_team();
+    const int c = P.chain_list[blockIdx.x];
+    const CandMeta m = P.meta[c];
+    const int p = m.p;
+    const int D = P.k.draws;
+    ChainRng rng;
+    rng.mode = P.rng_mode;
+    rng.variates = P.variates ? P.variates + (int64_t)D * (m.vec_off + 2 * (int64_t)c) : nullptr;
+    rng.sign_fix = P.sign_fix ? P.sign_fix + m.vec_off : nullptr;
+    rng.philox.k0 = (uint32_t)P.seed;
+    rng.philox.k1 = (uint32_t)(P.seed >> 32);
+    rng.stream_lo = (uint32_t)m.stream_id;
+    rng.stream_hi = (uint32_t)(m.stream_id >> 32) & 0x7fffffffu;
+    rng.gg = P.gg + 2 * (int64_t)D * blockIdx.x;
+    int bad = fokl::gibbs_chain(t, p, P.lamb + m.vec_off, P.ct + m.vec_off, P.k, rng, P.gam + (int64_t)D * m.gam_off,
+                                P.sigs + (int64_t)D * c, P.taus + (int64_t)D * c, red);
+    if (t.tid == 0 && bad) atomicOr(P.info + c, 1);
+}
+
+// betas[k][i] = sum_r Gamma[k][r] * Q[r*p + i]   (FR:1528 in the eigenbasis: beta = Q gamma)
+struct BetasParams {
+    const CandMeta *meta;
+    const int32_t *chain_list;
+    const double *gam, *Q;
+    double *betas;          // packed at D * vec_off
+    int D, tiles_i;
+};
+
+__global__ void __launch_bounds__(256) cand_betas_kernel(const BetasParams P)
+{
+    __shared__ double As[16][64 + 1];
+    __shared__ double Bs[16][64];
+    const int c = P.chain_list[blockIdx.y];
+    const CandMeta m = P.meta[c];
+    const int p = m.p;
+    const int ti = blockIdx.x % P.tiles_i, tk = blockIdx.x / P.tiles_i;
+    const int i0 = ti * 64, k0 = tk * 64;
+    if (i0 >= p) return;
+    const double *A = P.gam + (int64_t)P.D * m.gam_off;
+    const double *B = P.Q + m.mat_off;
+    double *C = P.betas + (int64_t)P.D * m.vec_off;
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    double acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+    for (int r0 = 0; r0 < p; r0 += 16) {
+        {
+            int row = tid >> 2, rr = (tid & 3) * 4;
+            int k = k0 + row;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                int r = r0 + rr + q;
+                As[rr + q][row] = (k < P.D && r < p) ? A[(int64_t)k * p + r] : 0.0;
+            }
+            int br = tid >> 4, ii = (tid & 15) * 4;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                int r = r0 + br, i = i0 + ii + q;
+                Bs[br][ii + q] = (r < p && i < p) ? B[(int64_t)r * p + i] : 0.0;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            double a[4], b[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { a[q] = As[r][ty * 4 + q]; b[q] = Bs[r][tx * 4 + q]; }
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+#pragma unroll
+                for (int z = 0; z < 4; ++z) acc[x][z] += a[x] * b[z];
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int x = 0; x < 4; ++x) {
+        int k = k0 + ty * 4 + x;
+        if (k >= P.D) continue;
+#pragma unroll
+        for (int z = 0; z < 4; ++z) {
+            int i = i0 + tx * 4 + z;
+            if (i < p) C[(int64_t)k * p + i] = acc[x][z];
+        }
+    }
+}
+
+struct StatsParams {
+    const CandMeta *meta;
+    const int32_t *chain_list;
+    const double *betas;
+    double *stats;
+    int D, from0, from1;
+};
+
+__global__ void cand_stats_kernel(const StatsParams P)
+{
+    const int c = P.chain_list[blockIdx.y];
+    const CandMeta m = P.meta[c];
+    const int p = m.p;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p) return;
+    const double *B = P.betas + (int64_t)P.D * m.vec_off;
+    double s0 = 0.0, s1 = 0.0;
+    for (int k = P.from0; k < P.D; ++k) {
+        double v = B[(int64_t)k * p + i];
+        s0 += v;
+        if (k >= P.from1) s1 += v;
+    }
+    const double n0 = (double)(P.D - P.from0), n1 = (double)(P.D - P.from1);
+    const double m0 = s0 / n0, m1 = s1 / n1;
+    double q = 0.0;
+    for (int k = P.from1; k < P.D; ++k) {
+        double d = B[(int64_t)k * p + i] - m1;
+        q += d * d;
+    }
+    double *S = P.stats + 3 * m.vec_off;
+    S[i] = m1;
+    S[p + i] = sqrt(q / n1);
+    S[2 * p + i] = m0;
+}
+
+template <typename T>
+T *carve(char *&cur, size_t count)
+{
+    uintptr_t a = ((uintptr_t)cur + 15) & ~(uintptr_t)15;
+    T *r = reinterpret_cast<T *>(a);
+    cur = reinterpret_cast<char *>(a + count * sizeof(T));
+    return r;
+}
+
+}  // namespace
+
+extern "C" int fokl_candidates_eval(fokl_ctx *ctx, const double *G, int64_t ldg, const double *Xty,
+                                    const int32_t *col_sets, const int32_t *set_offsets, int n_cand,
+                                    const fokl_hypers *hyp, const uint8_t *run_chain, int rng_mode, uint64_t seed,
+                                    const uint64_t *stream_ids, const double *variates, const double *sign_fix,
+                                    double *ev, double *betahat, double *lamb, double *Q, double *betas,
+                                    double *sigs, double *taus, double *stats, int32_t *info)
+{
+    FOKL_CHECK_CTX(ctx);
+    if (!G || !Xty || !col_sets || !set_offsets || !hyp || !ev || !info || n_cand < 1)
+        FOKL_FAIL(ctx, FOKL_EINVAL, "candidates_eval: bad argument");
+    if (rng_mode != FOKL_RNG_NONE && rng_mode != FOKL_RNG_INJECTED && rng_mode != FOKL_RNG_PHILOX)
+        FOKL_FAIL(ctx, FOKL_EINVAL, "candidates_eval: unknown rng_mode");
+    if (rng_mode == FOKL_RNG_INJECTED && !variates) FOKL_FAIL(ctx, FOKL_EINVAL, "candidates_eval: variates required");
+    if (rng_mode != FOKL_RNG_NONE && hyp->draws < 1) FOKL_FAIL(ctx, FOKL_EINVAL, "candidates_eval: draws < 1");
+    int rc = fokl_bind_device(ctx);
+    if (rc) return rc;
+
+    const int D = hyp->draws;
+    const size_t smem_cap = ctx->smem_optin ? ctx->smem_optin : 48 * 1024;
+    const int smem_wv_cap = (int)((smem_cap - kSmemHeaderDoubles * sizeof(double)) / sizeof(double));
+
+    std::vector<CandMeta> meta(n_cand);
+    std::vector<int32_t> chain_list;
+    int64_t vec = 0, mat = 0, wv = 0, gam = 0;
+    int pmax = 0, pmax_chain = 0;
+    for (int c = 0; c < n_cand; ++c) {
+        int p = set_offsets[c + 1] - set_offsets[c];
+        if (p < 1 || ldg < p) FOKL_FAIL(ctx, FOKL_EINVAL, "candidates_eval: empty or oversized column set");
+        if (col_sets[set_offsets[c]] < 0) FOKL_FAIL(ctx, FOKL_EINVAL, "candidates_eval: negative column index");
+        CandMeta &m = meta[c];
+        m.p = p; m.set_off = set_offsets[c]; m.pad = 0;
+        m.vec_off = vec; m.mat_off = mat;
+        const bool in_smem = (2 * (int64_t)p * p <= smem_wv_cap);
+        m.wv_off = wv;
+        if (!in_smem) wv += 2 * (int64_t)p * p;
+        const bool chain = rng_mode != FOKL_RNG_NONE && (!run_chain || run_chain[c]);
+        m.chain_idx = chain ? (int32_t)chain_list.size() : -1;
+        m.gam_off = gam;
+        m.stream_id = stream_ids ? stream_ids[c] : (uint64_t)c;
+        if (chain) { chain_list.push_back(c); gam += p; pmax_chain = std::max(pmax_chain, p); }
+        vec += p; mat += (int64_t)p * p;
+        pmax = std::max(pmax, p);
+    }
+    const int n_chain = (int)chain_list.size();
+    const int total_p = set_offsets[n_cand];
+
+    // ---- metadata upload ---------------------------------------------------------------------------------
+    size_t meta_bytes = 64 + (size_t)total_p * sizeof(int32_t) + (size_t)n_cand * sizeof(CandMeta) +
+                        (size_t)(n_chain + 1) * sizeof(int32_t) + 64;
+    char *dmeta = (char *)fokl_scratch(ctx, fokl_ctx::B_META, meta_bytes);
+    if (!dmeta) return FOKL_ENOMEM;
+    std::vector<char> hmeta(meta_bytes, 0);
+    char *dcur = dmeta;
+    int32_t *d_sets = carve<int32_t>(dcur, total_p);
+    CandMeta *d_meta = carve<CandMeta>(dcur, n_cand);
+    int32_t *d_chain = carve<int32_t>(dcur, n_chain + 1);
+    memcpy(hmeta.data() + ((char *)d_sets - dmeta), col_sets, (size_t)total_p * sizeof(int32_t));
+    memcpy(hmeta.data() + ((char *)d_meta - dmeta), meta.data(), (size_t)n_cand * sizeof(CandMeta));
+    if (n_chain) memcpy(hmeta.data() + ((char *)d_chain - dmeta), chain_list.data(), (size_t)n_chain * sizeof(int32_t));
+    FOKL_CUDA(ctx, cudaMemcpyAsync(dmeta, hmeta.data(), (size_t)(dcur - dmeta), cudaMemcpyHostToDevice, ctx->stream));
+
+    // ---- workspaces --------------------------------------------------------------------------------------
+    double *d_wv = nullptr;
+    if (wv > 0) {
+        d_wv = (double *)fokl_scratch(ctx, fokl_ctx::B_CAND_A, (size_t)wv * sizeof(double));
+        if (!d_wv) return FOKL_ENOMEM;
+    }
+    size_t b_bytes = 256 + (size_t)vec * (5 * sizeof(double) + sizeof(int32_t)) + (Q ? 0 : (size_t)mat * sizeof(double));
+    char *bcur = (char *)fokl_scratch(ctx, fokl_ctx::B_CAND_B, b_bytes);
+    if (!bcur) return FOKL_ENOMEM;
+    double *d_lam_raw = carve<double>(bcur, vec);
+    double *d_scratch = carve<double>(bcur, vec);
+    double *d_ct = carve<double>(bcur, vec);
+    double *d_lamb = lamb ? lamb : carve<double>(bcur, vec);
+    double *d_betahat = betahat ? betahat : carve<double>(bcur, vec);
+    int32_t *d_perm = carve<int32_t>(bcur, vec);
+    double *d_Q = Q ? Q : carve<double>(bcur, mat);
+
+    CandConst k;
+    k.a = hyp->a; k.b = hyp->b; k.atau = hyp->atau; k.btau = hyp->btau;
+    k.sigsqd0 = hyp->sigsqd0; k.tausqd0 = hyp->tausqd0; k.yty = hyp->yty; k.sum_y = hyp->sum_y;
+    k.n = (double)hyp->n; k.draws = D; k.from0 = hyp->stat_from0; k.from1 = hyp->stat_from1;
+
+    // ---- eig + betahat + BIC -------------------------------------------------------------------------------
+    {
+        EigParams P;
+        P.G = G; P.ldg = ldg; P.Xty = Xty; P.col_sets = d_sets; P.meta = d_meta; P.k = k;
+        P.wv = d_wv; P.lam_raw = d_lam_raw; P.scratch = d_scratch; P.ct = d_ct; P.perm = d_perm;
+        P.lamb = d_lamb; P.Q = d_Q; P.betahat = d_betahat; P.ev = ev; P.info = info;
+        int64_t need = 2 * (int64_t)pmax * pmax;
+        int wv_doubles = (int)std::min<int64_t>(need, smem_wv_cap);
+        if (need > smem_wv_cap) {
+            // the largest candidate spills to global memory; still give smaller ones what they need
+            int best = 0;
+            for (int c = 0; c < n_cand; ++c) {
+                int64_t q = 2 * (int64_t)meta[c].p * meta[c].p;
+                if (q <= smem_wv_cap) best = std::max<int>(best, (int)q);
+            }
+            wv_doubles = best;
+        }
+        P.smem_doubles = wv_doubles;
+        size_t smem = (size_t)(kSmemHeaderDoubles + wv_doubles) * sizeof(double);
+        FOKL_CUDA(ctx, cudaFuncSetAttribute(cand_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
+        cand_eig_kernel<<<n_cand, kEigThreads, smem, ctx->stream>>>(P);
+        FOKL_LAUNCH_CHECK(ctx);
+    }
+    if (n_chain == 0) return FOKL_OK;
+    if (hyp->stat_from0 < 0 || hyp->stat_from0 >= D || hyp->stat_from1 < 0 || hyp->stat_from1 >= D)
+        FOKL_FAIL(ctx, FOKL_EINVAL, "candidates_eval: statistic windows outside the chain");
+
+    // ---- chain -------------------------------------------------------------------------------------------------
+    size_t c_bytes = 256 + ((size_t)D * gam + (size_t)2 * D * n_chain) * sizeof(double);
+    char *ccur = (char *)fokl_scratch(ctx, fokl_ctx::B_CAND_C, c_bytes);
+    if (!ccur) return FOKL_ENOMEM;
+    double *d_gam = carve<double>(ccur, (size_t)D * gam);
+    double *d_gg = carve<double>(ccur, (size_t)2 * D * n_chain);
+    size_t d_bytes = 256 + (betas ? 0 : (size_t)D * vec * sizeof(double)) + (sigs ? 0 : (size_t)D * n_cand * sizeof(double)) +
+                     (taus ? 0 : (size_t)D * n_cand * sizeof(double));
+    char *ecur = (char *)fokl_scratch(ctx, fokl_ctx::B_CAND_D, d_bytes);
+    if (!ecur) return FOKL_ENOMEM;
+    double *d_betas = betas ? betas : carve<double>(ecur, (size_t)D * vec);
+    double *d_sigs = sigs ? sigs : carve<double>(ecur, (size_t)D * n_cand);
+    double *d_taus = taus ? taus : carve<double>(ecur, (size_t)D * n_cand);
+    {
+        ChainParams P;
+        P.meta = d_meta; P.chain_list = d_chain; P.k = k; P.lamb = d_lamb; P.ct = d_ct;
+        P.rng_mode = rng_mode; P.seed = seed; P.variates = variates; P.sign_fix = sign_fix;
+        P.gg = d_gg; P.gam = d_gam; P.sigs = d_sigs; P.taus = d_taus; P.info = info;
+        cand_chain_kernel<<<n_chain, kChainThreads, 0, ctx->stream>>>(P);
+        FOKL_LAUNCH_CHECK(ctx);
+    }
+    if (!betas && !stats) return FOKL_OK;
+    {
+        BetasParams P;
+        P.meta = d_meta; P.chain_list = d_chain; P.gam = d_gam; P.Q = d_Q; P.betas = d_betas; P.D = D;
+        P.tiles_i = (pmax_chain + 63) / 64;
+        dim3 grid((unsigned)(P.tiles_i * ((D + 63) / 64)), (unsigned)n_chain);
+        cand_betas_kernel<<<grid, 256, 0, ctx->stream>>>(P);
+        FOKL_LAUNCH_CHECK(ctx);
+    }
+    if (stats) {
+        StatsParams P;
+        P.meta = d_meta; P.chain_list = d_chain; P.betas = d_betas; P.stats = stats; P.D = D;
+        P.from0 = hyp->stat_from0; P.from1 = hyp->stat_from1;
+        dim3 grid((unsigned)((pmax_chain + 127) / 128), (unsigned)n_chain);
+        cand_stats_kernel<<<grid, 128, 0, ctx->stream>>>(P);
+        FOKL_LAUNCH_CHECK(ctx);
+    }
+    return FOKL_OK;
+}

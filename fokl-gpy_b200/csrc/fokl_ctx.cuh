@@ -1,0 +1,69 @@
+// fokl_ctx.cuh -- internal context shared by the translation units of libfokl_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include "../../include/fokl_b200.h"
+
+struct fokl_buf {
+    void *ptr = nullptr;
+    size_t bytes = 0;
+};
+
+struct fokl_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+    int64_t launches = 0;
+    int num_sms = 148;
+    size_t smem_optin = 0;
+
+    // basis tables (device)
+    double *cubic_tab = nullptr;
+    int cubic_orders = 0, cubic_pieces = 0;
+    double *bern_tab = nullptr;
+    int bern_orders = 0, bern_row = 0;
+
+    // deferred error flag written by kernels (device int), checked in fokl_ctx_synchronize
+    int *d_flag = nullptr;
+
+    // growable scratch buffers, indexed by purpose
+    enum { B_META = 0, B_BASIS, B_GRAM, B_CAND_A, B_CAND_B, B_CAND_C, B_CAND_D, B_MISC, B_COUNT };
+    fokl_buf bufs[B_COUNT];
+};
+
+#define FOKL_CHECK_CTX(ctx) \
+    do { if (!(ctx)) return FOKL_EINVAL; } while (0)
+
+#define FOKL_CUDA(ctx, call)                                                                      \
+    do {                                                                                          \
+        cudaError_t e__ = (call);                                                                 \
+        if (e__ != cudaSuccess) {                                                                 \
+            char b__[512];                                                                        \
+            snprintf(b__, sizeof b__, "%s:%d: %s -> %s", __FILE__, __LINE__, #call,               \
+                     cudaGetErrorString(e__));                                                    \
+            (ctx)->err = b__;                                                                     \
+            return FOKL_ECUDA;                                                                    \
+        }                                                                                         \
+    } while (0)
+
+#define FOKL_FAIL(ctx, code, msg) \
+    do { (ctx)->err = (msg); return (code); } while (0)
+
+// returns nullptr (and sets ctx->err) on failure
+void *fokl_scratch(fokl_ctx *ctx, int which, size_t bytes);
+
+static inline int fokl_bind_device(fokl_ctx *ctx)
+{
+    FOKL_CUDA(ctx, cudaSetDevice(ctx->device));
+    return FOKL_OK;
+}
+
+#define FOKL_LAUNCH_CHECK(ctx)                       \
+    do {                                             \
+        (ctx)->launches += 1;                        \
+        FOKL_CUDA(ctx, cudaGetLastError());          \
+    } while (0)

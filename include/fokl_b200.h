@@ -135,10 +135,11 @@ int fokl_candidates_eval(fokl_ctx *ctx, const double *G, int64_t ldg, const doub
 
 /* ---- checks / "next" rows ------------------------------------------------------------------- */
 
-/* residual moments of an explicit model: out (dev, 2 doubles) = { sum r, sum r^2 }, r = y - X[:, :p] beta
- * (the N-length form of FR:1551; used to cross-check the Gram-only BIC at full size). */
+/* residual moments of an explicit model: out (dev, 2 doubles) = { sum r, sum r^2 },
+ * r = y - X[:, cols] beta  (cols host, p entries, or NULL for the first p columns; beta dev, p).
+ * The N-length form of FR:1551; used to refine / cross-check the Gram-only BIC. */
 int fokl_residual_moments(fokl_ctx *ctx, const double *X, int64_t ld, int64_t n, int p,
-                          const double *beta, const double *y, double *out);
+                          const int32_t *cols, const double *beta, const double *y, double *out);
 
 /* evaluate (FR:966-969): out[i][d] = sum_j X[i][j] * betas[d][j]; X column-major (ld), betas row-major
  * n_draws x p (dev), out row-major n x n_draws (dev). */

@@ -249,16 +249,22 @@ def draw_variates(p, draws, astar, atau_star):
     return z, g1, g2
 
 
-def gibbs_from_X(X, data, a, b, atau, btau, draws, sigsqd, tausqd, dtd, literal=True, variates=None):
+def gibbs_from_X(X, data, a, b, atau, btau, draws, sigsqd, tausqd, dtd, literal=True, variates=None, gram=None):
     """FR:1492-1558 given the finished design matrix X (N x P, column 0 = ones).
 
     literal=True  : dense products per draw exactly as the reference writes them (bit-exact on the
                     same BLAS); draws come from the global numpy RNG.
     literal=False : eigenbasis form, O(p) per draw; `variates=(z, g1, g2)` may be injected.
+    gram=(XtX, Xty): parity-harness hook -- use these Gram bits (e.g. the device's) instead of X'X, X'y, so
+                    that LAPACK's eigenvector signs are those of the matrix the device factorised.
     Returns dict(betas, sigs, taus, betahat, ev, XtX, Xty, Lamb, Q)."""
     mmtx = X.shape[1] - 1
-    XtX = np.transpose(X).dot(X)
-    Xty = np.transpose(X).dot(data)
+    if gram is None:
+        XtX = np.transpose(X).dot(X)
+        Xty = np.transpose(X).dot(data)
+    else:
+        XtX = np.array(gram[0], dtype=np.float64)
+        Xty = np.array(gram[1], dtype=np.float64).reshape(-1, 1)
     Lamb, Q = eigh(XtX)
     Lamb_inv = np.diag(1 / Lamb)
     betahat = Q.dot(Lamb_inv).dot(np.transpose(Q)).dot(Xty)
@@ -347,12 +353,13 @@ class FitResult(dict):
 
 def fit(inputs, data, phis, kernel=CUBIC, a=4, b=None, atau=4, btau=None, tolerance=3, burnin=1000,
         draws=1000, gimmie=False, way3=False, threshav=0.05, threshstda=0.5, threshstdb=2, aic=False,
-        basis='c', literal=True, threads=1, on_gibbs=None, console=False):
+        basis='c', literal=True, threads=1, on_gibbs=None, console=False, gram_hook=None):
     """Forward selection of FR:1561-1760 on already-normalised `inputs` (N x M in [0, 1]) and
     `data` (N x 1).  relats_in = [] only (anything else crashes upstream at FR:1631).
 
     basis: 'c' (C helper) or 'py' (literal Python triple loop, the reference's real cost profile).
     on_gibbs(info): optional callback per `gibbs` invocation (for recording golden vectors / timing).
+    gram_hook(discmtx) -> (XtX, Xty) or None: parity-harness hook, see gibbs_from_X.
     Returns FitResult(betas, mtx, evs, n_gibbs, betas_full)."""
     inputs = np.asarray(inputs, dtype=np.float64)
     data = np.asarray(data, dtype=np.float64).reshape(-1, 1)
@@ -378,7 +385,8 @@ def fit(inputs, data, phis, kernel=CUBIC, a=4, b=None, atau=4, btau=None, tolera
         else:
             newcols = build(inputs, discmtx[nxin - 1:mmtx], phis, kernel)
             X = np.append(Xin, newcols, axis=1)
-        r = gibbs_from_X(X, data, a, b, atau, btau, total, sigsqd0, tausqd0, dtd, literal=literal)
+        gram = gram_hook(discmtx) if gram_hook is not None else None
+        r = gibbs_from_X(X, data, a, b, atau, btau, total, sigsqd0, tausqd0, dtd, literal=literal, gram=gram)
         counter[0] += 1
         X = X[:, 0:mmtx + 1]
         if on_gibbs is not None:

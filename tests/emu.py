@@ -1,0 +1,106 @@
+"""ctypes wrapper around tests/host_emu/fokl_emu.cpp (host emulation of the CUDA kernels' math)."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SRC = os.path.join(_HERE, 'host_emu', 'fokl_emu.cpp')
+_SO = os.path.join(_HERE, 'host_emu', 'libfokl_emu.so')
+_CSRC = os.path.join(os.path.dirname(_HERE), 'fokl-gpy_b200', 'csrc')
+
+_vp, _i64, _i32, _u64, _f64 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_uint64, ctypes.c_double
+
+
+class EmuHypers(ctypes.Structure):
+    _fields_ = [(k, _f64) for k in ('a', 'b', 'atau', 'btau', 'sigsqd0', 'tausqd0', 'yty', 'sum_y')] + \
+               [('n', _i64), ('draws', ctypes.c_int32), ('from0', ctypes.c_int32), ('from1', ctypes.c_int32),
+                ('reserved', ctypes.c_int32)]
+
+
+def _newest_dep():
+    deps = [_SRC] + [os.path.join(_CSRC, f) for f in ('fokl_math.cuh', 'cand_math.cuh')]
+    return max(os.path.getmtime(d) for d in deps)
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_SO) or os.path.getmtime(_SO) < _newest_dep():
+        subprocess.check_call(['g++', '-O2', '-ffp-contract=off', '-std=c++17', '-shared', '-fPIC', '-o', _SO, _SRC])
+    L = ctypes.CDLL(_SO)
+    L.emu_basis_cubic.argtypes = [_vp, _i64, _vp, _i32, _vp, _i32, _vp]
+    L.emu_basis_cubic.restype = _i32
+    L.emu_phind.argtypes = [_vp, _i64, _i32, _vp, _vp]
+    L.emu_phind.restype = _i32
+    L.emu_basis_bernoulli.argtypes = [_vp, _i64, _vp, _i32, _vp, _i32, _vp]
+    L.emu_basis_bernoulli.restype = None
+    L.emu_candidate.argtypes = [_vp, _i64, _vp, _vp, _i32, ctypes.POINTER(EmuHypers), _i32, _u64, _u64, _vp, _vp,
+                                _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
+    L.emu_candidate.restype = _i32
+    L.emu_philox_normals.argtypes = [_u64, _u64, _i32, _i32, _vp]
+    L.emu_philox_normals.restype = None
+    L.emu_philox_gammas.argtypes = [_u64, _u64, _i32, _f64, _vp]
+    L.emu_philox_gammas.restype = None
+    _lib = L
+    return L
+
+
+def basis_cubic(x, orders, tab):
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    orders = np.ascontiguousarray(orders, dtype=np.int32)
+    tab = np.ascontiguousarray(tab, dtype=np.float64)
+    out = np.zeros((len(x), len(orders)))
+    bad = lib().emu_basis_cubic(x.ctypes.data, len(x), orders.ctypes.data, len(orders), tab.ctypes.data, tab.shape[1],
+                                out.ctypes.data)
+    return out, bad
+
+
+def basis_bernoulli(x, orders, tab):
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    orders = np.ascontiguousarray(orders, dtype=np.int32)
+    tab = np.ascontiguousarray(tab, dtype=np.float64)
+    out = np.zeros((len(x), len(orders)))
+    lib().emu_basis_bernoulli(x.ctypes.data, len(x), orders.ctypes.data, len(orders), tab.ctypes.data, tab.shape[1],
+                              out.ctypes.data)
+    return out
+
+
+def phind(x, n_piece=499):
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    ph = np.zeros(len(x), dtype=np.int32)
+    xs = np.zeros(len(x))
+    bad = lib().emu_phind(x.ctypes.data, len(x), n_piece, ph.ctypes.data, xs.ctypes.data)
+    return ph, xs, bad
+
+
+def candidate(G, Xty, idx, hyp, rng_mode=0, seed=0, stream=0, variates=None, sign_fix=None):
+    """hyp: dict with a, b, atau, btau, sigsqd0, tausqd0, yty, sum_y, n, draws."""
+    G = np.ascontiguousarray(G, dtype=np.float64)
+    Xty = np.ascontiguousarray(np.asarray(Xty).reshape(-1), dtype=np.float64)
+    idx = np.ascontiguousarray(idx, dtype=np.int32)
+    p = len(idx)
+    D = int(hyp['draws'])
+    h = EmuHypers(hyp['a'], hyp['b'], hyp['atau'], hyp['btau'], hyp['sigsqd0'], hyp['tausqd0'], hyp['yty'],
+                  hyp['sum_y'], int(hyp['n']), D, int(np.ceil(D / 2)), int(np.ceil(D / 2 + 1)), 0)
+    ev = np.zeros(1)
+    betahat = np.zeros(p)
+    lamb = np.zeros(p)
+    Q = np.zeros((p, p))          # row r = eigenvector r (column-major p x p)
+    betas = np.zeros((D, p))
+    sigs = np.zeros(D)
+    taus = np.zeros(D)
+    info = np.zeros(1, dtype=np.int32)
+    v = None if variates is None else np.ascontiguousarray(variates, dtype=np.float64)
+    s = None if sign_fix is None else np.ascontiguousarray(sign_fix, dtype=np.float64)
+    lib().emu_candidate(G.ctypes.data, G.shape[1], Xty.ctypes.data, idx.ctypes.data, p, ctypes.byref(h), rng_mode,
+                        seed, stream, None if v is None else v.ctypes.data, None if s is None else s.ctypes.data,
+                        ev.ctypes.data, betahat.ctypes.data, lamb.ctypes.data, Q.ctypes.data, betas.ctypes.data,
+                        sigs.ctypes.data, taus.ctypes.data, info.ctypes.data)
+    return dict(ev=ev[0], betahat=betahat, lamb=lamb, Q=Q.T.copy(), betas=betas, sigs=sigs, taus=taus,
+                info=int(info[0]))

@@ -1,0 +1,121 @@
+// fokl_emu.cpp -- host emulation of the numerical core of the CUDA kernels (TEST INFRASTRUCTURE).
+//
+// Compiles fokl-gpy_b200/csrc/{fokl_math,cand_math}.cuh as plain C++ with a single-thread "Team"
+// (nlane = nwarp = 1, barriers are no-ops) so the CPU test-suite can check the kernel math
+// (basis evaluation, Jacobi eigensolver, betahat/BIC, eigenbasis Gibbs chain) against the oracle
+// without a GPU.  Build: g++ -O2 -ffp-contract=off -shared -fPIC.
+#include <cstdint>
+#include <cstring>
+#include <vector>
+#include "../../fokl-gpy_b200/csrc/cand_math.cuh"
+
+using namespace fokl;
+
+extern "C" {
+
+// cubic factor values: out[i * n_ord + s] = phi_{orders[s]}(x[i]);  tab [n_orders][n_piece][4]
+int emu_basis_cubic(const double *x, int64_t n, const int32_t *orders, int n_ord, const double *tab, int n_piece,
+                    double *out)
+{
+    int bad = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        int ph;
+        double xs, x2, x3;
+        if (!phind_xsm(x[i], n_piece, ph, xs)) bad = 1;
+        square_cube(xs, x2, x3);
+        for (int s = 0; s < n_ord; ++s) {
+            const double *c = tab + ((size_t)(orders[s] - 1) * n_piece + ph) * 4;
+            out[i * n_ord + s] = cubic_basis(c[0], c[1], c[2], c[3], xs, x2, x3);
+        }
+    }
+    return bad;
+}
+
+int emu_phind(const double *x, int64_t n, int n_piece, int32_t *ph, double *xsm)
+{
+    int bad = 0;
+    for (int64_t i = 0; i < n; ++i)
+        if (!phind_xsm(x[i], n_piece, ph[i], xsm[i])) bad = 1;
+    return bad;
+}
+
+// bernoulli factor values; tab [n_orders][row_len]
+void emu_basis_bernoulli(const double *x, int64_t n, const int32_t *orders, int n_ord, const double *tab, int row_len,
+                         double *out)
+{
+    std::vector<double> pw(row_len + 2);
+    for (int64_t i = 0; i < n; ++i)
+        for (int s = 0; s < n_ord; ++s) {
+            int d = orders[s];
+            powers_dd(x[i], d, pw.data());
+            out[i * n_ord + s] = bernoulli_basis(tab + (size_t)(d - 1) * row_len, d + 1, pw.data());
+        }
+}
+
+struct emu_hypers {
+    double a, b, atau, btau, sigsqd0, tausqd0, yty, sum_y;
+    int64_t n;
+    int32_t draws, from0, from1, reserved;
+};
+
+// One candidate, same stages as cand_eig_kernel + cand_chain_kernel + cand_betas_kernel.
+// rng_mode 0: no chain; 1: injected variates [D][p+2]; 2: philox(seed, stream)
+int emu_candidate(const double *G, int64_t ldg, const double *Xty, const int32_t *idx, int p, const emu_hypers *h,
+                  int rng_mode, uint64_t seed, uint64_t stream, const double *variates, const double *sign_fix,
+                  double *ev, double *betahat, double *lamb, double *Q, double *betas, double *sigs, double *taus,
+                  int32_t *info)
+{
+    Team t;
+    t.tid = 0; t.nthr = 1; t.lane = 0; t.nlane = 1; t.warp = 0; t.nwarp = 1;
+    std::vector<double> W((size_t)p * p), V((size_t)p * p), lam_raw(p), ct(p), scratch(p), red(16);
+    std::vector<int> perm(p);
+    volatile int flag = 0;
+    for (int e = 0; e < p * p; ++e) {
+        int col = e / p, row = e - col * p;
+        W[e] = G[(int64_t)idx[row] * ldg + idx[col]];
+    }
+    const double tol = 2.220446049250313e-16 * (2.0 * sqrt((double)p) + 6.0);
+    int sweeps = jacobi_eigh(t, W.data(), V.data(), p, p, 40, tol, &flag);
+    eig_finish(t, W.data(), V.data(), p, p, lam_raw.data(), perm.data(), lamb, Q);
+    CandConst k;
+    k.a = h->a; k.b = h->b; k.atau = h->atau; k.btau = h->btau; k.sigsqd0 = h->sigsqd0; k.tausqd0 = h->tausqd0;
+    k.yty = h->yty; k.sum_y = h->sum_y; k.n = (double)h->n; k.draws = h->draws; k.from0 = h->from0; k.from1 = h->from1;
+    *ev = ols_and_bic(t, G, ldg, Xty, idx, p, lamb, Q, k, ct.data(), betahat, scratch.data(), red.data());
+    *info = sweeps << 8;
+    if (rng_mode == 0) return 0;
+    const int D = h->draws;
+    std::vector<double> gam((size_t)D * p), gg((size_t)2 * D);
+    ChainRng rng;
+    rng.mode = rng_mode; rng.variates = variates; rng.sign_fix = sign_fix;
+    rng.philox.k0 = (uint32_t)seed; rng.philox.k1 = (uint32_t)(seed >> 32);
+    rng.stream_lo = (uint32_t)stream; rng.stream_hi = (uint32_t)(stream >> 32) & 0x7fffffffu;
+    rng.gg = gg.data();
+    int bad = gibbs_chain(t, p, lamb, ct.data(), k, rng, gam.data(), sigs, taus, red.data());
+    if (bad) *info |= 1;
+    for (int d = 0; d < D; ++d)
+        for (int i = 0; i < p; ++i) {
+            double s = 0.0;
+            for (int r = 0; r < p; ++r) s += gam[(size_t)d * p + r] * Q[(size_t)r * p + i];
+            betas[(size_t)d * p + i] = s;
+        }
+    return 0;
+}
+
+void emu_philox_normals(uint64_t seed, uint64_t stream, int draws, int p, double *out)
+{
+    Philox g;
+    g.k0 = (uint32_t)seed; g.k1 = (uint32_t)(seed >> 32);
+    for (int d = 0; d < draws; ++d)
+        for (int e = 0; e < p; ++e)
+            out[(size_t)d * p + e] = philox_normal(g, (uint32_t)stream, (uint32_t)(stream >> 32) & 0x7fffffffu, d, e);
+}
+
+void emu_philox_gammas(uint64_t seed, uint64_t stream, int draws, double shape, double *out)
+{
+    Philox g;
+    g.k0 = (uint32_t)seed; g.k1 = (uint32_t)(seed >> 32);
+    for (int d = 0; d < draws; ++d)
+        out[d] = philox_gamma(g, (uint32_t)stream, (uint32_t)(stream >> 32) & 0x7fffffffu, d, 0u, shape);
+}
+
+}  // extern "C"

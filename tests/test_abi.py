@@ -1,0 +1,44 @@
+"""The C-ABI library loads and exports every symbol include/fokl_b200.h declares (no compute calls: no GPU here)."""
+import os
+import re
+
+from conftest import ROOT
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, 'include', 'fokl_b200.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(fokl_[a-z_0-9]+)\s*\(', text)))
+
+
+def test_header_declares_the_documented_entry_points():
+    syms = declared_symbols()
+    for must in ('fokl_ctx_create', 'fokl_basis_build', 'fokl_gram_update', 'fokl_candidates_eval', 'fokl_last_error'):
+        assert must in syms
+
+
+def test_library_exports_every_declared_symbol_and_binding_matches():
+    from FoKL import _lib
+    _lib.build_library()
+    lib = _lib.load()
+    syms = declared_symbols()
+    for s in syms:
+        assert hasattr(lib, s), s
+    assert sorted(_lib.PROTOTYPES) == syms
+    assert lib.fokl_abi_version() == _lib.ABI_VERSION
+
+
+def test_hypers_struct_layout_matches_header():
+    import ctypes
+    from FoKL import _lib
+    assert ctypes.sizeof(_lib.Hypers) == 8 * 8 + 8 + 4 * 4
+    assert _lib.Hypers.n.offset == 64 and _lib.Hypers.draws.offset == 72
+
+
+def test_product_code_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, 'fokl-gpy_b200')
+    for base, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh')):
+                src = open(os.path.join(base, f)).read()
+                assert 'fokl_oracle' not in src and 'import emu' not in src, f

@@ -1,0 +1,126 @@
+"""Host-side mirror of the reference API (no GPU needed): constructor kwargs, clean, term generation, save/load,
+and that the hot path fails loudly without a CUDA device."""
+import itertools
+import pickle
+
+import numpy as np
+import pytest
+
+import fokl_oracle as fo
+from FoKL import FoKLRoutines, _selection, getKernels
+
+
+def test_constructor_defaults_and_errors(phis_cubic):
+    m = FoKLRoutines.FoKL(phis=phis_cubic)
+    assert (m.a, m.atau, m.tolerance, m.burnin, m.draws) == (4, 4, 3, 1000, 1000)
+    assert m.kernel == 'Cubic Splines' and m.b is None and m.btau is None and m.relats_in == []
+    assert m.gimmie is False and m.way3 is False and m.aic is False and m.setnos is None
+    assert (m.threshav, m.threshstda, m.threshstdb) == (0.05, 0.5, 2)
+    with pytest.raises(ValueError):
+        FoKLRoutines.FoKL(phis=phis_cubic, nonsense=1)
+    m2 = FoKLRoutines.FoKL(kernel=1, way3='on', aic='yes', UserWarnings=False)
+    assert m2.kernel == 'Bernoulli Polynomials' and m2.way3 is True and m2.aic is True and len(m2.phis) == 20
+    assert [len(r) for r in m2.phis] == list(range(2, 22))
+    assert set(['kernel', 'phis', 'relats_in', 'a', 'b', 'atau', 'btau', 'tolerance', 'burnin', 'draws', 'gimmie',
+                'way3', 'threshav', 'threshstda', 'threshstdb', 'aic', 'update', 'built']) == set(m.hypers)
+
+
+def test_class_identity_for_pickles(phis_cubic, tmp_path):
+    assert FoKLRoutines.FoKL.__module__ == 'FoKL.FoKLRoutines'
+    m = FoKLRoutines.FoKL(kernel=1, UserWarnings=False)
+    m.betas = np.ones((3, 2))
+    path = m.save(str(tmp_path / 'model'))
+    assert path.endswith('.fokl')
+    again = FoKLRoutines.load(str(tmp_path / 'model'))
+    assert isinstance(again, FoKLRoutines.FoKL) and np.array_equal(again.betas, m.betas)
+    assert b'FoKL.FoKLRoutines' in pickle.dumps(m)
+
+
+def test_clean_normalises_like_the_oracle(phis_cubic):
+    rng = np.random.default_rng(0)
+    x = rng.normal(size=(50, 3)) * [1, 10, 100]
+    y = rng.normal(size=50)
+    m = FoKLRoutines.FoKL(phis=phis_cubic, UserWarnings=False)
+    xi, yi = m.clean(x, y)
+    ref, mm = fo.normalize(x)
+    assert np.array_equal(xi, ref) and yi.shape == (50, 1)
+    assert np.allclose(np.array(m.minmax), np.array(mm))
+    assert m.trainlog is None and m.trainset()[0] is m.inputs
+    # list-of-columns input is auto-transposed; explicit minmax is honoured
+    m3 = FoKLRoutines.FoKL(phis=phis_cubic, UserWarnings=False)
+    xi3 = m3.clean([x[:, 0], x[:, 1]], minmax=[[-5, 5], [-50, 50]])
+    assert xi3.shape == (50, 2) and np.allclose(xi3[:, 0], (x[:, 0] + 5) / 10)
+    with pytest.raises(ValueError):
+        m3.clean(x, y, bogus=True)
+    with pytest.raises(ValueError):
+        m3.clean(x, np.ones((50, 2)))
+
+
+def test_evaluate_basis_matches_oracle(phis_cubic, phis_bern):
+    m = FoKLRoutines.FoKL(phis=phis_cubic, UserWarnings=False)
+    c = [phis_cubic[3][k][17] for k in range(4)]
+    assert m.evaluate_basis(c, 0.3) == fo.eval_basis(c, 0.3, fo.CUBIC)
+    assert m.evaluate_basis(c, 0.3, d=1) == c[1] + 2 * c[2] * 0.3 + 3 * c[3] * 0.3 ** 2
+    assert m.evaluate_basis(phis_bern[4], 0.7, kernel=1) == fo.eval_basis(phis_bern[4], 0.7, fo.BERNOULLI)
+    with pytest.raises(ValueError):
+        m.evaluate_basis(c, 0.3, kernel='nope')
+
+
+def test_term_generation_matches_reference_semantics():
+    for v in ([1, 0, 0, 0], [2, 1, 1, 0, 0], [2, 2, 0, 0], [3, 1, 0, 0, 0, 0], [1, 1, 1, 0, 0, 0], [3, 2, 1, 0], [4]):
+        want = np.unique(np.vstack(list(itertools.permutations(np.array(v, dtype=float))))[::-1], axis=0)
+        got = _selection.distinct_permutations(v)
+        assert np.array_equal(got.astype(float), want)
+    assert _selection.distinct_permutations([3, 2, 1, 0, 0, 0, 0, 0]).shape == (336, 8)
+    assert _selection.distinct_permutations([1, 1, 1] + [0] * 13).shape == (560, 16)
+    for ind, m, way3 in ((4, 5, True), (5, 3, True), (3, 4, False), (6, 2, False), (3, 1, False)):
+        sett = 1 if m == 1 else (3 if way3 else 2)
+        v = _selection.first_partition(ind, m, sett)
+        w = fo.initial_indvec(ind, m, sett)
+        while True:
+            assert list(w) == v
+            a, b = _selection.next_partition(v, m, way3), fo.advance_indvec(w, m, way3)
+            assert a == b
+            if not a:
+                break
+
+
+def test_numpy_variates_consume_the_stream_like_the_oracle():
+    src = _selection.NumpyVariates(4, 4, 100, 30)
+    np.random.seed(3)
+    got = src.draw(5)
+    s1 = np.random.get_state()[1].copy()
+    np.random.seed(3)
+    z, g1, g2 = fo.draw_variates(5, 30, 4 + 1 + 50 + 2.5, 4 + 2)
+    assert np.array_equal(got[:, :5], z) and np.array_equal(got[:, 5], g1) and np.array_equal(got[:, 6], g2)
+    assert np.array_equal(s1, np.random.get_state()[1])
+
+
+def test_fit_fails_loudly_without_a_gpu(phis_cubic):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    m = FoKLRoutines.FoKL(phis=phis_cubic, UserWarnings=False, ConsoleOutput=False)
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        m.fit(np.random.rand(20, 2), np.random.rand(20), clean=True)
+
+
+def test_out_of_scope_entry_points_say_so(phis_cubic):
+    m = FoKLRoutines.FoKL(phis=phis_cubic, UserWarnings=False)
+    with pytest.raises(NotImplementedError):
+        m.bss_derivatives()
+    with pytest.raises(NotImplementedError):
+        m.fitupdate(None, None)
+    m.clear()
+    assert hasattr(m, 'phis') and not hasattr(m, 'setnos')
+
+
+def test_regenerated_spline_table_is_deterministic_and_continuous():
+    tab = getKernels.regenerate_spline_table(6)
+    assert tab.shape == (6, 499, 4)
+    # C0 continuity across pieces: value at t = 1 of piece i equals value at t = 0 of piece i + 1
+    end = tab[:, :-1, :].sum(axis=2)
+    start = tab[:, 1:, 0]
+    assert np.max(np.abs(end - start)) < 1e-12
+    gold = np.load(__import__('os').path.join(__import__('conftest').GOLD, 'phis_cubic_48.npy'))
+    assert np.allclose(tab, gold[:6], rtol=0, atol=1e-9)

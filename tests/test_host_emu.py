@@ -1,0 +1,99 @@
+"""The numerical core of the CUDA kernels (fokl_math.cuh, cand_math.cuh) compiled for the host with a
+single-thread team and checked against the oracle -- runs without a GPU."""
+import numpy as np
+import pytest
+
+import emu
+import fokl_oracle as fo
+from conftest import load_golden
+
+
+def test_cubic_basis_bit_exact(cubic_table, phis_cubic):
+    g = load_golden('basis_values')
+    out, bad = emu.basis_cubic(g['x'], np.arange(1, 49), cubic_table)
+    assert bad == 0 and np.array_equal(out, g['cubic'])
+    rng = np.random.default_rng(5)
+    x = rng.random(50000)
+    orders = np.array([1, 2, 3, 7, 20, 48])
+    out, _ = emu.basis_cubic(x, orders, cubic_table)
+    assert np.array_equal(out, fo.basis_columns(x[:, None], orders[:, None], phis_cubic, fo.CUBIC))
+
+
+def test_phind_edges():
+    x = np.array([0.0, -0.0, 1e-300, 1 / 499, 1.0, 0.999999999, 2 / 499 + 1e-18])
+    ph, xs, bad = emu.phind(x)
+    rph, rxs = fo.inputs_to_phind(x[:, None])
+    assert bad == 0 and np.array_equal(ph, rph[:, 0]) and np.array_equal(xs, rxs[:, 0])
+    for bad_x in (1.0001, -0.01, np.nan, 2.0):
+        assert emu.phind(np.array([bad_x]))[2] == 1
+
+
+def test_bernoulli_basis_tolerance(bern_table, phis_bern):
+    rng = np.random.default_rng(6)
+    x = rng.random(20000)
+    orders = np.array([1, 2, 3, 5, 8, 10])
+    out = emu.basis_bernoulli(x, orders, bern_table)
+    ref = fo.basis_columns(x[:, None], orders[:, None], phis_bern, fo.BERNOULLI)
+    scale = np.abs(ref).max(axis=0)
+    assert np.all(np.abs(out - ref).max(axis=0) <= 1e-9 * scale)
+    assert np.array_equal(out[:, 0], ref[:, 0])
+    assert np.mean(out == ref) > 0.98
+
+
+def _problem(phis, n, m, seed):
+    rng = np.random.default_rng(seed)
+    x = rng.random((n, m))
+    y = (np.sin(2 * np.pi * x[:, 0]) + x[:, 0] * x[:, 1] + 0.05 * rng.standard_normal(n))[:, None]
+    terms = np.vstack([fo.distinct_perms(p).astype(int) for p in
+                       ([1] + [0] * (m - 1), [1, 1] + [0] * (m - 2), [2] + [0] * (m - 1), [2, 1] + [0] * (m - 2))])
+    X = np.hstack([np.ones((n, 1)), fo.basis_columns(x, terms, phis, fo.CUBIC)])
+    return X, y
+
+
+@pytest.mark.parametrize('n,m,seed', [(441, 2, 1), (3000, 3, 2)])
+def test_candidate_math_matches_oracle(phis_cubic, n, m, seed):
+    X, y = _problem(phis_cubic, n, m, seed)
+    a = atau = 4
+    b, btau = fo.default_b_btau(y, a, atau)
+    D = 250
+    dtd = y.T.dot(y)
+    np.random.seed(seed)
+    r = fo.gibbs_from_X(X, y, a, b, atau, btau, D, b / (1 + a), btau / (1 + atau), dtd, literal=True)
+    p = X.shape[1]
+    np.random.seed(seed)
+    z, g1, g2 = fo.draw_variates(p, D, a + 1 + n / 2 + p / 2, atau + (p - 1) / 2)
+    var = np.hstack([z, g1[:, None], g2[:, None]])
+    hyp = dict(a=a, b=b, atau=atau, btau=btau, sigsqd0=b / (1 + a), tausqd0=btau / (1 + atau),
+               yty=float(dtd[0, 0]), sum_y=float(y.sum()), n=n, draws=D)
+    e0 = emu.candidate(r['XtX'], r['Xty'], np.arange(p), hyp, rng_mode=0)
+    sign = np.sign(np.sum(e0['Q'] * r['Q'], axis=0))
+    e = emu.candidate(r['XtX'], r['Xty'], np.arange(p), hyp, rng_mode=1, variates=var, sign_fix=sign)
+    assert (e['info'] >> 8) < 40
+    assert np.all(np.abs(e['lamb'] - r['Lamb']) <= 1e-12 * r['Lamb'][-1])
+    assert abs(e['ev'] - r['ev']) <= 1e-10 * abs(r['ev'])
+    assert np.max(np.abs(e['betahat'] - r['betahat'][:, 0])) <= 1e-8 * np.max(np.abs(r['betahat']))
+    assert np.max(np.abs(e['betas'] - r['betas'])) <= 1e-8 * np.max(np.abs(r['betas']))
+    assert np.allclose(e['sigs'], r['sigs'][:, 0], rtol=1e-9)
+    assert np.allclose(e['taus'], r['taus'][:, 0], rtol=1e-8)
+    # a sub-model addressed through an index list into the same master Gram
+    idx = np.array([0, 2, 3, 5])
+    es = emu.candidate(r['XtX'], r['Xty'], idx, hyp, rng_mode=0)
+    rs = fo.gibbs_from_X(X[:, idx], y, a, b, atau, btau, 1, 1.0, 1.0, dtd, literal=False,
+                         variates=(np.zeros((1, 4)), np.ones(1), np.ones(1)))
+    assert abs(es['ev'] - rs['ev']) <= 1e-10 * abs(rs['ev'])
+
+
+def test_philox_streams_are_standard():
+    import ctypes
+    L = emu.lib()
+    out = np.zeros((4000, 8))
+    L.emu_philox_normals(123, 7, 4000, 8, out.ctypes.data)
+    assert abs(out.mean()) < 0.02 and abs(out.std() - 1) < 0.02
+    out2 = np.zeros((4000, 8))
+    L.emu_philox_normals(123, 8, 4000, 8, out2.ctypes.data)
+    assert not np.array_equal(out, out2)
+    for shape in (0.5, 1.0, 3.5, 5000.5):
+        g = np.zeros(20000)
+        L.emu_philox_gammas(99, 3, 20000, ctypes.c_double(shape), g.ctypes.data)
+        assert abs(g.mean() - shape) < 5 * np.sqrt(shape / 20000) + 1e-12
+        assert abs(g.var() - shape) < 0.1 * shape

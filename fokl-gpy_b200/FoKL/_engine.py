@@ -104,6 +104,7 @@ class Engine:
         self.n_global = 0
         self.sum_y = self.yty = 0.0
         self.gibbs_launch_batches = 0
+        self.profile = None      # set to {} to collect CUDA-event timings per stage (bench.py)
 
     # ------------------------------------------------------------------------------------------------
     def close(self):
@@ -134,6 +135,35 @@ class Engine:
     def _allreduce(self, t):
         if self.dist is not None:
             self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+
+    # ---- optional per-stage timing with CUDA events on the launching stream ------------------------
+    def _tic(self):
+        if self.profile is None:
+            return None
+        e = self.torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    def _toc(self, start, name, **extra):
+        if start is None:
+            return
+        e = self.torch.cuda.Event(enable_timing=True)
+        e.record()
+        self.profile.setdefault('_events', []).append((name, start, e, extra))
+
+    def profile_summary(self):
+        """Resolve recorded events: {stage: dict(ms=total, launches=count, **summed extras)}."""
+        out = {}
+        if not self.profile:
+            return out
+        self.torch.cuda.synchronize(self.device)
+        for name, a, b, extra in self.profile.get('_events', []):
+            d = out.setdefault(name, dict(ms=0.0, calls=0))
+            d['ms'] += a.elapsed_time(b)
+            d['calls'] += 1
+            for k, v in extra.items():
+                d[k] = d.get(k, 0) + v
+        return out
 
     # ------------------------------------------------------------------------------------------------
     def set_phis(self, phis, kernel):
@@ -237,10 +267,15 @@ class Engine:
         need = (p_old + c + 1) * c
         if self.block is None or self.block.numel() < need:
             self.block = torch.empty((int(need * 1.5) + 64,), dtype=torch.float64, device=self.device)
+        t = self._tic()
         self._ck(self.lib.fokl_gram_update(self.ctx, self.X.data_ptr(), self.ld, self.ds.n, p_old, c,
                                            self.ds.y.data_ptr(), self.block.data_ptr()))
+        self._toc(t, 'gram', flops=2.0 * self.ds.n * (p_old + c + 1) * c, bytes=8.0 * self.ds.n * (p_old + c + 1),
+                  cols=p_old + c + 1)
         if self.dist is not None:
+            t = self._tic()
             self._allreduce(self.block[:need])
+            self._toc(t, 'allreduce', bytes=8.0 * need)
         self._ck(self.lib.fokl_gram_scatter(self.ctx, self.block.data_ptr(), p_old, c, self.G.data_ptr(), self.Gcap,
                                             self.Xty.data_ptr()))
         self.P = p_old + c
@@ -254,8 +289,10 @@ class Engine:
         if c == 0:
             return
         self._ensure_columns(self.P + c)
+        t = self._tic()
         self._ck(self.lib.fokl_basis_build(self.ctx, self.kernel_id, self.ds.x.data_ptr(), self.ds.n, self.ds.ldx, m,
                                            terms.ctypes.data, c, self.X[self.P].data_ptr(), self.ld))
+        self._toc(t, 'basis', bytes=8.0 * self.ds.n * (m + c), cells=float(self.ds.n) * c)
         self._append_built(c)
 
     def compact(self, keep):
@@ -264,7 +301,9 @@ class Engine:
         p_new = len(keep)
         if p_new == self.P:
             return
+        t = self._tic()
         self._ck(self.lib.fokl_columns_compact(self.ctx, self.X.data_ptr(), self.ld, self.ds.n, keep.ctypes.data, p_new))
+        self._toc(t, 'compact')
         self._ck(self.lib.fokl_gram_compact(self.ctx, self.G.data_ptr(), self.Gcap, self.Xty.data_ptr(),
                                             keep.ctypes.data, p_new, self.G2.data_ptr(), self.Gcap, self.Xty2.data_ptr()))
         self.G, self.G2 = self.G2, self.G
@@ -328,11 +367,13 @@ class Engine:
         def ptr(t):
             return None if t is None else t.data_ptr()
 
+        t = self._tic()
         self._ck(self.lib.fokl_candidates_eval(
             self.ctx, self.G.data_ptr(), self.Gcap, self.Xty.data_ptr(), flat.ctypes.data, offs.ctypes.data, n_cand,
             ctypes.byref(hyp), None if rc_arr is None else rc_arr.ctypes.data, rng_mode, ctypes.c_uint64(int(seed)),
             None if sid is None else sid.ctypes.data, ptr(var_t), ptr(sf_t), ptr(ev), ptr(betahat), ptr(lamb), ptr(Q),
             ptr(betas), ptr(sigs), ptr(taus), ptr(stats), ptr(info)))
+        self._toc(t, 'candidates_chain' if chain_any else 'candidates_bic', cands=n_cand, pmax=int(p.max()))
         self.gibbs_launch_batches += 1
         res = CandidateResult()
         res.p, res.vec_off, res.mat_off, res.draws = p, vec_off, mat_off, D

@@ -102,8 +102,12 @@ class PhiloxVariates:
     still makes a fit reproducible), one stream per `gibbs` call index."""
     mode = _lib.RNG_PHILOX
 
-    def __init__(self):
+    def __init__(self, engine=None):
         self.seed = int(np.random.randint(0, 2 ** 31 - 1)) * (2 ** 31) + int(np.random.randint(0, 2 ** 31 - 1))
+        if engine is not None and engine.dist is not None:      # every rank must walk the same chain
+            t = engine.torch.tensor([self.seed], dtype=engine.torch.int64, device=engine.device)
+            engine.dist.broadcast(t, src=0, group=engine.group)
+            self.seed = int(t.item())
 
 
 def forward_select(engine, hy, m, n_phis, console=True, rng='philox', eager=False, on_substage=None,
@@ -122,7 +126,7 @@ def forward_select(engine, hy, m, n_phis, console=True, rng='philox', eager=Fals
         src = NumpyVariates(a, atau, n, D)
         seed = 0
     else:
-        src = PhiloxVariates()
+        src = PhiloxVariates(engine)
         seed = src.seed
     mode = src.mode
     sett = 1 if m == 1 else (3 if hy['way3'] else 2)

@@ -44,15 +44,10 @@ extern "C" int fokl_ctx_create(fokl_ctx **out, int device, void *cuda_stream)
     fokl_ctx *ctx = new fokl_ctx();
     ctx->device = device;
     if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return FOKL_ECUDA; }
-    if (cuda_stream) {
-        ctx->stream = (cudaStream_t)cuda_stream;
-    } else {
-        if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
-            delete ctx;
-            return FOKL_ECUDA;
-        }
-        ctx->own_stream = true;
-    }
+    // NULL is the CUDA legacy default stream -- the stream PyTorch enqueues on unless told otherwise, so
+    // device buffers produced by torch and kernels launched here stay ordered without extra events.
+    ctx->stream = (cudaStream_t)cuda_stream;
+    ctx->own_stream = false;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) {
         ctx->num_sms = prop.multiProcessorCount;

@@ -10,8 +10,8 @@
  *     across the ABI; fokl_last_error(ctx) returns a human-readable message for the last failure.
  *   - pointers documented "dev" are device pointers owned by the caller (e.g. torch tensors'
  *     data_ptr()); pointers documented "host" are plain host memory, read before the call returns.
- *   - work is enqueued on the ctx stream and is asynchronous unless stated; one ctx per
- *     (process, device); a ctx is not thread-safe.
+ *   - work is enqueued on the ctx stream (given at creation) and is asynchronous unless stated; one ctx
+ *     per (process, device, stream); a ctx is not thread-safe.
  *   - all floating point is IEEE float64; matrices are column-major unless stated.
  */
 #ifndef FOKL_B200_H
@@ -45,7 +45,8 @@ typedef struct fokl_ctx fokl_ctx;
 
 int fokl_abi_version(void);
 
-/* device: CUDA ordinal.  cuda_stream: a cudaStream_t to enqueue on, or NULL for a ctx-owned stream. */
+/* device: CUDA ordinal.  cuda_stream: the cudaStream_t all work is enqueued on; NULL is the CUDA legacy
+ * default stream (PyTorch's default), never a private stream. */
 int fokl_ctx_create(fokl_ctx **out, int device, void *cuda_stream);
 int fokl_ctx_destroy(fokl_ctx *ctx);
 const char *fokl_last_error(fokl_ctx *ctx);

@@ -1,0 +1,54 @@
+"""Exploration script (not part of the product): run one fit of a synthetic config with per-stage timing."""
+import argparse
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, 'fokl-gpy_b200'))
+sys.path.insert(0, ROOT)
+import bench_data  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--cfg', default='cfg4')
+    ap.add_argument('--n', type=int, default=0)
+    ap.add_argument('--eager', type=int, default=0)
+    ap.add_argument('--draws', type=int, default=1000)
+    a = ap.parse_args()
+    import torch
+    from FoKL import FoKLRoutines as FR
+    cfg = bench_data.CONFIGS[a.cfg]
+    n = a.n or cfg['n']
+    t0 = time.time()
+    x, y = bench_data.make_rows(a.cfg, 0, n, n_total=n)
+    print('data', x.shape, time.time() - t0, flush=True)
+    model = bench_data.make_model(FR, a.cfg, draws=a.draws)
+    FR.B200_CONFIG['eager_chains'] = bool(a.eager)
+    eng = FR._engine()
+    eng.profile = {}
+    np.random.seed(cfg['seed'])
+    subs = []
+    from FoKL import _selection
+    orig = _selection.forward_select
+
+    def patched(*args, **kw):
+        kw['on_substage'] = lambda ind, ev, terms: subs.append((ind, ev, terms.shape[0], time.time() - t1))
+        return orig(*args, **kw)
+    _selection.forward_select = patched
+    t1 = time.time()
+    betas, mtx, evs = model.fit(x, y, clean=True)
+    torch.cuda.synchronize()
+    print('fit wall', time.time() - t1, FR.LAST_FIT_INFO, flush=True)
+    for s in subs:
+        print(s)
+    for k, v in eng.profile_summary().items():
+        print(k, v)
+    print('terms', mtx.shape, 'evs', len(evs))
+
+
+if __name__ == '__main__':
+    main()

@@ -392,6 +392,24 @@ class Engine:
                 res.ev[c] = self.residual_bic(col_sets[c], betahat[vec_off[c]:vec_off[c] + p[c]])
         return res
 
+    def kill_scores(self, cols, positions, hyp):
+        """BIC of the model `cols` minus each column at `positions` (indices into cols), plus the model's own BIC,
+        from one Cholesky factorisation on the device.  Returns (ev numpy [k + 1], ok)."""
+        torch = self.torch
+        cols = np.ascontiguousarray(cols, dtype=np.int32)
+        positions = np.ascontiguousarray(positions, dtype=np.int32)
+        k = len(positions)
+        ev = torch.empty(k + 1, dtype=torch.float64, device=self.device)
+        info = torch.zeros(1, dtype=torch.int32, device=self.device)
+        t = self._tic()
+        self._ck(self.lib.fokl_kill_scores(self.ctx, self.G.data_ptr(), self.Gcap, self.Xty.data_ptr(), cols.ctypes.data,
+                                           len(cols), positions.ctypes.data if k else None, k, ctypes.byref(hyp),
+                                           ev.data_ptr(), info.data_ptr()))
+        self._toc(t, 'kill_scores', cands=k, pmax=len(cols))
+        evh = ev.cpu().numpy()
+        ok = int(info.item()) == 0 and bool(np.all(np.isfinite(evh)))
+        return evh, ok
+
     def residual_bic(self, cols, betahat_dev):
         """BIC of FR:1551-1554 from an explicit N-length residual pass over X (used when the Gram-only
         formula has lost too many digits to cancellation)."""

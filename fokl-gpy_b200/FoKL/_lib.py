@@ -50,6 +50,7 @@ PROTOTYPES = {
     'fokl_columns_compact': (_i32, [_vp, _vp, _i64, _i64, _vp, _i32]),
     'fokl_candidates_eval': (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _i32, ctypes.POINTER(Hypers), _vp, _i32, _u64,
                                     _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'fokl_kill_scores': (_i32, [_vp, _vp, _i64, _vp, _vp, _i32, _vp, _i32, ctypes.POINTER(Hypers), _vp, _vp]),
     'fokl_residual_moments': (_i32, [_vp, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp]),
     'fokl_predict_draws': (_i32, [_vp, _vp, _i64, _i64, _i32, _vp, _i32, _vp]),
     'fokl_column_minmax': (_i32, [_vp, _vp, _i64, _i64, _i32, _vp]),

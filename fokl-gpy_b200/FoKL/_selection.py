@@ -205,58 +205,140 @@ def forward_select(engine, hy, m, n_phis, console=True, rng='philox', eager=Fals
             bv0, bv1, cand_cols = bv0[order], bv1[order], new_cols[order]
             icpt = abs(float(st[2, 0]))                                # |mean(beters[h0:, 0])| (FR:1671)
 
-            # ---- kill proposals (FR:1666-1692), batched --------------------------------------------------------
+            # ---- kill proposals (FR:1666-1692) -------------------------------------------------------------------
             killed = []            # column indices (into current X) accepted for removal
             evmin = ev
             cur = 0
-            while cur < vm:
-                thr = hy['threshav'] * icpt
-                props = [i for i in range(cur, vm)
-                         if (bv1[i] > hy['threshstdb']) or (bv1[i] > hy['threshstda'] and bv0[i] < thr)]
-                if not props:
-                    break
-                sets, chains, ids = [], [], []
-                base = call_id[0]
-                for r, i in enumerate(props):
-                    drop = set(killed) | {int(cand_cols[i])}
-                    sets.append([c for c in full if c not in drop])
-                    ids.append(base + r + 1)
-                if mode == _lib.RNG_INJECTED:
-                    # stream parity: variates are consumed test by test, so run sequentially until one is accepted
+
+            def proposals(start, icpt_now):
+                thr = hy['threshav'] * icpt_now
+                return [i for i in range(start, vm)
+                        if (bv1[i] > hy['threshstdb']) or (bv1[i] > hy['threshstda'] and bv0[i] < thr)]
+
+            if mode == _lib.RNG_INJECTED or eager:
+                # literal order: one `gibbs`-equivalent evaluation (eig + chain) per proposal.  In parity mode the
+                # numpy stream is consumed test by test; in eager mode all proposals of a batch run side by side.
+                while cur < vm:
+                    props = proposals(cur, icpt)
+                    if not props:
+                        break
+                    sets = []
+                    for i in props:
+                        drop = set(killed) | {int(cand_cols[i])}
+                        sets.append([c for c in full if c not in drop])
+                    ids = [call_id[0] + r + 1 for r in range(len(props))]
                     accepted = None
-                    for r, i in enumerate(props):
-                        call_id[0] += 1
-                        n_gibbs += 1
-                        v = src.draw(len(sets[r]))
-                        rr = run([sets[r]], [v], [ids[r]])
-                        evt = float(rr.ev[0]) + aic_adj * len(sets[r])
-                        if evt < evmin:
-                            accepted = (i, evt, rr, 0)
+                    if mode == _lib.RNG_INJECTED:
+                        for r, i in enumerate(props):
+                            call_id[0] += 1
+                            n_gibbs += 1
+                            rr = run([sets[r]], [src.draw(len(sets[r]))], [ids[r]])
+                            evt = float(rr.ev[0]) + aic_adj * len(sets[r])
+                            if evt < evmin:
+                                accepted = (i, evt, rr, 0)
+                                break
+                    else:
+                        rr = run(sets, [True] * len(sets), ids)
+                        for r, i in enumerate(props):
+                            evt = float(rr.ev[r]) + aic_adj * len(sets[r])
+                            if evt < evmin:
+                                accepted = (i, evt, rr, r)
+                                break
+                        tested = (props.index(accepted[0]) + 1) if accepted else len(props)
+                        call_id[0] += tested
+                        n_gibbs += tested
+                    if accepted is None:
+                        break
+                    i, evt, rr, slot = accepted
+                    killed.append(int(cand_cols[i]))
+                    evmin = evt
+                    cur_betas = rr.betas_of(slot).clone()
+                    icpt = abs(float(rr.stats_of(slot)[2, 0].item()))
+                    cur = i + 1
+            else:
+                # fast path: every proposal of a round is scored from ONE Cholesky factorisation of the current
+                # model (fokl_kill_scores); the chains of the accepted models -- which only feed the next round's
+                # threshold through |mean intercept| (FR:1671) and the final draws (FR:1690) -- are run afterwards as
+                # one batch and every round's proposal list is re-checked against them (rolled back on a mismatch),
+                # so the outcome is exactly that of the sequential loop.
+                state = dict(killed=[], evmin=evmin, cur=0, icpt=icpt, calls=call_id[0], gibbs=n_gibbs)
+                rounds = []        # per accepted kill: dict(before=state copy, props, i, model cols, stream id, icpt_used)
+                while True:
+                    while state['cur'] < vm:
+                        props = proposals(state['cur'], state['icpt'])
+                        if not props:
                             break
-                else:
-                    rr = run(sets, [bool(eager)] * len(sets), ids)
-                    accepted = None
-                    for r, i in enumerate(props):
-                        evt = float(rr.ev[r]) + aic_adj * len(sets[r])
-                        if evt < evmin:
-                            accepted = (i, evt, rr, r)
+                        model = [c for c in full if c not in set(state['killed'])]
+                        pos = [model.index(int(cand_cols[i])) for i in props]
+                        scores, ok = engine.kill_scores(model, pos, hyp)
+                        n_batches += 1
+                        if not ok:
+                            # Gram not numerically positive definite: score the proposals through the spectral path
+                            sets_ = [[c for c in model if c != int(cand_cols[i])] for i in props]
+                            scores = run(sets_, [False] * len(sets_), [0] * len(sets_)).ev
+                        hit = None
+                        for r, i in enumerate(props):
+                            evt = float(scores[r]) + aic_adj * (len(model) - 1)
+                            if evt < state['evmin']:
+                                hit = (r, i, evt)
+                                break
+                        if hit is None:
+                            state['calls'] += len(props)
+                            state['gibbs'] += len(props)
                             break
-                    tested = (props.index(accepted[0]) + 1) if accepted else len(props)
-                    call_id[0] += tested
-                    n_gibbs += tested
-                    if accepted and not eager:
-                        # the accepted model's draws are needed (FR:1690): run its chain with its own stream id
-                        i, evt, _, r = accepted
-                        rr1 = run([sets[r]], [True], [ids[r]])
-                        accepted = (i, evt, rr1, 0)
-                if accepted is None:
-                    break
-                i, evt, rr, slot = accepted
-                killed.append(int(cand_cols[i]))
-                evmin = evt
-                cur_betas = rr.betas_of(slot).clone()
-                icpt = abs(float(rr.stats_of(slot)[2, 0].item()))
-                cur = i + 1
+                        r, i, evt = hit
+                        before = dict(state, killed=list(state['killed']))
+                        state['calls'] += r + 1
+                        state['gibbs'] += r + 1
+                        state['killed'] = state['killed'] + [int(cand_cols[i])]
+                        state['evmin'] = evt
+                        state['cur'] = i + 1
+                        rounds.append(dict(before=before, props=props, i=i, stream=state['calls'],
+                                           cols=[c for c in model if c != int(cand_cols[i])], icpt_used=state['icpt']))
+                    if not rounds:
+                        break
+                    # chains of all accepted models in one batch; verify the thresholds each later round used
+                    todo = [rd for rd in rounds if 'icpt_true' not in rd]
+                    if todo:
+                        rr = run([rd['cols'] for rd in todo], [True] * len(todo), [rd['stream'] for rd in todo])
+                        for slot, rd in enumerate(todo):
+                            rd['icpt_true'] = abs(float(rr.stats_of(slot)[2, 0].item()))
+                            rd['ev_true'] = float(rr.ev[slot]) + aic_adj * len(rd['cols'])
+                            rd['betas'] = rr.betas_of(slot).clone() if rd is rounds[-1] else None
+                            rd['rr'], rd['slot'] = rr, slot
+                    redo = None
+                    for k_, rd in enumerate(rounds):
+                        nxt_start = rd['i'] + 1
+                        used = rounds[k_ + 1]['props'] if k_ + 1 < len(rounds) else proposals(nxt_start, rd['icpt_used'])
+                        if proposals(nxt_start, rd['icpt_true']) != used:
+                            redo = k_
+                            break
+                    if redo is None:
+                        last_rd = rounds[-1]
+                        if last_rd['betas'] is None:
+                            last_rd['betas'] = last_rd['rr'].betas_of(last_rd['slot']).clone()
+                        cur_betas = last_rd['betas']
+                        icpt = last_rd['icpt_true']
+                        evmin = last_rd['ev_true']        # report the spectral-path BIC of the accepted model
+                        killed = list(state['killed'])
+                        for rd in rounds:
+                            rd.pop('rr', None)
+                        break
+                    # roll back to just after round `redo`, now with its true threshold, and continue from there
+                    rd = rounds[redo]
+                    rounds = rounds[:redo + 1]
+                    st_after = dict(rd['before'], killed=rd['before']['killed'] + [int(cand_cols[rd['i']])])
+                    st_after['calls'] = rd['stream']
+                    st_after['gibbs'] = rd['before']['gibbs'] + (rd['props'].index(rd['i']) + 1)
+                    st_after['evmin'] = rd['ev_true']
+                    st_after['cur'] = rd['i'] + 1
+                    st_after['icpt'] = rd['icpt_true']
+                    rd['icpt_used'] = rd['icpt_true']
+                    state = st_after
+                call_id[0] = state['calls']
+                n_gibbs = state['gibbs']
+                if not rounds:
+                    killed = []
 
             # ---- drop accepted kills (FR:1691-1695) ---------------------------------------------------------------
             if killed:

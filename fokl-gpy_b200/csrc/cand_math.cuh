@@ -284,3 +284,111 @@ FOKL_HD int gibbs_chain(const Team &t, int p, const double *lamb, const double *
 }
 
 }  // namespace fokl
+
+// ---- kill-proposal scores without refactorising each candidate ------------------------------------------
+// For the model with Gram A = G[idx][idx] (p x p, intercept first) the OLS fit of the model that drops column q
+// has  SSE_{-q} = SSE + betahat_q^2 / (A^-1)_qq.  One Cholesky factorisation of A therefore yields the BIC
+// (FR:1551-1554) of *every* single-column deletion the kill loop proposes (FR:1673-1685), instead of one
+// eigendecomposition per proposal.  y is centred on its mean for accuracy (column 0 is the ones column, so the
+// residual mean is zero and siglik = SSE / n).
+//   L: p x p workspace, column-major (ld = p); z, beta: p scratch; wbuf: nwarp * p scratch
+//   props: positions (within idx, never 0) of the proposals, k of them
+//   ev_out[0..k-1] = BIC of the model without props[j];  ev_out[k] = BIC of the model itself
+// Returns 0, or 1 if A is not numerically positive definite (caller falls back to the spectral path).
+namespace fokl {
+
+FOKL_HD void warp_sync(const Team &)
+{
+#if defined(__CUDA_ARCH__)
+    __syncwarp();
+#endif
+}
+
+FOKL_HD int kill_scores(const Team &t, const double *G, int64_t ldg, const double *Xty, const int *idx, int p,
+                        const int *props, int k, const CandConst &c, double *L, double *z, double *beta,
+                        double *wbuf, double *ev_out, volatile int *flag, double *red)
+{
+    for (int e = t.tid; e < p * p; e += t.nthr) {
+        int col = e / p, row = e - col * p;
+        L[e] = (row >= col) ? G[(int64_t)idx[row] * ldg + idx[col]] : 0.0;
+    }
+    if (t.tid == 0) *flag = 0;
+    t.sync();
+    // right-looking Cholesky; column j holds L[i][j], i >= j, at L[j*p + i]
+    for (int j = 0; j < p; ++j) {
+        const double d = L[(int64_t)j * p + j];
+        if (!(d > 0.0)) {
+            if (t.tid == 0) *flag = 1;
+            break;
+        }
+        const double r = sqrt(d);
+        t.sync();
+        for (int i = j + t.tid; i < p; i += t.nthr) L[(int64_t)j * p + i] = (i == j) ? r : L[(int64_t)j * p + i] / r;
+        t.sync();
+        const int rem = p - j - 1;
+        for (int64_t e = t.tid; e < (int64_t)rem * rem; e += t.nthr) {
+            int mc = (int)(e / rem), mr = (int)(e - (int64_t)mc * rem);
+            if (mr < mc) continue;
+            int m = j + 1 + mc, i = j + 1 + mr;
+            L[(int64_t)m * p + i] -= L[(int64_t)j * p + i] * L[(int64_t)j * p + m];
+        }
+        t.sync();
+    }
+    t.sync();
+    if (*flag) return 1;
+    const double ybar = c.sum_y / c.n;
+    const int64_t row0 = (int64_t)idx[0] * ldg;
+    // forward solve L z = X'y_c
+    for (int i = t.tid; i < p; i += t.nthr) z[i] = Xty[idx[i]] - ybar * G[row0 + idx[i]];
+    t.sync();
+    for (int j = 0; j < p; ++j) {
+        const double zj = z[j] / L[(int64_t)j * p + j];
+        t.sync();
+        if (t.tid == 0) z[j] = zj;
+        for (int i = j + 1 + t.tid; i < p; i += t.nthr) z[i] -= L[(int64_t)j * p + i] * zj;
+        t.sync();
+    }
+    double s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    for (int i = t.tid; i < p; i += t.nthr) s1 += z[i] * z[i];
+    team_sum3(t, s1, s2, s3, red, 0);
+    t.sync();
+    const double sse = (c.yty - c.n * ybar * ybar) - s1;
+    // back solve L' beta = z
+    for (int i = t.tid; i < p; i += t.nthr) beta[i] = z[i];
+    t.sync();
+    for (int j = p - 1; j >= 0; --j) {
+        const double bj = beta[j] / L[(int64_t)j * p + j];
+        t.sync();
+        if (t.tid == 0) beta[j] = bj;
+        for (int i = t.tid; i < j; i += t.nthr) beta[i] -= L[(int64_t)i * p + j] * bj;
+        t.sync();
+    }
+    // (A^-1)_qq = |L^-1 e_q|^2, one warp per proposal
+    const double ln_n = log(c.n);
+    for (int a = t.warp; a < k; a += t.nwarp) {
+        const int q = props[a];
+        double *w = wbuf + (int64_t)t.warp * p;
+        for (int i = q + t.lane; i < p; i += t.nlane) w[i] = (i == q) ? 1.0 : 0.0;
+        warp_sync(t);
+        double acc = 0.0;
+        for (int j = q; j < p; ++j) {
+            const double wj = w[j] / L[(int64_t)j * p + j];
+            acc += wj * wj;
+            warp_sync(t);
+            for (int i = j + 1 + t.lane; i < p; i += t.nlane) w[i] -= L[(int64_t)j * p + i] * wj;
+            warp_sync(t);
+        }
+        if (t.lane == 0) {
+            const double sig = (sse + beta[q] * beta[q] / acc) / c.n;
+            ev_out[a] = (double)(p - 1) * ln_n - 2.0 * (-(c.n / 2.0) * log(sig) - (c.n - 1.0) / 2.0);
+        }
+    }
+    if (t.tid == 0) {
+        const double sig = sse / c.n;
+        ev_out[k] = (double)p * ln_n - 2.0 * (-(c.n / 2.0) * log(sig) - (c.n - 1.0) / 2.0);
+    }
+    t.sync();
+    return 0;
+}
+
+}  // namespace fokl

@@ -227,6 +227,32 @@ __global__ void cand_stats_kernel(const StatsParams P)
     S[2 * p + i] = m0;
 }
 
+struct KillParams {
+    const double *G;
+    int64_t ldg;
+    const double *Xty;
+    const int32_t *cols, *props;
+    int p, k;
+    CandConst c;
+    double *L_global, *z, *beta, *wbuf, *ev;
+    int32_t *info;
+    int smem_doubles;
+};
+
+constexpr int kKillThreads = 1024;
+
+__global__ void __launch_bounds__(kKillThreads) kill_scores_kernel(const KillParams P)
+{
+    extern __shared__ __align__(16) double sh[];
+    const Team t = make_team();
+    double *red = sh;
+    volatile int *flag = reinterpret_cast<volatile int *>(sh + 2 * 3 * (kKillThreads / 32));
+    double *L = ((int64_t)P.p * P.p <= P.smem_doubles) ? (sh + 2 * 3 * (kKillThreads / 32) + 2) : P.L_global;
+    int bad = fokl::kill_scores(t, P.G, P.ldg, P.Xty, P.cols, P.p, P.props, P.k, P.c, L, P.z, P.beta, P.wbuf, P.ev,
+                                flag, red);
+    if (t.tid == 0) P.info[0] = bad;
+}
+
 template <typename T>
 T *carve(char *&cur, size_t count)
 {
@@ -386,5 +412,52 @@ extern "C" int fokl_candidates_eval(fokl_ctx *ctx, const double *G, int64_t ldg,
         cand_stats_kernel<<<grid, 128, 0, ctx->stream>>>(P);
         FOKL_LAUNCH_CHECK(ctx);
     }
+    return FOKL_OK;
+}
+
+extern "C" int fokl_kill_scores(fokl_ctx *ctx, const double *G, int64_t ldg, const double *Xty, const int32_t *cols,
+                                int p, const int32_t *props, int k, const fokl_hypers *hyp, double *ev, int32_t *info)
+{
+    FOKL_CHECK_CTX(ctx);
+    if (!G || !Xty || !cols || !hyp || !ev || !info || p < 1 || k < 0 || ldg < p || (k > 0 && !props))
+        FOKL_FAIL(ctx, FOKL_EINVAL, "kill_scores: bad argument");
+    for (int a = 0; a < k; ++a)
+        if (props[a] < 1 || props[a] >= p) FOKL_FAIL(ctx, FOKL_EINVAL, "kill_scores: proposal position out of range");
+    int rc = fokl_bind_device(ctx);
+    if (rc) return rc;
+    const size_t smem_cap = ctx->smem_optin ? ctx->smem_optin : 48 * 1024;
+    const int header = 2 * 3 * (kKillThreads / 32) + 2;
+    const int smem_l_cap = (int)(smem_cap / sizeof(double)) - header;
+    const bool in_smem = (int64_t)p * p <= smem_l_cap;
+
+    size_t meta_bytes = 64 + (size_t)(p + k + 1) * sizeof(int32_t);
+    char *dmeta = (char *)fokl_scratch(ctx, fokl_ctx::B_META, meta_bytes);
+    if (!dmeta) return FOKL_ENOMEM;
+    std::vector<int32_t> h((size_t)p + k + 1);
+    memcpy(h.data(), cols, (size_t)p * sizeof(int32_t));
+    if (k) memcpy(h.data() + p, props, (size_t)k * sizeof(int32_t));
+    FOKL_CUDA(ctx, cudaMemcpyAsync(dmeta, h.data(), (size_t)(p + k) * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+
+    size_t ws = 256 + ((size_t)(in_smem ? 0 : (size_t)p * p) + 2 * (size_t)p + (size_t)(kKillThreads / 32) * p) * sizeof(double);
+    char *wcur = (char *)fokl_scratch(ctx, fokl_ctx::B_CAND_A, ws);
+    if (!wcur) return FOKL_ENOMEM;
+    KillParams P;
+    P.G = G; P.ldg = ldg; P.Xty = Xty;
+    P.cols = reinterpret_cast<const int32_t *>(dmeta);
+    P.props = P.cols + p;
+    P.p = p; P.k = k;
+    P.c.a = hyp->a; P.c.b = hyp->b; P.c.atau = hyp->atau; P.c.btau = hyp->btau;
+    P.c.sigsqd0 = hyp->sigsqd0; P.c.tausqd0 = hyp->tausqd0; P.c.yty = hyp->yty; P.c.sum_y = hyp->sum_y;
+    P.c.n = (double)hyp->n; P.c.draws = hyp->draws; P.c.from0 = hyp->stat_from0; P.c.from1 = hyp->stat_from1;
+    P.z = carve<double>(wcur, p);
+    P.beta = carve<double>(wcur, p);
+    P.wbuf = carve<double>(wcur, (size_t)(kKillThreads / 32) * p);
+    P.L_global = in_smem ? nullptr : carve<double>(wcur, (size_t)p * p);
+    P.ev = ev; P.info = info;
+    P.smem_doubles = in_smem ? p * p : 0;
+    size_t smem = (size_t)(header + (in_smem ? p * p : 0)) * sizeof(double);
+    FOKL_CUDA(ctx, cudaFuncSetAttribute(kill_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
+    kill_scores_kernel<<<1, kKillThreads, smem, ctx->stream>>>(P);
+    FOKL_LAUNCH_CHECK(ctx);
     return FOKL_OK;
 }

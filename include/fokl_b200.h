@@ -134,6 +134,15 @@ int fokl_candidates_eval(fokl_ctx *ctx, const double *G, int64_t ldg, const doub
                          double *ev, double *betahat, double *lamb, double *Q, double *betas,
                          double *sigs, double *taus, double *stats, int32_t *info);
 
+/* BIC of every single-column deletion of one model, from ONE Cholesky factorisation of its Gram
+ * (SSE_{-q} = SSE + betahat_q^2 / (A^-1)_qq): what the kill loop FR:1669-1690 asks of `gibbs` for all its
+ * proposals at once.  cols (host, p entries, cols[0] = intercept) selects the model in G; props (host, k positions
+ * into cols, each >= 1) the columns proposed for deletion.  ev (dev, k + 1): ev[j] = BIC without props[j],
+ * ev[k] = BIC of the model itself (no aic adjustment).  info (dev, 1 int): 1 if the Gram is not numerically
+ * positive definite (scores invalid: use fokl_candidates_eval instead). */
+int fokl_kill_scores(fokl_ctx *ctx, const double *G, int64_t ldg, const double *Xty, const int32_t *cols, int p,
+                     const int32_t *props, int k, const fokl_hypers *hyp, double *ev, int32_t *info);
+
 /* ---- checks / "next" rows ------------------------------------------------------------------- */
 
 /* residual moments of an explicit model: out (dev, 2 doubles) = { sum r, sum r^2 },

@@ -43,6 +43,8 @@ def lib():
     L.emu_candidate.argtypes = [_vp, _i64, _vp, _vp, _i32, ctypes.POINTER(EmuHypers), _i32, _u64, _u64, _vp, _vp,
                                 _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
     L.emu_candidate.restype = _i32
+    L.emu_kill_scores.argtypes = [_vp, _i64, _vp, _vp, _i32, _vp, _i32, ctypes.POINTER(EmuHypers), _vp]
+    L.emu_kill_scores.restype = _i32
     L.emu_philox_normals.argtypes = [_u64, _u64, _i32, _i32, _vp]
     L.emu_philox_normals.restype = None
     L.emu_philox_gammas.argtypes = [_u64, _u64, _i32, _f64, _vp]
@@ -104,3 +106,17 @@ def candidate(G, Xty, idx, hyp, rng_mode=0, seed=0, stream=0, variates=None, sig
                         sigs.ctypes.data, taus.ctypes.data, info.ctypes.data)
     return dict(ev=ev[0], betahat=betahat, lamb=lamb, Q=Q.T.copy(), betas=betas, sigs=sigs, taus=taus,
                 info=int(info[0]))
+
+
+def kill_scores(G, Xty, idx, props, hyp):
+    G = np.ascontiguousarray(G, dtype=np.float64)
+    Xty = np.ascontiguousarray(np.asarray(Xty).reshape(-1), dtype=np.float64)
+    idx = np.ascontiguousarray(idx, dtype=np.int32)
+    props = np.ascontiguousarray(props, dtype=np.int32)
+    D = int(hyp['draws'])
+    h = EmuHypers(hyp['a'], hyp['b'], hyp['atau'], hyp['btau'], hyp['sigsqd0'], hyp['tausqd0'], hyp['yty'],
+                  hyp['sum_y'], int(hyp['n']), D, int(np.ceil(D / 2)), int(np.ceil(D / 2 + 1)), 0)
+    ev = np.zeros(len(props) + 1)
+    bad = lib().emu_kill_scores(G.ctypes.data, G.shape[1], Xty.ctypes.data, idx.ctypes.data, len(idx),
+                                props.ctypes.data, len(props), ctypes.byref(h), ev.ctypes.data)
+    return ev, bad

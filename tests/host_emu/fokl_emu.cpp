@@ -101,6 +101,21 @@ int emu_candidate(const double *G, int64_t ldg, const double *Xty, const int32_t
     return 0;
 }
 
+// kill_scores on the host: ev_out has k + 1 entries; returns the not-positive-definite flag
+int emu_kill_scores(const double *G, int64_t ldg, const double *Xty, const int32_t *idx, int p, const int32_t *props,
+                    int k, const emu_hypers *h, double *ev_out)
+{
+    Team t;
+    t.tid = 0; t.nthr = 1; t.lane = 0; t.nlane = 1; t.warp = 0; t.nwarp = 1;
+    std::vector<double> L((size_t)p * p), z(p), beta(p), wbuf(p), red(16);
+    volatile int flag = 0;
+    CandConst c;
+    c.a = h->a; c.b = h->b; c.atau = h->atau; c.btau = h->btau; c.sigsqd0 = h->sigsqd0; c.tausqd0 = h->tausqd0;
+    c.yty = h->yty; c.sum_y = h->sum_y; c.n = (double)h->n; c.draws = h->draws; c.from0 = h->from0; c.from1 = h->from1;
+    return kill_scores(t, G, ldg, Xty, idx, p, props, k, c, L.data(), z.data(), beta.data(), wbuf.data(), ev_out, &flag,
+                       red.data());
+}
+
 void emu_philox_normals(uint64_t seed, uint64_t stream, int draws, int p, double *out)
 {
     Philox g;

@@ -179,3 +179,25 @@ def test_residual_bic_cross_check(engine, phis_cubic):
     res = engine.evaluate([cols], hyp, rng_mode=_lib.RNG_NONE, refine_tol=None)
     ev2 = engine.residual_bic(cols, res.betahat[:len(cols)])
     assert abs(res.ev[0] - ev2) <= 1e-10 * abs(ev2)
+
+
+def test_kill_scores_equal_spectral_bic(engine, phis_cubic):
+    """fokl_kill_scores (one Cholesky, SSE_{-q} = SSE + b_q^2 / (A^-1)_qq) against the per-candidate spectral path."""
+    x, y, terms, X = make_problem(phis_cubic, 8000, 4, 21, way3=True, ind_max=3)
+    setup_engine(engine, phis_cubic, x, y, terms)
+    a = atau = 4
+    b, btau = fo.default_b_btau(y, a, atau)
+    hyp = engine.make_hypers(a, b, atau, btau, b / (1 + a), btau / (1 + atau), 10)
+    P = engine.P
+    model = [0] + list(range(2, P))
+    pos = list(range(1, len(model)))
+    ev, ok = engine.kill_scores(model, pos, hyp)
+    assert ok
+    sets = [[c for j, c in enumerate(model) if j != q] for q in pos] + [model]
+    ref = engine.evaluate(sets, hyp, rng_mode=_lib.RNG_NONE, refine_tol=None).ev
+    assert np.max(np.abs(ev - ref) / np.abs(ref)) < 1e-11
+    # a singular Gram (duplicated column) is reported, not silently scored
+    engine.append_terms(terms[:1])
+    dup = list(range(engine.P))
+    _, ok = engine.kill_scores(dup, [1], hyp)
+    assert not ok

@@ -97,3 +97,26 @@ def test_philox_streams_are_standard():
         L.emu_philox_gammas(99, 3, 20000, ctypes.c_double(shape), g.ctypes.data)
         assert abs(g.mean() - shape) < 5 * np.sqrt(shape / 20000) + 1e-12
         assert abs(g.var() - shape) < 0.1 * shape
+
+
+def test_kill_scores_math_matches_oracle_bic(phis_cubic):
+    X, y = _problem(phis_cubic, 2000, 3, 8)
+    n, P = X.shape
+    G, Xty = X.T @ X, (X.T @ y)[:, 0]
+    hyp = dict(a=4, b=1, atau=4, btau=1, sigsqd0=1, tausqd0=1, yty=float((y.T @ y)[0, 0]), sum_y=float(y.sum()), n=n,
+               draws=10)
+    idx = np.array([0] + list(range(2, P)))
+    props = np.arange(1, len(idx))
+    ev, bad = emu.kill_scores(G, Xty, idx, props, hyp)
+    assert bad == 0
+
+    def bic(cols):
+        r = fo.gibbs_from_X(X[:, cols], y, 4, 1, 4, 1, 1, 1.0, 1.0, y.T.dot(y), literal=False,
+                            variates=(np.zeros((1, len(cols))), np.ones(1), np.ones(1)))
+        return r['ev']
+    ref = np.array([bic([c for j, c in enumerate(idx) if j != q]) for q in props] + [bic(list(idx))])
+    assert np.max(np.abs(ev - ref) / np.abs(ref)) < 1e-12
+    G2 = G.copy()
+    G2[:, 2] = G2[:, 1]
+    G2[2, :] = G2[1, :]
+    assert emu.kill_scores(G2, Xty, np.arange(P), np.array([1]), hyp)[1] == 1

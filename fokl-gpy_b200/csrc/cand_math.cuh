@@ -317,7 +317,9 @@ FOKL_HD int kill_scores(const Team &t, const double *G, int64_t ldg, const doubl
     // right-looking Cholesky; column j holds L[i][j], i >= j, at L[j*p + i]
     for (int j = 0; j < p; ++j) {
         const double d = L[(int64_t)j * p + j];
-        if (!(d > 0.0)) {
+        // pivot relative to the column's own squared norm: below ~1e-11 the Schur complement is rounding noise
+        // (duplicated / linearly dependent columns) and the deletion formula would divide by it
+        if (!(d > 1e-11 * G[(int64_t)idx[j] * ldg + idx[j]])) {
             if (t.tid == 0) *flag = 1;
             break;
         }

@@ -270,7 +270,8 @@ class Engine:
         t = self._tic()
         self._ck(self.lib.fokl_gram_update(self.ctx, self.X.data_ptr(), self.ld, self.ds.n, p_old, c,
                                            self.ds.y.data_ptr(), self.block.data_ptr()))
-        self._toc(t, 'gram', flops=2.0 * self.ds.n * (p_old + c + 1) * c, bytes=8.0 * self.ds.n * (p_old + c + 1),
+        # algorithmic flops: cross block + upper triangle of the symmetric new block + X_new' y
+        self._toc(t, 'gram', flops=2.0 * self.ds.n * (p_old * c + c * (c + 1) / 2 + c), bytes=8.0 * self.ds.n * (p_old + c + 1),
                   cols=p_old + c + 1)
         if self.dist is not None:
             t = self._tic()
@@ -409,6 +410,33 @@ class Engine:
         evh = ev.cpu().numpy()
         ok = int(info.item()) == 0 and bool(np.all(np.isfinite(evh)))
         return evh, ok
+
+    def kill_loop(self, cols, cand_pos, bv0, bv1, hyp, threshav, threshstda, threshstdb, icpt, evmin, aic_adj, start):
+        """The kill loop of one substage (FR:1666-1690) in one launch (fokl_kill_loop).  Returns dict(n_acc, tested,
+        bad, acc, calls, ev) as host values (this call synchronises)."""
+        torch = self.torch
+        cols = np.ascontiguousarray(cols, dtype=np.int32)
+        cand_pos = np.ascontiguousarray(cand_pos, dtype=np.int32)
+        bv0 = np.ascontiguousarray(bv0, dtype=np.float64)
+        bv1 = np.ascontiguousarray(bv1, dtype=np.float64)
+        vm = len(cand_pos)
+        kp = _lib.KillParams(float(threshav), float(threshstda), float(threshstdb), float(icpt), float(evmin),
+                             float(aic_adj), int(start), 0)
+        # one output buffer: [3 + 2 vm] int32 viewed in the first doubles, then vm doubles
+        n_i = 3 + 2 * vm
+        n_i_d = (n_i + 1) // 2
+        out = torch.zeros(n_i_d + max(vm, 1), dtype=torch.float64, device=self.device)
+        t = self._tic()
+        self._ck(self.lib.fokl_kill_loop(self.ctx, self.G.data_ptr(), self.Gcap, self.Xty.data_ptr(), cols.ctypes.data,
+                                         len(cols), cand_pos.ctypes.data, bv0.ctypes.data, bv1.ctypes.data, vm,
+                                         ctypes.byref(hyp), ctypes.byref(kp), out.data_ptr(),
+                                         out.data_ptr() + 8 * n_i_d))
+        self._toc(t, 'kill_loop', cands=vm, pmax=len(cols))
+        h = out.cpu().numpy()
+        oi = h[:n_i_d].view(np.int32)
+        k = int(oi[0])
+        return dict(n_acc=k, tested=int(oi[1]), bad=int(oi[2]), acc=oi[3:3 + k].copy(),
+                    calls=oi[3 + vm:3 + vm + k].copy(), ev=h[n_i_d:n_i_d + k].copy())
 
     def residual_bic(self, cols, betahat_dev):
         """BIC of FR:1551-1554 from an explicit N-length residual pass over X (used when the Gram-only

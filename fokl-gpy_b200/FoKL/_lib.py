@@ -32,6 +32,13 @@ class Hypers(ctypes.Structure):
                 ('reserved', ctypes.c_int32)]
 
 
+class KillParams(ctypes.Structure):
+    """struct fokl_kill_params (include/fokl_b200.h)."""
+    _fields_ = [('threshav', ctypes.c_double), ('threshstda', ctypes.c_double), ('threshstdb', ctypes.c_double),
+                ('icpt', ctypes.c_double), ('evmin', ctypes.c_double), ('aic_adj', ctypes.c_double),
+                ('start', ctypes.c_int32), ('reserved', ctypes.c_int32)]
+
+
 PROTOTYPES = {
     'fokl_abi_version': (_i32, []),
     'fokl_ctx_create': (_i32, [ctypes.POINTER(_vp), _i32, _vp]),
@@ -51,6 +58,8 @@ PROTOTYPES = {
     'fokl_candidates_eval': (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _i32, ctypes.POINTER(Hypers), _vp, _i32, _u64,
                                     _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'fokl_kill_scores': (_i32, [_vp, _vp, _i64, _vp, _vp, _i32, _vp, _i32, ctypes.POINTER(Hypers), _vp, _vp]),
+    'fokl_kill_loop': (_i32, [_vp, _vp, _i64, _vp, _vp, _i32, _vp, _vp, _vp, _i32, ctypes.POINTER(Hypers),
+                              ctypes.POINTER(KillParams), _vp, _vp]),
     'fokl_residual_moments': (_i32, [_vp, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp]),
     'fokl_predict_draws': (_i32, [_vp, _vp, _i64, _i64, _i32, _vp, _i32, _vp]),
     'fokl_column_minmax': (_i32, [_vp, _vp, _i64, _i64, _i32, _vp]),

@@ -256,68 +256,65 @@ def forward_select(engine, hy, m, n_phis, console=True, rng='philox', eager=Fals
                     icpt = abs(float(rr.stats_of(slot)[2, 0].item()))
                     cur = i + 1
             else:
-                # fast path: every proposal of a round is scored from ONE Cholesky factorisation of the current
-                # model (fokl_kill_scores); the chains of the accepted models -- which only feed the next round's
-                # threshold through |mean intercept| (FR:1671) and the final draws (FR:1690) -- are run afterwards as
-                # one batch and every round's proposal list is re-checked against them (rolled back on a mismatch),
-                # so the outcome is exactly that of the sequential loop.
+                # fast path: the whole kill loop runs on the device in one launch (fokl_kill_loop: sweep-operator
+                # inverse of the model's Gram, one O(p^2) reverse sweep per accepted kill).  The chains of the accepted
+                # models -- which only feed later rounds' threshold through |mean intercept| (FR:1671) and the final
+                # draws (FR:1690) -- are run afterwards as one batch, only for the rounds whose remaining proposals can
+                # depend on that threshold, and every such round is re-checked against its true chain (the loop is
+                # re-run from the first round that differs), so the outcome is exactly that of the sequential loop.
+                bv1_sens = (bv1 > hy['threshstda']) & ~(bv1 > hy['threshstdb'])
+                sens_from = np.zeros(vm + 1, dtype=bool)          # any threshold-dependent candidate at index >= i
+                for i in range(vm - 1, -1, -1):
+                    sens_from[i] = sens_from[i + 1] or bool(bv1_sens[i])
                 state = dict(killed=[], evmin=evmin, cur=0, icpt=icpt, calls=call_id[0], gibbs=n_gibbs)
-                rounds = []        # per accepted kill: dict(before=state copy, props, i, model cols, stream id, icpt_used)
+                rounds = []        # accepted kills: dict(i, cols, stream, icpt_used, gibbs_after [, icpt_true, ev_true])
+                fallback = False
                 while True:
-                    while state['cur'] < vm:
-                        props = proposals(state['cur'], state['icpt'])
-                        if not props:
-                            break
+                    if state['cur'] < vm and proposals(state['cur'], state['icpt']):
                         model = [c for c in full if c not in set(state['killed'])]
-                        pos = [model.index(int(cand_cols[i])) for i in props]
-                        scores, ok = engine.kill_scores(model, pos, hyp)
+                        where = {c: k_ for k_, c in enumerate(model)}
+                        pos = [where.get(int(cand_cols[i]), 1) for i in range(vm)]
+                        r = engine.kill_loop(model, pos, bv0, bv1, hyp, hy['threshav'], hy['threshstda'],
+                                             hy['threshstdb'], state['icpt'], state['evmin'], aic_adj, state['cur'])
                         n_batches += 1
-                        if not ok:
-                            # Gram not numerically positive definite: score the proposals through the spectral path
-                            sets_ = [[c for c in model if c != int(cand_cols[i])] for i in props]
-                            scores = run(sets_, [False] * len(sets_), [0] * len(sets_)).ev
-                        hit = None
-                        for r, i in enumerate(props):
-                            evt = float(scores[r]) + aic_adj * (len(model) - 1)
-                            if evt < state['evmin']:
-                                hit = (r, i, evt)
-                                break
-                        if hit is None:
-                            state['calls'] += len(props)
-                            state['gibbs'] += len(props)
+                        if r['bad']:
+                            fallback = True
                             break
-                        r, i, evt = hit
-                        before = dict(state, killed=list(state['killed']))
-                        state['calls'] += r + 1
-                        state['gibbs'] += r + 1
-                        state['killed'] = state['killed'] + [int(cand_cols[i])]
-                        state['evmin'] = evt
-                        state['cur'] = i + 1
-                        rounds.append(dict(before=before, props=props, i=i, stream=state['calls'],
-                                           cols=[c for c in model if c != int(cand_cols[i])], icpt_used=state['icpt']))
+                        cols_k = model
+                        for k_ in range(r['n_acc']):
+                            i = int(r['acc'][k_])
+                            cols_k = [c for c in cols_k if c != int(cand_cols[i])]
+                            rounds.append(dict(i=i, cols=cols_k, stream=state['calls'] + int(r['calls'][k_]),
+                                               gibbs_after=state['gibbs'] + int(r['calls'][k_]),
+                                               ev_dev=float(r['ev'][k_]), icpt_used=state['icpt']))
+                        state['calls'] += r['tested']
+                        state['gibbs'] += r['tested']
+                        state['killed'] = state['killed'] + [int(cand_cols[int(i)]) for i in r['acc']]
+                        if r['n_acc']:
+                            state['evmin'] = float(r['ev'][-1])
+                            state['cur'] = int(r['acc'][-1]) + 1
                     if not rounds:
                         break
-                    # chains of all accepted models in one batch; verify the thresholds each later round used
-                    todo = [rd for rd in rounds if 'icpt_true' not in rd]
+                    # chains of the accepted models that matter: rounds with threshold-dependent proposals left, + last
+                    todo = [rd for k_, rd in enumerate(rounds)
+                            if 'icpt_true' not in rd and (sens_from[rd['i'] + 1] or k_ == len(rounds) - 1)]
                     if todo:
                         rr = run([rd['cols'] for rd in todo], [True] * len(todo), [rd['stream'] for rd in todo])
                         for slot, rd in enumerate(todo):
                             rd['icpt_true'] = abs(float(rr.stats_of(slot)[2, 0].item()))
                             rd['ev_true'] = float(rr.ev[slot]) + aic_adj * len(rd['cols'])
-                            rd['betas'] = rr.betas_of(slot).clone() if rd is rounds[-1] else None
                             rd['rr'], rd['slot'] = rr, slot
                     redo = None
                     for k_, rd in enumerate(rounds):
-                        nxt_start = rd['i'] + 1
-                        used = rounds[k_ + 1]['props'] if k_ + 1 < len(rounds) else proposals(nxt_start, rd['icpt_used'])
-                        if proposals(nxt_start, rd['icpt_true']) != used:
+                        if 'icpt_true' not in rd or rd['icpt_true'] == rd['icpt_used']:
+                            continue
+                        nxt = rd['i'] + 1
+                        if proposals(nxt, rd['icpt_true']) != proposals(nxt, rd['icpt_used']):
                             redo = k_
                             break
                     if redo is None:
                         last_rd = rounds[-1]
-                        if last_rd['betas'] is None:
-                            last_rd['betas'] = last_rd['rr'].betas_of(last_rd['slot']).clone()
-                        cur_betas = last_rd['betas']
+                        cur_betas = last_rd['rr'].betas_of(last_rd['slot']).clone()
                         icpt = last_rd['icpt_true']
                         evmin = last_rd['ev_true']        # report the spectral-path BIC of the accepted model
                         killed = list(state['killed'])
@@ -327,18 +324,45 @@ def forward_select(engine, hy, m, n_phis, console=True, rng='philox', eager=Fals
                     # roll back to just after round `redo`, now with its true threshold, and continue from there
                     rd = rounds[redo]
                     rounds = rounds[:redo + 1]
-                    st_after = dict(rd['before'], killed=rd['before']['killed'] + [int(cand_cols[rd['i']])])
-                    st_after['calls'] = rd['stream']
-                    st_after['gibbs'] = rd['before']['gibbs'] + (rd['props'].index(rd['i']) + 1)
-                    st_after['evmin'] = rd['ev_true']
-                    st_after['cur'] = rd['i'] + 1
-                    st_after['icpt'] = rd['icpt_true']
                     rd['icpt_used'] = rd['icpt_true']
-                    state = st_after
-                call_id[0] = state['calls']
-                n_gibbs = state['gibbs']
-                if not rounds:
-                    killed = []
+                    state = dict(killed=[c for c in full if c not in set(rd['cols'])], evmin=rd['ev_true'],
+                                 cur=rd['i'] + 1, icpt=rd['icpt_true'], calls=rd['stream'], gibbs=rd['gibbs_after'])
+                if fallback:
+                    # Gram not numerically positive definite (p >= N regimes): literal loop, one spectral evaluation
+                    # (eig + chain) per proposal, proposals of a round side by side
+                    killed, evmin, cur = [], ev, 0
+                    while cur < vm:
+                        props = proposals(cur, icpt)
+                        if not props:
+                            break
+                        sets = []
+                        for i in props:
+                            drop = set(killed) | {int(cand_cols[i])}
+                            sets.append([c for c in full if c not in drop])
+                        ids = [call_id[0] + r_ + 1 for r_ in range(len(props))]
+                        rr = run(sets, [True] * len(sets), ids)
+                        accepted = None
+                        for r_, i in enumerate(props):
+                            evt = float(rr.ev[r_]) + aic_adj * len(sets[r_])
+                            if evt < evmin:
+                                accepted = (i, evt, rr, r_)
+                                break
+                        tested = (props.index(accepted[0]) + 1) if accepted else len(props)
+                        call_id[0] += tested
+                        n_gibbs += tested
+                        if accepted is None:
+                            break
+                        i, evt, rr, slot = accepted
+                        killed.append(int(cand_cols[i]))
+                        evmin = evt
+                        cur_betas = rr.betas_of(slot).clone()
+                        icpt = abs(float(rr.stats_of(slot)[2, 0].item()))
+                        cur = i + 1
+                else:
+                    call_id[0] = state['calls']
+                    n_gibbs = state['gibbs']
+                    if not rounds:
+                        killed = []
 
             # ---- drop accepted kills (FR:1691-1695) ---------------------------------------------------------------
             if killed:

@@ -30,7 +30,7 @@ struct FactorMeta {          // one distinct (input, order) pair
     int16_t pad;
 };
 
-struct TermMeta {            // one output column
+struct alignas(8) TermMeta {  // one output column (read by the kernel as one packed 64-bit word)
     uint8_t cnt;             // number of factors (0 -> constant 1)
     uint8_t f[kMaxTermFactors];
 };
@@ -86,6 +86,7 @@ __global__ void __launch_bounds__(kThreads) basis_kernel(const BasisParams P)
     double *s_F = s_tab + tab_doubles;
     FactorMeta *s_fac = reinterpret_cast<FactorMeta *>(s_F + (size_t)P.n_factors * ROWS);
     TermMeta *s_term = reinterpret_cast<TermMeta *>(s_fac + P.n_factors);
+    const unsigned long long *s_term64 = reinterpret_cast<const unsigned long long *>(s_term);
 
     const int tid = threadIdx.x;
     // ---- stage coefficient tables and metadata ------------------------------------------------
@@ -106,7 +107,12 @@ __global__ void __launch_bounds__(kThreads) basis_kernel(const BasisParams P)
     for (int j = tid; j < P.n_terms; j += kThreads) s_term[j] = P.terms[j];
     __syncthreads();
 
-    for (int64_t tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+    // each CTA owns a contiguous range of row tiles: its C output streams stay inside the same few 2 MB pages
+    // (one per column) for the whole launch instead of hopping pages every tile
+    const int64_t per_cta = (P.n_tiles + gridDim.x - 1) / gridDim.x;
+    const int64_t tile_lo = (int64_t)blockIdx.x * per_cta;
+    const int64_t tile_hi = tile_lo + per_cta < P.n_tiles ? tile_lo + per_cta : P.n_tiles;
+    for (int64_t tile = tile_lo; tile < tile_hi; ++tile) {
         const int64_t row0 = tile * ROWS + (int64_t)tid * RPT;
         // ---- phase 1: factor values -------------------------------------------------------------
         {
@@ -166,47 +172,51 @@ __global__ void __launch_bounds__(kThreads) basis_kernel(const BasisParams P)
         }
         __syncthreads();
         // ---- phase 2: products, streamed to HBM -----------------------------------------------------
+        // (term metadata is read as one packed 64-bit word: byte 0 = factor count, bytes 1..7 = factor slots --
+        //  indexing a byte array of a struct copy would force it into local memory)
         {
             double pre[RPT];
 #pragma unroll
             for (int r = 0; r < RPT; ++r) pre[r] = 1.0;
-            int pf0 = -1, pf1 = -1;
+            unsigned pf01 = 0xffffffffu;
             const bool full = (row0 + RPT - 1 < P.n);
-            for (int j = 0; j < P.n_terms; ++j) {
-                const TermMeta tm = s_term[j];
+            const double *Fme = s_F + tid * RPT;
+            double *dst = P.out + row0;
+            for (int j = 0; j < P.n_terms; ++j, dst += P.ld) {
+                const unsigned long long w = s_term64[j];
+                const int cnt = (int)(w & 0xffu);
                 double v[RPT];
-                if (tm.cnt == 0) {
+                if (cnt == 0) {
 #pragma unroll
                     for (int r = 0; r < RPT; ++r) v[r] = 1.0;
                 } else {
+                    const unsigned f01 = (unsigned)(w >> 8) & 0xffffu;
                     int start;
-                    if (tm.cnt >= 3 && tm.f[0] == pf0 && tm.f[1] == pf1) {
+                    if (cnt >= 3 && f01 == pf01) {
                         start = 2;   // reuse (b0 * b1) from the previous term: same rounding, fewer LDS
                     } else {
-                        const double *a = s_F + (size_t)tm.f[0] * ROWS + tid * RPT;
+                        const double *a = Fme + (size_t)(f01 & 0xffu) * ROWS;
 #pragma unroll
                         for (int r = 0; r < RPT; ++r) pre[r] = a[r];
                         start = 1;
-                        if (tm.cnt >= 3) {
-                            const double *b = s_F + (size_t)tm.f[1] * ROWS + tid * RPT;
+                        pf01 = 0xffffffffu;
+                        if (cnt >= 3) {
+                            const double *b = Fme + (size_t)(f01 >> 8) * ROWS;
 #pragma unroll
                             for (int r = 0; r < RPT; ++r) pre[r] = __dmul_rn(pre[r], b[r]);
                             start = 2;
-                            pf0 = tm.f[0];
-                            pf1 = tm.f[1];
-                        } else {
-                            pf0 = -1;
+                            pf01 = f01;
                         }
                     }
 #pragma unroll
                     for (int r = 0; r < RPT; ++r) v[r] = pre[r];
-                    for (int q = start; q < tm.cnt; ++q) {
-                        const double *b = s_F + (size_t)tm.f[q] * ROWS + tid * RPT;
+                    unsigned long long rest = w >> (8 * (start + 1));
+                    for (int q = start; q < cnt; ++q, rest >>= 8) {
+                        const double *b = Fme + (size_t)(rest & 0xffu) * ROWS;
 #pragma unroll
                         for (int r = 0; r < RPT; ++r) v[r] = __dmul_rn(v[r], b[r]);
                     }
                 }
-                double *dst = P.out + (int64_t)j * P.ld + row0;
                 if (RPT == 2 && full) {
                     __stcs(reinterpret_cast<double2 *>(dst), make_double2(v[0], v[RPT - 1]));
                 } else {

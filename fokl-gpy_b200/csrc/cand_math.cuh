@@ -161,6 +161,120 @@ FOKL_HD void eig_finish(const Team &t, const double *W, const double *V, int p, 
     t.sync();
 }
 
+// ---- Cholesky + one-sided Jacobi on the factor (Veselic-Hari) ----------------------------------------
+// G = L L'.  Rotating the columns of W = L until they are mutually orthogonal gives W = U diag(sqrt(lambda)):
+// eigenvectors u_j = w_j / |w_j| and eigenvalues |w_j|^2 of G, with no accumulated rotation matrix (half the
+// memory and flops of jacobi_eigh) and high relative accuracy for the small eigenvalues.
+
+// Right-looking Cholesky of the lower triangle stored column-major in L (ld = p): on return column j holds
+// L[i][j], i >= j, and zeros above the diagonal.  Returns false if a pivot is not positive.
+FOKL_HD bool cholesky_lower(const Team &t, double *L, int p)
+{
+    bool ok = true;
+    for (int j = 0; j < p; ++j) {
+        const double d = L[(int64_t)j * p + j];
+        if (!(d > 0.0) || !(d < 1.7e308)) { ok = false; break; }
+        const double r = sqrt(d);
+        t.sync();
+        for (int i = j + t.tid; i < p; i += t.nthr) L[(int64_t)j * p + i] = (i == j) ? r : L[(int64_t)j * p + i] / r;
+        t.sync();
+        const int rem = p - j - 1;
+        for (int64_t e = t.tid; e < (int64_t)rem * rem; e += t.nthr) {
+            int mc = (int)(e / rem), mr = (int)(e - (int64_t)mc * rem);
+            if (mr < mc) continue;
+            int m = j + 1 + mc, i = j + 1 + mr;
+            L[(int64_t)m * p + i] -= L[(int64_t)j * p + i] * L[(int64_t)j * p + m];
+        }
+        t.sync();
+    }
+    t.sync();
+    return ok;
+}
+
+// Orthogonalise columns wi, wj (length p).  One warp per pair.
+FOKL_HD bool jacobi_pair_w(const Team &t, double *wi, double *wj, int p, double tol)
+{
+    double al = 0.0, be = 0.0, ga = 0.0;
+    for (int e = t.lane; e < p; e += t.nlane) {
+        double a = wi[e], b = wj[e];
+        al += a * a;
+        be += b * b;
+        ga += a * b;
+    }
+    warp_sum3(t, al, be, ga);
+    if (!(fabs(ga) > tol * sqrt(al * be))) return false;
+    double zeta = (be - al) / (2.0 * ga);
+    double tt = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+    double c = 1.0 / sqrt(1.0 + tt * tt);
+    double s = c * tt;
+    for (int e = t.lane; e < p; e += t.nlane) {
+        double a = wi[e], b = wj[e];
+        wi[e] = c * a - s * b;
+        wj[e] = s * a + c * b;
+    }
+    return true;
+}
+
+// Single-team driver (host emulation and reference for the cluster kernel): W (in: L, column-major ld) is rotated
+// in place.  Returns the number of sweeps.
+FOKL_HD int jacobi_w_sweeps(const Team &t, double *W, int p, int ld, int max_sweeps, double tol, volatile int *flag)
+{
+    if (p < 2) return 0;
+    const int n = p + (p & 1);
+    const int nm1 = n - 1;
+    int sweep = 0;
+    for (; sweep < max_sweeps; ++sweep) {
+        if (t.tid == 0) *flag = 0;
+        t.sync();
+        for (int r = 0; r < nm1; ++r) {
+            for (int k = t.warp; k < n / 2; k += t.nwarp) {
+                int i, j;
+                if (k == 0) { i = nm1; j = r; }
+                else { i = (r + k) % nm1; j = (r - k + nm1) % nm1; }
+                if (i > j) { int q = i; i = j; j = q; }
+                if (j >= p) continue;
+                bool rot = jacobi_pair_w(t, W + (int64_t)i * ld, W + (int64_t)j * ld, p, tol);
+                if (rot && t.lane == 0) *flag = 1;
+            }
+            t.sync();
+        }
+        int any = *flag;
+        t.sync();
+        if (!any) { ++sweep; break; }
+    }
+    return sweep;
+}
+
+// After jacobi_w_sweeps: eigenvalues = squared column norms, ascending; Q row r = normalised column (ld_q = p).
+FOKL_HD void eig_finish_w(const Team &t, const double *W, int p, int ld, double *lam_raw, int *perm, double *lamb,
+                          double *Q)
+{
+    for (int j = t.warp; j < p; j += t.nwarp) {
+        double s = 0.0;
+        for (int e = t.lane; e < p; e += t.nlane) s += W[(int64_t)j * ld + e] * W[(int64_t)j * ld + e];
+        s = warp_sum1(t, s);
+        if (t.lane == 0) lam_raw[j] = s;
+    }
+    t.sync();
+    for (int j = t.tid; j < p; j += t.nthr) {
+        double lj = lam_raw[j];
+        int rank = 0;
+        for (int i = 0; i < p; ++i) {
+            double li = lam_raw[i];
+            rank += (li < lj || (li == lj && i < j)) ? 1 : 0;
+        }
+        perm[rank] = j;
+    }
+    t.sync();
+    for (int r = t.warp; r < p; r += t.nwarp) {
+        int j = perm[r];
+        const double inv = 1.0 / sqrt(lam_raw[j]);
+        for (int e = t.lane; e < p; e += t.nlane) Q[(int64_t)r * p + e] = W[(int64_t)j * ld + e] * inv;
+        if (t.lane == 0) lamb[r] = lam_raw[j];
+    }
+    t.sync();
+}
+
 struct CandConst {
     double a, b, atau, btau, sigsqd0, tausqd0, yty, sum_y;
     double n;     // number of rows as double
@@ -391,6 +505,150 @@ FOKL_HD int kill_scores(const Team &t, const double *G, int64_t ldg, const doubl
     }
     t.sync();
     return 0;
+}
+
+}  // namespace fokl
+
+// ---- the whole kill loop of one substage on the device ---------------------------------------------------------
+// FR:1666-1690 asks `gibbs` for one BIC per proposal, sequentially, each against the kill set accepted so far.
+// All of those BICs follow from the *sweep operator* on the augmented, y-centred normal equations
+//     T = [ A  z ; z' s ],  A = G[idx][idx],  z = X'(y - ybar),  s = (y - ybar)'(y - ybar):
+// after sweeping every column, T = [ -A^-1  betahat ; betahat'  SSE ]; removing column q from the model is the
+// reverse sweep on q (one rank-1 update, O(p^2), fully parallel) and costs  SSE_{-q} = SSE + T_qy^2 / (-T_qq).
+// So one O(p^3) inversion + one O(p^2) update per *accepted* kill replaces one eigendecomposition per proposal,
+// and the loop runs without a host round trip.  The acceptance threshold reads |mean intercept draw| of the last
+// accepted model (FR:1671); the kernel uses the value it is given for the whole loop and the host verifies every
+// round against the true chains afterwards (FoKL/_selection.py), re-running from the first round that differs.
+//   T        (p + 1)^2 workspace (column-major, ld = p + 1)
+//   cand_pos position in idx (>= 1) of candidate i, candidates in the reference's order (ascending |mean|)
+//   out_i    [0] accepted kills, [1] proposals tested (= `gibbs` calls of the reference), [2] error flag,
+//            [3 + k] candidate index of the k-th accepted kill, [3 + vm + k] proposals tested up to and incl. it
+//   out_ev   [k] BIC (incl. the aic adjustment) of the model after the k-th accepted kill
+namespace fokl {
+
+struct KillLoopIn {
+    double threshav, threshstda, threshstdb;
+    double icpt;       // |mean(beters[h0:, 0])| used by the threshold test
+    double evmin;      // BIC (incl. aic adjustment) of the model the loop starts from
+    double aic_adj;    // (2 - ln n) if aic else 0, per model column
+    int start;         // first candidate index to consider
+};
+
+FOKL_HD void team_atomic_min(int *addr, int v)
+{
+#if defined(__CUDA_ARCH__)
+    atomicMin(addr, v);
+#else
+    if (v < *addr) *addr = v;
+#endif
+}
+
+FOKL_HD void team_atomic_add(int *addr, int v)
+{
+#if defined(__CUDA_ARCH__)
+    atomicAdd(addr, v);
+#else
+    *addr += v;
+#endif
+}
+
+// one (reverse) sweep of pivot k on the symmetric (ld x ld) matrix T; sign = +1 sweep, -1 reverse sweep
+FOKL_HD void sweep_pivot(const Team &t, double *T, int ld, int k, double sign)
+{
+    const double invD = 1.0 / T[(int64_t)k * ld + k];
+    const double *ck = T + (int64_t)k * ld;
+    const int total = ld * ld;
+    for (int e = t.tid; e < total; e += t.nthr) {
+        int j = e / ld, i = e - j * ld;
+        if (i == k || j == k) continue;
+        T[e] -= (ck[i] * ck[j]) * invD;
+    }
+    t.sync();
+    for (int i = t.tid; i < ld; i += t.nthr) {
+        if (i == k) continue;
+        double v = sign * ck[i] * invD;
+        T[(int64_t)k * ld + i] = v;
+        T[(int64_t)i * ld + k] = v;
+    }
+    t.sync();
+    if (t.tid == 0) T[(int64_t)k * ld + k] = -invD;
+    t.sync();
+}
+
+FOKL_HD int kill_loop(const Team &t, const double *G, int64_t ldg, const double *Xty, const int *idx, int p,
+                      const int *cand_pos, const double *bv0, const double *bv1, int vm, const CandConst &c,
+                      const KillLoopIn &in, double *T, int *out_i, double *out_ev, int *sh /* 4 shared ints */)
+{
+    const int ld = p + 1;
+    const double ybar = c.sum_y / c.n;
+    const int64_t row0 = (int64_t)idx[0] * ldg;
+    for (int e = t.tid; e < ld * ld; e += t.nthr) {
+        int j = e / ld, i = e - j * ld;
+        double v;
+        if (i < p && j < p) v = G[(int64_t)idx[i] * ldg + idx[j]];
+        else if (i == p && j == p) v = c.yty - c.n * ybar * ybar;
+        else {
+            int q = i < p ? i : j;
+            v = Xty[idx[q]] - ybar * G[row0 + idx[q]];
+        }
+        T[e] = v;
+    }
+    if (t.tid == 0) { sh[0] = 0; sh[1] = 0; sh[2] = 0; sh[3] = 0; }
+    t.sync();
+    int bad = 0;
+    for (int k = 0; k < p; ++k) {
+        const double d = T[(int64_t)k * ld + k];
+        if (!(d > 1e-11 * G[(int64_t)idx[k] * ldg + idx[k]])) { bad = 1; break; }   // not numerically positive definite
+        t.sync();
+        sweep_pivot(t, T, ld, k, 1.0);
+    }
+    int n_acc = 0, tested = 0, pa = p, cur = in.start;
+    double evmin = in.evmin;
+    const double ln_n = log(c.n);
+    const double thr = in.threshav * in.icpt;
+    while (!bad && cur < vm) {
+        if (t.tid == 0) { sh[0] = 0x7fffffff; sh[1] = 0; sh[2] = 0; }
+        t.sync();
+        const double sse = T[(int64_t)p * ld + p];
+        for (int i = cur + t.tid; i < vm; i += t.nthr) {
+            const bool prop = (bv1[i] > in.threshstdb) || (bv1[i] > in.threshstda && bv0[i] < thr);
+            if (!prop) continue;
+            const int q = cand_pos[i];
+            const double tqq = T[(int64_t)q * ld + q], tqy = T[(int64_t)p * ld + q];
+            if (!(tqq < 0.0)) { sh[2] = 1; continue; }
+            const double sig = (sse + tqy * tqy / (-tqq)) / c.n;
+            const double evt = (double)(pa - 1) * ln_n - 2.0 * (-(c.n / 2.0) * log(sig) - (c.n - 1.0) / 2.0) +
+                               in.aic_adj * (double)(pa - 1);
+            if (evt < evmin) team_atomic_min(&sh[0], i);
+        }
+        t.sync();
+        const int hit = sh[0];
+        if (sh[2]) { bad = 2; break; }
+        for (int i = cur + t.tid; i < vm && i <= hit; i += t.nthr) {
+            const bool prop = (bv1[i] > in.threshstdb) || (bv1[i] > in.threshstda && bv0[i] < thr);
+            if (prop) team_atomic_add(&sh[1], 1);
+        }
+        t.sync();
+        tested += sh[1];
+        if (hit == 0x7fffffff) break;
+        const int q = cand_pos[hit];
+        const double tqq = T[(int64_t)q * ld + q], tqy = T[(int64_t)p * ld + q];
+        const double sig = (sse + tqy * tqy / (-tqq)) / c.n;
+        evmin = (double)(pa - 1) * ln_n - 2.0 * (-(c.n / 2.0) * log(sig) - (c.n - 1.0) / 2.0) + in.aic_adj * (double)(pa - 1);
+        t.sync();
+        sweep_pivot(t, T, ld, q, -1.0);
+        if (t.tid == 0) {
+            out_i[3 + n_acc] = hit;
+            out_i[3 + vm + n_acc] = tested;
+            out_ev[n_acc] = evmin;
+        }
+        n_acc += 1;
+        pa -= 1;
+        cur = hit + 1;
+    }
+    if (t.tid == 0) { out_i[0] = n_acc; out_i[1] = tested; out_i[2] = bad; }
+    t.sync();
+    return bad;
 }
 
 }  // namespace fokl

@@ -7,6 +7,7 @@
 // The numerical core lives in cand_math.cuh (shared with the host emulation used by the CPU tests).
 #include "fokl_ctx.cuh"
 #include "cand_math.cuh"
+#include <cooperative_groups.h>
 #include <algorithm>
 #include <math.h>
 #include <string.h>
@@ -47,6 +48,7 @@ struct EigParams {
     double *lamb, *Q, *betahat, *ev;
     int32_t *info;
     int smem_doubles;    // dynamic shared memory available for W|V (after the header)
+    int only_flagged;
 };
 
 __device__ __forceinline__ Team make_team()
@@ -63,6 +65,9 @@ __global__ void __launch_bounds__(kEigThreads) cand_eig_kernel(const EigParams P
     extern __shared__ __align__(16) double sh[];
     const Team t = make_team();
     const CandMeta m = P.meta[blockIdx.x];
+    // fallback path: only candidates whose Gram failed the Cholesky of cand_chol_kernel (info bit 1) or that are too
+    // large for the cluster kernel (info bit 2)
+    if (P.only_flagged && !(P.info[blockIdx.x] & 6)) return;
     const int p = m.p;
     const int32_t *idx = P.col_sets + m.set_off;
     double *red = sh;
@@ -85,7 +90,263 @@ __global__ void __launch_bounds__(kEigThreads) cand_eig_kernel(const EigParams P
                                   P.betahat + m.vec_off, P.scratch + m.vec_off, red);
     if (t.tid == 0) {
         P.ev[blockIdx.x] = ev;
-        P.info[blockIdx.x] = sweeps << 8;
+        P.info[blockIdx.x] = (P.info[blockIdx.x] & 6) | (sweeps << 8);
+    }
+}
+
+// ---- Cholesky factor of every candidate's Gram (pre-pass of the cluster eigensolver) --------------------------------
+// L is written to the candidate's Q slot (p x p, column-major, zeros above the diagonal); the cluster kernel reads
+// it and later overwrites the slot with the eigenvectors.  info bit 1 (value 2): Gram not positive definite.
+constexpr int kCholThreads = 1024;
+
+struct CholParams {
+    const double *G;
+    int64_t ldg;
+    const int32_t *col_sets;
+    const CandMeta *meta;
+    double *Q;
+    int32_t *info;
+    int smem_doubles;
+};
+
+__global__ void __launch_bounds__(kCholThreads) cand_chol_kernel(const CholParams P)
+{
+    extern __shared__ __align__(16) double sh[];
+    const Team t = make_team();
+    const CandMeta m = P.meta[blockIdx.x];
+    if (m.pad) {                       // too large for the cluster eigensolver: straight to the fallback kernel
+        if (t.tid == 0) P.info[blockIdx.x] = 4;
+        return;
+    }
+    const int p = m.p;
+    const int32_t *idx = P.col_sets + m.set_off;
+    double *Lg = P.Q + m.mat_off;
+    const bool in_smem = ((int64_t)p * p <= P.smem_doubles);
+    double *L = in_smem ? sh : Lg;
+    for (int e = t.tid; e < p * p; e += t.nthr) {
+        int col = e / p, row = e - col * p;
+        L[e] = (row >= col) ? P.G[(int64_t)idx[row] * P.ldg + idx[col]] : 0.0;
+    }
+    t.sync();
+    const bool ok = fokl::cholesky_lower(t, L, p);
+    if (in_smem)
+        for (int e = t.tid; e < p * p; e += t.nthr) Lg[e] = L[e];
+    if (t.tid == 0) P.info[blockIdx.x] = ok ? 0 : 2;
+}
+
+// ---- cluster eigensolver: one-sided Jacobi on the Cholesky factor, columns distributed over a CTA cluster -------------
+// A cluster of cs CTAs holds the n = 2 cs m columns of W (n >= p, zero columns pad) in shared memory, m "top" and m
+// "bottom" columns per CTA; the pair (top[k], bottom[k]) is rotated by one warp.  After every round the columns move
+// one position along the chess-tournament ring (top row to the right, bottom row to the left, top[0] of CTA 0
+// fixed): inside a CTA that is an index rotation, and only the two columns that cross a CTA boundary travel, pushed
+// into the neighbour's staging buffer through distributed shared memory, one cluster barrier per round.  n - 1 rounds
+// visit every pair once (a sweep); sweeps repeat until no pair needed a rotation.
+constexpr int kEigJThreads = 1024;
+constexpr int kEigJMaxCluster = 16;
+constexpr int kEigJHeaderDoubles = 256;   // team_sum3 scratch: 2 * 3 * 32 warps
+
+struct EigJParams {
+    const double *G;
+    int64_t ldg;
+    const double *Xty;
+    const int32_t *col_sets;
+    const CandMeta *meta;
+    const int32_t *list;     // candidates of this launch (one cluster each)
+    CandConst k;
+    double *lam_raw;         // per candidate p + 64 doubles at vec_off + 64 * cand
+    double *scratch, *ct;    // packed by vec_off
+    double *lamb, *Q, *betahat, *ev;
+    int32_t *info;
+};
+
+__host__ __device__ inline int eigj_padded_n(int p, int cs)
+{
+    const int unit = 2 * cs;
+    int n = ((p + unit - 1) / unit) * unit;
+    if (n < 4 * cs) n = 4 * cs;        // at least two pair slots per CTA (the ring needs a rotating top slot in CTA 0)
+    return n;
+}
+__host__ __device__ inline int eigj_ld(int p) { return (p + 2) & ~1; }   // column + tag slot, even
+__host__ __device__ inline size_t eigj_smem_bytes(int p, int cs)
+{
+    const int m = eigj_padded_n(p, cs) / (2 * cs);
+    return (size_t)(2 * m + 4) * eigj_ld(p) * sizeof(double) + (size_t)(2 * m + 2 * kEigJMaxCluster + 8) * sizeof(int) +
+           kEigJHeaderDoubles * sizeof(double);
+}
+
+// one warp shifts the logical -> physical slot table by one position (all reads before any write)
+constexpr int kEigJMaxSlotsPerLane = 8;     // m <= 256
+__device__ __forceinline__ void rotate_top(int *slots, int m, int first, int incoming, int lane)
+{
+    int v[kEigJMaxSlotsPerLane];
+#pragma unroll
+    for (int q = 0; q < kEigJMaxSlotsPerLane; ++q) {
+        const int k = lane + 32 * q;
+        if (k < m) v[q] = (k > first) ? slots[k - 1] : (k == first ? incoming : slots[k]);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < kEigJMaxSlotsPerLane; ++q) {
+        const int k = lane + 32 * q;
+        if (k < m) slots[k] = v[q];
+    }
+}
+__device__ __forceinline__ void rotate_bot(int *slots, int m, int incoming, int lane)
+{
+    int v[kEigJMaxSlotsPerLane];
+#pragma unroll
+    for (int q = 0; q < kEigJMaxSlotsPerLane; ++q) {
+        const int k = lane + 32 * q;
+        if (k < m) v[q] = (k < m - 1) ? slots[k + 1] : incoming;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < kEigJMaxSlotsPerLane; ++q) {
+        const int k = lane + 32 * q;
+        if (k < m) slots[k] = v[q];
+    }
+}
+
+__global__ void __launch_bounds__(kEigJThreads, 1) cand_eigj_kernel(const EigJParams P)
+{
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int cs = (int)cluster.num_blocks(), cr = (int)cluster.block_rank();
+    const int cand = P.list[blockIdx.x / cs];
+    const CandMeta cm = P.meta[cand];
+    if (P.info[cand] & 6) return;                 // whole cluster takes the same branch: the fallback kernel does it
+    extern __shared__ __align__(16) double sh[];
+    const Team t = make_team();
+    const int p = cm.p;
+    const int n = eigj_padded_n(p, cs), m = n / (2 * cs), h = n / 2, ld = eigj_ld(p);
+    double *red = sh;                                         // reductions of ols_and_bic
+    double *cols = sh + kEigJHeaderDoubles;                                   // (2 m + 4) column buffers of ld doubles
+    int *slot_top = reinterpret_cast<int *>(cols + (size_t)(2 * m + 4) * ld);
+    int *slot_bot = slot_top + m;
+    int *flags = slot_bot + m;                                // [2][kEigJMaxCluster]
+    int *any_flag = flags + 2 * kEigJMaxCluster;              // [0] this CTA rotated something in this sweep
+    const double *Lg = P.Q + cm.mat_off;
+
+    // ---- load: top[g] = column g, bottom[g] = column h + g; columns >= p are zero padding (tag -1) -------------------
+    for (int k = t.warp; k < 2 * m; k += t.nwarp) {
+        const int g = (k < m) ? (cr * m + k) : (h + cr * m + (k - m));
+        double *dst = cols + (size_t)k * ld;
+        for (int e = t.lane; e < ld; e += 32) {
+            double v = 0.0;
+            if (e < p && g < p) v = Lg[(size_t)g * p + e];
+            if (e == p) v = (g < p) ? (double)g : -1.0;
+            dst[e] = v;
+        }
+    }
+    for (int k = t.tid; k < m; k += t.nthr) { slot_top[k] = k; slot_bot[k] = m + k; }
+    if (t.tid < 2 * kEigJMaxCluster) flags[t.tid] = 0;
+    if (t.tid == 0) any_flag[0] = 0;
+    __syncthreads();
+    if (cs > 1) cluster.sync();      // every CTA has read L and initialised its staging state before anybody pushes
+
+    const double tol = 2.220446049250313e-16 * (2.0 * sqrt((double)p) + 6.0);
+    int sweeps = 0;
+    int round = 0;
+    const int first = (cr == 0) ? 1 : 0;
+    for (; sweeps < 40; ++sweeps) {
+        for (int r = 0; r < n - 1; ++r, ++round) {
+            // ---- rotations -------------------------------------------------------------------------------------------
+            for (int k = t.warp; k < m; k += t.nwarp) {
+                double *a = cols + (size_t)slot_top[k] * ld, *b = cols + (size_t)slot_bot[k] * ld;
+                if (fokl::jacobi_pair_w(t, a, b, p, tol) && t.lane == 0) any_flag[0] = 1;
+            }
+            __syncthreads();
+            // ---- ring step ---------------------------------------------------------------------------------------------
+            const int par = round & 1;
+            const int t_out = slot_top[m - 1], b_out = slot_bot[0];
+            if (cs == 1) {
+                // the two travelling columns swap rows inside the only CTA: pure index exchange
+                __syncthreads();
+                if (t.warp == 0) rotate_top(slot_top, m, first, b_out, t.lane);
+                else if (t.warp == 1) rotate_bot(slot_bot, m, t_out, t.lane);
+                __syncthreads();
+                continue;
+            }
+            double *stage_top_in = cols + (size_t)(2 * m + par * 2 + 0) * ld;
+            double *stage_bot_in = cols + (size_t)(2 * m + par * 2 + 1) * ld;
+            if (t.warp == 0) {
+                const double *src = cols + (size_t)t_out * ld;
+                double *dst = (cr < cs - 1) ? cluster.map_shared_rank(stage_top_in, cr + 1) : stage_bot_in;
+                for (int e = t.lane; e < ld; e += 32) dst[e] = src[e];
+            } else if (t.warp == 1) {
+                const double *src = cols + (size_t)b_out * ld;
+                double *dst = (cr > 0) ? cluster.map_shared_rank(stage_bot_in, cr - 1) : stage_top_in;
+                for (int e = t.lane; e < ld; e += 32) dst[e] = src[e];
+            } else if (t.warp == 2 && r == n - 2 && t.lane < cs) {
+                // end of the sweep: tell every CTA of the cluster whether this one rotated anything
+                int *remote = cluster.map_shared_rank(flags, t.lane);
+                remote[(sweeps & 1) * kEigJMaxCluster + cr] = any_flag[0];
+            }
+            cluster.sync();
+            if (t.warp == 0) {
+                double *dst = cols + (size_t)t_out * ld;
+                for (int e = t.lane; e < ld; e += 32) dst[e] = stage_top_in[e];
+            } else if (t.warp == 1) {
+                double *dst = cols + (size_t)b_out * ld;
+                for (int e = t.lane; e < ld; e += 32) dst[e] = stage_bot_in[e];
+            } else if (t.warp == 2) {
+                rotate_top(slot_top, m, first, t_out, t.lane);
+            } else if (t.warp == 3) {
+                rotate_bot(slot_bot, m, b_out, t.lane);
+            }
+            __syncthreads();
+        }
+        int any;
+        if (cs == 1) {
+            any = any_flag[0];
+        } else {
+            any = 0;
+            for (int c = 0; c < cs; ++c) any |= flags[(sweeps & 1) * kEigJMaxCluster + c];
+        }
+        __syncthreads();
+        if (t.tid == 0) any_flag[0] = 0;
+        __syncthreads();
+        if (!any) { ++sweeps; break; }
+    }
+
+    // ---- eigenvalues = squared column norms; rank them across the cluster; eigenvectors = normalised columns ------------
+    double *lam_all = P.lam_raw + cm.vec_off + 64 * (int64_t)cand;     // n entries, indexed cr * 2m + physical slot
+    for (int k = t.warp; k < 2 * m; k += t.nwarp) {
+        const double *w = cols + (size_t)k * ld;
+        double s = 0.0;
+        for (int e = t.lane; e < p; e += 32) s += w[e] * w[e];
+        s = fokl::warp_sum1(t, s);
+        if (t.lane == 0) lam_all[cr * 2 * m + k] = (w[p] < 0.0) ? -1.0 : s;    // padding columns are marked, not ranked
+    }
+    __threadfence();
+    if (cs > 1) cluster.sync(); else __syncthreads();
+    double *lamb = P.lamb + cm.vec_off;
+    double *Q = P.Q + cm.mat_off;
+    for (int k = t.warp; k < 2 * m; k += t.nwarp) {
+        const double *w = cols + (size_t)k * ld;
+        if (w[p] < 0.0) continue;
+        const int gme = cr * 2 * m + k;
+        const double lj = lam_all[gme];
+        int rank = 0;
+        for (int g = t.lane; g < n; g += 32) {
+            const double li = lam_all[g];
+            if (li >= 0.0 && (li < lj || (li == lj && g < gme))) ++rank;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) rank += __shfl_xor_sync(0xffffffffu, rank, o);
+        const double inv = 1.0 / sqrt(lj);
+        for (int e = t.lane; e < p; e += 32) Q[(size_t)rank * p + e] = w[e] * inv;
+        if (t.lane == 0) lamb[rank] = lj;
+    }
+    __threadfence();
+    if (cs > 1) cluster.sync(); else __syncthreads();
+    if (cr != 0) return;
+    const int32_t *idx = P.col_sets + cm.set_off;
+    double ev = fokl::ols_and_bic(t, P.G, P.ldg, P.Xty, idx, p, lamb, Q, P.k, P.ct + cm.vec_off, P.betahat + cm.vec_off,
+                                  P.scratch + cm.vec_off, red);
+    if (t.tid == 0) {
+        P.ev[cand] = ev;
+        P.info[cand] = (P.info[cand] & 6) | (sweeps << 8);
     }
 }
 
@@ -253,6 +514,32 @@ __global__ void __launch_bounds__(kKillThreads) kill_scores_kernel(const KillPar
     if (t.tid == 0) P.info[0] = bad;
 }
 
+struct KillLoopParams {
+    const double *G;
+    int64_t ldg;
+    const double *Xty;
+    const int32_t *cols, *cand_pos;
+    const double *bv0, *bv1;
+    int p, vm;
+    CandConst c;
+    fokl::KillLoopIn in;
+    double *T_global;
+    int32_t *out_i;
+    double *out_ev;
+    int smem_doubles;
+};
+
+__global__ void __launch_bounds__(kKillThreads) kill_loop_kernel(const KillLoopParams P)
+{
+    extern __shared__ __align__(16) double sh[];
+    const Team t = make_team();
+    int *shi = reinterpret_cast<int *>(sh);                       // 4 ints
+    const int64_t need = (int64_t)(P.p + 1) * (P.p + 1);
+    double *T = (need <= P.smem_doubles) ? (sh + 2) : P.T_global;
+    fokl::kill_loop(t, P.G, P.ldg, P.Xty, P.cols, P.p, P.cand_pos, P.bv0, P.bv1, P.vm, P.c, P.in, T, P.out_i, P.out_ev,
+                    shi);
+}
+
 template <typename T>
 T *carve(char *&cur, size_t count)
 {
@@ -285,8 +572,30 @@ extern "C" int fokl_candidates_eval(fokl_ctx *ctx, const double *G, int64_t ldg,
     const size_t smem_cap = ctx->smem_optin ? ctx->smem_optin : 48 * 1024;
     const int smem_wv_cap = (int)((smem_cap - kSmemHeaderDoubles * sizeof(double)) / sizeof(double));
 
+    if (!ctx->cluster_probed) {
+        // clusters of 16 CTAs are "non-portable": use them only if this device can co-schedule one at full shared memory
+        ctx->cluster_probed = true;
+        if (cudaFuncSetAttribute(cand_eigj_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
+            cudaFuncSetAttribute(cand_eigj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap) == cudaSuccess) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(kEigJMaxCluster);
+            cfg.blockDim = dim3(kEigJThreads);
+            cfg.dynamicSmemBytes = smem_cap;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = kEigJMaxCluster;
+            attr[0].val.clusterDim.y = 1;
+            attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            int nc = 0;
+            if (cudaOccupancyMaxActiveClusters(&nc, cand_eigj_kernel, &cfg) == cudaSuccess && nc >= 1) ctx->max_cluster = kEigJMaxCluster;
+        }
+        cudaGetLastError();
+    }
     std::vector<CandMeta> meta(n_cand);
     std::vector<int32_t> chain_list;
+    std::vector<int> eig_class(n_cand, 0);
     int64_t vec = 0, mat = 0, wv = 0, gam = 0;
     int pmax = 0, pmax_chain = 0;
     for (int c = 0; c < n_cand; ++c) {
@@ -296,6 +605,14 @@ extern "C" int fokl_candidates_eval(fokl_ctx *ctx, const double *G, int64_t ldg,
         CandMeta &m = meta[c];
         m.p = p; m.set_off = set_offsets[c]; m.pad = 0;
         m.vec_off = vec; m.mat_off = mat;
+        // cluster size of the Jacobi eigensolver: <= 32 column pairs per CTA, columns must fit in shared memory
+        {
+            int cs = 1;
+            while (cs < kEigJMaxCluster && (p + 1) / 2 > 32 * cs) cs *= 2;
+            while (cs <= kEigJMaxCluster && eigj_smem_bytes(p, cs) > smem_cap) cs *= 2;
+            if (cs > ctx->max_cluster) m.pad = 1;          // too large: two-matrix Jacobi in global memory (fallback)
+            else eig_class[c] = cs;
+        }
         const bool in_smem = (2 * (int64_t)p * p <= smem_wv_cap);
         m.wv_off = wv;
         if (!in_smem) wv += 2 * (int64_t)p * p;
@@ -311,8 +628,18 @@ extern "C" int fokl_candidates_eval(fokl_ctx *ctx, const double *G, int64_t ldg,
     const int total_p = set_offsets[n_cand];
 
     // ---- metadata upload ---------------------------------------------------------------------------------
+    std::vector<int32_t> eig_list;                 // candidates grouped by cluster size
+    int class_begin[6] = {0, 0, 0, 0, 0, 0};       // cs = 1, 2, 4, 8, 16
+    bool any_fallback = false;
+    for (int q = 0, cs = 1; q < 5; ++q, cs *= 2) {
+        class_begin[q] = (int)eig_list.size();
+        for (int c = 0; c < n_cand; ++c)
+            if (eig_class[c] == cs) eig_list.push_back(c);
+    }
+    class_begin[5] = (int)eig_list.size();
+    for (int c = 0; c < n_cand; ++c) any_fallback = any_fallback || meta[c].pad;
     size_t meta_bytes = 64 + (size_t)total_p * sizeof(int32_t) + (size_t)n_cand * sizeof(CandMeta) +
-                        (size_t)(n_chain + 1) * sizeof(int32_t) + 64;
+                        (size_t)(n_chain + 1) * sizeof(int32_t) + (size_t)(n_cand + 1) * sizeof(int32_t) + 96;
     char *dmeta = (char *)fokl_scratch(ctx, fokl_ctx::B_META, meta_bytes);
     if (!dmeta) return FOKL_ENOMEM;
     std::vector<char> hmeta(meta_bytes, 0);
@@ -320,6 +647,9 @@ extern "C" int fokl_candidates_eval(fokl_ctx *ctx, const double *G, int64_t ldg,
     int32_t *d_sets = carve<int32_t>(dcur, total_p);
     CandMeta *d_meta = carve<CandMeta>(dcur, n_cand);
     int32_t *d_chain = carve<int32_t>(dcur, n_chain + 1);
+    int32_t *d_eig_list = carve<int32_t>(dcur, n_cand + 1);
+    if (!eig_list.empty())
+        memcpy(hmeta.data() + ((char *)d_eig_list - dmeta), eig_list.data(), eig_list.size() * sizeof(int32_t));
     memcpy(hmeta.data() + ((char *)d_sets - dmeta), col_sets, (size_t)total_p * sizeof(int32_t));
     memcpy(hmeta.data() + ((char *)d_meta - dmeta), meta.data(), (size_t)n_cand * sizeof(CandMeta));
     if (n_chain) memcpy(hmeta.data() + ((char *)d_chain - dmeta), chain_list.data(), (size_t)n_chain * sizeof(int32_t));
@@ -331,10 +661,12 @@ extern "C" int fokl_candidates_eval(fokl_ctx *ctx, const double *G, int64_t ldg,
         d_wv = (double *)fokl_scratch(ctx, fokl_ctx::B_CAND_A, (size_t)wv * sizeof(double));
         if (!d_wv) return FOKL_ENOMEM;
     }
-    size_t b_bytes = 256 + (size_t)vec * (5 * sizeof(double) + sizeof(int32_t)) + (Q ? 0 : (size_t)mat * sizeof(double));
+    size_t b_bytes = 512 + (size_t)vec * (6 * sizeof(double) + sizeof(int32_t)) + (size_t)n_cand * 64 * sizeof(double) +
+                     (Q ? 0 : (size_t)mat * sizeof(double));
     char *bcur = (char *)fokl_scratch(ctx, fokl_ctx::B_CAND_B, b_bytes);
     if (!bcur) return FOKL_ENOMEM;
     double *d_lam_raw = carve<double>(bcur, vec);
+    double *d_lam_all = carve<double>(bcur, vec + (size_t)n_cand * 64);
     double *d_scratch = carve<double>(bcur, vec);
     double *d_ct = carve<double>(bcur, vec);
     double *d_lamb = lamb ? lamb : carve<double>(bcur, vec);
@@ -348,11 +680,56 @@ extern "C" int fokl_candidates_eval(fokl_ctx *ctx, const double *G, int64_t ldg,
     k.n = (double)hyp->n; k.draws = D; k.from0 = hyp->stat_from0; k.from1 = hyp->stat_from1;
 
     // ---- eig + betahat + BIC -------------------------------------------------------------------------------
+    // (1) Cholesky factor of every candidate (into its Q slot); (2) per cluster-size class, the cluster Jacobi on the
+    // factor + betahat + BIC; (3) the two-matrix Jacobi for candidates whose Gram is not positive definite or that do
+    // not fit a cluster (exits immediately for everyone else).
+    {
+        CholParams C;
+        C.G = G; C.ldg = ldg; C.col_sets = d_sets; C.meta = d_meta; C.Q = d_Q; C.info = info;
+        int64_t need = 0;
+        for (int c = 0; c < n_cand; ++c)
+            if (!meta[c].pad && (int64_t)meta[c].p * meta[c].p * (int64_t)sizeof(double) <= (int64_t)smem_cap)
+                need = std::max<int64_t>(need, (int64_t)meta[c].p * meta[c].p);
+        C.smem_doubles = (int)need;
+        FOKL_CUDA(ctx, cudaFuncSetAttribute(cand_chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
+        cand_chol_kernel<<<n_cand, kCholThreads, (size_t)need * sizeof(double), ctx->stream>>>(C);
+        FOKL_LAUNCH_CHECK(ctx);
+    }
+    {
+        EigJParams J;
+        J.G = G; J.ldg = ldg; J.Xty = Xty; J.col_sets = d_sets; J.meta = d_meta; J.k = k;
+        J.lam_raw = d_lam_all; J.scratch = d_scratch; J.ct = d_ct; J.lamb = d_lamb; J.Q = d_Q; J.betahat = d_betahat;
+        J.ev = ev; J.info = info;
+        FOKL_CUDA(ctx, cudaFuncSetAttribute(cand_eigj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
+        for (int q = 0, cs = 1; q < 5; ++q, cs *= 2) {
+            const int cnt = class_begin[q + 1] - class_begin[q];
+            if (cnt == 0) continue;
+            size_t smem = 0;
+            for (int e = class_begin[q]; e < class_begin[q + 1]; ++e)
+                smem = std::max(smem, eigj_smem_bytes(meta[eig_list[e]].p, cs));
+            J.list = d_eig_list + class_begin[q];
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)(cnt * cs));
+            cfg.blockDim = dim3(kEigJThreads);
+            cfg.dynamicSmemBytes = smem;
+            cfg.stream = ctx->stream;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = (unsigned)cs;
+            attr[0].val.clusterDim.y = 1;
+            attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            FOKL_CUDA(ctx, cudaLaunchKernelEx(&cfg, cand_eigj_kernel, J));
+            FOKL_LAUNCH_CHECK(ctx);
+        }
+    }
     {
         EigParams P;
         P.G = G; P.ldg = ldg; P.Xty = Xty; P.col_sets = d_sets; P.meta = d_meta; P.k = k;
         P.wv = d_wv; P.lam_raw = d_lam_raw; P.scratch = d_scratch; P.ct = d_ct; P.perm = d_perm;
         P.lamb = d_lamb; P.Q = d_Q; P.betahat = d_betahat; P.ev = ev; P.info = info;
+        P.only_flagged = 1;
         int64_t need = 2 * (int64_t)pmax * pmax;
         int wv_doubles = (int)std::min<int64_t>(need, smem_wv_cap);
         if (need > smem_wv_cap) {
@@ -370,6 +747,7 @@ extern "C" int fokl_candidates_eval(fokl_ctx *ctx, const double *G, int64_t ldg,
         cand_eig_kernel<<<n_cand, kEigThreads, smem, ctx->stream>>>(P);
         FOKL_LAUNCH_CHECK(ctx);
     }
+    (void)any_fallback;
     if (n_chain == 0) return FOKL_OK;
     if (hyp->stat_from0 < 0 || hyp->stat_from0 >= D || hyp->stat_from1 < 0 || hyp->stat_from1 >= D)
         FOKL_FAIL(ctx, FOKL_EINVAL, "candidates_eval: statistic windows outside the chain");
@@ -458,6 +836,64 @@ extern "C" int fokl_kill_scores(fokl_ctx *ctx, const double *G, int64_t ldg, con
     size_t smem = (size_t)(header + (in_smem ? p * p : 0)) * sizeof(double);
     FOKL_CUDA(ctx, cudaFuncSetAttribute(kill_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
     kill_scores_kernel<<<1, kKillThreads, smem, ctx->stream>>>(P);
+    FOKL_LAUNCH_CHECK(ctx);
+    return FOKL_OK;
+}
+
+extern "C" int fokl_kill_loop(fokl_ctx *ctx, const double *G, int64_t ldg, const double *Xty, const int32_t *cols, int p,
+                              const int32_t *cand_pos, const double *bv0, const double *bv1, int vm,
+                              const fokl_hypers *hyp, const fokl_kill_params *kp, int32_t *out_i, double *out_ev)
+{
+    FOKL_CHECK_CTX(ctx);
+    if (!G || !Xty || !cols || !hyp || !kp || !out_i || !out_ev || p < 1 || vm < 0 || ldg < p ||
+        (vm > 0 && (!cand_pos || !bv0 || !bv1)))
+        FOKL_FAIL(ctx, FOKL_EINVAL, "kill_loop: bad argument");
+    if (kp->start < 0 || kp->start > vm) FOKL_FAIL(ctx, FOKL_EINVAL, "kill_loop: start outside the candidate list");
+    for (int i = kp->start; i < vm; ++i)
+        if (cand_pos[i] < 1 || cand_pos[i] >= p) FOKL_FAIL(ctx, FOKL_EINVAL, "kill_loop: candidate position out of range");
+    int rc = fokl_bind_device(ctx);
+    if (rc) return rc;
+    const size_t smem_cap = ctx->smem_optin ? ctx->smem_optin : 48 * 1024;
+    const int smem_t_cap = (int)(smem_cap / sizeof(double)) - 2;
+    const int64_t need = (int64_t)(p + 1) * (p + 1);
+    const bool in_smem = need <= smem_t_cap;
+
+    // metadata: cols (p ints), cand_pos (vm ints), bv0, bv1 (vm doubles each)
+    size_t off_pos = (size_t)p * sizeof(int32_t);
+    size_t off_bv = (off_pos + (size_t)vm * sizeof(int32_t) + 15) & ~(size_t)15;
+    size_t meta_bytes = off_bv + 2 * (size_t)vm * sizeof(double) + 16;
+    char *dmeta = (char *)fokl_scratch(ctx, fokl_ctx::B_META, meta_bytes);
+    if (!dmeta) return FOKL_ENOMEM;
+    std::vector<char> h(meta_bytes, 0);
+    memcpy(h.data(), cols, (size_t)p * sizeof(int32_t));
+    if (vm) {
+        memcpy(h.data() + off_pos, cand_pos, (size_t)vm * sizeof(int32_t));
+        memcpy(h.data() + off_bv, bv0, (size_t)vm * sizeof(double));
+        memcpy(h.data() + off_bv + (size_t)vm * sizeof(double), bv1, (size_t)vm * sizeof(double));
+    }
+    FOKL_CUDA(ctx, cudaMemcpyAsync(dmeta, h.data(), meta_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    double *Tg = nullptr;
+    if (!in_smem) {
+        Tg = (double *)fokl_scratch(ctx, fokl_ctx::B_CAND_A, (size_t)need * sizeof(double));
+        if (!Tg) return FOKL_ENOMEM;
+    }
+    KillLoopParams P;
+    P.G = G; P.ldg = ldg; P.Xty = Xty;
+    P.cols = reinterpret_cast<const int32_t *>(dmeta);
+    P.cand_pos = reinterpret_cast<const int32_t *>(dmeta + off_pos);
+    P.bv0 = reinterpret_cast<const double *>(dmeta + off_bv);
+    P.bv1 = P.bv0 + vm;
+    P.p = p; P.vm = vm;
+    P.c.a = hyp->a; P.c.b = hyp->b; P.c.atau = hyp->atau; P.c.btau = hyp->btau;
+    P.c.sigsqd0 = hyp->sigsqd0; P.c.tausqd0 = hyp->tausqd0; P.c.yty = hyp->yty; P.c.sum_y = hyp->sum_y;
+    P.c.n = (double)hyp->n; P.c.draws = hyp->draws; P.c.from0 = hyp->stat_from0; P.c.from1 = hyp->stat_from1;
+    P.in.threshav = kp->threshav; P.in.threshstda = kp->threshstda; P.in.threshstdb = kp->threshstdb;
+    P.in.icpt = kp->icpt; P.in.evmin = kp->evmin; P.in.aic_adj = kp->aic_adj; P.in.start = kp->start;
+    P.T_global = Tg; P.out_i = out_i; P.out_ev = out_ev;
+    P.smem_doubles = in_smem ? (int)need : 0;
+    size_t smem = (size_t)(2 + (in_smem ? need : 0)) * sizeof(double);
+    FOKL_CUDA(ctx, cudaFuncSetAttribute(kill_loop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
+    kill_loop_kernel<<<1, kKillThreads, smem, ctx->stream>>>(P);
     FOKL_LAUNCH_CHECK(ctx);
     return FOKL_OK;
 }

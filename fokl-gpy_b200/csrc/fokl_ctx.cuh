@@ -20,6 +20,8 @@ struct fokl_ctx {
     int64_t launches = 0;
     int num_sms = 148;
     size_t smem_optin = 0;
+    int max_cluster = 8;      // largest thread-block cluster the eigensolver may use (portable limit)
+    bool cluster_probed = false;
 
     // basis tables (device)
     double *cubic_tab = nullptr;

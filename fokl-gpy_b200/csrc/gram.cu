@@ -97,36 +97,56 @@ __global__ void __launch_bounds__(kGramThreads, 2) gram_kernel(const GramParams 
 #pragma unroll
         for (int b = 0; b < 2; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
 
+    // 8 x 8 output fragments this warp really has to compute: inside the (p + 1) x c block and not strictly below
+    // the diagonal of the symmetric X_new' X_new part (fokl_gram_scatter mirrors the upper triangle)
+    unsigned fmask = 0;
 #pragma unroll
-    for (int s = 0; s < STAGES - 1; ++s) {
-        if (s < nk) load_stage(s, s);
-        cp_async_commit();
-    }
-    const int frag_r = lane >> 2, frag_k = lane & 3;
-    for (int kt = 0; kt < nk; ++kt) {
-        cp_async_wait<STAGES - 2>();
-        __syncthreads();
-        {
-            int nxt = kt + STAGES - 1;
-            if (nxt < nk) load_stage(nxt, nxt % STAGES);
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+            const int i0 = ta * TM + wm * 32 + mt * 8, j0 = tb * TN + wn * 16 + nt * 8;
+            const bool has_y = (i0 <= p) && (p < i0 + 8);
+            const bool below = (i0 - P.p_old > j0 + 7) && !has_y;
+            if (i0 <= p && j0 < P.c && !below) fmask |= 1u << (mt * 2 + nt);
+        }
+    const bool cta_active = __syncthreads_or(fmask != 0);
+
+    if (cta_active) {
+#pragma unroll
+        for (int s = 0; s < STAGES - 1; ++s) {
+            if (s < nk) load_stage(s, s);
             cp_async_commit();
         }
-        const double *As = smem + (size_t)(kt % STAGES) * kStageDoubles;
-        const double *Bs = As + (size_t)TM * STRIDE;
+        const int frag_r = lane >> 2, frag_k = lane & 3;
+        for (int kt = 0; kt < nk; ++kt) {
+            cp_async_wait<STAGES - 2>();
+            __syncthreads();
+            {
+                int nxt = kt + STAGES - 1;
+                if (nxt < nk) load_stage(nxt, nxt % STAGES);
+                cp_async_commit();
+            }
+            if (fmask == 0) continue;
+            const double *As = smem + (size_t)(kt % STAGES) * kStageDoubles;
+            const double *Bs = As + (size_t)TM * STRIDE;
 #pragma unroll
-        for (int kk = 0; kk < KB / 4; ++kk) {
-            double af[4], bf[2];
+            for (int kk = 0; kk < KB / 4; ++kk) {
+                double af[4], bf[2];
 #pragma unroll
-            for (int mt = 0; mt < 4; ++mt) af[mt] = As[(wm * 32 + mt * 8 + frag_r) * STRIDE + kk * 4 + frag_k];
+                for (int mt = 0; mt < 4; ++mt)
+                    if (fmask & (3u << (mt * 2))) af[mt] = As[(wm * 32 + mt * 8 + frag_r) * STRIDE + kk * 4 + frag_k];
 #pragma unroll
-            for (int nt = 0; nt < 2; ++nt) bf[nt] = Bs[(wn * 16 + nt * 8 + frag_r) * STRIDE + kk * 4 + frag_k];
+                for (int nt = 0; nt < 2; ++nt)
+                    if (fmask & (0x55u << nt)) bf[nt] = Bs[(wn * 16 + nt * 8 + frag_r) * STRIDE + kk * 4 + frag_k];
 #pragma unroll
-            for (int mt = 0; mt < 4; ++mt)
+                for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
-                for (int nt = 0; nt < 2; ++nt) dmma_m8n8k4(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
+                    for (int nt = 0; nt < 2; ++nt)
+                        if (fmask & (1u << (mt * 2 + nt))) dmma_m8n8k4(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
+            }
         }
+        cp_async_wait<0>();
     }
-    cp_async_wait<0>();
 
     double *out = P.out + (size_t)blockIdx.y * (size_t)(p + 1) * P.c;
 #pragma unroll

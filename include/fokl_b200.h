@@ -76,7 +76,9 @@ int fokl_fill_ones(fokl_ctx *ctx, double *col, int64_t n);
 /* ---- K2: Gram / projection update, replaces XtX = X'X, Xty = X'y (FR:1492-1494) ----------------
  * Computes only what is new when columns [p_old, p_old + c) were appended to X:
  *   block[(i) * c + j] = sum_n A_i[n] * X[n][p_old + j],  i = 0 .. p_old + c   (row-major (p+1) x c)
- * where A_i = column i of X for i < p_old + c and A_{p_old+c} = y.  Deterministic summation order.   */
+ * where A_i = column i of X for i < p_old + c and A_{p_old+c} = y.  Deterministic summation order.
+ * Entries strictly below the diagonal of the symmetric X_new' X_new part (p_old + j < i < p_old + c) are optional:
+ * 8 x 8 fragments lying entirely there are skipped and read back as 0; fokl_gram_scatter mirrors the upper triangle. */
 int fokl_gram_update(fokl_ctx *ctx, const double *X, int64_t ld, int64_t n, int p_old, int c,
                      const double *y, double *block);
 
@@ -142,6 +144,27 @@ int fokl_candidates_eval(fokl_ctx *ctx, const double *G, int64_t ldg, const doub
  * positive definite (scores invalid: use fokl_candidates_eval instead). */
 int fokl_kill_scores(fokl_ctx *ctx, const double *G, int64_t ldg, const double *Xty, const int32_t *cols, int p,
                      const int32_t *props, int k, const fokl_hypers *hyp, double *ev, int32_t *info);
+
+/* The whole kill loop of one substage (FR:1666-1690) in one launch: sweep-operator inverse of the model's Gram, then
+ * for every proposal in the reference's order the BIC of the model without it, accepting the first that lowers the
+ * BIC and continuing from the next candidate against the reduced model (one O(p^2) reverse sweep per accepted kill).
+ * cols (host, p, cols[0] = intercept): the model; cand_pos (host, vm): position in cols of candidate i (candidates in
+ * ascending |mean| order, FR:1664); bv0 / bv1 (host, vm): |mean| and std/|mean| of each candidate (FR:1656-1658).
+ * kp->icpt is the |mean intercept draw| the threshold test FR:1671 uses for the whole loop (the caller verifies it
+ * against the accepted models' chains).  Outputs (dev): out_i (3 + 2 vm ints) = { accepted kills, proposals tested,
+ * error flag (1 Gram not positive definite, 2 breakdown), candidate index of each accepted kill [vm], proposals tested
+ * up to and including it [vm] }; out_ev (vm doubles) = BIC incl. aic adjustment after each accepted kill. */
+typedef struct fokl_kill_params {
+    double threshav, threshstda, threshstdb;   /* FR:1670-1671                                     */
+    double icpt;                               /* |mean(beters[h0:, 0])|                           */
+    double evmin;                              /* BIC (incl. aic adjustment) of the starting model */
+    double aic_adj;                            /* (2 - ln n) if aic else 0, per model column       */
+    int32_t start;                             /* first candidate index to consider                */
+    int32_t reserved;
+} fokl_kill_params;
+int fokl_kill_loop(fokl_ctx *ctx, const double *G, int64_t ldg, const double *Xty, const int32_t *cols, int p,
+                   const int32_t *cand_pos, const double *bv0, const double *bv1, int vm, const fokl_hypers *hyp,
+                   const fokl_kill_params *kp, int32_t *out_i, double *out_ev);
 
 /* ---- checks / "next" rows ------------------------------------------------------------------- */
 

@@ -45,6 +45,8 @@ def lib():
     L.emu_candidate.restype = _i32
     L.emu_kill_scores.argtypes = [_vp, _i64, _vp, _vp, _i32, _vp, _i32, ctypes.POINTER(EmuHypers), _vp]
     L.emu_kill_scores.restype = _i32
+    L.emu_kill_loop.argtypes = [_vp, _i64, _vp, _vp, _i32, _vp, _vp, _vp, _i32, ctypes.POINTER(EmuHypers), _vp, _i32, _vp, _vp]
+    L.emu_kill_loop.restype = _i32
     L.emu_philox_normals.argtypes = [_u64, _u64, _i32, _i32, _vp]
     L.emu_philox_normals.restype = None
     L.emu_philox_gammas.argtypes = [_u64, _u64, _i32, _f64, _vp]
@@ -120,3 +122,27 @@ def kill_scores(G, Xty, idx, props, hyp):
     bad = lib().emu_kill_scores(G.ctypes.data, G.shape[1], Xty.ctypes.data, idx.ctypes.data, len(idx),
                                 props.ctypes.data, len(props), ctypes.byref(h), ev.ctypes.data)
     return ev, bad
+
+
+def kill_loop(G, Xty, idx, cand_pos, bv0, bv1, hyp, threshav=0.05, threshstda=0.5, threshstdb=2.0, icpt=1.0,
+              evmin=0.0, aic_adj=0.0, start=0):
+    """Returns dict(n_acc, tested, bad, acc (candidate indices), calls (tested count at each acceptance), ev)."""
+    G = np.ascontiguousarray(G, dtype=np.float64)
+    Xty = np.ascontiguousarray(np.asarray(Xty).reshape(-1), dtype=np.float64)
+    idx = np.ascontiguousarray(idx, dtype=np.int32)
+    cand_pos = np.ascontiguousarray(cand_pos, dtype=np.int32)
+    bv0 = np.ascontiguousarray(bv0, dtype=np.float64)
+    bv1 = np.ascontiguousarray(bv1, dtype=np.float64)
+    vm = len(cand_pos)
+    D = int(hyp['draws'])
+    h = EmuHypers(hyp['a'], hyp['b'], hyp['atau'], hyp['btau'], hyp['sigsqd0'], hyp['tausqd0'], hyp['yty'],
+                  hyp['sum_y'], int(hyp['n']), D, int(np.ceil(D / 2)), int(np.ceil(D / 2 + 1)), 0)
+    params = np.array([threshav, threshstda, threshstdb, icpt, evmin, aic_adj], dtype=np.float64)
+    out_i = np.zeros(3 + 2 * max(vm, 1), dtype=np.int32)
+    out_ev = np.zeros(max(vm, 1))
+    bad = lib().emu_kill_loop(G.ctypes.data, G.shape[1], Xty.ctypes.data, idx.ctypes.data, len(idx), cand_pos.ctypes.data,
+                              bv0.ctypes.data, bv1.ctypes.data, vm, ctypes.byref(h), params.ctypes.data, start,
+                              out_i.ctypes.data, out_ev.ctypes.data)
+    k = int(out_i[0])
+    return dict(n_acc=k, tested=int(out_i[1]), bad=int(bad), acc=out_i[3:3 + k].copy(),
+                calls=out_i[3 + vm:3 + vm + k].copy(), ev=out_ev[:k].copy())

@@ -75,13 +75,27 @@ int emu_candidate(const double *G, int64_t ldg, const double *Xty, const int32_t
         W[e] = G[(int64_t)idx[row] * ldg + idx[col]];
     }
     const double tol = 2.220446049250313e-16 * (2.0 * sqrt((double)p) + 6.0);
-    int sweeps = jacobi_eigh(t, W.data(), V.data(), p, p, 40, tol, &flag);
-    eig_finish(t, W.data(), V.data(), p, p, lam_raw.data(), perm.data(), lamb, Q);
+    // device order: Cholesky + Jacobi on the factor; the two-matrix Jacobi only if the Gram is not positive definite
+    std::vector<double> L((size_t)p * p, 0.0);
+    for (int e = 0; e < p * p; ++e) {
+        int col = e / p, row = e - col * p;
+        if (row >= col) L[e] = W[e];
+    }
+    int sweeps;
+    int chol_failed = 0;
+    if (cholesky_lower(t, L.data(), p)) {
+        sweeps = jacobi_w_sweeps(t, L.data(), p, p, 40, tol, &flag);
+        eig_finish_w(t, L.data(), p, p, lam_raw.data(), perm.data(), lamb, Q);
+    } else {
+        chol_failed = 2;
+        sweeps = jacobi_eigh(t, W.data(), V.data(), p, p, 40, tol, &flag);
+        eig_finish(t, W.data(), V.data(), p, p, lam_raw.data(), perm.data(), lamb, Q);
+    }
     CandConst k;
     k.a = h->a; k.b = h->b; k.atau = h->atau; k.btau = h->btau; k.sigsqd0 = h->sigsqd0; k.tausqd0 = h->tausqd0;
     k.yty = h->yty; k.sum_y = h->sum_y; k.n = (double)h->n; k.draws = h->draws; k.from0 = h->from0; k.from1 = h->from1;
     *ev = ols_and_bic(t, G, ldg, Xty, idx, p, lamb, Q, k, ct.data(), betahat, scratch.data(), red.data());
-    *info = sweeps << 8;
+    *info = (sweeps << 8) | chol_failed;
     if (rng_mode == 0) return 0;
     const int D = h->draws;
     std::vector<double> gam((size_t)D * p), gg((size_t)2 * D);
@@ -114,6 +128,24 @@ int emu_kill_scores(const double *G, int64_t ldg, const double *Xty, const int32
     c.yty = h->yty; c.sum_y = h->sum_y; c.n = (double)h->n; c.draws = h->draws; c.from0 = h->from0; c.from1 = h->from1;
     return kill_scores(t, G, ldg, Xty, idx, p, props, k, c, L.data(), z.data(), beta.data(), wbuf.data(), ev_out, &flag,
                        red.data());
+}
+
+// kill_loop on the host: params = {threshav, threshstda, threshstdb, icpt, evmin, aic_adj}; returns the error flag
+int emu_kill_loop(const double *G, int64_t ldg, const double *Xty, const int32_t *idx, int p, const int32_t *cand_pos,
+                  const double *bv0, const double *bv1, int vm, const emu_hypers *h, const double *params, int start,
+                  int32_t *out_i, double *out_ev)
+{
+    Team t;
+    t.tid = 0; t.nthr = 1; t.lane = 0; t.nlane = 1; t.warp = 0; t.nwarp = 1;
+    std::vector<double> T((size_t)(p + 1) * (p + 1));
+    int sh[4];
+    CandConst c;
+    c.a = h->a; c.b = h->b; c.atau = h->atau; c.btau = h->btau; c.sigsqd0 = h->sigsqd0; c.tausqd0 = h->tausqd0;
+    c.yty = h->yty; c.sum_y = h->sum_y; c.n = (double)h->n; c.draws = h->draws; c.from0 = h->from0; c.from1 = h->from1;
+    KillLoopIn in;
+    in.threshav = params[0]; in.threshstda = params[1]; in.threshstdb = params[2]; in.icpt = params[3];
+    in.evmin = params[4]; in.aic_adj = params[5]; in.start = start;
+    return kill_loop(t, G, ldg, Xty, idx, p, cand_pos, bv0, bv1, vm, c, in, T.data(), out_i, out_ev, sh);
 }
 
 void emu_philox_normals(uint64_t seed, uint64_t stream, int draws, int p, double *out)

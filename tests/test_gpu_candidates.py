@@ -201,3 +201,104 @@ def test_kill_scores_equal_spectral_bic(engine, phis_cubic):
     dup = list(range(engine.P))
     _, ok = engine.kill_scores(dup, [1], hyp)
     assert not ok
+
+
+def test_kill_loop_kernel_matches_host_emulation(engine, phis_cubic):
+    """fokl_kill_loop (one CTA, sweep operator) against the single-thread host build of the same math, which
+    tests/test_host_emu.py pins to the literal sequential loop of the oracle."""
+    import torch
+    import emu
+    rng = np.random.default_rng(21)
+    n, m = 5000, 4
+    x = rng.random((n, m))
+    y = np.sin(2 * np.pi * x[:, 0]) + x[:, 1] * x[:, 2] + 0.1 * rng.standard_normal(n)
+    terms = np.vstack([fo.distinct_perms(p).astype(int) for p in
+                       ([1, 0, 0, 0], [1, 1, 0, 0], [2, 0, 0, 0], [2, 1, 0, 0], [1, 1, 1, 0], [2, 1, 1, 0])])
+    engine.set_phis(phis_cubic, fo.CUBIC)
+    ds = engine.upload(x, y)
+    engine.begin_fit(ds)
+    engine.append_terms(terms)
+    P = engine.P
+    G = engine.G[:P, :P].cpu().numpy()
+    Xty = engine.Xty[:P].cpu().numpy()
+    hyp = engine.make_hypers(4, 1, 4, 1, 1, 1, 10)
+    hd = dict(a=4, b=1, atau=4, btau=1, sigsqd0=1, tausqd0=1, yty=engine.yty, sum_y=engine.sum_y, n=n, draws=10)
+    for vm, aic in ((12, False), (40, True)):
+        cols = list(range(P))
+        cand = list(rng.permutation(np.arange(P - vm, P)))
+        bv0 = np.sort(rng.random(vm))
+        bv1 = rng.random(vm) * 3
+        aic_adj = (2 - np.log(n)) if aic else 0.0
+        full = float(engine.evaluate([cols], hyp).ev[0]) + aic_adj * P
+        pos = [cols.index(c) for c in cand]
+        want = emu.kill_loop(G, Xty, cols, pos, bv0, bv1, hd, threshav=0.3, icpt=2.0, evmin=full, aic_adj=aic_adj)
+        got = engine.kill_loop(cols, pos, bv0, bv1, hyp, 0.3, 0.5, 2.0, 2.0, full, aic_adj, 0)
+        assert got['bad'] == 0 and got['n_acc'] == want['n_acc'] > 0
+        assert list(got['acc']) == list(want['acc']) and list(got['calls']) == list(want['calls'])
+        assert got['tested'] == want['tested']
+        assert np.allclose(got['ev'], want['ev'], rtol=1e-12, atol=0)
+
+
+@pytest.mark.parametrize('sizes', [(1, 2, 3, 5, 31, 64), (65, 100, 128), (129, 200, 256), (300, 440), (470, 600), (700,)])
+def test_eigensolver_all_cluster_classes(engine, sizes):
+    """Cholesky + cluster Jacobi (cluster sizes 1, 2, 4, 8, 16) and the global-memory fallback against
+    scipy.linalg.eigh on the same Gram bits: eigenvalues to 1e-12 of the largest, orthonormal eigenvectors,
+    reconstruction, betahat."""
+    import torch
+    from scipy.linalg import eigh
+    rng = np.random.default_rng(sum(sizes))
+    pmax = max(sizes)
+    n = 4 * pmax + 50
+    X = rng.standard_normal((n, pmax)) * (1.0 + 3.0 * rng.random(pmax))
+    X[:, 0] = 1.0
+    y = X[:, :min(5, pmax)] @ rng.standard_normal(min(5, pmax)) + 0.1 * rng.standard_normal(n)
+    G = X.T @ X
+    Xty = X.T @ y
+    cap = max(pmax, 64)
+    engine.G = torch.zeros((cap, cap), dtype=torch.float64, device=engine.device)
+    engine.Xty = torch.zeros(cap, dtype=torch.float64, device=engine.device)
+    engine.G[:pmax, :pmax] = torch.from_numpy(G).to(engine.device)
+    engine.Xty[:pmax] = torch.from_numpy(Xty).to(engine.device)
+    engine.Gcap = cap
+    engine.n_global, engine.sum_y, engine.yty = n, float(y.sum()), float(y @ y)
+    hyp = engine.make_hypers(4, 1, 4, 1, 1, 1, 10)
+    sets = [list(range(p)) for p in sizes]
+    res = engine.evaluate(sets, hyp, want_eig=True, refine_tol=None)
+    info = res.info
+    for c, p in enumerate(sizes):
+        lam = res.lamb[res.vec_off[c]:res.vec_off[c] + p].cpu().numpy()
+        Q = res.Q[res.mat_off[c]:res.mat_off[c] + p * p].view(p, p).cpu().numpy().T      # columns = eigenvectors
+        lam_ref, _ = eigh(G[:p, :p])
+        assert (info[c] & 2) == 0, (p, info[c])          # positive definite: no Cholesky failure
+        print('eig p', p, 'info', info[c] & 7, 'sweeps', info[c] >> 8)
+        assert (info[c] >> 8) < 40
+        assert np.all(np.diff(lam) >= 0)
+        assert np.max(np.abs(lam - lam_ref)) <= 1e-12 * lam_ref[-1], p
+        assert np.max(np.abs(Q.T @ Q - np.eye(p))) < 1e-11, p
+        assert np.max(np.abs((Q * lam) @ Q.T - G[:p, :p])) <= 1e-11 * lam_ref[-1], p
+        bh = res.betahat[res.vec_off[c]:res.vec_off[c] + p].cpu().numpy()
+        bh_ref = np.linalg.solve(G[:p, :p], Xty[:p])
+        assert np.max(np.abs(bh - bh_ref)) <= 1e-8 * np.max(np.abs(bh_ref)), p
+        r = y - X[:, :p] @ bh_ref
+        ev_ref = p * np.log(n) - 2 * (-(n / 2) * np.log(np.var(r)) - (n - 1) / 2)
+        assert abs(res.ev[c] - ev_ref) <= 1e-9 * abs(ev_ref), p
+
+
+def test_eigensolver_not_positive_definite_falls_back(engine):
+    """A singular Gram (duplicated column) fails the Cholesky pre-pass and is solved by the two-matrix Jacobi."""
+    import torch
+    from scipy.linalg import eigh
+    rng = np.random.default_rng(3)
+    X = rng.standard_normal((50, 8))
+    X[:, 5] = X[:, 2]
+    G = X.T @ X
+    engine.G = torch.zeros((64, 64), dtype=torch.float64, device=engine.device)
+    engine.Xty = torch.zeros(64, dtype=torch.float64, device=engine.device)
+    engine.G[:8, :8] = torch.from_numpy(G).to(engine.device)
+    engine.Gcap = 64
+    engine.n_global, engine.sum_y, engine.yty = 50, 1.0, 60.0
+    hyp = engine.make_hypers(4, 1, 4, 1, 1, 1, 10)
+    res = engine.evaluate([list(range(8))], hyp, want_eig=True, refine_tol=None)
+    lam = res.lamb[:8].cpu().numpy()
+    lam_ref, _ = eigh(G)
+    assert np.max(np.abs(lam - lam_ref)) <= 1e-12 * lam_ref[-1]

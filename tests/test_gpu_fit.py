@@ -124,9 +124,12 @@ def test_isotherm_known_answer_trace(phis_bern):
     assert np.allclose(evs[:3], [v for _, v in QMAX_TRACE[:3]], rtol=1e-9, atol=0)
 
 
-def test_philox_fit_selects_same_terms_and_is_reproducible(phis_cubic):
+@pytest.mark.parametrize('name', ['two_way_cubic', 'way3_cubic', 'cfg1_sigmoid'])
+def test_philox_fit_selects_same_terms_and_is_reproducible(name, phis_cubic):
+    """Fast path (device kill loop + batched verification chains) == literal path (one spectral evaluation per
+    proposal), bit for bit, and repeatable."""
     from FoKL import FoKLRoutines as FR
-    g = load_golden('two_way_cubic')
+    g = load_golden(name)
     _, b1, m1, e1, info1, _ = fit_device(FR, g, phis_cubic, rng='philox')
     _, b2, m2, e2, _, _ = fit_device(FR, g, phis_cubic, rng='philox')
     assert np.array_equal(b1, b2) and np.array_equal(m1, m2) and np.array_equal(e1, e2)

@@ -120,3 +120,61 @@ def test_kill_scores_math_matches_oracle_bic(phis_cubic):
     G2[:, 2] = G2[:, 1]
     G2[2, :] = G2[1, :]
     assert emu.kill_scores(G2, Xty, np.arange(P), np.array([1]), hyp)[1] == 1
+
+
+def _literal_kill_loop(X, y, idx, cand_cols, bv0, bv1, thr, evmin, aic_adj, threshstda=0.5, threshstdb=2.0):
+    """FR:1666-1690 with one oracle `gibbs` BIC per proposal (no draws needed: BIC is draw-independent)."""
+    def bic(cols):
+        r = fo.gibbs_from_X(X[:, cols], y, 4, 1, 4, 1, 1, 1.0, 1.0, y.T.dot(y), literal=False,
+                            variates=(np.zeros((1, len(cols))), np.ones(1), np.ones(1)))
+        return r['ev'] + aic_adj * len(cols)
+    killed, acc, calls, evs, tested = [], [], [], [], 0
+    for i in range(len(cand_cols)):
+        if bv1[i] > threshstdb or (bv1[i] > threshstda and bv0[i] < thr):
+            tested += 1
+            cols = [c for c in idx if c not in killed and c != cand_cols[i]]
+            ev = bic(cols)
+            if ev < evmin:
+                killed.append(cand_cols[i]); acc.append(i); calls.append(tested); evs.append(ev); evmin = ev
+    return acc, calls, evs, tested
+
+
+@pytest.mark.parametrize('aic', [False, True])
+def test_kill_loop_matches_sequential_oracle_loop(phis_cubic, aic):
+    rng = np.random.default_rng(11)
+    n, m = 4000, 3
+    x = rng.random((n, m))
+    y = (np.sin(2 * np.pi * x[:, 0]) + x[:, 1] * x[:, 2] + 0.1 * rng.standard_normal(n))[:, None]
+    terms = np.vstack([fo.distinct_perms(p).astype(int) for p in ([1, 0, 0], [1, 1, 0], [2, 0, 0], [2, 1, 0], [1, 1, 1])])
+    X = np.hstack([np.ones((n, 1)), fo.basis_columns(x, terms, phis_cubic, fo.CUBIC)])
+    P = X.shape[1]
+    G, Xty = X.T @ X, (X.T @ y)[:, 0]
+    hyp = dict(a=4, b=1, atau=4, btau=1, sigsqd0=1, tausqd0=1, yty=float((y.T @ y)[0, 0]), sum_y=float(y.sum()), n=n,
+               draws=10)
+    idx = list(range(P))
+    vm = 10
+    cand_cols = list(rng.permutation(np.arange(P - vm, P)))       # the new terms, in "ascending |mean|" order
+    bv0 = np.sort(rng.random(vm))
+    bv1 = rng.random(vm) * 3
+    aic_adj = (2 - np.log(n)) if aic else 0.0
+    full = fo.gibbs_from_X(X, y, 4, 1, 4, 1, 1, 1.0, 1.0, y.T.dot(y), literal=False,
+                           variates=(np.zeros((1, P)), np.ones(1), np.ones(1)))['ev'] + aic_adj * P
+    icpt, threshav = 2.0, 0.3
+    acc, calls, evs, tested = _literal_kill_loop(X, y, idx, cand_cols, bv0, bv1, threshav * icpt, full, aic_adj)
+    r = emu.kill_loop(G, Xty, idx, [idx.index(c) for c in cand_cols], bv0, bv1, hyp, threshav=threshav, icpt=icpt,
+                      evmin=full, aic_adj=aic_adj)
+    assert r['bad'] == 0 and len(acc) > 0
+    assert list(r['acc']) == acc and list(r['calls']) == calls and r['tested'] == tested
+    assert np.allclose(r['ev'], evs, rtol=1e-11, atol=0)
+    # restart from the middle of the loop reproduces the tail
+    k = len(acc) // 2
+    if k:
+        killed = [cand_cols[i] for i in acc[:k]]
+        idx2 = [c for c in idx if c not in killed]
+        pos2 = [idx2.index(c) if c in idx2 else -1 for c in cand_cols]
+        r2 = emu.kill_loop(G, Xty, idx2, pos2, bv0, bv1, hyp, threshav=threshav, icpt=icpt, evmin=evs[k - 1],
+                           aic_adj=aic_adj, start=acc[k - 1] + 1)
+        assert list(r2['acc']) == acc[k:] and np.allclose(r2['ev'], evs[k:], rtol=1e-11)
+    # a duplicated column is reported, not scored
+    G2 = G.copy(); G2[:, 2] = G2[:, 1]; G2[2, :] = G2[1, :]
+    assert emu.kill_loop(G2, Xty, idx, [idx.index(c) for c in cand_cols], bv0, bv1, hyp, evmin=full)['bad'] == 1

@@ -105,6 +105,38 @@ def _merge_dicts(d1, d2):
     return d
 
 
+def _column_minmax_host(inputs):
+    """Per-column [min, max] of a host array; under torch.distributed the bounds are reduced over all ranks (every
+    rank holds a row shard of the same dataset and must normalise it identically)."""
+    mm = inputs.shape[1]
+    bounds = [[np.min(inputs[:, m]), np.max(inputs[:, m])] for m in range(mm)]
+    try:
+        import torch
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dev = torch.device('cuda', torch.cuda.current_device()) if dist.get_backend() == 'nccl' else torch.device('cpu')
+            lo = torch.tensor([b[0] for b in bounds], dtype=torch.float64, device=dev)
+            hi = torch.tensor([b[1] for b in bounds], dtype=torch.float64, device=dev)
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            bounds = [[a, b] for a, b in zip(lo.cpu().numpy(), hi.cpu().numpy())]
+    except ImportError:
+        pass
+    return bounds
+
+
+class _DeviceInputs:
+    """Normalised inputs that so far exist only in HBM (fit(clean=True) normalised them on the device).  `FoKL.inputs`
+    copies them to a host numpy array on first access, so the attribute behaves exactly like the reference's."""
+
+    def __init__(self, ds):
+        self.ds = ds
+
+    def to_numpy(self):
+        ds = self.ds
+        return np.ascontiguousarray(ds.x[:, :ds.n].t().contiguous().cpu().numpy())
+
+
 _CLEAN_DEFAULTS = {'train': 1, 'AutoTranspose': True, 'SingleInstance': False, 'bit': 64, 'normalize': True,
                    'minmax': None, 'pillow': None, 'pillow_type': 'percent'}
 
@@ -155,10 +187,40 @@ class FoKL:
             setattr(self, key, value)
         self.setnos = None
 
+    # `inputs` is stored like any other attribute (same key in __dict__ and in the pickle as the reference); the
+    # property only materialises a device-resident normalised dataset on first access.
+    @property
+    def inputs(self):
+        try:
+            v = self.__dict__['inputs']
+        except KeyError:
+            raise AttributeError("'FoKL' object has no attribute 'inputs'") from None
+        if isinstance(v, _DeviceInputs):
+            v = v.to_numpy()
+            self.__dict__['inputs'] = v
+        return v
+
+    @inputs.setter
+    def inputs(self, value):
+        self.__dict__['inputs'] = value
+
+    @inputs.deleter
+    def inputs(self):
+        try:
+            del self.__dict__['inputs']
+        except KeyError:
+            raise AttributeError('inputs') from None
+
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        if isinstance(state.get('inputs'), _DeviceInputs):
+            state['inputs'] = self.inputs
+        return state
+
     # ------------------------------------------------------------------------------------------------
     # dataset formatting (host side; FR:248-542)
     # ------------------------------------------------------------------------------------------------
-    def _format(self, inputs, data=None, AutoTranspose=True, SingleInstance=False, bit=64):
+    def _format(self, inputs, data=None, AutoTranspose=True, SingleInstance=False, bit=64, _copy=True):
         """inputs -> [n x m] ndarray, data -> [n x 1] ndarray (FR:248-316)."""
         import pandas as pd
         AutoTranspose = _str_to_bool(AutoTranspose)
@@ -181,7 +243,7 @@ class FoKL:
             warnings.warn("'data' was auto-converted to numpy. Convert manually for assured accuracy.",
                           category=UserWarning)
 
-        inputs = np.array(inputs)
+        inputs = np.array(inputs) if _copy else np.asarray(inputs)
         if inputs.ndim > 2:
             inputs = np.squeeze(inputs)
         if inputs.dtype != datatype:
@@ -216,6 +278,15 @@ class FoKL:
     def _normalize(self, inputs, minmax=None, pillow=None, pillow_type='percent'):
         """Min-max normalise the columns of `inputs` in place; updates self.minmax (FR:318-439)."""
         mm = inputs.shape[1]
+        minmax = self._normalize_bounds(mm, lambda: _column_minmax_host(inputs), minmax, pillow, pillow_type)
+        for m in range(mm):
+            inputs[:, m] = (inputs[:, m] - minmax[m][0]) / (minmax[m][1] - minmax[m][0])
+        return inputs
+
+    def _normalize_bounds(self, mm, column_minmax, minmax=None, pillow=None, pillow_type='percent'):
+        """The [min, max] pair per input that `_normalize` applies (FR:318-435): user `minmax`, else the model's, else
+        the data's (`column_minmax()` -> [[min, max], ...], evaluated only when needed), widened by `pillow`.
+        Sets self.minmax."""
         pillow_types = ['percent', 'absolute']
         if isinstance(pillow_type, str):
             pillow_type = [pillow_type] * mm
@@ -249,7 +320,7 @@ class FoKL:
             if hasattr(self, 'minmax'):
                 minmax = self.minmax
             else:
-                minmax = list([np.min(inputs[:, m]), np.max(inputs[:, m])] for m in range(mm))
+                minmax = column_minmax()
         else:
             if isinstance(minmax[0], (int, float)):
                 lm = len(minmax)
@@ -289,10 +360,7 @@ class FoKL:
                               "model will not be valid for the new bounds requested. Train a new model with these "
                               "new bounds.", category=UserWarning)
         self.minmax = minmax
-
-        for m in range(mm):
-            inputs[:, m] = (inputs[:, m] - minmax[m][0]) / (minmax[m][1] - minmax[m][0])
-        return inputs
+        return minmax
 
     def clean(self, inputs, data=None, kwargs_from_other=None, _setattr=False, **kwargs):
         """Format and (by default) normalise a dataset; see the reference for the keywords (FR:441-507):
@@ -580,6 +648,37 @@ class FoKL:
             plt.legend()
         plt.show()
 
+    def _clean_on_device(self, inputs, data, kwargs_to_clean):
+        """`clean` for `fit(clean=True)` with the normalisation (FR:373-377, 436-437) done in HBM: the raw inputs are
+        copied to the device once, per-column min / max and (x - min) / (max - min) run there (bit-identical to the
+        host expression), and `self.inputs` is materialised on the host only if somebody reads it.  Returns the
+        DeviceDataset, or None when the request needs the host path (train < 1, bit != 64, normalize=False, more
+        than 32 inputs, small datasets where the host pass is free)."""
+        current = _process_kwargs(dict(_CLEAN_DEFAULTS), dict(kwargs_to_clean))
+        if current['train'] != 1 or current['bit'] != 64 or _str_to_bool(current['normalize']) is not True:
+            return None
+        try:
+            import pandas as pd
+            if isinstance(inputs, (pd.DataFrame, pd.Series)) or isinstance(data, (pd.DataFrame, pd.Series)):
+                return None
+        except ImportError:
+            pass
+        raw = np.asarray(inputs)
+        if raw.dtype != np.float64 or np.asarray(data).dtype != np.float64 or raw.size < (1 << 20):
+            return None
+        raw, data = self._format(raw, data, current['AutoTranspose'], current['SingleInstance'], current['bit'],
+                                 _copy=False)
+        n, mm = raw.shape
+        if mm > 32 or data.shape[0] != n:
+            return None
+        eng = _engine()
+        ds = eng.upload_clean(raw, data, lambda column_minmax: self._normalize_bounds(
+            mm, column_minmax, current['minmax'], current['pillow'], current['pillow_type']))
+        self.__dict__['inputs'] = _DeviceInputs(ds)
+        self.data = data
+        self.trainlog = None
+        return ds
+
     # ------------------------------------------------------------------------------------------------
     # training hot path (FR:1202-1760)
     # ------------------------------------------------------------------------------------------------
@@ -613,7 +712,12 @@ class FoKL:
         self.ConsoleOutput = default_for_fit['ConsoleOutput']
 
         resident = isinstance(inputs, DeviceDataset)
-        if not resident:
+        ds = None
+        if not resident and default_for_fit['clean'] is True and inputs is not None and data is not None:
+            ds = self._clean_on_device(inputs, data, kwargs_to_clean)
+        if ds is not None:
+            data = self.data
+        elif not resident:
             failed = False
             if default_for_fit['clean'] is True:
                 try:
@@ -669,7 +773,7 @@ class FoKL:
         eng.set_phis(self.phis, self.kernel)
         if resident:
             ds = inputs
-        else:
+        elif ds is None:
             ds = eng.upload(inputs, data)
         eng.begin_fit(ds)
         n = eng.n_global

@@ -171,6 +171,11 @@ class Engine:
         if key == self._phis_key:
             return
         tab = np.ascontiguousarray(pack_phis(phis, kernel))
+        if getattr(self, '_phis_tab', None) is not None and self._phis_kernel == kernel and \
+                self._phis_tab.shape == tab.shape and np.array_equal(self._phis_tab, tab):
+            self._phis_key = key         # same table as the one already on the device (e.g. a second sp500() call)
+            self._phis_ref = phis
+            return
         if kernel == CUBIC:
             self._ck(self.lib.fokl_set_phis_cubic(self.ctx, tab.ctypes.data, tab.shape[0], tab.shape[1]))
             self.kernel_id = _lib.KERNEL_CUBIC
@@ -180,6 +185,7 @@ class Engine:
         else:
             raise ValueError("The kernel %r is not currently supported." % (kernel,))
         self.n_orders = tab.shape[0]
+        self._phis_tab, self._phis_kernel = tab, kernel
         self._phis_key = key
         self._phis_ref = phis   # keep alive so id() stays unique
 
@@ -197,11 +203,37 @@ class Engine:
         ldx = _round_up(max(n, 1), 16)
         x = torch.zeros((m, ldx), dtype=torch.float64, device=self.device)
         y = torch.zeros((ldx,), dtype=torch.float64, device=self.device)
-        xr = torch.from_numpy(inputs).to(self.device, non_blocking=False)
+        xr = torch.from_numpy(inputs).to(self.device, non_blocking=True)     # async DMA when the host pages are pinned
         x[:, :n].copy_(xr.t())
         y[:n].copy_(torch.from_numpy(data).to(self.device))
         self.h2d_bytes = inputs.nbytes + data.nbytes
         return DeviceDataset(x, y, n, m, ldx)
+
+    def upload_clean(self, inputs, data, resolve_minmax):
+        """Host numpy RAW inputs (N x M float64) and data -> DeviceDataset with the inputs min-max normalised in HBM.
+        resolve_minmax(column_minmax) -> [[min, max], ...] is the host policy (user bounds, pillow, warnings);
+        column_minmax() computes the data's per-column bounds on the device (reduced over all ranks)."""
+        torch = self.torch
+        ds = self.upload(inputs, data)
+        n, m = ds.n, ds.m
+
+        def column_minmax():
+            mmx = torch.empty(2 * m, dtype=torch.float64, device=self.device)
+            self._ck(self.lib.fokl_column_minmax(self.ctx, ds.x.data_ptr(), n, ds.ldx, m, mmx.data_ptr()))
+            if self.dist is not None:
+                lo, hi = mmx[0::2].contiguous(), mmx[1::2].contiguous()
+                self.dist.all_reduce(lo, op=self.dist.ReduceOp.MIN, group=self.group)
+                self.dist.all_reduce(hi, op=self.dist.ReduceOp.MAX, group=self.group)
+                mmx = torch.stack([lo, hi], dim=1).reshape(-1)
+            h = mmx.cpu().numpy()
+            return [[h[2 * k], h[2 * k + 1]] for k in range(m)]
+
+        bounds = resolve_minmax(column_minmax)
+        flat = np.ascontiguousarray(np.asarray(bounds, dtype=np.float64).reshape(-1))
+        if flat.shape[0] != 2 * m:
+            raise ValueError("Input 'minmax' must correspond to input variables (i.e., columns of 'inputs').")
+        self._ck(self.lib.fokl_normalize(self.ctx, ds.x.data_ptr(), n, ds.ldx, m, flat.ctypes.data))
+        return ds
 
     def begin_fit(self, ds):
         """Bind a dataset; allocate X (ones column) and the Gram state; compute the data moments."""

@@ -8,7 +8,9 @@
 //            shared memory F[factor][row] -- coefficient tables of the orders in use are staged in shared
 //            memory (cubic: [slot][piece][4], one 32-byte gather per factor; Bernoulli: whole table);
 //   phase 2: forms each term's product (increasing input index, like FR:1466-1483) from F and streams it to
-//            the column-major design matrix with coalesced 16-byte stores (2 adjacent rows per thread).
+//            the column-major design matrix with coalesced 16-byte stores (2 adjacent rows per thread).  Every term
+//            is padded to NF factors with a row of ones (x * 1.0 is exact), so the loop body is branch-free:
+//            one 8-byte metadata word, NF 16-byte shared loads, 2 (NF - 1) DMUL, one 16-byte streaming store.
 // HBM traffic = read N*M inputs once + write N*C outputs: 8*N*(M + C) bytes -- the kernel's roofline.
 #include "fokl_ctx.cuh"
 #include "fokl_math.cuh"
@@ -30,9 +32,8 @@ struct FactorMeta {          // one distinct (input, order) pair
     int16_t pad;
 };
 
-struct alignas(8) TermMeta {  // one output column (read by the kernel as one packed 64-bit word)
-    uint8_t cnt;             // number of factors (0 -> constant 1)
-    uint8_t f[kMaxTermFactors];
+struct alignas(8) TermMeta {  // one output column, read by the kernel as one packed 64-bit word:
+    uint8_t f[8];             // factor slots in increasing input order, padded with the "ones" slot (index n_factors)
 };
 
 struct BasisParams {
@@ -73,18 +74,18 @@ __device__ __forceinline__ double eval_factor_bernoulli(const double *c, int n_c
     return __dadd_rn(c[0], s);
 }
 
-template <int KERNEL, int RPT>
+template <int KERNEL, int RPT, int NF>
 __global__ void __launch_bounds__(kThreads) basis_kernel(const BasisParams P)
 {
     constexpr int ROWS = kThreads * RPT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // layout: [staged table][F: n_factors * ROWS doubles][factors][terms]
+    // layout: [staged table][F: (n_factors + 1) * ROWS doubles, last row = ones][factors][terms]
     double *s_tab = reinterpret_cast<double *>(smem_raw);
     size_t tab_doubles = (KERNEL == FOKL_KERNEL_CUBIC) ? (size_t)P.n_slots * P.n_piece * 4
                                                        : (size_t)P.n_slots * P.n_piece;
     tab_doubles = (tab_doubles + 1) & ~(size_t)1;   // keep F 16-byte aligned
     double *s_F = s_tab + tab_doubles;
-    FactorMeta *s_fac = reinterpret_cast<FactorMeta *>(s_F + (size_t)P.n_factors * ROWS);
+    FactorMeta *s_fac = reinterpret_cast<FactorMeta *>(s_F + (size_t)(P.n_factors + 1) * ROWS);
     TermMeta *s_term = reinterpret_cast<TermMeta *>(s_fac + P.n_factors);
     const unsigned long long *s_term64 = reinterpret_cast<const unsigned long long *>(s_term);
 
@@ -103,6 +104,7 @@ __global__ void __launch_bounds__(kThreads) basis_kernel(const BasisParams P)
             for (int e = tid; e < per; e += kThreads) s_tab[(size_t)s * per + e] = __ldg(src + e);
         }
     }
+    for (int e = tid; e < ROWS; e += kThreads) s_F[(size_t)P.n_factors * ROWS + e] = 1.0;
     for (int f = tid; f < P.n_factors; f += kThreads) s_fac[f] = P.factors[f];
     for (int j = tid; j < P.n_terms; j += kThreads) s_term[j] = P.terms[j];
     __syncthreads();
@@ -172,54 +174,44 @@ __global__ void __launch_bounds__(kThreads) basis_kernel(const BasisParams P)
         }
         __syncthreads();
         // ---- phase 2: products, streamed to HBM -----------------------------------------------------
-        // (term metadata is read as one packed 64-bit word: byte 0 = factor count, bytes 1..7 = factor slots --
-        //  indexing a byte array of a struct copy would force it into local memory)
         {
-            double pre[RPT];
-#pragma unroll
-            for (int r = 0; r < RPT; ++r) pre[r] = 1.0;
-            unsigned pf01 = 0xffffffffu;
+            constexpr int kShift = (RPT == 2) ? 12 : 11;       // log2(ROWS * sizeof(double))
             const bool full = (row0 + RPT - 1 < P.n);
-            const double *Fme = s_F + tid * RPT;
+            const unsigned char *Fb = reinterpret_cast<const unsigned char *>(s_F + tid * RPT);
             double *dst = P.out + row0;
-            for (int j = 0; j < P.n_terms; ++j, dst += P.ld) {
+            const int nt = P.n_terms;
+            auto product = [&](int j, double (&v)[RPT]) {
                 const unsigned long long w = s_term64[j];
-                const int cnt = (int)(w & 0xffu);
-                double v[RPT];
-                if (cnt == 0) {
-#pragma unroll
-                    for (int r = 0; r < RPT; ++r) v[r] = 1.0;
+                const double *a = reinterpret_cast<const double *>(Fb + ((size_t)(w & 0xffu) << kShift));
+                if (RPT == 2) {
+                    const double2 t2 = *reinterpret_cast<const double2 *>(a);
+                    v[0] = t2.x; v[RPT - 1] = t2.y;
                 } else {
-                    const unsigned f01 = (unsigned)(w >> 8) & 0xffffu;
-                    int start;
-                    if (cnt >= 3 && f01 == pf01) {
-                        start = 2;   // reuse (b0 * b1) from the previous term: same rounding, fewer LDS
+                    v[0] = a[0];
+                }
+#pragma unroll
+                for (int q = 1; q < NF; ++q) {
+                    const double *b = reinterpret_cast<const double *>(Fb + ((size_t)((w >> (8 * q)) & 0xffu) << kShift));
+                    if (RPT == 2) {
+                        const double2 t2 = *reinterpret_cast<const double2 *>(b);
+                        v[0] = __dmul_rn(v[0], t2.x); v[RPT - 1] = __dmul_rn(v[RPT - 1], t2.y);
                     } else {
-                        const double *a = Fme + (size_t)(f01 & 0xffu) * ROWS;
-#pragma unroll
-                        for (int r = 0; r < RPT; ++r) pre[r] = a[r];
-                        start = 1;
-                        pf01 = 0xffffffffu;
-                        if (cnt >= 3) {
-                            const double *b = Fme + (size_t)(f01 >> 8) * ROWS;
-#pragma unroll
-                            for (int r = 0; r < RPT; ++r) pre[r] = __dmul_rn(pre[r], b[r]);
-                            start = 2;
-                            pf01 = f01;
-                        }
-                    }
-#pragma unroll
-                    for (int r = 0; r < RPT; ++r) v[r] = pre[r];
-                    unsigned long long rest = w >> (8 * (start + 1));
-                    for (int q = start; q < cnt; ++q, rest >>= 8) {
-                        const double *b = Fme + (size_t)(rest & 0xffu) * ROWS;
-#pragma unroll
-                        for (int r = 0; r < RPT; ++r) v[r] = __dmul_rn(v[r], b[r]);
+                        v[0] = __dmul_rn(v[0], b[0]);
                     }
                 }
-                if (RPT == 2 && full) {
-                    __stcs(reinterpret_cast<double2 *>(dst), make_double2(v[0], v[RPT - 1]));
-                } else {
+            };
+            if (full) {
+#pragma unroll 4
+                for (int j = 0; j < nt; ++j, dst += P.ld) {
+                    double v[RPT];
+                    product(j, v);
+                    if (RPT == 2) __stcs(reinterpret_cast<double2 *>(dst), make_double2(v[0], v[RPT - 1]));
+                    else __stcs(dst, v[0]);
+                }
+            } else {
+                for (int j = 0; j < nt; ++j, dst += P.ld) {
+                    double v[RPT];
+                    product(j, v);
 #pragma unroll
                     for (int r = 0; r < RPT; ++r)
                         if (row0 + r < P.n) __stcs(dst + r, v[r]);
@@ -235,6 +227,7 @@ struct LaunchPlan {
     std::vector<TermMeta> terms;
     std::vector<int16_t> slot_order;
     int first_term = 0;
+    int max_cnt = 0;
 };
 
 }  // namespace
@@ -282,8 +275,8 @@ extern "C" int fokl_basis_build(fokl_ctx *ctx, int kernel, const double *x, int6
             if (cnt > kMaxTermFactors) FOKL_FAIL(ctx, FOKL_EINVAL, "basis_build: more than 7 interacting inputs in a term");
             if ((int)cur.factors.size() + need_new > kMaxFactors || (int)cur.terms.size() >= kMaxTermsPerLaunch) flush();
             TermMeta tm;
-            tm.cnt = 0;
-            for (int q = 0; q < kMaxTermFactors; ++q) tm.f[q] = 0;
+            int filled = 0;
+            for (int q = 0; q < 8; ++q) tm.f[q] = 0xff;           // 0xff = "ones" slot, patched per launch below
             for (int k = 0; k < m; ++k) {
                 int d = row[k];
                 if (d == 0) continue;
@@ -294,8 +287,9 @@ extern "C" int fokl_basis_build(fokl_ctx *ctx, int kernel, const double *x, int6
                     fm.k = (int16_t)k; fm.d = (int16_t)d; fm.slot = -1; fm.pad = 0;
                     cur.factors.push_back(fm);
                 }
-                tm.f[tm.cnt++] = (uint8_t)fi;
+                tm.f[filled++] = (uint8_t)fi;
             }
+            cur.max_cnt = std::max(cur.max_cnt, filled);
             cur.terms.push_back(tm);
         }
         flush();
@@ -316,7 +310,7 @@ extern "C" int fokl_basis_build(fokl_ctx *ctx, int kernel, const double *x, int6
         std::vector<FactorMeta> sorted(nf);
         for (int i = 0; i < nf; ++i) { sorted[i] = pl.factors[order[i]]; inv[order[i]] = i; }
         for (TermMeta &tm : pl.terms)
-            for (int q = 0; q < tm.cnt; ++q) tm.f[q] = (uint8_t)inv[tm.f[q]];
+            for (int q = 0; q < 8; ++q) tm.f[q] = (tm.f[q] == 0xff) ? (uint8_t)nf : (uint8_t)inv[tm.f[q]];
         // staged-table slots: distinct orders, as many as fit next to F
         std::vector<int16_t> orders;
         for (const FactorMeta &fm : sorted)
@@ -326,7 +320,7 @@ extern "C" int fokl_basis_build(fokl_ctx *ctx, int kernel, const double *x, int6
         const int nt = (int)pl.terms.size();
         auto smem_need = [&](int rpt, int nslots) {
             size_t tab_bytes = ((nslots * per_slot / sizeof(double) + 1) & ~(size_t)1) * sizeof(double);
-            return tab_bytes + (size_t)nf * kThreads * rpt * sizeof(double) + (size_t)nf * sizeof(FactorMeta) +
+            return tab_bytes + (size_t)(nf + 1) * kThreads * rpt * sizeof(double) + (size_t)nf * sizeof(FactorMeta) +
                    (size_t)nt * sizeof(TermMeta) + 16;
         };
         int rpt = aligned2 ? 2 : 1;
@@ -369,8 +363,12 @@ extern "C" int fokl_basis_build(fokl_ctx *ctx, int kernel, const double *x, int6
         const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, smem_cap / std::max<size_t>(smem, 1)));
         int grid = (int)std::min<int64_t>(P.n_tiles, (int64_t)ctx->num_sms * ctas_per_sm);
         void (*kern)(const BasisParams) = nullptr;
-        if (kernel == FOKL_KERNEL_CUBIC) kern = rpt == 2 ? basis_kernel<FOKL_KERNEL_CUBIC, 2> : basis_kernel<FOKL_KERNEL_CUBIC, 1>;
-        else kern = rpt == 2 ? basis_kernel<FOKL_KERNEL_BERNOULLI, 2> : basis_kernel<FOKL_KERNEL_BERNOULLI, 1>;
+        const int nfc = pl.max_cnt <= 1 ? 1 : (pl.max_cnt == 2 ? 2 : (pl.max_cnt == 3 ? 3 : 7));
+#define FOKL_PICK(K, R)                                                                                               \
+    (nfc == 1 ? basis_kernel<K, R, 1> : nfc == 2 ? basis_kernel<K, R, 2> : nfc == 3 ? basis_kernel<K, R, 3> : basis_kernel<K, R, 7>)
+        if (kernel == FOKL_KERNEL_CUBIC) kern = rpt == 2 ? FOKL_PICK(FOKL_KERNEL_CUBIC, 2) : FOKL_PICK(FOKL_KERNEL_CUBIC, 1);
+        else kern = rpt == 2 ? FOKL_PICK(FOKL_KERNEL_BERNOULLI, 2) : FOKL_PICK(FOKL_KERNEL_BERNOULLI, 1);
+#undef FOKL_PICK
         FOKL_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
         kern<<<grid, kThreads, smem, ctx->stream>>>(P);
         FOKL_LAUNCH_CHECK(ctx);

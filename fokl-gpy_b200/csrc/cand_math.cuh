@@ -191,8 +191,11 @@ FOKL_HD bool cholesky_lower(const Team &t, double *L, int p)
     return ok;
 }
 
-// Orthogonalise columns wi, wj (length p).  One warp per pair.
-FOKL_HD bool jacobi_pair_w(const Team &t, double *wi, double *wj, int p, double tol)
+// Orthogonalise columns wi, wj (length p); the rotated columns go to wi_out / wj_out (either may alias its input;
+// a column whose output differs from its input is copied there even when no rotation is needed, together with the
+// `extra` trailing elements that travel with it).  One warp per pair.
+FOKL_HD bool jacobi_pair_w(const Team &t, const double *wi, const double *wj, double *wi_out, double *wj_out, int p,
+                           int extra, double tol)
 {
     double al = 0.0, be = 0.0, ga = 0.0;
     for (int e = t.lane; e < p; e += t.nlane) {
@@ -202,17 +205,35 @@ FOKL_HD bool jacobi_pair_w(const Team &t, double *wi, double *wj, int p, double 
         ga += a * b;
     }
     warp_sum3(t, al, be, ga);
-    if (!(fabs(ga) > tol * sqrt(al * be))) return false;
-    double zeta = (be - al) / (2.0 * ga);
-    double tt = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-    double c = 1.0 / sqrt(1.0 + tt * tt);
-    double s = c * tt;
-    for (int e = t.lane; e < p; e += t.nlane) {
-        double a = wi[e], b = wj[e];
-        wi[e] = c * a - s * b;
-        wj[e] = s * a + c * b;
+    const bool rot = fabs(ga) > tol * sqrt(al * be);
+    if (rot) {
+        // tan(theta) = 2 ga / (d + sign(d) sqrt(d^2 + 4 ga^2)), d = |wj|^2 - |wi|^2 (the smaller root), one sqrt, one
+        // division, one reciprocal square root on the critical path
+        const double d = be - al;
+        const double r = sqrt(d * d + 4.0 * ga * ga);
+        const double tt = (2.0 * ga) / (d + copysign(r, d));
+#if defined(__CUDA_ARCH__)
+        const double c = rsqrt(1.0 + tt * tt);
+#else
+        const double c = 1.0 / sqrt(1.0 + tt * tt);
+#endif
+        const double s = c * tt;
+        for (int e = t.lane; e < p; e += t.nlane) {
+            double a = wi[e], b = wj[e];
+            wi_out[e] = c * a - s * b;
+            wj_out[e] = s * a + c * b;
+        }
+        if (wi_out != wi)
+            for (int e = p + t.lane; e < p + extra; e += t.nlane) wi_out[e] = wi[e];
+        if (wj_out != wj)
+            for (int e = p + t.lane; e < p + extra; e += t.nlane) wj_out[e] = wj[e];
+    } else {
+        if (wi_out != wi)
+            for (int e = t.lane; e < p + extra; e += t.nlane) wi_out[e] = wi[e];
+        if (wj_out != wj)
+            for (int e = t.lane; e < p + extra; e += t.nlane) wj_out[e] = wj[e];
     }
-    return true;
+    return rot;
 }
 
 // Single-team driver (host emulation and reference for the cluster kernel): W (in: L, column-major ld) is rotated
@@ -233,7 +254,8 @@ FOKL_HD int jacobi_w_sweeps(const Team &t, double *W, int p, int ld, int max_swe
                 else { i = (r + k) % nm1; j = (r - k + nm1) % nm1; }
                 if (i > j) { int q = i; i = j; j = q; }
                 if (j >= p) continue;
-                bool rot = jacobi_pair_w(t, W + (int64_t)i * ld, W + (int64_t)j * ld, p, tol);
+                double *wi = W + (int64_t)i * ld, *wj = W + (int64_t)j * ld;
+                bool rot = jacobi_pair_w(t, wi, wj, wi, wj, p, 0, tol);
                 if (rot && t.lane == 0) *flag = 1;
             }
             t.sync();
@@ -331,68 +353,112 @@ FOKL_HD double ols_and_bic(const Team &t, const double *G, int64_t ldg, const do
     return (double)p * log(k.n) - 2.0 * lik;
 }
 
-struct ChainRng {
-    int mode;                 // FOKL_RNG_INJECTED = 1, FOKL_RNG_PHILOX = 2
-    const double *variates;   // injected: D rows of [z(p), g1, g2]
-    const double *sign_fix;   // optional p
-    Philox philox;
-    uint32_t stream_lo, stream_hi;
-    double *gg;               // philox: scratch D x 2 pre-generated standard gammas
-};
+// One variate of the free-running stream of a `gibbs` call: row d of the chain consumes normal(p), then
+// standard_gamma(astar), standard_gamma(atau_star) -- the order of FR:1527, 1541, 1547.  Counter-based, so the
+// D x (p + 2) table can be filled by any number of threads in any order (cand_variates_kernel) and the chain
+// itself only streams it.
+FOKL_HD double philox_variate(const Philox &g, uint32_t stream_lo, uint32_t stream_hi, int d, int e, int p,
+                              double astar, double atau_star)
+{
+    if (e < p) return philox_normal(g, stream_lo, stream_hi, (uint32_t)d, (uint32_t)e);
+    if (e == p) return philox_gamma(g, stream_lo, stream_hi, (uint32_t)d, 0u, astar);
+    return philox_gamma(g, stream_lo, stream_hi, (uint32_t)d, 1024u, atau_star);
+}
+
+FOKL_HD double chain_astar(const CandConst &k, int p) { return k.a + 1.0 + k.n / 2.0 + (double)p / 2.0; }
+FOKL_HD double chain_atau_star(const CandConst &k, int p) { return k.atau + (double)(p - 1) / 2.0; }
+
+#if defined(__CUDA_ARCH__)
+#define FOKL_RCP(x) __drcp_rn(x)
+#define FOKL_RSQRT(x) rsqrt(x)
+#else
+#define FOKL_RCP(x) (1.0 / (x))
+#define FOKL_RSQRT(x) (1.0 / sqrt(x))
+#endif
 
 // The draw loop of FR:1519-1548 in the eigenbasis (gamma = Q' beta):
 //   d_j = 1/(lamb_j + 1/tau^2);  gamma_j = d_j ct_j + sqrt(sig^2) sqrt(d_j) z_j
 //   bstar = b + 0.5 (sum lamb gamma^2 - 2 sum gamma ct + yty + sum gamma^2 / tau^2)
 //   sig^2 = 1 / ((1/bstar) G1);  btau* = (1/(2 sig^2)) sum gamma^2 + btau;  tau^2 = 1 / ((1/btau*) G2)
+// The D draws are strictly sequential, so the loop is arranged around its dependent chain: the state carried from
+// draw to draw is (sqrt(sig^2), 1/tau^2); sig^2 = bstar / G1 and tau^2 = btau* / G2 are formed with the reciprocals
+// of the (prefetched) gamma variates, 1/(2 sig^2) = G1 / (2 bstar), and sqrt(d_j) is one rsqrt -- two reciprocals and
+// one rsqrt on the critical path per draw instead of seven divisions and two square roots (same values to a few ulp).
+// variates: D rows of [z_0 .. z_{p-1}, G1, G2] (injected numpy stream or the Philox table); sign_fix optional (p).
 // gam (out) D x p row-major, sigs/taus (out) D.  Returns 1 if bstar < 0 was seen.
 FOKL_HD int gibbs_chain(const Team &t, int p, const double *lamb, const double *ct, const CandConst &k,
-                        const ChainRng &rng, double *gam, double *sigs, double *taus, double *red)
+                        const double *variates, const double *sign_fix, double *gam, double *sigs, double *taus,
+                        double *red)
 {
     const int D = k.draws;
-    const double astar = k.a + 1.0 + k.n / 2.0 + (double)p / 2.0;
-    const double atau_star = k.atau + (double)(p - 1) / 2.0;
-    if (rng.mode == 2) {
-        for (int d = t.tid; d < D; d += t.nthr) {
-            rng.gg[2 * d + 0] = philox_gamma(rng.philox, rng.stream_lo, rng.stream_hi, (uint32_t)d, 0u, astar);
-            rng.gg[2 * d + 1] = philox_gamma(rng.philox, rng.stream_lo, rng.stream_hi, (uint32_t)d, 1024u,
-                                             atau_star);
-        }
-        t.sync();
-    }
-    double sig = k.sigsqd0, tau = k.tausqd0;
+    const int w = p + 2;
+    double ssig = sqrt(k.sigsqd0), itau = 1.0 / k.tausqd0;
     int bad = 0;
+    // each thread owns elements e = tid, tid + nthr, ...; the first two are kept in registers, next row prefetched
+    const int e0 = t.tid, e1 = t.tid + t.nthr;
+    const bool h0 = e0 < p, h1 = e1 < p;
+    double l0 = 0.0, c0 = 0.0, f0 = 1.0, l1 = 0.0, c1 = 0.0, f1 = 1.0;
+    if (h0) { l0 = lamb[e0]; c0 = ct[e0]; if (sign_fix) f0 = sign_fix[e0]; }
+    if (h1) { l1 = lamb[e1]; c1 = ct[e1]; if (sign_fix) f1 = sign_fix[e1]; }
+    // software pipeline over the variate table, two rows deep: warps issue in order, so a value loaded in iteration
+    // d - 1 is first touched in iteration d (row d + 1 is only *loaded* while row d is being used)
+    double z0 = h0 ? f0 * variates[e0] : 0.0, z1 = h1 ? f1 * variates[e1] : 0.0;
+    double g1 = variates[p], g2 = variates[p + 1];
+    double ig1 = 1.0 / g1, ig2 = 1.0 / g2;
+    double zr0 = 0.0, zr1 = 0.0, gr1 = 1.0, gr2 = 1.0;              // raw row d + 1
+    if (D > 1) {
+        const double *r1 = variates + w;
+        if (h0) zr0 = r1[e0];
+        if (h1) zr1 = r1[e1];
+        gr1 = r1[p];
+        gr2 = r1[p + 1];
+    }
     for (int d = 0; d < D; ++d) {
-        const double itau = 1.0 / tau;
-        const double ssig = sqrt(sig);
+        const double *row = variates + (int64_t)d * w;
+        double zq0 = 0.0, zq1 = 0.0, gq1 = 1.0, gq2 = 1.0;          // raw row d + 2 (in flight during this iteration)
+        if (d + 2 < D) {
+            const double *r2 = row + 2 * w;
+            if (h0) zq0 = r2[e0];
+            if (h1) zq1 = r2[e1];
+            gq1 = r2[p];
+            gq2 = r2[p + 1];
+        }
         double s1 = 0.0, s2 = 0.0, s3 = 0.0;
-        for (int e = t.tid; e < p; e += t.nthr) {
-            double z;
-            if (rng.mode == 1) z = rng.variates[(int64_t)d * (p + 2) + e];
-            else z = philox_normal(rng.philox, rng.stream_lo, rng.stream_hi, (uint32_t)d, (uint32_t)e);
-            if (rng.sign_fix) z *= rng.sign_fix[e];
+        if (h0) {
+            double rs = FOKL_RSQRT(l0 + itau);
+            double g = (rs * rs) * c0 + (ssig * rs) * z0;
+            gam[(int64_t)d * p + e0] = g;
+            s1 += l0 * g * g; s2 += g * c0; s3 += g * g;
+        }
+        if (h1) {
+            double rs = FOKL_RSQRT(l1 + itau);
+            double g = (rs * rs) * c1 + (ssig * rs) * z1;
+            gam[(int64_t)d * p + e1] = g;
+            s1 += l1 * g * g; s2 += g * c1; s3 += g * g;
+        }
+        for (int e = t.tid + 2 * t.nthr; e < p; e += t.nthr) {
+            double z = row[e];
+            if (sign_fix) z *= sign_fix[e];
             double l = lamb[e], c = ct[e];
-            double dj = 1.0 / (l + itau);
-            double g = dj * c + ssig * sqrt(dj) * z;
+            double rs = FOKL_RSQRT(l + itau);
+            double g = (rs * rs) * c + (ssig * rs) * z;
             gam[(int64_t)d * p + e] = g;
-            s1 += l * g * g;
-            s2 += g * c;
-            s3 += g * g;
+            s1 += l * g * g; s2 += g * c; s3 += g * g;
         }
+        // next row's values (loaded one iteration ago): off the critical path, overlaps the reduction
+        const double zn0 = f0 * zr0, zn1 = f1 * zr1;
+        const double ign1 = 1.0 / gr1, ign2 = 1.0 / gr2;
         team_sum3(t, s1, s2, s3, red, d & 1);
-        double g1, g2;
-        if (rng.mode == 1) {
-            g1 = rng.variates[(int64_t)d * (p + 2) + p];
-            g2 = rng.variates[(int64_t)d * (p + 2) + p + 1];
-        } else {
-            g1 = rng.gg[2 * d];
-            g2 = rng.gg[2 * d + 1];
-        }
-        double bstar = k.b + 0.5 * (s1 - 2.0 * s2 + k.yty + s3 / tau);
-        if (bstar < 0.0) { sig = nan(""); bad = 1; }
-        else sig = 1.0 / ((1.0 / bstar) * g1);
-        double btau_star = (1.0 / (2.0 * sig)) * s3 + k.btau;
-        tau = 1.0 / ((1.0 / btau_star) * g2);
-        if (t.tid == 0) { sigs[d] = sig; taus[d] = tau; }
+        const double bstar = k.b + 0.5 * (s1 - 2.0 * s2 + k.yty + s3 * itau);
+        double sig, rb;
+        if (bstar < 0.0) { sig = nan(""); rb = sig; bad = 1; }
+        else { sig = bstar * ig1; rb = FOKL_RCP(bstar); }
+        const double btau_star = (0.5 * g1 * rb) * s3 + k.btau;
+        itau = g2 * FOKL_RCP(btau_star);
+        ssig = sqrt(sig);
+        if (t.tid == 0) { sigs[d] = sig; taus[d] = btau_star * ig2; }
+        z0 = zn0; z1 = zn1; g1 = gr1; g2 = gr2; ig1 = ign1; ig2 = ign2;
+        zr0 = zq0; zr1 = zq1; gr1 = gq1; gr2 = gq2;
     }
     return bad;
 }

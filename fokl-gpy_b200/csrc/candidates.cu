@@ -16,11 +16,10 @@
 namespace {
 
 using fokl::CandConst;
-using fokl::ChainRng;
 using fokl::Team;
 
 constexpr int kEigThreads = 256;
-constexpr int kChainThreads = 128;
+constexpr int kChainThreads = 256;      // upper bound; launched with ~p/2 threads (two elements per thread in registers)
 constexpr int kSmemHeaderDoubles = 64;   // reduction scratch (2*3*8) + flag
 
 struct CandMeta {
@@ -141,7 +140,8 @@ __global__ void __launch_bounds__(kCholThreads) cand_chol_kernel(const CholParam
 // fixed): inside a CTA that is an index rotation, and only the two columns that cross a CTA boundary travel, pushed
 // into the neighbour's staging buffer through distributed shared memory, one cluster barrier per round.  n - 1 rounds
 // visit every pair once (a sweep); sweeps repeat until no pair needed a rotation.
-constexpr int kEigJThreads = 1024;
+constexpr int kEigJThreads = 512;       // <= 16 column pairs per CTA in flight, 128 registers per thread
+constexpr int kEigJMaxNV = 11;          // double2 per lane per column: p <= 64 * 11 = 704
 constexpr int kEigJMaxCluster = 16;
 constexpr int kEigJHeaderDoubles = 256;   // team_sum3 scratch: 2 * 3 * 32 warps
 
@@ -161,50 +161,194 @@ struct EigJParams {
 
 __host__ __device__ inline int eigj_padded_n(int p, int cs)
 {
+    if (cs == 1) return (p + 1) & ~1;
     const int unit = 2 * cs;
     int n = ((p + unit - 1) / unit) * unit;
     if (n < 4 * cs) n = 4 * cs;        // at least two pair slots per CTA (the ring needs a rotating top slot in CTA 0)
     return n;
 }
-__host__ __device__ inline int eigj_ld(int p) { return (p + 2) & ~1; }   // column + tag slot, even
+__host__ __device__ inline int eigj_ld(int p) { return (p + 1) & ~1; }   // even: columns are moved as double2
+__host__ __device__ inline int eigj_slots(int p, int cs)                // column buffers per CTA
+{
+    const int n = eigj_padded_n(p, cs);
+    return cs == 1 ? n : 2 * (n / (2 * cs) + 1);                         // cs > 1: m + 1 top and m + 1 bottom (one spare each)
+}
 __host__ __device__ inline size_t eigj_smem_bytes(int p, int cs)
 {
-    const int m = eigj_padded_n(p, cs) / (2 * cs);
-    return (size_t)(2 * m + 4) * eigj_ld(p) * sizeof(double) + (size_t)(2 * m + 2 * kEigJMaxCluster + 8) * sizeof(int) +
+    return (size_t)eigj_slots(p, cs) * (eigj_ld(p) + 1) * sizeof(double) + (size_t)(2 * kEigJMaxCluster + 8) * sizeof(int) +
            kEigJHeaderDoubles * sizeof(double);
 }
-
-// one warp shifts the logical -> physical slot table by one position (all reads before any write)
-constexpr int kEigJMaxSlotsPerLane = 8;     // m <= 256
-__device__ __forceinline__ void rotate_top(int *slots, int m, int first, int incoming, int lane)
+__host__ __device__ inline int eigj_threads(int p, int cs)
 {
-    int v[kEigJMaxSlotsPerLane];
-#pragma unroll
-    for (int q = 0; q < kEigJMaxSlotsPerLane; ++q) {
-        const int k = lane + 32 * q;
-        if (k < m) v[q] = (k > first) ? slots[k - 1] : (k == first ? incoming : slots[k]);
-    }
-    __syncwarp();
-#pragma unroll
-    for (int q = 0; q < kEigJMaxSlotsPerLane; ++q) {
-        const int k = lane + 32 * q;
-        if (k < m) slots[k] = v[q];
-    }
+    const int pairs = eigj_padded_n(p, cs) / (2 * cs);
+    int w = pairs < 1 ? 1 : (pairs > kEigJThreads / 32 ? kEigJThreads / 32 : pairs);
+    if (w < 4) w = 4;                                                      // ols_and_bic / ranking like a few warps
+    return 32 * w;
 }
-__device__ __forceinline__ void rotate_bot(int *slots, int m, int incoming, int lane)
+
+// Physical slot of a logical position (cluster layout, cs > 1) from the running round counters rt = round mod (m+1),
+// r0 = round mod m.  Every row keeps one spare slot: the column that leaves a CTA is written by the rotating warp
+// straight into the *spare* slot of its destination row (possibly in the neighbouring CTA, through distributed shared
+// memory), and the slot it vacates is the next spare.
+struct RingLayout {
+    int m, cr, rt, r0;
+    __device__ __forceinline__ static int wrap_neg(int x, int mod) { return x < 0 ? x + mod : x; }
+    __device__ __forceinline__ static int wrap_pos(int x, int mod) { return x >= mod ? x - mod : x; }
+    __device__ __forceinline__ int top(int k) const
+    {
+        if (cr == 0) return k == 0 ? m : wrap_neg(k - 1 - r0, m);         // CTA 0: logical 0 is the fixed player (slot m)
+        return wrap_neg(k - rt, m + 1);
+    }
+    __device__ __forceinline__ int top_spare(int c) const { return c == 0 ? wrap_neg(m - 1 - r0, m) : wrap_neg(m - rt, m + 1); }
+    __device__ __forceinline__ int bot(int k) const { return (m + 1) + wrap_pos(k + rt, m + 1); }
+    __device__ __forceinline__ int bot_spare() const { return (m + 1) + wrap_pos(m + rt, m + 1); }
+    __device__ __forceinline__ void advance()
+    {
+        rt = (rt + 1 == m + 1) ? 0 : rt + 1;
+        r0 = (r0 + 1 == m) ? 0 : r0 + 1;
+    }
+};
+
+// One warp orthogonalises a pair of columns.  Both columns are loaded once into registers (NV double2 per lane), the
+// three inner products, the rotation and the stores work from there; a column whose destination differs from its
+// source (it leaves this CTA's row) is written there whether or not a rotation was needed.
+template <int NV>
+__device__ __forceinline__ bool pair_rotate_reg(const double *a, const double *b, double *a_out, double *b_out, int nv2,
+                                                double tol, int lane)
 {
-    int v[kEigJMaxSlotsPerLane];
+    const double2 *a2 = reinterpret_cast<const double2 *>(a), *b2 = reinterpret_cast<const double2 *>(b);
+    double2 av[NV], bv[NV];
 #pragma unroll
-    for (int q = 0; q < kEigJMaxSlotsPerLane; ++q) {
-        const int k = lane + 32 * q;
-        if (k < m) v[q] = (k < m - 1) ? slots[k + 1] : incoming;
+    for (int q = 0; q < NV; ++q) {
+        const int i = lane + 32 * q;
+        if (i < nv2) { av[q] = a2[i]; bv[q] = b2[i]; }
+        else { av[q] = make_double2(0.0, 0.0); bv[q] = make_double2(0.0, 0.0); }
     }
-    __syncwarp();
+    double al = 0.0, be = 0.0, ga = 0.0;
 #pragma unroll
-    for (int q = 0; q < kEigJMaxSlotsPerLane; ++q) {
-        const int k = lane + 32 * q;
-        if (k < m) slots[k] = v[q];
+    for (int q = 0; q < NV; ++q) {
+        al = fma(av[q].x, av[q].x, al); al = fma(av[q].y, av[q].y, al);
+        be = fma(bv[q].x, bv[q].x, be); be = fma(bv[q].y, bv[q].y, be);
+        ga = fma(av[q].x, bv[q].x, ga); ga = fma(av[q].y, bv[q].y, ga);
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        al += __shfl_xor_sync(0xffffffffu, al, o);
+        be += __shfl_xor_sync(0xffffffffu, be, o);
+        ga += __shfl_xor_sync(0xffffffffu, ga, o);
+    }
+    const bool rot = ga * ga > (tol * tol) * (al * be);          // |ga| > tol sqrt(al be) without the square root
+    double2 *ao = reinterpret_cast<double2 *>(a_out), *bo = reinterpret_cast<double2 *>(b_out);
+    if (rot) {
+        // Rotation that annihilates ga, from the double angle: with d = |b|^2 - |a|^2 and r = sqrt(d^2 + 4 ga^2),
+        // cos 2t = |d| / r, sin 2t = 2 ga sign(d) / r; c = sqrt((1 + cos 2t) / 2), s = sin 2t / (2 c).  Two dependent
+        // rsqrt and a few multiplies (no division, no sqrt); c^2 + s^2 = 1 to rounding.
+        const double d = be - al;
+        const double rinv = rsqrt(fma(d, d, 4.0 * ga * ga));
+        const double u = fma(0.5 * fabs(d), rinv, 0.5);             // (1 + cos 2t) / 2  in [1/2, 1]
+        const double ic = rsqrt(u);
+        const double c = u * ic;
+        const double s = copysign(ga * rinv, ga * d) * ic;          // d == 0 -> sign(ga): the 45 degree rotation
+#pragma unroll
+        for (int q = 0; q < NV; ++q) {
+            const int i = lane + 32 * q;
+            if (i < nv2) {
+                ao[i] = make_double2(c * av[q].x - s * bv[q].x, c * av[q].y - s * bv[q].y);
+                bo[i] = make_double2(s * av[q].x + c * bv[q].x, s * av[q].y + c * bv[q].y);
+            }
+        }
+    } else {
+        if (a_out != a) {
+#pragma unroll
+            for (int q = 0; q < NV; ++q) {
+                const int i = lane + 32 * q;
+                if (i < nv2) ao[i] = av[q];
+            }
+        }
+        if (b_out != b) {
+#pragma unroll
+            for (int q = 0; q < NV; ++q) {
+                const int i = lane + 32 * q;
+                if (i < nv2) bo[i] = bv[q];
+            }
+        }
+    }
+    return rot;
+}
+
+struct EigJShared {
+    double *cols, *tags;      // column buffers (ld doubles each) and the original column index of each (-1 = padding)
+    int *flags, *any_flag;
+};
+
+// All sweeps of one candidate.  Returns the number of sweeps; `ring` is left at the final round.
+template <int NV>
+__device__ int eigj_sweeps(cooperative_groups::cluster_group &cluster, const Team &t, const EigJShared &S, RingLayout &ring,
+                           int cs, int cr, int n, int m, int ld, double tol)
+{
+    const int nv2 = ld / 2, h = n / 2;
+    int sweeps = 0;
+    for (; sweeps < 40; ++sweeps) {
+        if (cs == 1) {
+            // classic round-robin on static columns: pair k of round r is ((r + k) mod (n-1), (r - k) mod (n-1)), n-1 fixed
+            const int nm1 = n - 1;
+            for (int r = 0; r < nm1; ++r) {
+                for (int k = t.warp; k < h; k += t.nwarp) {
+                    int i, j;
+                    if (k == 0) { i = nm1; j = r; }
+                    else { i = RingLayout::wrap_pos(r + k, nm1); j = RingLayout::wrap_pos(r - k + nm1, nm1); }
+                    double *a = S.cols + (size_t)i * ld, *b = S.cols + (size_t)j * ld;
+                    if (pair_rotate_reg<NV>(a, b, a, b, nv2, tol, t.lane) && t.lane == 0) S.any_flag[0] = 1;
+                }
+                __syncthreads();
+            }
+        } else {
+            for (int r = 0; r < n - 1; ++r) {
+                for (int k = t.warp; k < m; k += t.nwarp) {
+                    const int sa = ring.top(k), sb = ring.bot(k);
+                    double *a = S.cols + (size_t)sa * ld, *b = S.cols + (size_t)sb * ld;
+                    double *a_out = a, *b_out = b;
+                    if (k == m - 1) {            // top column leaves to the right (last CTA: into its own bottom row)
+                        const int dst = (cr < cs - 1) ? ring.top_spare(cr + 1) : ring.bot_spare();
+                        double *dcol = S.cols + (size_t)dst * ld, *dtag = S.tags + dst;
+                        if (cr < cs - 1) { dcol = cluster.map_shared_rank(dcol, cr + 1); dtag = cluster.map_shared_rank(dtag, cr + 1); }
+                        a_out = dcol;
+                        if (t.lane == 0) *dtag = S.tags[sa];
+                    }
+                    if (k == 0) {                // bottom column leaves to the left (CTA 0: into its own top row)
+                        const int dst = (cr > 0) ? ring.bot_spare() : ring.top_spare(0);
+                        double *dcol = S.cols + (size_t)dst * ld, *dtag = S.tags + dst;
+                        if (cr > 0) { dcol = cluster.map_shared_rank(dcol, cr - 1); dtag = cluster.map_shared_rank(dtag, cr - 1); }
+                        b_out = dcol;
+                        if (t.lane == 0) *dtag = S.tags[sb];
+                    }
+                    if (pair_rotate_reg<NV>(a, b, a_out, b_out, nv2, tol, t.lane) && t.lane == 0) S.any_flag[0] = 1;
+                }
+                if (r == n - 2) {
+                    // end of the sweep: tell every CTA of the cluster whether this one rotated anything
+                    __syncthreads();
+                    if (t.tid < cs) {
+                        int *remote = cluster.map_shared_rank(S.flags, t.tid);
+                        remote[(sweeps & 1) * kEigJMaxCluster + cr] = S.any_flag[0];
+                    }
+                }
+                cluster.sync();
+                ring.advance();
+            }
+        }
+        int any;
+        if (cs == 1) {
+            any = S.any_flag[0];
+        } else {
+            any = 0;
+            for (int c = 0; c < cs; ++c) any |= S.flags[(sweeps & 1) * kEigJMaxCluster + c];
+        }
+        __syncthreads();
+        if (t.tid == 0) S.any_flag[0] = 0;
+        __syncthreads();
+        if (!any) { ++sweeps; break; }
+    }
+    return sweeps;
 }
 
 __global__ void __launch_bounds__(kEigJThreads, 1) cand_eigj_kernel(const EigJParams P)
@@ -218,114 +362,68 @@ __global__ void __launch_bounds__(kEigJThreads, 1) cand_eigj_kernel(const EigJPa
     extern __shared__ __align__(16) double sh[];
     const Team t = make_team();
     const int p = cm.p;
-    const int n = eigj_padded_n(p, cs), m = n / (2 * cs), h = n / 2, ld = eigj_ld(p);
+    const int n = eigj_padded_n(p, cs), ld = eigj_ld(p), slots = eigj_slots(p, cs);
+    const int m = n / (2 * cs), h = n / 2;
     double *red = sh;                                         // reductions of ols_and_bic
-    double *cols = sh + kEigJHeaderDoubles;                                   // (2 m + 4) column buffers of ld doubles
-    int *slot_top = reinterpret_cast<int *>(cols + (size_t)(2 * m + 4) * ld);
-    int *slot_bot = slot_top + m;
-    int *flags = slot_bot + m;                                // [2][kEigJMaxCluster]
-    int *any_flag = flags + 2 * kEigJMaxCluster;              // [0] this CTA rotated something in this sweep
+    EigJShared S;
+    S.cols = sh + kEigJHeaderDoubles;
+    S.tags = S.cols + (size_t)slots * ld;
+    S.flags = reinterpret_cast<int *>(S.tags + slots);        // [2][kEigJMaxCluster]
+    S.any_flag = S.flags + 2 * kEigJMaxCluster;               // [0] this CTA rotated something in this sweep
     const double *Lg = P.Q + cm.mat_off;
-
-    // ---- load: top[g] = column g, bottom[g] = column h + g; columns >= p are zero padding (tag -1) -------------------
-    for (int k = t.warp; k < 2 * m; k += t.nwarp) {
-        const int g = (k < m) ? (cr * m + k) : (h + cr * m + (k - m));
-        double *dst = cols + (size_t)k * ld;
-        for (int e = t.lane; e < ld; e += 32) {
-            double v = 0.0;
-            if (e < p && g < p) v = Lg[(size_t)g * p + e];
-            if (e == p) v = (g < p) ? (double)g : -1.0;
-            dst[e] = v;
-        }
-    }
-    for (int k = t.tid; k < m; k += t.nthr) { slot_top[k] = k; slot_bot[k] = m + k; }
-    if (t.tid < 2 * kEigJMaxCluster) flags[t.tid] = 0;
-    if (t.tid == 0) any_flag[0] = 0;
-    __syncthreads();
-    if (cs > 1) cluster.sync();      // every CTA has read L and initialised its staging state before anybody pushes
-
     const double tol = 2.220446049250313e-16 * (2.0 * sqrt((double)p) + 6.0);
-    int sweeps = 0;
-    int round = 0;
-    const int first = (cr == 0) ? 1 : 0;
-    for (; sweeps < 40; ++sweeps) {
-        for (int r = 0; r < n - 1; ++r, ++round) {
-            // ---- rotations -------------------------------------------------------------------------------------------
-            for (int k = t.warp; k < m; k += t.nwarp) {
-                double *a = cols + (size_t)slot_top[k] * ld, *b = cols + (size_t)slot_bot[k] * ld;
-                if (fokl::jacobi_pair_w(t, a, b, p, tol) && t.lane == 0) any_flag[0] = 1;
-            }
-            __syncthreads();
-            // ---- ring step ---------------------------------------------------------------------------------------------
-            const int par = round & 1;
-            const int t_out = slot_top[m - 1], b_out = slot_bot[0];
-            if (cs == 1) {
-                // the two travelling columns swap rows inside the only CTA: pure index exchange
-                __syncthreads();
-                if (t.warp == 0) rotate_top(slot_top, m, first, b_out, t.lane);
-                else if (t.warp == 1) rotate_bot(slot_bot, m, t_out, t.lane);
-                __syncthreads();
-                continue;
-            }
-            double *stage_top_in = cols + (size_t)(2 * m + par * 2 + 0) * ld;
-            double *stage_bot_in = cols + (size_t)(2 * m + par * 2 + 1) * ld;
-            if (t.warp == 0) {
-                const double *src = cols + (size_t)t_out * ld;
-                double *dst = (cr < cs - 1) ? cluster.map_shared_rank(stage_top_in, cr + 1) : stage_bot_in;
-                for (int e = t.lane; e < ld; e += 32) dst[e] = src[e];
-            } else if (t.warp == 1) {
-                const double *src = cols + (size_t)b_out * ld;
-                double *dst = (cr > 0) ? cluster.map_shared_rank(stage_bot_in, cr - 1) : stage_top_in;
-                for (int e = t.lane; e < ld; e += 32) dst[e] = src[e];
-            } else if (t.warp == 2 && r == n - 2 && t.lane < cs) {
-                // end of the sweep: tell every CTA of the cluster whether this one rotated anything
-                int *remote = cluster.map_shared_rank(flags, t.lane);
-                remote[(sweeps & 1) * kEigJMaxCluster + cr] = any_flag[0];
-            }
-            cluster.sync();
-            if (t.warp == 0) {
-                double *dst = cols + (size_t)t_out * ld;
-                for (int e = t.lane; e < ld; e += 32) dst[e] = stage_top_in[e];
-            } else if (t.warp == 1) {
-                double *dst = cols + (size_t)b_out * ld;
-                for (int e = t.lane; e < ld; e += 32) dst[e] = stage_bot_in[e];
-            } else if (t.warp == 2) {
-                rotate_top(slot_top, m, first, t_out, t.lane);
-            } else if (t.warp == 3) {
-                rotate_bot(slot_bot, m, b_out, t.lane);
-            }
-            __syncthreads();
-        }
-        int any;
-        if (cs == 1) {
-            any = any_flag[0];
-        } else {
-            any = 0;
-            for (int c = 0; c < cs; ++c) any |= flags[(sweeps & 1) * kEigJMaxCluster + c];
-        }
-        __syncthreads();
-        if (t.tid == 0) any_flag[0] = 0;
-        __syncthreads();
-        if (!any) { ++sweeps; break; }
+    RingLayout ring;
+    ring.m = m; ring.cr = cr; ring.rt = 0; ring.r0 = 0;
+
+    // ---- load the Cholesky factor: columns >= p are zero padding (tag -1) ----------------------------------------------
+    // cs == 1: column g in slot g.  cs > 1: top logical k <- column cr*m + k, bottom logical k <- column h + cr*m + k.
+    const int n_local = (cs == 1) ? n : 2 * m;
+    for (int k = t.warp; k < n_local; k += t.nwarp) {
+        int g, slot;
+        if (cs == 1) { g = k; slot = k; }
+        else if (k < m) { g = cr * m + k; slot = ring.top(k); }
+        else { g = h + cr * m + (k - m); slot = ring.bot(k - m); }
+        double *dst = S.cols + (size_t)slot * ld;
+        for (int e = t.lane; e < ld; e += 32) dst[e] = (e < p && g < p) ? Lg[(size_t)g * p + e] : 0.0;
+        if (t.lane == 0) S.tags[slot] = (g < p) ? (double)g : -1.0;
+    }
+    if (t.tid < 2 * kEigJMaxCluster) S.flags[t.tid] = 0;
+    if (t.tid == 0) S.any_flag[0] = 0;
+    __syncthreads();
+    if (cs > 1) cluster.sync();      // every CTA is resident and initialised before anybody writes into a neighbour
+
+    int sweeps;
+    const int nv = (ld / 2 + 31) / 32;
+    switch (nv) {
+    case 1: sweeps = eigj_sweeps<1>(cluster, t, S, ring, cs, cr, n, m, ld, tol); break;
+    case 2: sweeps = eigj_sweeps<2>(cluster, t, S, ring, cs, cr, n, m, ld, tol); break;
+    case 3: sweeps = eigj_sweeps<3>(cluster, t, S, ring, cs, cr, n, m, ld, tol); break;
+    case 4: sweeps = eigj_sweeps<4>(cluster, t, S, ring, cs, cr, n, m, ld, tol); break;
+    case 5: case 6: sweeps = eigj_sweeps<6>(cluster, t, S, ring, cs, cr, n, m, ld, tol); break;
+    case 7: case 8: sweeps = eigj_sweeps<8>(cluster, t, S, ring, cs, cr, n, m, ld, tol); break;
+    default: sweeps = eigj_sweeps<kEigJMaxNV>(cluster, t, S, ring, cs, cr, n, m, ld, tol); break;
     }
 
     // ---- eigenvalues = squared column norms; rank them across the cluster; eigenvectors = normalised columns ------------
-    double *lam_all = P.lam_raw + cm.vec_off + 64 * (int64_t)cand;     // n entries, indexed cr * 2m + physical slot
-    for (int k = t.warp; k < 2 * m; k += t.nwarp) {
-        const double *w = cols + (size_t)k * ld;
+    double *lam_all = P.lam_raw + cm.vec_off + 64 * (int64_t)cand;     // n entries, indexed cr * n_local + k
+    auto live_slot = [&](int k) { return cs == 1 ? k : (k < m ? ring.top(k) : ring.bot(k - m)); };
+    for (int k = t.warp; k < n_local; k += t.nwarp) {
+        const int slot = live_slot(k);
+        const double *w = S.cols + (size_t)slot * ld;
         double s = 0.0;
         for (int e = t.lane; e < p; e += 32) s += w[e] * w[e];
         s = fokl::warp_sum1(t, s);
-        if (t.lane == 0) lam_all[cr * 2 * m + k] = (w[p] < 0.0) ? -1.0 : s;    // padding columns are marked, not ranked
+        if (t.lane == 0) lam_all[cr * n_local + k] = (S.tags[slot] < 0.0) ? -1.0 : s;    // padding columns: marked, not ranked
     }
     __threadfence();
     if (cs > 1) cluster.sync(); else __syncthreads();
     double *lamb = P.lamb + cm.vec_off;
     double *Q = P.Q + cm.mat_off;
-    for (int k = t.warp; k < 2 * m; k += t.nwarp) {
-        const double *w = cols + (size_t)k * ld;
-        if (w[p] < 0.0) continue;
-        const int gme = cr * 2 * m + k;
+    for (int k = t.warp; k < n_local; k += t.nwarp) {
+        const int slot = live_slot(k);
+        const double *w = S.cols + (size_t)slot * ld;
+        if (S.tags[slot] < 0.0) continue;
+        const int gme = cr * n_local + k;
         const double lj = lam_all[gme];
         int rank = 0;
         for (int g = t.lane; g < n; g += 32) {
@@ -357,10 +455,39 @@ struct ChainParams {
     const double *lamb, *ct;
     int rng_mode;
     uint64_t seed;
-    const double *variates, *sign_fix;
-    double *gg, *gam, *sigs, *taus;
+    const double *variates;   // injected: caller's table (packed over all candidates); philox: d_var (packed over chains)
+    double *var_philox;       // philox: table filled by cand_variates_kernel
+    const double *sign_fix;
+    double *gam, *sigs, *taus;
     int32_t *info;
 };
+
+// offset (doubles) of the D x (p + 2) variate table of chain `slot` = candidate c
+__device__ __forceinline__ int64_t variates_offset(const ChainParams &P, const CandMeta &m, int c)
+{
+    return (P.rng_mode == FOKL_RNG_INJECTED) ? (int64_t)P.k.draws * (m.vec_off + 2 * (int64_t)c)
+                                             : (int64_t)P.k.draws * (m.gam_off + 2 * (int64_t)m.chain_idx);
+}
+
+// Philox table of every chain: one thread per variate (grid.y = chain), so the RNG (log / cos / rejection loops)
+// is off the sequential critical path of the draw loop.
+__global__ void __launch_bounds__(256) cand_variates_kernel(const ChainParams P)
+{
+    const int c = P.chain_list[blockIdx.y];
+    const CandMeta m = P.meta[c];
+    const int p = m.p, w = p + 2;
+    const int64_t total = (int64_t)P.k.draws * w;
+    fokl::Philox g;
+    g.k0 = (uint32_t)P.seed;
+    g.k1 = (uint32_t)(P.seed >> 32);
+    const uint32_t slo = (uint32_t)m.stream_id, shi = (uint32_t)(m.stream_id >> 32) & 0x7fffffffu;
+    const double astar = fokl::chain_astar(P.k, p), atau_star = fokl::chain_atau_star(P.k, p);
+    double *out = P.var_philox + variates_offset(P, m, c);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int d = (int)(i / w), e = (int)(i - (int64_t)d * w);
+        out[i] = fokl::philox_variate(g, slo, shi, d, e, p, astar, atau_star);
+    }
+}
 
 __global__ void __launch_bounds__(kChainThreads) cand_chain_kernel(const ChainParams P)
 {
@@ -370,16 +497,9 @@ __global__ void __launch_bounds__(kChainThreads) cand_chain_kernel(const ChainPa
     const CandMeta m = P.meta[c];
     const int p = m.p;
     const int D = P.k.draws;
-    ChainRng rng;
-    rng.mode = P.rng_mode;
-    rng.variates = P.variates ? P.variates + (int64_t)D * (m.vec_off + 2 * (int64_t)c) : nullptr;
-    rng.sign_fix = P.sign_fix ? P.sign_fix + m.vec_off : nullptr;
-    rng.philox.k0 = (uint32_t)P.seed;
-    rng.philox.k1 = (uint32_t)(P.seed >> 32);
-    rng.stream_lo = (uint32_t)m.stream_id;
-    rng.stream_hi = (uint32_t)(m.stream_id >> 32) & 0x7fffffffu;
-    rng.gg = P.gg + 2 * (int64_t)D * blockIdx.x;
-    int bad = fokl::gibbs_chain(t, p, P.lamb + m.vec_off, P.ct + m.vec_off, P.k, rng, P.gam + (int64_t)D * m.gam_off,
+    const double *var = (P.rng_mode == FOKL_RNG_INJECTED ? P.variates : P.var_philox) + variates_offset(P, m, c);
+    const double *sf = P.sign_fix ? P.sign_fix + m.vec_off : nullptr;
+    int bad = fokl::gibbs_chain(t, p, P.lamb + m.vec_off, P.ct + m.vec_off, P.k, var, sf, P.gam + (int64_t)D * m.gam_off,
                                 P.sigs + (int64_t)D * c, P.taus + (int64_t)D * c, red);
     if (t.tid == 0 && bad) atomicOr(P.info + c, 1);
 }
@@ -608,9 +728,9 @@ extern "C" int fokl_candidates_eval(fokl_ctx *ctx, const double *G, int64_t ldg,
         // cluster size of the Jacobi eigensolver: <= 32 column pairs per CTA, columns must fit in shared memory
         {
             int cs = 1;
-            while (cs < kEigJMaxCluster && (p + 1) / 2 > 32 * cs) cs *= 2;
+            while (cs < ctx->max_cluster && (p + 1) / 2 > (kEigJThreads / 32) * cs) cs *= 2;   // one pair per warp if possible
             while (cs <= kEigJMaxCluster && eigj_smem_bytes(p, cs) > smem_cap) cs *= 2;
-            if (cs > ctx->max_cluster) m.pad = 1;          // too large: two-matrix Jacobi in global memory (fallback)
+            if (cs > ctx->max_cluster || p > 64 * kEigJMaxNV) m.pad = 1;   // too large: two-matrix Jacobi in global memory
             else eig_class[c] = cs;
         }
         const bool in_smem = (2 * (int64_t)p * p <= smem_wv_cap);
@@ -705,12 +825,15 @@ extern "C" int fokl_candidates_eval(fokl_ctx *ctx, const double *G, int64_t ldg,
             const int cnt = class_begin[q + 1] - class_begin[q];
             if (cnt == 0) continue;
             size_t smem = 0;
-            for (int e = class_begin[q]; e < class_begin[q + 1]; ++e)
+            int threads = 32;
+            for (int e = class_begin[q]; e < class_begin[q + 1]; ++e) {
                 smem = std::max(smem, eigj_smem_bytes(meta[eig_list[e]].p, cs));
+                threads = std::max(threads, eigj_threads(meta[eig_list[e]].p, cs));
+            }
             J.list = d_eig_list + class_begin[q];
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3((unsigned)(cnt * cs));
-            cfg.blockDim = dim3(kEigJThreads);
+            cfg.blockDim = dim3((unsigned)threads);
             cfg.dynamicSmemBytes = smem;
             cfg.stream = ctx->stream;
             cudaLaunchAttribute attr[1];
@@ -753,11 +876,12 @@ extern "C" int fokl_candidates_eval(fokl_ctx *ctx, const double *G, int64_t ldg,
         FOKL_FAIL(ctx, FOKL_EINVAL, "candidates_eval: statistic windows outside the chain");
 
     // ---- chain -------------------------------------------------------------------------------------------------
-    size_t c_bytes = 256 + ((size_t)D * gam + (size_t)2 * D * n_chain) * sizeof(double);
+    const bool philox = rng_mode == FOKL_RNG_PHILOX;
+    size_t c_bytes = 256 + ((size_t)D * gam + (philox ? (size_t)D * (gam + 2 * (size_t)n_chain) : 0)) * sizeof(double);
     char *ccur = (char *)fokl_scratch(ctx, fokl_ctx::B_CAND_C, c_bytes);
     if (!ccur) return FOKL_ENOMEM;
     double *d_gam = carve<double>(ccur, (size_t)D * gam);
-    double *d_gg = carve<double>(ccur, (size_t)2 * D * n_chain);
+    double *d_var = philox ? carve<double>(ccur, (size_t)D * (gam + 2 * (size_t)n_chain)) : nullptr;
     size_t d_bytes = 256 + (betas ? 0 : (size_t)D * vec * sizeof(double)) + (sigs ? 0 : (size_t)D * n_cand * sizeof(double)) +
                      (taus ? 0 : (size_t)D * n_cand * sizeof(double));
     char *ecur = (char *)fokl_scratch(ctx, fokl_ctx::B_CAND_D, d_bytes);
@@ -768,9 +892,16 @@ extern "C" int fokl_candidates_eval(fokl_ctx *ctx, const double *G, int64_t ldg,
     {
         ChainParams P;
         P.meta = d_meta; P.chain_list = d_chain; P.k = k; P.lamb = d_lamb; P.ct = d_ct;
-        P.rng_mode = rng_mode; P.seed = seed; P.variates = variates; P.sign_fix = sign_fix;
-        P.gg = d_gg; P.gam = d_gam; P.sigs = d_sigs; P.taus = d_taus; P.info = info;
-        cand_chain_kernel<<<n_chain, kChainThreads, 0, ctx->stream>>>(P);
+        P.rng_mode = rng_mode; P.seed = seed; P.variates = variates; P.var_philox = d_var; P.sign_fix = sign_fix;
+        P.gam = d_gam; P.sigs = d_sigs; P.taus = d_taus; P.info = info;
+        if (philox) {
+            const int64_t per_chain = (int64_t)D * (pmax_chain + 2);
+            dim3 grid((unsigned)std::min<int64_t>((per_chain + 255) / 256, 2048), (unsigned)n_chain);
+            cand_variates_kernel<<<grid, 256, 0, ctx->stream>>>(P);
+            FOKL_LAUNCH_CHECK(ctx);
+        }
+        const int chain_threads = std::max(32, std::min(kChainThreads, 32 * ((pmax_chain / 2 + 31) / 32)));
+        cand_chain_kernel<<<n_chain, chain_threads, 0, ctx->stream>>>(P);
         FOKL_LAUNCH_CHECK(ctx);
     }
     if (!betas && !stats) return FOKL_OK;

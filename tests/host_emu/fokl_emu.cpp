@@ -98,13 +98,19 @@ int emu_candidate(const double *G, int64_t ldg, const double *Xty, const int32_t
     *info = (sweeps << 8) | chol_failed;
     if (rng_mode == 0) return 0;
     const int D = h->draws;
-    std::vector<double> gam((size_t)D * p), gg((size_t)2 * D);
-    ChainRng rng;
-    rng.mode = rng_mode; rng.variates = variates; rng.sign_fix = sign_fix;
-    rng.philox.k0 = (uint32_t)seed; rng.philox.k1 = (uint32_t)(seed >> 32);
-    rng.stream_lo = (uint32_t)stream; rng.stream_hi = (uint32_t)(stream >> 32) & 0x7fffffffu;
-    rng.gg = gg.data();
-    int bad = gibbs_chain(t, p, lamb, ct.data(), k, rng, gam.data(), sigs, taus, red.data());
+    std::vector<double> gam((size_t)D * p), table;
+    const double *var = variates;
+    if (rng_mode == 2) {
+        Philox g;
+        g.k0 = (uint32_t)seed; g.k1 = (uint32_t)(seed >> 32);
+        table.resize((size_t)D * (p + 2));
+        for (int d = 0; d < D; ++d)
+            for (int e = 0; e < p + 2; ++e)
+                table[(size_t)d * (p + 2) + e] = philox_variate(g, (uint32_t)stream, (uint32_t)(stream >> 32) & 0x7fffffffu, d, e,
+                                                                p, chain_astar(k, p), chain_atau_star(k, p));
+        var = table.data();
+    }
+    int bad = gibbs_chain(t, p, lamb, ct.data(), k, var, sign_fix, gam.data(), sigs, taus, red.data());
     if (bad) *info |= 1;
     for (int d = 0; d < D; ++d)
         for (int i = 0; i < p; ++i) {

@@ -165,3 +165,39 @@ def test_cfg2_rank_deficient_rounds_run(phis_cubic):
     _, betas, mtx, evs, _, _ = fit_device(FR, g, phis_cubic, rng='philox')
     assert betas.shape[0] == 1000 and mtx.shape[1] == 2
     assert np.allclose(evs[:3], g['evs'][:3], rtol=1e-8, atol=0)
+
+
+def test_clean_on_device_equals_host_clean(phis_cubic, tmp_path):
+    """fit(clean=True) on a large dataset normalises in HBM (FoKL._clean_on_device): the normalised inputs, minmax and
+    the whole fit must be bit-identical to the host `clean` path, and `inputs` stays an ordinary (picklable) attribute."""
+    from FoKL import FoKLRoutines as FR
+    rng = np.random.default_rng(17)
+    n, m = 300_000, 4
+    raw = rng.random((n, m)) * np.array([3.0, 10.0, 0.5, 7.0]) + np.array([-1.0, 5.0, 0.0, 100.0])
+    u = (raw - raw.min(axis=0)) / (raw.max(axis=0) - raw.min(axis=0))
+    y = np.sin(2 * np.pi * u[:, 0]) + u[:, 1] * u[:, 2] + 0.05 * rng.standard_normal(n)
+
+    def run(force_host, **kw):
+        model = FR.FoKL(phis=phis_cubic, draws=60, burnin=60, tolerance=2, UserWarnings=False, ConsoleOutput=False)
+        if force_host:
+            model._clean_on_device = lambda *a, **k: None
+        np.random.seed(5)
+        out = model.fit(raw.copy(), y.copy(), clean=True, **kw)
+        return model, out
+
+    md, (bd, td, ed) = run(False)
+    assert isinstance(md.__dict__['inputs'], FR._DeviceInputs)          # nothing copied back yet
+    mh, (bh, th, eh) = run(True)
+    assert np.array_equal(td, th) and np.array_equal(ed, eh) and np.array_equal(bd, bh)
+    assert md.minmax == mh.minmax
+    assert np.array_equal(md.inputs, mh.inputs) and isinstance(md.__dict__['inputs'], np.ndarray)
+    assert np.array_equal(md.data, mh.data) and md.trainlog is None
+    # user bounds + pillow go through the same host policy
+    md2, (b2, t2, e2) = run(False, minmax=[[-2.0, 3.0], [0.0, 20.0], [0.0, 1.0], [90.0, 110.0]], pillow=0.1)
+    mh2, (b3, t3, e3) = run(True, minmax=[[-2.0, 3.0], [0.0, 20.0], [0.0, 1.0], [90.0, 110.0]], pillow=0.1)
+    assert md2.minmax == mh2.minmax and np.array_equal(e2, e3) and np.array_equal(t2, t3)
+    # pickling materialises the device-resident inputs
+    md3, _ = run(False)
+    path = md3.save(str(tmp_path / 'dev'))
+    again = FR.load(path)
+    assert np.array_equal(again.inputs, mh.inputs)

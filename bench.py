@@ -51,6 +51,7 @@ def parse():
     ap.add_argument('--n', type=int, default=0, help='override the number of rows (debugging only)')
     ap.add_argument('--draws', type=int, default=1000)
     ap.add_argument('--cpu-rows', type=int, default=4000, help='rows of the bounded CPU sample')
+    ap.add_argument('--cpu-seconds', type=float, default=25.0, help='wall-time budget of the bounded CPU sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     return ap.parse_args()
@@ -114,22 +115,43 @@ class Clocks:
 # ---------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port on a bounded sample
 # ---------------------------------------------------------------------------------------------------
-def cpu_fit_once(a, phis, rows):
+class _CpuBudget(Exception):
+    pass
+
+
+def cpu_fit_once(a, phis, rows, budget_s):
+    """The CPU oracle's fit on `rows` rows of the workload, cut off after `budget_s` seconds of wall time: returns
+    (gibbs calls completed, seconds up to the last completed call, threads, largest model width reached)."""
     sys.path.insert(0, os.path.join(ROOT, 'oracle'))
     import fokl_oracle as fo
     c = bench_data.CONFIGS[a.workload]
     x, y = bench_data.make_rows(a.workload, 0, rows, n_total=rows)
     np.random.seed(c['seed'])
     threads = os.cpu_count() or 1
+    state = dict(calls=0, t=0.0, pmax=0)
     t0 = time.perf_counter()
-    r = fo.fit(x, y, phis, kernel=c['kernel'], way3=c['way3'], draws=a.draws, burnin=a.draws, threads=threads)
-    dt = time.perf_counter() - t0
-    return r.n_gibbs, dt, threads
+
+    def on_gibbs(info):
+        state['calls'] = info['call']
+        state['t'] = time.perf_counter() - t0
+        state['pmax'] = max(state['pmax'], info['discmtx'].shape[0] + 1)
+        if budget_s and state['t'] > budget_s:
+            raise _CpuBudget()
+
+    try:
+        fo.fit(x, y, phis, kernel=c['kernel'], way3=c['way3'], draws=a.draws, burnin=a.draws, threads=threads,
+               on_gibbs=on_gibbs)
+    except _CpuBudget:
+        pass
+    return state['calls'], state['t'], threads, state['pmax']
 
 
-def cpu_sample_desc(a, rows):
-    return ('oracle port (numpy + C basis helper; faster than the reference, whose basis build is a Python triple '
-            'loop) of one complete fit on the %s generator at N=%d rows, %d+%d draws' % (a.workload, rows, a.draws, a.draws))
+def cpu_sample_desc(a, rows, budget_s, calls, pmax):
+    return ('oracle port (numpy/OpenBLAS/LAPACK like the reference + a C basis helper, i.e. faster than the reference, '
+            'whose basis build is a Python triple loop) of the %s fit at N=%d rows, %d+%d draws, cut off after %.0f s: '
+            'the first %d gibbs calls (model width up to %d columns). The complete CPU fit at N=4000 takes 300 s '
+            '(0.62 candidate-models/s on 8 cores, see BASELINE.md)'
+            % (a.workload, rows, a.draws, a.draws, budget_s, calls, pmax))
 
 
 def run_reference(a):
@@ -139,18 +161,21 @@ def run_reference(a):
     phis = load_phis(a)
     n_total = a.n or bench_data.CONFIGS[a.workload]['n']
     for _ in range(a.warmup):
-        cpu_fit_once(a, phis, max(500, a.cpu_rows // 8))
-    tot_models, tot_s, threads = 0, 0.0, 1
+        cpu_fit_once(a, phis, a.cpu_rows, 2.0)
+    tot_models, tot_s, threads, pmax = 0, 0.0, 1, 0
+    budget = a.cpu_seconds * 2.0       # each step: a bounded sample of the fit
     for _ in range(a.steps):
-        m, dt, threads = cpu_fit_once(a, phis, a.cpu_rows)
+        m, dt, threads, pm = cpu_fit_once(a, phis, a.cpu_rows, budget)
         tot_models += m
         tot_s += dt
+        pmax = max(pmax, pm)
     v = tot_models / tot_s
     line = {'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': a.gpus, 'steps': a.steps,
             'warmup': a.warmup, 'ms_per_step': 1e3 * tot_s / a.steps, 'higher_is_better': True, 'scaling': 'strong',
             'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
             'config': config_dict(a, n_total, 1, {'cpu_sample_rows': a.cpu_rows}),
-            'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': cpu_sample_desc(a, a.cpu_rows)},
+            'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+                             'sample': cpu_sample_desc(a, a.cpu_rows, budget, tot_models // max(a.steps, 1), pmax)},
             'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
     print(json.dumps(line), flush=True)
@@ -323,9 +348,9 @@ def main():
 
     cpu = None
     if world == 1 and not a.no_cpu_baseline:
-        mdl, dt, threads = cpu_fit_once(a, phis, a.cpu_rows)
-        cpu = {'value': mdl / dt, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': cpu_sample_desc(a, a.cpu_rows),
-               'seconds': dt}
+        mdl, dt, threads, pm = cpu_fit_once(a, phis, a.cpu_rows, a.cpu_seconds)
+        cpu = {'value': mdl / dt, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+               'sample': cpu_sample_desc(a, a.cpu_rows, a.cpu_seconds, mdl, pm), 'seconds': dt}
 
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': a.steps, 'warmup': a.warmup,
             'ms_per_step': ms / a.steps, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,

@@ -1,0 +1,107 @@
+"""World-size-2 `gloo` tests (CPU) of the host-side multi-rank logic: row sharding of the
+synthetic workloads, the SUM allreduce of partial Gram blocks / data moments, the MIN/MAX allreduce behind
+`clean`'s normalisation bounds and the seed broadcast.  The device kernels are not involved; the partial Gram
+of a shard is formed with numpy exactly as `fokl_gram_update` defines its output block."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, out_dir):
+    import torch
+    import torch.distributed as dist
+    for p in (os.path.join(ROOT, 'fokl-gpy_b200'), os.path.join(ROOT, 'oracle'), ROOT):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        import bench_data
+        import fokl_oracle as fo
+        from FoKL import FoKLRoutines as FR
+        from FoKL import _selection
+        n_total = 3001                      # not divisible by the world size: ragged last shard
+        per = -(-n_total // world)
+        lo, hi = rank * per, min((rank + 1) * per, n_total)
+        x, y = bench_data.make_rows('cfg3', lo, hi, n_total=n_total)
+
+        # (1) normalisation bounds: every rank must see the global per-column min / max
+        raw = 3.0 * x - 1.0
+        bounds = np.array(FR._column_minmax_host(raw))
+
+        # (2) Gram block of the shard: [X_old X_new y]' X_new, then one SUM allreduce (Engine._append_built)
+        from FoKL import getKernels
+        phis = getKernels.bernoulli()
+        terms_old = np.array([[1, 0, 0, 0], [0, 1, 0, 0]])
+        terms_new = np.array([[0, 0, 1, 0], [0, 0, 0, 1], [1, 1, 0, 0]])
+        Xo = np.hstack([np.ones((hi - lo, 1)), fo.basis_columns(x, terms_old, phis, fo.BERNOULLI)])
+        Xn = fo.basis_columns(x, terms_new, phis, fo.BERNOULLI)
+        block = np.vstack([Xo.T @ Xn, Xn.T @ Xn, y[None, :] @ Xn])
+        mom = np.array([float(hi - lo), y.sum(), y @ y])
+        tb, tm = torch.from_numpy(block.copy()), torch.from_numpy(mom.copy())
+        dist.all_reduce(tb, op=dist.ReduceOp.SUM)
+        dist.all_reduce(tm, op=dist.ReduceOp.SUM)
+
+        # (3) the Philox seed is rank 0's (PhiloxVariates broadcast)
+        class _Eng:
+            pass
+        eng = _Eng()
+        eng.torch, eng.dist, eng.group, eng.device = torch, dist, None, torch.device('cpu')
+        np.random.seed(100 + rank)          # deliberately different host RNG state per rank
+        seed = _selection.PhiloxVariates(eng).seed
+        np.savez(os.path.join(out_dir, 'rank%d.npz' % rank), bounds=bounds, block=tb.numpy(), mom=tm.numpy(),
+                 seed=np.array([seed], dtype=np.int64), rows=np.array([lo, hi]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_row_sharding_allreduce(tmp_path):
+    import torch.multiprocessing as mp
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    sys.path.insert(0, os.path.join(ROOT, 'fokl-gpy_b200'))
+    import bench_data
+    import fokl_oracle as fo
+    from FoKL import getKernels
+    world = 2
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    r = [np.load(os.path.join(str(tmp_path), 'rank%d.npz' % k)) for k in range(world)]
+
+    n_total = 3001
+    x, y = bench_data.make_rows('cfg3', 0, n_total, n_total=n_total)
+    # shards tile the dataset exactly
+    assert r[0]['rows'][0] == 0 and r[0]['rows'][1] == r[1]['rows'][0] and r[1]['rows'][1] == n_total
+    raw = 3.0 * x - 1.0
+    want = np.array([[raw[:, k].min(), raw[:, k].max()] for k in range(raw.shape[1])])
+    for k in range(world):
+        assert np.array_equal(r[k]['bounds'], want)
+    phis = getKernels.bernoulli()
+    Xo = np.hstack([np.ones((n_total, 1)),
+                    fo.basis_columns(x, np.array([[1, 0, 0, 0], [0, 1, 0, 0]]), phis, fo.BERNOULLI)])
+    Xn = fo.basis_columns(x, np.array([[0, 0, 1, 0], [0, 0, 0, 1], [1, 1, 0, 0]]), phis, fo.BERNOULLI)
+    block = np.vstack([Xo.T @ Xn, Xn.T @ Xn, y[None, :] @ Xn])
+    for k in range(world):
+        assert np.allclose(r[k]['block'], block, rtol=1e-12, atol=1e-12 * np.abs(block).max())
+        assert np.allclose(r[k]['mom'], [n_total, y.sum(), y @ y], rtol=1e-13)
+    # allreduce results are bit-identical on both ranks (replicated candidate evaluation relies on it)
+    assert np.array_equal(r[0]['block'], r[1]['block'])
+    assert r[0]['seed'][0] == r[1]['seed'][0]
+
+
+def test_shards_are_independent_of_world_size():
+    sys.path.insert(0, ROOT)
+    import bench_data
+    full_x, full_y = bench_data.make_rows('cfg4', 0, 1000, n_total=1000)
+    for world in (2, 4, 8):
+        per = -(-1000 // world)
+        xs, ys = zip(*[bench_data.make_rows('cfg4', k * per, min((k + 1) * per, 1000), n_total=1000)
+                       for k in range(world)])
+        assert np.array_equal(np.concatenate(xs), full_x)
+        assert np.array_equal(np.concatenate(ys), full_y)

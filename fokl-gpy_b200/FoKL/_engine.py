@@ -259,18 +259,27 @@ class Engine:
         return self
 
     def _ensure_columns(self, need):
+        """Grow the column-major design matrix to at least `need` columns (geometric growth, contents kept).  The
+        free-memory query (cudaMemGetInfo costs tens of milliseconds on a busy device) is only made after an
+        allocation has actually failed."""
         torch = self.torch
         if self.X is not None and need <= self.Pcap:
             return
         new_cap = max(need, int(self.Pcap * 1.5) + 8)
-        free, _ = torch.cuda.mem_get_info(self.device)
         col_bytes = self.ld * 8
-        max_extra = int(free * 0.9) // col_bytes
-        if new_cap > max_extra:
-            new_cap = max(need, max_extra)
-        if new_cap > max_extra:
+        Xn = None
+        try:
+            Xn = torch.empty((new_cap, self.ld), dtype=torch.float64, device=self.device)
+        except torch.OutOfMemoryError:
+            torch.cuda.empty_cache()
+            free, _ = torch.cuda.mem_get_info(self.device)
+            new_cap = min(new_cap, max(need, int(free * 0.9) // col_bytes))
+            try:
+                Xn = torch.empty((new_cap, self.ld), dtype=torch.float64, device=self.device)
+            except torch.OutOfMemoryError:
+                Xn = None
+        if Xn is None:
             raise MemoryError("design matrix of %d columns x %d rows does not fit in device memory" % (need, self.ds.n))
-        Xn = torch.empty((new_cap, self.ld), dtype=torch.float64, device=self.device)
         if self.X is not None and self.P > 0:
             Xn[:self.P].copy_(self.X[:self.P])
         self.X = Xn

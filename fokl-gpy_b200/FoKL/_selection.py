@@ -169,8 +169,13 @@ def forward_select(engine, hy, m, n_phis, console=True, rng='philox', eager=Fals
             variates = np.concatenate([
                 (v if v is not None else np.zeros((D, len(s_) + 2))).reshape(-1) for v, s_ in zip(chains, col_sets)])
             flags = np.array([v is not None for v in chains], dtype=np.uint8)
-            return engine.evaluate(col_sets, hyp, rng_mode=mode, run_chain=flags, seed=seed, stream_ids=sid,
-                                   variates=variates, sign_fix=np.concatenate(signs), want_betas=True)
+            out = engine.evaluate(col_sets, hyp, rng_mode=mode, run_chain=flags, seed=seed, stream_ids=sid,
+                                  variates=variates, sign_fix=np.concatenate(signs), want_betas=True)
+            if recorder is not None and hasattr(recorder, 'on_result'):
+                for c, cols in enumerate(col_sets):
+                    recorder.on_result(tuple(map(tuple, terms[np.asarray(cols[1:], dtype=np.int64) - 1])),
+                                       float(out.ev[c]))
+            return out
         flags = np.array([bool(v) for v in chains], dtype=np.uint8)
         any_chain = bool(flags.any())
         return engine.evaluate(col_sets, hyp, rng_mode=mode if any_chain else _lib.RNG_NONE, run_chain=flags,

@@ -3,30 +3,47 @@
 // Replaces XtX = X'X and Xty = X'y of the reference (src/FoKL/FoKLRoutines.py:1492-1494), which
 // recomputes the full P x P product on every `gibbs` call.  Here only the block that is new when C
 // columns are appended is formed:   block = [X_old  X_new  y]' X_new     ((P_old + C + 1) x C)
+// and of its symmetric X_new' X_new part only the 8 x 8 fragments on or above the diagonal.
 //
-// X is column-major, so both MMA operands are contiguous along the reduction (row) index: a CTA streams
-// KB-row slabs of 64 "A" columns and 64 "B" columns into shared memory with cp.async (3-stage ring),
-// and 8 warps issue mma.sync.m8n8k4.f64 on a 64 x 64 output tile.  The row range is split across
-// CTAs (blockIdx.y); partial tiles go to a workspace and are summed in a fixed order (deterministic).
-// blockIdx.x (the tile) varies fastest so CTAs of one row slab run together and share it through L2.
+// Work decomposition (gram_plan.h): the needed fragments are grouped into 2 x 2-fragment blocks and the blocks into
+// tiles of <= 4 blocks per warp; a CTA (8 or 16 warps, 4 blocks = 16 DMMA accumulators per warp) owns one tile for one
+// contiguous range of rows.  X is column-major, so both MMA operands are contiguous along the reduction (row) index: the CTA
+// streams KB-row slabs of the tile's distinct operand columns ("slots", each staged ONCE however many blocks use it)
+// into shared memory with cp.async (3/4-stage ring, [slot][KB + 4] layout = conflict-free fragment loads) and issues
+// mma.sync.m8n8k4.f64 from there.  Grid = tiles x row splits ~ one CTA per resident slot; the per-split accumulators go to a
+// workspace in fragment order (coalesced 16-byte stores) and gram_reduce_kernel sums them in a fixed order
+// (deterministic, no atomics) while scattering to the (P_old + C + 1) x C block.
 #include "fokl_ctx.cuh"
+#include "gram_plan.h"
 #include <algorithm>
+#include <stdlib.h>
+#include <string.h>
 
 namespace {
 
-constexpr int TM = 64, TN = 64, KB = 32, STRIDE = KB + 4, STAGES = 3;
-constexpr int kGramThreads = 256;
-constexpr size_t kStageDoubles = (size_t)(TM + TN) * STRIDE;
-constexpr size_t kGramSmem = STAGES * kStageDoubles * sizeof(double);
+using fokl::GramBlockMeta;
+using fokl::GramTileMeta;
+using fokl::kGramBlocksPerWarp;
+
+constexpr int kMaxStages = 4;            // cp.async ring depth: 4, or 3 when that buys a deeper slab
+constexpr int kPad = 4;                     // row stride KB + 4 doubles: fragment loads hit 16 distinct 8-byte banks
 
 struct GramParams {
     const double *X;
     const double *y;
     int64_t ld, n;
-    int p_old, c;          // A side: columns 0 .. p_old + c - 1 of X, then y; B side: columns p_old .. p_old + c - 1
-    int tiles_b;
+    int p;                                  // p_old + c: slot source p means y
+    int kb;                                 // rows per pipeline stage: 16, 32 or 64
+    int kb_shift;                           // log2(kb / 2)
+    int stages;                             // ring depth (3 or 4)
+    int max_slots;                          // shared-memory stage = max_slots * (kb + 4) doubles
     int64_t rows_per_split;
-    double *out;           // nsplit x (p + 1) x c partials (or the final block when nsplit == 1)
+    const GramTileMeta *tiles;
+    const int32_t *slot_src;
+    const GramBlockMeta *blocks;
+    double *part;                           // [split][tile][64 blocks][4 fragments][64]
+    int n_tiles;
+    int tile_blocks;                        // workspace stride: warps * 4 blocks per tile
 };
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem, int src_bytes)
@@ -45,129 +62,185 @@ __device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, do
                  : "d"(a), "d"(b));
 }
 
-__global__ void __launch_bounds__(kGramThreads, 2) gram_kernel(const GramParams P)
+// D += A * B on one 8 x 8 x 4 fragment, executed only where `on` is non-zero.  The predicate lives inside the asm so
+// the compiler neither branches around the warp-synchronous instruction nor re-converges after it; `on` is
+// warp-uniform (it comes from the block's fragment mask).
+template <unsigned BIT>
+__device__ __forceinline__ void dmma_m8n8k4_if(double &c0, double &c1, double a, double b, unsigned on)
 {
-    extern __shared__ __align__(16) double smem[];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = warp >> 2, wn = warp & 3;
-    const int p = P.p_old + P.c;
-    const int ta = blockIdx.x / P.tiles_b, tb = blockIdx.x % P.tiles_b;
-    const int64_t n_lo = (int64_t)blockIdx.y * P.rows_per_split;
-    const int64_t n_hi = (n_lo + P.rows_per_split < P.n) ? n_lo + P.rows_per_split : P.n;
-    const int nk = (int)((n_hi - n_lo + KB - 1) / KB);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b32 t;\n"
+        "and.b32 t, %4, %5;\n"
+        "setp.ne.u32 p, t, 0;\n"
+        "@p mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+        "}\n"
+        : "+d"(c0), "+d"(c1)
+        : "d"(a), "d"(b), "r"(on), "n"(BIT));
+}
 
-    // per-thread copy assignments: 8 x 16-byte segments per stage
-    const double *src_col[8];
-    int dst_off[8], seg_row[8];
+// The row loop of one CTA for a warp that owns NB blocks (q = warp + 16 b, b < NB).  NB is a template parameter so
+// the fragment loads of a k-step are all issued ahead of its DMMAs without per-block branches; MASKED selects the
+// predicated DMMA form for warps that own a block with skipped fragments (diagonal / edge blocks).
+template <int WARPS, int NB, bool MASKED>
+__device__ __forceinline__ void gram_rows(const GramParams &P, const GramTileMeta &tm, double *stages,
+                                          const double *const *s_ptr, size_t stage_doubles, int stride, int64_t n_lo,
+                                          int64_t n_hi, int nk, int tid, int lane, int warp, double *out)
+{
+    constexpr int NBA = NB > 0 ? NB : 1;
+    constexpr int kGramWarps = WARPS, kGramThreads = WARPS * 32;
+    int a_off[NBA], b_off[NBA];
+    unsigned msk[NBA];
+    const int frag_r = lane >> 2, frag_k = lane & 3;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-        int idx = q * kGramThreads + tid;
-        int col = idx >> 4, seg = idx & 15;          // col 0..127 (A then B), seg 0..15
-        const double *base = nullptr;
-        if (col < TM) {
-            int i = ta * TM + col;
-            if (i < p) base = P.X + (int64_t)i * P.ld;
-            else if (i == p) base = P.y;
-        } else {
-            int j = tb * TN + (col - TM);
-            if (j < P.c) base = P.X + (int64_t)(P.p_old + j) * P.ld;
-        }
-        src_col[q] = base;
-        dst_off[q] = col * STRIDE + seg * 2;
-        seg_row[q] = seg * 2;
+    for (int b = 0; b < NB; ++b) {
+        const GramBlockMeta bm = P.blocks[tm.blk_off + warp + kGramWarps * b];
+        a_off[b] = (bm.a_slot + frag_r) * stride + frag_k;
+        b_off[b] = (bm.b_slot + frag_r) * stride + frag_k;
+        msk[b] = bm.mask;
     }
-
-    auto load_stage = [&](int kt, int buf) {
-        double *dst = smem + (size_t)buf * kStageDoubles;
-        const int64_t r0 = n_lo + (int64_t)kt * KB;
+    double acc[NBA][4][2];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            if (src_col[q] == nullptr) continue;
-            int64_t r = r0 + seg_row[q];
-            int64_t left = n_hi - r;
-            int bytes = left >= 2 ? 16 : (left == 1 ? 8 : 0);
-            const double *src = bytes ? src_col[q] + r : src_col[q];
-            cp_async16(dst + dst_off[q], src, bytes);
+    for (int b = 0; b < NB; ++b)
+#pragma unroll
+        for (int f = 0; f < 4; ++f) acc[b][f][0] = acc[b][f][1] = 0.0;
+
+    const int segs = tm.n_slots << P.kb_shift;                     // 16-byte segments per stage
+    const int seg_mask = (1 << P.kb_shift) - 1;
+    auto load_stage = [&](int kt, int buf) {
+        double *dst = stages + (size_t)buf * stage_doubles;
+        const int64_t r0 = n_lo + (int64_t)kt * P.kb;
+        for (int sg = tid; sg < segs; sg += kGramThreads) {
+            const int slot = sg >> P.kb_shift, part = sg & seg_mask;
+            const double *col = s_ptr[slot];
+            if (col == nullptr) continue;
+            const int64_t r = r0 + part * 2;
+            const int64_t left = n_hi - r;
+            const int bytes = left >= 2 ? 16 : (left == 1 ? 8 : 0);
+            cp_async16(dst + slot * stride + part * 2, bytes ? col + r : col, bytes);
         }
     };
 
-    double acc[4][2][2];
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 2; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
-
-    // 8 x 8 output fragments this warp really has to compute: inside the (p + 1) x c block and not strictly below
-    // the diagonal of the symmetric X_new' X_new part (fokl_gram_scatter mirrors the upper triangle)
-    unsigned fmask = 0;
-#pragma unroll
-    for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-        for (int nt = 0; nt < 2; ++nt) {
-            const int i0 = ta * TM + wm * 32 + mt * 8, j0 = tb * TN + wn * 16 + nt * 8;
-            const bool has_y = (i0 <= p) && (p < i0 + 8);
-            const bool below = (i0 - P.p_old > j0 + 7) && !has_y;
-            if (i0 <= p && j0 < P.c && !below) fmask |= 1u << (mt * 2 + nt);
-        }
-    const bool cta_active = __syncthreads_or(fmask != 0);
-
-    if (cta_active) {
-#pragma unroll
-        for (int s = 0; s < STAGES - 1; ++s) {
-            if (s < nk) load_stage(s, s);
+    const int stages_n = P.stages;
+    for (int s = 0; s < stages_n - 1; ++s) {
+        if (s < nk) load_stage(s, s);
+        cp_async_commit();
+    }
+    const int half = 8 * stride;                                   // second fragment row / column of a block
+    for (int kt = 0; kt < nk; ++kt) {
+        if (stages_n == 4) cp_async_wait<2>();
+        else cp_async_wait<1>();
+        __syncthreads();
+        {
+            const int nxt = kt + stages_n - 1;
+            if (nxt < nk) load_stage(nxt, nxt % stages_n);
             cp_async_commit();
         }
-        const int frag_r = lane >> 2, frag_k = lane & 3;
-        for (int kt = 0; kt < nk; ++kt) {
-            cp_async_wait<STAGES - 2>();
-            __syncthreads();
-            {
-                int nxt = kt + STAGES - 1;
-                if (nxt < nk) load_stage(nxt, nxt % STAGES);
-                cp_async_commit();
-            }
-            if (fmask == 0) continue;
-            const double *As = smem + (size_t)(kt % STAGES) * kStageDoubles;
-            const double *Bs = As + (size_t)TM * STRIDE;
+        if (NB == 0) continue;
+        const double *S = stages + (size_t)(kt % stages_n) * stage_doubles;
+        for (int k0 = 0; k0 < P.kb; k0 += 16) {
 #pragma unroll
-            for (int kk = 0; kk < KB / 4; ++kk) {
-                double af[4], bf[2];
+            for (int kk = 0; kk < 16; kk += 4) {
+                double a0[NBA], a1[NBA], b0[NBA], b1[NBA];
 #pragma unroll
-                for (int mt = 0; mt < 4; ++mt)
-                    if (fmask & (3u << (mt * 2))) af[mt] = As[(wm * 32 + mt * 8 + frag_r) * STRIDE + kk * 4 + frag_k];
+                for (int b = 0; b < NB; ++b) {
+                    const double *pa = S + a_off[b] + k0 + kk, *pb = S + b_off[b] + k0 + kk;
+                    a0[b] = pa[0]; a1[b] = pa[half]; b0[b] = pb[0]; b1[b] = pb[half];
+                }
 #pragma unroll
-                for (int nt = 0; nt < 2; ++nt)
-                    if (fmask & (0x55u << nt)) bf[nt] = Bs[(wn * 16 + nt * 8 + frag_r) * STRIDE + kk * 4 + frag_k];
-#pragma unroll
-                for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-                    for (int nt = 0; nt < 2; ++nt)
-                        if (fmask & (1u << (mt * 2 + nt))) dmma_m8n8k4(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
+                for (int b = 0; b < NB; ++b) {
+                    if (MASKED) {
+                        dmma_m8n8k4_if<1u>(acc[b][0][0], acc[b][0][1], a0[b], b0[b], msk[b]);
+                        dmma_m8n8k4_if<2u>(acc[b][1][0], acc[b][1][1], a0[b], b1[b], msk[b]);
+                        dmma_m8n8k4_if<4u>(acc[b][2][0], acc[b][2][1], a1[b], b0[b], msk[b]);
+                        dmma_m8n8k4_if<8u>(acc[b][3][0], acc[b][3][1], a1[b], b1[b], msk[b]);
+                    } else {
+                        dmma_m8n8k4(acc[b][0][0], acc[b][0][1], a0[b], b0[b]);
+                        dmma_m8n8k4(acc[b][1][0], acc[b][1][1], a0[b], b1[b]);
+                        dmma_m8n8k4(acc[b][2][0], acc[b][2][1], a1[b], b0[b]);
+                        dmma_m8n8k4(acc[b][3][0], acc[b][3][1], a1[b], b1[b]);
+                    }
+                }
             }
         }
-        cp_async_wait<0>();
     }
+    cp_async_wait<0>();
 
-    double *out = P.out + (size_t)blockIdx.y * (size_t)(p + 1) * P.c;
+    // accumulators in fragment order: lane l holds C[l >> 2][(l & 3) * 2 + {0, 1}] = row-major 8 x 8 at offset 2 l
 #pragma unroll
-    for (int mt = 0; mt < 4; ++mt)
+    for (int b = 0; b < NB; ++b) {
+        const int q = warp + kGramWarps * b;
 #pragma unroll
-        for (int nt = 0; nt < 2; ++nt) {
-            int i = ta * TM + wm * 32 + mt * 8 + (lane >> 2);
-            int j = tb * TN + wn * 16 + nt * 8 + (lane & 3) * 2;
-            if (i <= p) {
-                if (j < P.c) out[(size_t)i * P.c + j] = acc[mt][nt][0];
-                if (j + 1 < P.c) out[(size_t)i * P.c + j + 1] = acc[mt][nt][1];
-            }
-        }
+        for (int f = 0; f < 4; ++f)
+            *reinterpret_cast<double2 *>(out + (size_t)q * 256 + f * 64 + lane * 2) = make_double2(acc[b][f][0], acc[b][f][1]);
+    }
 }
 
-__global__ void gram_reduce_kernel(const double *__restrict__ part, int nsplit, int64_t elems, double *__restrict__ out)
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 16 / WARPS) gram_kernel(const GramParams P)
 {
-    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < elems; e += (int64_t)gridDim.x * blockDim.x) {
+    constexpr int kGramWarps = WARPS, kGramThreads = WARPS * 32;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const GramTileMeta tm = P.tiles[blockIdx.x];
+    const int stride = P.kb + kPad;
+    const size_t stage_doubles = (size_t)P.max_slots * stride;
+    double *stages = reinterpret_cast<double *>(smem_raw);
+    const double **s_ptr = reinterpret_cast<const double **>(stages + P.stages * stage_doubles);
+
+    const int64_t n_lo = (int64_t)blockIdx.y * P.rows_per_split;
+    const int64_t n_hi = (n_lo + P.rows_per_split < P.n) ? n_lo + P.rows_per_split : P.n;
+    const int nk = n_hi > n_lo ? (int)((n_hi - n_lo + P.kb - 1) / P.kb) : 0;
+
+    // operand column pointers; padding slots stay zero in every stage (never written by cp.async)
+    for (int s = tid; s < tm.n_slots; s += kGramThreads) {
+        const int src = P.slot_src[tm.slot_off + s];
+        s_ptr[s] = src < 0 ? nullptr : (src == P.p ? P.y : P.X + (int64_t)src * P.ld);
+    }
+    for (size_t e = tid; e < P.stages * stage_doubles; e += kGramThreads) stages[e] = 0.0;
+    __syncthreads();
+
+    double *out = P.part + ((size_t)blockIdx.y * P.n_tiles + blockIdx.x) * (size_t)(P.tile_blocks * 256);
+    // blocks of this warp: q = warp + 16 b < n_blk
+    const int nb = tm.n_blk > warp ? (tm.n_blk - warp + kGramWarps - 1) / kGramWarps : 0;
+    bool partial = false;
+    for (int b = 0; b < nb; ++b) partial |= P.blocks[tm.blk_off + warp + kGramWarps * b].mask != 15u;
+#define FOKL_ROWS(NB)                                                                                                  \
+    if (partial) gram_rows<WARPS, NB, true>(P, tm, stages, s_ptr, stage_doubles, stride, n_lo, n_hi, nk, tid, lane, warp, out); \
+    else gram_rows<WARPS, NB, false>(P, tm, stages, s_ptr, stage_doubles, stride, n_lo, n_hi, nk, tid, lane, warp, out);        \
+    break;
+    switch (nb) {
+    case 0: gram_rows<WARPS, 0, false>(P, tm, stages, s_ptr, stage_doubles, stride, n_lo, n_hi, nk, tid, lane, warp, out); break;
+    case 1: FOKL_ROWS(1)
+    case 2: FOKL_ROWS(2)
+    case 3: FOKL_ROWS(3)
+    default: FOKL_ROWS(4)
+    }
+#undef FOKL_ROWS
+}
+
+// Sum the row splits in a fixed order and scatter the fragments to the (p + 1) x c block.  One thread per
+// accumulator element of every block of every tile.
+__global__ void gram_reduce_kernel(const double *__restrict__ part, int nsplit, int n_tiles, const GramTileMeta *tiles,
+                                   const GramBlockMeta *blocks, const int32_t *slot_arow, const int32_t *slot_bcol,
+                                   int c, int tile_blocks, double *__restrict__ out)
+{
+    const int tile = blockIdx.y;
+    const GramTileMeta tm = tiles[tile];
+    const int total = tm.n_blk * 256;
+    const size_t tile_stride = (size_t)tile_blocks * 256;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+        const int q = e >> 8, f = (e >> 6) & 3, idx = e & 63;
+        const GramBlockMeta bm = blocks[tm.blk_off + q];
+        if (!(bm.mask >> f & 1u)) continue;                 // fragment not computed: the block entry stays 0
+        const int arow = slot_arow[tm.slot_off + bm.a_slot + 8 * (f >> 1) + (idx >> 3)];
+        const int bcol = slot_bcol[tm.slot_off + bm.b_slot + 8 * (f & 1) + (idx & 7)];
+        if (arow < 0 || bcol < 0) continue;
         double s = 0.0;
-        for (int k = 0; k < nsplit; ++k) s += part[(size_t)k * elems + e];
-        out[e] = s;
+        const double *src = part + (size_t)tile * tile_stride + e;
+        for (int k = 0; k < nsplit; ++k) s += src[(size_t)k * n_tiles * tile_stride];
+        out[(size_t)arow * c + bcol] = s;
     }
 }
 
@@ -181,36 +254,91 @@ extern "C" int fokl_gram_update(fokl_ctx *ctx, const double *X, int64_t ld, int6
         FOKL_FAIL(ctx, FOKL_EINVAL, "gram_update: bad argument");
     if ((ld % 2) != 0 || ((uintptr_t)X % 16) != 0 || ((uintptr_t)y % 16) != 0)
         FOKL_FAIL(ctx, FOKL_EINVAL, "gram_update: X and y must be 16-byte aligned and ld even");
+    if (p_old + c + 1 > 65000) FOKL_FAIL(ctx, FOKL_EINVAL, "gram_update: more than 65000 columns");
     int rc = fokl_bind_device(ctx);
     if (rc) return rc;
     const int p = p_old + c;
-    const int tiles_a = (p + 1 + TM - 1) / TM, tiles_b = (c + TN - 1) / TN;
-    const int tiles = tiles_a * tiles_b;
-    const int64_t chunks = (n + KB - 1) / KB;
-    int64_t want = ((int64_t)ctx->num_sms * 4 + tiles - 1) / tiles;          // ~2 waves of 2 CTAs/SM
-    int64_t max_split = std::max<int64_t>(1, chunks / 8);                    // >= 8 slabs per CTA
-    int nsplit = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(want, max_split), 65535));
-    int64_t rows_per_split = ((chunks + nsplit - 1) / nsplit) * KB;
+
+    // CTA shape: 16 warps / one CTA per SM, or 8 warps / two co-resident CTAs per SM with half the blocks each (one
+    // CTA's barrier and pipeline-fill bubbles then overlap the other's DMMAs).  FOKL_GRAM_WARPS overrides (tuning).
+    int warps = 8;
+    if (const char *e = getenv("FOKL_GRAM_WARPS")) warps = atoi(e) == 16 ? 16 : 8;
+    const int ctas_per_sm = fokl::kGramMaxWarps / warps;
+    const int kTileBlocks = fokl::gram_tile_blocks(warps);
+    // shared-memory budget -> slot cap at the smallest slab (KB = 16), then the deepest slab that fits the plan
+    const size_t smem_total = ctx->smem_optin ? ctx->smem_optin : 48 * 1024;
+    const size_t smem_cap = (warps == 16 ? smem_total : (smem_total + 1024) / 2 - 1024) - 1024;
+    auto smem_need = [&](int slots, int kb, int stages) {
+        return (size_t)stages * slots * (kb + kPad) * sizeof(double) + (size_t)slots * sizeof(double *);
+    };
+    int cap = 32;
+    while (smem_need(cap + 16, 16, kMaxStages) <= smem_cap) cap += 16;
+    const fokl::GramPlan plan = fokl::gram_make_plan(p_old, c, cap, warps);
+    const int n_tiles = (int)plan.tiles.size();
+    if (n_tiles == 0 || plan.max_slots > cap) FOKL_FAIL(ctx, FOKL_ESTATE, "gram_update: empty or oversized plan");
+    // deepest slab that fits (fewer CTA-wide barriers per row), giving up one ring stage for it if necessary
+    int kb = 16, stages = kMaxStages;
+    for (int cand_kb = 64; cand_kb >= 32; cand_kb /= 2) {
+        if (n < (int64_t)cand_kb * 4) continue;
+        if (smem_need(plan.max_slots, cand_kb, 4) <= smem_cap) { kb = cand_kb; stages = 4; break; }
+        if (smem_need(plan.max_slots, cand_kb, 3) <= smem_cap) { kb = cand_kb; stages = 3; break; }
+    }
+    int kb_shift = 0;
+    while ((2 << kb_shift) < kb) ++kb_shift;
+
+    // row splits: about one resident CTA slot each
+    const int64_t chunks = (n + kb - 1) / kb;
+    const int slots_total = ctx->num_sms * ctas_per_sm;
+    int64_t want = std::max<int64_t>(1, slots_total / n_tiles);
+    if (n_tiles > slots_total) want = 1;
+    int nsplit = (int)std::max<int64_t>(1, std::min<int64_t>(want, chunks));
+    int64_t rows_per_split = ((chunks + nsplit - 1) / nsplit) * kb;
     nsplit = (int)((n + rows_per_split - 1) / rows_per_split);
-    const int64_t elems = (int64_t)(p + 1) * c;
+
+    // upload the plan (one buffer)
+    const size_t n_slots = plan.slot_src.size(), n_blocks = plan.blocks.size();
+    size_t off_tiles = 0;
+    size_t off_src = off_tiles + (size_t)n_tiles * sizeof(GramTileMeta);
+    size_t off_arow = off_src + n_slots * sizeof(int32_t);
+    size_t off_bcol = off_arow + n_slots * sizeof(int32_t);
+    size_t off_blk = off_bcol + n_slots * sizeof(int32_t);
+    size_t meta_bytes = off_blk + n_blocks * sizeof(GramBlockMeta);
+    std::vector<unsigned char> host(meta_bytes);
+    memcpy(host.data() + off_tiles, plan.tiles.data(), (size_t)n_tiles * sizeof(GramTileMeta));
+    memcpy(host.data() + off_src, plan.slot_src.data(), n_slots * sizeof(int32_t));
+    memcpy(host.data() + off_arow, plan.slot_arow.data(), n_slots * sizeof(int32_t));
+    memcpy(host.data() + off_bcol, plan.slot_bcol.data(), n_slots * sizeof(int32_t));
+    memcpy(host.data() + off_blk, plan.blocks.data(), n_blocks * sizeof(GramBlockMeta));
+    const size_t part_bytes = (size_t)nsplit * n_tiles * kTileBlocks * 256 * sizeof(double);
+    const size_t part_off = (meta_bytes + 255) & ~(size_t)255;
+    unsigned char *buf = (unsigned char *)fokl_scratch(ctx, fokl_ctx::B_GRAM, part_off + part_bytes);
+    if (!buf) return FOKL_ENOMEM;
+    // stream-ordered behind any kernel still reading the previous plan; pageable source = staged before return
+    FOKL_CUDA(ctx, cudaMemcpyAsync(buf, host.data(), meta_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    FOKL_CUDA(ctx, cudaMemsetAsync(block, 0, (size_t)(p + 1) * c * sizeof(double), ctx->stream));
 
     GramParams P;
-    P.X = X; P.y = y; P.ld = ld; P.n = n; P.p_old = p_old; P.c = c; P.tiles_b = tiles_b;
+    P.X = X; P.y = y; P.ld = ld; P.n = n; P.p = p;
+    P.kb = kb; P.kb_shift = kb_shift; P.stages = stages; P.max_slots = plan.max_slots;
     P.rows_per_split = rows_per_split;
-    if (nsplit == 1) {
-        P.out = block;
+    P.tiles = reinterpret_cast<const GramTileMeta *>(buf + off_tiles);
+    P.slot_src = reinterpret_cast<const int32_t *>(buf + off_src);
+    P.blocks = reinterpret_cast<const GramBlockMeta *>(buf + off_blk);
+    P.part = reinterpret_cast<double *>(buf + part_off);
+    P.n_tiles = n_tiles;
+    P.tile_blocks = kTileBlocks;
+    const size_t smem = smem_need(plan.max_slots, kb, stages);
+    if (warps == 16) {
+        FOKL_CUDA(ctx, cudaFuncSetAttribute(gram_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
+        gram_kernel<16><<<dim3(n_tiles, nsplit), 512, smem, ctx->stream>>>(P);
     } else {
-        double *part = (double *)fokl_scratch(ctx, fokl_ctx::B_GRAM, (size_t)nsplit * elems * sizeof(double));
-        if (!part) return FOKL_ENOMEM;
-        P.out = part;
+        FOKL_CUDA(ctx, cudaFuncSetAttribute(gram_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
+        gram_kernel<8><<<dim3(n_tiles, nsplit), 256, smem, ctx->stream>>>(P);
     }
-    FOKL_CUDA(ctx, cudaFuncSetAttribute(gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGramSmem));
-    gram_kernel<<<dim3(tiles, nsplit), kGramThreads, kGramSmem, ctx->stream>>>(P);
     FOKL_LAUNCH_CHECK(ctx);
-    if (nsplit > 1) {
-        int blocks = (int)std::min<int64_t>((elems + 255) / 256, 1024);
-        gram_reduce_kernel<<<blocks, 256, 0, ctx->stream>>>(P.out, nsplit, elems, block);
-        FOKL_LAUNCH_CHECK(ctx);
-    }
+    gram_reduce_kernel<<<dim3(kTileBlocks, n_tiles), 256, 0, ctx->stream>>>(
+        P.part, nsplit, n_tiles, P.tiles, P.blocks, reinterpret_cast<const int32_t *>(buf + off_arow),
+        reinterpret_cast<const int32_t *>(buf + off_bcol), c, kTileBlocks, block);
+    FOKL_LAUNCH_CHECK(ctx);
     return FOKL_OK;
 }

@@ -353,12 +353,13 @@ class FitResult(dict):
 
 def fit(inputs, data, phis, kernel=CUBIC, a=4, b=None, atau=4, btau=None, tolerance=3, burnin=1000,
         draws=1000, gimmie=False, way3=False, threshav=0.05, threshstda=0.5, threshstdb=2, aic=False,
-        basis='c', literal=True, threads=1, on_gibbs=None, console=False, gram_hook=None):
+        basis='c', literal=True, threads=1, on_gibbs=None, console=False, gram_hook=None, on_substage=None):
     """Forward selection of FR:1561-1760 on already-normalised `inputs` (N x M in [0, 1]) and
     `data` (N x 1).  relats_in = [] only (anything else crashes upstream at FR:1631).
 
     basis: 'c' (C helper) or 'py' (literal Python triple loop, the reference's real cost profile).
     on_gibbs(info): optional callback per `gibbs` invocation (for recording golden vectors / timing).
+    on_substage(ind, ev): optional callback at the end of every substage (where the reference prints [ind, ev]).
     gram_hook(discmtx) -> (XtX, Xty) or None: parity-harness hook, see gibbs_from_X.
     Returns FitResult(betas, mtx, evs, n_gibbs, betas_full)."""
     inputs = np.asarray(inputs, dtype=np.float64)
@@ -452,6 +453,8 @@ def fit(inputs, data, phis, kernel=CUBIC, a=4, b=None, atau=4, btau=None, tolera
             X = xers
             if console:
                 print([ind, float(ev)])
+            if on_substage is not None:
+                on_substage(ind, float(ev))
             if np.size(evs) > 0:
                 if ev < np.min(evs):
                     betas = beters

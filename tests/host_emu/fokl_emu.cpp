@@ -172,3 +172,43 @@ void emu_philox_gammas(uint64_t seed, uint64_t stream, int draws, double shape, 
 }
 
 }  // extern "C"
+
+// ---- K2 work plan (csrc/gram_plan.h): host walk of tiles / blocks / fragments exactly as gram_kernel +
+// gram_reduce_kernel use them.  A is [n][p + 1] row-major with y as the last column; out is (p + 1) x c and must be
+// pre-filled by the caller; cover (same shape, int) counts how many times each entry was written.
+#include "../../fokl-gpy_b200/csrc/gram_plan.h"
+extern "C" int emu_gram_plan(const double *A, int64_t n, int p_old, int c, int max_slots_cap, int warps, double *out, int32_t *cover,
+                             int32_t *stats /* n_tiles, max_slots, total_blocks, max_blocks_per_tile */)
+{
+    const int p = p_old + c;
+    GramPlan pl = gram_make_plan(p_old, c, max_slots_cap, warps);
+    const int kTileBlocks = gram_tile_blocks(warps);
+    stats[0] = (int32_t)pl.tiles.size();
+    stats[1] = pl.max_slots;
+    stats[2] = (int32_t)pl.blocks.size();
+    stats[3] = 0;
+    for (const GramTileMeta &tm : pl.tiles) {
+        if (tm.n_blk > stats[3]) stats[3] = tm.n_blk;
+        if (tm.n_blk > kTileBlocks || tm.n_slots > max_slots_cap || (tm.n_slots % 8) != 0) return -1;
+        for (int q = 0; q < tm.n_blk; ++q) {
+            const GramBlockMeta bm = pl.blocks[tm.blk_off + q];
+            if (bm.a_slot + 16 > tm.n_slots || bm.b_slot + 16 > tm.n_slots) return -2;
+            if (bm.mask == 0 || bm.mask > 15) return -4;
+            for (int f = 0; f < 4; ++f)
+                for (int idx = 0; idx < 64; ++idx) {
+                    if (!(bm.mask >> f & 1)) continue;
+                    const int sa = tm.slot_off + bm.a_slot + 8 * (f >> 1) + (idx >> 3);
+                    const int sb = tm.slot_off + bm.b_slot + 8 * (f & 1) + (idx & 7);
+                    const int arow = pl.slot_arow[sa], bcol = pl.slot_bcol[sb];
+                    if (arow < 0 || bcol < 0) continue;
+                    const int ca = pl.slot_src[sa], cb = pl.slot_src[sb];
+                    if (ca != arow || cb != p_old + bcol || cb >= p) return -3;
+                    double s = 0.0;
+                    for (int64_t i = 0; i < n; ++i) s += A[i * (p + 1) + ca] * A[i * (p + 1) + cb];
+                    out[(size_t)arow * c + bcol] = s;
+                    cover[(size_t)arow * c + bcol] += 1;
+                }
+        }
+    }
+    return 0;
+}

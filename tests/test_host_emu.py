@@ -178,3 +178,28 @@ def test_kill_loop_matches_sequential_oracle_loop(phis_cubic, aic):
     # a duplicated column is reported, not scored
     G2 = G.copy(); G2[:, 2] = G2[:, 1]; G2[2, :] = G2[1, :]
     assert emu.kill_loop(G2, Xty, idx, [idx.index(c) for c in cand_cols], bv0, bv1, hyp, evmin=full)['bad'] == 1
+
+
+@pytest.mark.parametrize('warps', [16, 8])
+@pytest.mark.parametrize('p_old,c,cap', [(1, 1, 352), (1, 8, 352), (9, 28, 352), (37, 56, 352), (50, 168, 352),
+                                          (71, 168, 352), (3, 5, 32), (130, 40, 64), (20, 300, 128), (400, 17, 352)])
+def test_gram_work_plan_covers_the_block_exactly_once(p_old, c, cap, warps):
+    """K2 plan (csrc/gram_plan.h): every entry of [X_old X_new y]' X_new that fokl_gram_scatter reads (all old / y rows,
+    and the new x new part on or above the diagonal) is produced by exactly one fragment of one block of one tile, from
+    the right pair of columns; tiles respect the block and shared-memory-slot budgets."""
+    rng = np.random.default_rng(p_old * 1000 + c)
+    n = 7
+    A = rng.standard_normal((n, p_old + c + 1))
+    rc, out, cover, st = emu.gram_plan(A, p_old, c, cap, warps)
+    assert rc == 0, rc
+    ref = A.T @ A[:, p_old:p_old + c]
+    a, j = np.meshgrid(np.arange(p_old + c + 1) - p_old, np.arange(c), indexing='ij')
+    needed = ~((a > j) & (a < c))
+    assert np.all(cover[needed] == 1)
+    assert np.all(cover <= 1)
+    got = cover == 1
+    assert np.allclose(out[got], ref[got], rtol=1e-13, atol=1e-13)
+    assert st['max_blocks_per_tile'] <= 4 * warps and st['max_slots'] <= cap
+    # balanced: no tile is much smaller than the largest unless the slot cap forced a cut
+    if p_old + c + 32 <= cap:
+        assert st['n_tiles'] == -(-st['blocks'] // (4 * warps))

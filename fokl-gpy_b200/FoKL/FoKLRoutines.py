@@ -259,7 +259,7 @@ class FoKL:
                               "'AutoTranspose=False' to disable.", category=UserWarning)
 
         if data is not None:
-            data = np.squeeze(np.array(data))
+            data = np.squeeze(np.array(data) if _copy else np.asarray(data))
             if data.dtype != datatype:
                 data = np.array(data, dtype=datatype)
                 warnings.warn(f"'data' was converted to float{bit}. May require user-confirmation that "
@@ -713,10 +713,12 @@ class FoKL:
 
         resident = isinstance(inputs, DeviceDataset)
         ds = None
+        device_moments = resident      # b / btau defaults from the device's sum(y), sum(y^2) instead of host np.var
         if not resident and default_for_fit['clean'] is True and inputs is not None and data is not None:
             ds = self._clean_on_device(inputs, data, kwargs_to_clean)
         if ds is not None:
             data = self.data
+            device_moments = True      # large dataset cleaned in HBM: no extra host pass over `data`
         elif not resident:
             failed = False
             if default_for_fit['clean'] is True:
@@ -781,7 +783,7 @@ class FoKL:
         # b / btau defaults from the data moments (FR:1322-1348: np.var ddof 0, |mean|)
         a, b, atau, btau = self.a, self.b, self.atau, self.btau
         if btau is None or b is None:
-            if resident:
+            if device_moments or eng.world > 1:   # row shards: only the all-reduced moments describe the whole dataset
                 data_mean = eng.sum_y / n
                 sigmasq = eng.yty / n - data_mean ** 2
             else:

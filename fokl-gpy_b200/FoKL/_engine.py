@@ -107,7 +107,13 @@ class Engine:
         self.profile = None      # set to {} to collect CUDA-event timings per stage (bench.py)
 
     # ------------------------------------------------------------------------------------------------
+    def release(self):
+        """Free the design-matrix buffer kept between fits."""
+        self.X = None
+        self.Pcap = 0
+
     def close(self):
+        self.X = None
         if getattr(self, 'ctx', None) is not None and self.ctx:
             self.lib.fokl_ctx_destroy(self.ctx)
             self.ctx = None
@@ -240,10 +246,14 @@ class Engine:
         torch = self.torch
         self.ds = ds
         n = ds.n
-        self.ld = ds.ldx
-        self.Pcap = 0
-        self.X = None
-        self._ensure_columns(64 if n * 64 * 8 < (4 << 30) else 16)
+        if self.X is None or self.X.shape[1] != ds.ldx:
+            # first fit with this row count: start small, grow geometrically.  Later fits of the same shape reuse the
+            # design-matrix buffer at the capacity the previous fit reached (no allocator churn, no growth copies);
+            # Engine.release() / close() gives it back.
+            self.ld = ds.ldx
+            self.Pcap = 0
+            self.X = None
+            self._ensure_columns(64 if n * 64 * 8 < (4 << 30) else 16)
         self._ck(self.lib.fokl_fill_ones(self.ctx, self.X.data_ptr(), n))
         self.P = 0
         mom = torch.zeros(3, dtype=torch.float64, device=self.device)

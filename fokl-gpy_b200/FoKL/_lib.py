@@ -9,8 +9,10 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(os.path.dirname(_HERE), 'csrc')
 SO_PATH = os.path.join(CSRC, 'libfokl_b200.so')
+if os.environ.get('FOKL_B200_LIB'):        # kernel-variant experiments (tools/): another build of the same sources
+    SO_PATH = os.path.abspath(os.environ['FOKL_B200_LIB'])
 SOURCES = ['ctx.cu', 'basis.cu', 'gram.cu', 'candidates.cu']
-HEADERS = ['fokl_ctx.cuh', 'fokl_math.cuh', 'cand_math.cuh']
+HEADERS = ['fokl_ctx.cuh', 'fokl_math.cuh', 'cand_math.cuh', 'gram_plan.h']
 
 ABI_VERSION = 1
 KERNEL_CUBIC, KERNEL_BERNOULLI = 0, 1

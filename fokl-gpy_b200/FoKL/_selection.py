@@ -215,10 +215,14 @@ def forward_select(engine, hy, m, n_phis, console=True, rng='philox', eager=Fals
             evmin = ev
             cur = 0
 
+            with np.errstate(invalid='ignore'):
+                always = bv1 > hy['threshstdb']                       # proposed whatever the intercept is
+                maybe = bv1 > hy['threshstda']
+
             def proposals(start, icpt_now):
-                thr = hy['threshav'] * icpt_now
-                return [i for i in range(start, vm)
-                        if (bv1[i] > hy['threshstdb']) or (bv1[i] > hy['threshstda'] and bv0[i] < thr)]
+                with np.errstate(invalid='ignore'):
+                    mask = always | (maybe & (bv0 < hy['threshav'] * icpt_now))
+                return (np.nonzero(mask[start:])[0] + start).tolist()
 
             if mode == _lib.RNG_INJECTED or eager:
                 # literal order: one `gibbs`-equivalent evaluation (eig + chain) per proposal.  In parity mode the
@@ -305,8 +309,10 @@ def forward_select(engine, hy, m, n_phis, console=True, rng='philox', eager=Fals
                             if 'icpt_true' not in rd and (sens_from[rd['i'] + 1] or k_ == len(rounds) - 1)]
                     if todo:
                         rr = run([rd['cols'] for rd in todo], [True] * len(todo), [rd['stream'] for rd in todo])
+                        stats_h = rr.stats.cpu().numpy()          # one read-back for the whole batch
                         for slot, rd in enumerate(todo):
-                            rd['icpt_true'] = abs(float(rr.stats_of(slot)[2, 0].item()))
+                            # mean(beters[h0:, 0]) of this model: row 2, column 0 of its 3 x p statistics block
+                            rd['icpt_true'] = abs(float(stats_h[3 * rr.vec_off[slot] + 2 * rr.p[slot]]))
                             rd['ev_true'] = float(rr.ev[slot]) + aic_adj * len(rd['cols'])
                             rd['rr'], rd['slot'] = rr, slot
                     redo = None

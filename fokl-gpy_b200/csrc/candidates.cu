@@ -6,6 +6,7 @@
 // BIC FR:1551-1554, and the reductions over the draws at FR:1656-1658, 1671.
 // The numerical core lives in cand_math.cuh (shared with the host emulation used by the CPU tests).
 #include "fokl_ctx.cuh"
+#include <stdlib.h>
 #include "cand_math.cuh"
 #include <cooperative_groups.h>
 #include <algorithm>
@@ -713,6 +714,9 @@ extern "C" int fokl_candidates_eval(fokl_ctx *ctx, const double *G, int64_t ldg,
         }
         cudaGetLastError();
     }
+    int force_cs = 0;                    // tuning knob for tools/eig_batch_diag.py: force the eigensolver's cluster size
+    if (const char *e = getenv("FOKL_EIGJ_CS")) force_cs = atoi(e);
+    if (force_cs != 1 && force_cs != 2 && force_cs != 4 && force_cs != 8 && force_cs != 16) force_cs = 0;
     std::vector<CandMeta> meta(n_cand);
     std::vector<int32_t> chain_list;
     std::vector<int> eig_class(n_cand, 0);
@@ -729,6 +733,10 @@ extern "C" int fokl_candidates_eval(fokl_ctx *ctx, const double *G, int64_t ldg,
         {
             int cs = 1;
             while (cs < ctx->max_cluster && (p + 1) / 2 > (kEigJThreads / 32) * cs) cs *= 2;   // one pair per warp if possible
+            // ... but a batch should fit the device in one wave: a cluster of cs CTAs finishes a candidate ~cs^0.6
+            // times faster, n_cand * cs / num_sms waves cost cs times more (profiles/r01_eig_batch_diag.txt)
+            while (cs > 1 && (int64_t)n_cand * cs > ctx->num_sms) cs /= 2;
+            if (force_cs > 0) cs = force_cs;
             while (cs <= kEigJMaxCluster && eigj_smem_bytes(p, cs) > smem_cap) cs *= 2;
             if (cs > ctx->max_cluster || p > 64 * kEigJMaxNV) m.pad = 1;   // too large: two-matrix Jacobi in global memory
             else eig_class[c] = cs;
@@ -799,6 +807,31 @@ extern "C" int fokl_candidates_eval(fokl_ctx *ctx, const double *G, int64_t ldg,
     k.sigsqd0 = hyp->sigsqd0; k.tausqd0 = hyp->tausqd0; k.yty = hyp->yty; k.sum_y = hyp->sum_y;
     k.n = (double)hyp->n; k.draws = D; k.from0 = hyp->stat_from0; k.from1 = hyp->stat_from1;
 
+    // ---- chain workspaces (allocated up front: the Philox variate tables are filled while the eigensolver runs) --------
+    const bool philox = rng_mode == FOKL_RNG_PHILOX;
+    double *d_gam = nullptr, *d_var = nullptr, *d_betas = nullptr, *d_sigs = nullptr, *d_taus = nullptr;
+    if (n_chain > 0) {
+        if (hyp->stat_from0 < 0 || hyp->stat_from0 >= D || hyp->stat_from1 < 0 || hyp->stat_from1 >= D)
+            FOKL_FAIL(ctx, FOKL_EINVAL, "candidates_eval: statistic windows outside the chain");
+        size_t c_bytes = 256 + ((size_t)D * gam + (philox ? (size_t)D * (gam + 2 * (size_t)n_chain) : 0)) * sizeof(double);
+        char *ccur = (char *)fokl_scratch(ctx, fokl_ctx::B_CAND_C, c_bytes);
+        if (!ccur) return FOKL_ENOMEM;
+        d_gam = carve<double>(ccur, (size_t)D * gam);
+        d_var = philox ? carve<double>(ccur, (size_t)D * (gam + 2 * (size_t)n_chain)) : nullptr;
+        size_t d_bytes = 256 + (betas ? 0 : (size_t)D * vec * sizeof(double)) + (sigs ? 0 : (size_t)D * n_cand * sizeof(double)) +
+                         (taus ? 0 : (size_t)D * n_cand * sizeof(double));
+        char *ecur = (char *)fokl_scratch(ctx, fokl_ctx::B_CAND_D, d_bytes);
+        if (!ecur) return FOKL_ENOMEM;
+        d_betas = betas ? betas : carve<double>(ecur, (size_t)D * vec);
+        d_sigs = sigs ? sigs : carve<double>(ecur, (size_t)D * n_cand);
+        d_taus = taus ? taus : carve<double>(ecur, (size_t)D * n_cand);
+    }
+    ChainParams CP;
+    CP.meta = d_meta; CP.chain_list = d_chain; CP.k = k; CP.lamb = d_lamb; CP.ct = d_ct;
+    CP.rng_mode = rng_mode; CP.seed = seed; CP.variates = variates; CP.var_philox = d_var; CP.sign_fix = sign_fix;
+    CP.gam = d_gam; CP.sigs = d_sigs; CP.taus = d_taus; CP.info = info;
+    bool variates_forked = false;
+
     // ---- eig + betahat + BIC -------------------------------------------------------------------------------
     // (1) Cholesky factor of every candidate (into its Q slot); (2) per cluster-size class, the cluster Jacobi on the
     // factor + betahat + BIC; (3) the two-matrix Jacobi for candidates whose Gram is not positive definite or that do
@@ -821,7 +854,23 @@ extern "C" int fokl_candidates_eval(fokl_ctx *ctx, const double *G, int64_t ldg,
         J.lam_raw = d_lam_all; J.scratch = d_scratch; J.ct = d_ct; J.lamb = d_lamb; J.Q = d_Q; J.betahat = d_betahat;
         J.ev = ev; J.info = info;
         FOKL_CUDA(ctx, cudaFuncSetAttribute(cand_eigj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
-        for (int q = 0, cs = 1; q < 5; ++q, cs *= 2) {
+        // one launch per cluster size; the launches are independent of one another, so the second and later ones go to
+        // auxiliary streams and fill the SMs the first leaves idle (largest clusters = longest candidates first)
+        int used_aux = 0;
+        bool first = true;
+        rc = fokl_fork_point(ctx);           // after the Cholesky pre-pass, before any eigensolver launch
+        if (rc) return rc;
+        if (n_chain > 0 && philox) {
+            // Philox table of every chain (independent of the eigensolver): last auxiliary stream
+            cudaStream_t sv = fokl_aux_fork(ctx, fokl_ctx::kAux - 1);
+            if (!sv) FOKL_FAIL(ctx, FOKL_ECUDA, "candidates_eval: auxiliary stream");
+            const int64_t per_chain = (int64_t)D * (pmax_chain + 2);
+            dim3 grid((unsigned)std::min<int64_t>((per_chain + 255) / 256, 2048), (unsigned)n_chain);
+            cand_variates_kernel<<<grid, 256, 0, sv>>>(CP);
+            FOKL_LAUNCH_CHECK(ctx);
+            variates_forked = true;
+        }
+        for (int q = 4, cs = 16; q >= 0; --q, cs /= 2) {
             const int cnt = class_begin[q + 1] - class_begin[q];
             if (cnt == 0) continue;
             size_t smem = 0;
@@ -831,11 +880,18 @@ extern "C" int fokl_candidates_eval(fokl_ctx *ctx, const double *G, int64_t ldg,
                 threads = std::max(threads, eigj_threads(meta[eig_list[e]].p, cs));
             }
             J.list = d_eig_list + class_begin[q];
+            cudaStream_t st = ctx->stream;
+            if (!first && used_aux < fokl_ctx::kAux - 1) {
+                st = fokl_aux_fork(ctx, used_aux);
+                if (!st) FOKL_FAIL(ctx, FOKL_ECUDA, "candidates_eval: auxiliary stream");
+                ++used_aux;
+            }
+            first = false;
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3((unsigned)(cnt * cs));
             cfg.blockDim = dim3((unsigned)threads);
             cfg.dynamicSmemBytes = smem;
-            cfg.stream = ctx->stream;
+            cfg.stream = st;
             cudaLaunchAttribute attr[1];
             attr[0].id = cudaLaunchAttributeClusterDimension;
             attr[0].val.clusterDim.x = (unsigned)cs;
@@ -845,6 +901,10 @@ extern "C" int fokl_candidates_eval(fokl_ctx *ctx, const double *G, int64_t ldg,
             cfg.numAttrs = 1;
             FOKL_CUDA(ctx, cudaLaunchKernelEx(&cfg, cand_eigj_kernel, J));
             FOKL_LAUNCH_CHECK(ctx);
+        }
+        for (int i = 0; i < used_aux; ++i) {
+            rc = fokl_aux_join(ctx, i);
+            if (rc) return rc;
         }
     }
     {
@@ -872,36 +932,15 @@ extern "C" int fokl_candidates_eval(fokl_ctx *ctx, const double *G, int64_t ldg,
     }
     (void)any_fallback;
     if (n_chain == 0) return FOKL_OK;
-    if (hyp->stat_from0 < 0 || hyp->stat_from0 >= D || hyp->stat_from1 < 0 || hyp->stat_from1 >= D)
-        FOKL_FAIL(ctx, FOKL_EINVAL, "candidates_eval: statistic windows outside the chain");
 
     // ---- chain -------------------------------------------------------------------------------------------------
-    const bool philox = rng_mode == FOKL_RNG_PHILOX;
-    size_t c_bytes = 256 + ((size_t)D * gam + (philox ? (size_t)D * (gam + 2 * (size_t)n_chain) : 0)) * sizeof(double);
-    char *ccur = (char *)fokl_scratch(ctx, fokl_ctx::B_CAND_C, c_bytes);
-    if (!ccur) return FOKL_ENOMEM;
-    double *d_gam = carve<double>(ccur, (size_t)D * gam);
-    double *d_var = philox ? carve<double>(ccur, (size_t)D * (gam + 2 * (size_t)n_chain)) : nullptr;
-    size_t d_bytes = 256 + (betas ? 0 : (size_t)D * vec * sizeof(double)) + (sigs ? 0 : (size_t)D * n_cand * sizeof(double)) +
-                     (taus ? 0 : (size_t)D * n_cand * sizeof(double));
-    char *ecur = (char *)fokl_scratch(ctx, fokl_ctx::B_CAND_D, d_bytes);
-    if (!ecur) return FOKL_ENOMEM;
-    double *d_betas = betas ? betas : carve<double>(ecur, (size_t)D * vec);
-    double *d_sigs = sigs ? sigs : carve<double>(ecur, (size_t)D * n_cand);
-    double *d_taus = taus ? taus : carve<double>(ecur, (size_t)D * n_cand);
     {
-        ChainParams P;
-        P.meta = d_meta; P.chain_list = d_chain; P.k = k; P.lamb = d_lamb; P.ct = d_ct;
-        P.rng_mode = rng_mode; P.seed = seed; P.variates = variates; P.var_philox = d_var; P.sign_fix = sign_fix;
-        P.gam = d_gam; P.sigs = d_sigs; P.taus = d_taus; P.info = info;
-        if (philox) {
-            const int64_t per_chain = (int64_t)D * (pmax_chain + 2);
-            dim3 grid((unsigned)std::min<int64_t>((per_chain + 255) / 256, 2048), (unsigned)n_chain);
-            cand_variates_kernel<<<grid, 256, 0, ctx->stream>>>(P);
-            FOKL_LAUNCH_CHECK(ctx);
+        if (variates_forked) {
+            rc = fokl_aux_join(ctx, fokl_ctx::kAux - 1);
+            if (rc) return rc;
         }
         const int chain_threads = std::max(32, std::min(kChainThreads, 32 * ((pmax_chain / 2 + 31) / 32)));
-        cand_chain_kernel<<<n_chain, chain_threads, 0, ctx->stream>>>(P);
+        cand_chain_kernel<<<n_chain, chain_threads, 0, ctx->stream>>>(CP);
         FOKL_LAUNCH_CHECK(ctx);
     }
     if (!betas && !stats) return FOKL_OK;

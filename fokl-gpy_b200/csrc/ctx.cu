@@ -35,6 +35,32 @@ void *fokl_scratch(fokl_ctx *ctx, int which, size_t bytes)
     return b.ptr;
 }
 
+int fokl_fork_point(fokl_ctx *ctx)
+{
+    if (!ctx->ev_fork) FOKL_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    FOKL_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+    return FOKL_OK;
+}
+
+cudaStream_t fokl_aux_fork(fokl_ctx *ctx, int i)
+{
+    if (i < 0 || i >= fokl_ctx::kAux || !ctx->ev_fork) return nullptr;
+    if (!ctx->aux[i]) {
+        if (cudaStreamCreateWithFlags(&ctx->aux[i], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    }
+    if (cudaStreamWaitEvent(ctx->aux[i], ctx->ev_fork, 0) != cudaSuccess) return nullptr;
+    return ctx->aux[i];
+}
+
+int fokl_aux_join(fokl_ctx *ctx, int i)
+{
+    if (i < 0 || i >= fokl_ctx::kAux || !ctx->aux[i]) FOKL_FAIL(ctx, FOKL_ESTATE, "aux stream join without fork");
+    FOKL_CUDA(ctx, cudaEventRecord(ctx->ev_join[i], ctx->aux[i]));
+    FOKL_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join[i], 0));
+    return FOKL_OK;
+}
+
 extern "C" int fokl_ctx_create(fokl_ctx **out, int device, void *cuda_stream)
 {
     if (!out) return FOKL_EINVAL;
@@ -72,6 +98,11 @@ extern "C" int fokl_ctx_destroy(fokl_ctx *ctx)
     if (ctx->cubic_tab) cudaFree(ctx->cubic_tab);
     if (ctx->bern_tab) cudaFree(ctx->bern_tab);
     if (ctx->d_flag) cudaFree(ctx->d_flag);
+    for (int i = 0; i < fokl_ctx::kAux; ++i) {
+        if (ctx->aux[i]) { cudaStreamSynchronize(ctx->aux[i]); cudaStreamDestroy(ctx->aux[i]); }
+        if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
+    }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return FOKL_OK;

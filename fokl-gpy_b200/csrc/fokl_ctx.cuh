@@ -32,6 +32,13 @@ struct fokl_ctx {
     // deferred error flag written by kernels (device int), checked in fokl_ctx_synchronize
     int *d_flag = nullptr;
 
+    // auxiliary streams (lazily created, non-blocking): independent kernels of one call -- the eigensolver launches
+    // of different cluster sizes, the variate tables -- run side by side and are joined back into `stream` by events
+    enum { kAux = 3 };
+    cudaStream_t aux[kAux] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr;
+    cudaEvent_t ev_join[kAux] = {nullptr, nullptr, nullptr};
+
     // growable scratch buffers, indexed by purpose
     enum { B_META = 0, B_BASIS, B_GRAM, B_CAND_A, B_CAND_B, B_CAND_C, B_CAND_D, B_MISC, B_COUNT };
     fokl_buf bufs[B_COUNT];
@@ -57,6 +64,13 @@ struct fokl_ctx {
 
 // returns nullptr (and sets ctx->err) on failure
 void *fokl_scratch(fokl_ctx *ctx, int which, size_t bytes);
+
+// Fork point: everything enqueued on ctx->stream so far.  fokl_aux_fork(i) then makes aux stream `i` wait for the
+// most recent fork point and returns it (nullptr on error).
+int fokl_fork_point(fokl_ctx *ctx);
+cudaStream_t fokl_aux_fork(fokl_ctx *ctx, int i);
+// Join: make ctx->stream wait for everything enqueued on aux stream `i`.
+int fokl_aux_join(fokl_ctx *ctx, int i);
 
 static inline int fokl_bind_device(fokl_ctx *ctx)
 {

@@ -6,7 +6,7 @@
 // and of its symmetric X_new' X_new part only the 8 x 8 fragments on or above the diagonal.
 //
 // Work decomposition (gram_plan.h): the needed fragments are grouped into 2 x 2-fragment blocks and the blocks into
-// tiles of <= 4 blocks per warp; a CTA (8 or 16 warps, 4 blocks = 16 DMMA accumulators per warp) owns one tile for one
+// tiles of <= 4 blocks per warp; a CTA (16 warps, 4 blocks = 16 DMMA accumulators per warp) owns one tile for one
 // contiguous range of rows.  X is column-major, so both MMA operands are contiguous along the reduction (row) index: the CTA
 // streams KB-row slabs of the tile's distinct operand columns ("slots", each staged ONCE however many blocks use it)
 // into shared memory with cp.async (3/4-stage ring, [slot][KB + 4] layout = conflict-free fragment loads) and issues
@@ -132,14 +132,17 @@ __device__ __forceinline__ void gram_rows(const GramParams &P, const GramTileMet
         if (stages_n == 4) cp_async_wait<2>();
         else cp_async_wait<1>();
         __syncthreads();
-        {
-            const int nxt = kt + stages_n - 1;
-            if (nxt < nk) load_stage(nxt, nxt % stages_n);
-            cp_async_commit();
-        }
-        if (NB == 0) continue;
+        // refill the ring one k-block into the stage (when the slab has more than one), so the DMMAs restart right after
+        // the barrier instead of behind the cp.async issue: K2 94 -> 85 ms per cfg4 fit (profiles/r01_gram_variants.txt)
+        const int load_at = (NB == 0 || P.kb < 32) ? 0 : 16;
         const double *S = stages + (size_t)(kt % stages_n) * stage_doubles;
         for (int k0 = 0; k0 < P.kb; k0 += 16) {
+            if (k0 == load_at) {
+                const int nxt = kt + stages_n - 1;
+                if (nxt < nk) load_stage(nxt, nxt % stages_n);
+                cp_async_commit();
+                if (NB == 0) break;
+            }
 #pragma unroll
             for (int kk = 0; kk < 16; kk += 4) {
                 double a0[NBA], a1[NBA], b0[NBA], b1[NBA];
@@ -205,7 +208,9 @@ __global__ void __launch_bounds__(WARPS * 32, 16 / WARPS) gram_kernel(const Gram
     // blocks of this warp: q = warp + 16 b < n_blk
     const int nb = tm.n_blk > warp ? (tm.n_blk - warp + kGramWarps - 1) / kGramWarps : 0;
     bool partial = false;
+#ifndef FOKL_GRAM_NOMASK
     for (int b = 0; b < nb; ++b) partial |= P.blocks[tm.blk_off + warp + kGramWarps * b].mask != 15u;
+#endif
 #define FOKL_ROWS(NB)                                                                                                  \
     if (partial) gram_rows<WARPS, NB, true>(P, tm, stages, s_ptr, stage_doubles, stride, n_lo, n_hi, nk, tid, lane, warp, out); \
     else gram_rows<WARPS, NB, false>(P, tm, stages, s_ptr, stage_doubles, stride, n_lo, n_hi, nk, tid, lane, warp, out);        \
@@ -259,10 +264,10 @@ extern "C" int fokl_gram_update(fokl_ctx *ctx, const double *X, int64_t ld, int6
     if (rc) return rc;
     const int p = p_old + c;
 
-    // CTA shape: 16 warps / one CTA per SM, or 8 warps / two co-resident CTAs per SM with half the blocks each (one
-    // CTA's barrier and pipeline-fill bubbles then overlap the other's DMMAs).  FOKL_GRAM_WARPS overrides (tuning).
-    int warps = 8;
-    if (const char *e = getenv("FOKL_GRAM_WARPS")) warps = atoi(e) == 16 ? 16 : 8;
+    // CTA shape: 16 warps, one CTA per SM.  (Measured alternative, profiles/r01_gram_variants.txt: 8 warps with two
+    // co-resident CTAs per SM and half the blocks each is 1.65x slower -- more duplicated operand traffic and
+    // instruction-cache misses between the two CTAs' code paths.)
+    const int warps = 16;
     const int ctas_per_sm = fokl::kGramMaxWarps / warps;
     const int kTileBlocks = fokl::gram_tile_blocks(warps);
     // shared-memory budget -> slot cap at the smallest slab (KB = 16), then the deepest slab that fits the plan
@@ -328,13 +333,8 @@ extern "C" int fokl_gram_update(fokl_ctx *ctx, const double *X, int64_t ld, int6
     P.n_tiles = n_tiles;
     P.tile_blocks = kTileBlocks;
     const size_t smem = smem_need(plan.max_slots, kb, stages);
-    if (warps == 16) {
-        FOKL_CUDA(ctx, cudaFuncSetAttribute(gram_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
-        gram_kernel<16><<<dim3(n_tiles, nsplit), 512, smem, ctx->stream>>>(P);
-    } else {
-        FOKL_CUDA(ctx, cudaFuncSetAttribute(gram_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
-        gram_kernel<8><<<dim3(n_tiles, nsplit), 256, smem, ctx->stream>>>(P);
-    }
+    FOKL_CUDA(ctx, cudaFuncSetAttribute(gram_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
+    gram_kernel<16><<<dim3(n_tiles, nsplit), 512, smem, ctx->stream>>>(P);
     FOKL_LAUNCH_CHECK(ctx);
     gram_reduce_kernel<<<dim3(kTileBlocks, n_tiles), 256, 0, ctx->stream>>>(
         P.part, nsplit, n_tiles, P.tiles, P.blocks, reinterpret_cast<const int32_t *>(buf + off_arow),

@@ -327,6 +327,21 @@ def main():
     def stage(name):
         return prof.get(name, {'ms': 0.0, 'calls': 0})
 
+    # DRAM traffic per launch from the committed `ncu --set full` capture of this same command (tools/ncu_traffic.py
+    # over the .ncu-rep of one cfg4 fit); a number taken under the profiler is evidence, not a timing
+    traffic = {}
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'r01_ncu_traffic.json')) as f:
+            traffic = json.load(f)
+    except Exception:
+        pass
+
+    def traffic_of(kernel):
+        t = traffic.get(kernel)
+        if not t or a.workload != 'cfg4' or a.n or world != 1:
+            return None
+        return t['traffic_bytes_per_launch']
+
     tot_ms = ms
     shares = {k: v['ms'] / tot_ms for k, v in prof.items()}
     b = stage('basis')
@@ -334,7 +349,8 @@ def main():
     if b['calls']:
         ach = b['bytes'] / (b['ms'] * 1e-3) / 1e9
         roof = {'kernel': 'basis_kernel (K1)', 'bound': 'hbm', 'achieved': ach, 'peak': hbm_peak, 'unit': 'GB/s',
-                'frac': ach / hbm_peak, 'traffic': None, 'peak_source': hbm_src, 'launches': b['calls'],
+                'frac': ach / hbm_peak, 'traffic': traffic_of('basis_kernel'), 'peak_source': hbm_src,
+                'launches': b['calls'],
                 'avg_launch_ms': b['ms'] / b['calls'], 'bytes_per_launch': b['bytes'] / b['calls'],
                 'share_of_step': shares.get('basis')}
     g = stage('gram')
@@ -342,7 +358,7 @@ def main():
     if g['calls'] and fp64_peak:
         ach = g['flops'] / (g['ms'] * 1e-3) / 1e12
         roof_g = {'kernel': 'gram_kernel (K2, FP64 DMMA)', 'bound': 'tensor', 'achieved': ach, 'peak': fp64_peak,
-                  'unit': 'TFLOP/s', 'frac': ach / fp64_peak, 'traffic': None,
+                  'unit': 'TFLOP/s', 'frac': ach / fp64_peak, 'traffic': traffic_of('gram_kernel'),
                   'peak_source': 'in-run cuBLAS DGEMM 4096^3 (torch.matmul f64), best of 5', 'launches': g['calls'],
                   'avg_launch_ms': g['ms'] / g['calls'], 'share_of_step': shares.get('gram')}
 

@@ -435,14 +435,19 @@ class Engine:
         res.betahat, res.lamb, res.Q = betahat, lamb, Q
         # ---- refine near-interpolating / degenerate fits with an N-length residual pass (FR:1551) --------
         if refine_tol is not None and refine_tol > 0:
-            n = float(self.n_global)
-            var_y = self.yty / n - (self.sum_y / n) ** 2
-            with np.errstate(all='ignore'):
-                siglik = np.exp((res.ev - p * np.log(n) - (n - 1.0)) / n)
-            bad = ~np.isfinite(res.ev) | ~(siglik > refine_tol * var_y)
+            bad = self.refine_mask(res.ev, p, refine_tol)
             for c in np.nonzero(bad)[0]:
                 res.ev[c] = self.residual_bic(col_sets[c], betahat[vec_off[c]:vec_off[c] + p[c]])
         return res
+
+    def refine_mask(self, ev, p, refine_tol=1e-7):
+        """Candidates whose Gram-only BIC is not trustworthy (non-finite, or a residual variance below refine_tol of
+        var(y): catastrophic cancellation) and must be recomputed from an N-length residual pass."""
+        n = float(self.n_global)
+        var_y = self.yty / n - (self.sum_y / n) ** 2
+        with np.errstate(all='ignore'):
+            siglik = np.exp((ev - p * np.log(n) - (n - 1.0)) / n)
+        return ~np.isfinite(ev) | ~(siglik > refine_tol * var_y)
 
     def kill_scores(self, cols, positions, hyp):
         """BIC of the model `cols` minus each column at `positions` (indices into cols), plus the model's own BIC,

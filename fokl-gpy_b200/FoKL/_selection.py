@@ -141,7 +141,7 @@ def forward_select(engine, hy, m, n_phis, console=True, rng='philox', eager=Fals
     n_gibbs = 0
     n_batches = 0
 
-    def run(col_sets, chains, ids):
+    def run(col_sets, chains, ids, refine=True):
         nonlocal n_batches
         n_batches += 1
         sid = np.asarray(ids, dtype=np.uint64)
@@ -179,7 +179,7 @@ def forward_select(engine, hy, m, n_phis, console=True, rng='philox', eager=Fals
         flags = np.array([bool(v) for v in chains], dtype=np.uint8)
         any_chain = bool(flags.any())
         return engine.evaluate(col_sets, hyp, rng_mode=mode if any_chain else _lib.RNG_NONE, run_chain=flags,
-                               seed=seed, stream_ids=sid, want_betas=any_chain)
+                               seed=seed, stream_ids=sid, want_betas=any_chain, refine_tol=1e-7 if refine else None)
 
     ind = 1
     finished = False
@@ -308,13 +308,43 @@ def forward_select(engine, hy, m, n_phis, console=True, rng='philox', eager=Fals
                     todo = [rd for k_, rd in enumerate(rounds)
                             if 'icpt_true' not in rd and (sens_from[rd['i'] + 1] or k_ == len(rounds) - 1)]
                     if todo:
-                        rr = run([rd['cols'] for rd in todo], [True] * len(todo), [rd['stream'] for rd in todo])
-                        stats_h = rr.stats.cpu().numpy()          # one read-back for the whole batch
-                        for slot, rd in enumerate(todo):
-                            # mean(beters[h0:, 0]) of this model: row 2, column 0 of its 3 x p statistics block
-                            rd['icpt_true'] = abs(float(stats_h[3 * rr.vec_off[slot] + 2 * rr.p[slot]]))
-                            rd['ev_true'] = float(rr.ev[slot]) + aic_adj * len(rd['cols'])
-                            rd['rr'], rd['slot'] = rr, slot
+                        # The models of a batch are independent: with several ranks each evaluates every world-th one
+                        # (all ranks hold the full Gram) and the two scalars per model that drive the loop are summed
+                        # into place by one allreduce, so every rank takes the same decisions.
+                        world = engine.world if engine.dist is not None else 1
+                        mine = list(range(engine.rank, len(todo), world)) if world > 1 else list(range(len(todo)))
+                        vals = np.zeros((len(todo) + 1, 2))
+
+                        def chains_of(which, refine):
+                            rr = run([todo[i]['cols'] for i in which], [True] * len(which),
+                                     [todo[i]['stream'] for i in which], refine=refine)
+                            stats_h = rr.stats.cpu().numpy()      # one read-back for the whole batch
+                            for slot, i in enumerate(which):
+                                # mean(beters[h0:, 0]) of this model: row 2, column 0 of its 3 x p statistics block
+                                vals[i, 0] = abs(float(stats_h[3 * rr.vec_off[slot] + 2 * rr.p[slot]]))
+                                vals[i, 1] = float(rr.ev[slot]) + aic_adj * len(todo[i]['cols'])
+                                todo[i]['rr'], todo[i]['slot'] = rr, slot
+                            return rr
+
+                        if world > 1:
+                            if mine:
+                                rr_ = chains_of(mine, refine=False)
+                                vals[len(todo), 0] = float(np.any(engine.refine_mask(rr_.ev, rr_.p)))
+                            t = torch.from_numpy(vals).to(engine.device)
+                            engine._allreduce(t)
+                            vals = t.cpu().numpy()
+                            for i, rd in enumerate(todo):
+                                rd['owner'] = i % world
+                            if vals[len(todo), 0] > 0:
+                                # some model needs the N-length residual pass (a collective): evaluate the batch replicated
+                                vals = np.zeros((len(todo) + 1, 2))
+                                chains_of(list(range(len(todo))), refine=True)
+                                for rd in todo:
+                                    rd['owner'] = -1
+                        else:
+                            chains_of(mine, refine=True)
+                        for i, rd in enumerate(todo):
+                            rd['icpt_true'], rd['ev_true'] = float(vals[i, 0]), float(vals[i, 1])
                     redo = None
                     for k_, rd in enumerate(rounds):
                         if 'icpt_true' not in rd or rd['icpt_true'] == rd['icpt_used']:
@@ -325,7 +355,17 @@ def forward_select(engine, hy, m, n_phis, console=True, rng='philox', eager=Fals
                             break
                     if redo is None:
                         last_rd = rounds[-1]
-                        cur_betas = last_rd['rr'].betas_of(last_rd['slot']).clone()
+                        owner = last_rd.get('owner', -1)          # -1: every rank ran this model's chain itself
+                        if owner < 0 or owner == engine.rank:
+                            cur_betas = last_rd['rr'].betas_of(last_rd['slot']).clone()
+                        if owner >= 0:
+                            # the accepted model's draws live on the rank that ran its chain
+                            if owner != engine.rank:
+                                cur_betas = torch.empty((D, len(last_rd['cols'])), dtype=torch.float64,
+                                                        device=engine.device)
+                            g = engine.group
+                            src = engine.dist.get_global_rank(g, owner) if g is not None else owner
+                            engine.dist.broadcast(cur_betas, src=src, group=g)
                         icpt = last_rd['icpt_true']
                         evmin = last_rd['ev_true']        # report the spectral-path BIC of the accepted model
                         killed = list(state['killed'])

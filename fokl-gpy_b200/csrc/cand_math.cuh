@@ -463,6 +463,78 @@ FOKL_HD int gibbs_chain(const Team &t, int p, const double *lamb, const double *
     return bad;
 }
 
+#if defined(__CUDACC__)
+// The same draw loop for ONE warp holding E elements per lane in registers (p <= 32 E): the three sums are five
+// shuffle steps with no shared memory and no CTA barrier on the per-draw critical path, and the variate rows are
+// prefetched two draws ahead into registers.  The D draws are sequential, so a chain's time is D times the latency
+// of one draw -- this halves it against the multi-warp version for the model sizes of a fit (p <= 256).
+template <int E>
+__device__ int gibbs_chain_warp(int lane, int p, const double *lamb, const double *ct, const CandConst &k,
+                                const double *variates, const double *sign_fix, double *gam, double *sigs, double *taus)
+{
+    const int D = k.draws;
+    const int w = p + 2;
+    double ssig = sqrt(k.sigsqd0), itau = 1.0 / k.tausqd0;
+    int bad = 0;
+    double l[E], c[E], f[E], z[E], zr[E];
+    bool h[E];
+#pragma unroll
+    for (int q = 0; q < E; ++q) {
+        const int e = lane + 32 * q;
+        h[q] = e < p;
+        l[q] = h[q] ? lamb[e] : 1.0;
+        c[q] = h[q] ? ct[e] : 0.0;
+        f[q] = (h[q] && sign_fix) ? sign_fix[e] : 1.0;
+        z[q] = h[q] ? f[q] * variates[e] : 0.0;
+        zr[q] = (h[q] && D > 1) ? variates[w + e] : 0.0;
+    }
+    double g1 = variates[p], g2 = variates[p + 1];
+    double ig1 = 1.0 / g1, ig2 = 1.0 / g2;
+    double gr1 = D > 1 ? variates[w + p] : 1.0, gr2 = D > 1 ? variates[w + p + 1] : 1.0;
+    for (int d = 0; d < D; ++d) {
+        const double *r2 = variates + (int64_t)(d + 2) * w;
+        const bool more = d + 2 < D;
+        double zq[E];
+#pragma unroll
+        for (int q = 0; q < E; ++q) zq[q] = (more && h[q]) ? r2[lane + 32 * q] : 0.0;
+        const double gq1 = more ? r2[p] : 1.0, gq2 = more ? r2[p + 1] : 1.0;
+        double s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        double *grow = gam + (int64_t)d * p;
+#pragma unroll
+        for (int q = 0; q < E; ++q) {
+            const double rs = FOKL_RSQRT(l[q] + itau);
+            const double g = h[q] ? (rs * rs) * c[q] + (ssig * rs) * z[q] : 0.0;
+            if (h[q]) grow[lane + 32 * q] = g;
+            s1 += l[q] * g * g; s2 += g * c[q]; s3 += g * g;
+        }
+        // next row's values (loaded one iteration ago): off the critical path, overlaps the reduction
+        double zn[E];
+#pragma unroll
+        for (int q = 0; q < E; ++q) zn[q] = f[q] * zr[q];
+        const double ign1 = 1.0 / gr1, ign2 = 1.0 / gr2;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+            s3 += __shfl_xor_sync(0xffffffffu, s3, o);
+        }
+        const double bstar = k.b + 0.5 * (s1 - 2.0 * s2 + k.yty + s3 * itau);
+        double sig, rb;
+        if (bstar < 0.0) { sig = nan(""); rb = sig; bad = 1; }
+        else { sig = bstar * ig1; rb = FOKL_RCP(bstar); }
+        const double btau_star = (0.5 * g1 * rb) * s3 + k.btau;
+        itau = g2 * FOKL_RCP(btau_star);
+        ssig = sqrt(sig);
+        if (lane == 0) { sigs[d] = sig; taus[d] = btau_star * ig2; }
+#pragma unroll
+        for (int q = 0; q < E; ++q) { z[q] = zn[q]; zr[q] = zq[q]; }
+        g1 = gr1; g2 = gr2; ig1 = ign1; ig2 = ign2;
+        gr1 = gq1; gr2 = gq2;
+    }
+    return bad;
+}
+#endif
+
 }  // namespace fokl
 
 // ---- kill-proposal scores without refactorising each candidate ------------------------------------------
@@ -619,31 +691,47 @@ FOKL_HD void team_atomic_add(int *addr, int v)
 }
 
 // one (reverse) sweep of pivot k on the symmetric (ld x ld) matrix T; sign = +1 sweep, -1 reverse sweep
-FOKL_HD void sweep_pivot(const Team &t, double *T, int ld, int k, double sign)
+// One pivot of the sweep operator on the symmetric (ld x ld) tableau T.  rowbuf (ld doubles of shared memory) takes a
+// copy of pivot row k, after which every entry is final in ONE pass: T[i][j] -= (ck[i] ck[j]) / d off the pivot
+// cross, sign * ck[i] / d on it, -1 / d at the pivot.  A warp walks whole rows (consecutive lanes = consecutive
+// addresses) four strides at a time, so each lane has four independent loads in flight: the tableau of a 220-column
+// model lives in L2, and the earlier one-element-at-a-time walk paid the full L2 latency per element.
+FOKL_HD void sweep_pivot(const Team &t, double *T, int ld, int k, double sign, double *rowbuf)
 {
-    const double invD = 1.0 / T[(int64_t)k * ld + k];
-    const double *ck = T + (int64_t)k * ld;
-    const int total = ld * ld;
-    for (int e = t.tid; e < total; e += t.nthr) {
-        int j = e / ld, i = e - j * ld;
-        if (i == k || j == k) continue;
-        T[e] -= (ck[i] * ck[j]) * invD;
-    }
+    for (int i = t.tid; i < ld; i += t.nthr) rowbuf[i] = T[(int64_t)k * ld + i];
     t.sync();
-    for (int i = t.tid; i < ld; i += t.nthr) {
-        if (i == k) continue;
-        double v = sign * ck[i] * invD;
-        T[(int64_t)k * ld + i] = v;
-        T[(int64_t)i * ld + k] = v;
+    const double invD = 1.0 / rowbuf[k];
+    const int step = t.nlane;
+    for (int j = t.warp; j < ld; j += t.nwarp) {
+        double *Tj = T + (int64_t)j * ld;
+        const double ckj = rowbuf[j];
+        if (j == k) {
+            for (int i = t.lane; i < ld; i += step) Tj[i] = (i == k) ? -invD : sign * rowbuf[i] * invD;
+            continue;
+        }
+        const double vk = sign * ckj * invD;
+        int i = t.lane;
+        for (; i + 3 * step < ld; i += 4 * step) {
+            const double a0 = Tj[i], a1 = Tj[i + step], a2 = Tj[i + 2 * step], a3 = Tj[i + 3 * step];
+            const double r0 = a0 - (rowbuf[i] * ckj) * invD, r1 = a1 - (rowbuf[i + step] * ckj) * invD;
+            const double r2 = a2 - (rowbuf[i + 2 * step] * ckj) * invD, r3 = a3 - (rowbuf[i + 3 * step] * ckj) * invD;
+            Tj[i] = (i == k) ? vk : r0;
+            Tj[i + step] = (i + step == k) ? vk : r1;
+            Tj[i + 2 * step] = (i + 2 * step == k) ? vk : r2;
+            Tj[i + 3 * step] = (i + 3 * step == k) ? vk : r3;
+        }
+        for (; i < ld; i += step) {
+            const double r0 = Tj[i] - (rowbuf[i] * ckj) * invD;
+            Tj[i] = (i == k) ? vk : r0;
+        }
     }
-    t.sync();
-    if (t.tid == 0) T[(int64_t)k * ld + k] = -invD;
     t.sync();
 }
 
 FOKL_HD int kill_loop(const Team &t, const double *G, int64_t ldg, const double *Xty, const int *idx, int p,
                       const int *cand_pos, const double *bv0, const double *bv1, int vm, const CandConst &c,
-                      const KillLoopIn &in, double *T, int *out_i, double *out_ev, int *sh /* 4 shared ints */)
+                      const KillLoopIn &in, double *T, int *out_i, double *out_ev, int *sh /* 4 shared ints */,
+                      double *rowbuf /* p + 1 shared doubles */)
 {
     const int ld = p + 1;
     const double ybar = c.sum_y / c.n;
@@ -666,7 +754,7 @@ FOKL_HD int kill_loop(const Team &t, const double *G, int64_t ldg, const double 
         const double d = T[(int64_t)k * ld + k];
         if (!(d > 1e-11 * G[(int64_t)idx[k] * ldg + idx[k]])) { bad = 1; break; }   // not numerically positive definite
         t.sync();
-        sweep_pivot(t, T, ld, k, 1.0);
+        sweep_pivot(t, T, ld, k, 1.0, rowbuf);
     }
     int n_acc = 0, tested = 0, pa = p, cur = in.start;
     double evmin = in.evmin;
@@ -702,7 +790,7 @@ FOKL_HD int kill_loop(const Team &t, const double *G, int64_t ldg, const double 
         const double sig = (sse + tqy * tqy / (-tqq)) / c.n;
         evmin = (double)(pa - 1) * ln_n - 2.0 * (-(c.n / 2.0) * log(sig) - (c.n - 1.0) / 2.0) + in.aic_adj * (double)(pa - 1);
         t.sync();
-        sweep_pivot(t, T, ld, q, -1.0);
+        sweep_pivot(t, T, ld, q, -1.0, rowbuf);
         if (t.tid == 0) {
             out_i[3 + n_acc] = hit;
             out_i[3 + vm + n_acc] = tested;

@@ -505,6 +505,20 @@ __global__ void __launch_bounds__(kChainThreads) cand_chain_kernel(const ChainPa
     if (t.tid == 0 && bad) atomicOr(P.info + c, 1);
 }
 
+// One warp per chain, E elements per lane in registers (models of up to 32 E columns).
+template <int E>
+__global__ void __launch_bounds__(32) cand_chain_warp_kernel(const ChainParams P)
+{
+    const int c = P.chain_list[blockIdx.x];
+    const CandMeta m = P.meta[c];
+    const int D = P.k.draws;
+    const double *var = (P.rng_mode == FOKL_RNG_INJECTED ? P.variates : P.var_philox) + variates_offset(P, m, c);
+    const double *sf = P.sign_fix ? P.sign_fix + m.vec_off : nullptr;
+    int bad = fokl::gibbs_chain_warp<E>(threadIdx.x, m.p, P.lamb + m.vec_off, P.ct + m.vec_off, P.k, var, sf,
+                                        P.gam + (int64_t)D * m.gam_off, P.sigs + (int64_t)D * c, P.taus + (int64_t)D * c);
+    if (threadIdx.x == 0 && bad) atomicOr(P.info + c, 1);
+}
+
 // betas[k][i] = sum_r Gamma[k][r] * Q[r*p + i]   (FR:1528 in the eigenbasis: beta = Q gamma)
 struct BetasParams {
     const CandMeta *meta;
@@ -655,10 +669,11 @@ __global__ void __launch_bounds__(kKillThreads) kill_loop_kernel(const KillLoopP
     extern __shared__ __align__(16) double sh[];
     const Team t = make_team();
     int *shi = reinterpret_cast<int *>(sh);                       // 4 ints
+    double *rowbuf = sh + 2;                                      // p + 1 doubles (+ 1 pad): copy of the pivot row
     const int64_t need = (int64_t)(P.p + 1) * (P.p + 1);
-    double *T = (need <= P.smem_doubles) ? (sh + 2) : P.T_global;
+    double *T = (need <= P.smem_doubles) ? (sh + 2 + ((P.p + 2) & ~1)) : P.T_global;
     fokl::kill_loop(t, P.G, P.ldg, P.Xty, P.cols, P.p, P.cand_pos, P.bv0, P.bv1, P.vm, P.c, P.in, T, P.out_i, P.out_ev,
-                    shi);
+                    shi, rowbuf);
 }
 
 template <typename T>
@@ -939,8 +954,16 @@ extern "C" int fokl_candidates_eval(fokl_ctx *ctx, const double *G, int64_t ldg,
             rc = fokl_aux_join(ctx, fokl_ctx::kAux - 1);
             if (rc) return rc;
         }
-        const int chain_threads = std::max(32, std::min(kChainThreads, 32 * ((pmax_chain / 2 + 31) / 32)));
-        cand_chain_kernel<<<n_chain, chain_threads, 0, ctx->stream>>>(CP);
+        if (pmax_chain <= 64) {
+            cand_chain_warp_kernel<2><<<n_chain, 32, 0, ctx->stream>>>(CP);
+        } else if (pmax_chain <= 128) {
+            cand_chain_warp_kernel<4><<<n_chain, 32, 0, ctx->stream>>>(CP);
+        } else if (pmax_chain <= 256) {
+            cand_chain_warp_kernel<8><<<n_chain, 32, 0, ctx->stream>>>(CP);
+        } else {
+            const int chain_threads = std::max(32, std::min(kChainThreads, 32 * ((pmax_chain / 2 + 31) / 32)));
+            cand_chain_kernel<<<n_chain, chain_threads, 0, ctx->stream>>>(CP);
+        }
         FOKL_LAUNCH_CHECK(ctx);
     }
     if (!betas && !stats) return FOKL_OK;
@@ -1024,7 +1047,8 @@ extern "C" int fokl_kill_loop(fokl_ctx *ctx, const double *G, int64_t ldg, const
     int rc = fokl_bind_device(ctx);
     if (rc) return rc;
     const size_t smem_cap = ctx->smem_optin ? ctx->smem_optin : 48 * 1024;
-    const int smem_t_cap = (int)(smem_cap / sizeof(double)) - 2;
+    const int head = 2 + ((p + 2) & ~1);                         // flags + pivot-row copy
+    const int smem_t_cap = (int)(smem_cap / sizeof(double)) - head;
     const int64_t need = (int64_t)(p + 1) * (p + 1);
     const bool in_smem = need <= smem_t_cap;
 
@@ -1061,7 +1085,7 @@ extern "C" int fokl_kill_loop(fokl_ctx *ctx, const double *G, int64_t ldg, const
     P.in.icpt = kp->icpt; P.in.evmin = kp->evmin; P.in.aic_adj = kp->aic_adj; P.in.start = kp->start;
     P.T_global = Tg; P.out_i = out_i; P.out_ev = out_ev;
     P.smem_doubles = in_smem ? (int)need : 0;
-    size_t smem = (size_t)(2 + (in_smem ? need : 0)) * sizeof(double);
+    size_t smem = (size_t)(head + (in_smem ? need : 0)) * sizeof(double);
     FOKL_CUDA(ctx, cudaFuncSetAttribute(kill_loop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
     kill_loop_kernel<<<1, kKillThreads, smem, ctx->stream>>>(P);
     FOKL_LAUNCH_CHECK(ctx);

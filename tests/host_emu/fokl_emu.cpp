@@ -151,7 +151,8 @@ int emu_kill_loop(const double *G, int64_t ldg, const double *Xty, const int32_t
     KillLoopIn in;
     in.threshav = params[0]; in.threshstda = params[1]; in.threshstdb = params[2]; in.icpt = params[3];
     in.evmin = params[4]; in.aic_adj = params[5]; in.start = start;
-    return kill_loop(t, G, ldg, Xty, idx, p, cand_pos, bv0, bv1, vm, c, in, T.data(), out_i, out_ev, sh);
+    std::vector<double> rowbuf(p + 1);
+    return kill_loop(t, G, ldg, Xty, idx, p, cand_pos, bv0, bv1, vm, c, in, T.data(), out_i, out_ev, sh, rowbuf.data());
 }
 
 void emu_philox_normals(uint64_t seed, uint64_t stream, int draws, int p, double *out)

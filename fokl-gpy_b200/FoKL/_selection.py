@@ -271,28 +271,41 @@ def forward_select(engine, hy, m, n_phis, console=True, rng='philox', eager=Fals
                 # draws (FR:1690) -- are run afterwards as one batch, only for the rounds whose remaining proposals can
                 # depend on that threshold, and every such round is re-checked against its true chain (the loop is
                 # re-run from the first round that differs), so the outcome is exactly that of the sequential loop.
-                bv1_sens = (bv1 > hy['threshstda']) & ~(bv1 > hy['threshstdb'])
-                sens_from = np.zeros(vm + 1, dtype=bool)          # any threshold-dependent candidate at index >= i
-                for i in range(vm - 1, -1, -1):
-                    sens_from[i] = sens_from[i + 1] or bool(bv1_sens[i])
+                # Round k's chain matters only through the threshold it sets for the candidates examined before the next
+                # acceptance, i.e. indices (i_k, i_{k+1}] of the sorted list (to the end for the last round): if none of
+                # them is threshold-dependent (threshstda < bv1 <= threshstdb) the chain of round k is never looked at.
+                with np.errstate(invalid='ignore'):
+                    bv1_sens = (bv1 > hy['threshstda']) & ~(bv1 > hy['threshstdb'])
+                sens_cum = np.concatenate([[0], np.cumsum(bv1_sens)])      # threshold-dependent candidates in [0, j)
+
+                def span(k_):
+                    return rounds[k_]['i'] + 1, (vm if k_ == len(rounds) - 1 else rounds[k_ + 1]['i'] + 1)
+
+                def prop_mask(icpt_now):
+                    with np.errstate(invalid='ignore'):
+                        return always | (maybe & (bv0 < hy['threshav'] * icpt_now))
                 state = dict(killed=[], evmin=evmin, cur=0, icpt=icpt, calls=call_id[0], gibbs=n_gibbs)
                 rounds = []        # accepted kills: dict(i, cols, stream, icpt_used, gibbs_after [, icpt_true, ev_true])
                 fallback = False
                 while True:
                     if state['cur'] < vm and proposals(state['cur'], state['icpt']):
-                        model = [c for c in full if c not in set(state['killed'])]
-                        where = {c: k_ for k_, c in enumerate(model)}
-                        pos = [where.get(int(cand_cols[i]), 1) for i in range(vm)]
+                        # column bookkeeping on numpy masks (the lists are up to 160 models x 220 columns per substage)
+                        alive = np.ones(len(full), dtype=bool)
+                        alive[np.asarray(state['killed'], dtype=np.int64)] = False
+                        model = np.nonzero(alive)[0].astype(np.int32)
+                        where = np.ones(len(full), dtype=np.int32)            # killed candidates: any valid position
+                        where[model] = np.arange(len(model), dtype=np.int32)
+                        pos = where[cand_cols]
                         r = engine.kill_loop(model, pos, bv0, bv1, hyp, hy['threshav'], hy['threshstda'],
                                              hy['threshstdb'], state['icpt'], state['evmin'], aic_adj, state['cur'])
                         n_batches += 1
                         if r['bad']:
                             fallback = True
                             break
-                        cols_k = model
                         for k_ in range(r['n_acc']):
                             i = int(r['acc'][k_])
-                            cols_k = [c for c in cols_k if c != int(cand_cols[i])]
+                            alive[int(cand_cols[i])] = False
+                            cols_k = np.nonzero(alive)[0].astype(np.int32)
                             rounds.append(dict(i=i, cols=cols_k, stream=state['calls'] + int(r['calls'][k_]),
                                                gibbs_after=state['gibbs'] + int(r['calls'][k_]),
                                                ev_dev=float(r['ev'][k_]), icpt_used=state['icpt']))
@@ -305,8 +318,11 @@ def forward_select(engine, hy, m, n_phis, console=True, rng='philox', eager=Fals
                     if not rounds:
                         break
                     # chains of the accepted models that matter: rounds with threshold-dependent proposals left, + last
-                    todo = [rd for k_, rd in enumerate(rounds)
-                            if 'icpt_true' not in rd and (sens_from[rd['i'] + 1] or k_ == len(rounds) - 1)]
+                    todo = []
+                    for k_, rd in enumerate(rounds):
+                        lo_, hi_ = span(k_)
+                        if 'icpt_true' not in rd and (k_ == len(rounds) - 1 or sens_cum[hi_] > sens_cum[lo_]):
+                            todo.append(rd)
                     if todo:
                         # The models of a batch are independent: with several ranks each evaluates every world-th one
                         # (all ranks hold the full Gram) and the two scalars per model that drive the loop are summed
@@ -349,8 +365,8 @@ def forward_select(engine, hy, m, n_phis, console=True, rng='philox', eager=Fals
                     for k_, rd in enumerate(rounds):
                         if 'icpt_true' not in rd or rd['icpt_true'] == rd['icpt_used']:
                             continue
-                        nxt = rd['i'] + 1
-                        if proposals(nxt, rd['icpt_true']) != proposals(nxt, rd['icpt_used']):
+                        lo_, hi_ = span(k_)
+                        if not np.array_equal(prop_mask(rd['icpt_true'])[lo_:hi_], prop_mask(rd['icpt_used'])[lo_:hi_]):
                             redo = k_
                             break
                     if redo is None:
@@ -376,7 +392,7 @@ def forward_select(engine, hy, m, n_phis, console=True, rng='philox', eager=Fals
                     rd = rounds[redo]
                     rounds = rounds[:redo + 1]
                     rd['icpt_used'] = rd['icpt_true']
-                    state = dict(killed=[c for c in full if c not in set(rd['cols'])], evmin=rd['ev_true'],
+                    state = dict(killed=sorted(set(full) - set(int(c_) for c_ in rd['cols'])), evmin=rd['ev_true'],
                                  cur=rd['i'] + 1, icpt=rd['icpt_true'], calls=rd['stream'], gibbs=rd['gibbs_after'])
                 if fallback:
                     # Gram not numerically positive definite (p >= N regimes): literal loop, one spectral evaluation

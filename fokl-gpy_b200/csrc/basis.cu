@@ -21,6 +21,7 @@
 #include "fokl_ctx.cuh"
 #include "fokl_math.cuh"
 #include <algorithm>
+#include <stdlib.h>
 #include <string.h>
 #include <type_traits>
 #include <vector>
@@ -57,6 +58,8 @@ struct BasisParams {
     int *flag;
     int64_t n_tiles;
     int tab_stride;              // cubic: doubles between the coefficient planes of a staged slot
+    int direct;                  // every term is one factor (main effects): phase 1 stores straight to its column
+                                 // (FactorMeta.pad = the term index), no factor buffer, no barrier, no phase 2
     unsigned long long terms[kMaxTermsPerLaunch];   // TermMeta words
 };
 static_assert(sizeof(BasisParams) <= 32000, "kernel parameter space");
@@ -95,7 +98,7 @@ __global__ void __launch_bounds__(kThreads) basis_kernel(const __grid_constant__
                                                        : (size_t)P.n_slots * P.n_piece;
     tab_doubles = (tab_doubles + 1) & ~(size_t)1;   // keep F 16-byte aligned
     double *s_F = s_tab + tab_doubles;
-    FactorMeta *s_fac = reinterpret_cast<FactorMeta *>(s_F + (size_t)(P.n_factors + 1) * ROWS);
+    FactorMeta *s_fac = reinterpret_cast<FactorMeta *>(s_F + ((NF == 1 && P.direct) ? (size_t)0 : (size_t)(P.n_factors + 1) * ROWS));
 
     const int tid = threadIdx.x;
     // ---- stage coefficient tables and metadata ------------------------------------------------
@@ -114,7 +117,8 @@ __global__ void __launch_bounds__(kThreads) basis_kernel(const __grid_constant__
             for (int e = tid; e < per; e += kThreads) s_tab[(size_t)s * per + e] = __ldg(src + e);
         }
     }
-    for (int e = tid; e < ROWS; e += kThreads) s_F[(size_t)P.n_factors * ROWS + e] = 1.0;
+    if (!(NF == 1 && P.direct))
+        for (int e = tid; e < ROWS; e += kThreads) s_F[(size_t)P.n_factors * ROWS + e] = 1.0;
     for (int f = tid; f < P.n_factors; f += kThreads) s_fac[f] = P.factors[f];
     __syncthreads();
 
@@ -173,13 +177,23 @@ __global__ void __launch_bounds__(kThreads) basis_kernel(const __grid_constant__
 #pragma unroll
                     for (int r = 0; r < RPT; ++r) v[r] = eval_factor_bernoulli(cp, fm.d + 1, xv[r]);
                 }
-                if (RPT == 2) {
+                if (NF == 1 && P.direct) {
+                    double *d = P.out + (int64_t)fm.pad * P.ld + row0;
+                    if (RPT == 2 && row0 + 1 < P.n) {
+                        __stcs(reinterpret_cast<double2 *>(d), make_double2(v[0], v[RPT - 1]));
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < RPT; ++r)
+                            if (row0 + r < P.n) __stcs(d + r, v[r]);
+                    }
+                } else if (RPT == 2) {
                     *reinterpret_cast<double2 *>(s_F + (size_t)f * ROWS + tid * 2) = make_double2(v[0], v[RPT - 1]);
                 } else {
                     s_F[(size_t)f * ROWS + tid] = v[0];
                 }
             }
         }
+        if (NF == 1 && P.direct) continue;
         __syncthreads();
         // ---- phase 2: products, streamed to HBM -----------------------------------------------------
         {
@@ -369,9 +383,20 @@ extern "C" int fokl_basis_build(fokl_ctx *ctx, int kernel, const double *x, int6
         const int tab_stride = row_len + 1;     // cubic coefficient planes: any stride works for the 8-byte gathers
         const size_t per_slot = (kernel == FOKL_KERNEL_CUBIC ? (size_t)tab_stride * 4 : (size_t)row_len) * sizeof(double);
         const int nt = (int)pl.terms.size();
+        // main-effect substages: every term is exactly one factor and no factor is shared -> direct stores
+        bool direct = pl.max_cnt == 1 && nt == nf;
+        if (direct) {
+            std::vector<int> seen(nf, 0);
+            for (const TermMeta &tm : pl.terms) {
+                if (tm.f[0] >= nf || seen[tm.f[0]]++) { direct = false; break; }
+            }
+        }
+        if (direct)
+            for (int j = 0; j < nt; ++j) sorted[pl.terms[j].f[0]].pad = (int16_t)j;
         auto smem_need = [&](int rpt, int nslots) {
             size_t tab_bytes = ((nslots * per_slot / sizeof(double) + 1) & ~(size_t)1) * sizeof(double);
-            return tab_bytes + (size_t)(nf + 1) * kThreads * rpt * sizeof(double) + (size_t)nf * sizeof(FactorMeta) + 16;
+            return tab_bytes + (direct ? (size_t)0 : (size_t)(nf + 1) * kThreads * rpt * sizeof(double)) +
+                   (size_t)nf * sizeof(FactorMeta) + 16;
         };
         int rpt = aligned2 ? 2 : 1;
         int nslots = (int)orders.size();
@@ -403,6 +428,7 @@ extern "C" int fokl_basis_build(fokl_ctx *ctx, int kernel, const double *x, int6
         P.n_factors = nf; P.n_terms = nt; P.n_slots = nslots;
         P.factors = reinterpret_cast<const FactorMeta *>(dmeta + off_fac);
         P.tab_stride = tab_stride;
+        P.direct = direct ? 1 : 0;
         memcpy(P.terms, pl.terms.data(), (size_t)nt * sizeof(TermMeta));
         P.slot_order = reinterpret_cast<const int16_t *>(dmeta + off_slot);
         P.flag = ctx->d_flag;

@@ -468,6 +468,30 @@ FOKL_HD int gibbs_chain(const Team &t, int p, const double *lamb, const double *
 // shuffle steps with no shared memory and no CTA barrier on the per-draw critical path, and the variate rows are
 // prefetched two draws ahead into registers.  The D draws are sequential, so a chain's time is D times the latency
 // of one draw -- this halves it against the multi-warp version for the model sizes of a fit (p <= 256).
+// Branch-free reciprocal square root / reciprocal of a positive double: the double-precision MUFU seed
+// (rsqrt.approx.ftz.f64 / rcp.approx.ftz.f64, ~2^-22) and two Newton steps (~1e-16 relative error).  Unlike rsqrt() /
+// 1.0 / x there is no slow-path branch or call, so the E independent evaluations of a draw interleave in the one
+// warp that runs the chain and the dependent chain per evaluation is MUFU + 6 FMA-class instructions.
+__device__ __forceinline__ double rsqrt_pos(double x)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double h = 0.5 * x;
+    double t = fma(-h * y, y, 0.5);
+    y = fma(y, t, y);
+    t = fma(-h * y, y, 0.5);
+    return fma(y, t, y);
+}
+__device__ __forceinline__ double rcp_pos(double x)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double r = fma(-x, y, 1.0);
+    y = fma(y, r, y);
+    r = fma(-x, y, 1.0);
+    return fma(y, r, y);
+}
+
 template <int E>
 __device__ int gibbs_chain_warp(int lane, int p, const double *lamb, const double *ct, const CandConst &k,
                                 const double *variates, const double *sign_fix, double *gam, double *sigs, double *taus)
@@ -489,7 +513,7 @@ __device__ int gibbs_chain_warp(int lane, int p, const double *lamb, const doubl
         zr[q] = (h[q] && D > 1) ? variates[w + e] : 0.0;
     }
     double g1 = variates[p], g2 = variates[p + 1];
-    double ig1 = 1.0 / g1, ig2 = 1.0 / g2;
+    double ig1 = rcp_pos(g1), ig2 = rcp_pos(g2);
     double gr1 = D > 1 ? variates[w + p] : 1.0, gr2 = D > 1 ? variates[w + p + 1] : 1.0;
     for (int d = 0; d < D; ++d) {
         const double *r2 = variates + (int64_t)(d + 2) * w;
@@ -498,20 +522,31 @@ __device__ int gibbs_chain_warp(int lane, int p, const double *lamb, const doubl
 #pragma unroll
         for (int q = 0; q < E; ++q) zq[q] = (more && h[q]) ? r2[lane + 32 * q] : 0.0;
         const double gq1 = more ? r2[p] : 1.0, gq2 = more ? r2[p + 1] : 1.0;
-        double s1 = 0.0, s2 = 0.0, s3 = 0.0;
         double *grow = gam + (int64_t)d * p;
+        double gq[E];
 #pragma unroll
         for (int q = 0; q < E; ++q) {
-            const double rs = FOKL_RSQRT(l[q] + itau);
-            const double g = h[q] ? (rs * rs) * c[q] + (ssig * rs) * z[q] : 0.0;
-            if (h[q]) grow[lane + 32 * q] = g;
-            s1 += l[q] * g * g; s2 += g * c[q]; s3 += g * g;
+            const double rs = rsqrt_pos(l[q] + itau);
+            gq[q] = h[q] ? (rs * rs) * c[q] + (ssig * rs) * z[q] : 0.0;
+            if (h[q]) grow[lane + 32 * q] = gq[q];
         }
+        // two independent partial sums per quantity: the adds of a draw do not form one E-long dependent chain
+        double s1 = 0.0, s2 = 0.0, s3 = 0.0, s1b = 0.0, s2b = 0.0, s3b = 0.0;
+#pragma unroll
+        for (int q = 0; q < E; q += 2) {
+            const double g = gq[q], gg = g * g;
+            s1 = fma(l[q], gg, s1); s2 = fma(g, c[q], s2); s3 += gg;
+            if (q + 1 < E) {
+                const double g_ = gq[q + 1], gg_ = g_ * g_;
+                s1b = fma(l[q + 1], gg_, s1b); s2b = fma(g_, c[q + 1], s2b); s3b += gg_;
+            }
+        }
+        s1 += s1b; s2 += s2b; s3 += s3b;
         // next row's values (loaded one iteration ago): off the critical path, overlaps the reduction
         double zn[E];
 #pragma unroll
         for (int q = 0; q < E; ++q) zn[q] = f[q] * zr[q];
-        const double ign1 = 1.0 / gr1, ign2 = 1.0 / gr2;
+        const double ign1 = rcp_pos(gr1), ign2 = rcp_pos(gr2);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             s1 += __shfl_xor_sync(0xffffffffu, s1, o);
@@ -521,10 +556,10 @@ __device__ int gibbs_chain_warp(int lane, int p, const double *lamb, const doubl
         const double bstar = k.b + 0.5 * (s1 - 2.0 * s2 + k.yty + s3 * itau);
         double sig, rb;
         if (bstar < 0.0) { sig = nan(""); rb = sig; bad = 1; }
-        else { sig = bstar * ig1; rb = FOKL_RCP(bstar); }
+        else { sig = bstar * ig1; rb = rcp_pos(bstar); }
         const double btau_star = (0.5 * g1 * rb) * s3 + k.btau;
-        itau = g2 * FOKL_RCP(btau_star);
-        ssig = sqrt(sig);
+        itau = g2 * rcp_pos(btau_star);
+        ssig = sig * rsqrt_pos(sig);
         if (lane == 0) { sigs[d] = sig; taus[d] = btau_star * ig2; }
 #pragma unroll
         for (int q = 0; q < E; ++q) { z[q] = zn[q]; zr[q] = zq[q]; }

@@ -33,7 +33,7 @@ struct GramParams {
     const double *y;
     int64_t ld, n;
     int p;                                  // p_old + c: slot source p means y
-    int kb;                                 // rows per pipeline stage: 16, 32 or 64
+    int kb;                                 // rows per pipeline stage: 16 ... 256
     int kb_shift;                           // log2(kb / 2)
     int stages;                             // ring depth (3 or 4)
     int max_slots;                          // shared-memory stage = max_slots * (kb + 4) doubles
@@ -282,8 +282,10 @@ extern "C" int fokl_gram_update(fokl_ctx *ctx, const double *X, int64_t ld, int6
     const int n_tiles = (int)plan.tiles.size();
     if (n_tiles == 0 || plan.max_slots > cap) FOKL_FAIL(ctx, FOKL_ESTATE, "gram_update: empty or oversized plan");
     // deepest slab that fits (fewer CTA-wide barriers per row), giving up one ring stage for it if necessary
+    // (up to 256 rows for the narrow main-effect blocks: their launches are bound by the per-slab barrier latency)
     int kb = 16, stages = kMaxStages;
-    for (int cand_kb = 64; cand_kb >= 32; cand_kb /= 2) {
+    for (int cand_kb = 256; cand_kb >= 32; cand_kb /= 2) {
+        if (cand_kb > 64 && plan.max_slots * (cand_kb + kPad) * (int)sizeof(double) > 40 * 1024) continue;   // <= 40 KB per stage
         if (n < (int64_t)cand_kb * 4) continue;
         if (smem_need(plan.max_slots, cand_kb, 4) <= smem_cap) { kb = cand_kb; stages = 4; break; }
         if (smem_need(plan.max_slots, cand_kb, 3) <= smem_cap) { kb = cand_kb; stages = 3; break; }

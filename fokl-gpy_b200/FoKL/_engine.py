@@ -265,7 +265,10 @@ class Engine:
         self.yty = float(momh[2])
         self.Gcap = 0
         self._ensure_gram(64)
-        self._append_built(1)      # Gram entries of the ones column: G00 = n, Xty0 = sum y
+        # Gram entries of the ones column are the moments just reduced (G00 = n, Xty0 = sum y): no N-length pass
+        self.G[0, 0] = float(self.n_global)
+        self.Xty[0] = self.sum_y
+        self.P = 1
         return self
 
     def _ensure_columns(self, need):

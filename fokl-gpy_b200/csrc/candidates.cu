@@ -10,6 +10,7 @@
 #include "cand_math.cuh"
 #include <cooperative_groups.h>
 #include <algorithm>
+#include <queue>
 #include <math.h>
 #include <string.h>
 #include <vector>
@@ -744,14 +745,9 @@ extern "C" int fokl_candidates_eval(fokl_ctx *ctx, const double *G, int64_t ldg,
         CandMeta &m = meta[c];
         m.p = p; m.set_off = set_offsets[c]; m.pad = 0;
         m.vec_off = vec; m.mat_off = mat;
-        // cluster size of the Jacobi eigensolver: <= 32 column pairs per CTA, columns must fit in shared memory
+        // cluster size of the Jacobi eigensolver: the smallest whose column buffers fit in shared memory; raised below
         {
-            int cs = 1;
-            while (cs < ctx->max_cluster && (p + 1) / 2 > (kEigJThreads / 32) * cs) cs *= 2;   // one pair per warp if possible
-            // ... but a batch should fit the device in one wave: a cluster of cs CTAs finishes a candidate ~cs^0.6
-            // times faster, n_cand * cs / num_sms waves cost cs times more (profiles/r01_eig_batch_diag.txt)
-            while (cs > 1 && (int64_t)n_cand * cs > ctx->num_sms) cs /= 2;
-            if (force_cs > 0) cs = force_cs;
+            int cs = force_cs > 0 ? force_cs : 1;
             while (cs <= kEigJMaxCluster && eigj_smem_bytes(p, cs) > smem_cap) cs *= 2;
             if (cs > ctx->max_cluster || p > 64 * kEigJMaxNV) m.pad = 1;   // too large: two-matrix Jacobi in global memory
             else eig_class[c] = cs;
@@ -769,6 +765,43 @@ extern "C" int fokl_candidates_eval(fokl_ctx *ctx, const double *G, int64_t ldg,
     }
     const int n_chain = (int)chain_list.size();
     const int total_p = set_offsets[n_cand];
+
+    // ---- cluster sizes of the batch ---------------------------------------------------------------------------------
+    // A candidate's eigensolve is a fixed number of rounds whose length shrinks with the cluster size until every column
+    // pair has a warp of its own, and a cluster pays one cluster barrier + DSMEM exchange per round: per round about
+    // a(p) * ceil(pairs per CTA / 16) + [cs > 1] * b(p) microseconds with a = 0.25 + 0.0035 p, b = 0.005 p
+    // (fit to profiles/r01_eig_batch_diag.txt).  A batch ends with its slowest candidate, so while the batch still fits the
+    // device in one wave (sum of cluster sizes <= SMs) the cluster of the currently slowest candidate is raised.
+    if (force_cs == 0) {
+        auto est = [&](int p, int cs) {
+            const int n = eigj_padded_n(p, cs);
+            const int pairs = (n / 2 + cs - 1) / cs;
+            const double a = 0.25 + 0.0035 * p, b = cs > 1 ? 0.005 * p : 0.0;
+            return (double)(n - 1) * (a * ((pairs + kEigJThreads / 32 - 1) / (kEigJThreads / 32)) + b);
+        };
+        int64_t ctas = 0;
+        std::priority_queue<std::pair<double, int>> heap;
+        for (int c = 0; c < n_cand; ++c) {
+            ctas += std::max(eig_class[c], 1);
+            if (eig_class[c] > 0) heap.push({est(meta[c].p, eig_class[c]), c});
+        }
+        while (!heap.empty()) {
+            const double t = heap.top().first;
+            const int c = heap.top().second;
+            heap.pop();
+            const int cs = eig_class[c], p = meta[c].p;
+            int best = cs;
+            double tb = t;
+            for (int c2 = cs * 2; c2 <= ctx->max_cluster && ctas - cs + c2 <= ctx->num_sms; c2 *= 2) {
+                const double t2 = est(p, c2);
+                if (t2 < 0.97 * t) { best = c2; tb = t2; break; }
+            }
+            if (best == cs) break;              // the slowest candidate cannot be made faster: the batch time is set
+            ctas += best - cs;
+            eig_class[c] = best;
+            heap.push({tb, c});
+        }
+    }
 
     // ---- metadata upload ---------------------------------------------------------------------------------
     std::vector<int32_t> eig_list;                 // candidates grouped by cluster size

@@ -80,6 +80,157 @@ __device__ __forceinline__ void dmma_m8n8k4_if(double &c0, double &c1, double a,
         : "d"(a), "d"(b), "r"(on), "n"(BIT));
 }
 
+// ---- mbarrier + bulk-copy primitives (sm_90+ PTX) ---------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// Spin until the phase with the given parity has completed.  A wait that never ends (a protocol bug) traps instead of
+// hanging the device.
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
+{
+    const unsigned addr = smem_u32(bar);
+    unsigned done = 0;
+    for (unsigned spin = 0; !done; ++spin) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (spin > (1u << 26)) __trap();
+    }
+}
+// global -> shared bulk copy (TMA engine, no tensor map), completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void *smem, const void *gmem, unsigned bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(smem)),
+                 "l"(gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// Consumer side of the mbarrier ring for a warp that owns NB work items (positions q = warp + 16 b): wait for a slab,
+// issue its DMMAs, hand the stage back.  No CTA-wide barrier: warps drift up to stages - 1 slabs apart.
+template <int WARPS, int NB, bool MASKED>
+__device__ __forceinline__ void gram_consume(const GramParams &P, const GramTileMeta &tm, const double *stages, size_t stage_doubles,
+                                             int stride, uint64_t *full, uint64_t *empty, int nk, int lane, int warp, double *out)
+{
+    constexpr int kGramWarps = WARPS;
+    int a_off[NB], b_off[NB];
+    unsigned msk[NB];
+    const int frag_r = lane >> 2, frag_k = lane & 3;
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        const GramBlockMeta bm = P.blocks[tm.blk_off + warp + kGramWarps * b];
+        a_off[b] = (bm.a_slot + frag_r) * stride + frag_k + 16 * bm.phase;     // this item's first 16-row chunk
+        b_off[b] = (bm.b_slot + frag_r) * stride + frag_k + 16 * bm.phase;
+        msk[b] = bm.mask;
+    }
+    double acc[NB][4][2];
+#pragma unroll
+    for (int b = 0; b < NB; ++b)
+#pragma unroll
+        for (int f = 0; f < 4; ++f) acc[b][f][0] = acc[b][f][1] = 0.0;
+
+    const int stages_n = P.stages;
+    const int kstep = 16 * tm.ksplit;
+    const int half = 8 * stride;                                   // second fragment row / column of a block
+    int st = 0;
+    unsigned ph = 0;
+    for (int kt = 0; kt < nk; ++kt) {
+        mbar_wait(full + st, ph);
+        const double *S = stages + (size_t)st * stage_doubles;
+        for (int k0 = 0; k0 < P.kb; k0 += kstep) {
+#pragma unroll
+            for (int kk = 0; kk < 16; kk += 4) {
+                double a0[NB], a1[NB], b0[NB], b1[NB];
+#pragma unroll
+                for (int b = 0; b < NB; ++b) {
+                    const double *pa = S + a_off[b] + k0 + kk, *pb = S + b_off[b] + k0 + kk;
+                    a0[b] = pa[0]; a1[b] = pa[half]; b0[b] = pb[0]; b1[b] = pb[half];
+                }
+#pragma unroll
+                for (int b = 0; b < NB; ++b) {
+                    if (MASKED) {
+                        dmma_m8n8k4_if<1u>(acc[b][0][0], acc[b][0][1], a0[b], b0[b], msk[b]);
+                        dmma_m8n8k4_if<2u>(acc[b][1][0], acc[b][1][1], a0[b], b1[b], msk[b]);
+                        dmma_m8n8k4_if<4u>(acc[b][2][0], acc[b][2][1], a1[b], b0[b], msk[b]);
+                        dmma_m8n8k4_if<8u>(acc[b][3][0], acc[b][3][1], a1[b], b1[b], msk[b]);
+                    } else {
+                        dmma_m8n8k4(acc[b][0][0], acc[b][0][1], a0[b], b0[b]);
+                        dmma_m8n8k4(acc[b][1][0], acc[b][1][1], a0[b], b1[b]);
+                        dmma_m8n8k4(acc[b][2][0], acc[b][2][1], a1[b], b0[b]);
+                        dmma_m8n8k4(acc[b][3][0], acc[b][3][1], a1[b], b1[b]);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + st);                    // this warp is done reading the stage
+        if (++st == stages_n) { st = 0; ph ^= 1u; }
+    }
+    // accumulators in fragment order: lane l holds C[l >> 2][(l & 3) * 2 + {0, 1}] = row-major 8 x 8 at offset 2 l
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        const int q = warp + kGramWarps * b;
+#pragma unroll
+        for (int f = 0; f < 4; ++f)
+            *reinterpret_cast<double2 *>(out + (size_t)q * 256 + f * 64 + lane * 2) = make_double2(acc[b][f][0], acc[b][f][1]);
+    }
+}
+
+// Producer warp of the mbarrier ring: one bulk copy per staged column and slab (KB rows = KB * 8 contiguous bytes),
+// all completing on the stage's `full` barrier; a stage is refilled as soon as every consumer warp has released it.
+__device__ __forceinline__ void gram_produce(const GramParams &P, const GramTileMeta &tm, double *stages, size_t stage_doubles,
+                                             int stride, const double *const *s_ptr, uint64_t *full, uint64_t *empty,
+                                             int64_t n_lo, int64_t n_hi, int nk, int lane)
+{
+    int n_real = 0;
+    for (int slot = lane; slot < tm.n_slots; slot += 32) n_real += s_ptr[slot] != nullptr;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) n_real += __shfl_xor_sync(0xffffffffu, n_real, o);
+    const unsigned slab_bytes = (unsigned)P.kb * 8u;
+    const int stages_n = P.stages;
+    int st = 0;
+    unsigned ph = 0;
+    for (int kt = 0; kt < nk; ++kt) {
+        if (kt >= stages_n) mbar_wait(empty + st, ph ^ 1u);        // the previous use of this stage has been consumed
+        double *dst = stages + (size_t)st * stage_doubles;
+        const int64_t r0 = n_lo + (int64_t)kt * P.kb;
+        const int64_t left = n_hi - r0;
+        if (left >= P.kb) {
+            if (lane == 0) mbar_arrive_expect_tx(full + st, (unsigned)n_real * slab_bytes);
+            __syncwarp();
+            for (int slot = lane; slot < tm.n_slots; slot += 32) {
+                const double *col = s_ptr[slot];
+                if (col != nullptr) bulk_g2s(dst + (size_t)slot * stride, col + r0, slab_bytes, full + st);
+            }
+        } else {
+            // last, partial slab of the matrix: plain copies with zero fill (rows >= n never enter a product)
+            for (int slot = 0; slot < tm.n_slots; ++slot) {
+                const double *col = s_ptr[slot];
+                if (col == nullptr) continue;
+                for (int k = lane; k < P.kb; k += 32) dst[(size_t)slot * stride + k] = k < left ? col[r0 + k] : 0.0;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full + st);
+        }
+        if (++st == stages_n) { st = 0; ph ^= 1u; }
+    }
+}
+
 // The row loop of one CTA for a warp that owns NB blocks (q = warp + 16 b, b < NB).  NB is a template parameter so
 // the fragment loads of a k-step are all issued ahead of its DMMAs without per-block branches; MASKED selects the
 // predicated DMMA form for warps that own a block with skipped fragments (diagonal / edge blocks).
@@ -134,7 +285,7 @@ __device__ __forceinline__ void gram_rows(const GramParams &P, const GramTileMet
         __syncthreads();
         // refill the ring one k-block into the stage (when the slab has more than one), so the DMMAs restart right after
         // the barrier instead of behind the cp.async issue: K2 94 -> 85 ms per cfg4 fit (profiles/r01_gram_variants.txt)
-        const int load_at = (NB == 0 || P.kb < 32) ? 0 : 16;
+        const int load_at = (NB == 0 || P.kb < 32) ? 0 : 16;       // (tiles of this kernel are never k-split)
         const double *S = stages + (size_t)(kt % stages_n) * stage_doubles;
         for (int k0 = 0; k0 < P.kb; k0 += 16) {
             if (k0 == load_at) {
@@ -205,18 +356,91 @@ __global__ void __launch_bounds__(WARPS * 32, 16 / WARPS) gram_kernel(const Gram
     __syncthreads();
 
     double *out = P.part + ((size_t)blockIdx.y * P.n_tiles + blockIdx.x) * (size_t)(P.tile_blocks * 256);
-    // blocks of this warp: q = warp + 16 b < n_blk
-    const int nb = tm.n_blk > warp ? (tm.n_blk - warp + kGramWarps - 1) / kGramWarps : 0;
+    // work items of this warp: positions q = warp + 16 b < n_blk, filled from b = 0 (mask 0 = hole)
+    int nb = 0;
     bool partial = false;
-#ifndef FOKL_GRAM_NOMASK
-    for (int b = 0; b < nb; ++b) partial |= P.blocks[tm.blk_off + warp + kGramWarps * b].mask != 15u;
-#endif
+    for (int b = 0; b < kGramBlocksPerWarp; ++b) {
+        const int q = warp + kGramWarps * b;
+        if (q >= tm.n_blk) break;
+        const unsigned mk = P.blocks[tm.blk_off + q].mask;
+        if (mk == 0u) break;
+        nb = b + 1;
+        partial |= mk != 15u;
+    }
 #define FOKL_ROWS(NB)                                                                                                  \
     if (partial) gram_rows<WARPS, NB, true>(P, tm, stages, s_ptr, stage_doubles, stride, n_lo, n_hi, nk, tid, lane, warp, out); \
     else gram_rows<WARPS, NB, false>(P, tm, stages, s_ptr, stage_doubles, stride, n_lo, n_hi, nk, tid, lane, warp, out);        \
     break;
     switch (nb) {
     case 0: gram_rows<WARPS, 0, false>(P, tm, stages, s_ptr, stage_doubles, stride, n_lo, n_hi, nk, tid, lane, warp, out); break;
+    case 1: FOKL_ROWS(1)
+    case 2: FOKL_ROWS(2)
+    case 3: FOKL_ROWS(3)
+    default: FOKL_ROWS(4)
+    }
+#undef FOKL_ROWS
+}
+
+// K2 with the mbarrier ring: WARPS consumer warps + one producer warp per CTA.
+template <int WARPS>
+__global__ void __launch_bounds__((WARPS + 1) * 32, 1) gram_kernel_mb(const GramParams P)
+{
+    constexpr int kGramWarps = WARPS, kThreads = (WARPS + 1) * 32;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const GramTileMeta tm = P.tiles[blockIdx.x];
+    const int stride = P.kb + kPad;
+    const size_t stage_doubles = (size_t)P.max_slots * stride;
+    double *stages = reinterpret_cast<double *>(smem_raw);
+    const double **s_ptr = reinterpret_cast<const double **>(stages + P.stages * stage_doubles);
+    uint64_t *full = reinterpret_cast<uint64_t *>(s_ptr + P.max_slots);
+    uint64_t *empty = full + kMaxStages;
+
+    const int64_t n_lo = (int64_t)blockIdx.y * P.rows_per_split;
+    const int64_t n_hi = (n_lo + P.rows_per_split < P.n) ? n_lo + P.rows_per_split : P.n;
+    const int nk = n_hi > n_lo ? (int)((n_hi - n_lo + P.kb - 1) / P.kb) : 0;
+
+    // work items of this warp: positions q = warp + 16 b < n_blk, filled from b = 0 (mask 0 = hole)
+    int nb = 0;
+    bool partial = false;
+    if (warp < kGramWarps) {
+        for (int b = 0; b < kGramBlocksPerWarp; ++b) {
+            const int q = warp + kGramWarps * b;
+            if (q >= tm.n_blk) break;
+            const unsigned mk = P.blocks[tm.blk_off + q].mask;
+            if (mk == 0u) break;
+            nb = b + 1;
+            partial |= mk != 15u;
+        }
+    }
+    // operand column pointers; padding slots stay zero in every stage (never written by a copy)
+    for (int s = tid; s < tm.n_slots; s += kThreads) {
+        const int src = P.slot_src[tm.slot_off + s];
+        s_ptr[s] = src < 0 ? nullptr : (src == P.p ? P.y : P.X + (int64_t)src * P.ld);
+    }
+    for (size_t e = tid; e < P.stages * stage_doubles; e += kThreads) stages[e] = 0.0;
+    const int active = __syncthreads_count(lane == 0 && nb > 0);   // consumer warps that own work (and release stages)
+    if (tid == 0) {
+        for (int s = 0; s < P.stages; ++s) {
+            mbar_init(full + s, 1u);
+            mbar_init(empty + s, (unsigned)active);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // the zero fill (generic proxy) precedes the bulk copies
+    __syncthreads();
+
+    if (warp == kGramWarps) {
+        if (active > 0) gram_produce(P, tm, stages, stage_doubles, stride, s_ptr, full, empty, n_lo, n_hi, nk, lane);
+        return;
+    }
+    double *out = P.part + ((size_t)blockIdx.y * P.n_tiles + blockIdx.x) * (size_t)(P.tile_blocks * 256);
+#define FOKL_ROWS(NB)                                                                                                          \
+    if (partial) gram_consume<WARPS, NB, true>(P, tm, stages, stage_doubles, stride, full, empty, nk, lane, warp, out);         \
+    else gram_consume<WARPS, NB, false>(P, tm, stages, stage_doubles, stride, full, empty, nk, lane, warp, out);                \
+    break;
+    switch (nb) {
+    case 0: break;
     case 1: FOKL_ROWS(1)
     case 2: FOKL_ROWS(2)
     case 3: FOKL_ROWS(3)
@@ -238,13 +462,15 @@ __global__ void gram_reduce_kernel(const double *__restrict__ part, int nsplit, 
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
         const int q = e >> 8, f = (e >> 6) & 3, idx = e & 63;
         const GramBlockMeta bm = blocks[tm.blk_off + q];
-        if (!(bm.mask >> f & 1u)) continue;                 // fragment not computed: the block entry stays 0
+        if (bm.phase != 0 || !(bm.mask >> f & 1u)) continue;   // not the head item of a block / fragment not computed
         const int arow = slot_arow[tm.slot_off + bm.a_slot + 8 * (f >> 1) + (idx >> 3)];
         const int bcol = slot_bcol[tm.slot_off + bm.b_slot + 8 * (f & 1) + (idx & 7)];
         if (arow < 0 || bcol < 0) continue;
         double s = 0.0;
-        const double *src = part + (size_t)tile * tile_stride + e;
-        for (int k = 0; k < nsplit; ++k) s += src[(size_t)k * n_tiles * tile_stride];
+        for (int qq = q; qq >= 0; qq = blocks[tm.blk_off + qq].next) {      // the block's items in phase order
+            const double *src = part + (size_t)tile * tile_stride + (size_t)qq * 256 + (e & 255);
+            for (int k = 0; k < nsplit; ++k) s += src[(size_t)k * n_tiles * tile_stride];
+        }
         out[(size_t)arow * c + bcol] = s;
     }
 }
@@ -264,34 +490,70 @@ extern "C" int fokl_gram_update(fokl_ctx *ctx, const double *X, int64_t ld, int6
     if (rc) return rc;
     const int p = p_old + c;
 
-    // CTA shape: 16 warps, one CTA per SM.  (Measured alternative, profiles/r01_gram_variants.txt: 8 warps with two
+    // CTA shape: one CTA of 16 warps per SM.  (Measured alternative, profiles/r01_gram_variants.txt: 8 warps with two
     // co-resident CTAs per SM and half the blocks each is 1.65x slower -- more duplicated operand traffic and
     // instruction-cache misses between the two CTAs' code paths.)
-    const int warps = 16;
-    const int ctas_per_sm = fokl::kGramMaxWarps / warps;
-    const int kTileBlocks = fokl::gram_tile_blocks(warps);
-    // shared-memory budget -> slot cap at the smallest slab (KB = 16), then the deepest slab that fits the plan
+    // Two pipelines feed the DMMAs (profiles/r01_gram_ksplit.txt):
+    //  * mbarrier ring (gram_kernel_mb): 15 consumer warps + 1 producer warp issuing one bulk copy per staged column and
+    //    slab; no CTA-wide barrier.  A bulk copy costs the SM's copy engine ~60 cycles whatever its size, so this needs
+    //    slabs of >= 64 rows (>= 512-byte copies): tiles of up to ~130 staged columns.  (A 17th warp would put five
+    //    warps on one SM sub-partition and cap the kernel at 96 registers per thread.)
+    //  * cp.async ring (gram_kernel): 16 warps, 16-byte cp.async by every thread and one __syncthreads per slab; the
+    //    wide tiles of the three-way substages (~220 staged columns, 32-row slabs) run faster here.
+    const int ctas_per_sm = 1;
     const size_t smem_total = ctx->smem_optin ? ctx->smem_optin : 48 * 1024;
-    const size_t smem_cap = (warps == 16 ? smem_total : (smem_total + 1024) / 2 - 1024) - 1024;
+    const size_t smem_cap = smem_total - 1024;
     auto smem_need = [&](int slots, int kb, int stages) {
-        return (size_t)stages * slots * (kb + kPad) * sizeof(double) + (size_t)slots * sizeof(double *);
+        return (size_t)stages * slots * (kb + kPad) * sizeof(double) + (size_t)slots * sizeof(double *) +
+               2 * kMaxStages * sizeof(uint64_t);
     };
     int cap = 32;
     while (smem_need(cap + 16, 16, kMaxStages) <= smem_cap) cap += 16;
-    const fokl::GramPlan plan = fokl::gram_make_plan(p_old, c, cap, warps);
-    const int n_tiles = (int)plan.tiles.size();
-    if (n_tiles == 0 || plan.max_slots > cap) FOKL_FAIL(ctx, FOKL_ESTATE, "gram_update: empty or oversized plan");
-    // deepest slab that fits (fewer CTA-wide barriers per row), giving up one ring stage for it if necessary
-    // (up to 256 rows for the narrow main-effect blocks: their launches are bound by the per-slab barrier latency)
-    int kb = 16, stages = kMaxStages;
-    for (int cand_kb = 256; cand_kb >= 32; cand_kb /= 2) {
-        if (cand_kb > 64 && plan.max_slots * (cand_kb + kPad) * (int)sizeof(double) > 40 * 1024) continue;   // <= 40 KB per stage
-        if (n < (int64_t)cand_kb * 4) continue;
-        if (smem_need(plan.max_slots, cand_kb, 4) <= smem_cap) { kb = cand_kb; stages = 4; break; }
-        if (smem_need(plan.max_slots, cand_kb, 3) <= smem_cap) { kb = cand_kb; stages = 3; break; }
+    // tuning knobs (tools/gram_sweep.py): FOKL_GRAM_KERNEL = mb | cpasync, FOKL_GRAM_KB, FOKL_GRAM_STAGES
+    const char *env_kernel = getenv("FOKL_GRAM_KERNEL");
+    const int env_kb = getenv("FOKL_GRAM_KB") ? atoi(getenv("FOKL_GRAM_KB")) : 0;
+    const int env_stages = getenv("FOKL_GRAM_STAGES") ? atoi(getenv("FOKL_GRAM_STAGES")) : 0;
+    bool use_mb = !(env_kernel && !strcmp(env_kernel, "cpasync"));
+    int warps = 15, kb = 0, stages = 0;
+    fokl::GramPlan plan;
+    if (use_mb) {
+        plan = fokl::gram_make_plan(p_old, c, cap, warps);
+        if (plan.tiles.empty() || plan.max_slots > cap) FOKL_FAIL(ctx, FOKL_ESTATE, "gram_update: empty or oversized plan");
+        // deepest slab that leaves a ring of >= 3 stages (>= 2 for slabs of >= 128 rows)
+        for (int cand_kb = 256; cand_kb >= 64 && kb == 0; cand_kb /= 2) {
+            if (n < (int64_t)cand_kb * 4) continue;
+            for (int st = kMaxStages; st >= (cand_kb >= 128 ? 2 : 3); --st)
+                if (smem_need(plan.max_slots, cand_kb, st) <= smem_cap) { kb = cand_kb; stages = st; break; }
+        }
+        if (kb == 0 && !env_kernel) use_mb = false;
     }
+    if (!use_mb) {
+        warps = 16;
+        plan = fokl::gram_make_plan(p_old, c, cap, warps);
+        if (plan.tiles.empty() || plan.max_slots > cap) FOKL_FAIL(ctx, FOKL_ESTATE, "gram_update: empty or oversized plan");
+        // deepest slab that fits (fewer CTA-wide barriers per row), giving up one ring stage for it if necessary
+        kb = 0;
+        for (int cand_kb = 256; cand_kb >= 32; cand_kb /= 2) {
+            if (cand_kb > 64 && plan.max_slots * (cand_kb + kPad) * (int)sizeof(double) > 40 * 1024) continue;   // <= 40 KB per stage
+            if (n < (int64_t)cand_kb * 4) continue;
+            if (smem_need(plan.max_slots, cand_kb, 4) <= smem_cap) { kb = cand_kb; stages = 4; break; }
+            if (smem_need(plan.max_slots, cand_kb, 3) <= smem_cap) { kb = cand_kb; stages = 3; break; }
+        }
+    }
+    if (kb == 0) { kb = 16; stages = kMaxStages; }
+    if (env_kb >= 16 && env_kb <= 256 && (env_kb & (env_kb - 1)) == 0) kb = env_kb;
+    if (env_stages >= 2 && env_stages <= kMaxStages) stages = env_stages;
+    if (!use_mb && stages < 3) stages = 3;            // the cp.async ring waits on groups of a 3- or 4-deep ring
+    if (smem_need(plan.max_slots, kb, stages) > smem_cap) FOKL_FAIL(ctx, FOKL_EINVAL, "gram_update: slab does not fit in shared memory");
+    const int n_tiles = (int)plan.tiles.size();
+    const int kTileBlocks = fokl::gram_tile_blocks(warps);
     int kb_shift = 0;
     while ((2 << kb_shift) < kb) ++kb_shift;
+    // placement: 1 = sequential deal (the default: 4 - 6 % faster than the balanced deal on the wide tiles and within
+    // 2 % elsewhere, profiles/r01_gram_ksplit.txt), 0 = balanced deal
+    const int place_mode = getenv("FOKL_GRAM_PLACE") ? atoi(getenv("FOKL_GRAM_PLACE")) : 1;
+    // k-split of tiles with few blocks (gram_plan.h); the cp.async kernel works whole slabs per item
+    fokl::gram_plan_place(plan, warps, use_mb ? kb / 16 : 1, place_mode);
 
     // row splits: about one resident CTA slot each
     const int64_t chunks = (n + kb - 1) / kb;
@@ -335,8 +597,13 @@ extern "C" int fokl_gram_update(fokl_ctx *ctx, const double *X, int64_t ld, int6
     P.n_tiles = n_tiles;
     P.tile_blocks = kTileBlocks;
     const size_t smem = smem_need(plan.max_slots, kb, stages);
-    FOKL_CUDA(ctx, cudaFuncSetAttribute(gram_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
-    gram_kernel<16><<<dim3(n_tiles, nsplit), 512, smem, ctx->stream>>>(P);
+    if (!use_mb) {
+        FOKL_CUDA(ctx, cudaFuncSetAttribute(gram_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
+        gram_kernel<16><<<dim3(n_tiles, nsplit), 512, smem, ctx->stream>>>(P);
+    } else {
+        FOKL_CUDA(ctx, cudaFuncSetAttribute(gram_kernel_mb<15>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
+        gram_kernel_mb<15><<<dim3(n_tiles, nsplit), 16 * 32, smem, ctx->stream>>>(P);
+    }
     FOKL_LAUNCH_CHECK(ctx);
     gram_reduce_kernel<<<dim3(kTileBlocks, n_tiles), 256, 0, ctx->stream>>>(
         P.part, nsplit, n_tiles, P.tiles, P.blocks, reinterpret_cast<const int32_t *>(buf + off_arow),

@@ -28,12 +28,16 @@ constexpr int kGramRect = 8;            // rectangles of 8 x 8 blocks = 128 x 12
 
 struct GramTileMeta {
     int32_t slot_off, n_slots;          // into slot_* arrays; n_slots is a multiple of 8
-    int32_t blk_off, n_blk;             // into blocks
+    int32_t blk_off, n_blk;             // into blocks; n_blk = positions in use (work items and holes)
+    int32_t ksplit, pad;                // every block of the tile is shared by `ksplit` work items (power of two)
 };
 
+// One work item = one 2 x 2-fragment block restricted to the 16-row chunks  phase, phase + ksplit, ...  of every slab.
 struct GramBlockMeta {
     uint16_t a_slot, b_slot;            // first of 16 consecutive tile-local slots on the row / column side
-    uint32_t mask;                      // bit f = fragment (f >> 1, f & 1) of the block is needed
+    uint8_t mask;                       // bit f = fragment (f >> 1, f & 1) of the block is needed
+    uint8_t phase;                      // 0 .. ksplit - 1; the phase-0 item is the head of its block's item chain
+    int16_t next;                       // tile-local position of the block's next item, -1 = last
 };
 
 struct GramPlan {
@@ -44,6 +48,133 @@ struct GramPlan {
     std::vector<GramBlockMeta> blocks;
     int max_slots = 0;
 };
+
+// k-split of a tile with few blocks.  A warp keeps at most 4 blocks' accumulators, and a block's DMMAs all issue from
+// the one warp that owns it, so a tile with fewer blocks than the CTA has positions (warps * 4) leaves tensor-pipe issue
+// slots idle (8 new columns against 50 old ones = 5 blocks: 5 of 16 warps busy, one block each).  Such a tile hands
+// every block to `ksplit` work items that take the 16-row chunks  phase, phase + ksplit, ...  of each slab; the items of
+// a block are summed (in phase order, then in row-split order) by gram_reduce_kernel.
+//
+// Placement.  Warp w owns the positions w, w + warps, ... (at most 4, filled from the first).  Per k-step an item costs
+// its warp four DMMA issue slots of ~25 cycles (a lone warp cannot issue them faster, and a predicated-off DMMA keeps its
+// slot: ncu source view, profiles/r01_gram_ksplit.txt) and the tensor pipe of the warp's SM sub-partition (w mod 4)
+// 16 cycles per needed fragment; the split with the smallest per-slab makespan
+//     max(100 * max_warp(items), 16 * max_subpartition(fragments)) / ksplit
+// wins, ties to the smaller split.  Two deals:
+//   mode 1 (used by K2)  sequential: the items in list order -- blocks with skipped fragments first, so that as few
+//          warps as possible run the predicated DMMA form, then the full blocks in rectangle order, the items of a
+//          block adjacent -- fill warp 0's positions, then warp 1's, ...
+//   mode 0 balanced: items with skipped fragments are packed into as few warps as an even deal allows, full ones go
+//          to the other warps, and within a kind an item goes to the sub-partition with the least fragments so far.
+//          Measured 4 - 6 % slower than mode 1 on the wide three-way tiles and equal within 2 % elsewhere.
+// Unused positions below n_blk are holes (mask 0).
+struct GramPlacement {
+    std::vector<int> pos;               // item (block g, phase f) = index g * ksplit + f -> tile-local position
+    int n_pos = 0;
+    double cost = 0.0;
+};
+
+inline int gram_popcount4(unsigned m) { return (int)((m & 1u) + (m >> 1 & 1u) + (m >> 2 & 1u) + (m >> 3 & 1u)); }
+
+inline GramPlacement gram_place_items(const std::vector<int> &weight, int r, int warps, int mode = 0)
+{
+    const int nb = (int)weight.size(), n_items = nb * r;
+    const int per = (n_items + warps - 1) / warps;                 // items per warp when dealt evenly
+    GramPlacement pc;
+    pc.pos.assign(n_items, -1);
+    if (mode == 1) {
+        // sequential deal: the items in list order (blocks with skipped fragments come first) fill warp 0's positions,
+        // then warp 1's, ...
+        int next = 0, max_cnt = 0;
+        int sl[4] = {0, 0, 0, 0};
+        for (int w = 0; w < warps; ++w) {
+            int cnt = 0;
+            for (int q = w; q < n_items; q += warps) { pc.pos[next] = q; sl[w & 3] += weight[next / r]; ++next; ++cnt; }
+            max_cnt = std::max(max_cnt, cnt);
+        }
+        pc.n_pos = n_items;
+        pc.cost = std::max(100.0 * max_cnt, 16.0 * std::max(std::max(sl[0], sl[1]), std::max(sl[2], sl[3]))) / r;
+        return pc;
+    }
+    std::vector<int> order(n_items);
+    for (int i = 0; i < n_items; ++i) order[i] = i;
+    // items with skipped fragments first (lightest last among them), then the full ones
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
+        const int wx = weight[x / r], wy = weight[y / r];
+        if ((wx == 4) != (wy == 4)) return wx != 4;
+        return wx > wy;
+    });
+    std::vector<int> wload(warps, 0), wcnt(warps, 0), wmasked(warps, 0);
+    int sload[4] = {0, 0, 0, 0};
+    for (int it : order) {
+        const bool part = weight[it / r] != 4;
+        // preference classes (lower = better).  An item with skipped fragments joins a warp that already runs the
+        // predicated form while that warp is under the even deal, else opens an untouched warp; a full item goes to
+        // an untouched or unpredicated warp under the even deal (spread, not packed), then to any unpredicated one.
+        int best = -1, best_cls = 9;
+        for (int w = 0; w < warps; ++w) {
+            if (wcnt[w] >= kGramBlocksPerWarp) continue;
+            int cls;
+            if (part) cls = (wmasked[w] && wcnt[w] < per) ? 0 : (wcnt[w] == 0 ? 1 : (wmasked[w] ? 2 : 3));
+            else cls = (!wmasked[w] && wcnt[w] < per) ? 0 : (!wmasked[w] ? 1 : 2);
+            bool better;
+            if (best < 0 || cls < best_cls) better = true;
+            else if (cls > best_cls) better = false;
+            else if (sload[w & 3] != sload[best & 3]) better = sload[w & 3] < sload[best & 3];
+            else if (wcnt[w] != wcnt[best]) better = wcnt[w] < wcnt[best];
+            else better = wload[w] < wload[best];
+            if (better) { best = w; best_cls = cls; }
+        }
+        pc.pos[it] = best + warps * wcnt[best];
+        pc.n_pos = std::max(pc.n_pos, pc.pos[it] + 1);
+        ++wcnt[best];
+        wmasked[best] |= part ? 1 : 0;
+        wload[best] += weight[it / r];
+        sload[best & 3] += weight[it / r];
+    }
+    const int max_cnt = *std::max_element(wcnt.begin(), wcnt.end());
+    const int max_frag = std::max(std::max(sload[0], sload[1]), std::max(sload[2], sload[3]));
+    pc.cost = std::max(100.0 * max_cnt, 16.0 * max_frag) / r;
+    return pc;
+}
+
+// Place the blocks of every tile of a fresh plan for slabs of `kchunks` 16-row chunks (KB / 16 = the largest
+// admissible ksplit).  Call once per plan.
+inline void gram_plan_place(GramPlan &pl, int warps, int kchunks, int mode = 0)
+{
+    const int cap = gram_tile_blocks(warps);
+    std::vector<GramBlockMeta> out;
+    for (GramTileMeta &tm : pl.tiles) {
+        std::vector<GramBlockMeta> base;
+        std::vector<int> weight;
+        for (int q = 0; q < tm.n_blk; ++q) {
+            const GramBlockMeta &bm = pl.blocks[tm.blk_off + q];
+            if (bm.phase == 0 && bm.mask != 0) { base.push_back(bm); weight.push_back(gram_popcount4(bm.mask)); }
+        }
+        const int nb = (int)base.size();
+        GramPlacement best;
+        int best_r = 0;
+        for (int r = 1; r <= kchunks && nb * r <= cap; r *= 2) {
+            GramPlacement pc = gram_place_items(weight, r, warps, mode);
+            if (best_r == 0 || pc.cost < best.cost * 0.999) { best = pc; best_r = r; }
+        }
+        GramBlockMeta hole;
+        hole.a_slot = hole.b_slot = 0; hole.mask = 0; hole.phase = 0; hole.next = -1;
+        std::vector<GramBlockMeta> placed(best.n_pos, hole);
+        for (int g = 0; g < nb; ++g)
+            for (int f = 0; f < best_r; ++f) {
+                GramBlockMeta bm = base[g];
+                bm.phase = (uint8_t)f;
+                bm.next = (int16_t)(f + 1 < best_r ? best.pos[g * best_r + f + 1] : -1);
+                placed[best.pos[g * best_r + f]] = bm;
+            }
+        tm.blk_off = (int32_t)out.size();
+        tm.n_blk = best.n_pos;
+        tm.ksplit = best_r;
+        out.insert(out.end(), placed.begin(), placed.end());
+    }
+    pl.blocks.swap(out);
+}
 
 // max_slots_cap: most staged columns a tile may have (shared-memory budget), multiple of 16 and >= 32.
 inline GramPlan gram_make_plan(int p_old, int c, int max_slots_cap, int warps = kGramMaxWarps)
@@ -130,28 +261,23 @@ inline GramPlan gram_make_plan(int p_old, int c, int max_slots_cap, int warps = 
             bm.a_slot = (uint16_t)(frag_local[2 * order[q].first] * 8);
             bm.b_slot = (uint16_t)(frag_local[2 * order[q].second] * 8);
             bm.mask = 0;
+            bm.phase = 0;
+            bm.next = -1;
             for (int f = 0; f < 4; ++f) {
                 int i = 2 * order[q].first + (f >> 1), j = 2 * order[q].second + (f & 1);
-                if (i < fa && j < fb && frag_needed(i, j)) bm.mask |= 1u << f;
+                if (i < fa && j < fb && frag_needed(i, j)) bm.mask |= (uint8_t)(1u << f);
             }
             (bm.mask == 15u ? full_blk : part_blk).push_back(bm);
         }
-        // Warp w owns the blocks at positions w, w + warps, ... < n_blk.  Blocks with skipped fragments need the predicated
-        // DMMA form, which costs issue slots: hand them to as few warps as possible (warp 0's positions first, then
-        // warp 1's, ...), the fully needed blocks to the rest.
-        {
-            std::vector<GramBlockMeta> seq(part_blk);
-            seq.insert(seq.end(), full_blk.begin(), full_blk.end());
-            std::vector<GramBlockMeta> placed(n_blk);
-            size_t next = 0;
-            for (int w = 0; w < warps; ++w)
-                for (int q = w; q < n_blk; q += warps) placed[q] = seq[next++];
-            pl.blocks.insert(pl.blocks.end(), placed.begin(), placed.end());
-        }
+        // blocks with skipped fragments first (see gram_plan_place)
+        pl.blocks.insert(pl.blocks.end(), part_blk.begin(), part_blk.end());
+        pl.blocks.insert(pl.blocks.end(), full_blk.begin(), full_blk.end());
+        tm.ksplit = 1;
+        tm.pad = 0;
         pl.tiles.push_back(tm);
         pl.max_slots = std::max(pl.max_slots, (int)tm.n_slots);
     }
-    return pl;
+    return pl;      // blocks still in list order, one item each: the caller runs gram_plan_place() once
 }
 
 }  // namespace fokl

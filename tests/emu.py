@@ -51,7 +51,7 @@ def lib():
     L.emu_philox_normals.restype = None
     L.emu_philox_gammas.argtypes = [_u64, _u64, _i32, _f64, _vp]
     L.emu_philox_gammas.restype = None
-    L.emu_gram_plan.argtypes = [_vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp]
+    L.emu_gram_plan.argtypes = [_vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp]
     L.emu_gram_plan.restype = _i32
     _lib = L
     return L
@@ -150,15 +150,16 @@ def kill_loop(G, Xty, idx, cand_pos, bv0, bv1, hyp, threshav=0.05, threshstda=0.
                 calls=out_i[3 + vm:3 + vm + k].copy(), ev=out_ev[:k].copy())
 
 
-def gram_plan(A, p_old, c, cap=352, warps=16):
-    """Walk the K2 work plan on the host: returns (block (p + 1) x c with NaN where nothing was written, cover counts,
-    stats dict)."""
+def gram_plan(A, p_old, c, cap=352, warps=16, kchunks=1, mode=1):
+    """Walk the K2 work plan on the host (slabs of kchunks 16-row chunks): returns (block (p + 1) x c with NaN where
+    nothing was written, cover counts, stats dict)."""
     A = np.ascontiguousarray(A, dtype=np.float64)
     n, p1 = A.shape
     assert p1 == p_old + c + 1
     out = np.full((p1, c), np.nan)
     cover = np.zeros((p1, c), dtype=np.int32)
-    stats = np.zeros(4, dtype=np.int32)
-    rc = lib().emu_gram_plan(A.ctypes.data, n, p_old, c, cap, warps, out.ctypes.data, cover.ctypes.data, stats.ctypes.data)
+    stats = np.zeros(5, dtype=np.int32)
+    rc = lib().emu_gram_plan(A.ctypes.data, n, p_old, c, cap, warps, kchunks, mode, out.ctypes.data, cover.ctypes.data,
+                             stats.ctypes.data)
     return rc, out, cover, dict(n_tiles=int(stats[0]), max_slots=int(stats[1]), blocks=int(stats[2]),
-                                max_blocks_per_tile=int(stats[3]))
+                                max_positions_per_tile=int(stats[3]), max_ksplit=int(stats[4]))

@@ -178,23 +178,57 @@ void emu_philox_gammas(uint64_t seed, uint64_t stream, int draws, double shape, 
 // gram_reduce_kernel use them.  A is [n][p + 1] row-major with y as the last column; out is (p + 1) x c and must be
 // pre-filled by the caller; cover (same shape, int) counts how many times each entry was written.
 #include "../../fokl-gpy_b200/csrc/gram_plan.h"
-extern "C" int emu_gram_plan(const double *A, int64_t n, int p_old, int c, int max_slots_cap, int warps, double *out, int32_t *cover,
-                             int32_t *stats /* n_tiles, max_slots, total_blocks, max_blocks_per_tile */)
+extern "C" int emu_gram_plan(const double *A, int64_t n, int p_old, int c, int max_slots_cap, int warps, int kchunks, int mode, double *out,
+                             int32_t *cover, int32_t *stats /* n_tiles, max_slots, total_blocks, max_positions_per_tile, max_ksplit */)
 {
     const int p = p_old + c;
     GramPlan pl = gram_make_plan(p_old, c, max_slots_cap, warps);
+    gram_plan_place(pl, warps, kchunks, mode);
     const int kTileBlocks = gram_tile_blocks(warps);
     stats[0] = (int32_t)pl.tiles.size();
     stats[1] = pl.max_slots;
-    stats[2] = (int32_t)pl.blocks.size();
+    stats[2] = 0;
     stats[3] = 0;
+    stats[4] = 0;
     for (const GramTileMeta &tm : pl.tiles) {
         if (tm.n_blk > stats[3]) stats[3] = tm.n_blk;
+        if (tm.ksplit > stats[4]) stats[4] = tm.ksplit;
         if (tm.n_blk > kTileBlocks || tm.n_slots > max_slots_cap || (tm.n_slots % 8) != 0) return -1;
+        if (tm.ksplit < 1 || tm.ksplit > kchunks || (kchunks % tm.ksplit) != 0) return -5;
+        // positions of a warp are filled from its first one (the kernel stops at the first hole)
+        for (int w = 0; w < warps; ++w) {
+            bool hole = false;
+            for (int q = w; q < tm.n_blk; q += warps) {
+                const bool h = pl.blocks[tm.blk_off + q].mask == 0;
+                if (hole && !h) return -6;
+                hole = hole || h;
+            }
+        }
+        // gram_kernel: every item accumulates its own chunks; gram_reduce_kernel: the head walks the chain
+        std::vector<double> part((size_t)tm.n_blk * 256, 0.0);
         for (int q = 0; q < tm.n_blk; ++q) {
             const GramBlockMeta bm = pl.blocks[tm.blk_off + q];
+            if (bm.mask == 0) continue;
             if (bm.a_slot + 16 > tm.n_slots || bm.b_slot + 16 > tm.n_slots) return -2;
-            if (bm.mask == 0 || bm.mask > 15) return -4;
+            if (bm.mask > 15 || bm.phase >= tm.ksplit) return -4;
+            if (bm.next >= tm.n_blk || (bm.next >= 0 && pl.blocks[tm.blk_off + bm.next].phase != bm.phase + 1)) return -7;
+            if ((bm.next < 0) != (bm.phase == tm.ksplit - 1)) return -7;
+            for (int f = 0; f < 4; ++f)
+                for (int idx = 0; idx < 64; ++idx) {
+                    if (!(bm.mask >> f & 1)) continue;
+                    const int ca = pl.slot_src[tm.slot_off + bm.a_slot + 8 * (f >> 1) + (idx >> 3)];
+                    const int cb = pl.slot_src[tm.slot_off + bm.b_slot + 8 * (f & 1) + (idx & 7)];
+                    if (ca < 0 || cb < 0) continue;
+                    double s = 0.0;
+                    for (int64_t i = 0; i < n; ++i)
+                        if ((int)((i / 16) % tm.ksplit) == bm.phase) s += A[i * (p + 1) + ca] * A[i * (p + 1) + cb];
+                    part[(size_t)q * 256 + f * 64 + idx] = s;
+                }
+        }
+        for (int q = 0; q < tm.n_blk; ++q) {
+            const GramBlockMeta bm = pl.blocks[tm.blk_off + q];
+            if (bm.mask == 0 || bm.phase != 0) continue;
+            ++stats[2];
             for (int f = 0; f < 4; ++f)
                 for (int idx = 0; idx < 64; ++idx) {
                     if (!(bm.mask >> f & 1)) continue;
@@ -205,7 +239,14 @@ extern "C" int emu_gram_plan(const double *A, int64_t n, int p_old, int c, int m
                     const int ca = pl.slot_src[sa], cb = pl.slot_src[sb];
                     if (ca != arow || cb != p_old + bcol || cb >= p) return -3;
                     double s = 0.0;
-                    for (int64_t i = 0; i < n; ++i) s += A[i * (p + 1) + ca] * A[i * (p + 1) + cb];
+                    int links = 0;
+                    for (int qq = q; qq >= 0; qq = pl.blocks[tm.blk_off + qq].next) {
+                        const GramBlockMeta it = pl.blocks[tm.blk_off + qq];
+                        if (it.a_slot != bm.a_slot || it.b_slot != bm.b_slot || it.mask != bm.mask) return -8;
+                        s += part[(size_t)qq * 256 + f * 64 + idx];
+                        if (++links > tm.ksplit) return -8;
+                    }
+                    if (links != tm.ksplit) return -8;
                     out[(size_t)arow * c + bcol] = s;
                     cover[(size_t)arow * c + bcol] += 1;
                 }

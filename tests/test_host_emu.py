@@ -180,17 +180,18 @@ def test_kill_loop_matches_sequential_oracle_loop(phis_cubic, aic):
     assert emu.kill_loop(G2, Xty, idx, [idx.index(c) for c in cand_cols], bv0, bv1, hyp, evmin=full)['bad'] == 1
 
 
-@pytest.mark.parametrize('warps', [16, 8])
+@pytest.mark.parametrize('warps,kchunks,mode', [(16, 1, 1), (15, 4, 1), (15, 16, 1), (15, 8, 0), (16, 16, 0), (8, 8, 1)])
 @pytest.mark.parametrize('p_old,c,cap', [(1, 1, 352), (1, 8, 352), (9, 28, 352), (37, 56, 352), (50, 168, 352),
                                           (71, 168, 352), (3, 5, 32), (130, 40, 64), (20, 300, 128), (400, 17, 352)])
-def test_gram_work_plan_covers_the_block_exactly_once(p_old, c, cap, warps):
+def test_gram_work_plan_covers_the_block_exactly_once(p_old, c, cap, warps, kchunks, mode):
     """K2 plan (csrc/gram_plan.h): every entry of [X_old X_new y]' X_new that fokl_gram_scatter reads (all old / y rows,
     and the new x new part on or above the diagonal) is produced by exactly one fragment of one block of one tile, from
-    the right pair of columns; tiles respect the block and shared-memory-slot budgets."""
+    the right pair of columns, as the sum of the block's k-split work items over disjoint 16-row chunks; tiles respect
+    the position and shared-memory-slot budgets."""
     rng = np.random.default_rng(p_old * 1000 + c)
-    n = 7
+    n = 16 * 2 * kchunks + 5
     A = rng.standard_normal((n, p_old + c + 1))
-    rc, out, cover, st = emu.gram_plan(A, p_old, c, cap, warps)
+    rc, out, cover, st = emu.gram_plan(A, p_old, c, cap, warps, kchunks, mode)
     assert rc == 0, rc
     ref = A.T @ A[:, p_old:p_old + c]
     a, j = np.meshgrid(np.arange(p_old + c + 1) - p_old, np.arange(c), indexing='ij')
@@ -198,8 +199,19 @@ def test_gram_work_plan_covers_the_block_exactly_once(p_old, c, cap, warps):
     assert np.all(cover[needed] == 1)
     assert np.all(cover <= 1)
     got = cover == 1
-    assert np.allclose(out[got], ref[got], rtol=1e-13, atol=1e-13)
-    assert st['max_blocks_per_tile'] <= 4 * warps and st['max_slots'] <= cap
+    assert np.allclose(out[got], ref[got], rtol=1e-12, atol=1e-12)
+    assert st['max_positions_per_tile'] <= 4 * warps and st['max_slots'] <= cap and st['max_ksplit'] <= kchunks
     # balanced: no tile is much smaller than the largest unless the slot cap forced a cut
     if p_old + c + 32 <= cap:
         assert st['n_tiles'] == -(-st['blocks'] // (4 * warps))
+
+
+def test_gram_k_split_fills_the_cta():
+    """A narrow substage (8 new columns against 50 old ones: 4 blocks) is split over the 16-row chunks of a slab so
+    that every warp of the CTA has work; a wide one (168 new columns) is left alone."""
+    A = np.random.default_rng(0).standard_normal((300, 50 + 8 + 1))
+    rc, _, _, st = emu.gram_plan(A, 50, 8, 352, 16, 16)
+    assert rc == 0 and st['max_ksplit'] >= 4 and st['max_positions_per_tile'] >= 16
+    A = np.random.default_rng(0).standard_normal((40, 50 + 168 + 1))
+    rc, _, _, st = emu.gram_plan(A, 50, 168, 352, 16, 4)
+    assert rc == 0 and st['max_ksplit'] == 1

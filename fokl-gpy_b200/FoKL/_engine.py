@@ -6,7 +6,9 @@ group; every numerical stage is a hand-written sm_100a kernel behind the C ABI (
 HBM layout (all float64):
     x     [M][ldx]     normalised inputs, column-major (one input per row of the tensor), ldx = ceil16(N)
     y     [ldx]        data
-    X     [Pcap][ld]   design matrix, column-major: X[j] is column j (N doubles), column 0 = ones
+    X     [Pcap][ld]   design matrix, column-major: X[j] is column j (N doubles), column 0 = ones; allocated as
+                       rows 1.. of a [1 + Pcap][ld] buffer whose row 0 is a copy of y, so that K2 sees [y | X] as one
+                       2-D tensor (TMA tensor maps, csrc/gram.cu)
     G     [Gcap][Gcap] master Gram X'X of the columns currently in X (symmetric), Xty [Gcap]
 Multi-GPU: every rank holds N/world rows of x, y, X; Gram blocks are summed with one NCCL allreduce per
 substage, after which every rank owns the full G (axis 1).
@@ -97,7 +99,7 @@ class Engine:
         self.kernel_id = None
         self.n_orders = 0
         self.ds = None
-        self.X = None
+        self.X = self.Xfull = None
         self.P = 0
         self.G = self.Xty = self.G2 = self.Xty2 = None
         self.block = None
@@ -109,11 +111,11 @@ class Engine:
     # ------------------------------------------------------------------------------------------------
     def release(self):
         """Free the design-matrix buffer kept between fits."""
-        self.X = None
+        self.X = self.Xfull = None
         self.Pcap = 0
 
     def close(self):
-        self.X = None
+        self.X = self.Xfull = None
         if getattr(self, 'ctx', None) is not None and self.ctx:
             self.lib.fokl_ctx_destroy(self.ctx)
             self.ctx = None
@@ -255,6 +257,7 @@ class Engine:
             self.X = None
             self._ensure_columns(64 if n * 64 * 8 < (4 << 30) else 16)
         self._ck(self.lib.fokl_fill_ones(self.ctx, self.X.data_ptr(), n))
+        self.Xfull[0].copy_(ds.y)
         self.P = 0
         mom = torch.zeros(3, dtype=torch.float64, device=self.device)
         self._ck(self.lib.fokl_y_moments(self.ctx, ds.y.data_ptr(), n, mom.data_ptr()))
@@ -282,20 +285,21 @@ class Engine:
         col_bytes = self.ld * 8
         Xn = None
         try:
-            Xn = torch.empty((new_cap, self.ld), dtype=torch.float64, device=self.device)
+            Xn = torch.empty((new_cap + 1, self.ld), dtype=torch.float64, device=self.device)
         except torch.OutOfMemoryError:
             torch.cuda.empty_cache()
             free, _ = torch.cuda.mem_get_info(self.device)
-            new_cap = min(new_cap, max(need, int(free * 0.9) // col_bytes))
+            new_cap = min(new_cap, max(need, int(free * 0.9) // col_bytes - 1))
             try:
-                Xn = torch.empty((new_cap, self.ld), dtype=torch.float64, device=self.device)
+                Xn = torch.empty((new_cap + 1, self.ld), dtype=torch.float64, device=self.device)
             except torch.OutOfMemoryError:
                 Xn = None
         if Xn is None:
             raise MemoryError("design matrix of %d columns x %d rows does not fit in device memory" % (need, self.ds.n))
         if self.X is not None and self.P > 0:
-            Xn[:self.P].copy_(self.X[:self.P])
-        self.X = Xn
+            Xn[:self.P + 1].copy_(self.Xfull[:self.P + 1])      # y row + the columns built so far
+        self.Xfull = Xn
+        self.X = Xn[1:]
         self.Pcap = new_cap
 
     def _ensure_gram(self, need):
@@ -323,7 +327,7 @@ class Engine:
             self.block = torch.empty((int(need * 1.5) + 64,), dtype=torch.float64, device=self.device)
         t = self._tic()
         self._ck(self.lib.fokl_gram_update(self.ctx, self.X.data_ptr(), self.ld, self.ds.n, p_old, c,
-                                           self.ds.y.data_ptr(), self.block.data_ptr()))
+                                           self.Xfull.data_ptr(), self.block.data_ptr()))
         # algorithmic flops: cross block + upper triangle of the symmetric new block + X_new' y
         self._toc(t, 'gram', flops=2.0 * self.ds.n * (p_old * c + c * (c + 1) / 2 + c), bytes=8.0 * self.ds.n * (p_old + c + 1),
                   cols=p_old + c + 1)

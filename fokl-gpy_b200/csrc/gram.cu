@@ -15,6 +15,7 @@
 // (deterministic, no atomics) while scattering to the (P_old + C + 1) x C block.
 #include "fokl_ctx.cuh"
 #include "gram_plan.h"
+#include <cuda.h>            // CUtensorMap types only: the encoder is fetched through cudaGetDriverEntryPoint
 #include <algorithm>
 #include <stdlib.h>
 #include <string.h>
@@ -26,6 +27,7 @@ using fokl::GramTileMeta;
 using fokl::kGramBlocksPerWarp;
 
 constexpr int kMaxStages = 4;            // cp.async ring depth: 4, or 3 when that buys a deeper slab
+constexpr int kMaxStagesTma = 8;         // TMA ring depth
 constexpr int kPad = 4;                     // row stride KB + 4 doubles: fragment loads hit 16 distinct 8-byte banks
 
 struct GramParams {
@@ -113,6 +115,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
         if (spin > (1u << 26)) __trap();
     }
 }
+// One lane of the (converged) warp, the same for the whole warp: lets the compiler issue a warp-uniform instruction once.
+__device__ __forceinline__ bool elect_one()
+{
+    unsigned pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+// A run of staged columns that are consecutive both in the tile's slot list and in X: what the producer walks.
+struct GramRun {
+    const double *src;      // column of the first slot
+    int32_t slot0, len;
+};
 // global -> shared bulk copy (TMA engine, no tensor map), completion counted in bytes on an mbarrier
 __device__ __forceinline__ void bulk_g2s(void *smem, const void *gmem, unsigned bytes, uint64_t *bar)
 {
@@ -193,14 +213,12 @@ __device__ __forceinline__ void gram_consume(const GramParams &P, const GramTile
 
 // Producer warp of the mbarrier ring: one bulk copy per staged column and slab (KB rows = KB * 8 contiguous bytes),
 // all completing on the stage's `full` barrier; a stage is refilled as soon as every consumer warp has released it.
-__device__ __forceinline__ void gram_produce(const GramParams &P, const GramTileMeta &tm, double *stages, size_t stage_doubles,
-                                             int stride, const double *const *s_ptr, uint64_t *full, uint64_t *empty,
-                                             int64_t n_lo, int64_t n_hi, int nk, int lane)
+// The whole warp walks the runs with warp-uniform operands and one elected lane issues each copy (per-lane operands
+// would make the compiler serialise the warp lane by lane, ~55 cycles per copy: profiles/r01_gram_ksplit.txt).
+__device__ __forceinline__ void gram_produce(const GramParams &P, double *stages, size_t stage_doubles, int stride,
+                                             const GramRun *runs, int n_runs, int n_real, uint64_t *full, uint64_t *empty,
+                                             int64_t n_lo, int64_t n_hi, int nk, int64_t ld, int lane)
 {
-    int n_real = 0;
-    for (int slot = lane; slot < tm.n_slots; slot += 32) n_real += s_ptr[slot] != nullptr;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) n_real += __shfl_xor_sync(0xffffffffu, n_real, o);
     const unsigned slab_bytes = (unsigned)P.kb * 8u;
     const int stages_n = P.stages;
     int st = 0;
@@ -211,24 +229,209 @@ __device__ __forceinline__ void gram_produce(const GramParams &P, const GramTile
         const int64_t r0 = n_lo + (int64_t)kt * P.kb;
         const int64_t left = n_hi - r0;
         if (left >= P.kb) {
-            if (lane == 0) mbar_arrive_expect_tx(full + st, (unsigned)n_real * slab_bytes);
+            if (elect_one()) mbar_arrive_expect_tx(full + st, (unsigned)n_real * slab_bytes);
             __syncwarp();
-            for (int slot = lane; slot < tm.n_slots; slot += 32) {
-                const double *col = s_ptr[slot];
-                if (col != nullptr) bulk_g2s(dst + (size_t)slot * stride, col + r0, slab_bytes, full + st);
+            for (int r = 0; r < n_runs; ++r) {
+                const GramRun run = runs[r];
+                const double *src = run.src + r0;
+                double *d = dst + (size_t)run.slot0 * stride;
+                for (int i = 0; i < run.len; ++i) {
+                    if (elect_one()) bulk_g2s(d, src, slab_bytes, full + st);
+                    src += ld;
+                    d += stride;
+                }
             }
         } else {
             // last, partial slab of the matrix: plain copies with zero fill (rows >= n never enter a product)
-            for (int slot = 0; slot < tm.n_slots; ++slot) {
-                const double *col = s_ptr[slot];
-                if (col == nullptr) continue;
-                for (int k = lane; k < P.kb; k += 32) dst[(size_t)slot * stride + k] = k < left ? col[r0 + k] : 0.0;
+            for (int r = 0; r < n_runs; ++r) {
+                const GramRun run = runs[r];
+                for (int i = 0; i < run.len; ++i)
+                    for (int k = lane; k < P.kb; k += 32)
+                        dst[(size_t)(run.slot0 + i) * stride + k] = k < left ? run.src[(int64_t)i * ld + r0 + k] : 0.0;
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(full + st);
         }
         if (++st == stages_n) { st = 0; ph ^= 1u; }
     }
+}
+
+// ---- 2-D tensor-map TMA ring (gram_kernel_tma) -------------------------------------------------------------------------
+// Stage layout: [16-row chunk][slot][16 doubles], every 128-byte row written by the copy engine with the 128-byte
+// swizzle (16-byte unit j of slot row s lands at unit j ^ (s & 7)).  A DMMA fragment load touches 8 slot rows x 4
+// reduction indices; the reduction index is free to permute, so k-step t of a chunk uses the rows {2t, 2t+1, 2t+8, 2t+9}
+// of the chunk: the two 16-byte units t and t + 4 of each slot row, which the swizzle spreads over all 32 banks for the
+// 4 slot rows of a half warp (conflict-free, no padding).
+__device__ __forceinline__ void tma_load_2d(void *smem, const CUtensorMap *map, int c0, int c1, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::"r"(
+                     smem_u32(smem)),
+                 "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+
+struct GramTmaMaps {
+    CUtensorMap m[fokl::kGramBoxKinds];
+};
+
+template <int WARPS, int NB, bool MASKED>
+__device__ __forceinline__ void gram_consume_tma(const GramParams &P, const GramTileMeta &tm, const double *stages, size_t stage_doubles,
+                                                 uint64_t *full, uint64_t *empty, int nk, int lane, int warp, double *out)
+{
+    constexpr int kGramWarps = WARPS;
+    const int frag_r = lane >> 2, frag_k = lane & 3;
+    // lane constants of the swizzled address: unit = (t + 4 h) ^ r with h = frag_k >> 1; element within the unit = frag_k & 1
+    const int lane_off = 8 * ((frag_k >> 1) ^ (frag_r >> 2)) + (frag_k & 1);
+    const int r3 = frag_r & 3;
+    int a_off[NB], b_off[NB], ph0[NB];
+    unsigned msk[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        const GramBlockMeta bm = P.blocks[tm.blk_off + warp + kGramWarps * b];
+        a_off[b] = (bm.a_slot + frag_r) * 16 + lane_off;
+        b_off[b] = (bm.b_slot + frag_r) * 16 + lane_off;
+        ph0[b] = bm.phase;
+        msk[b] = bm.mask;
+    }
+    double acc[NB][4][2];
+#pragma unroll
+    for (int b = 0; b < NB; ++b)
+#pragma unroll
+        for (int f = 0; f < 4; ++f) acc[b][f][0] = acc[b][f][1] = 0.0;
+
+    const int stages_n = P.stages;
+    const int chunks = P.kb >> 4, ksplit = tm.ksplit;
+    const int chunk_doubles = P.max_slots * 16;
+    constexpr int half = 8 * 16;                                   // second fragment row / column of a block: 8 slot rows on
+    int st = 0;
+    unsigned ph = 0;
+    for (int kt = 0; kt < nk; ++kt) {
+        mbar_wait(full + st, ph);
+        const double *S = stages + (size_t)st * stage_doubles;
+        for (int c0 = 0; c0 < chunks; c0 += ksplit) {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int toff = 2 * (t ^ r3);
+                double a0[NB], a1[NB], b0[NB], b1[NB];
+#pragma unroll
+                for (int b = 0; b < NB; ++b) {
+                    const double *base = S + (c0 + ph0[b]) * chunk_doubles + toff;
+                    const double *pa = base + a_off[b], *pb = base + b_off[b];
+                    a0[b] = pa[0]; a1[b] = pa[half]; b0[b] = pb[0]; b1[b] = pb[half];
+                }
+#pragma unroll
+                for (int b = 0; b < NB; ++b) {
+                    if (MASKED) {
+                        dmma_m8n8k4_if<1u>(acc[b][0][0], acc[b][0][1], a0[b], b0[b], msk[b]);
+                        dmma_m8n8k4_if<2u>(acc[b][1][0], acc[b][1][1], a0[b], b1[b], msk[b]);
+                        dmma_m8n8k4_if<4u>(acc[b][2][0], acc[b][2][1], a1[b], b0[b], msk[b]);
+                        dmma_m8n8k4_if<8u>(acc[b][3][0], acc[b][3][1], a1[b], b1[b], msk[b]);
+                    } else {
+                        dmma_m8n8k4(acc[b][0][0], acc[b][0][1], a0[b], b0[b]);
+                        dmma_m8n8k4(acc[b][1][0], acc[b][1][1], a0[b], b1[b]);
+                        dmma_m8n8k4(acc[b][2][0], acc[b][2][1], a1[b], b0[b]);
+                        dmma_m8n8k4(acc[b][3][0], acc[b][3][1], a1[b], b1[b]);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + st);                    // this warp is done reading the stage
+        if (++st == stages_n) { st = 0; ph ^= 1u; }
+    }
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        const int q = warp + kGramWarps * b;
+#pragma unroll
+        for (int f = 0; f < 4; ++f)
+            *reinterpret_cast<double2 *>(out + (size_t)q * 256 + f * 64 + lane * 2) = make_double2(acc[b][f][0], acc[b][f][1]);
+    }
+}
+
+// K2 with the tensor-map ring: WARPS consumer warps + one producer warp per CTA; the producer issues one 2-D copy per box
+// and 16-row chunk.  Rows >= n and columns >= 1 + p of [y | X] are outside the tensor map and arrive as zeros.
+template <int WARPS>
+__global__ void __launch_bounds__((WARPS + 1) * 32, 1)
+gram_kernel_tma(const GramParams P, const __grid_constant__ GramTmaMaps maps, const fokl::GramBoxMeta *__restrict__ boxes)
+{
+    constexpr int kGramWarps = WARPS;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const GramTileMeta tm = P.tiles[blockIdx.x];
+    const size_t stage_doubles = (size_t)(P.kb >> 4) * P.max_slots * 16;
+    // the swizzle pattern is a function of the shared-memory address: stages start on a 1024-byte boundary
+    double *stages = reinterpret_cast<double *>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+    uint64_t *full = reinterpret_cast<uint64_t *>(stages + P.stages * stage_doubles);
+    uint64_t *empty = full + kMaxStagesTma;
+
+    const int64_t n_lo = (int64_t)blockIdx.y * P.rows_per_split;
+    const int64_t n_hi = (n_lo + P.rows_per_split < P.n) ? n_lo + P.rows_per_split : P.n;
+    const int nk = n_hi > n_lo ? (int)((n_hi - n_lo + P.kb - 1) / P.kb) : 0;
+
+    int nb = 0;
+    bool partial = false;
+    if (warp < kGramWarps) {
+        for (int b = 0; b < kGramBlocksPerWarp; ++b) {
+            const int q = warp + kGramWarps * b;
+            if (q >= tm.n_blk) break;
+            const unsigned mk = P.blocks[tm.blk_off + q].mask;
+            if (mk == 0u) break;
+            nb = b + 1;
+            partial |= mk != 15u;
+        }
+    }
+    const int active = __syncthreads_count(lane == 0 && nb > 0);   // consumer warps that own work (and release stages)
+    if (tid == 0) {
+        for (int s = 0; s < P.stages; ++s) {
+            mbar_init(full + s, 1u);
+            mbar_init(empty + s, (unsigned)active);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    __syncthreads();
+
+    if (warp == kGramWarps) {
+        if (active == 0) return;
+        // bytes per stage: every box is written in full (zero fill included)
+        int cols = 0;
+        for (int b = 0; b < tm.n_box; ++b) cols += boxes[tm.box_off + b].ncols;
+        const int chunks = P.kb >> 4;
+        const unsigned stage_bytes = (unsigned)(cols * chunks) * 128u;
+        const int stages_n = P.stages;
+        int st = 0;
+        unsigned ph = 0;
+        for (int kt = 0; kt < nk; ++kt) {
+            if (kt >= stages_n) mbar_wait(empty + st, ph ^ 1u);
+            double *dst = stages + (size_t)st * stage_doubles;
+            const int64_t r0 = n_lo + (int64_t)kt * P.kb;
+            if (elect_one()) mbar_arrive_expect_tx(full + st, stage_bytes);
+            __syncwarp();
+            for (int b = 0; b < tm.n_box; ++b) {
+                const fokl::GramBoxMeta bx = boxes[tm.box_off + b];
+                const CUtensorMap *mp = &maps.m[bx.kind];
+                for (int c = 0; c < chunks; ++c) {
+                    if (elect_one())
+                        tma_load_2d(dst + ((size_t)c * P.max_slots + bx.slot0) * 16, mp, (int)(r0 + 16 * c), bx.xcol0, full + st);
+                }
+            }
+            if (++st == stages_n) { st = 0; ph ^= 1u; }
+        }
+        return;
+    }
+    double *out = P.part + ((size_t)blockIdx.y * P.n_tiles + blockIdx.x) * (size_t)(P.tile_blocks * 256);
+#define FOKL_ROWS(NB)                                                                                                  \
+    if (partial) gram_consume_tma<WARPS, NB, true>(P, tm, stages, stage_doubles, full, empty, nk, lane, warp, out);     \
+    else gram_consume_tma<WARPS, NB, false>(P, tm, stages, stage_doubles, full, empty, nk, lane, warp, out);            \
+    break;
+    switch (nb) {
+    case 0: break;
+    case 1: FOKL_ROWS(1)
+    case 2: FOKL_ROWS(2)
+    case 3: FOKL_ROWS(3)
+    default: FOKL_ROWS(4)
+    }
+#undef FOKL_ROWS
 }
 
 // The row loop of one CTA for a warp that owns NB blocks (q = warp + 16 b, b < NB).  NB is a template parameter so
@@ -392,9 +595,11 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) gram_kernel_mb(const Gram
     const int stride = P.kb + kPad;
     const size_t stage_doubles = (size_t)P.max_slots * stride;
     double *stages = reinterpret_cast<double *>(smem_raw);
-    const double **s_ptr = reinterpret_cast<const double **>(stages + P.stages * stage_doubles);
-    uint64_t *full = reinterpret_cast<uint64_t *>(s_ptr + P.max_slots);
+    // (same shared-memory carve-up as the cp.async kernel: the column-pointer area holds the run table, 16 bytes per run)
+    GramRun *runs = reinterpret_cast<GramRun *>(stages + P.stages * stage_doubles);
+    uint64_t *full = reinterpret_cast<uint64_t *>(reinterpret_cast<const double **>(runs) + P.max_slots);
     uint64_t *empty = full + kMaxStages;
+    int *run_info = reinterpret_cast<int *>(empty + kMaxStages);      // [0] runs, [1] staged (non-padding) slots
 
     const int64_t n_lo = (int64_t)blockIdx.y * P.rows_per_split;
     const int64_t n_hi = (n_lo + P.rows_per_split < P.n) ? n_lo + P.rows_per_split : P.n;
@@ -413,10 +618,26 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) gram_kernel_mb(const Gram
             partial |= mk != 15u;
         }
     }
-    // operand column pointers; padding slots stay zero in every stage (never written by a copy)
-    for (int s = tid; s < tm.n_slots; s += kThreads) {
-        const int src = P.slot_src[tm.slot_off + s];
-        s_ptr[s] = src < 0 ? nullptr : (src == P.p ? P.y : P.X + (int64_t)src * P.ld);
+    // runs of staged columns (at most n_slots / 2 of them fit the table: a run of one slot next to padding at worst);
+    // padding slots stay zero in every stage (never written by a copy)
+    if (tid == 0) {
+        int n_runs = 0, n_real = 0, prev = -2;
+        for (int sl = 0; sl < tm.n_slots; ++sl) {
+            const int src = P.slot_src[tm.slot_off + sl];
+            if (src < 0) { prev = -2; continue; }
+            ++n_real;
+            if (src == prev + 1 && src != P.p && n_runs > 0) {
+                ++runs[n_runs - 1].len;
+            } else {
+                runs[n_runs].src = src == P.p ? P.y : P.X + (int64_t)src * P.ld;
+                runs[n_runs].slot0 = sl;
+                runs[n_runs].len = 1;
+                ++n_runs;
+            }
+            prev = src;
+        }
+        run_info[0] = n_runs;
+        run_info[1] = n_real;
     }
     for (size_t e = tid; e < P.stages * stage_doubles; e += kThreads) stages[e] = 0.0;
     const int active = __syncthreads_count(lane == 0 && nb > 0);   // consumer warps that own work (and release stages)
@@ -431,7 +652,8 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) gram_kernel_mb(const Gram
     __syncthreads();
 
     if (warp == kGramWarps) {
-        if (active > 0) gram_produce(P, tm, stages, stage_doubles, stride, s_ptr, full, empty, n_lo, n_hi, nk, lane);
+        if (active > 0)
+            gram_produce(P, stages, stage_doubles, stride, runs, run_info[0], run_info[1], full, empty, n_lo, n_hi, nk, P.ld, lane);
         return;
     }
     double *out = P.part + ((size_t)blockIdx.y * P.n_tiles + blockIdx.x) * (size_t)(P.tile_blocks * 256);
@@ -477,6 +699,42 @@ __global__ void gram_reduce_kernel(const double *__restrict__ part, int nsplit, 
 
 }  // namespace
 
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn tensor_map_encoder()
+{
+    static EncodeTiledFn fn = []() -> EncodeTiledFn {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            return nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+// [y | X] as a (cols x rows) float64 tensor, fetched in boxes of `box_cols` columns x 16 rows with the 128-byte swizzle;
+// rows >= n and columns >= cols read as zeros.
+bool encode_gram_map(CUtensorMap *map, const double *base, int64_t ld, int64_t n, int cols, int box_cols)
+{
+    EncodeTiledFn enc = tensor_map_encoder();
+    if (!enc) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)n, (cuuint64_t)cols};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(double)};
+    const cuuint32_t box[2] = {16u, (cuuint32_t)box_cols};
+    const cuuint32_t estr[2] = {1u, 1u};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double *>(base), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace
+
 extern "C" int fokl_gram_update(fokl_ctx *ctx, const double *X, int64_t ld, int64_t n, int p_old, int c,
                                 const double *y, double *block)
 {
@@ -505,7 +763,7 @@ extern "C" int fokl_gram_update(fokl_ctx *ctx, const double *X, int64_t ld, int6
     const size_t smem_cap = smem_total - 1024;
     auto smem_need = [&](int slots, int kb, int stages) {
         return (size_t)stages * slots * (kb + kPad) * sizeof(double) + (size_t)slots * sizeof(double *) +
-               2 * kMaxStages * sizeof(uint64_t);
+               2 * kMaxStages * sizeof(uint64_t) + 16;
     };
     int cap = 32;
     while (smem_need(cap + 16, 16, kMaxStages) <= smem_cap) cap += 16;
@@ -513,21 +771,42 @@ extern "C" int fokl_gram_update(fokl_ctx *ctx, const double *X, int64_t ld, int6
     const char *env_kernel = getenv("FOKL_GRAM_KERNEL");
     const int env_kb = getenv("FOKL_GRAM_KB") ? atoi(getenv("FOKL_GRAM_KB")) : 0;
     const int env_stages = getenv("FOKL_GRAM_STAGES") ? atoi(getenv("FOKL_GRAM_STAGES")) : 0;
-    bool use_mb = !(env_kernel && !strcmp(env_kernel, "cpasync"));
+    // * tensor-map ring (gram_kernel_tma): when y is stored in the row in front of X (the engine's [y | X] buffer) the
+    //   operands of a tile are a handful of column runs of one 2-D tensor; one TMA copy moves a box of up to 128 columns
+    //   x 16 rows, so the copy count no longer grows with the staged columns and the ring is 4 - 8 stages deep.
+    //   A box is 16 rows deep (the swizzle span), so narrow tiles would move 1 KB per copy: they stay on the bulk-copy ring.
+    const bool can_tma = (y + ld == X) && (ld % 16) == 0 && tensor_map_encoder() != nullptr;
+    bool use_tma = can_tma && env_kernel && !strcmp(env_kernel, "tma");
+    bool use_mb = !use_tma && !(env_kernel && !strcmp(env_kernel, "cpasync"));
     int warps = 15, kb = 0, stages = 0;
     fokl::GramPlan plan;
-    if (use_mb) {
+    auto smem_need_tma = [&](int slots, int kb_, int st) {
+        return (size_t)st * (kb_ / 16) * slots * 128 + 2 * kMaxStagesTma * sizeof(uint64_t) + 1024;
+    };
+    if (use_mb || use_tma) {
         plan = fokl::gram_make_plan(p_old, c, cap, warps);
         if (plan.tiles.empty() || plan.max_slots > cap) FOKL_FAIL(ctx, FOKL_ESTATE, "gram_update: empty or oversized plan");
+    }
+    if (use_mb) {
         // deepest slab that leaves a ring of >= 3 stages (>= 2 for slabs of >= 128 rows)
         for (int cand_kb = 256; cand_kb >= 64 && kb == 0; cand_kb /= 2) {
             if (n < (int64_t)cand_kb * 4) continue;
             for (int st = kMaxStages; st >= (cand_kb >= 128 ? 2 : 3); --st)
                 if (smem_need(plan.max_slots, cand_kb, st) <= smem_cap) { kb = cand_kb; stages = st; break; }
         }
-        if (kb == 0 && !env_kernel) use_mb = false;
+        if (kb == 0 && !env_kernel) { use_mb = false; use_tma = can_tma; }       // wide tile: tensor-map ring, else cp.async
     }
-    if (!use_mb) {
+    if (use_tma) {
+        // deepest slab that leaves a ring of >= 4 stages
+        kb = 0;
+        for (int cand_kb = 256; cand_kb >= 16 && kb == 0; cand_kb /= 2) {
+            if (cand_kb > 16 && n < (int64_t)cand_kb * 4) continue;
+            for (int st = kMaxStagesTma; st >= (cand_kb > 16 ? 4 : 2); --st)
+                if (smem_need_tma(plan.max_slots, cand_kb, st) <= smem_cap) { kb = cand_kb; stages = st; break; }
+        }
+        if (kb == 0) use_tma = false;
+    }
+    if (!use_mb && !use_tma) {
         warps = 16;
         plan = fokl::gram_make_plan(p_old, c, cap, warps);
         if (plan.tiles.empty() || plan.max_slots > cap) FOKL_FAIL(ctx, FOKL_ESTATE, "gram_update: empty or oversized plan");
@@ -542,9 +821,10 @@ extern "C" int fokl_gram_update(fokl_ctx *ctx, const double *X, int64_t ld, int6
     }
     if (kb == 0) { kb = 16; stages = kMaxStages; }
     if (env_kb >= 16 && env_kb <= 256 && (env_kb & (env_kb - 1)) == 0) kb = env_kb;
-    if (env_stages >= 2 && env_stages <= kMaxStages) stages = env_stages;
-    if (!use_mb && stages < 3) stages = 3;            // the cp.async ring waits on groups of a 3- or 4-deep ring
-    if (smem_need(plan.max_slots, kb, stages) > smem_cap) FOKL_FAIL(ctx, FOKL_EINVAL, "gram_update: slab does not fit in shared memory");
+    if (env_stages >= 2 && env_stages <= (use_tma ? kMaxStagesTma : kMaxStages)) stages = env_stages;
+    if (!use_mb && !use_tma && stages < 3) stages = 3;            // the cp.async ring waits on groups of a 3- or 4-deep ring
+    if ((use_tma ? smem_need_tma(plan.max_slots, kb, stages) : smem_need(plan.max_slots, kb, stages)) > smem_cap)
+        FOKL_FAIL(ctx, FOKL_EINVAL, "gram_update: slab does not fit in shared memory");
     const int n_tiles = (int)plan.tiles.size();
     const int kTileBlocks = fokl::gram_tile_blocks(warps);
     int kb_shift = 0;
@@ -553,7 +833,7 @@ extern "C" int fokl_gram_update(fokl_ctx *ctx, const double *X, int64_t ld, int6
     // 2 % elsewhere, profiles/r01_gram_ksplit.txt), 0 = balanced deal
     const int place_mode = getenv("FOKL_GRAM_PLACE") ? atoi(getenv("FOKL_GRAM_PLACE")) : 1;
     // k-split of tiles with few blocks (gram_plan.h); the cp.async kernel works whole slabs per item
-    fokl::gram_plan_place(plan, warps, use_mb ? kb / 16 : 1, place_mode);
+    fokl::gram_plan_place(plan, warps, (use_mb || use_tma) ? kb / 16 : 1, place_mode);
 
     // row splits: about one resident CTA slot each
     const int64_t chunks = (n + kb - 1) / kb;
@@ -571,13 +851,15 @@ extern "C" int fokl_gram_update(fokl_ctx *ctx, const double *X, int64_t ld, int6
     size_t off_arow = off_src + n_slots * sizeof(int32_t);
     size_t off_bcol = off_arow + n_slots * sizeof(int32_t);
     size_t off_blk = off_bcol + n_slots * sizeof(int32_t);
-    size_t meta_bytes = off_blk + n_blocks * sizeof(GramBlockMeta);
+    size_t off_box = (off_blk + n_blocks * sizeof(GramBlockMeta) + 15) & ~(size_t)15;
+    size_t meta_bytes = off_box + plan.boxes.size() * sizeof(fokl::GramBoxMeta);
     std::vector<unsigned char> host(meta_bytes);
     memcpy(host.data() + off_tiles, plan.tiles.data(), (size_t)n_tiles * sizeof(GramTileMeta));
     memcpy(host.data() + off_src, plan.slot_src.data(), n_slots * sizeof(int32_t));
     memcpy(host.data() + off_arow, plan.slot_arow.data(), n_slots * sizeof(int32_t));
     memcpy(host.data() + off_bcol, plan.slot_bcol.data(), n_slots * sizeof(int32_t));
     memcpy(host.data() + off_blk, plan.blocks.data(), n_blocks * sizeof(GramBlockMeta));
+    memcpy(host.data() + off_box, plan.boxes.data(), plan.boxes.size() * sizeof(fokl::GramBoxMeta));
     const size_t part_bytes = (size_t)nsplit * n_tiles * kTileBlocks * 256 * sizeof(double);
     const size_t part_off = (meta_bytes + 255) & ~(size_t)255;
     unsigned char *buf = (unsigned char *)fokl_scratch(ctx, fokl_ctx::B_GRAM, part_off + part_bytes);
@@ -596,8 +878,16 @@ extern "C" int fokl_gram_update(fokl_ctx *ctx, const double *X, int64_t ld, int6
     P.part = reinterpret_cast<double *>(buf + part_off);
     P.n_tiles = n_tiles;
     P.tile_blocks = kTileBlocks;
-    const size_t smem = smem_need(plan.max_slots, kb, stages);
-    if (!use_mb) {
+    const size_t smem = use_tma ? smem_need_tma(plan.max_slots, kb, stages) : smem_need(plan.max_slots, kb, stages);
+    if (use_tma) {
+        GramTmaMaps maps;
+        for (int k = 0; k < fokl::kGramBoxKinds; ++k)
+            if (!encode_gram_map(&maps.m[k], y, ld, n, p + 1, fokl::kGramBoxCols[k]))
+                FOKL_FAIL(ctx, FOKL_ECUDA, "gram_update: cuTensorMapEncodeTiled failed");
+        FOKL_CUDA(ctx, cudaFuncSetAttribute(gram_kernel_tma<15>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
+        gram_kernel_tma<15><<<dim3(n_tiles, nsplit), 16 * 32, smem, ctx->stream>>>(
+            P, maps, reinterpret_cast<const fokl::GramBoxMeta *>(buf + off_box));
+    } else if (!use_mb) {
         FOKL_CUDA(ctx, cudaFuncSetAttribute(gram_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
         gram_kernel<16><<<dim3(n_tiles, nsplit), 512, smem, ctx->stream>>>(P);
     } else {

@@ -3,7 +3,7 @@
 //
 // The block K2 has to form is   [X_old  X_new  y]' X_new     ((P_old + C + 1) x C).
 // Plan vocabulary:
-//   A-list   the (P_old + C + 1) operand columns in the order  new_0 .. new_{C-1} | pad to 8 | old_0 .. old_{P_old-1}, y |
+//   A-list   the (P_old + C + 1) operand columns in the order  new_0 .. new_{C-1} | pad to 8 | y, old_0 .. old_{P_old-1} |
 //            pad to 8.  Putting the new columns first makes the symmetric X_new' X_new part start on an 8-column
 //            boundary, so "this 8 x 8 fragment lies entirely below the diagonal" is the plain test  i > j.
 //   fragment one 8 x 8 piece of the output (one mma.sync.m8n8k4.f64 accumulator): rows = 8 consecutive A-list entries,
@@ -30,6 +30,19 @@ struct GramTileMeta {
     int32_t slot_off, n_slots;          // into slot_* arrays; n_slots is a multiple of 8
     int32_t blk_off, n_blk;             // into blocks; n_blk = positions in use (work items and holes)
     int32_t ksplit, pad;                // every block of the tile is shared by `ksplit` work items (power of two)
+    int32_t box_off, n_box;             // into boxes (TMA path)
+};
+
+// TMA path: the engine keeps y in the row in front of X ("[y | X]": column 0 = y, column 1 + j = X column j), so every
+// 8-slot group of a tile is 8 consecutive columns of that buffer and consecutive groups merge into runs; a run is
+// fetched as boxes of kGramBoxCols[kind] columns x 16 rows, one 2-D tensor-map copy each.  Columns past the end of the
+// buffer's used part (padding slots of the last new group) are zero-filled by the copy engine.
+constexpr int kGramBoxKinds = 3;
+constexpr int kGramBoxCols[kGramBoxKinds] = {8, 32, 128};
+struct GramBoxMeta {
+    int32_t slot0;                      // first tile-local slot
+    int32_t xcol0;                      // first column of [y | X]
+    int32_t kind, ncols;                // box kind and its column count (kGramBoxCols[kind])
 };
 
 // One work item = one 2 x 2-fragment block restricted to the 16-row chunks  phase, phase + ksplit, ...  of every slab.
@@ -46,6 +59,7 @@ struct GramPlan {
     std::vector<int32_t> slot_arow;     // per slot: row of the output block, -1 = none
     std::vector<int32_t> slot_bcol;     // per slot: column of the output block (new-column index), -1 = none
     std::vector<GramBlockMeta> blocks;
+    std::vector<GramBoxMeta> boxes;
     int max_slots = 0;
 };
 
@@ -187,8 +201,8 @@ inline GramPlan gram_make_plan(int p_old, int c, int max_slots_cap, int warps = 
     const int fa = fb + fo;                          // A-list length in fragments
     auto alist_src = [&](int e) -> int {             // A-list entry -> X column (p = y, -1 = pad)
         if (e < fb * 8) return e < c ? p_old + e : -1;
-        int o = e - fb * 8;
-        return o < p_old ? o : (o == p_old ? p : -1);
+        int o = e - fb * 8;                          // y first: [y | X_old] is one run of the engine's [y | X] buffer
+        return o == 0 ? p : (o <= p_old ? o - 1 : -1);
     };
     auto frag_needed = [&](int i, int j) { return i >= fb || i <= j; };
     const int ba = (fa + 1) / 2, bb = (fb + 1) / 2;  // block rows / cols (a block = fragment pair)
@@ -274,6 +288,32 @@ inline GramPlan gram_make_plan(int p_old, int c, int max_slots_cap, int warps = 
         pl.blocks.insert(pl.blocks.end(), full_blk.begin(), full_blk.end());
         tm.ksplit = 1;
         tm.pad = 0;
+        // boxes: runs of 8-slot groups that are consecutive in [y | X], cut greedily into the largest box kinds
+        tm.box_off = (int32_t)pl.boxes.size();
+        {
+            auto xcol = [&](int src) { return src == p ? 0 : src + 1; };
+            const int n_grp = tm.n_slots / 8;
+            int g = 0;
+            while (g < n_grp) {
+                const int x0 = xcol(pl.slot_src[tm.slot_off + 8 * g]);
+                int len = 1;
+                while (g + len < n_grp && xcol(pl.slot_src[tm.slot_off + 8 * (g + len)]) == x0 + 8 * len) ++len;
+                int done = 0;
+                while (done < len) {
+                    int kind = kGramBoxKinds - 1;
+                    while (kind > 0 && kGramBoxCols[kind] > 8 * (len - done)) --kind;
+                    GramBoxMeta bx;
+                    bx.slot0 = 8 * (g + done);
+                    bx.xcol0 = x0 + 8 * done;
+                    bx.kind = kind;
+                    bx.ncols = kGramBoxCols[kind];
+                    pl.boxes.push_back(bx);
+                    done += kGramBoxCols[kind] / 8;
+                }
+                g += len;
+            }
+        }
+        tm.n_box = (int32_t)pl.boxes.size() - tm.box_off;
         pl.tiles.push_back(tm);
         pl.max_slots = std::max(pl.max_slots, (int)tm.n_slots);
     }

@@ -5,13 +5,21 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def gram_block(engine, Xh, yh, p_old, c):
+def gram_block(engine, Xh, yh, p_old, c, joint=False):
+    """joint: y stored in the row in front of X (the engine's [y | X] buffer -> tensor-map TMA kernel); otherwise y is
+    a separate buffer (mbarrier / cp.async kernels)."""
     import torch
     n, p = Xh.shape
     ld = ((n + 15) // 16) * 16
-    X = torch.zeros((p, ld), dtype=torch.float64, device=engine.device)
+    full = torch.zeros((p + 1, ld), dtype=torch.float64, device=engine.device)
+    X = full[1:]
     X[:, :n] = torch.from_numpy(np.ascontiguousarray(Xh.T)).to(engine.device)
-    y = torch.zeros(ld, dtype=torch.float64, device=engine.device)
+    if joint:
+        y = full[0]
+        # rows n .. ld of the buffer are never read as data: poison them
+        full[:, n:] = float('nan')
+    else:
+        y = torch.zeros(ld, dtype=torch.float64, device=engine.device)
     y[:n] = torch.from_numpy(yh).to(engine.device)
     block = torch.full(((p_old + c + 1) * c,), np.nan, dtype=torch.float64, device=engine.device)
     engine._ck(engine.lib.fokl_gram_update(engine.ctx, X.data_ptr(), ld, n, p_old, c, y.data_ptr(), block.data_ptr()))
@@ -19,14 +27,17 @@ def gram_block(engine, Xh, yh, p_old, c):
     return block.cpu().numpy().reshape(p_old + c + 1, c)
 
 
+@pytest.mark.parametrize('joint', [False, True])
 @pytest.mark.parametrize('n,p_old,c', [(1, 1, 1), (10, 1, 2), (33, 3, 5), (1000, 9, 8), (4097, 63, 1), (4097, 64, 64),
                                         (2500, 65, 67), (100000, 130, 40), (300001, 20, 168)])
-def test_gram_block_matches_numpy(engine, n, p_old, c):
+def test_gram_block_matches_numpy(engine, n, p_old, c, joint, monkeypatch):
+    if joint:       # every shape through the tensor-map kernel (the library would pick it for wide tiles only)
+        monkeypatch.setenv('FOKL_GRAM_KERNEL', 'tma')
     rng = np.random.default_rng(n + p_old)
     Xh = rng.standard_normal((n, p_old + c))
     Xh[:, 0] = 1.0
     yh = rng.standard_normal(n)
-    got = gram_block(engine, Xh, yh, p_old, c)
+    got = gram_block(engine, Xh, yh, p_old, c, joint)
     A = np.hstack([Xh, yh[:, None]])
     ref = A.T @ Xh[:, p_old:]
     scale = np.sqrt(np.outer(np.sum(A * A, axis=0), np.sum(Xh[:, p_old:] ** 2, axis=0)))
@@ -38,7 +49,7 @@ def test_gram_block_matches_numpy(engine, n, p_old, c):
     assert np.all(ok | (below & (got == 0.0)))
     assert np.all(ok[~below])
     # deterministic: a second run gives identical bits
-    again = gram_block(engine, Xh, yh, p_old, c)
+    again = gram_block(engine, Xh, yh, p_old, c, joint)
     assert np.array_equal(got, again)
     # scattered into the master Gram the block is exactly symmetric and complete
     import torch

@@ -28,8 +28,8 @@ def main():
     shapes = [tuple(int(v) for v in s.split(',')) for s in a.shapes.split(';')] if a.shapes else SHAPES
     pmax = max(p + c for p, c in shapes)
     g = torch.Generator(device='cuda').manual_seed(1)
-    X = torch.rand((pmax, ld), dtype=torch.float64, device='cuda', generator=g) - 0.5
-    y = torch.rand((ld,), dtype=torch.float64, device='cuda', generator=g)
+    full = torch.rand((pmax + 1, ld), dtype=torch.float64, device='cuda', generator=g) - 0.5
+    X, y = full[1:], full[0]           # [y | X]: the engine's layout (tensor-map TMA kernel unless a knob says otherwise)
     block = torch.empty(((pmax + 1) * max(c for _, c in shapes) + 64,), dtype=torch.float64, device='cuda')
     variants = a.variants.split(';')
     knobs = ('FOKL_GRAM_KERNEL', 'FOKL_GRAM_KB', 'FOKL_GRAM_STAGES', 'FOKL_GRAM_PLACE')

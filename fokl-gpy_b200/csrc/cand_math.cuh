@@ -168,6 +168,33 @@ FOKL_HD void eig_finish(const Team &t, const double *W, const double *V, int p, 
 
 // Right-looking Cholesky of the lower triangle stored column-major in L (ld = p): on return column j holds
 // L[i][j], i >= j, and zeros above the diagonal.  Returns false if a pivot is not positive.
+// Packed form: column j of the lower triangle holds its p - j entries (j .. p-1) at chol_col(j, p); half the footprint of
+// the square form, so the factor of a 226-column model is computed in shared memory.  One warp per trailing column,
+// lanes along the rows (contiguous), no index arithmetic per element.
+FOKL_HD int64_t chol_col(int j, int p) { return (int64_t)j * p - (int64_t)j * (j - 1) / 2; }
+
+FOKL_HD bool cholesky_lower_packed(const Team &t, double *L, int p)
+{
+    bool ok = true;
+    for (int j = 0; j < p; ++j) {
+        double *Lj = L + chol_col(j, p) - j;                     // Lj[i] = L(i, j), i >= j
+        const double d = Lj[j];
+        if (!(d > 0.0) || !(d < 1.7e308)) { ok = false; break; }
+        const double r = sqrt(d);
+        t.sync();
+        for (int i = j + t.tid; i < p; i += t.nthr) Lj[i] = (i == j) ? r : Lj[i] / r;
+        t.sync();
+        for (int m = j + 1 + t.warp; m < p; m += t.nwarp) {
+            double *Lm = L + chol_col(m, p) - m;
+            const double lmj = Lj[m];
+            for (int i = m + t.lane; i < p; i += t.nlane) Lm[i] -= Lj[i] * lmj;
+        }
+        t.sync();
+    }
+    t.sync();
+    return ok;
+}
+
 FOKL_HD bool cholesky_lower(const Team &t, double *L, int p)
 {
     bool ok = true;
@@ -763,7 +790,34 @@ FOKL_HD void sweep_pivot(const Team &t, double *T, int ld, int k, double sign, d
     t.sync();
 }
 
-FOKL_HD int kill_loop(const Team &t, const double *G, int64_t ldg, const double *Xty, const int *idx, int p,
+// The tableau is symmetric, and the sweep keeps it so: the packed form stores the lower triangle row by row
+// (T(i, j), i >= j, at i (i + 1) / 2 + j), half the footprint -- the tableau of a 226-column model (206 KB) then fits the
+// shared memory of one SM instead of living in L2 (3 x 6 ms -> 3 x ~1 ms of kill loop per cfg4 fit).
+FOKL_HD int64_t tri_index(int i, int j) { return i >= j ? (int64_t)i * (i + 1) / 2 + j : (int64_t)j * (j + 1) / 2 + i; }
+
+FOKL_HD void sweep_pivot_packed(const Team &t, double *T, int ld, int k, double sign, double *rowbuf)
+{
+    for (int i = t.tid; i < ld; i += t.nthr) rowbuf[i] = T[tri_index(k, i)];
+    t.sync();
+    const double invD = 1.0 / rowbuf[k];
+    for (int j = t.warp; j < ld; j += t.nwarp) {                  // row j: entries (j, 0 .. j), contiguous
+        double *Tj = T + (int64_t)j * (j + 1) / 2;
+        const double ckj = rowbuf[j];
+        if (j == k) {
+            for (int i = t.lane; i <= j; i += t.nlane) Tj[i] = (i == k) ? -invD : sign * rowbuf[i] * invD;
+            continue;
+        }
+        const double vk = sign * ckj * invD;
+        for (int i = t.lane; i <= j; i += t.nlane) {
+            const double r0 = Tj[i] - (rowbuf[i] * ckj) * invD;
+            Tj[i] = (i == k) ? vk : r0;
+        }
+    }
+    t.sync();
+}
+
+template <bool PACKED>
+FOKL_HD int kill_loop_t(const Team &t, const double *G, int64_t ldg, const double *Xty, const int *idx, int p,
                       const int *cand_pos, const double *bv0, const double *bv1, int vm, const CandConst &c,
                       const KillLoopIn &in, double *T, int *out_i, double *out_ev, int *sh /* 4 shared ints */,
                       double *rowbuf /* p + 1 shared doubles */)
@@ -773,6 +827,7 @@ FOKL_HD int kill_loop(const Team &t, const double *G, int64_t ldg, const double 
     const int64_t row0 = (int64_t)idx[0] * ldg;
     for (int e = t.tid; e < ld * ld; e += t.nthr) {
         int j = e / ld, i = e - j * ld;
+        if (PACKED && i < j) continue;
         double v;
         if (i < p && j < p) v = G[(int64_t)idx[i] * ldg + idx[j]];
         else if (i == p && j == p) v = c.yty - c.n * ybar * ybar;
@@ -780,16 +835,17 @@ FOKL_HD int kill_loop(const Team &t, const double *G, int64_t ldg, const double 
             int q = i < p ? i : j;
             v = Xty[idx[q]] - ybar * G[row0 + idx[q]];
         }
-        T[e] = v;
+        T[PACKED ? tri_index(i, j) : (int64_t)e] = v;
     }
     if (t.tid == 0) { sh[0] = 0; sh[1] = 0; sh[2] = 0; sh[3] = 0; }
     t.sync();
     int bad = 0;
     for (int k = 0; k < p; ++k) {
-        const double d = T[(int64_t)k * ld + k];
+        const double d = T[PACKED ? tri_index(k, k) : (int64_t)k * ld + k];
         if (!(d > 1e-11 * G[(int64_t)idx[k] * ldg + idx[k]])) { bad = 1; break; }   // not numerically positive definite
         t.sync();
-        sweep_pivot(t, T, ld, k, 1.0, rowbuf);
+        if (PACKED) sweep_pivot_packed(t, T, ld, k, 1.0, rowbuf);
+        else sweep_pivot(t, T, ld, k, 1.0, rowbuf);
     }
     int n_acc = 0, tested = 0, pa = p, cur = in.start;
     double evmin = in.evmin;
@@ -798,12 +854,12 @@ FOKL_HD int kill_loop(const Team &t, const double *G, int64_t ldg, const double 
     while (!bad && cur < vm) {
         if (t.tid == 0) { sh[0] = 0x7fffffff; sh[1] = 0; sh[2] = 0; }
         t.sync();
-        const double sse = T[(int64_t)p * ld + p];
+        const double sse = T[PACKED ? tri_index(p, p) : (int64_t)p * ld + p];
         for (int i = cur + t.tid; i < vm; i += t.nthr) {
             const bool prop = (bv1[i] > in.threshstdb) || (bv1[i] > in.threshstda && bv0[i] < thr);
             if (!prop) continue;
             const int q = cand_pos[i];
-            const double tqq = T[(int64_t)q * ld + q], tqy = T[(int64_t)p * ld + q];
+            const double tqq = T[PACKED ? tri_index(q, q) : (int64_t)q * ld + q], tqy = T[PACKED ? tri_index(p, q) : (int64_t)p * ld + q];
             if (!(tqq < 0.0)) { sh[2] = 1; continue; }
             const double sig = (sse + tqy * tqy / (-tqq)) / c.n;
             const double evt = (double)(pa - 1) * ln_n - 2.0 * (-(c.n / 2.0) * log(sig) - (c.n - 1.0) / 2.0) +
@@ -821,11 +877,12 @@ FOKL_HD int kill_loop(const Team &t, const double *G, int64_t ldg, const double 
         tested += sh[1];
         if (hit == 0x7fffffff) break;
         const int q = cand_pos[hit];
-        const double tqq = T[(int64_t)q * ld + q], tqy = T[(int64_t)p * ld + q];
+        const double tqq = T[PACKED ? tri_index(q, q) : (int64_t)q * ld + q], tqy = T[PACKED ? tri_index(p, q) : (int64_t)p * ld + q];
         const double sig = (sse + tqy * tqy / (-tqq)) / c.n;
         evmin = (double)(pa - 1) * ln_n - 2.0 * (-(c.n / 2.0) * log(sig) - (c.n - 1.0) / 2.0) + in.aic_adj * (double)(pa - 1);
         t.sync();
-        sweep_pivot(t, T, ld, q, -1.0, rowbuf);
+        if (PACKED) sweep_pivot_packed(t, T, ld, q, -1.0, rowbuf);
+        else sweep_pivot(t, T, ld, q, -1.0, rowbuf);
         if (t.tid == 0) {
             out_i[3 + n_acc] = hit;
             out_i[3 + vm + n_acc] = tested;
@@ -838,6 +895,16 @@ FOKL_HD int kill_loop(const Team &t, const double *G, int64_t ldg, const double 
     if (t.tid == 0) { out_i[0] = n_acc; out_i[1] = tested; out_i[2] = bad; }
     t.sync();
     return bad;
+}
+
+// T: (p + 1)^2 doubles (full form) or (p + 1)(p + 2) / 2 doubles (packed form)
+FOKL_HD int kill_loop(const Team &t, const double *G, int64_t ldg, const double *Xty, const int *idx, int p,
+                      const int *cand_pos, const double *bv0, const double *bv1, int vm, const CandConst &c,
+                      const KillLoopIn &in, double *T, int *out_i, double *out_ev, int *sh /* 4 shared ints */,
+                      double *rowbuf /* p + 1 shared doubles */, bool packed = false)
+{
+    return packed ? kill_loop_t<true>(t, G, ldg, Xty, idx, p, cand_pos, bv0, bv1, vm, c, in, T, out_i, out_ev, sh, rowbuf)
+                  : kill_loop_t<false>(t, G, ldg, Xty, idx, p, cand_pos, bv0, bv1, vm, c, in, T, out_i, out_ev, sh, rowbuf);
 }
 
 }  // namespace fokl

@@ -122,16 +122,30 @@ __global__ void __launch_bounds__(kCholThreads) cand_chol_kernel(const CholParam
     const int p = m.p;
     const int32_t *idx = P.col_sets + m.set_off;
     double *Lg = P.Q + m.mat_off;
-    const bool in_smem = ((int64_t)p * p <= P.smem_doubles);
-    double *L = in_smem ? sh : Lg;
-    for (int e = t.tid; e < p * p; e += t.nthr) {
-        int col = e / p, row = e - col * p;
-        L[e] = (row >= col) ? P.G[(int64_t)idx[row] * P.ldg + idx[col]] : 0.0;
+    const bool in_smem = ((int64_t)p * (p + 1) / 2 <= P.smem_doubles);
+    bool ok;
+    if (in_smem) {
+        // packed lower triangle in shared memory; written out in the square form the eigensolver reads
+        double *L = sh;
+        for (int col = t.warp; col < p; col += t.nwarp) {
+            double *Lc = L + fokl::chol_col(col, p) - col;
+            const int64_t gcol = (int64_t)idx[col] * P.ldg;
+            for (int row = col + t.lane; row < p; row += t.nlane) Lc[row] = P.G[gcol + idx[row]];    // G is symmetric
+        }
+        t.sync();
+        ok = fokl::cholesky_lower_packed(t, L, p);
+        for (int col = t.warp; col < p; col += t.nwarp) {
+            const double *Lc = L + fokl::chol_col(col, p) - col;
+            for (int row = t.lane; row < p; row += t.nlane) Lg[(int64_t)col * p + row] = row >= col ? Lc[row] : 0.0;
+        }
+    } else {
+        for (int e = t.tid; e < p * p; e += t.nthr) {
+            int col = e / p, row = e - col * p;
+            Lg[e] = (row >= col) ? P.G[(int64_t)idx[row] * P.ldg + idx[col]] : 0.0;
+        }
+        t.sync();
+        ok = fokl::cholesky_lower(t, Lg, p);
     }
-    t.sync();
-    const bool ok = fokl::cholesky_lower(t, L, p);
-    if (in_smem)
-        for (int e = t.tid; e < p * p; e += t.nthr) Lg[e] = L[e];
     if (t.tid == 0) P.info[blockIdx.x] = ok ? 0 : 2;
 }
 
@@ -597,31 +611,54 @@ struct StatsParams {
     int D, from0, from1;
 };
 
-__global__ void cand_stats_kernel(const StatsParams P)
+// Column statistics of the draws (FR:1656-1658, 1671): per column the mean over rows from1.., the standard deviation
+// over rows from1.. (two-pass, like numpy) and the mean over rows from0...  A CTA takes 32 columns; its 16 row lanes
+// walk interleaved rows (coalesced 256-byte reads, 16 independent partial sums per column instead of one 1000-deep
+// dependent chain) and are summed in a fixed order.
+constexpr int kStatsRows = 16;
+
+__global__ void __launch_bounds__(32 * kStatsRows) cand_stats_kernel(const StatsParams P)
 {
+    __shared__ double red[2][kStatsRows][33];
     const int c = P.chain_list[blockIdx.y];
     const CandMeta m = P.meta[c];
     const int p = m.p;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= p) return;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int i = blockIdx.x * 32 + tx;
+    if (blockIdx.x * 32 >= p) return;
+    const bool on = i < p;
     const double *B = P.betas + (int64_t)P.D * m.vec_off;
     double s0 = 0.0, s1 = 0.0;
-    for (int k = P.from0; k < P.D; ++k) {
-        double v = B[(int64_t)k * p + i];
-        s0 += v;
-        if (k >= P.from1) s1 += v;
-    }
+    if (on)
+        for (int k = P.from0 + ty; k < P.D; k += kStatsRows) {
+            const double v = B[(int64_t)k * p + i];
+            s0 += v;
+            if (k >= P.from1) s1 += v;
+        }
+    red[0][ty][tx] = s0;
+    red[1][ty][tx] = s1;
+    __syncthreads();
+    s0 = 0.0; s1 = 0.0;
+    for (int r = 0; r < kStatsRows; ++r) { s0 += red[0][r][tx]; s1 += red[1][r][tx]; }
     const double n0 = (double)(P.D - P.from0), n1 = (double)(P.D - P.from1);
     const double m0 = s0 / n0, m1 = s1 / n1;
     double q = 0.0;
-    for (int k = P.from1; k < P.D; ++k) {
-        double d = B[(int64_t)k * p + i] - m1;
-        q += d * d;
+    if (on)
+        for (int k = P.from1 + ty; k < P.D; k += kStatsRows) {
+            const double d = B[(int64_t)k * p + i] - m1;
+            q += d * d;
+        }
+    __syncthreads();
+    red[0][ty][tx] = q;
+    __syncthreads();
+    if (ty == 0 && on) {
+        q = 0.0;
+        for (int r = 0; r < kStatsRows; ++r) q += red[0][r][tx];
+        double *S = P.stats + 3 * m.vec_off;
+        S[i] = m1;
+        S[p + i] = sqrt(q / n1);
+        S[2 * p + i] = m0;
     }
-    double *S = P.stats + 3 * m.vec_off;
-    S[i] = m1;
-    S[p + i] = sqrt(q / n1);
-    S[2 * p + i] = m0;
 }
 
 struct KillParams {
@@ -671,10 +708,11 @@ __global__ void __launch_bounds__(kKillThreads) kill_loop_kernel(const KillLoopP
     const Team t = make_team();
     int *shi = reinterpret_cast<int *>(sh);                       // 4 ints
     double *rowbuf = sh + 2;                                      // p + 1 doubles (+ 1 pad): copy of the pivot row
-    const int64_t need = (int64_t)(P.p + 1) * (P.p + 1);
-    double *T = (need <= P.smem_doubles) ? (sh + 2 + ((P.p + 2) & ~1)) : P.T_global;
+    // packed symmetric tableau in shared memory when it fits, else the full form in global memory (L2)
+    const bool packed = P.smem_doubles > 0;
+    double *T = packed ? (sh + 2 + ((P.p + 2) & ~1)) : P.T_global;
     fokl::kill_loop(t, P.G, P.ldg, P.Xty, P.cols, P.p, P.cand_pos, P.bv0, P.bv1, P.vm, P.c, P.in, T, P.out_i, P.out_ev,
-                    shi, rowbuf);
+                    shi, rowbuf, packed);
 }
 
 template <typename T>
@@ -888,9 +926,10 @@ extern "C" int fokl_candidates_eval(fokl_ctx *ctx, const double *G, int64_t ldg,
         CholParams C;
         C.G = G; C.ldg = ldg; C.col_sets = d_sets; C.meta = d_meta; C.Q = d_Q; C.info = info;
         int64_t need = 0;
-        for (int c = 0; c < n_cand; ++c)
-            if (!meta[c].pad && (int64_t)meta[c].p * meta[c].p * (int64_t)sizeof(double) <= (int64_t)smem_cap)
-                need = std::max<int64_t>(need, (int64_t)meta[c].p * meta[c].p);
+        for (int c = 0; c < n_cand; ++c) {
+            const int64_t tri = (int64_t)meta[c].p * (meta[c].p + 1) / 2;
+            if (!meta[c].pad && tri * (int64_t)sizeof(double) <= (int64_t)smem_cap) need = std::max<int64_t>(need, tri);
+        }
         C.smem_doubles = (int)need;
         FOKL_CUDA(ctx, cudaFuncSetAttribute(cand_chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
         cand_chol_kernel<<<n_cand, kCholThreads, (size_t)need * sizeof(double), ctx->stream>>>(C);
@@ -1012,8 +1051,8 @@ extern "C" int fokl_candidates_eval(fokl_ctx *ctx, const double *G, int64_t ldg,
         StatsParams P;
         P.meta = d_meta; P.chain_list = d_chain; P.betas = d_betas; P.stats = stats; P.D = D;
         P.from0 = hyp->stat_from0; P.from1 = hyp->stat_from1;
-        dim3 grid((unsigned)((pmax_chain + 127) / 128), (unsigned)n_chain);
-        cand_stats_kernel<<<grid, 128, 0, ctx->stream>>>(P);
+        dim3 grid((unsigned)((pmax_chain + 31) / 32), (unsigned)n_chain);
+        cand_stats_kernel<<<grid, dim3(32, kStatsRows), 0, ctx->stream>>>(P);
         FOKL_LAUNCH_CHECK(ctx);
     }
     return FOKL_OK;
@@ -1082,8 +1121,10 @@ extern "C" int fokl_kill_loop(fokl_ctx *ctx, const double *G, int64_t ldg, const
     const size_t smem_cap = ctx->smem_optin ? ctx->smem_optin : 48 * 1024;
     const int head = 2 + ((p + 2) & ~1);                         // flags + pivot-row copy
     const int smem_t_cap = (int)(smem_cap / sizeof(double)) - head;
-    const int64_t need = (int64_t)(p + 1) * (p + 1);
-    const bool in_smem = need <= smem_t_cap;
+    const int64_t need_packed = (int64_t)(p + 1) * (p + 2) / 2;            // symmetric tableau, lower triangle
+    const int64_t need_full = (int64_t)(p + 1) * (p + 1);
+    const bool in_smem = need_packed <= smem_t_cap;
+    const int64_t need = in_smem ? need_packed : need_full;
 
     // metadata: cols (p ints), cand_pos (vm ints), bv0, bv1 (vm doubles each)
     size_t off_pos = (size_t)p * sizeof(int32_t);

@@ -45,7 +45,7 @@ def lib():
     L.emu_candidate.restype = _i32
     L.emu_kill_scores.argtypes = [_vp, _i64, _vp, _vp, _i32, _vp, _i32, ctypes.POINTER(EmuHypers), _vp]
     L.emu_kill_scores.restype = _i32
-    L.emu_kill_loop.argtypes = [_vp, _i64, _vp, _vp, _i32, _vp, _vp, _vp, _i32, ctypes.POINTER(EmuHypers), _vp, _i32, _vp, _vp]
+    L.emu_kill_loop.argtypes = [_vp, _i64, _vp, _vp, _i32, _vp, _vp, _vp, _i32, ctypes.POINTER(EmuHypers), _vp, _i32, _i32, _vp, _vp]
     L.emu_kill_loop.restype = _i32
     L.emu_philox_normals.argtypes = [_u64, _u64, _i32, _i32, _vp]
     L.emu_philox_normals.restype = None
@@ -127,8 +127,9 @@ def kill_scores(G, Xty, idx, props, hyp):
 
 
 def kill_loop(G, Xty, idx, cand_pos, bv0, bv1, hyp, threshav=0.05, threshstda=0.5, threshstdb=2.0, icpt=1.0,
-              evmin=0.0, aic_adj=0.0, start=0):
-    """Returns dict(n_acc, tested, bad, acc (candidate indices), calls (tested count at each acceptance), ev)."""
+              evmin=0.0, aic_adj=0.0, start=0, packed=True):
+    """Returns dict(n_acc, tested, bad, acc (candidate indices), calls (tested count at each acceptance), ev).
+    packed: symmetric tableau stored as its lower triangle (the shared-memory form) or in full (the global-memory form)."""
     G = np.ascontiguousarray(G, dtype=np.float64)
     Xty = np.ascontiguousarray(np.asarray(Xty).reshape(-1), dtype=np.float64)
     idx = np.ascontiguousarray(idx, dtype=np.int32)
@@ -144,7 +145,7 @@ def kill_loop(G, Xty, idx, cand_pos, bv0, bv1, hyp, threshav=0.05, threshstda=0.
     out_ev = np.zeros(max(vm, 1))
     bad = lib().emu_kill_loop(G.ctypes.data, G.shape[1], Xty.ctypes.data, idx.ctypes.data, len(idx), cand_pos.ctypes.data,
                               bv0.ctypes.data, bv1.ctypes.data, vm, ctypes.byref(h), params.ctypes.data, start,
-                              out_i.ctypes.data, out_ev.ctypes.data)
+                              int(bool(packed)), out_i.ctypes.data, out_ev.ctypes.data)
     k = int(out_i[0])
     return dict(n_acc=k, tested=int(out_i[1]), bad=int(bad), acc=out_i[3:3 + k].copy(),
                 calls=out_i[3 + vm:3 + vm + k].copy(), ev=out_ev[:k].copy())

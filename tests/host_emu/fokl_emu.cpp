@@ -139,7 +139,7 @@ int emu_kill_scores(const double *G, int64_t ldg, const double *Xty, const int32
 // kill_loop on the host: params = {threshav, threshstda, threshstdb, icpt, evmin, aic_adj}; returns the error flag
 int emu_kill_loop(const double *G, int64_t ldg, const double *Xty, const int32_t *idx, int p, const int32_t *cand_pos,
                   const double *bv0, const double *bv1, int vm, const emu_hypers *h, const double *params, int start,
-                  int32_t *out_i, double *out_ev)
+                  int packed, int32_t *out_i, double *out_ev)
 {
     Team t;
     t.tid = 0; t.nthr = 1; t.lane = 0; t.nlane = 1; t.warp = 0; t.nwarp = 1;
@@ -152,7 +152,7 @@ int emu_kill_loop(const double *G, int64_t ldg, const double *Xty, const int32_t
     in.threshav = params[0]; in.threshstda = params[1]; in.threshstdb = params[2]; in.icpt = params[3];
     in.evmin = params[4]; in.aic_adj = params[5]; in.start = start;
     std::vector<double> rowbuf(p + 1);
-    return kill_loop(t, G, ldg, Xty, idx, p, cand_pos, bv0, bv1, vm, c, in, T.data(), out_i, out_ev, sh, rowbuf.data());
+    return kill_loop(t, G, ldg, Xty, idx, p, cand_pos, bv0, bv1, vm, c, in, T.data(), out_i, out_ev, sh, rowbuf.data(), packed != 0);
 }
 
 void emu_philox_normals(uint64_t seed, uint64_t stream, int draws, int p, double *out)

@@ -139,8 +139,9 @@ def _literal_kill_loop(X, y, idx, cand_cols, bv0, bv1, thr, evmin, aic_adj, thre
     return acc, calls, evs, tested
 
 
+@pytest.mark.parametrize('packed', [True, False])
 @pytest.mark.parametrize('aic', [False, True])
-def test_kill_loop_matches_sequential_oracle_loop(phis_cubic, aic):
+def test_kill_loop_matches_sequential_oracle_loop(phis_cubic, aic, packed):
     rng = np.random.default_rng(11)
     n, m = 4000, 3
     x = rng.random((n, m))
@@ -162,7 +163,7 @@ def test_kill_loop_matches_sequential_oracle_loop(phis_cubic, aic):
     icpt, threshav = 2.0, 0.3
     acc, calls, evs, tested = _literal_kill_loop(X, y, idx, cand_cols, bv0, bv1, threshav * icpt, full, aic_adj)
     r = emu.kill_loop(G, Xty, idx, [idx.index(c) for c in cand_cols], bv0, bv1, hyp, threshav=threshav, icpt=icpt,
-                      evmin=full, aic_adj=aic_adj)
+                      evmin=full, aic_adj=aic_adj, packed=packed)
     assert r['bad'] == 0 and len(acc) > 0
     assert list(r['acc']) == acc and list(r['calls']) == calls and r['tested'] == tested
     assert np.allclose(r['ev'], evs, rtol=1e-11, atol=0)
@@ -173,11 +174,12 @@ def test_kill_loop_matches_sequential_oracle_loop(phis_cubic, aic):
         idx2 = [c for c in idx if c not in killed]
         pos2 = [idx2.index(c) if c in idx2 else -1 for c in cand_cols]
         r2 = emu.kill_loop(G, Xty, idx2, pos2, bv0, bv1, hyp, threshav=threshav, icpt=icpt, evmin=evs[k - 1],
-                           aic_adj=aic_adj, start=acc[k - 1] + 1)
+                           aic_adj=aic_adj, start=acc[k - 1] + 1, packed=packed)
         assert list(r2['acc']) == acc[k:] and np.allclose(r2['ev'], evs[k:], rtol=1e-11)
     # a duplicated column is reported, not scored
     G2 = G.copy(); G2[:, 2] = G2[:, 1]; G2[2, :] = G2[1, :]
-    assert emu.kill_loop(G2, Xty, idx, [idx.index(c) for c in cand_cols], bv0, bv1, hyp, evmin=full)['bad'] == 1
+    assert emu.kill_loop(G2, Xty, idx, [idx.index(c) for c in cand_cols], bv0, bv1, hyp, evmin=full,
+                         packed=packed)['bad'] == 1
 
 
 @pytest.mark.parametrize('warps,kchunks,mode', [(16, 1, 1), (15, 4, 1), (15, 16, 1), (15, 8, 0), (16, 16, 0), (8, 8, 1)])

@@ -843,7 +843,159 @@ class FoKL:
                           "reference package on the saved model (same pickle layout).")
 
     def bss_derivatives(self, **kwargs):
-        raise NotImplementedError("bss_derivatives (reference FR:594-805) is outside the B200 hot path")
+        """Gradient (or chosen first / second partial derivatives) of the fitted function with respect to the inputs
+        (FR:594-805).  Keywords as upstream: inputs, kernel, d1, d2, draws, betas, phis, mtx, minmax, IndividualDraws,
+        ReturnFullArray, ReturnBasis.  The derivative design matrices come from the derivative form of the basis
+        kernel (fokl_basis_build_deriv) and the products with the draws from fokl_predict_draws, both on the device."""
+        default = {'inputs': None, 'kernel': self.kernel, 'd1': None, 'd2': None, 'draws': self.draws, 'betas': None,
+                   'phis': None, 'mtx': self.mtx, 'minmax': self.minmax, 'IndividualDraws': False,
+                   'ReturnFullArray': False, 'ReturnBasis': False}
+        current = _process_kwargs(default, kwargs)
+        for boolean in ['IndividualDraws', 'ReturnFullArray', 'ReturnBasis']:
+            current[boolean] = _str_to_bool(current[boolean])
+        inputs = self.inputs if current['inputs'] is None else current['inputs']
+        betas = self.betas if current['betas'] is None else current['betas']
+        phis = self.phis if current['phis'] is None else current['phis']
+        kernel, draws, span = current['kernel'], current['draws'], current['minmax']
+        if isinstance(kernel, int):
+            kernel = self.kernels[kernel]
+
+        inputs = np.array(inputs)
+        if inputs.ndim == 1:
+            inputs = inputs[:, np.newaxis]
+        if isinstance(betas, list):
+            betas = np.array(betas)
+            if betas.ndim == 1:
+                betas = betas[:, np.newaxis]
+        mtx = current['mtx']
+        if isinstance(mtx, int):
+            mtx = np.array(mtx)[np.newaxis, np.newaxis]
+        else:
+            mtx = np.array(mtx)
+            if mtx.ndim == 1:
+                mtx = mtx[:, np.newaxis]
+        if len(span) == 2 and not isinstance(span[0], (list, np.ndarray)):
+            span = [span]
+        if np.max(np.max(inputs)) > 1 or np.min(np.min(inputs)) < 0:
+            warnings.warn("Input 'inputs' should be normalized (0-1). Auto-normalization is in-development.",
+                          category=UserWarning)
+        N = np.shape(inputs)[0]
+        B, M = np.shape(mtx)
+        betas = np.asarray(betas, dtype=np.float64)
+        if B != np.shape(betas)[1] - 1:
+            betas = np.transpose(betas)
+            if B != np.shape(betas)[1] - 1:
+                raise ValueError(
+                    "The shape of 'betas' does not align with the shape of 'mtx'. Transposing did not fix this.")
+
+        def as_mask(di, second):
+            """d1 / d2 keyword -> boolean row over the inputs (FR:686-725)."""
+            if di is None:
+                return np.zeros(M, dtype=bool) if second else np.ones(M, dtype=bool)
+            if isinstance(di, str):
+                return np.ones(M, dtype=bool) if _str_to_bool(di) else np.zeros(M, dtype=bool)
+            if isinstance(di, list):
+                if len(di) == 1:
+                    di = di[0]
+                elif len(di) == M:
+                    return np.array(di) != 0
+                else:
+                    raise ValueError("Keyword input 'd1' and/or 'd2', if entered as a list, must be of equal length to "
+                                     "the number of input variables.")
+            if isinstance(di, bool):
+                return np.ones(M, dtype=bool) * di
+            if isinstance(di, int):
+                row = np.zeros(M, dtype=bool)
+                row[di] = True
+                return row
+            raise ValueError(
+                "Keyword input 'd1' and/or 'd2' is limited to an integer indexing an input variable, or to a list "
+                "of booleans corresponding to the input variables.")
+
+        derv = [as_mask(current['d1'], False), as_mask(current['d2'], True)]
+        if not any(derv[0]) and not any(derv[1]):
+            warnings.warn("Function 'bss_derivatives' was called but no derivatives were requested.",
+                          category=UserWarning)
+            return
+
+        cubic = kernel == self.kernels[0]
+        if not cubic and kernel != self.kernels[1]:
+            raise ValueError(f"The kernel {kernel} is not currently supported. Please select from the following: "
+                             f"{self.kernels}.")
+        L_phis = len(phis[0][0]) if cubic else 1
+        divisors = np.ones((M, 3))
+        for m in range(M):
+            span_L = (span[m][1] - span[m][0]) / L_phis
+            divisors[m] = [1, span_L, span_L ** 2]
+
+        # one launch of the derivative basis kernel for every requested (input, derivative order) pair: the terms that
+        # contain the input, with that input's factor differentiated (the other terms contribute exactly 0, FR:785-787)
+        terms_i = np.asarray(mtx, dtype=np.int64)
+        pairs, t_rows, d_rows = [], [], []
+        for m in range(M):
+            for di in (0, 1):
+                if not derv[di][m]:
+                    continue
+                idx = np.nonzero(terms_i[:, m] != 0)[0]
+                pairs.append((m, di, idx, sum(len(r) for r in t_rows) if t_rows else 0))
+                if len(idx):
+                    t_rows.append(terms_i[idx])
+                    dr = np.zeros((len(idx), M), dtype=np.uint8)
+                    dr[:, m] = di + 1
+                    d_rows.append(dr)
+        dy = np.zeros([N, M, 2, draws])
+        bsel = np.ascontiguousarray(betas[-draws:, :], dtype=np.float64)
+        if t_rows:
+            import torch
+            eng = _engine()
+            eng.set_phis(phis, kernel)
+            x64 = np.ascontiguousarray(inputs, dtype=np.float64)
+            ds = eng.upload(x64, np.zeros(N))
+            t16 = np.ascontiguousarray(np.concatenate(t_rows, axis=0), dtype=np.int16)
+            d8 = np.ascontiguousarray(np.concatenate(d_rows, axis=0), dtype=np.uint8)
+            dv = np.ascontiguousarray(divisors, dtype=np.float64)
+            X = torch.empty((t16.shape[0], ds.ldx), dtype=torch.float64, device=eng.device)
+            eng._ck(eng.lib.fokl_basis_build_deriv(eng.ctx, eng.kernel_id, ds.x.data_ptr(), N, ds.ldx, M,
+                                                   t16.ctypes.data, d8.ctypes.data, dv.ctypes.data, t16.shape[0],
+                                                   X.data_ptr(), ds.ldx))
+            eng.synchronize()       # surfaces the out-of-range flag (inputs outside [0, 1]) as ValueError
+            for m, di, idx, off in pairs:
+                if not len(idx):
+                    continue
+                b = torch.from_numpy(np.ascontiguousarray(bsel[:, idx + 1])).to(eng.device)
+                out = torch.empty((N, draws), dtype=torch.float64, device=eng.device)
+                eng._ck(eng.lib.fokl_predict_draws(eng.ctx, X[off].data_ptr(), ds.ldx, N, len(idx), b.data_ptr(), draws,
+                                                   out.data_ptr()))
+                dy[:, m, di, :] = out.cpu().numpy()
+
+        if not current['IndividualDraws'] and draws > 1:
+            dy = np.mean(dy, axis=3)[:, :, :, np.newaxis]
+        if not current['ReturnFullArray']:
+            dy = np.concatenate([dy[:, :, 0, :], dy[:, :, 1, :]], axis=1)
+            dy = dy[:, ~np.all(dy == 0, axis=0)]
+        dy = np.squeeze(dy)
+
+        if current['ReturnBasis']:
+            # development option of the reference (FR:782-783): the plain basis value of the last factor its loops visit
+            basis = np.zeros(N)
+            m_last, di_last = max((m, di) for m, di, _, _ in pairs)
+            if cubic:
+                Xe, phind, _ = self._inputs_to_phind(np.asarray(inputs, dtype=np.float64), phis, kernel)
+            else:
+                Xe, phind = np.asarray(inputs, dtype=np.float64), None
+            for b_ in range(B - 1, -1, -1):
+                row = terms_i[b_]
+                upto = M if row[m_last] else m_last        # the md loop stops at the differentiated input if absent
+                visited = [md for md in range(upto) if row[md]]
+                if visited:
+                    md = visited[-1]
+                    num = int(row[md]) - 1
+                    for n_ in range(N):
+                        c = [phis[num][k][int(phind[n_, md])] for k in range(4)] if cubic else phis[num]
+                        basis[n_] = self.evaluate_basis(c, Xe[n_, md], kernel=kernel)
+                    break
+            return dy, basis
+        return dy
 
     def fitupdate(self, inputs, data):
         raise NotImplementedError("fitupdate (reference FR:1850-2583) is outside the B200 hot path")

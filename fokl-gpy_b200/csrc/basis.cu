@@ -32,12 +32,13 @@ constexpr int kThreads = 256;
 constexpr int kMaxTermFactors = 7;     // interacting inputs per term (fit uses <= 3)
 constexpr int kMaxFactors = 96;        // distinct (input, order) pairs per launch
 constexpr int kMaxTermsPerLaunch = 2040;  // term metadata travels in the kernel parameter space (8 B each)
+constexpr int kMaxPrefetchInputs = 8;  // distinct inputs of a launch whose rows phase 1 requests up front
 
 struct FactorMeta {          // one distinct (input, order) pair
     int16_t k;               // input column
     int16_t d;               // order (1-based, phis[d-1])
     int16_t slot;            // staged-table slot of this order (cubic), -1 = read global table
-    int16_t pad;
+    int16_t pad;             // direct path: the term index; derivative launches: derivative order e of this factor
 };
 
 struct alignas(8) TermMeta {  // one output column, read by the kernel as one packed 64-bit word:
@@ -60,6 +61,10 @@ struct BasisParams {
     int tab_stride;              // cubic: doubles between the coefficient planes of a staged slot
     int direct;                  // every term is one factor (main effects): phase 1 stores straight to its column
                                  // (FactorMeta.pad = the term index), no factor buffer, no barrier, no phase 2
+    const double *fac_div;       // derivative launches: per factor, the divisor span_L**e of FR:762-763 (1 for e = 0)
+    int n_in;                    // distinct inputs in use if <= kMaxPrefetchInputs (phase 1 prefetch form), else 0
+    int16_t in_k[kMaxPrefetchInputs];    // their input indices, ascending
+    int16_t in_end[kMaxPrefetchInputs];  // one past the last factor (sorted by input) of each
     unsigned long long terms[kMaxTermsPerLaunch];   // TermMeta words
 };
 static_assert(sizeof(BasisParams) <= 32000, "kernel parameter space");
@@ -87,7 +92,13 @@ __device__ __forceinline__ double eval_factor_bernoulli(const double *c, int n_c
     return __dadd_rn(c[0], s);
 }
 
-template <int KERNEL, int RPT, int NF>
+// DERIV = true is the bss_derivatives form (FR:594-805): factors are evaluated at the twice-normalised input of
+// FR:584-586 instead of xsm, and a factor with FactorMeta.pad = e > 0 is the e-th derivative of its basis function
+// divided by fac_div (FR:780-781).  The fit path only ever instantiates DERIV = false.
+// PF = true is the phase-1 form that requests the rows of every input in use up front (more registers: used for
+// launches whose shared-memory footprint allows at most 3 CTAs per SM anyway, where the exposed load latency of the
+// input-by-input form is not covered by other CTAs; measured in profiles/r01_k1_prefetch.txt).
+template <int KERNEL, int RPT, int NF, bool DERIV = false, bool PF = false>
 __global__ void __launch_bounds__(kThreads) basis_kernel(const __grid_constant__ BasisParams P)
 {
     constexpr int ROWS = kThreads * RPT;
@@ -131,34 +142,25 @@ __global__ void __launch_bounds__(kThreads) basis_kernel(const __grid_constant__
         const int64_t row0 = tile * ROWS + (int64_t)tid * RPT;
         // ---- phase 1: factor values -------------------------------------------------------------
         {
-            double xv[RPT], xs[RPT], x2[RPT], x3[RPT];
-            int ph[RPT];
-            int cur_k = -1;
-            for (int f = 0; f < P.n_factors; ++f) {
-                const FactorMeta fm = s_fac[f];
-                if (fm.k != cur_k) {
-                    cur_k = fm.k;
-                    const double *xc = P.x + (int64_t)cur_k * P.ldx;
-                    if (RPT == 2 && row0 + 1 < P.n) {
-                        double2 t = *reinterpret_cast<const double2 *>(xc + row0);
-                        xv[0] = t.x;
-                        xv[RPT - 1] = t.y;
-                    } else {
-#pragma unroll
-                        for (int r = 0; r < RPT; ++r) xv[r] = (row0 + r < P.n) ? xc[row0 + r] : 0.5;
-                    }
-                    if (KERNEL == FOKL_KERNEL_CUBIC) {
-#pragma unroll
-                        for (int r = 0; r < RPT; ++r) {
-                            bool ok = fokl::phind_xsm(xv[r], P.n_piece, ph[r], xs[r]);
-                            if (ph[r] > P.n_piece - 1) { ok = false; ph[r] = P.n_piece - 1; }
-                            if (!ok && row0 + r < P.n) atomicOr(P.flag, 1);
-                            fokl::square_cube(xs[r], x2[r], x3[r]);
-                        }
-                    }
-                }
+            // one factor's values for this thread's rows, to the factor buffer (or straight to its column)
+            auto eval_store = [&](int f, const FactorMeta fm, const double (&xv)[RPT], const int (&ph)[RPT],
+                                  const double (&xs)[RPT], const double (&x2)[RPT], const double (&x3)[RPT]) {
                 double v[RPT];
-                if (KERNEL == FOKL_KERNEL_CUBIC) {
+                if (DERIV && fm.pad > 0) {
+                    const double dv = __ldg(P.fac_div + f);
+#pragma unroll
+                    for (int r = 0; r < RPT; ++r) {
+                        double t;
+                        if (KERNEL == FOKL_KERNEL_CUBIC) {
+                            const double *cp = P.tab + ((size_t)(fm.d - 1) * P.n_piece + ph[r]) * 4;
+                            t = fm.pad == 1 ? fokl::cubic_basis_d1(__ldg(cp + 1), __ldg(cp + 2), __ldg(cp + 3), xs[r], x2[r])
+                                            : fokl::cubic_basis_d2(__ldg(cp + 2), __ldg(cp + 3), xs[r]);
+                        } else {
+                            t = fokl::bernoulli_basis_deriv(P.tab + (size_t)(fm.d - 1) * P.n_piece, fm.d + 1, xv[r], fm.pad);
+                        }
+                        v[r] = __ddiv_rn(t, dv);
+                    }
+                } else if (KERNEL == FOKL_KERNEL_CUBIC) {
 #pragma unroll
                     for (int r = 0; r < RPT; ++r) {
                         if (fm.slot >= 0) {
@@ -190,6 +192,62 @@ __global__ void __launch_bounds__(kThreads) basis_kernel(const __grid_constant__
                     *reinterpret_cast<double2 *>(s_F + (size_t)f * ROWS + tid * 2) = make_double2(v[0], v[RPT - 1]);
                 } else {
                     s_F[(size_t)f * ROWS + tid] = v[0];
+                }
+            };
+            auto load_rows = [&](int k, double (&xv)[RPT]) {
+                const double *xc = P.x + (int64_t)k * P.ldx;
+                if (RPT == 2 && row0 + 1 < P.n) {
+                    double2 t = *reinterpret_cast<const double2 *>(xc + row0);
+                    xv[0] = t.x;
+                    xv[RPT - 1] = t.y;
+                } else {
+#pragma unroll
+                    for (int r = 0; r < RPT; ++r) xv[r] = (row0 + r < P.n) ? xc[row0 + r] : 0.5;
+                }
+            };
+            auto locate = [&](const double (&xv)[RPT], int (&ph)[RPT], double (&xs)[RPT], double (&x2)[RPT],
+                              double (&x3)[RPT]) {
+                if (KERNEL == FOKL_KERNEL_CUBIC) {
+#pragma unroll
+                    for (int r = 0; r < RPT; ++r) {
+                        bool ok = fokl::phind_xsm(xv[r], P.n_piece, ph[r], xs[r]);
+                        if (ph[r] > P.n_piece - 1) { ok = false; ph[r] = P.n_piece - 1; }
+                        if (!ok && row0 + r < P.n) atomicOr(P.flag, 1);
+                        if (DERIV) xs[r] = fokl::twice_normalised(xv[r], P.n_piece, ph[r]);
+                        fokl::square_cube(xs[r], x2[r], x3[r]);
+                    }
+                }
+            };
+            if (PF) {
+                // the rows of every input in use are requested back to back (one exposed HBM latency per tile instead
+                // of one per input), then the factors are evaluated input by input (they are sorted by input)
+                double xin[kMaxPrefetchInputs][RPT];
+#pragma unroll
+                for (int i = 0; i < kMaxPrefetchInputs; ++i)
+                    if (i < P.n_in) load_rows(P.in_k[i], xin[i]);
+                int f = 0;
+#pragma unroll
+                for (int i = 0; i < kMaxPrefetchInputs; ++i) {
+                    if (i < P.n_in) {
+                        double xs[RPT], x2[RPT], x3[RPT];
+                        int ph[RPT];
+                        locate(xin[i], ph, xs, x2, x3);
+                        const int f_end = P.in_end[i];
+                        for (; f < f_end; ++f) eval_store(f, s_fac[f], xin[i], ph, xs, x2, x3);
+                    }
+                }
+            } else {
+                double xv[RPT], xs[RPT], x2[RPT], x3[RPT];
+                int ph[RPT];
+                int cur_k = -1;
+                for (int f = 0; f < P.n_factors; ++f) {
+                    const FactorMeta fm = s_fac[f];
+                    if (fm.k != cur_k) {
+                        cur_k = fm.k;
+                        load_rows(cur_k, xv);
+                        locate(xv, ph, xs, x2, x3);
+                    }
+                    eval_store(f, fm, xv, ph, xs, x2, x3);
                 }
             }
         }
@@ -289,8 +347,10 @@ struct LaunchPlan {
 
 }  // namespace
 
-extern "C" int fokl_basis_build(fokl_ctx *ctx, int kernel, const double *x, int64_t n, int64_t ldx, int m,
-                                const int16_t *terms, int c, double *Xnew, int64_t ld)
+// deriv (C x M, values 0 / 1 / 2) and divisors (M x 3, host) are null for the fit path
+static int basis_build_impl(fokl_ctx *ctx, int kernel, const double *x, int64_t n, int64_t ldx, int m,
+                            const int16_t *terms, const uint8_t *deriv, const double *divisors, int c, double *Xnew,
+                            int64_t ld)
 {
     FOKL_CHECK_CTX(ctx);
     if (!x || !terms || !Xnew || n < 0 || m < 1 || c < 0 || ldx < n || ld < n)
@@ -309,7 +369,7 @@ extern "C" int fokl_basis_build(fokl_ctx *ctx, int kernel, const double *x, int6
     std::vector<LaunchPlan> plans;
     {
         LaunchPlan cur;
-        std::vector<int> fac_index((size_t)m * (n_orders + 1), -1);
+        std::vector<int> fac_index((size_t)m * (n_orders + 1) * 3, -1);
         auto flush = [&]() {
             if (!cur.terms.empty()) plans.push_back(cur);
             int next = cur.first_term + (int)cur.terms.size();
@@ -327,7 +387,9 @@ extern "C" int fokl_basis_build(fokl_ctx *ctx, int kernel, const double *x, int6
                 if (kernel == FOKL_KERNEL_BERNOULLI && d + 1 > row_len)
                     FOKL_FAIL(ctx, FOKL_EINVAL, "basis_build: bernoulli row too short for order");
                 ++cnt;
-                if (fac_index[(size_t)k * (n_orders + 1) + d] < 0) ++need_new;
+                const int e = deriv ? deriv[(size_t)j * m + k] : 0;
+                if (e < 0 || e > 2) FOKL_FAIL(ctx, FOKL_EINVAL, "basis_build: derivative order must be 0, 1 or 2");
+                if (fac_index[((size_t)k * (n_orders + 1) + d) * 3 + e] < 0) ++need_new;
             }
             if (cnt > kMaxTermFactors) FOKL_FAIL(ctx, FOKL_EINVAL, "basis_build: more than 7 interacting inputs in a term");
             if ((int)cur.factors.size() + need_new > kMaxFactors || (int)cur.terms.size() >= kMaxTermsPerLaunch) flush();
@@ -337,11 +399,12 @@ extern "C" int fokl_basis_build(fokl_ctx *ctx, int kernel, const double *x, int6
             for (int k = 0; k < m; ++k) {
                 int d = row[k];
                 if (d == 0) continue;
-                int &fi = fac_index[(size_t)k * (n_orders + 1) + d];
+                const int e = deriv ? deriv[(size_t)j * m + k] : 0;
+                int &fi = fac_index[((size_t)k * (n_orders + 1) + d) * 3 + e];
                 if (fi < 0) {
                     fi = (int)cur.factors.size();
                     FactorMeta fm;
-                    fm.k = (int16_t)k; fm.d = (int16_t)d; fm.slot = -1; fm.pad = 0;
+                    fm.k = (int16_t)k; fm.d = (int16_t)d; fm.slot = -1; fm.pad = (int16_t)e;
                     cur.factors.push_back(fm);
                 }
                 tm.f[filled++] = (uint8_t)fi;
@@ -362,7 +425,8 @@ extern "C" int fokl_basis_build(fokl_ctx *ctx, int kernel, const double *x, int6
         for (int i = 0; i < nf; ++i) order[i] = i;
         std::sort(order.begin(), order.end(), [&](int a, int b) {
             if (pl.factors[a].k != pl.factors[b].k) return pl.factors[a].k < pl.factors[b].k;
-            return pl.factors[a].d < pl.factors[b].d;
+            if (pl.factors[a].d != pl.factors[b].d) return pl.factors[a].d < pl.factors[b].d;
+            return pl.factors[a].pad < pl.factors[b].pad;
         });
         std::vector<FactorMeta> sorted(nf);
         for (int i = 0; i < nf; ++i) { sorted[i] = pl.factors[order[i]]; inv[order[i]] = i; }
@@ -384,7 +448,7 @@ extern "C" int fokl_basis_build(fokl_ctx *ctx, int kernel, const double *x, int6
         const size_t per_slot = (kernel == FOKL_KERNEL_CUBIC ? (size_t)tab_stride * 4 : (size_t)row_len) * sizeof(double);
         const int nt = (int)pl.terms.size();
         // main-effect substages: every term is exactly one factor and no factor is shared -> direct stores
-        bool direct = pl.max_cnt == 1 && nt == nf;
+        bool direct = pl.max_cnt == 1 && nt == nf && !deriv;
         if (direct) {
             std::vector<int> seen(nf, 0);
             for (const TermMeta &tm : pl.terms) {
@@ -398,7 +462,7 @@ extern "C" int fokl_basis_build(fokl_ctx *ctx, int kernel, const double *x, int6
             return tab_bytes + (direct ? (size_t)0 : (size_t)(nf + 1) * kThreads * rpt * sizeof(double)) +
                    (size_t)nf * sizeof(FactorMeta) + 16;
         };
-        int rpt = aligned2 ? 2 : 1;
+        int rpt = (aligned2 && !deriv) ? 2 : 1;
         int nslots = (int)orders.size();
         // prefer two resident CTAs per SM; otherwise shrink rows per thread, then staged slots
         if (rpt == 2 && smem_need(2, nslots) > smem_cap / 2) rpt = 1;
@@ -412,9 +476,14 @@ extern "C" int fokl_basis_build(fokl_ctx *ctx, int kernel, const double *x, int6
         // upload metadata
         size_t off_fac = 0;
         size_t off_slot = (off_fac + (size_t)nf * sizeof(FactorMeta) + 15) & ~(size_t)15;
-        size_t meta_bytes = off_slot + (size_t)(nslots + 1) * sizeof(int16_t);
+        size_t off_div = (off_slot + (size_t)(nslots + 1) * sizeof(int16_t) + 15) & ~(size_t)15;
+        size_t meta_bytes = off_div + (deriv ? (size_t)nf * sizeof(double) : 0);
         std::vector<unsigned char> host(meta_bytes, 0);
         memcpy(host.data() + off_fac, sorted.data(), (size_t)nf * sizeof(FactorMeta));
+        if (deriv) {
+            double *dv = reinterpret_cast<double *>(host.data() + off_div);
+            for (int i = 0; i < nf; ++i) dv[i] = sorted[i].pad > 0 ? divisors[(size_t)sorted[i].k * 3 + sorted[i].pad] : 1.0;
+        }
         if (nslots) memcpy(host.data() + off_slot, orders.data(), (size_t)nslots * sizeof(int16_t));
         // the copy is stream-ordered behind any kernel still reading the previous metadata
         unsigned char *dmeta = (unsigned char *)fokl_scratch(ctx, fokl_ctx::B_BASIS, meta_bytes);
@@ -429,6 +498,20 @@ extern "C" int fokl_basis_build(fokl_ctx *ctx, int kernel, const double *x, int6
         P.factors = reinterpret_cast<const FactorMeta *>(dmeta + off_fac);
         P.tab_stride = tab_stride;
         P.direct = direct ? 1 : 0;
+        P.fac_div = deriv ? reinterpret_cast<const double *>(dmeta + off_div) : nullptr;
+        {
+            int n_in = 0;
+            bool fits = true;
+            for (int i = 0; i < nf && fits; ++i) {
+                if (n_in == 0 || sorted[i].k != P.in_k[n_in - 1]) {
+                    if (n_in == kMaxPrefetchInputs) { fits = false; break; }
+                    P.in_k[n_in++] = sorted[i].k;
+                }
+                P.in_end[n_in - 1] = (int16_t)(i + 1);
+            }
+            for (int i = fits ? n_in : 0; i < kMaxPrefetchInputs; ++i) { P.in_k[i] = 0; P.in_end[i] = 0; }
+            P.n_in = fits ? n_in : 0;
+        }
         memcpy(P.terms, pl.terms.data(), (size_t)nt * sizeof(TermMeta));
         P.slot_order = reinterpret_cast<const int16_t *>(dmeta + off_slot);
         P.flag = ctx->d_flag;
@@ -438,16 +521,45 @@ extern "C" int fokl_basis_build(fokl_ctx *ctx, int kernel, const double *x, int6
         const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, smem_cap / std::max<size_t>(smem, 1)));
         int grid = (int)std::min<int64_t>(P.n_tiles, (int64_t)ctx->num_sms * ctas_per_sm);
         void (*kern)(const BasisParams) = nullptr;
+        const bool pf = P.n_in > 0 && !deriv && !getenv("FOKL_BASIS_NOPF") &&
+                        (direct ? getenv("FOKL_BASIS_PF_DIRECT") != nullptr : smem_cap / std::max<size_t>(smem, 1) <= 3);
         static_assert(sizeof(TermMeta) == sizeof(unsigned long long), "TermMeta is one 64-bit word");
         const int nfc = pl.max_cnt <= 1 ? 1 : (pl.max_cnt == 2 ? 2 : (pl.max_cnt == 3 ? 3 : 7));
-#define FOKL_PICK(K, R)                                                                                               \
-    (nfc == 1 ? basis_kernel<K, R, 1> : nfc == 2 ? basis_kernel<K, R, 2> : nfc == 3 ? basis_kernel<K, R, 3> : basis_kernel<K, R, 7>)
-        if (kernel == FOKL_KERNEL_CUBIC) kern = rpt == 2 ? FOKL_PICK(FOKL_KERNEL_CUBIC, 2) : FOKL_PICK(FOKL_KERNEL_CUBIC, 1);
-        else kern = rpt == 2 ? FOKL_PICK(FOKL_KERNEL_BERNOULLI, 2) : FOKL_PICK(FOKL_KERNEL_BERNOULLI, 1);
+#define FOKL_PICK(K, R, F)                                                                                            \
+    (nfc == 1 ? basis_kernel<K, R, 1, false, F> : nfc == 2 ? basis_kernel<K, R, 2, false, F>                          \
+                                                : nfc == 3 ? basis_kernel<K, R, 3, false, F> : basis_kernel<K, R, 7, false, F>)
+        if (kernel == FOKL_KERNEL_CUBIC) {
+            if (pf) kern = rpt == 2 ? FOKL_PICK(FOKL_KERNEL_CUBIC, 2, true) : FOKL_PICK(FOKL_KERNEL_CUBIC, 1, true);
+            else kern = rpt == 2 ? FOKL_PICK(FOKL_KERNEL_CUBIC, 2, false) : FOKL_PICK(FOKL_KERNEL_CUBIC, 1, false);
+        } else {
+            if (pf) kern = rpt == 2 ? FOKL_PICK(FOKL_KERNEL_BERNOULLI, 2, true) : FOKL_PICK(FOKL_KERNEL_BERNOULLI, 1, true);
+            else kern = rpt == 2 ? FOKL_PICK(FOKL_KERNEL_BERNOULLI, 2, false) : FOKL_PICK(FOKL_KERNEL_BERNOULLI, 1, false);
+        }
 #undef FOKL_PICK
+        if (deriv)
+            kern = kernel == FOKL_KERNEL_CUBIC ? basis_kernel<FOKL_KERNEL_CUBIC, 1, 7, true>
+                                               : basis_kernel<FOKL_KERNEL_BERNOULLI, 1, 7, true>;
         FOKL_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
         kern<<<grid, kThreads, smem, ctx->stream>>>(P);
         FOKL_LAUNCH_CHECK(ctx);
     }
     return FOKL_OK;
+}
+
+extern "C" int fokl_basis_build(fokl_ctx *ctx, int kernel, const double *x, int64_t n, int64_t ldx, int m,
+                                const int16_t *terms, int c, double *Xnew, int64_t ld)
+{
+    return basis_build_impl(ctx, kernel, x, n, ldx, m, terms, nullptr, nullptr, c, Xnew, ld);
+}
+
+// bss_derivatives form of K1 (FR:594-805): column j = prod_k f_jk with f_jk the basis function of order terms[j][k]
+// (deriv[j][k] = 0) or its first / second derivative divided by divisors[k][deriv[j][k]] (FR:780-781), every factor
+// evaluated at the twice-normalised input of FR:584-586.  deriv and divisors are host arrays.
+extern "C" int fokl_basis_build_deriv(fokl_ctx *ctx, int kernel, const double *x, int64_t n, int64_t ldx, int m,
+                                      const int16_t *terms, const uint8_t *deriv, const double *divisors, int c,
+                                      double *Xnew, int64_t ld)
+{
+    FOKL_CHECK_CTX(ctx);
+    if (!deriv || !divisors) FOKL_FAIL(ctx, FOKL_EINVAL, "basis_build_deriv: bad argument");
+    return basis_build_impl(ctx, kernel, x, n, ldx, m, terms, deriv, divisors, c, Xnew, ld);
 }

@@ -85,6 +85,61 @@ FOKL_HD double bernoulli_basis(const double *c, int n_coef, const double *pw)
     return FOKL_ADD(c[0], s);
 }
 
+// ---- bss_derivatives (FoKLRoutines.py:594-805) --------------------------------------------------
+// The derivative routine does not use xsm: it evaluates every factor at the "twice normalised" input of
+// FR:584-586,  X = fl(fl(x - fl(phind * r)) / r)  with  r = fl(1 / n_piece)  (phind 0-based).
+FOKL_HD double twice_normalised(double x, int n_piece, int ph)
+{
+    const double r = 1.0 / (double)n_piece;
+    const double xmin = FOKL_MUL((double)ph, r);
+#if defined(__CUDA_ARCH__)
+    return __ddiv_rn(__dsub_rn(x, xmin), r);
+#else
+    return (x - xmin) / r;
+#endif
+}
+
+// evaluate_basis, cubic, d = 1 (FR:838): c1 + 2*c2*x + 3*c3*(x**2), left to right (2*c2 is exact).
+FOKL_HD double cubic_basis_d1(double c1, double c2, double c3, double x, double x2)
+{
+    double s = FOKL_ADD(c1, FOKL_MUL(FOKL_MUL(2.0, c2), x));
+    return FOKL_ADD(s, FOKL_MUL(FOKL_MUL(3.0, c3), x2));
+}
+
+// evaluate_basis, cubic, d = 2 (FR:840): 2*c2 + 6*c3*x.
+FOKL_HD double cubic_basis_d2(double c2, double c3, double x)
+{
+    return FOKL_ADD(FOKL_MUL(2.0, c2), FOKL_MUL(FOKL_MUL(6.0, c3), x));
+}
+
+// evaluate_basis, Bernoulli, d = 1 (FR:845): c[1] + sum(k*c[k]*x**(k-1), k = 2 ..) and d = 2 (FR:847):
+// sum((k-1)*k*c[k]*x**(k-2), k = 2 ..), Python's sum() accumulating left to right from 0; the powers are correctly
+// rounded (double-double running product, like powers_dd) and x**0 == 1 exactly.
+FOKL_HD double bernoulli_basis_deriv(const double *c, int n_coef, double x, int d)
+{
+    double h = x, l = 0.0, s = 0.0;      // h + l ~ x^e
+    int e = 1;
+    for (int q = 2; q < n_coef; ++q) {
+        const int need = q - d;
+        const double coef = FOKL_MUL(d == 1 ? (double)q : (double)((q - 1) * q), c[q]);
+        double term = coef;
+        if (need > 0) {
+            while (e < need) {
+                double p = FOKL_MUL(h, x);
+                double err = FOKL_FMA(h, x, -p);
+                double t = FOKL_FMA(l, x, err);
+                double nh = FOKL_ADD(p, t);
+                l = FOKL_SUB(t, FOKL_SUB(nh, p));
+                h = nh;
+                ++e;
+            }
+            term = FOKL_MUL(coef, h);
+        }
+        s = FOKL_ADD(s, term);
+    }
+    return d == 1 ? FOKL_ADD(c[1], s) : s;
+}
+
 // ---- Philox4x32-10 counter RNG (free-running mode) ---------------------------------------------
 struct Philox {
     uint32_t k0, k1;

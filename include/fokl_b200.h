@@ -70,6 +70,16 @@ int fokl_set_phis_bernoulli(fokl_ctx *ctx, const double *tab, int n_orders, int 
 int fokl_basis_build(fokl_ctx *ctx, int kernel, const double *x, int64_t n, int64_t ldx, int m,
                      const int16_t *terms, int c, double *Xnew, int64_t ld);
 
+/* K1, derivative form: the design-matrix columns of FoKL.bss_derivatives (FR:594-805; factor evaluation FR:770-781,
+ * evaluate_basis d = 1, 2 at FR:837-847).
+ * deriv     host C x M row-major, 0 / 1 / 2: derivative order of the factor of input k in term j (0 = plain factor)
+ * divisors  host M x 3 row-major: divisors[k][e] = span_L[e] of FR:762-763 for input k ([k][0] is not read)
+ * Column j = prod_k f_jk, f_jk = phi_{terms[j][k]}(X_ik) or its e-th derivative divided by divisors[k][e]; every
+ * factor is evaluated at the twice-normalised input X of FR:584-586 (cubic) or at x itself (Bernoulli).             */
+int fokl_basis_build_deriv(fokl_ctx *ctx, int kernel, const double *x, int64_t n, int64_t ldx, int m,
+                           const int16_t *terms, const uint8_t *deriv, const double *divisors, int c,
+                           double *Xnew, int64_t ld);
+
 /* fill a column with ones (X[:, 0], FR:1436). */
 int fokl_fill_ones(fokl_ctx *ctx, double *col, int64_t n);
 

@@ -9,6 +9,7 @@ It restates, in numpy float64 (plus a small C helper for the basis loop), the al
     inputs_to_phind     FR:570-589      spline piece index / local coordinate
     eval_basis          FR:834-843      one basis function at one point (d = 0)
     basis_columns       FR:1446-1485    X[i, j] = prod_k phi_{d_jk}(x_ik)
+    bss_derivatives     FR:594-805      partial derivatives of the fitted function (a section-8f "next" row)
     default_b_btau      FR:1322-1348    data-dependent defaults of b, btau
     gibbs               FR:1396-1558    Gram, eigh, betahat, Gibbs chain, BIC
     distinct_perms      FR:1350-1354 + FR:1616   == np.unique(perms(v), axis=0)
@@ -151,6 +152,102 @@ def basis_columns(x, terms, phis, kernel, table=None, threads=1):
     if rc != 0:
         raise ValueError('inputs are not normalised to [0, 1] (FR:590-591)')
     return out
+
+
+# --------------------------------------------------------------------------------------------------
+# bss_derivatives (FR:594-805)
+# --------------------------------------------------------------------------------------------------
+
+def twice_normalised(x, n_piece=499):
+    """FR:570-586: the `X` output of _inputs_to_phind, (x - (phind - 1) * r) / r with r = 1 / n_piece and the
+    1-based phind -- what bss_derivatives evaluates the cubic factors at (not xsm)."""
+    x = np.asarray(x, dtype=np.float64)
+    phind1 = np.array(np.ceil(x * n_piece), dtype=np.uint16)
+    phind1 = phind1 + (phind1 == 0)
+    r = 1 / n_piece
+    xmin = np.array((phind1 - 1) * r, dtype=x.dtype)
+    return (x - xmin) / r, phind1 - 1
+
+
+def eval_basis_d(c, x, kernel, d):
+    """FR:834-847 for d = 0, 1, 2 (Python / numpy scalar semantics)."""
+    if d == 0:
+        return eval_basis(c, x, kernel)
+    if kernel == CUBIC:
+        if d == 1:
+            return c[1] + 2 * c[2] * x + 3 * c[3] * (x ** 2)
+        return 2 * c[2] + 6 * c[3] * x
+    if d == 1:
+        return c[1] + sum(k * c[k] * (x ** (k - 1)) for k in range(2, len(c)))
+    return sum((k - 1) * k * c[k] * (x ** (k - 2)) for k in range(2, len(c)))
+
+
+def derivative_columns(x, terms, phis, kernel, wrt, order, span):
+    """Design-matrix columns of d^order / d x_wrt^order of every term (FR:757-790): N x B, zero for the terms that do
+    not contain input `wrt`.  `span` = max - min of that input's normalisation (FR:742-745)."""
+    x = np.asarray(x, dtype=np.float64)
+    n, m = x.shape
+    terms = np.asarray(terms)
+    if kernel == CUBIC:
+        n_piece = len(phis[0][0])
+        xe, phind = twice_normalised(x, n_piece)
+        span_l = span / n_piece
+    else:
+        xe, phind, span_l = x, None, span / 1
+    div = [1, span_l, span_l ** 2]
+    out = np.zeros((n, terms.shape[0]))
+    for i in range(n):
+        for b in range(terms.shape[0]):
+            if int(terms[b][wrt]) == 0:
+                continue                              # FR:785-787: phi = 0
+            phi = 1
+            for k in range(m):
+                num = int(terms[b][k])
+                if num == 0:
+                    continue
+                if kernel == CUBIC:
+                    c = [phis[num - 1][q][int(phind[i, k])] for q in range(4)]
+                else:
+                    c = phis[num - 1]
+                if k == wrt:
+                    phi *= eval_basis_d(c, xe[i, k], kernel, order) / div[order]
+                else:
+                    phi *= eval_basis_d(c, xe[i, k], kernel, 0)
+            out[i, b] = phi
+    return out
+
+
+def bss_derivatives(inputs, betas, mtx, phis, kernel, minmax, d1=None, d2=None, draws=None,
+                    individual_draws=False, full_array=False):
+    """FR:594-805 with d1 / d2 given as boolean masks over the inputs (None: all first, no second derivatives).
+    Returns what the reference returns (squeezed N x (#requested) [x draws] array, or N x M x 2 [x draws])."""
+    inputs = np.asarray(inputs, dtype=np.float64)
+    if inputs.ndim == 1:
+        inputs = inputs[:, None]
+    betas = np.asarray(betas, dtype=np.float64)
+    mtx = np.asarray(mtx)
+    n, m = inputs.shape
+    nb = mtx.shape[0]
+    if draws is None:
+        draws = betas.shape[0]
+    masks = [np.ones(m, bool) if d1 is None else np.asarray(d1, bool),
+             np.zeros(m, bool) if d2 is None else np.asarray(d2, bool)]
+    dy = np.zeros((draws, n, m, 2))
+    for k in range(m):
+        span = minmax[k][1] - minmax[k][0]
+        for di in (0, 1):
+            if not masks[di][k]:
+                continue
+            cols = derivative_columns(inputs, mtx, phis, kernel, k, di + 1, span)
+            for b in range(nb):                       # FR:790: accumulated term by term
+                dy[:, :, k, di] = dy[:, :, k, di] + betas[-draws:, b + 1][:, None] * cols[:, b][None, :]
+    dy = np.transpose(dy, (1, 2, 3, 0))
+    if not individual_draws and draws > 1:
+        dy = np.mean(dy, axis=3)[:, :, :, None]
+    if not full_array:
+        dy = np.concatenate([dy[:, :, 0, :], dy[:, :, 1, :]], axis=1)
+        dy = dy[:, ~np.all(dy == 0, axis=0)]
+    return np.squeeze(dy)
 
 
 # --------------------------------------------------------------------------------------------------

@@ -218,11 +218,42 @@ def case_basis_values():
     print('basis_values', vals_c.shape, vals_b.shape, bt.shape)
 
 
+def case_bss_derivatives():
+    """Pin bss_derivatives (FR:594-805): the unmodified reference on a hand-made model (no fit needed: inputs, betas,
+    mtx, minmax are all keyword inputs), cubic and Bernoulli, first and second derivatives, mean and per-draw forms."""
+    FR = ref_harness.load_reference()
+    rng = np.random.default_rng(77)
+    n, m, draws = 37, 3, 6
+    x = rng.random((n, m))
+    x[0, 0], x[1, 1], x[2, 2], x[3, 0] = 0.0, 1.0, 1 / 499, 0.5
+    mtx = np.array([[1, 0, 0], [0, 2, 0], [0, 0, 3], [1, 1, 0], [2, 0, 1], [0, 3, 2], [1, 2, 1], [4, 0, 0], [0, 0, 1]],
+                   dtype=np.float64)
+    betas = rng.standard_normal((draws + 2, mtx.shape[0] + 1))
+    minmax = [[-1.0, 3.0], [0.0, 1.0], [10.0, 10.7]]
+    out = dict(x=x, mtx=mtx, betas=betas, minmax=np.array(minmax), draws=draws)
+    tab = np.load(os.path.join(GOLD, 'phis_cubic_48.npy'))
+    models = dict(cubic=FR.FoKL(phis=spline_table.to_phis(tab), UserWarnings=False),
+                  bern=FR.FoKL(kernel=1, UserWarnings=False))
+    import warnings
+    for name, model in models.items():
+        model.mtx, model.minmax, model.draws, model.betas = mtx, minmax, draws, betas
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            kw = dict(inputs=x, betas=betas, mtx=mtx, minmax=minmax, draws=draws)
+            out[name + '_grad'] = model.bss_derivatives(**kw)                                   # defaults: gradient
+            out[name + '_d1d2'] = model.bss_derivatives(d1=[1, 0, 1], d2=[0, 1, 1], **kw)
+            out[name + '_full_draws'] = model.bss_derivatives(d1=True, d2=True, IndividualDraws=True,
+                                                              ReturnFullArray=True, **kw)
+            out[name + '_d2_only'] = model.bss_derivatives(d1=False, d2=1, **kw)
+    np.savez_compressed(os.path.join(GOLD, 'bss_derivatives.npz'), **out)
+    print('bss_derivatives', {k: np.shape(v) for k, v in out.items()})
+
+
 CASES = dict(isotherm_gp=case_isotherm_gp, isotherm_qmax=case_isotherm_qmax,
              cfg2_default=lambda: case_cfg2(False), cfg2_changed=lambda: case_cfg2(True),
              cfg1_sigmoid=case_cfg1_sigmoid, way3_bernoulli=case_way3_bernoulli,
              way3_cubic=case_way3_cubic, two_way_cubic=case_two_way_cubic, m1_cubic=case_m1,
-             basis_values=case_basis_values)
+             basis_values=case_basis_values, bss_derivatives=case_bss_derivatives)
 
 if __name__ == '__main__':
     todo = sys.argv[1:] or list(CASES)

@@ -40,6 +40,10 @@ def lib():
     L.emu_phind.restype = _i32
     L.emu_basis_bernoulli.argtypes = [_vp, _i64, _vp, _i32, _vp, _i32, _vp]
     L.emu_basis_bernoulli.restype = None
+    L.emu_deriv_cubic.argtypes = [_vp, _i64, _vp, _i32, _vp, _i32, _i32, _f64, _vp]
+    L.emu_deriv_cubic.restype = _i32
+    L.emu_deriv_bernoulli.argtypes = [_vp, _i64, _vp, _i32, _vp, _i32, _i32, _f64, _vp]
+    L.emu_deriv_bernoulli.restype = None
     L.emu_candidate.argtypes = [_vp, _i64, _vp, _vp, _i32, ctypes.POINTER(EmuHypers), _i32, _u64, _u64, _vp, _vp,
                                 _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
     L.emu_candidate.restype = _i32
@@ -74,6 +78,18 @@ def basis_bernoulli(x, orders, tab):
     out = np.zeros((len(x), len(orders)))
     lib().emu_basis_bernoulli(x.ctypes.data, len(x), orders.ctypes.data, len(orders), tab.ctypes.data, tab.shape[1],
                               out.ctypes.data)
+    return out
+
+
+def deriv_factors(x, orders, tab, e, div, cubic=True):
+    """bss_derivatives factor values: e-th derivative of the basis functions `orders` at x, divided by div (e > 0)."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    orders = np.ascontiguousarray(orders, dtype=np.int32)
+    tab = np.ascontiguousarray(tab, dtype=np.float64)
+    out = np.zeros((len(x), len(orders)))
+    fn = lib().emu_deriv_cubic if cubic else lib().emu_deriv_bernoulli
+    fn(x.ctypes.data, len(x), orders.ctypes.data, len(orders), tab.ctypes.data, tab.shape[1], int(e), float(div),
+       out.ctypes.data)
     return out
 
 

@@ -52,6 +52,44 @@ void emu_basis_bernoulli(const double *x, int64_t n, const int32_t *orders, int 
         }
 }
 
+// bss_derivatives factor values (FR:770-781): out[i][s] = e-th derivative (e = 0, 1, 2) of the basis function of order
+// orders[s] at the twice-normalised input (cubic) / at x (Bernoulli), divided by div when e > 0.
+int emu_deriv_cubic(const double *x, int64_t n, const int32_t *orders, int n_ord, const double *tab, int n_piece, int e,
+                    double div, double *out)
+{
+    int bad = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        int ph;
+        double xs, x2, x3;
+        if (!phind_xsm(x[i], n_piece, ph, xs)) bad = 1;
+        xs = twice_normalised(x[i], n_piece, ph);
+        square_cube(xs, x2, x3);
+        for (int s = 0; s < n_ord; ++s) {
+            const double *c = tab + ((size_t)(orders[s] - 1) * n_piece + ph) * 4;
+            double v = e == 0 ? cubic_basis(c[0], c[1], c[2], c[3], xs, x2, x3)
+                     : e == 1 ? cubic_basis_d1(c[1], c[2], c[3], xs, x2) / div : cubic_basis_d2(c[2], c[3], xs) / div;
+            out[i * n_ord + s] = v;
+        }
+    }
+    return bad;
+}
+
+void emu_deriv_bernoulli(const double *x, int64_t n, const int32_t *orders, int n_ord, const double *tab, int row_len,
+                         int e, double div, double *out)
+{
+    for (int64_t i = 0; i < n; ++i)
+        for (int s = 0; s < n_ord; ++s) {
+            int d = orders[s];
+            if (e == 0) {
+                std::vector<double> pw(row_len + 2);
+                powers_dd(x[i], d, pw.data());
+                out[i * n_ord + s] = bernoulli_basis(tab + (size_t)(d - 1) * row_len, d + 1, pw.data());
+            } else {
+                out[i * n_ord + s] = bernoulli_basis_deriv(tab + (size_t)(d - 1) * row_len, d + 1, x[i], e) / div;
+            }
+        }
+}
+
 struct emu_hypers {
     double a, b, atau, btau, sigsqd0, tausqd0, yty, sum_y;
     int64_t n;

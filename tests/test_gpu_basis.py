@@ -106,3 +106,73 @@ def test_bernoulli_way3(engine, phis_bern):
     got = build_on_device(engine, phis_bern, fo.BERNOULLI, x, terms)
     ref = fo.basis_columns(x, terms, phis_bern, fo.BERNOULLI)
     assert np.allclose(got, ref, rtol=1e-12, atol=1e-15)
+
+
+# ---- bss_derivatives (FR:594-805; a SURVEY section-8f "next" row) ------------------------------------------------
+
+def _deriv_model(FR, phis, kernel, g):
+    model = FR.FoKL(phis=phis, kernel=kernel, UserWarnings=False)
+    model.mtx, model.minmax, model.draws, model.betas = g['mtx'], g['minmax'].tolist(), int(g['draws']), g['betas']
+    return model, dict(inputs=g['x'], betas=g['betas'], mtx=g['mtx'], minmax=g['minmax'].tolist(), draws=int(g['draws']))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', ['cubic', 'bern'])
+def test_bss_derivatives_against_reference_golden(name, phis_cubic, phis_bern):
+    """FoKL.bss_derivatives through the derivative basis kernel vs the outputs of the unmodified reference
+    (tests/golden/bss_derivatives.npz, oracle/gen_golden.py).  Tolerance: rtol 1e-9 of the column scale (the design
+    columns are bit-exact for cubic splines; the product with the draws sums in a different order)."""
+    import warnings
+    from FoKL import FoKLRoutines as FR
+    from conftest import load_golden
+    g = load_golden('bss_derivatives')
+    phis, kernel = (phis_cubic, 'Cubic Splines') if name == 'cubic' else (phis_bern, 'Bernoulli Polynomials')
+    model, kw = _deriv_model(FR, phis, kernel, g)
+
+    def close(got, want):
+        assert np.shape(got) == np.shape(want)
+        scale = np.max(np.abs(want), axis=0, keepdims=True) + 1e-300
+        assert np.max(np.abs(got - want) / scale) < 1e-9
+
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        close(model.bss_derivatives(**kw), g[name + '_grad'])
+        close(model.bss_derivatives(d1=[1, 0, 1], d2=[0, 1, 1], **kw), g[name + '_d1d2'])
+        close(model.bss_derivatives(d1=True, d2=True, IndividualDraws=True, ReturnFullArray=True, **kw),
+              g[name + '_full_draws'])
+        close(model.bss_derivatives(d1=False, d2=1, **kw), g[name + '_d2_only'])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('n', [1, 255, 4097])
+def test_derivative_columns_bit_exact_cubic(engine, phis_cubic, n):
+    """fokl_basis_build_deriv vs the oracle's literal loop (FR:757-790): bit-exact for cubic splines, ragged sizes,
+    first and second derivatives, 1- to 3-way terms."""
+    import torch
+    import fokl_oracle as fo
+    rng = np.random.default_rng(n)
+    m = 3
+    x = rng.random((n, m))
+    x[0, 0] = 1.0
+    terms = np.array([[1, 0, 0], [0, 2, 0], [3, 1, 0], [2, 0, 5], [1, 2, 3], [0, 0, 7]])
+    span = [2.5, 1.0, 0.3]
+    engine.set_phis(phis_cubic, 'Cubic Splines')
+    ds = engine.upload(x, np.zeros(n))
+    for wrt in range(m):
+        for order in (1, 2):
+            idx = np.nonzero(terms[:, wrt])[0]
+            want = fo.derivative_columns(x, terms, phis_cubic, fo.CUBIC, wrt, order, span[wrt])[:, idx]
+            t16 = np.ascontiguousarray(terms[idx], dtype=np.int16)
+            d8 = np.zeros((len(idx), m), dtype=np.uint8)
+            d8[:, wrt] = order
+            dv = np.ones((m, 3))
+            for k in range(m):
+                s_l = span[k] / 499
+                dv[k] = [1, s_l, s_l ** 2]
+            X = torch.empty((len(idx), ds.ldx), dtype=torch.float64, device=engine.device)
+            engine._ck(engine.lib.fokl_basis_build_deriv(engine.ctx, engine.kernel_id, ds.x.data_ptr(), n, ds.ldx, m,
+                                                         t16.ctypes.data, d8.ctypes.data, dv.ctypes.data, len(idx),
+                                                         X.data_ptr(), ds.ldx))
+            engine.synchronize()
+            got = X[:, :n].cpu().numpy().T
+            assert np.array_equal(got, want), (wrt, order)

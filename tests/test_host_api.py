@@ -108,9 +108,15 @@ def test_fit_fails_loudly_without_a_gpu(phis_cubic):
 def test_out_of_scope_entry_points_say_so(phis_cubic):
     m = FoKLRoutines.FoKL(phis=phis_cubic, UserWarnings=False)
     with pytest.raises(NotImplementedError):
-        m.bss_derivatives()
-    with pytest.raises(NotImplementedError):
         m.fitupdate(None, None)
+    # bss_derivatives: keyword handling mirrors FR:626-740 and fails before any device work
+    m.mtx, m.minmax, m.draws = np.array([[1.0, 0.0], [1.0, 2.0]]), [[0, 1], [0, 1]], 2
+    with pytest.raises(ValueError, match="does not align"):
+        m.bss_derivatives(inputs=np.random.rand(4, 2), betas=np.ones((2, 5)))
+    with pytest.raises(ValueError, match="equal length"):
+        m.bss_derivatives(inputs=np.random.rand(4, 2), betas=np.ones((2, 3)), d1=[1, 0, 0])
+    with pytest.warns(UserWarning, match="no derivatives were requested"):
+        assert m.bss_derivatives(inputs=np.random.rand(4, 2), betas=np.ones((2, 3)), d1=False) is None
     m.clear()
     assert hasattr(m, 'phis') and not hasattr(m, 'setnos')
 

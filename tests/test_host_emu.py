@@ -217,3 +217,36 @@ def test_gram_k_split_fills_the_cta():
     A = np.random.default_rng(0).standard_normal((40, 50 + 168 + 1))
     rc, _, _, st = emu.gram_plan(A, 50, 168, 352, 16, 4)
     assert rc == 0 and st['max_ksplit'] == 1
+
+
+@pytest.mark.parametrize('e', [0, 1, 2])
+def test_derivative_factor_math_matches_oracle(cubic_table, phis_cubic, bern_table, phis_bern, e):
+    """The device's bss_derivatives factor math (fokl_math.cuh: twice_normalised, cubic_basis_d1/d2,
+    bernoulli_basis_deriv) against the oracle's Python-scalar evaluation (FR:584-586, 834-847, 780-781)."""
+    rng = np.random.default_rng(40 + e)
+    x = np.concatenate([rng.random(3000), [0.0, 1.0, 1 / 499, 0.5, 2 / 499, 1 - 2 ** -53]])
+    span = 3.7
+    # cubic: bit-exact
+    orders = np.array([1, 2, 5, 17, 48])
+    xe, ph = fo.twice_normalised(x[:, None])
+    div = [1, span / 499, (span / 499) ** 2][e]
+    ref = np.zeros((len(x), len(orders)))
+    for i in range(len(x)):
+        for j, o in enumerate(orders):
+            c = [phis_cubic[o - 1][q][int(ph[i, 0])] for q in range(4)]
+            v = fo.eval_basis_d(c, xe[i, 0], fo.CUBIC, e)
+            ref[i, j] = v / div if e else v
+    out = emu.deriv_factors(x, orders, cubic_table, e, div, cubic=True)
+    assert np.array_equal(out, ref)
+    # Bernoulli: the running double-double power is correctly rounded, libm pow() is not always: tolerance
+    orders = np.array([1, 2, 3, 5, 8, 10])
+    div = [1, span, span ** 2][e]
+    ref = np.zeros((300, len(orders)))
+    for i in range(300):
+        for j, o in enumerate(orders):
+            v = fo.eval_basis_d(phis_bern[o - 1], np.float64(x[i]), fo.BERNOULLI, e)
+            ref[i, j] = v / div
+    out = emu.deriv_factors(x[:300], orders, bern_table, e, div, cubic=False)
+    scale = np.max(np.abs(ref), axis=0) + 1e-300
+    assert np.max(np.abs(out - ref) / scale) < 1e-9
+    assert np.mean(out == ref) > 0.5

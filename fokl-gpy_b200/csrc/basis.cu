@@ -95,9 +95,9 @@ __device__ __forceinline__ double eval_factor_bernoulli(const double *c, int n_c
 // DERIV = true is the bss_derivatives form (FR:594-805): factors are evaluated at the twice-normalised input of
 // FR:584-586 instead of xsm, and a factor with FactorMeta.pad = e > 0 is the e-th derivative of its basis function
 // divided by fac_div (FR:780-781).  The fit path only ever instantiates DERIV = false.
-// PF = true is the phase-1 form that requests the rows of every input in use up front (more registers: used for
-// launches whose shared-memory footprint allows at most 3 CTAs per SM anyway, where the exposed load latency of the
-// input-by-input form is not covered by other CTAs; measured in profiles/r01_k1_prefetch.txt).
+// PF = true is the phase-1 form that requests the rows of every input in use up front (more registers: used for the
+// main-effect launches and for launches whose shared-memory footprint allows at most 3 CTAs per SM anyway, where the
+// exposed load latency of the input-by-input form is not covered by other CTAs; profiles/r01_k1_prefetch.txt).
 template <int KERNEL, int RPT, int NF, bool DERIV = false, bool PF = false>
 __global__ void __launch_bounds__(kThreads) basis_kernel(const __grid_constant__ BasisParams P)
 {
@@ -522,7 +522,7 @@ static int basis_build_impl(fokl_ctx *ctx, int kernel, const double *x, int64_t 
         int grid = (int)std::min<int64_t>(P.n_tiles, (int64_t)ctx->num_sms * ctas_per_sm);
         void (*kern)(const BasisParams) = nullptr;
         const bool pf = P.n_in > 0 && !deriv && !getenv("FOKL_BASIS_NOPF") &&
-                        (direct ? getenv("FOKL_BASIS_PF_DIRECT") != nullptr : smem_cap / std::max<size_t>(smem, 1) <= 3);
+                        (direct || smem_cap / std::max<size_t>(smem, 1) <= 3);
         static_assert(sizeof(TermMeta) == sizeof(unsigned long long), "TermMeta is one 64-bit word");
         const int nfc = pl.max_cnt <= 1 ? 1 : (pl.max_cnt == 2 ? 2 : (pl.max_cnt == 3 ? 3 : 7));
 #define FOKL_PICK(K, R, F)                                                                                            \

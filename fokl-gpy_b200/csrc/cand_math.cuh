@@ -412,10 +412,14 @@ FOKL_HD double chain_atau_star(const CandConst &k, int p) { return k.atau + (dou
 // of the (prefetched) gamma variates, 1/(2 sig^2) = G1 / (2 bstar), and sqrt(d_j) is one rsqrt -- two reciprocals and
 // one rsqrt on the critical path per draw instead of seven divisions and two square roots (same values to a few ulp).
 // variates: D rows of [z_0 .. z_{p-1}, G1, G2] (injected numpy stream or the Philox table); sign_fix optional (p).
+// canon (used when sign_fix is null, i.e. free-running mode): orient every eigenvector so that its projection on
+// X'y is non-negative, z_j *= sign(ct_j).  The sign an eigensolver returns is arbitrary and flips under last-place
+// changes of the Gram (another summation order: row shards, row permutations), which would pair the normals with
+// other directions; with this convention the chain is a function of the Gram alone.
 // gam (out) D x p row-major, sigs/taus (out) D.  Returns 1 if bstar < 0 was seen.
 FOKL_HD int gibbs_chain(const Team &t, int p, const double *lamb, const double *ct, const CandConst &k,
                         const double *variates, const double *sign_fix, double *gam, double *sigs, double *taus,
-                        double *red)
+                        double *red, bool canon = false)
 {
     const int D = k.draws;
     const int w = p + 2;
@@ -425,8 +429,8 @@ FOKL_HD int gibbs_chain(const Team &t, int p, const double *lamb, const double *
     const int e0 = t.tid, e1 = t.tid + t.nthr;
     const bool h0 = e0 < p, h1 = e1 < p;
     double l0 = 0.0, c0 = 0.0, f0 = 1.0, l1 = 0.0, c1 = 0.0, f1 = 1.0;
-    if (h0) { l0 = lamb[e0]; c0 = ct[e0]; if (sign_fix) f0 = sign_fix[e0]; }
-    if (h1) { l1 = lamb[e1]; c1 = ct[e1]; if (sign_fix) f1 = sign_fix[e1]; }
+    if (h0) { l0 = lamb[e0]; c0 = ct[e0]; if (sign_fix) f0 = sign_fix[e0]; else if (canon && c0 < 0.0) f0 = -1.0; }
+    if (h1) { l1 = lamb[e1]; c1 = ct[e1]; if (sign_fix) f1 = sign_fix[e1]; else if (canon && c1 < 0.0) f1 = -1.0; }
     // software pipeline over the variate table, two rows deep: warps issue in order, so a value loaded in iteration
     // d - 1 is first touched in iteration d (row d + 1 is only *loaded* while row d is being used)
     double z0 = h0 ? f0 * variates[e0] : 0.0, z1 = h1 ? f1 * variates[e1] : 0.0;
@@ -465,8 +469,9 @@ FOKL_HD int gibbs_chain(const Team &t, int p, const double *lamb, const double *
         }
         for (int e = t.tid + 2 * t.nthr; e < p; e += t.nthr) {
             double z = row[e];
-            if (sign_fix) z *= sign_fix[e];
             double l = lamb[e], c = ct[e];
+            if (sign_fix) z *= sign_fix[e];
+            else if (canon && c < 0.0) z = -z;
             double rs = FOKL_RSQRT(l + itau);
             double g = (rs * rs) * c + (ssig * rs) * z;
             gam[(int64_t)d * p + e] = g;
@@ -521,7 +526,8 @@ __device__ __forceinline__ double rcp_pos(double x)
 
 template <int E>
 __device__ int gibbs_chain_warp(int lane, int p, const double *lamb, const double *ct, const CandConst &k,
-                                const double *variates, const double *sign_fix, double *gam, double *sigs, double *taus)
+                                const double *variates, const double *sign_fix, double *gam, double *sigs, double *taus,
+                                bool canon = false)
 {
     const int D = k.draws;
     const int w = p + 2;
@@ -535,7 +541,7 @@ __device__ int gibbs_chain_warp(int lane, int p, const double *lamb, const doubl
         h[q] = e < p;
         l[q] = h[q] ? lamb[e] : 1.0;
         c[q] = h[q] ? ct[e] : 0.0;
-        f[q] = (h[q] && sign_fix) ? sign_fix[e] : 1.0;
+        f[q] = (h[q] && sign_fix) ? sign_fix[e] : ((canon && c[q] < 0.0) ? -1.0 : 1.0);
         z[q] = h[q] ? f[q] * variates[e] : 0.0;
         zr[q] = (h[q] && D > 1) ? variates[w + e] : 0.0;
     }

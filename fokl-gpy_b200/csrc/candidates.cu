@@ -516,7 +516,7 @@ __global__ void __launch_bounds__(kChainThreads) cand_chain_kernel(const ChainPa
     const double *var = (P.rng_mode == FOKL_RNG_INJECTED ? P.variates : P.var_philox) + variates_offset(P, m, c);
     const double *sf = P.sign_fix ? P.sign_fix + m.vec_off : nullptr;
     int bad = fokl::gibbs_chain(t, p, P.lamb + m.vec_off, P.ct + m.vec_off, P.k, var, sf, P.gam + (int64_t)D * m.gam_off,
-                                P.sigs + (int64_t)D * c, P.taus + (int64_t)D * c, red);
+                                P.sigs + (int64_t)D * c, P.taus + (int64_t)D * c, red, P.rng_mode == FOKL_RNG_PHILOX);
     if (t.tid == 0 && bad) atomicOr(P.info + c, 1);
 }
 
@@ -530,7 +530,8 @@ __global__ void __launch_bounds__(32) cand_chain_warp_kernel(const ChainParams P
     const double *var = (P.rng_mode == FOKL_RNG_INJECTED ? P.variates : P.var_philox) + variates_offset(P, m, c);
     const double *sf = P.sign_fix ? P.sign_fix + m.vec_off : nullptr;
     int bad = fokl::gibbs_chain_warp<E>(threadIdx.x, m.p, P.lamb + m.vec_off, P.ct + m.vec_off, P.k, var, sf,
-                                        P.gam + (int64_t)D * m.gam_off, P.sigs + (int64_t)D * c, P.taus + (int64_t)D * c);
+                                        P.gam + (int64_t)D * m.gam_off, P.sigs + (int64_t)D * c, P.taus + (int64_t)D * c,
+                                        P.rng_mode == FOKL_RNG_PHILOX);
     if (threadIdx.x == 0 && bad) atomicOr(P.info + c, 1);
 }
 

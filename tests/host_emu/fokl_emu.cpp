@@ -148,7 +148,7 @@ int emu_candidate(const double *G, int64_t ldg, const double *Xty, const int32_t
                                                                 p, chain_astar(k, p), chain_atau_star(k, p));
         var = table.data();
     }
-    int bad = gibbs_chain(t, p, lamb, ct.data(), k, var, sign_fix, gam.data(), sigs, taus, red.data());
+    int bad = gibbs_chain(t, p, lamb, ct.data(), k, var, sign_fix, gam.data(), sigs, taus, red.data(), rng_mode == 2);
     if (bad) *info |= 1;
     for (int d = 0; d < D; ++d)
         for (int i = 0; i < p; ++i) {

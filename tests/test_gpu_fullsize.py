@@ -93,8 +93,6 @@ def test_cfg4_full_size_properties(phis_cubic):
     assert np.array_equal(mtx, mtx3) and np.array_equal(evs2, evs3) and np.array_equal(betas2, betas3)
     # (f) row order does not matter: the same terms built in one go on a row-permuted copy of the dataset give the
     # same Gram (different summation order and a different K2 work plan: all columns in one launch) and the same BIC.
-    # (A row-permuted *fit* is only statistically equivalent: Gram bits that differ in the last place flip
-    # eigenvector signs, which pairs the Philox normals with other directions -- SURVEY section 0.7.)
     import torch
     from FoKL import _lib
     model, _, mtx_last, _ = _fit(FR, 'cfg4', phis_cubic, x, y, seed=4, gimmie=True)
@@ -116,6 +114,11 @@ def test_cfg4_full_size_properties(phis_cubic):
     assert np.allclose(eng.Xty[:P].cpu().numpy(), xty, rtol=1e-10, atol=1e-10 * np.sqrt(n))
     ev_p = eng.evaluate([list(range(P))], hyp, rng_mode=_lib.RNG_NONE, refine_tol=None).ev[0]
     assert np.isclose(ev, ev_p, rtol=1e-9, atol=0)
+    # (g) ... and, because the free-running chain orients every eigenvector by its projection on X'y (cand_math.cuh,
+    # gibbs_chain `canon`), the whole row-permuted fit walks the same path: same terms, same BIC trace
+    _, _, mtx_p, evs_p = _fit(FR, 'cfg4', phis_cubic, x[perm], y[perm], seed=4)
+    assert np.array_equal(mtx, mtx_p)
+    assert np.allclose(evs2, evs_p, rtol=1e-9, atol=0)
     FR._engine().release()
 
 

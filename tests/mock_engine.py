@@ -1,0 +1,109 @@
+"""A numpy / host-emulation stand-in for FoKL._engine.Engine, so that the host side of the selection loop
+(FoKL/_selection.py: batching, speculation, roll-back, bookkeeping) can be tested without a GPU.
+
+TEST INFRASTRUCTURE.  Design columns come from the oracle's basis loop, Gram products from numpy, and the candidate
+math (eigensolver, BIC, Philox Gibbs chain, kill loop) from tests/host_emu -- the kernels' own math compiled for the
+host.  Only the interface forward_select() uses is provided."""
+import numpy as np
+import torch
+
+import emu
+import fokl_oracle as fo
+from FoKL import _lib
+from FoKL._engine import CandidateResult, Engine
+
+
+class MockEngine:
+    def __init__(self, x, y, phis, kernel):
+        self.torch = torch
+        self.device = torch.device('cpu')
+        self.dist, self.group, self.world, self.rank = None, None, 1, 0
+        self.profile = None
+        self.x = np.ascontiguousarray(x, dtype=np.float64)
+        self.y = np.ascontiguousarray(y, dtype=np.float64).reshape(-1)
+        self.phis, self.kernel = phis, kernel
+        self.calls = []              # (kind, detail) log of the device work the loop asked for
+        n = len(self.y)
+        self.n_global, self.sum_y, self.yty = n, float(self.y.sum()), float(self.y @ self.y)
+        self.X = np.ones((n, 1))
+        self._gram()
+
+    def _gram(self):
+        self.G = self.X.T @ self.X
+        self.Xty = self.X.T @ self.y
+        self.P = self.X.shape[1]
+
+    # ---- K1 / K2 / compaction ----------------------------------------------------------------------------------
+    def append_terms(self, terms):
+        terms = np.asarray(terms, dtype=np.int64)
+        self.calls.append(('append', len(terms)))
+        if len(terms) == 0:
+            return
+        cols = fo.basis_columns(self.x, terms, self.phis, self.kernel)
+        self.X = np.hstack([self.X, cols])
+        self._gram()
+
+    def compact(self, keep):
+        keep = np.asarray(keep, dtype=np.int64)
+        self.calls.append(('compact', len(keep)))
+        if len(keep) == self.P:
+            return
+        self.X = self.X[:, keep]
+        self.G = self.G[np.ix_(keep, keep)].copy()
+        self.Xty = self.Xty[keep].copy()
+        self.P = len(keep)
+
+    def truncate(self, p):
+        """Drop the columns from p on (roll-back of a speculative append)."""
+        self.calls.append(('truncate', p))
+        self.X = self.X[:, :p]
+        self.G = self.G[:p, :p].copy()
+        self.Xty = self.Xty[:p].copy()
+        self.P = p
+
+    # ---- K3 / K4 ----------------------------------------------------------------------------------------------
+    def make_hypers(self, a, b, atau, btau, sigsqd0, tausqd0, draws):
+        return dict(a=float(a), b=float(b), atau=float(atau), btau=float(btau), sigsqd0=float(sigsqd0),
+                    tausqd0=float(tausqd0), yty=self.yty, sum_y=self.sum_y, n=self.n_global, draws=int(draws))
+
+    def evaluate(self, col_sets, hyp, rng_mode=_lib.RNG_NONE, run_chain=None, seed=0, stream_ids=None, variates=None,
+                 sign_fix=None, want_betas=False, want_eig=False, refine_tol=1e-7, gram=None):
+        G, Xty = gram if gram is not None else (self.G, self.Xty)
+        self.calls.append(('evaluate', [len(s) for s in col_sets]))
+        n_cand = len(col_sets)
+        p = np.array([len(s) for s in col_sets], dtype=np.int64)
+        D = int(hyp['draws'])
+        h0, h1 = int(np.ceil(D / 2)), int(np.ceil(D / 2 + 1))
+        res = CandidateResult()
+        res.p, res.draws = p, D
+        res.vec_off = np.concatenate([[0], np.cumsum(p)[:-1]]).astype(np.int64)
+        res.mat_off = np.concatenate([[0], np.cumsum(p * p)[:-1]]).astype(np.int64)
+        ev = np.zeros(n_cand)
+        stats, betas, betahat = [], [], []
+        for c, cols in enumerate(col_sets):
+            chain = rng_mode != _lib.RNG_NONE and (run_chain is None or bool(run_chain[c]))
+            r = emu.candidate(G, Xty, np.asarray(cols, dtype=np.int32), hyp, rng_mode=rng_mode if chain else 0,
+                              seed=int(seed), stream=int(stream_ids[c]) if stream_ids is not None else 0)
+            ev[c] = r['ev']
+            betahat.append(r['betahat'])
+            b = r['betas'] if chain else np.zeros((D, len(cols)))
+            betas.append(b.reshape(-1))
+            stats.append(np.stack([b[h1:].mean(axis=0), b[h1:].std(axis=0), b[h0:].mean(axis=0)]).reshape(-1)
+                         if chain else np.zeros(3 * len(cols)))
+        res.ev = ev
+        res.info = np.zeros(n_cand, dtype=np.int32)
+        res.stats = torch.from_numpy(np.concatenate(stats))
+        res.betas = torch.from_numpy(np.concatenate(betas))
+        res.betahat = torch.from_numpy(np.concatenate(betahat))
+        res.sigs = res.taus = res.lamb = res.Q = None
+        return res
+
+    refine_mask = Engine.refine_mask
+
+    def kill_loop(self, cols, cand_pos, bv0, bv1, hyp, threshav, threshstda, threshstdb, icpt, evmin, aic_adj, start):
+        self.calls.append(('kill_loop', len(cand_pos)))
+        return emu.kill_loop(self.G, self.Xty, cols, cand_pos, bv0, bv1, hyp, threshav=threshav, threshstda=threshstda,
+                             threshstdb=threshstdb, icpt=icpt, evmin=evmin, aic_adj=aic_adj, start=start)
+
+    def _allreduce(self, t):
+        pass

@@ -31,6 +31,8 @@ B200_CONFIG = {
     'rng': os.environ.get('FOKL_B200_RNG', 'philox'),       # 'philox' | 'numpy'
     'eager_chains': os.environ.get('FOKL_B200_EAGER', '0') not in ('0', '', 'false', 'False'),
     'device': None,                                         # torch device / index; None = current device
+    # evaluate the chains that verify a substage together with the next substage's full model (same fit, bit for bit)
+    'pipeline': os.environ.get('FOKL_B200_PIPELINE', '1') not in ('0', '', 'false', 'False'),
 }
 
 _ENGINES = {}
@@ -805,7 +807,7 @@ class FoKL:
         t0 = time.perf_counter()
         launches0 = eng.launch_count()
         out = forward_select(eng, hy, ds.m, len(self.phis), console=self.ConsoleOutput, rng=B200_CONFIG['rng'],
-                             eager=B200_CONFIG['eager_chains'])
+                             eager=B200_CONFIG['eager_chains'], pipeline=B200_CONFIG['pipeline'])
         eng.synchronize()
         LAST_FIT_INFO.clear()
         LAST_FIT_INFO.update(n_gibbs=out['n_gibbs'], n_batches=out['n_batches'], seconds=time.perf_counter() - t0,

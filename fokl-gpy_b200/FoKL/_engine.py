@@ -54,7 +54,7 @@ class DeviceDataset:
 
 class CandidateResult:
     __slots__ = ('ev', 'info', 'stats', 'betas', 'sigs', 'taus', 'betahat', 'lamb', 'Q', 'p', 'vec_off', 'mat_off',
-                 'draws')
+                 'draws', 'refined')
 
     def betas_of(self, c):
         o = self.draws * self.vec_off[c]
@@ -63,6 +63,32 @@ class CandidateResult:
     def stats_of(self, c):
         o = 3 * self.vec_off[c]
         return self.stats[o:o + 3 * self.p[c]].view(3, self.p[c])
+
+
+class PendingCandidates:
+    """A batch of candidate models enqueued by Engine.evaluate_launch; finish() reads the BICs back."""
+
+    def __init__(self, engine, res, ev, info, col_sets, side, keep_alive):
+        self.engine, self.res, self.ev, self.info = engine, res, ev, info
+        self.col_sets, self.side, self.keep_alive = col_sets, side, keep_alive
+
+    def finish(self, refine_tol=None):
+        """Synchronise and return the CandidateResult.  refine_tol > 0: near-interpolating / degenerate fits are
+        recomputed from an N-length residual pass over the *current* X (FR:1551), so the models must still be there."""
+        eng, res = self.engine, self.res
+        if self.side:
+            eng.torch.cuda.current_stream(eng.device).wait_stream(eng.side_stream)
+        res.ev = self.ev.cpu().numpy()
+        res.info = self.info.cpu().numpy()
+        res.refined = np.zeros(len(res.ev), dtype=bool)
+        if refine_tol is not None and refine_tol > 0:
+            bad = eng.refine_mask(res.ev, res.p, refine_tol)
+            res.refined = bad
+            for c in np.nonzero(bad)[0]:
+                res.ev[c] = eng.residual_bic(self.col_sets[c],
+                                             res.betahat[res.vec_off[c]:res.vec_off[c] + res.p[c]])
+        self.keep_alive = None
+        return res
 
 
 class Engine:
@@ -107,6 +133,8 @@ class Engine:
         self.sum_y = self.yty = 0.0
         self.gibbs_launch_batches = 0
         self.profile = None      # set to {} to collect CUDA-event timings per stage (bench.py)
+        self.ctx_side = None
+        self.side_stream = None
 
     # ------------------------------------------------------------------------------------------------
     def release(self):
@@ -116,6 +144,9 @@ class Engine:
 
     def close(self):
         self.X = self.Xfull = None
+        if getattr(self, 'ctx_side', None) is not None and self.ctx_side:
+            self.lib.fokl_ctx_destroy(self.ctx_side)
+            self.ctx_side = None
         if getattr(self, 'ctx', None) is not None and self.ctx:
             self.lib.fokl_ctx_destroy(self.ctx)
             self.ctx = None
@@ -138,7 +169,10 @@ class Engine:
         self._ck(self.lib.fokl_ctx_synchronize(self.ctx))
 
     def launch_count(self):
-        return int(self.lib.fokl_launch_count(self.ctx))
+        n = int(self.lib.fokl_launch_count(self.ctx))
+        if getattr(self, 'ctx_side', None) is not None and self.ctx_side:
+            n += int(self.lib.fokl_launch_count(self.ctx_side))
+        return n
 
     def _allreduce(self, t):
         if self.dist is not None:
@@ -387,7 +421,38 @@ class Engine:
         """K3/K4 on a batch of candidate models (lists of column indices into the current X / G).
 
         Returns a CandidateResult; `ev` is a host numpy array (this call synchronises)."""
+        return self.evaluate_launch(col_sets, hyp, rng_mode=rng_mode, run_chain=run_chain, seed=seed,
+                                    stream_ids=stream_ids, variates=variates, sign_fix=sign_fix, want_betas=want_betas,
+                                    want_eig=want_eig).finish(refine_tol)
+
+    def _side(self):
+        """Second context on a private (non-blocking) stream: a batch launched there runs next to the work of the main
+        context (used for the chains that verify a substage while the next substage's full model is evaluated)."""
+        if getattr(self, 'ctx_side', None) is None:
+            self.side_stream = self.torch.cuda.Stream(device=self.device)
+            ctx = ctypes.c_void_p()
+            rc = self.lib.fokl_ctx_create(ctypes.byref(ctx), self.dev_index, ctypes.c_void_p(self.side_stream.cuda_stream))
+            if rc != 0:
+                raise RuntimeError("fokl_ctx_create (side context) failed with code %d" % rc)
+            self.ctx_side = ctx
+        return self.ctx_side
+
+    def gram_state(self):
+        """(G, Xty, ldg) of the current model as tensor references: stays valid (for reading) across the next
+        append_terms / one compact, which write to other buffers or to rows / columns beyond the current P."""
+        return (self.G, self.Xty, self.Gcap)
+
+    def truncate(self, p):
+        """Forget the columns from p on (roll-back of a speculative append_terms)."""
+        self.P = int(p)
+
+    def evaluate_launch(self, col_sets, hyp, rng_mode=_lib.RNG_NONE, run_chain=None, seed=0, stream_ids=None,
+                        variates=None, sign_fix=None, want_betas=False, want_eig=False, gram=None, side=False):
+        """Enqueue K3/K4 for a batch of candidate models and return a PendingCandidates; nothing is read back until
+        its finish().  gram: (G, Xty, ldg) to index instead of the current Gram (gram_state() of an earlier model);
+        side: enqueue on the side context's stream, concurrently with the main stream's work."""
         torch = self.torch
+        G, Xty, ldg = gram if gram is not None else (self.G, self.Xty, self.Gcap)
         n_cand = len(col_sets)
         p = np.array([len(s) for s in col_sets], dtype=np.int64)
         offs = np.zeros(n_cand + 1, dtype=np.int32)
@@ -426,26 +491,30 @@ class Engine:
         def ptr(t):
             return None if t is None else t.data_ptr()
 
-        t = self._tic()
-        self._ck(self.lib.fokl_candidates_eval(
-            self.ctx, self.G.data_ptr(), self.Gcap, self.Xty.data_ptr(), flat.ctypes.data, offs.ctypes.data, n_cand,
+        ctx = self.ctx
+        t = None
+        if side:
+            ctx = self._side()
+            # everything enqueued so far on the main stream (Gram updates, the zero-fills above) happens-before
+            self.side_stream.wait_stream(torch.cuda.current_stream(self.device))
+        else:
+            t = self._tic()
+        rc = self.lib.fokl_candidates_eval(
+            ctx, G.data_ptr(), ldg, Xty.data_ptr(), flat.ctypes.data, offs.ctypes.data, n_cand,
             ctypes.byref(hyp), None if rc_arr is None else rc_arr.ctypes.data, rng_mode, ctypes.c_uint64(int(seed)),
             None if sid is None else sid.ctypes.data, ptr(var_t), ptr(sf_t), ptr(ev), ptr(betahat), ptr(lamb), ptr(Q),
-            ptr(betas), ptr(sigs), ptr(taus), ptr(stats), ptr(info)))
-        self._toc(t, 'candidates_chain' if chain_any else 'candidates_bic', cands=n_cand, pmax=int(p.max()))
+            ptr(betas), ptr(sigs), ptr(taus), ptr(stats), ptr(info))
+        if rc != 0:
+            msg = self.lib.fokl_last_error(ctx)
+            raise RuntimeError("libfokl_b200 error %d: %s" % (rc, msg.decode() if msg else ''))
+        if not side:
+            self._toc(t, 'candidates_chain' if chain_any else 'candidates_bic', cands=n_cand, pmax=int(p.max()))
         self.gibbs_launch_batches += 1
         res = CandidateResult()
         res.p, res.vec_off, res.mat_off, res.draws = p, vec_off, mat_off, D
-        res.ev = ev.cpu().numpy()
-        res.info = info.cpu().numpy()
         res.stats, res.betas, res.sigs, res.taus = stats, betas, sigs, taus
         res.betahat, res.lamb, res.Q = betahat, lamb, Q
-        # ---- refine near-interpolating / degenerate fits with an N-length residual pass (FR:1551) --------
-        if refine_tol is not None and refine_tol > 0:
-            bad = self.refine_mask(res.ev, p, refine_tol)
-            for c in np.nonzero(bad)[0]:
-                res.ev[c] = self.residual_bic(col_sets[c], betahat[vec_off[c]:vec_off[c] + p[c]])
-        return res
+        return PendingCandidates(self, res, ev, info, col_sets, side, (G, Xty, var_t, sf_t))
 
     def refine_mask(self, ev, p, refine_tol=1e-7):
         """Candidates whose Gram-only BIC is not trustworthy (non-finite, or a residual variance below refine_tol of

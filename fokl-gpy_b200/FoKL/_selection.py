@@ -111,10 +111,13 @@ class PhiloxVariates:
 
 
 def forward_select(engine, hy, m, n_phis, console=True, rng='philox', eager=False, on_substage=None,
-                   recorder=None):
+                   recorder=None, pipeline=None):
     """Run the selection loop on an Engine that has a dataset bound (engine.begin_fit).
 
     hy: dict with a, b, atau, btau, tolerance, total_draws, gimmie, way3, threshav, threshstda, threshstdb, aic.
+    pipeline (default: on for the free-running fast path): evaluate the chains that verify substage s together with
+    the full model of substage s + 1 (see the module docstring of the driver loop below); the result is bit-identical
+    to pipeline=False.
     Returns dict(betas=(D x P) numpy of the chosen model, mtx, evs, n_gibbs, n_batches)."""
     torch = engine.torch
     n = engine.n_global
@@ -131,19 +134,24 @@ def forward_select(engine, hy, m, n_phis, console=True, rng='philox', eager=Fals
     mode = src.mode
     sett = 1 if m == 1 else (3 if hy['way3'] else 2)
     tolerance = hy['tolerance']
+    literal = mode == _lib.RNG_INJECTED or eager
+    if pipeline is None:
+        pipeline = True
+    pipeline = False if (literal or not pipeline) else pipeline      # True, or 'always' (tests: speculate even when
+    #                                                                   the stopping rule is predicted to fire)
+    world = engine.world if engine.dist is not None else 1
 
+    # selection state (FR:1590-1604)
     terms = np.zeros((0, m), dtype=np.int64)     # damtx: row j <-> column j + 1 of X
     evs = []
     best = None            # (betas tensor, mtx)
     last = None
     greater = 0
-    call_id = [0]
-    n_gibbs = 0
-    n_batches = 0
+    cnt = dict(calls=0, gibbs=0, batches=0)      # `gibbs` call index (Philox stream id), gibbs-equivalents, launches
 
     def run(col_sets, chains, ids, refine=True):
-        nonlocal n_batches
-        n_batches += 1
+        """One synchronous batch of spectral evaluations on the current Gram."""
+        cnt['batches'] += 1
         sid = np.asarray(ids, dtype=np.uint64)
         if mode == _lib.RNG_INJECTED:
             # Parity mode.  Eigenvector signs are arbitrary and LAPACK's choice is what pairs each injected
@@ -181,294 +189,461 @@ def forward_select(engine, hy, m, n_phis, console=True, rng='philox', eager=Fals
         return engine.evaluate(col_sets, hyp, rng_mode=mode if any_chain else _lib.RNG_NONE, run_chain=flags,
                                seed=seed, stream_ids=sid, want_betas=any_chain, refine_tol=1e-7 if refine else None)
 
-    ind = 1
-    finished = False
-    while True:
-        part = first_partition(ind, m, sett)
-        while True:
-            vecs = distinct_permutations(part)
-            vm = vecs.shape[0]
-            p_old = engine.P                     # columns of the model accepted so far (incl. intercept)
-            engine.append_terms(vecs)
-            terms = np.concatenate([terms, vecs], axis=0)
-            dam = terms.shape[0]
-            full = list(range(engine.P))
-
-            # ---- full model (FR:1650) -----------------------------------------------------------------------
-            call_id[0] += 1
-            n_gibbs += 1
-            chain_arg = src.draw(len(full)) if mode == _lib.RNG_INJECTED else True
-            res = run([full], [chain_arg], [call_id[0]])
-            ev = float(res.ev[0]) + aic_adj * (dam + 1)
-            st = res.stats_of(0).cpu().numpy()
-            cur_betas = res.betas_of(0)
-            new_cols = np.arange(p_old, p_old + vm)
-            with np.errstate(all='ignore'):
-                bv0 = np.abs(st[0, new_cols])                          # |mean| over rows h1.. (FR:1656)
-                bv1 = st[1, new_cols] / np.abs(st[2, new_cols])        # std / |mean over rows h0..| (FR:1657-58)
-            order = np.argsort(bv0, kind='quicksort')
-            bv0, bv1, cand_cols = bv0[order], bv1[order], new_cols[order]
-            icpt = abs(float(st[2, 0]))                                # |mean(beters[h0:, 0])| (FR:1671)
-
-            # ---- kill proposals (FR:1666-1692) -------------------------------------------------------------------
-            killed = []            # column indices (into current X) accepted for removal
-            evmin = ev
-            cur = 0
-
-            with np.errstate(invalid='ignore'):
-                always = bv1 > hy['threshstdb']                       # proposed whatever the intercept is
-                maybe = bv1 > hy['threshstda']
-
-            def proposals(start, icpt_now):
-                with np.errstate(invalid='ignore'):
-                    mask = always | (maybe & (bv0 < hy['threshav'] * icpt_now))
-                return (np.nonzero(mask[start:])[0] + start).tolist()
-
-            if mode == _lib.RNG_INJECTED or eager:
-                # literal order: one `gibbs`-equivalent evaluation (eig + chain) per proposal.  In parity mode the
-                # numpy stream is consumed test by test; in eager mode all proposals of a batch run side by side.
-                while cur < vm:
-                    props = proposals(cur, icpt)
-                    if not props:
-                        break
-                    sets = []
-                    for i in props:
-                        drop = set(killed) | {int(cand_cols[i])}
-                        sets.append([c for c in full if c not in drop])
-                    ids = [call_id[0] + r + 1 for r in range(len(props))]
-                    accepted = None
-                    if mode == _lib.RNG_INJECTED:
-                        for r, i in enumerate(props):
-                            call_id[0] += 1
-                            n_gibbs += 1
-                            rr = run([sets[r]], [src.draw(len(sets[r]))], [ids[r]])
-                            evt = float(rr.ev[0]) + aic_adj * len(sets[r])
-                            if evt < evmin:
-                                accepted = (i, evt, rr, 0)
-                                break
-                    else:
-                        rr = run(sets, [True] * len(sets), ids)
-                        for r, i in enumerate(props):
-                            evt = float(rr.ev[r]) + aic_adj * len(sets[r])
-                            if evt < evmin:
-                                accepted = (i, evt, rr, r)
-                                break
-                        tested = (props.index(accepted[0]) + 1) if accepted else len(props)
-                        call_id[0] += tested
-                        n_gibbs += tested
-                    if accepted is None:
-                        break
-                    i, evt, rr, slot = accepted
-                    killed.append(int(cand_cols[i]))
-                    evmin = evt
-                    cur_betas = rr.betas_of(slot).clone()
-                    icpt = abs(float(rr.stats_of(slot)[2, 0].item()))
-                    cur = i + 1
-            else:
-                # fast path: the whole kill loop runs on the device in one launch (fokl_kill_loop: sweep-operator
-                # inverse of the model's Gram, one O(p^2) reverse sweep per accepted kill).  The chains of the accepted
-                # models -- which only feed later rounds' threshold through |mean intercept| (FR:1671) and the final
-                # draws (FR:1690) -- are run afterwards as one batch, only for the rounds whose remaining proposals can
-                # depend on that threshold, and every such round is re-checked against its true chain (the loop is
-                # re-run from the first round that differs), so the outcome is exactly that of the sequential loop.
-                # Round k's chain matters only through the threshold it sets for the candidates examined before the next
-                # acceptance, i.e. indices (i_k, i_{k+1}] of the sorted list (to the end for the last round): if none of
-                # them is threshold-dependent (threshstda < bv1 <= threshstdb) the chain of round k is never looked at.
-                with np.errstate(invalid='ignore'):
-                    bv1_sens = (bv1 > hy['threshstda']) & ~(bv1 > hy['threshstdb'])
-                sens_cum = np.concatenate([[0], np.cumsum(bv1_sens)])      # threshold-dependent candidates in [0, j)
-
-                def span(k_):
-                    return rounds[k_]['i'] + 1, (vm if k_ == len(rounds) - 1 else rounds[k_ + 1]['i'] + 1)
-
-                def prop_mask(icpt_now):
-                    with np.errstate(invalid='ignore'):
-                        return always | (maybe & (bv0 < hy['threshav'] * icpt_now))
-                state = dict(killed=[], evmin=evmin, cur=0, icpt=icpt, calls=call_id[0], gibbs=n_gibbs)
-                rounds = []        # accepted kills: dict(i, cols, stream, icpt_used, gibbs_after [, icpt_true, ev_true])
-                fallback = False
-                while True:
-                    if state['cur'] < vm and proposals(state['cur'], state['icpt']):
-                        # column bookkeeping on numpy masks (the lists are up to 160 models x 220 columns per substage)
-                        alive = np.ones(len(full), dtype=bool)
-                        alive[np.asarray(state['killed'], dtype=np.int64)] = False
-                        model = np.nonzero(alive)[0].astype(np.int32)
-                        where = np.ones(len(full), dtype=np.int32)            # killed candidates: any valid position
-                        where[model] = np.arange(len(model), dtype=np.int32)
-                        pos = where[cand_cols]
-                        r = engine.kill_loop(model, pos, bv0, bv1, hyp, hy['threshav'], hy['threshstda'],
-                                             hy['threshstdb'], state['icpt'], state['evmin'], aic_adj, state['cur'])
-                        n_batches += 1
-                        if r['bad']:
-                            fallback = True
-                            break
-                        for k_ in range(r['n_acc']):
-                            i = int(r['acc'][k_])
-                            alive[int(cand_cols[i])] = False
-                            cols_k = np.nonzero(alive)[0].astype(np.int32)
-                            rounds.append(dict(i=i, cols=cols_k, stream=state['calls'] + int(r['calls'][k_]),
-                                               gibbs_after=state['gibbs'] + int(r['calls'][k_]),
-                                               ev_dev=float(r['ev'][k_]), icpt_used=state['icpt']))
-                        state['calls'] += r['tested']
-                        state['gibbs'] += r['tested']
-                        state['killed'] = state['killed'] + [int(cand_cols[int(i)]) for i in r['acc']]
-                        if r['n_acc']:
-                            state['evmin'] = float(r['ev'][-1])
-                            state['cur'] = int(r['acc'][-1]) + 1
-                    if not rounds:
-                        break
-                    # chains of the accepted models that matter: rounds with threshold-dependent proposals left, + last
-                    todo = []
-                    for k_, rd in enumerate(rounds):
-                        lo_, hi_ = span(k_)
-                        if 'icpt_true' not in rd and (k_ == len(rounds) - 1 or sens_cum[hi_] > sens_cum[lo_]):
-                            todo.append(rd)
-                    if todo:
-                        # The models of a batch are independent: with several ranks each evaluates every world-th one
-                        # (all ranks hold the full Gram) and the two scalars per model that drive the loop are summed
-                        # into place by one allreduce, so every rank takes the same decisions.
-                        world = engine.world if engine.dist is not None else 1
-                        mine = list(range(engine.rank, len(todo), world)) if world > 1 else list(range(len(todo)))
-                        vals = np.zeros((len(todo) + 1, 2))
-
-                        def chains_of(which, refine):
-                            rr = run([todo[i]['cols'] for i in which], [True] * len(which),
-                                     [todo[i]['stream'] for i in which], refine=refine)
-                            stats_h = rr.stats.cpu().numpy()      # one read-back for the whole batch
-                            for slot, i in enumerate(which):
-                                # mean(beters[h0:, 0]) of this model: row 2, column 0 of its 3 x p statistics block
-                                vals[i, 0] = abs(float(stats_h[3 * rr.vec_off[slot] + 2 * rr.p[slot]]))
-                                vals[i, 1] = float(rr.ev[slot]) + aic_adj * len(todo[i]['cols'])
-                                todo[i]['rr'], todo[i]['slot'] = rr, slot
-                            return rr
-
-                        if world > 1:
-                            if mine:
-                                rr_ = chains_of(mine, refine=False)
-                                vals[len(todo), 0] = float(np.any(engine.refine_mask(rr_.ev, rr_.p)))
-                            t = torch.from_numpy(vals).to(engine.device)
-                            engine._allreduce(t)
-                            vals = t.cpu().numpy()
-                            for i, rd in enumerate(todo):
-                                rd['owner'] = i % world
-                            if vals[len(todo), 0] > 0:
-                                # some model needs the N-length residual pass (a collective): evaluate the batch replicated
-                                vals = np.zeros((len(todo) + 1, 2))
-                                chains_of(list(range(len(todo))), refine=True)
-                                for rd in todo:
-                                    rd['owner'] = -1
-                        else:
-                            chains_of(mine, refine=True)
-                        for i, rd in enumerate(todo):
-                            rd['icpt_true'], rd['ev_true'] = float(vals[i, 0]), float(vals[i, 1])
-                    redo = None
-                    for k_, rd in enumerate(rounds):
-                        if 'icpt_true' not in rd or rd['icpt_true'] == rd['icpt_used']:
-                            continue
-                        lo_, hi_ = span(k_)
-                        if not np.array_equal(prop_mask(rd['icpt_true'])[lo_:hi_], prop_mask(rd['icpt_used'])[lo_:hi_]):
-                            redo = k_
-                            break
-                    if redo is None:
-                        last_rd = rounds[-1]
-                        owner = last_rd.get('owner', -1)          # -1: every rank ran this model's chain itself
-                        if owner < 0 or owner == engine.rank:
-                            cur_betas = last_rd['rr'].betas_of(last_rd['slot']).clone()
-                        if owner >= 0:
-                            # the accepted model's draws live on the rank that ran its chain
-                            if owner != engine.rank:
-                                cur_betas = torch.empty((D, len(last_rd['cols'])), dtype=torch.float64,
-                                                        device=engine.device)
-                            g = engine.group
-                            src = engine.dist.get_global_rank(g, owner) if g is not None else owner
-                            engine.dist.broadcast(cur_betas, src=src, group=g)
-                        icpt = last_rd['icpt_true']
-                        evmin = last_rd['ev_true']        # report the spectral-path BIC of the accepted model
-                        killed = list(state['killed'])
-                        for rd in rounds:
-                            rd.pop('rr', None)
-                        break
-                    # roll back to just after round `redo`, now with its true threshold, and continue from there
-                    rd = rounds[redo]
-                    rounds = rounds[:redo + 1]
-                    rd['icpt_used'] = rd['icpt_true']
-                    state = dict(killed=sorted(set(full) - set(int(c_) for c_ in rd['cols'])), evmin=rd['ev_true'],
-                                 cur=rd['i'] + 1, icpt=rd['icpt_true'], calls=rd['stream'], gibbs=rd['gibbs_after'])
-                if fallback:
-                    # Gram not numerically positive definite (p >= N regimes): literal loop, one spectral evaluation
-                    # (eig + chain) per proposal, proposals of a round side by side
-                    killed, evmin, cur = [], ev, 0
-                    while cur < vm:
-                        props = proposals(cur, icpt)
-                        if not props:
-                            break
-                        sets = []
-                        for i in props:
-                            drop = set(killed) | {int(cand_cols[i])}
-                            sets.append([c for c in full if c not in drop])
-                        ids = [call_id[0] + r_ + 1 for r_ in range(len(props))]
-                        rr = run(sets, [True] * len(sets), ids)
-                        accepted = None
-                        for r_, i in enumerate(props):
-                            evt = float(rr.ev[r_]) + aic_adj * len(sets[r_])
-                            if evt < evmin:
-                                accepted = (i, evt, rr, r_)
-                                break
-                        tested = (props.index(accepted[0]) + 1) if accepted else len(props)
-                        call_id[0] += tested
-                        n_gibbs += tested
-                        if accepted is None:
-                            break
-                        i, evt, rr, slot = accepted
-                        killed.append(int(cand_cols[i]))
-                        evmin = evt
-                        cur_betas = rr.betas_of(slot).clone()
-                        icpt = abs(float(rr.stats_of(slot)[2, 0].item()))
-                        cur = i + 1
-                else:
-                    call_id[0] = state['calls']
-                    n_gibbs = state['gibbs']
-                    if not rounds:
-                        killed = []
-
-            # ---- drop accepted kills (FR:1691-1695) ---------------------------------------------------------------
-            if killed:
-                keep = [c for c in full if c not in set(killed)]
-                engine.compact(keep)
-                terms = np.delete(terms, [c - 1 for c in killed], axis=0)
-            ev = evmin
-            last = (cur_betas, terms.copy())
-            if console:
-                print([ind, float(ev)])
-            if on_substage is not None:
-                on_substage(ind, ev, terms)
-
-            # ---- bookkeeping (FR:1701-1721) -----------------------------------------------------------------------
-            if evs:
-                if ev < np.min(evs):
-                    best = last
-                    greater = 1
-                    evs.append(ev)
-                elif greater < tolerance:
-                    greater += 1
-                    evs.append(ev)
-                else:
-                    finished = True
-                    evs.append(ev)
-                    break
-            else:
-                greater += 1
-                best = last
-                evs.append(ev)
-            if not next_partition(part, m, hy['way3']):
-                break
-        if finished:
-            break
+    # ---- the partition walk (FR:1605-1616, 1722-1740) as a pure function of (ind, part) --------------------------
+    def walk_next(ind, part):
+        part = list(part)
+        if next_partition(part, m, hy['way3']):
+            return ind, part
         ind += 1
         if ind > n_phis:
+            return None
+        return ind, first_partition(ind, m, sett)
+
+    # ---- phase A: append the new terms' columns (K1 + K2) -----------------------------------------------------------
+    def open_substage(ind, part, terms_in):
+        vecs = distinct_permutations(part)
+        p_old = engine.P                     # columns of the model accepted so far (incl. intercept)
+        engine.append_terms(vecs)
+        return dict(ind=ind, part=list(part), vecs=vecs, vm=vecs.shape[0], p_old=p_old,
+                    terms=np.concatenate([terms_in, vecs], axis=0), full=list(range(engine.P)))
+
+    # ---- phase B: the full model (FR:1650), evaluated as (launch, finish) so that other work can ride along ------------
+    def full_launch(S):
+        cnt['calls'] += 1
+        cnt['gibbs'] += 1
+        S['full_id'] = cnt['calls']
+        if literal:
+            return None
+        cnt['batches'] += 1
+        return engine.evaluate_launch([S['full']], hyp, rng_mode=mode, run_chain=np.ones(1, dtype=np.uint8), seed=seed,
+                                      stream_ids=np.asarray([S['full_id']], dtype=np.uint64), want_betas=True)
+
+    def full_finish(S, handle):
+        nonlocal terms
+        full = S['full']
+        if handle is None:
+            terms = S['terms']               # the parity recorder keys candidates by their term rows
+            chain_arg = src.draw(len(full)) if mode == _lib.RNG_INJECTED else True
+            res = run([full], [chain_arg], [S['full_id']])
+        else:
+            res = handle.finish(1e-7)
+        S['ev'] = float(res.ev[0]) + aic_adj * (S['terms'].shape[0] + 1)
+        # a (nearly) interpolating full model: its BIC came from the residual pass because the Gram-only form has lost
+        # its digits to cancellation (Engine.refine_mask) -- the device kill loop scores with the same Gram-only form,
+        # so this substage takes the literal path
+        S['refined'] = bool(getattr(res, 'refined', np.zeros(1, dtype=bool))[0])
+        st = res.stats_of(0).cpu().numpy()
+        S['betas'] = res.betas_of(0)
+        new_cols = np.arange(S['p_old'], S['p_old'] + S['vm'])
+        with np.errstate(all='ignore'):
+            bv0 = np.abs(st[0, new_cols])                          # |mean| over rows h1.. (FR:1656)
+            bv1 = st[1, new_cols] / np.abs(st[2, new_cols])        # std / |mean over rows h0..| (FR:1657-58)
+        order = np.argsort(bv0, kind='quicksort')
+        S['bv0'], S['bv1'], S['cand_cols'] = bv0[order], bv1[order], new_cols[order]
+        S['icpt'] = abs(float(st[2, 0]))                           # |mean(beters[h0:, 0])| (FR:1671)
+        with np.errstate(invalid='ignore'):
+            S['always'] = S['bv1'] > hy['threshstdb']              # proposed whatever the intercept is
+            S['maybe'] = S['bv1'] > hy['threshstda']
+
+    def prop_mask(S, icpt_now):
+        with np.errstate(invalid='ignore'):
+            return S['always'] | (S['maybe'] & (S['bv0'] < hy['threshav'] * icpt_now))
+
+    def proposals(S, start, icpt_now):
+        return (np.nonzero(prop_mask(S, icpt_now)[start:])[0] + start).tolist()
+
+    # ---- phase C, literal order (FR:1666-1692): one `gibbs`-equivalent evaluation (eig + chain) per proposal ------------
+    def kill_literal(S, parity):
+        """In parity mode the numpy stream is consumed test by test; otherwise all proposals of a round run side by
+        side (also the fall-back of the fast path when the Gram is not numerically positive definite)."""
+        full, cand_cols, vm = S['full'], S['cand_cols'], S['vm']
+        killed, evmin, cur, icpt, cur_betas = [], S['ev'], 0, S['icpt'], S['betas']
+        while cur < vm:
+            props = proposals(S, cur, icpt)
+            if not props:
+                break
+            sets = []
+            for i in props:
+                drop = set(killed) | {int(cand_cols[i])}
+                sets.append([c for c in full if c not in drop])
+            ids = [cnt['calls'] + r + 1 for r in range(len(props))]
+            accepted = None
+            if parity:
+                for r, i in enumerate(props):
+                    cnt['calls'] += 1
+                    cnt['gibbs'] += 1
+                    rr = run([sets[r]], [src.draw(len(sets[r]))], [ids[r]])
+                    evt = float(rr.ev[0]) + aic_adj * len(sets[r])
+                    if evt < evmin:
+                        accepted = (i, evt, rr, 0)
+                        break
+            else:
+                rr = run(sets, [True] * len(sets), ids)
+                for r, i in enumerate(props):
+                    evt = float(rr.ev[r]) + aic_adj * len(sets[r])
+                    if evt < evmin:
+                        accepted = (i, evt, rr, r)
+                        break
+                tested = (props.index(accepted[0]) + 1) if accepted else len(props)
+                cnt['calls'] += tested
+                cnt['gibbs'] += tested
+            if accepted is None:
+                break
+            i, evt, rr, slot = accepted
+            killed.append(int(cand_cols[i]))
+            evmin = evt
+            cur_betas = rr.betas_of(slot).clone()
+            icpt = abs(float(rr.stats_of(slot)[2, 0].item()))
+            cur = i + 1
+        return dict(killed=killed, evmin=evmin, betas=cur_betas, calls=cnt['calls'], gibbs=cnt['gibbs'])
+
+    # ---- chains of accepted models: launch / collect ----------------------------------------------------------------
+    # The models of a batch are independent: with several ranks each evaluates every world-th one (all ranks hold the
+    # full Gram) and the two scalars per model that drive the loop are summed into place by one allreduce, so every
+    # rank takes the same decisions.
+    def chains_launch(todo, which, gram=None, side=False):
+        if not which:
+            return None
+        cnt['batches'] += 1
+        return engine.evaluate_launch([todo[i]['cols'] for i in which], hyp, rng_mode=mode,
+                                      run_chain=np.ones(len(which), dtype=np.uint8), seed=seed,
+                                      stream_ids=np.asarray([todo[i]['stream'] for i in which], dtype=np.uint64),
+                                      want_betas=True, gram=gram, side=side)
+
+    def chains_collect(todo, which, handle, vals, refine):
+        """Fill vals[i] = (|mean intercept|, BIC) and todo[i]['rr' / 'slot'] for the models `which`; returns True if a
+        model's Gram-only BIC is not trustworthy and refine is off (see Engine.refine_mask)."""
+        if handle is None:
+            return False
+        rr = handle.finish(1e-7 if refine else None)
+        stats_h = rr.stats.cpu().numpy()      # one read-back for the whole batch
+        for slot, i in enumerate(which):
+            # mean(beters[h0:, 0]) of this model: row 2, column 0 of its 3 x p statistics block
+            vals[i, 0] = abs(float(stats_h[3 * rr.vec_off[slot] + 2 * rr.p[slot]]))
+            vals[i, 1] = float(rr.ev[slot]) + aic_adj * len(todo[i]['cols'])
+            todo[i]['rr'], todo[i]['slot'] = rr, slot
+        return (not refine) and bool(np.any(engine.refine_mask(rr.ev, rr.p)))
+
+    def my_share(todo):
+        return list(range(engine.rank, len(todo), world)) if world > 1 else list(range(len(todo)))
+
+    def chains_reduce(todo, vals, need_refine):
+        """All ranks: sum the per-model scalars into place; returns True if any rank flagged a model for refinement."""
+        if world > 1:
+            vals[len(todo), 0] = float(need_refine)
+            t = torch.from_numpy(vals).to(engine.device)
+            engine._allreduce(t)
+            vals[:] = t.cpu().numpy()
+            for i, rd in enumerate(todo):
+                rd['owner'] = i % world
+            need_refine = vals[len(todo), 0] > 0
+        return bool(need_refine)
+
+    def chains_now(todo):
+        """Synchronous form: evaluate `todo` on the current Gram (X still holds every column: refinement possible)."""
+        vals = np.zeros((len(todo) + 1, 2))
+        mine = my_share(todo)
+        if world > 1:
+            need = chains_collect(todo, mine, chains_launch(todo, mine), vals, refine=False)
+            if chains_reduce(todo, vals, need):
+                # some model needs the N-length residual pass (a collective): evaluate the batch replicated
+                vals = np.zeros((len(todo) + 1, 2))
+                everything = list(range(len(todo)))
+                chains_collect(todo, everything, chains_launch(todo, everything), vals, refine=True)
+                for rd in todo:
+                    rd['owner'] = -1
+        else:
+            chains_collect(todo, mine, chains_launch(todo, mine), vals, refine=True)
+        for i, rd in enumerate(todo):
+            rd['icpt_true'], rd['ev_true'] = float(vals[i, 0]), float(vals[i, 1])
+
+    # ---- phase C, fast path: a generator that yields when it needs chains --------------------------------------------
+    def kill_fast(S):
+        """The whole kill loop runs on the device in one launch (fokl_kill_loop: sweep-operator inverse of the model's
+        Gram, one O(p^2) reverse sweep per accepted kill).  The chains of the accepted models -- which only feed later
+        rounds' threshold through |mean intercept| (FR:1671) and the final draws (FR:1690) -- are run afterwards as one
+        batch, only for the rounds whose remaining proposals can depend on that threshold, and every such round is
+        re-checked against its true chain (the loop is re-run from the first round that differs), so the outcome is
+        exactly that of the sequential loop.  Round k's chain matters only through the threshold it sets for the
+        candidates examined before the next acceptance, i.e. indices (i_k, i_{k+1}] of the sorted list (to the end for
+        the last round): if none of them is threshold-dependent (threshstda < bv1 <= threshstdb) the chain of round k
+        is never looked at.
+
+        Protocol: `yield (todo, outlook)` asks the driver for the chains of `todo` (it fills icpt_true / ev_true / rr /
+        slot / owner of every entry) and is answered with 'done' -- or with 'speculated' if the driver has, on the
+        strength of `outlook` (the outcome if every check passes; None after the first request), already compacted the
+        engine and moved on; then a failed check makes the generator `yield 'rollback'` (the driver restores the
+        substage's columns and Gram) before it continues.  Returns the substage's outcome."""
+        full, cand_cols, vm, bv0, bv1 = S['full'], S['cand_cols'], S['vm'], S['bv0'], S['bv1']
+        with np.errstate(invalid='ignore'):
+            bv1_sens = (bv1 > hy['threshstda']) & ~(bv1 > hy['threshstdb'])
+        sens_cum = np.concatenate([[0], np.cumsum(bv1_sens)])      # threshold-dependent candidates in [0, j)
+        bv0_finite = bv0[:int(np.count_nonzero(~np.isnan(bv0)))]   # argsort puts NaN last
+
+        def span(k_):
+            return rounds[k_]['i'] + 1, (vm if k_ == len(rounds) - 1 else rounds[k_ + 1]['i'] + 1)
+
+        state = dict(killed=[], evmin=S['ev'], cur=0, icpt=S['icpt'], calls=cnt['calls'], gibbs=cnt['gibbs'])
+        rounds = []        # accepted kills: dict(i, cols, stream, icpt_used, gibbs_after [, icpt_true, ev_true])
+        first_request = True
+        while True:
+            if state['cur'] < vm and proposals(S, state['cur'], state['icpt']):
+                # column bookkeeping on numpy masks (the lists are up to 160 models x 220 columns per substage)
+                alive = np.ones(len(full), dtype=bool)
+                alive[np.asarray(state['killed'], dtype=np.int64)] = False
+                model = np.nonzero(alive)[0].astype(np.int32)
+                where = np.ones(len(full), dtype=np.int32)            # killed candidates: any valid position
+                where[model] = np.arange(len(model), dtype=np.int32)
+                pos = where[cand_cols]
+                r = engine.kill_loop(model, pos, bv0, bv1, hyp, hy['threshav'], hy['threshstda'],
+                                     hy['threshstdb'], state['icpt'], state['evmin'], aic_adj, state['cur'])
+                cnt['batches'] += 1
+                if r['bad']:
+                    # Gram not numerically positive definite (p >= N regimes): literal loop, one spectral evaluation
+                    # (eig + chain) per proposal, proposals of a round side by side.  (Only ever seen on the first
+                    # launch of a substage: a later one works on a principal sub-matrix of a factorisable Gram.)
+                    return kill_literal(S, parity=False)
+                for k_ in range(r['n_acc']):
+                    i = int(r['acc'][k_])
+                    alive[int(cand_cols[i])] = False
+                    cols_k = np.nonzero(alive)[0].astype(np.int32)
+                    rounds.append(dict(i=i, cols=cols_k, stream=state['calls'] + int(r['calls'][k_]),
+                                       gibbs_after=state['gibbs'] + int(r['calls'][k_]),
+                                       ev_dev=float(r['ev'][k_]), icpt_used=state['icpt']))
+                state['calls'] += r['tested']
+                state['gibbs'] += r['tested']
+                state['killed'] = state['killed'] + [int(cand_cols[int(i)]) for i in r['acc']]
+                if r['n_acc']:
+                    state['evmin'] = float(r['ev'][-1])
+                    state['cur'] = int(r['acc'][-1]) + 1
+            if not rounds:
+                return dict(killed=[], evmin=S['ev'], betas=S['betas'], calls=state['calls'], gibbs=state['gibbs'])
+            # chains of the accepted models that matter: rounds with threshold-dependent proposals left, + last
+            todo = []
+            for k_, rd in enumerate(rounds):
+                lo_, hi_ = span(k_)
+                if 'icpt_true' not in rd and (k_ == len(rounds) - 1 or sens_cum[hi_] > sens_cum[lo_]):
+                    todo.append(rd)
+            speculated = False
+            if todo:
+                outlook = dict(killed=list(state['killed']), ev=state['evmin'], calls=state['calls'],
+                               gibbs=state['gibbs']) if first_request else None
+                answer = yield (todo, outlook)
+                first_request = False
+                speculated = answer == 'speculated'
+            def first_changed_round():
+                """First round whose true chain proposes other candidates in its span than the speculated threshold
+                did.  Only the threshold-dependent candidates can differ, and only where `bv0 < threshav * icpt`
+                flips; bv0 is sorted ascending, so those are a contiguous index range (NaN sorts last and compares
+                false either way)."""
+                ks = [k_ for k_, rd in enumerate(rounds) if 'icpt_true' in rd and rd['icpt_true'] != rd['icpt_used']]
+                if not ks:
+                    return None
+                t0 = hy['threshav'] * np.array([rounds[k_]['icpt_used'] for k_ in ks])
+                t1 = hy['threshav'] * np.array([rounds[k_]['icpt_true'] for k_ in ks])
+                if np.isnan(t0).any() or np.isnan(t1).any():
+                    for k_ in ks:
+                        lo_, hi_ = span(k_)
+                        if not np.array_equal(prop_mask(S, rounds[k_]['icpt_true'])[lo_:hi_],
+                                              prop_mask(S, rounds[k_]['icpt_used'])[lo_:hi_]):
+                            return k_
+                    return None
+                lo_ = np.array([rounds[k_]['i'] + 1 for k_ in ks])
+                hi_ = np.array([vm if k_ == len(rounds) - 1 else rounds[k_ + 1]['i'] + 1 for k_ in ks])
+                a_ = np.maximum(lo_, np.searchsorted(bv0_finite, np.minimum(t0, t1), side='left'))
+                b_ = np.maximum(a_, np.minimum(hi_, np.searchsorted(bv0_finite, np.maximum(t0, t1), side='left')))
+                changed = np.nonzero(sens_cum[b_] > sens_cum[a_])[0]
+                return ks[int(changed[0])] if len(changed) else None
+
+            redo = first_changed_round()
+            unrefined = any(rd.get('unrefined') for rd in todo)
+            if speculated and (redo is not None or unrefined):
+                yield 'rollback'
+                if unrefined:
+                    # a Gram-only BIC of the batch was not trustworthy: now that X holds the columns again, redo the
+                    # batch with the residual pass and check again
+                    for rd in todo:
+                        for key in ('icpt_true', 'ev_true', 'rr', 'slot', 'owner', 'unrefined'):
+                            rd.pop(key, None)
+                    yield (todo, None)
+                    redo = first_changed_round()
+            if redo is None:
+                last_rd = rounds[-1]
+                owner = last_rd.get('owner', -1)          # -1: every rank ran this model's chain itself
+                cur_betas = None
+                if owner < 0 or owner == engine.rank:
+                    cur_betas = last_rd['rr'].betas_of(last_rd['slot']).clone()
+                if owner >= 0:
+                    # the accepted model's draws live on the rank that ran its chain
+                    if owner != engine.rank:
+                        cur_betas = torch.empty((D, len(last_rd['cols'])), dtype=torch.float64, device=engine.device)
+                    g = engine.group
+                    src_rank = engine.dist.get_global_rank(g, owner) if g is not None else owner
+                    engine.dist.broadcast(cur_betas, src=src_rank, group=g)
+                for rd in rounds:
+                    rd.pop('rr', None)
+                # report the spectral-path BIC of the accepted model
+                return dict(killed=list(state['killed']), evmin=last_rd['ev_true'], betas=cur_betas,
+                            calls=state['calls'], gibbs=state['gibbs'])
+            # roll back to just after round `redo`, now with its true threshold, and continue from there
+            rd = rounds[redo]
+            rounds = rounds[:redo + 1]
+            rd['icpt_used'] = rd['icpt_true']
+            state = dict(killed=sorted(set(full) - set(int(c_) for c_ in rd['cols'])), evmin=rd['ev_true'],
+                         cur=rd['i'] + 1, icpt=rd['icpt_true'], calls=rd['stream'], gibbs=rd['gibbs_after'])
+
+    def drive(gen, request):
+        """Answer a kill_fast generator synchronously until it returns its outcome."""
+        while True:
+            todo, _ = request
+            chains_now(todo)
+            try:
+                request = gen.send('done')
+            except StopIteration as stop:
+                return stop.value
+
+    # ---- phase D: drop the accepted kills (FR:1691-1695) and the bookkeeping of FR:1701-1721 ----------------------------
+    def close_substage(S, outcome, compacted):
+        """Returns True when the fit is finished.  compacted: the engine and `terms` already reflect outcome['killed']
+        (the driver speculated on it)."""
+        nonlocal terms, last, best, greater
+        killed = outcome['killed']
+        if compacted:
+            terms_s = S['terms_final']
+        else:
+            terms_s = S['terms']
+            if killed:
+                keep = [c for c in S['full'] if c not in set(killed)]
+                engine.compact(keep)
+                terms_s = np.delete(terms_s, [c - 1 for c in killed], axis=0)
+            terms = terms_s
+        cnt['calls'], cnt['gibbs'] = outcome['calls'], outcome['gibbs']
+        ev = outcome['evmin']
+        last = (outcome['betas'], terms_s.copy())
+        if console:
+            print([S['ind'], float(ev)])
+        if on_substage is not None:
+            on_substage(S['ind'], ev, terms_s)
+        if evs:
+            if ev < np.min(evs):
+                best = last
+                greater = 1
+                evs.append(ev)
+            elif greater < tolerance:
+                greater += 1
+                evs.append(ev)
+            else:
+                evs.append(ev)
+                return True
+        else:
+            greater += 1
+            best = last
+            evs.append(ev)
+        return False
+
+    def will_finish(ev_outlook):
+        """The stopping rule of FR:1701-1721 applied to a BIC that is not final yet (a prediction only)."""
+        return bool(evs) and not (ev_outlook < np.min(evs)) and greater >= tolerance
+
+    # ---- driver ------------------------------------------------------------------------------------------------------------
+    # Sequential form, per substage s:  A(s) append -> B(s) full model -> C(s) kill loop [-> chains of the accepted
+    # models -> checks] -> D(s) compact + bookkeeping.  B and the chains of C are latency-bound (one eigensolver + one
+    # 2000-draw chain each) and leave the device almost idle, so the pipelined form runs the chains of C(s) *together
+    # with* B(s + 1): after the kill loop it assumes the checks will pass (they almost always do), compacts, appends the
+    # terms of s + 1, and launches the full model of s + 1 on the main context and the chains of s -- which index the
+    # Gram as it was before the compaction -- on the side context.  Every decision is then taken from the true chains
+    # exactly as in the sequential form; if a check fails (or the fit turns out to be finished) the speculative work
+    # is discarded and the substage's columns are rebuilt.  Philox streams are keyed by the `gibbs` call index, so
+    # both forms draw the same variates and give bit-identical fits.
+    step = (1, first_partition(1, m, sett))
+    S = open_substage(step[0], step[1], terms)
+    carry = None            # dict(S=previous substage, gen=its generator, todo, gram=its Gram before compaction, cnt0)
+    while True:
+        # ---- B(s) [+ chains of s - 1] ----
+        if carry is not None:
+            # the side batch goes first: its stream waits for what the main stream holds *now* (K1 + K2 of s, which
+            # it must not share the SMs with), not for the full model enqueued next
+            todo, vals, mine = carry['todo'], np.zeros((len(carry['todo']) + 1, 2)), my_share(carry['todo'])
+            side = chains_launch(todo, mine, gram=carry['gram'], side=True)
+        handle = full_launch(S)
+        full_finish(S, handle)
+        if carry is not None:
+            need = chains_collect(todo, mine, side, vals, refine=False)
+            need = chains_reduce(todo, vals, need)
+            for i, rd in enumerate(todo):
+                rd['icpt_true'], rd['ev_true'] = float(vals[i, 0]), float(vals[i, 1])
+                if need:
+                    rd['unrefined'] = True
+            prev, gen = carry['S'], carry['gen']
+            carry_cnt_after = dict(cnt)
+            try:
+                request = gen.send('speculated')
+                outcome = None
+            except StopIteration as stop:
+                request, outcome = None, stop.value
+            if outcome is None:
+                # a check failed: rebuild substage s - 1 as it was before the speculation and finish it synchronously
+                assert request == 'rollback'
+                engine.truncate(prev['p_old'])
+                engine.append_terms(prev['vecs'])
+                cnt['calls'], cnt['gibbs'] = carry['cnt0']['calls'], carry['cnt0']['gibbs']
+                terms = prev['terms']
+                try:
+                    request = gen.send('done')
+                    outcome = drive(gen, request)
+                except StopIteration as stop:
+                    outcome = stop.value
+                carry = None
+                S = prev
+                finished = close_substage(S, outcome, compacted=False)
+                step = walk_next(S['ind'], S['part'])
+                if finished or step is None:
+                    break
+                S = open_substage(step[0], step[1], terms)
+                continue
+            carry = None
+            saved = dict(cnt)
+            finished = close_substage(prev, outcome, compacted=True)
+            cnt.update(calls=saved['calls'], gibbs=saved['gibbs'])      # the speculative substage's counters stand
+            if finished:
+                engine.truncate(S['p_old'])                              # drop the speculative columns of s
+                cnt['calls'], cnt['gibbs'] = outcome['calls'], outcome['gibbs']
+                break
+        # ---- C(s) ----
+        if literal or S['refined']:
+            outcome = kill_literal(S, parity=(mode == _lib.RNG_INJECTED))
+            request = None
+        else:
+            gen = kill_fast(S)
+            try:
+                request = next(gen)
+                outcome = None
+            except StopIteration as stop:
+                request, outcome = None, stop.value
+        step = walk_next(S['ind'], S['part'])
+        if request is not None:
+            todo, outlook = request
+            if pipeline and step is not None and outlook is not None and \
+                    (pipeline == 'always' or not will_finish(outlook['ev'])):
+                # speculate on `outlook`: D(s) without its bookkeeping, then A(s + 1)
+                gram = engine.gram_state()
+                cnt0 = dict(cnt)
+                killed = outlook['killed']
+                keep = [c for c in S['full'] if c not in set(killed)]
+                engine.compact(keep)
+                S['terms_final'] = np.delete(S['terms'], [c - 1 for c in killed], axis=0)
+                terms = S['terms_final']
+                cnt['calls'], cnt['gibbs'] = outlook['calls'], outlook['gibbs']
+                carry = dict(S=S, gen=gen, todo=todo, gram=gram, cnt0=cnt0)
+                S = open_substage(step[0], step[1], terms)
+                continue
+            outcome = drive(gen, request)
+        finished = close_substage(S, outcome, compacted=False)
+        if finished or step is None:
             break
+        S = open_substage(step[0], step[1], terms)
 
     chosen = last if hy['gimmie'] else best
     betas = chosen[0].cpu().numpy()
     return dict(betas=betas, mtx=chosen[1].astype(np.float64), evs=np.array(evs, dtype=np.float64),
-                n_gibbs=n_gibbs, n_batches=n_batches)
+                n_gibbs=cnt['gibbs'], n_batches=cnt['batches'])

@@ -96,7 +96,40 @@ class MockEngine:
         res.betas = torch.from_numpy(np.concatenate(betas))
         res.betahat = torch.from_numpy(np.concatenate(betahat))
         res.sigs = res.taus = res.lamb = res.Q = None
+        self._refine(res, col_sets, refine_tol, gram)
         return res
+
+    def _refine(self, res, col_sets, refine_tol, gram):
+        res.refined = np.zeros(len(res.ev), dtype=bool)
+        if refine_tol is not None and refine_tol > 0:
+            bad = self.refine_mask(res.ev, res.p, refine_tol)
+            res.refined = bad
+            assert gram is None or not np.any(bad), 'refinement needs the columns in X'
+            for c in np.nonzero(bad)[0]:
+                self.calls.append(('refine', len(col_sets[c])))
+                res.ev[c] = self.residual_bic(col_sets[c], res.betahat[res.vec_off[c]:res.vec_off[c] + res.p[c]])
+
+    def residual_bic(self, cols, betahat):
+        r = self.y - self.X[:, np.asarray(cols, dtype=np.int64)] @ betahat.numpy()
+        n = float(self.n_global)
+        siglik = (r @ r) / n - (r.sum() / n) ** 2
+        with np.errstate(all='ignore'):
+            lik = -(n / 2) * np.log(siglik) - (n - 1) / 2
+        return len(cols) * np.log(n) - 2 * lik
+
+    def evaluate_launch(self, col_sets, hyp, gram=None, side=False, **kw):
+        self.calls.append(('launch', 'side' if side else 'main'))
+        res = self.evaluate(col_sets, hyp, gram=gram, refine_tol=None, **kw)
+        eng = self
+
+        class Handle:
+            def finish(self, refine_tol=None):
+                eng._refine(res, col_sets, refine_tol, gram)
+                return res
+        return Handle()
+
+    def gram_state(self):
+        return (self.G, self.Xty)
 
     refine_mask = Engine.refine_mask
 

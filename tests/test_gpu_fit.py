@@ -20,10 +20,11 @@ def rng_digest():
     return hashlib.sha256(st[1].tobytes() + bytes(str((st[2], st[3], repr(st[4]))), 'ascii')).hexdigest()
 
 
-def fit_device(FR, g, phis, rng='numpy', recorder=None, eager=False):
+def fit_device(FR, g, phis, rng='numpy', recorder=None, eager=False, pipeline=True):
     from FoKL import _selection
     FR.B200_CONFIG['rng'] = rng
     FR.B200_CONFIG['eager_chains'] = eager
+    FR.B200_CONFIG['pipeline'] = pipeline
     orig = _selection.forward_select
     if recorder is not None:
         def patched(*a, **k):
@@ -44,6 +45,7 @@ def fit_device(FR, g, phis, rng='numpy', recorder=None, eager=False):
         _selection.forward_select = orig
         FR.B200_CONFIG['rng'] = 'philox'
         FR.B200_CONFIG['eager_chains'] = False
+        FR.B200_CONFIG['pipeline'] = True
 
 
 class Diverged(Exception):
@@ -193,6 +195,10 @@ def test_philox_fit_selects_same_terms_and_is_reproducible(name, phis_cubic):
     _, b3, m3, e3, info3, _ = fit_device(FR, g, phis_cubic, rng='philox', eager=True)
     assert np.array_equal(m1, m3) and np.array_equal(e1, e3) and np.array_equal(b1, b3)
     assert info1['n_gibbs'] == info3['n_gibbs']
+    # the pipelined form (chains of substage s next to the full model of s + 1, on the side context) == the sequential
+    _, b4, m4, e4, info4, _ = fit_device(FR, g, phis_cubic, rng='philox', pipeline=False)
+    assert np.array_equal(m1, m4) and np.array_equal(e1, e4) and np.array_equal(b1, b4)
+    assert info1['n_gibbs'] == info4['n_gibbs']
 
 
 def test_api_surface_after_fit(phis_cubic, tmp_path):

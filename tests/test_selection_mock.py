@@ -9,7 +9,7 @@ from FoKL import _selection
 from mock_engine import MockEngine
 
 
-def _run(x, y, phis, kernel, eager, seed, way3=True, draws=80, tolerance=3, aic=False, **hy_kw):
+def _run(x, y, phis, kernel, eager, seed, way3=True, draws=80, tolerance=3, aic=False, pipeline=None, **hy_kw):
     eng = MockEngine(x, y, phis, kernel)
     a, atau = 4.0, 4.0
     b, btau = fo.default_b_btau(y, a, atau)
@@ -17,7 +17,8 @@ def _run(x, y, phis, kernel, eager, seed, way3=True, draws=80, tolerance=3, aic=
               threshav=0.05, threshstda=0.5, threshstdb=2.0, aic=aic)
     hy.update(hy_kw)
     np.random.seed(seed)
-    out = _selection.forward_select(eng, hy, x.shape[1], len(phis), console=False, rng='philox', eager=eager)
+    out = _selection.forward_select(eng, hy, x.shape[1], len(phis), console=False, rng='philox', eager=eager,
+                                    pipeline=pipeline)
     return out, eng
 
 
@@ -35,12 +36,57 @@ def _data(n, m, seed, noise=0.1):
 @pytest.mark.parametrize('n,m,seed,kw', [
     (300, 3, 1, {}), (500, 2, 2, dict(way3=False)), (200, 4, 3, {}), (400, 3, 4, dict(aic=True)),
     (250, 3, 5, dict(threshav=0.6, threshstda=0.05)), (150, 1, 6, {}), (300, 3, 7, dict(tolerance=1)),
-    (300, 3, 8, dict(gimmie=True))])
+    (300, 3, 8, dict(gimmie=True)),
+    # every proposal threshold-dependent and the threshold in the middle of the candidates: the true chains change
+    # the proposal mask, i.e. the speculation fails and the substage is rolled back (checked below)
+    (210, 3, 22, dict(threshav=1.0, threshstda=0.01, threshstdb=1e9, noise=0.5, rollback=True)),
+    (230, 4, 38, dict(threshav=1.0, threshstda=0.01, threshstdb=1e9, noise=0.5, rollback=True)),
+    (250, 4, 47, dict(threshav=2.0, threshstda=0.01, threshstdb=1e9, noise=0.5, rollback=True))])
 def test_fast_path_equals_literal_path(phis_cubic, n, m, seed, kw):
-    x, y = _data(n, m, seed)
+    kw = dict(kw)
+    x, y = _data(n, m, seed, noise=kw.pop('noise', 0.1))
+    rollback = kw.pop('rollback', False)
     fast, eng_f = _run(x, y, phis_cubic, fo.CUBIC, False, seed, **kw)
     slow, eng_s = _run(x, y, phis_cubic, fo.CUBIC, True, seed, **kw)
     assert np.array_equal(fast['mtx'], slow['mtx'])
     assert np.array_equal(fast['evs'], slow['evs'])
     assert np.array_equal(fast['betas'], slow['betas'])
     assert fast['n_gibbs'] == slow['n_gibbs']
+    # ... and the sequential form of the fast path (no speculation across substages) as well
+    seq, eng_q = _run(x, y, phis_cubic, fo.CUBIC, False, seed, pipeline=False, **kw)
+    assert np.array_equal(fast['mtx'], seq['mtx']) and np.array_equal(fast['evs'], seq['evs'])
+    assert np.array_equal(fast['betas'], seq['betas']) and fast['n_gibbs'] == seq['n_gibbs']
+    assert ('launch', 'side') not in eng_q.calls
+    if 'tolerance' not in kw and m > 1:
+        assert ('launch', 'side') in eng_f.calls      # the pipelined form did speculate
+    rolled = sum(1 for i, c in enumerate(eng_f.calls[:-1]) if c[0] == 'truncate' and eng_f.calls[i + 1][0] == 'append')
+    assert (rolled > 0) == rollback
+    # the engine ends on the last substage's model in every form
+    assert eng_f.P == eng_s.P == eng_q.P
+
+
+def test_speculation_discarded_when_the_fit_finishes(phis_cubic):
+    """pipeline='always' speculates even when the stopping rule is predicted to fire: the last substage's speculative
+    successor must be dropped again and the result must not change."""
+    x, y = _data(300, 3, 1)
+    ref, eng_r = _run(x, y, phis_cubic, fo.CUBIC, False, 1, pipeline=False)
+    alw, eng_a = _run(x, y, phis_cubic, fo.CUBIC, False, 1, pipeline='always')
+    assert np.array_equal(ref['mtx'], alw['mtx']) and np.array_equal(ref['evs'], alw['evs'])
+    assert np.array_equal(ref['betas'], alw['betas']) and ref['n_gibbs'] == alw['n_gibbs']
+    assert eng_a.calls[-1][0] == 'truncate' and eng_a.P == eng_r.P
+
+
+def test_interpolating_model_takes_the_literal_path(phis_cubic):
+    """A (nearly) interpolating model: the Gram-only BIC loses its digits to cancellation and is recomputed from the
+    residual pass over X (Engine.refine_mask); the device kill loop scores with the same Gram-only form, so such a
+    substage must run the literal loop.  Same result in every form."""
+    rng = np.random.default_rng(12)
+    x = rng.random((250, 3))
+    y = 1.0 + 2.0 * fo.basis_columns(x, np.array([[1, 0, 0]]), phis_cubic, fo.CUBIC)[:, 0]
+    fast, eng_f = _run(x, y, phis_cubic, fo.CUBIC, False, 12)
+    seq, eng_q = _run(x, y, phis_cubic, fo.CUBIC, False, 12, pipeline=False)
+    slow, eng_s = _run(x, y, phis_cubic, fo.CUBIC, True, 12)
+    for other in (seq, slow):
+        assert np.array_equal(fast['mtx'], other['mtx']) and np.array_equal(fast['evs'], other['evs'])
+        assert np.array_equal(fast['betas'], other['betas']) and fast['n_gibbs'] == other['n_gibbs']
+    assert any(c[0] == 'refine' for c in eng_f.calls) and not any(c[0] == 'kill_loop' for c in eng_f.calls)

@@ -374,6 +374,8 @@ def main():
             'candidate_models_per_step': models / a.steps, 'terms_selected': infos[-1]['terms'],
             'substages': infos[-1]['substages'], 'wall_ms_per_step': wall_ms / a.steps,
             'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clk, 'roofline': roof, 'roofline_gram': roof_g,
+            'roofline_note': "roofline = the basis-matrix kernel BASELINE.json's metric names (HBM-bound); "
+                             "roofline_gram = the kernel with the largest share of the step (FP64 tensor pipe)",
             'stage_ms_per_step': {k: v['ms'] / a.steps for k, v in prof.items()},
             'cpu_baseline': cpu}
     print(json.dumps(line), flush=True)

@@ -14,23 +14,35 @@ from FoKL._engine import CandidateResult, Engine
 
 
 class MockEngine:
-    def __init__(self, x, y, phis, kernel):
+    def __init__(self, x, y, phis, kernel, dist=None):
+        """x, y: this rank's row shard.  dist: an initialised torch.distributed (gloo) module for the multi-rank form --
+        partial Gram blocks and data moments are summed over the ranks like Engine._append_built / begin_fit do."""
         self.torch = torch
         self.device = torch.device('cpu')
         self.dist, self.group, self.world, self.rank = None, None, 1, 0
+        if dist is not None and dist.get_world_size() > 1:
+            self.dist, self.world, self.rank = dist, dist.get_world_size(), dist.get_rank()
         self.profile = None
         self.x = np.ascontiguousarray(x, dtype=np.float64)
         self.y = np.ascontiguousarray(y, dtype=np.float64).reshape(-1)
         self.phis, self.kernel = phis, kernel
         self.calls = []              # (kind, detail) log of the device work the loop asked for
         n = len(self.y)
-        self.n_global, self.sum_y, self.yty = n, float(self.y.sum()), float(self.y @ self.y)
+        mom = self._sum(np.array([float(n), float(self.y.sum()), float(self.y @ self.y)]))
+        self.n_global, self.sum_y, self.yty = int(round(mom[0])), float(mom[1]), float(mom[2])
         self.X = np.ones((n, 1))
         self._gram()
 
+    def _sum(self, a):
+        if self.dist is None:
+            return a
+        t = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64).copy())
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return t.numpy()
+
     def _gram(self):
-        self.G = self.X.T @ self.X
-        self.Xty = self.X.T @ self.y
+        self.G = self._sum(self.X.T @ self.X)
+        self.Xty = self._sum(self.X.T @ self.y)
         self.P = self.X.shape[1]
 
     # ---- K1 / K2 / compaction ----------------------------------------------------------------------------------
@@ -112,7 +124,8 @@ class MockEngine:
     def residual_bic(self, cols, betahat):
         r = self.y - self.X[:, np.asarray(cols, dtype=np.int64)] @ betahat.numpy()
         n = float(self.n_global)
-        siglik = (r @ r) / n - (r.sum() / n) ** 2
+        sr, srr = self._sum(np.array([r.sum(), r @ r]))
+        siglik = srr / n - (sr / n) ** 2
         with np.errstate(all='ignore'):
             lik = -(n / 2) * np.log(siglik) - (n - 1) / 2
         return len(cols) * np.log(n) - 2 * lik
@@ -139,4 +152,5 @@ class MockEngine:
                              threshstdb=threshstdb, icpt=icpt, evmin=evmin, aic_adj=aic_adj, start=start)
 
     def _allreduce(self, t):
-        pass
+        if self.dist is not None:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)

@@ -95,6 +95,60 @@ def test_two_rank_row_sharding_allreduce(tmp_path):
     assert r[0]['seed'][0] == r[1]['seed'][0]
 
 
+def _select_worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    for p in (os.path.join(ROOT, 'fokl-gpy_b200'), os.path.join(ROOT, 'oracle'), os.path.join(ROOT, 'tests'), ROOT):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        import spline_table
+        from test_selection_mock import select_on_mock, synthetic
+        phis = spline_table.to_phis(np.load(os.path.join(ROOT, 'tests', 'golden', 'phis_cubic_48.npy')))
+        x, y = synthetic(401, 3, 9)                       # ragged shards
+        per = -(-len(y) // world)
+        lo, hi = rank * per, min((rank + 1) * per, len(y))
+        for tag, kw in (('pipe', {}), ('seq', dict(pipeline=False))):
+            np.random.seed(50 + rank)                     # the Philox seed must come from rank 0 all the same
+            out, eng = select_on_mock(x[lo:hi], y[lo:hi], phis, dist=dist, **kw)
+            np.savez(os.path.join(out_dir, '%s_rank%d.npz' % (tag, rank)), mtx=out['mtx'], evs=out['evs'],
+                     betas=out['betas'], n_gibbs=out['n_gibbs'],
+                     side=sum(1 for c in eng.calls if c == ('launch', 'side')),
+                     evaluated=sum(len(c[1]) for c in eng.calls if c[0] == 'evaluate'))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_selection_loop_on_the_stand_in_engine(tmp_path, phis_cubic):
+    """The whole selection loop on two gloo ranks (row shards; tests/mock_engine.py): Gram blocks summed over the
+    ranks, the chains of the accepted models dealt between them (one allreduce of the scalars that drive the loop, the
+    accepted model's draws broadcast from their owner), in the pipelined and in the sequential form.  Both ranks must
+    hold the same fit, it must be the single-rank fit of the whole dataset, and each rank must have evaluated only
+    its share of the models."""
+    import torch.multiprocessing as mp
+    from test_selection_mock import select_on_mock, synthetic
+    world = 2
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_select_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    x, y = synthetic(401, 3, 9)
+    np.random.seed(50)
+    single, eng1 = select_on_mock(x, y, phis_cubic)
+    single_evaluated = sum(len(c[1]) for c in eng1.calls if c[0] == 'evaluate')
+    for tag in ('pipe', 'seq'):
+        r = [np.load(os.path.join(str(tmp_path), '%s_rank%d.npz' % (tag, k))) for k in range(world)]
+        for key in ('mtx', 'evs', 'betas', 'n_gibbs'):
+            assert np.array_equal(r[0][key], r[1][key]), (tag, key)
+        assert np.array_equal(r[0]['mtx'], single['mtx']) and int(r[0]['n_gibbs']) == single['n_gibbs']
+        assert np.allclose(r[0]['evs'], single['evs'], rtol=1e-9, atol=0)
+        assert np.allclose(r[0]['betas'].mean(axis=0), single['betas'].mean(axis=0), rtol=1e-6, atol=1e-9)
+        assert min(int(r[0]['evaluated']), int(r[1]['evaluated'])) < single_evaluated      # the chains were dealt
+    assert int(np.load(os.path.join(str(tmp_path), 'pipe_rank0.npz'))['side']) > 0
+    assert int(np.load(os.path.join(str(tmp_path), 'seq_rank0.npz'))['side']) == 0
+
+
 def test_shards_are_independent_of_world_size():
     sys.path.insert(0, ROOT)
     import bench_data

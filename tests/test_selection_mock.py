@@ -9,6 +9,19 @@ from FoKL import _selection
 from mock_engine import MockEngine
 
 
+def select_on_mock(x, y, phis, dist=None, pipeline=None, draws=80):
+    """forward_select on a (possibly row-sharded) stand-in engine with fixed hyper-parameters; the caller seeds numpy."""
+    eng = MockEngine(x, y, phis, fo.CUBIC, dist=dist)
+    hy = dict(a=4.0, b=0.5, atau=4.0, btau=10.0, tolerance=3, total_draws=draws, gimmie=False, way3=True,
+              threshav=0.05, threshstda=0.5, threshstdb=2.0, aic=False)
+    out = _selection.forward_select(eng, hy, x.shape[1], len(phis), console=False, rng='philox', pipeline=pipeline)
+    return out, eng
+
+
+def synthetic(n, m, seed, noise=0.1):
+    return _data(n, m, seed, noise)
+
+
 def _run(x, y, phis, kernel, eager, seed, way3=True, draws=80, tolerance=3, aic=False, pipeline=None, **hy_kw):
     eng = MockEngine(x, y, phis, kernel)
     a, atau = 4.0, 4.0

@@ -403,13 +403,19 @@ def forward_select(engine, hy, m, n_phis, console=True, rng='philox', eager=Fals
                     # (eig + chain) per proposal, proposals of a round side by side.  (Only ever seen on the first
                     # launch of a substage: a later one works on a principal sub-matrix of a factorisable Gram.)
                     return kill_literal(S, parity=False)
-                for k_ in range(r['n_acc']):
-                    i = int(r['acc'][k_])
-                    alive[int(cand_cols[i])] = False
-                    cols_k = np.nonzero(alive)[0].astype(np.int32)
-                    rounds.append(dict(i=i, cols=cols_k, stream=state['calls'] + int(r['calls'][k_]),
-                                       gibbs_after=state['gibbs'] + int(r['calls'][k_]),
-                                       ev_dev=float(r['ev'][k_]), icpt_used=state['icpt']))
+                n_acc = int(r['n_acc'])
+                if n_acc:
+                    # column lists of the n_acc nested models in one shot: model k = alive minus the first k + 1 kills
+                    kcols = cand_cols[np.asarray(r['acc'][:n_acc], dtype=np.int64)]
+                    member = np.repeat(alive[None, :], n_acc, axis=0)
+                    rr_, cc_ = np.tril_indices(n_acc)
+                    member[rr_, kcols[cc_]] = False
+                    flat_cols = np.nonzero(member)[1].astype(np.int32)
+                    cuts = np.cumsum(len(model) - 1 - np.arange(n_acc))[:-1]
+                    for k_, cols_k in enumerate(np.split(flat_cols, cuts)):
+                        rounds.append(dict(i=int(r['acc'][k_]), cols=cols_k, stream=state['calls'] + int(r['calls'][k_]),
+                                           gibbs_after=state['gibbs'] + int(r['calls'][k_]),
+                                           ev_dev=float(r['ev'][k_]), icpt_used=state['icpt']))
                 state['calls'] += r['tested']
                 state['gibbs'] += r['tested']
                 state['killed'] = state['killed'] + [int(cand_cols[int(i)]) for i in r['acc']]

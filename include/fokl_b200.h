@@ -131,7 +131,9 @@ typedef struct fokl_hypers {
  * rng_mode FOKL_RNG_INJECTED: variates (dev) holds for candidate c, at D * (vec_off[c] + 2c), D rows of
  *   [z_0 .. z_{p-1}, g1, g2] = normal(p), standard_gamma(astar), standard_gamma(atau_star) in the
  *   order one reference `gibbs` call consumes them (FR:1527, 1541, 1547).
- * rng_mode FOKL_RNG_PHILOX: stream_ids (host, n_cand) select independent Philox streams of `seed`.
+ * rng_mode FOKL_RNG_PHILOX: stream_ids (host, n_cand) select independent Philox streams of `seed`; every eigenvector
+ *   is oriented so that its projection on X'y is non-negative (z_j *= sign(q_j . Xty)): the chain is then a function
+ *   of the Gram alone, whatever sign the eigensolver happened to return (FR:1525-1528 leaves it to LAPACK).
  * sign_fix (dev, packed like betahat, or NULL): z_j is multiplied by sign_fix[j] (parity harness only:
  *   aligns eigenvector signs with another eigensolver).
  * Outputs (dev; any of betahat/lamb/Q/betas/sigs/taus/stats may be NULL):

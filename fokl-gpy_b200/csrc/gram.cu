@@ -691,7 +691,17 @@ __global__ void gram_reduce_kernel(const double *__restrict__ part, int nsplit, 
         double s = 0.0;
         for (int qq = q; qq >= 0; qq = blocks[tm.blk_off + qq].next) {      // the block's items in phase order
             const double *src = part + (size_t)tile * tile_stride + (size_t)qq * 256 + (e & 255);
-            for (int k = 0; k < nsplit; ++k) s += src[(size_t)k * n_tiles * tile_stride];
+            // same ascending order (same bits), eight loads in flight instead of one dependent load per add
+            const size_t kstride = (size_t)n_tiles * tile_stride;
+            int k = 0;
+            for (; k + 8 <= nsplit; k += 8) {
+                double v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = __ldcg(src + (size_t)(k + j) * kstride);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) s += v[j];
+            }
+            for (; k < nsplit; ++k) s += __ldcg(src + (size_t)k * kstride);
         }
         out[(size_t)arow * c + bcol] = s;
     }

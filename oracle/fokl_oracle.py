@@ -10,6 +10,7 @@ It restates, in numpy float64 (plus a small C helper for the basis loop), the al
     eval_basis          FR:834-843      one basis function at one point (d = 0)
     basis_columns       FR:1446-1485    X[i, j] = prod_k phi_{d_jk}(x_ik)
     bss_derivatives     FR:594-805      partial derivatives of the fitted function (a section-8f "next" row)
+    evaluate            FR:851-980      mean prediction and 95 % bounds from the draws (a section-8f "next" row)
     default_b_btau      FR:1322-1348    data-dependent defaults of b, btau
     gibbs               FR:1396-1558    Gram, eigh, betahat, Gibbs chain, BIC
     distinct_perms      FR:1350-1354 + FR:1616   == np.unique(perms(v), axis=0)
@@ -248,6 +249,35 @@ def bss_derivatives(inputs, betas, mtx, phis, kernel, minmax, d1=None, d2=None, 
         dy = np.concatenate([dy[:, :, 0, :], dy[:, :, 1, :]], axis=1)
         dy = dy[:, ~np.all(dy == 0, axis=0)]
     return np.squeeze(dy)
+
+
+# --------------------------------------------------------------------------------------------------
+# evaluate (FR:851-980) -- the prediction path, a section-8f "next" row
+# --------------------------------------------------------------------------------------------------
+
+def evaluate(normputs, betas, mtx, phis, kernel, setnos, draws, return_bounds=False):
+    """Mean prediction (and 95 % bounds) at already-normalised inputs from the draws `betas[setnos[:draws]]`:
+    X as in FR:940-957, one matrix-vector product per draw (FR:960-962), bounds from the sorted draws (FR:966-972)."""
+    normputs = np.asarray(normputs, dtype=np.float64)
+    if normputs.ndim == 1:
+        normputs = normputs[:, None]
+    n = normputs.shape[0]
+    X = np.hstack([np.ones((n, 1)), basis_columns(normputs, np.asarray(mtx).astype(int), phis, kernel)])
+    if draws == 1:
+        setnos = [0]
+    modells = np.zeros((n, draws))
+    for i in range(draws):
+        modells[:, i] = np.transpose(np.matmul(X, np.transpose(np.array(betas[setnos[i], :]))))
+    mean = np.mean(modells, 1)
+    if not return_bounds:
+        return mean
+    bounds = np.zeros((n, 2))
+    cut = int(np.floor(draws * 0.025) + 1)
+    for i in range(n):
+        drawset = np.sort(modells[i, :])
+        bounds[i, 0] = drawset[cut]
+        bounds[i, 1] = drawset[draws - cut]
+    return mean, bounds
 
 
 # --------------------------------------------------------------------------------------------------

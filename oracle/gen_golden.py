@@ -249,11 +249,47 @@ def case_bss_derivatives():
     print('bss_derivatives', {k: np.shape(v) for k, v in out.items()})
 
 
+def case_evaluate():
+    """Pin evaluate / coverage3 (FR:851-1200): the unmodified reference on a hand-made model (betas, mtx, minmax given,
+    no fit), cubic and Bernoulli, mean + 95 % bounds + the 'rmse' of coverage3, raw inputs cleaned with the model's
+    minmax and already-normalised inputs."""
+    FR = ref_harness.load_reference()
+    rng = np.random.default_rng(91)
+    n, m, rows = 53, 3, 120
+    x = rng.random((n, m))
+    x[0, 0], x[1, 1], x[2, 2] = 0.0, 1.0, 1 / 499
+    mtx = np.array([[1, 0, 0], [0, 2, 0], [0, 0, 3], [1, 1, 0], [2, 0, 1], [0, 3, 2], [1, 2, 1], [4, 0, 0]], dtype=np.float64)
+    betas = rng.standard_normal((rows, mtx.shape[0] + 1))
+    data = rng.standard_normal(n)
+    minmax = [[-1.0, 3.0], [0.0, 1.0], [10.0, 10.7]]
+    raw = np.array([[lo + (hi - lo) * v for v, (lo, hi) in zip(row, minmax)] for row in x])
+    out = dict(x=x, raw=raw, mtx=mtx, betas=betas, data=data, minmax=np.array(minmax), draws=100, seed=7)
+    tab = np.load(os.path.join(GOLD, 'phis_cubic_48.npy'))
+    models = dict(cubic=FR.FoKL(phis=spline_table.to_phis(tab), UserWarnings=False),
+                  bern=FR.FoKL(kernel=1, UserWarnings=False))
+    import warnings
+    for name, model in models.items():
+        model.mtx, model.minmax, model.draws, model.betas = mtx, minmax, 100, betas
+        model.inputs, model.data = x, data
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            np.random.seed(7)
+            mean, bounds = model.evaluate(x, ReturnBounds=1)                 # draws setnos from the global RNG (FR:933-937)
+            out[name + '_setnos'] = np.array(model.setnos)
+            out[name + '_mean'], out[name + '_bounds'] = mean, bounds
+            out[name + '_mean_raw'] = model.evaluate(raw, clean=True)       # same setnos, inputs normalised by minmax
+            out[name + '_mean_20'] = model.evaluate(x, draws=20)
+            cm, cb, rmse = model.coverage3(inputs=x, data=data, draws=100)
+            out[name + '_cov_mean'], out[name + '_cov_bounds'], out[name + '_cov_rmse'] = cm, cb, rmse
+    np.savez_compressed(os.path.join(GOLD, 'evaluate.npz'), **out)
+    print('evaluate', {k: np.shape(v) for k, v in out.items()})
+
+
 CASES = dict(isotherm_gp=case_isotherm_gp, isotherm_qmax=case_isotherm_qmax,
              cfg2_default=lambda: case_cfg2(False), cfg2_changed=lambda: case_cfg2(True),
              cfg1_sigmoid=case_cfg1_sigmoid, way3_bernoulli=case_way3_bernoulli,
              way3_cubic=case_way3_cubic, two_way_cubic=case_two_way_cubic, m1_cubic=case_m1,
-             basis_values=case_basis_values, bss_derivatives=case_bss_derivatives)
+             basis_values=case_basis_values, bss_derivatives=case_bss_derivatives, evaluate=case_evaluate)
 
 if __name__ == '__main__':
     todo = sys.argv[1:] or list(CASES)

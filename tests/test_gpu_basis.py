@@ -176,3 +176,40 @@ def test_derivative_columns_bit_exact_cubic(engine, phis_cubic, n):
             engine.synchronize()
             got = X[:, :n].cpu().numpy().T
             assert np.array_equal(got, want), (wrt, order)
+
+
+# ---- evaluate / coverage3 (FR:851-1200) ------------------------------------------------------
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', ['cubic', 'bern'])
+def test_evaluate_and_coverage3_against_reference_golden(name, phis_cubic, phis_bern):
+    """FoKL.evaluate / coverage3 on the device (K1 + fokl_predict_draws) vs outputs of the unmodified reference
+    (tests/golden/evaluate.npz, oracle/gen_golden.py): same `setnos` from the seeded global RNG (FR:933-937), mean and
+    95 % bounds to rtol 1e-9 of the output scale, the coverage3 'rmse' as the reference computes it (FR:1193)."""
+    import warnings
+    from FoKL import FoKLRoutines as FR
+    from conftest import load_golden
+    g = load_golden('evaluate')
+    phis, kernel = (phis_cubic, 'Cubic Splines') if name == 'cubic' else (phis_bern, 'Bernoulli Polynomials')
+    model = FR.FoKL(phis=phis, kernel=kernel, UserWarnings=False)
+    model.mtx, model.minmax, model.draws, model.betas = g['mtx'], g['minmax'].tolist(), 100, g['betas']
+    model.inputs, model.data = g['x'], g['data']
+    scale = np.max(np.abs(g[name + '_mean'])) + 1e-300
+
+    def close(got, want):
+        assert np.shape(got) == np.shape(want)
+        assert np.max(np.abs(np.asarray(got) - want)) < 1e-9 * scale
+
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        np.random.seed(int(g['seed']))
+        mean, bounds = model.evaluate(g['x'], ReturnBounds=1)
+        assert np.array_equal(model.setnos, g[name + '_setnos'])
+        close(mean, g[name + '_mean'])
+        close(bounds, g[name + '_bounds'])
+        close(model.evaluate(g['raw'], clean=True), g[name + '_mean_raw'])
+        close(model.evaluate(g['x'], draws=20), g[name + '_mean_20'])
+        cm, cb, rmse = model.coverage3(inputs=g['x'], data=g['data'], draws=100)
+        close(cm, g[name + '_cov_mean'])
+        close(cb, g[name + '_cov_bounds'])
+        assert abs(float(rmse) - float(g[name + '_cov_rmse'])) < 1e-9 * scale

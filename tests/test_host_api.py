@@ -1,6 +1,7 @@
 """Host-side mirror of the reference API (no GPU needed): constructor kwargs, clean, term generation, save/load,
 and that the hot path fails loudly without a CUDA device."""
 import itertools
+import os
 import pickle
 
 import numpy as np
@@ -130,3 +131,22 @@ def test_regenerated_spline_table_is_deterministic_and_continuous():
     assert np.max(np.abs(end - start)) < 1e-12
     gold = np.load(__import__('os').path.join(__import__('conftest').GOLD, 'phis_cubic_48.npy'))
     assert np.allclose(tab, gold[:6], rtol=0, atol=1e-9)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver times next to the GPU arm) needs no GPU: one JSON line with
+    the metric / unit / config of the GPU arm, impl = reference, cpu_baseline and a zero-copy e2e object."""
+    import json
+    import subprocess
+    import sys
+    from conftest import ROOT
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1',
+                          '--warmup', '0', '--cpu-seconds', '1', '--cpu-rows', '600'], capture_output=True, text=True,
+                         timeout=240, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line['impl'] == 'reference' and line['metric'] == 'FoKL.fit candidate-models/sec'
+    assert line['unit'] == 'candidate-models/s' and line['higher_is_better'] is True and line['value'] > 0
+    assert line['config']['workload'].startswith('cfg4') and line['dtype'] == 'f64'
+    assert line['cpu_baseline']['kind'] == 'port' and line['cpu_baseline']['cores'] >= 1
+    assert line['e2e'] == {'value': line['value'], 'unit': line['unit'], 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}

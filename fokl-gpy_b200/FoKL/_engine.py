@@ -54,7 +54,7 @@ class DeviceDataset:
 
 class CandidateResult:
     __slots__ = ('ev', 'info', 'stats', 'betas', 'sigs', 'taus', 'betahat', 'lamb', 'Q', 'p', 'vec_off', 'mat_off',
-                 'draws', 'refined')
+                 'draws', 'refined', 'stats_host')
 
     def betas_of(self, c):
         o = self.draws * self.vec_off[c]
@@ -76,10 +76,19 @@ class PendingCandidates:
         """Synchronise and return the CandidateResult.  refine_tol > 0: near-interpolating / degenerate fits are
         recomputed from an N-length residual pass over the *current* X (FR:1551), so the models must still be there."""
         eng, res = self.engine, self.res
+        res.stats_host = None
         if self.side:
+            # read back on the side stream itself: the main stream may hold later work (the next kill loop) that these
+            # copies must not queue behind; afterwards the main stream may touch the batch's tensors
+            with eng.torch.cuda.stream(eng.side_stream):
+                res.ev = self.ev.cpu().numpy()
+                res.info = self.info.cpu().numpy()
+                if res.stats is not None:
+                    res.stats_host = res.stats.cpu().numpy()
             eng.torch.cuda.current_stream(eng.device).wait_stream(eng.side_stream)
-        res.ev = self.ev.cpu().numpy()
-        res.info = self.info.cpu().numpy()
+        else:
+            res.ev = self.ev.cpu().numpy()
+            res.info = self.info.cpu().numpy()
         res.refined = np.zeros(len(res.ev), dtype=bool)
         if refine_tol is not None and refine_tol > 0:
             bad = eng.refine_mask(res.ev, res.p, refine_tol)
@@ -546,6 +555,12 @@ class Engine:
     def kill_loop(self, cols, cand_pos, bv0, bv1, hyp, threshav, threshstda, threshstdb, icpt, evmin, aic_adj, start):
         """The kill loop of one substage (FR:1666-1690) in one launch (fokl_kill_loop).  Returns dict(n_acc, tested,
         bad, acc, calls, ev) as host values (this call synchronises)."""
+        return self.kill_loop_launch(cols, cand_pos, bv0, bv1, hyp, threshav, threshstda, threshstdb, icpt, evmin,
+                                     aic_adj, start).finish()
+
+    def kill_loop_launch(self, cols, cand_pos, bv0, bv1, hyp, threshav, threshstda, threshstdb, icpt, evmin, aic_adj,
+                         start):
+        """Enqueue fokl_kill_loop; the returned handle's finish() reads the result back (host work can go in between)."""
         torch = self.torch
         cols = np.ascontiguousarray(cols, dtype=np.int32)
         cand_pos = np.ascontiguousarray(cand_pos, dtype=np.int32)
@@ -564,11 +579,15 @@ class Engine:
                                          ctypes.byref(hyp), ctypes.byref(kp), out.data_ptr(),
                                          out.data_ptr() + 8 * n_i_d))
         self._toc(t, 'kill_loop', cands=vm, pmax=len(cols))
-        h = out.cpu().numpy()
-        oi = h[:n_i_d].view(np.int32)
-        k = int(oi[0])
-        return dict(n_acc=k, tested=int(oi[1]), bad=int(oi[2]), acc=oi[3:3 + k].copy(),
-                    calls=oi[3 + vm:3 + vm + k].copy(), ev=h[n_i_d:n_i_d + k].copy())
+
+        class _Pending:
+            def finish(_self):
+                h = out.cpu().numpy()
+                oi = h[:n_i_d].view(np.int32)
+                k = int(oi[0])
+                return dict(n_acc=k, tested=int(oi[1]), bad=int(oi[2]), acc=oi[3:3 + k].copy(),
+                            calls=oi[3 + vm:3 + vm + k].copy(), ev=h[n_i_d:n_i_d + k].copy())
+        return _Pending()
 
     def residual_bic(self, cols, betahat_dev):
         """BIC of FR:1551-1554 from an explicit N-length residual pass over X (used when the Gram-only

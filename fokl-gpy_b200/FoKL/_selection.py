@@ -316,7 +316,9 @@ def forward_select(engine, hy, m, n_phis, console=True, rng='philox', eager=Fals
         if handle is None:
             return False
         rr = handle.finish(1e-7 if refine else None)
-        stats_h = rr.stats.cpu().numpy()      # one read-back for the whole batch
+        stats_h = getattr(rr, 'stats_host', None)      # one read-back for the whole batch
+        if stats_h is None:
+            stats_h = rr.stats.cpu().numpy()
         for slot, i in enumerate(which):
             # mean(beters[h0:, 0]) of this model: row 2, column 0 of its 3 x p statistics block
             vals[i, 0] = abs(float(stats_h[3 * rr.vec_off[slot] + 2 * rr.p[slot]]))
@@ -369,11 +371,13 @@ def forward_select(engine, hy, m, n_phis, console=True, rng='philox', eager=Fals
         the last round): if none of them is threshold-dependent (threshstda < bv1 <= threshstdb) the chain of round k
         is never looked at.
 
-        Protocol: `yield (todo, outlook)` asks the driver for the chains of `todo` (it fills icpt_true / ev_true / rr /
-        slot / owner of every entry) and is answered with 'done' -- or with 'speculated' if the driver has, on the
-        strength of `outlook` (the outcome if every check passes; None after the first request), already compacted the
-        engine and moved on; then a failed check makes the generator `yield 'rollback'` (the driver restores the
-        substage's columns and Gram) before it continues.  Returns the substage's outcome."""
+        Protocol: `yield ('kill', model, pos, icpt, evmin, start)` asks the driver for one fokl_kill_loop launch and is
+        answered with its result (so the driver can do host work while the kernel runs); `yield ('chains', todo,
+        outlook)` asks for the chains of `todo` (the driver fills icpt_true / ev_true / rr / slot / owner of every
+        entry) and is answered with 'done' -- or with 'speculated' if the driver has, on the strength of `outlook` (the
+        outcome if every check passes; None after the first request), already compacted the engine and moved on; then a
+        failed check makes the generator `yield ('rollback',)` (the driver restores the substage's columns and Gram)
+        before it continues.  Returns the substage's outcome."""
         full, cand_cols, vm, bv0, bv1 = S['full'], S['cand_cols'], S['vm'], S['bv0'], S['bv1']
         with np.errstate(invalid='ignore'):
             bv1_sens = (bv1 > hy['threshstda']) & ~(bv1 > hy['threshstdb'])
@@ -395,8 +399,7 @@ def forward_select(engine, hy, m, n_phis, console=True, rng='philox', eager=Fals
                 where = np.ones(len(full), dtype=np.int32)            # killed candidates: any valid position
                 where[model] = np.arange(len(model), dtype=np.int32)
                 pos = where[cand_cols]
-                r = engine.kill_loop(model, pos, bv0, bv1, hyp, hy['threshav'], hy['threshstda'],
-                                     hy['threshstdb'], state['icpt'], state['evmin'], aic_adj, state['cur'])
+                r = yield ('kill', model, pos, state['icpt'], state['evmin'], state['cur'])
                 cnt['batches'] += 1
                 if r['bad']:
                     # Gram not numerically positive definite (p >= N regimes): literal loop, one spectral evaluation
@@ -434,7 +437,7 @@ def forward_select(engine, hy, m, n_phis, console=True, rng='philox', eager=Fals
             if todo:
                 outlook = dict(killed=list(state['killed']), ev=state['evmin'], calls=state['calls'],
                                gibbs=state['gibbs']) if first_request else None
-                answer = yield (todo, outlook)
+                answer = yield ('chains', todo, outlook)
                 first_request = False
                 speculated = answer == 'speculated'
             def first_changed_round():
@@ -464,14 +467,14 @@ def forward_select(engine, hy, m, n_phis, console=True, rng='philox', eager=Fals
             redo = first_changed_round()
             unrefined = any(rd.get('unrefined') for rd in todo)
             if speculated and (redo is not None or unrefined):
-                yield 'rollback'
+                yield ('rollback',)
                 if unrefined:
                     # a Gram-only BIC of the batch was not trustworthy: now that X holds the columns again, redo the
                     # batch with the residual pass and check again
                     for rd in todo:
                         for key in ('icpt_true', 'ev_true', 'rr', 'slot', 'owner', 'unrefined'):
                             rd.pop(key, None)
-                    yield (todo, None)
+                    yield ('chains', todo, None)
                     redo = first_changed_round()
             if redo is None:
                 last_rd = rounds[-1]
@@ -498,15 +501,30 @@ def forward_select(engine, hy, m, n_phis, console=True, rng='philox', eager=Fals
             state = dict(killed=sorted(set(full) - set(int(c_) for c_ in rd['cols'])), evmin=rd['ev_true'],
                          cur=rd['i'] + 1, icpt=rd['icpt_true'], calls=rd['stream'], gibbs=rd['gibbs_after'])
 
-    def drive(gen, request):
+    def kill_launch(S, request):
+        _, model, pos, icpt_now, evmin_now, start = request
+        return engine.kill_loop_launch(model, pos, S['bv0'], S['bv1'], hyp, hy['threshav'], hy['threshstda'],
+                                       hy['threshstdb'], icpt_now, evmin_now, aic_adj, start)
+
+    def step_gen(gen, answer=None, first=False):
+        """Advance a kill_fast generator: (request, None) or (None, outcome)."""
+        try:
+            return (next(gen) if first else gen.send(answer)), None
+        except StopIteration as stop:
+            return None, stop.value
+
+    def drive(gen, request, S):
         """Answer a kill_fast generator synchronously until it returns its outcome."""
         while True:
-            todo, _ = request
-            chains_now(todo)
-            try:
-                request = gen.send('done')
-            except StopIteration as stop:
-                return stop.value
+            if request[0] == 'kill':
+                answer = kill_launch(S, request).finish()
+            else:
+                assert request[0] == 'chains', request[0]
+                chains_now(request[1])
+                answer = 'done'
+            request, outcome = step_gen(gen, answer)
+            if request is None:
+                return outcome
 
     # ---- phase D: drop the accepted kills (FR:1691-1695) and the bookkeeping of FR:1701-1721 ----------------------------
     def close_substage(S, outcome, compacted):
@@ -573,6 +591,14 @@ def forward_select(engine, hy, m, n_phis, console=True, rng='philox', eager=Fals
             side = chains_launch(todo, mine, gram=carry['gram'], side=True)
         handle = full_launch(S)
         full_finish(S, handle)
+        # C(s) starts here: its kill-loop launch is enqueued before the host turns to the chains of s - 1, so the
+        # collection / checks / bookkeeping of s - 1 (and any wait for a long side batch) run while that kernel does
+        gen_s = request = outcome_s = pending_kill = None
+        if not (literal or S['refined']):
+            gen_s = kill_fast(S)
+            request, outcome_s = step_gen(gen_s, first=True)
+            if request is not None and request[0] == 'kill':
+                pending_kill = kill_launch(S, request)
         if carry is not None:
             need = chains_collect(todo, mine, side, vals, refine=False)
             need = chains_reduce(todo, vals, need)
@@ -581,24 +607,18 @@ def forward_select(engine, hy, m, n_phis, console=True, rng='philox', eager=Fals
                 if need:
                     rd['unrefined'] = True
             prev, gen = carry['S'], carry['gen']
-            carry_cnt_after = dict(cnt)
-            try:
-                request = gen.send('speculated')
-                outcome = None
-            except StopIteration as stop:
-                request, outcome = None, stop.value
+            req_prev, outcome = step_gen(gen, 'speculated')
             if outcome is None:
                 # a check failed: rebuild substage s - 1 as it was before the speculation and finish it synchronously
-                assert request == 'rollback'
+                # (what was started for substage s, including its kill loop, is dropped)
+                assert req_prev[0] == 'rollback'
                 engine.truncate(prev['p_old'])
                 engine.append_terms(prev['vecs'])
                 cnt['calls'], cnt['gibbs'] = carry['cnt0']['calls'], carry['cnt0']['gibbs']
                 terms = prev['terms']
-                try:
-                    request = gen.send('done')
-                    outcome = drive(gen, request)
-                except StopIteration as stop:
-                    outcome = stop.value
+                req_prev, outcome = step_gen(gen, 'done')
+                if outcome is None:
+                    outcome = drive(gen, req_prev, prev)
                 carry = None
                 S = prev
                 finished = close_substage(S, outcome, compacted=False)
@@ -615,20 +635,18 @@ def forward_select(engine, hy, m, n_phis, console=True, rng='philox', eager=Fals
                 engine.truncate(S['p_old'])                              # drop the speculative columns of s
                 cnt['calls'], cnt['gibbs'] = outcome['calls'], outcome['gibbs']
                 break
-        # ---- C(s) ----
-        if literal or S['refined']:
+        # ---- C(s), continued ----
+        if gen_s is None:
             outcome = kill_literal(S, parity=(mode == _lib.RNG_INJECTED))
-            request = None
         else:
-            gen = kill_fast(S)
-            try:
-                request = next(gen)
-                outcome = None
-            except StopIteration as stop:
-                request, outcome = None, stop.value
+            outcome = outcome_s
+            if pending_kill is not None:
+                request, outcome = step_gen(gen_s, pending_kill.finish())
+            while request is not None and request[0] == 'kill':
+                request, outcome = step_gen(gen_s, kill_launch(S, request).finish())
         step = walk_next(S['ind'], S['part'])
         if request is not None:
-            todo, outlook = request
+            _, todo, outlook = request
             if pipeline and step is not None and outlook is not None and \
                     (pipeline == 'always' or not will_finish(outlook['ev'])):
                 # speculate on `outlook`: D(s) without its bookkeeping, then A(s + 1)
@@ -640,10 +658,10 @@ def forward_select(engine, hy, m, n_phis, console=True, rng='philox', eager=Fals
                 S['terms_final'] = np.delete(S['terms'], [c - 1 for c in killed], axis=0)
                 terms = S['terms_final']
                 cnt['calls'], cnt['gibbs'] = outlook['calls'], outlook['gibbs']
-                carry = dict(S=S, gen=gen, todo=todo, gram=gram, cnt0=cnt0)
+                carry = dict(S=S, gen=gen_s, todo=todo, gram=gram, cnt0=cnt0)
                 S = open_substage(step[0], step[1], terms)
                 continue
-            outcome = drive(gen, request)
+            outcome = drive(gen_s, request, S)
         finished = close_substage(S, outcome, compacted=False)
         if finished or step is None:
             break

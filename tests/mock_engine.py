@@ -151,6 +151,15 @@ class MockEngine:
         return emu.kill_loop(self.G, self.Xty, cols, cand_pos, bv0, bv1, hyp, threshav=threshav, threshstda=threshstda,
                              threshstdb=threshstdb, icpt=icpt, evmin=evmin, aic_adj=aic_adj, start=start)
 
+    def kill_loop_launch(self, *args):
+        r = self.kill_loop(*args)
+        self.calls.append(('kill_launch', 0))
+
+        class Handle:
+            def finish(self):
+                return r
+        return Handle()
+
     def _allreduce(self, t):
         if self.dist is not None:
             self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)

@@ -13,6 +13,7 @@ HBM layout (all float64):
 Multi-GPU: every rank holds N/world rows of x, y, X; Gram blocks are summed with one NCCL allreduce per
 substage, after which every rank owns the full G (axis 1).
 """
+import contextlib
 import ctypes
 import math
 
@@ -85,7 +86,11 @@ class PendingCandidates:
                 res.info = self.info.cpu().numpy()
                 if res.stats is not None:
                     res.stats_host = res.stats.cpu().numpy()
-            eng.torch.cuda.current_stream(eng.device).wait_stream(eng.side_stream)
+            main_stream = eng.torch.cuda.current_stream(eng.device)
+            main_stream.wait_stream(eng.side_stream)
+            for tns in (res.stats, res.betas, res.sigs, res.taus, res.betahat, res.lamb, res.Q, self.ev, self.info):
+                if tns is not None:
+                    tns.record_stream(main_stream)      # allocated on the side stream's pool, read on the main stream
         else:
             res.ev = self.ev.cpu().numpy()
             res.info = self.info.cpu().numpy()
@@ -444,6 +449,9 @@ class Engine:
             if rc != 0:
                 raise RuntimeError("fokl_ctx_create (side context) failed with code %d" % rc)
             self.ctx_side = ctx
+            # its batches run next to the main context's full-model evaluation (one cluster of up to 16 CTAs)
+            sms = self.torch.cuda.get_device_properties(self.device).multi_processor_count
+            self.lib.fokl_ctx_set_sm_budget(ctx, max(sms - 16, 16))
         return self.ctx_side
 
     def gram_state(self):
@@ -455,47 +463,66 @@ class Engine:
         """Forget the columns from p on (roll-back of a speculative append_terms)."""
         self.P = int(p)
 
+    def mark(self):
+        """An event on the main stream: evaluate_launch(side=True, after=mark) then orders the side batch after the work
+        enqueued up to here only, not after what the main stream is given later."""
+        e = self.torch.cuda.Event()
+        e.record(self.torch.cuda.current_stream(self.device))
+        return e
+
     def evaluate_launch(self, col_sets, hyp, rng_mode=_lib.RNG_NONE, run_chain=None, seed=0, stream_ids=None,
-                        variates=None, sign_fix=None, want_betas=False, want_eig=False, gram=None, side=False):
+                        variates=None, sign_fix=None, want_betas=False, want_eig=False, gram=None, side=False,
+                        after=None):
         """Enqueue K3/K4 for a batch of candidate models and return a PendingCandidates; nothing is read back until
         its finish().  gram: (G, Xty, ldg) to index instead of the current Gram (gram_state() of an earlier model);
         side: enqueue on the side context's stream, concurrently with the main stream's work."""
         torch = self.torch
         G, Xty, ldg = gram if gram is not None else (self.G, self.Xty, self.Gcap)
-        n_cand = len(col_sets)
-        p = np.array([len(s) for s in col_sets], dtype=np.int64)
-        offs = np.zeros(n_cand + 1, dtype=np.int32)
-        offs[1:] = np.cumsum(p)
-        flat = np.ascontiguousarray(np.concatenate([np.asarray(s, dtype=np.int32) for s in col_sets]))
-        vec_off = np.concatenate([[0], np.cumsum(p)[:-1]]).astype(np.int64)
-        mat_off = np.concatenate([[0], np.cumsum(p * p)[:-1]]).astype(np.int64)
-        total_p = int(p.sum())
-        D = int(hyp.draws)
-        f64 = dict(dtype=torch.float64, device=self.device)
-        ev = torch.empty(n_cand, **f64)
-        info = torch.zeros(n_cand, dtype=torch.int32, device=self.device)
-        betahat = torch.empty(total_p, **f64)
-        chain_any = rng_mode != _lib.RNG_NONE and (run_chain is None or bool(np.any(run_chain)))
-        stats = torch.zeros(3 * total_p, **f64) if chain_any else None
-        betas = torch.empty(D * total_p, **f64) if (chain_any and want_betas) else None
-        sigs = torch.empty(D * n_cand, **f64) if (chain_any and want_betas) else None
-        taus = torch.empty(D * n_cand, **f64) if (chain_any and want_betas) else None
-        lamb = torch.empty(total_p, **f64) if want_eig else None
-        Q = torch.empty(int((p * p).sum()), **f64) if want_eig else None
-        rc_arr = None
-        if run_chain is not None:
-            rc_arr = np.ascontiguousarray(run_chain, dtype=np.uint8)
-        sid = None
-        if stream_ids is not None:
-            sid = np.ascontiguousarray(stream_ids, dtype=np.uint64)
-        var_t = None
-        if rng_mode == _lib.RNG_INJECTED:
-            var_t = variates if torch.is_tensor(variates) else torch.from_numpy(
-                np.ascontiguousarray(variates, dtype=np.float64)).to(self.device)
-        sf_t = None
-        if sign_fix is not None:
-            sf_t = sign_fix if torch.is_tensor(sign_fix) else torch.from_numpy(
-                np.ascontiguousarray(sign_fix, dtype=np.float64)).to(self.device)
+        main_stream = torch.cuda.current_stream(self.device)
+        if side:
+            self._side()
+            # Order the side stream after the main stream's work up to `after` (or up to now), then make every
+            # allocation / zero-fill / upload of this batch on the side stream itself: a fill enqueued on the main stream
+            # behind later main-stream work could otherwise land after the batch's kernels have written their results.
+            if after is not None:
+                self.side_stream.wait_event(after)
+            else:
+                self.side_stream.wait_stream(main_stream)
+        with (torch.cuda.stream(self.side_stream) if side else contextlib.nullcontext()):
+            n_cand = len(col_sets)
+            p = np.array([len(s) for s in col_sets], dtype=np.int64)
+            offs = np.zeros(n_cand + 1, dtype=np.int32)
+            offs[1:] = np.cumsum(p)
+            flat = np.ascontiguousarray(np.concatenate([np.asarray(s, dtype=np.int32) for s in col_sets]))
+            vec_off = np.concatenate([[0], np.cumsum(p)[:-1]]).astype(np.int64)
+            mat_off = np.concatenate([[0], np.cumsum(p * p)[:-1]]).astype(np.int64)
+            total_p = int(p.sum())
+            D = int(hyp.draws)
+            f64 = dict(dtype=torch.float64, device=self.device)
+            ev = torch.empty(n_cand, **f64)
+            info = torch.zeros(n_cand, dtype=torch.int32, device=self.device)
+            betahat = torch.empty(total_p, **f64)
+            chain_any = rng_mode != _lib.RNG_NONE and (run_chain is None or bool(np.any(run_chain)))
+            stats = torch.zeros(3 * total_p, **f64) if chain_any else None
+            betas = torch.empty(D * total_p, **f64) if (chain_any and want_betas) else None
+            sigs = torch.empty(D * n_cand, **f64) if (chain_any and want_betas) else None
+            taus = torch.empty(D * n_cand, **f64) if (chain_any and want_betas) else None
+            lamb = torch.empty(total_p, **f64) if want_eig else None
+            Q = torch.empty(int((p * p).sum()), **f64) if want_eig else None
+            rc_arr = None
+            if run_chain is not None:
+                rc_arr = np.ascontiguousarray(run_chain, dtype=np.uint8)
+            sid = None
+            if stream_ids is not None:
+                sid = np.ascontiguousarray(stream_ids, dtype=np.uint64)
+            var_t = None
+            if rng_mode == _lib.RNG_INJECTED:
+                var_t = variates if torch.is_tensor(variates) else torch.from_numpy(
+                    np.ascontiguousarray(variates, dtype=np.float64)).to(self.device)
+            sf_t = None
+            if sign_fix is not None:
+                sf_t = sign_fix if torch.is_tensor(sign_fix) else torch.from_numpy(
+                    np.ascontiguousarray(sign_fix, dtype=np.float64)).to(self.device)
 
         def ptr(t):
             return None if t is None else t.data_ptr()
@@ -504,8 +531,6 @@ class Engine:
         t = None
         if side:
             ctx = self._side()
-            # everything enqueued so far on the main stream (Gram updates, the zero-fills above) happens-before
-            self.side_stream.wait_stream(torch.cuda.current_stream(self.device))
         else:
             t = self._tic()
         rc = self.lib.fokl_candidates_eval(

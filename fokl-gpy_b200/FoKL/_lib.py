@@ -52,6 +52,7 @@ PROTOTYPES = {
     'fokl_set_phis_bernoulli': (_i32, [_vp, _vp, _i32, _i32]),
     'fokl_basis_build': (_i32, [_vp, _i32, _vp, _i64, _i64, _i32, _vp, _i32, _vp, _i64]),
     'fokl_basis_build_deriv': (_i32, [_vp, _i32, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _i32, _vp, _i64]),
+    'fokl_ctx_set_sm_budget': (_i32, [_vp, _i32]),
     'fokl_fill_ones': (_i32, [_vp, _vp, _i64]),
     'fokl_gram_update': (_i32, [_vp, _vp, _i64, _i64, _i32, _i32, _vp, _vp]),
     'fokl_y_moments': (_i32, [_vp, _vp, _i64, _vp]),

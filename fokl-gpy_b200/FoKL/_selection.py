@@ -301,14 +301,14 @@ def forward_select(engine, hy, m, n_phis, console=True, rng='philox', eager=Fals
     # The models of a batch are independent: with several ranks each evaluates every world-th one (all ranks hold the
     # full Gram) and the two scalars per model that drive the loop are summed into place by one allreduce, so every
     # rank takes the same decisions.
-    def chains_launch(todo, which, gram=None, side=False):
+    def chains_launch(todo, which, gram=None, side=False, after=None):
         if not which:
             return None
         cnt['batches'] += 1
         return engine.evaluate_launch([todo[i]['cols'] for i in which], hyp, rng_mode=mode,
                                       run_chain=np.ones(len(which), dtype=np.uint8), seed=seed,
                                       stream_ids=np.asarray([todo[i]['stream'] for i in which], dtype=np.uint64),
-                                      want_betas=True, gram=gram, side=side)
+                                      want_betas=True, gram=gram, side=side, after=after)
 
     def chains_collect(todo, which, handle, vals, refine):
         """Fill vals[i] = (|mean intercept|, BIC) and todo[i]['rr' / 'slot'] for the models `which`; returns True if a
@@ -584,12 +584,14 @@ def forward_select(engine, hy, m, n_phis, console=True, rng='philox', eager=Fals
     carry = None            # dict(S=previous substage, gen=its generator, todo, gram=its Gram before compaction, cnt0)
     while True:
         # ---- B(s) [+ chains of s - 1] ----
-        if carry is not None:
-            # the side batch goes first: its stream waits for what the main stream holds *now* (K1 + K2 of s, which
-            # it must not share the SMs with), not for the full model enqueued next
-            todo, vals, mine = carry['todo'], np.zeros((len(carry['todo']) + 1, 2)), my_share(carry['todo'])
-            side = chains_launch(todo, mine, gram=carry['gram'], side=True)
+        mark = engine.mark() if carry is not None else None
         handle = full_launch(S)
+        if carry is not None:
+            # the side batch's stream waits for what the main stream held at `mark` (K1 + K2 of s, which it must not
+            # share the SMs with), not for the full model just enqueued -- whose single cluster is launched first so that
+            # the batch's many clusters fill the device around it
+            todo, vals, mine = carry['todo'], np.zeros((len(carry['todo']) + 1, 2)), my_share(carry['todo'])
+            side = chains_launch(todo, mine, gram=carry['gram'], side=True, after=mark)
         full_finish(S, handle)
         # C(s) starts here: its kill-loop launch is enqueued before the host turns to the chains of s - 1, so the
         # collection / checks / bookkeeping of s - 1 (and any wait for a long side batch) run while that kernel does

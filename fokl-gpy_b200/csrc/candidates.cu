@@ -819,6 +819,7 @@ extern "C" int fokl_candidates_eval(fokl_ctx *ctx, const double *G, int64_t ldg,
             return (double)(n - 1) * (a * ((pairs + kEigJThreads / 32 - 1) / (kEigJThreads / 32)) + b);
         };
         int64_t ctas = 0;
+        const int sm_budget = (ctx->sm_budget > 0 && ctx->sm_budget < ctx->num_sms) ? ctx->sm_budget : ctx->num_sms;
         std::priority_queue<std::pair<double, int>> heap;
         for (int c = 0; c < n_cand; ++c) {
             ctas += std::max(eig_class[c], 1);
@@ -831,7 +832,7 @@ extern "C" int fokl_candidates_eval(fokl_ctx *ctx, const double *G, int64_t ldg,
             const int cs = eig_class[c], p = meta[c].p;
             int best = cs;
             double tb = t;
-            for (int c2 = cs * 2; c2 <= ctx->max_cluster && ctas - cs + c2 <= ctx->num_sms; c2 *= 2) {
+            for (int c2 = cs * 2; c2 <= ctx->max_cluster && ctas - cs + c2 <= sm_budget; c2 *= 2) {
                 const double t2 = est(p, c2);
                 if (t2 < 0.97 * t) { best = c2; tb = t2; break; }
             }

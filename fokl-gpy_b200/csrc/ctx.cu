@@ -112,6 +112,13 @@ extern "C" const char *fokl_last_error(fokl_ctx *ctx) { return ctx ? ctx->err.c_
 
 extern "C" int64_t fokl_launch_count(fokl_ctx *ctx) { return ctx ? ctx->launches : -1; }
 
+extern "C" int fokl_ctx_set_sm_budget(fokl_ctx *ctx, int sms)
+{
+    FOKL_CHECK_CTX(ctx);
+    ctx->sm_budget = sms > 0 ? sms : 0;
+    return FOKL_OK;
+}
+
 extern "C" int fokl_ctx_synchronize(fokl_ctx *ctx)
 {
     FOKL_CHECK_CTX(ctx);

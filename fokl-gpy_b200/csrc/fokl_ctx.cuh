@@ -19,6 +19,7 @@ struct fokl_ctx {
     std::string err;
     int64_t launches = 0;
     int num_sms = 148;
+    int sm_budget = 0;        // > 0: SMs a batch of candidate models may plan for (fokl_ctx_set_sm_budget)
     size_t smem_optin = 0;
     int max_cluster = 8;      // largest thread-block cluster the eigensolver may use (portable limit)
     bool cluster_probed = false;

@@ -54,6 +54,10 @@ const char *fokl_last_error(fokl_ctx *ctx);
 int fokl_ctx_synchronize(fokl_ctx *ctx);
 /* number of kernels this ctx has launched since creation (for bench.py's gpu_launches). */
 int64_t fokl_launch_count(fokl_ctx *ctx);
+/* SMs a batch of candidate models may plan its eigensolver clusters for (0 = the whole device).  A second context
+ * whose batches run next to another context's work (the pipelined selection loop) is given the device minus the
+ * other's share, so that the two together still fit in one wave. */
+int fokl_ctx_set_sm_budget(fokl_ctx *ctx, int sms);
 
 /* ---- basis tables: replaces getKernels.sp500()/bernoulli() output consumed at FR:1480-1482 ----
  * cubic:     tab (host) [n_orders][n_piece][4]  -- phis[s][k][piece] transposed to (s, piece, k)

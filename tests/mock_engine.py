@@ -130,7 +130,10 @@ class MockEngine:
             lik = -(n / 2) * np.log(siglik) - (n - 1) / 2
         return len(cols) * np.log(n) - 2 * lik
 
-    def evaluate_launch(self, col_sets, hyp, gram=None, side=False, **kw):
+    def mark(self):
+        return None
+
+    def evaluate_launch(self, col_sets, hyp, gram=None, side=False, after=None, **kw):
         self.calls.append(('launch', 'side' if side else 'main'))
         res = self.evaluate(col_sets, hyp, gram=gram, refine_tol=None, **kw)
         eng = self

@@ -91,6 +91,14 @@ def test_cfg4_full_size_properties(phis_cubic):
     assert np.array_equal(evs, evs2)
     _, betas3, mtx3, evs3 = _fit(FR, 'cfg4', phis_cubic, x, y, seed=4)
     assert np.array_equal(mtx, mtx3) and np.array_equal(evs2, evs3) and np.array_equal(betas2, betas3)
+    # (e') the pipelined selection loop (side context next to the main one: stream-ordering bugs show up at this size,
+    # where the full-model evaluation is long) == the sequential loop, bit for bit
+    FR.B200_CONFIG['pipeline'] = False
+    try:
+        _, betas4, mtx4, evs4 = _fit(FR, 'cfg4', phis_cubic, x, y, seed=4)
+    finally:
+        FR.B200_CONFIG['pipeline'] = True
+    assert np.array_equal(mtx, mtx4) and np.array_equal(evs2, evs4) and np.array_equal(betas2, betas4)
     # (f) row order does not matter: the same terms built in one go on a row-permuted copy of the dataset give the
     # same Gram (different summation order and a different K2 work plan: all columns in one launch) and the same BIC.
     import torch

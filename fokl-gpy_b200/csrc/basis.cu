@@ -69,11 +69,6 @@ struct BasisParams {
 };
 static_assert(sizeof(BasisParams) <= 32000, "kernel parameter space");
 
-__device__ __forceinline__ double eval_factor_cubic(const double *cf, double xs, double x2, double x3)
-{
-    return fokl::cubic_basis(cf[0], cf[1], cf[2], cf[3], xs, x2, x3);
-}
-
 // Bernoulli with on-the-fly correctly rounded powers (no local array)
 __device__ __forceinline__ double eval_factor_bernoulli(const double *c, int n_coef, double x)
 {

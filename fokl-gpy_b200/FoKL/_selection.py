@@ -1,18 +1,17 @@
 """Host side of the forward-selection loop of `FoKL.fit` (reference: src/FoKL/FoKLRoutines.py:1561-1760).
 
-The loop is inherently sequential in its stages; what it asks of the device per substage is
-  (1) append the new terms' columns to X and extend the Gram (K1 + K2),
-  (2) evaluate the full model (eig + BIC + Gibbs chain + column statistics),
-  (3) evaluate kill proposals -- here as *batches* of independent candidate models (one CTA each) instead
-      of one `gibbs` call at a time -- and
-  (4) drop the accepted kills (column / Gram compaction).
-The batching is exact: a proposal's outcome depends only on the kill set accepted so far and on the
-draws of the last accepted model (FR:1670-1690), so all proposals that pass the threshold test under the
-current state are evaluated together, the first (in the reference's order) that lowers the BIC is
-accepted, and the remainder is re-batched under the new state.
+The loop is inherently sequential in its stages; what it asks of the device per substage s is
+  A(s)  append the new terms' columns to X and extend the Gram (K1 + K2),
+  B(s)  evaluate the full model (eigensolver + BIC + Gibbs chain + column statistics, FR:1650),
+  C(s)  the kill loop FR:1666-1690 -- literally (one `gibbs`-equivalent evaluation per proposal: parity mode, eager
+        mode, degenerate Grams) or on the fast path: one device launch that walks all proposals on the sweep-operator
+        tableau of the model's Gram, followed by one batch of chains for the accepted models whose draws can influence a
+        later decision, each speculated outcome re-checked against its true chain -- and
+  D(s)  drop the accepted kills (column / Gram compaction) and the bookkeeping of FR:1701-1721.
+The fast path is exact: a proposal's outcome depends only on the kill set accepted so far and, through one threshold,
+on the draws of the last accepted model (FR:1670-1690).  `forward_select` drives these phases as a software pipeline
+(the batch of C(s) next to B(s + 1)); see the comment above its driver loop.
 """
-import math
-
 import numpy as np
 
 from . import _lib

@@ -285,11 +285,51 @@ def case_evaluate():
     print('evaluate', {k: np.shape(v) for k, v in out.items()})
 
 
+def case_clean():
+    """Pin clean / _format / _normalize / generate_trainlog (FR:251-543): outputs of the unmodified reference for the
+    keyword combinations the examples use (plain, explicit minmax, pillow in percent and absolute form, a random train
+    split drawn from the seeded global RNG, list-of-columns and 1-D inputs)."""
+    FR = ref_harness.load_reference()
+    import warnings
+    rng = np.random.default_rng(123)
+    x = rng.normal(size=(40, 3)) * [1.0, 10.0, 100.0] + [0.0, 5.0, -50.0]
+    y = rng.normal(size=40)
+    out = dict(x=x, y=y)
+    tab = np.load(os.path.join(GOLD, 'phis_cubic_48.npy'))
+    phis = spline_table.to_phis(tab)
+    variants = dict(
+        plain=dict(),
+        minmax=dict(minmax=[[-5.0, 5.0], [-40.0, 40.0], [-400.0, 400.0]]),
+        pillow_pct=dict(pillow=0.1),
+        pillow_abs=dict(pillow=[[0.5, 0.25], [1.0, 2.0], [3.0, 4.0]], pillow_type='absolute'),
+        train=dict(train=0.6),
+    )
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        for name, kw in variants.items():
+            model = FR.FoKL(phis=phis, UserWarnings=False)
+            np.random.seed(11)
+            model.clean(x, y, _setattr=True, **kw)
+            out[name + '_inputs'] = np.asarray(model.inputs)
+            out[name + '_data'] = np.asarray(model.data)
+            out[name + '_minmax'] = np.asarray(model.minmax, dtype=np.float64)
+            out[name + '_trainlog'] = np.zeros(0, dtype=bool) if model.trainlog is None else np.asarray(model.trainlog)
+            ti, td = model.trainset()
+            out[name + '_train_inputs'], out[name + '_train_data'] = np.asarray(ti), np.asarray(td)
+        model = FR.FoKL(phis=phis, UserWarnings=False)
+        out['cols_inputs'] = np.asarray(model.clean([x[:, 0], x[:, 1]]))
+        model = FR.FoKL(phis=phis, UserWarnings=False)
+        xi, yi = model.clean(x[:, 2], y)
+        out['oned_inputs'], out['oned_data'] = np.asarray(xi), np.asarray(yi)
+    np.savez_compressed(os.path.join(GOLD, 'clean.npz'), **out)
+    print('clean', {k: np.shape(v) for k, v in out.items()})
+
+
 CASES = dict(isotherm_gp=case_isotherm_gp, isotherm_qmax=case_isotherm_qmax,
              cfg2_default=lambda: case_cfg2(False), cfg2_changed=lambda: case_cfg2(True),
              cfg1_sigmoid=case_cfg1_sigmoid, way3_bernoulli=case_way3_bernoulli,
              way3_cubic=case_way3_cubic, two_way_cubic=case_two_way_cubic, m1_cubic=case_m1,
-             basis_values=case_basis_values, bss_derivatives=case_bss_derivatives, evaluate=case_evaluate)
+             basis_values=case_basis_values, bss_derivatives=case_bss_derivatives, evaluate=case_evaluate, clean=case_clean)
 
 if __name__ == '__main__':
     todo = sys.argv[1:] or list(CASES)

@@ -150,3 +150,41 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line['config']['workload'].startswith('cfg4') and line['dtype'] == 'f64'
     assert line['cpu_baseline']['kind'] == 'port' and line['cpu_baseline']['cores'] >= 1
     assert line['e2e'] == {'value': line['value'], 'unit': line['unit'], 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
+
+
+def test_clean_against_reference_golden(phis_cubic):
+    """Host `clean` (format, normalise with minmax / pillow, random train split from the seeded global RNG) against
+    outputs of the unmodified reference (tests/golden/clean.npz, oracle/gen_golden.py): bit-identical."""
+    import warnings
+    from conftest import load_golden
+    g = load_golden('clean')
+    x, y = g['x'], g['y']
+    variants = dict(
+        plain=dict(),
+        minmax=dict(minmax=[[-5.0, 5.0], [-40.0, 40.0], [-400.0, 400.0]]),
+        pillow_pct=dict(pillow=0.1),
+        pillow_abs=dict(pillow=[[0.5, 0.25], [1.0, 2.0], [3.0, 4.0]], pillow_type='absolute'),
+        train=dict(train=0.6),
+    )
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        for name, kw in variants.items():
+            model = FoKLRoutines.FoKL(phis=phis_cubic, UserWarnings=False)
+            np.random.seed(11)
+            model.clean(x, y, _setattr=True, **kw)
+            assert np.array_equal(np.asarray(model.inputs), g[name + '_inputs']), name
+            assert np.array_equal(np.asarray(model.data), g[name + '_data']), name
+            assert np.array_equal(np.asarray(model.minmax, dtype=np.float64), g[name + '_minmax']), name
+            want_log = g[name + '_trainlog']
+            if want_log.size == 0:
+                assert model.trainlog is None, name
+            else:
+                assert np.array_equal(model.trainlog, want_log), name
+            ti, td = model.trainset()
+            assert np.array_equal(np.asarray(ti), g[name + '_train_inputs']), name
+            assert np.array_equal(np.asarray(td), g[name + '_train_data']), name
+        model = FoKLRoutines.FoKL(phis=phis_cubic, UserWarnings=False)
+        assert np.array_equal(np.asarray(model.clean([x[:, 0], x[:, 1]])), g['cols_inputs'])
+        model = FoKLRoutines.FoKL(phis=phis_cubic, UserWarnings=False)
+        xi, yi = model.clean(x[:, 2], y)
+        assert np.array_equal(np.asarray(xi), g['oned_inputs']) and np.array_equal(np.asarray(yi), g['oned_data'])

@@ -325,11 +325,38 @@ def case_clean():
     print('clean', {k: np.shape(v) for k, v in out.items()})
 
 
+def case_constructor():
+    """Pin the constructor's attribute set and defaults (FR:111-246) as JSON: tests/golden/constructor.json."""
+    import json
+    import warnings
+    FR = ref_harness.load_reference()
+    warnings.simplefilter('ignore')
+
+    def dump(m):
+        d = {}
+        for k, v in vars(m).items():
+            if k == 'phis':
+                d[k] = [len(v), len(v[0])]
+            elif isinstance(v, (list, tuple)):
+                d[k] = list(v)
+            elif isinstance(v, np.generic):
+                d[k] = v.item()
+            else:
+                d[k] = v
+        return d
+    out = {'default_kernel1': dump(FR.FoKL(kernel=1)),
+           'custom': dump(FR.FoKL(kernel='Bernoulli Polynomials', a=9, b=0.01, atau=3, btau=4000, aic=True, tolerance=5,
+                                  draws=200, burnin=50, way3=True, gimmie=True, threshav=0.1, threshstda=0.4,
+                                  threshstdb=3, UserWarnings=False, ConsoleOutput=False))}
+    json.dump(out, open(os.path.join(GOLD, 'constructor.json'), 'w'), indent=1, sort_keys=True)
+    print('constructor', sorted(out['default_kernel1']))
+
+
 CASES = dict(isotherm_gp=case_isotherm_gp, isotherm_qmax=case_isotherm_qmax,
              cfg2_default=lambda: case_cfg2(False), cfg2_changed=lambda: case_cfg2(True),
              cfg1_sigmoid=case_cfg1_sigmoid, way3_bernoulli=case_way3_bernoulli,
              way3_cubic=case_way3_cubic, two_way_cubic=case_two_way_cubic, m1_cubic=case_m1,
-             basis_values=case_basis_values, bss_derivatives=case_bss_derivatives, evaluate=case_evaluate, clean=case_clean)
+             basis_values=case_basis_values, bss_derivatives=case_bss_derivatives, evaluate=case_evaluate, clean=case_clean, constructor=case_constructor)
 
 if __name__ == '__main__':
     todo = sys.argv[1:] or list(CASES)

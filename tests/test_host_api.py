@@ -188,3 +188,36 @@ def test_clean_against_reference_golden(phis_cubic):
         model = FoKLRoutines.FoKL(phis=phis_cubic, UserWarnings=False)
         xi, yi = model.clean(x[:, 2], y)
         assert np.array_equal(np.asarray(xi), g['oned_inputs']) and np.array_equal(np.asarray(yi), g['oned_data'])
+
+
+def test_constructor_state_equals_the_reference():
+    """Attribute set, defaults, `hypers` / `keep` lists of a fresh model == the unmodified reference's
+    (tests/golden/constructor.json, oracle/gen_golden.py)."""
+    import json
+    import warnings
+    from conftest import GOLD
+    want = json.load(open(os.path.join(GOLD, 'constructor.json')))
+
+    def dump(m):
+        d = {}
+        for k, v in vars(m).items():
+            if k.startswith('_'):
+                continue
+            if k == 'phis':
+                d[k] = [len(v), len(v[0])]
+            elif isinstance(v, (list, tuple)):
+                d[k] = list(v)
+            elif isinstance(v, np.generic):
+                d[k] = v.item()
+            else:
+                d[k] = v
+        return d
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        got = {'default_kernel1': dump(FoKLRoutines.FoKL(kernel=1)),
+               'custom': dump(FoKLRoutines.FoKL(kernel='Bernoulli Polynomials', a=9, b=0.01, atau=3, btau=4000, aic=True,
+                                                tolerance=5, draws=200, burnin=50, way3=True, gimmie=True, threshav=0.1,
+                                                threshstda=0.4, threshstdb=3, UserWarnings=False, ConsoleOutput=False))}
+    for case in want:
+        assert got[case] == want[case], (case, {k: (got[case].get(k), want[case].get(k)) for k in
+                                               set(got[case]) | set(want[case]) if got[case].get(k) != want[case].get(k)})

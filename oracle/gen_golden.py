@@ -352,11 +352,36 @@ def case_constructor():
     print('constructor', sorted(out['default_kernel1']))
 
 
+def case_ref_pickle():
+    """A model trained and saved by the unmodified reference (`save`, FR:1807-1846): tests/golden/ref_model.fokl, plus
+    what the reference's own `evaluate` returns for it -- the drop-in must load the file and predict the same."""
+    import shutil
+    import tempfile
+    import warnings
+    FR = ref_harness.load_reference()
+    rng = np.random.default_rng(55)
+    x = rng.random((60, 2))
+    y = np.sin(2 * np.pi * x[:, 0]) + x[:, 0] * x[:, 1] + 0.05 * rng.standard_normal(60)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        np.random.seed(55)
+        model = FR.FoKL(kernel=1, draws=40, burnin=40, UserWarnings=False, ConsoleOutput=False)
+        model.fit(x, y, clean=True)
+        mean, bounds = model.evaluate(ReturnBounds=1)          # fixes model.setnos, which is saved with the model
+        tmp = tempfile.mkdtemp()
+        path = model.save(os.path.join(tmp, 'ref_model'))
+        shutil.copy(path, os.path.join(GOLD, 'ref_model.fokl'))
+    np.savez_compressed(os.path.join(GOLD, 'ref_model_expect.npz'), betas=model.betas, mtx=model.mtx, evs=model.evs,
+                        inputs=np.asarray(model.inputs), data=np.asarray(model.data), minmax=np.asarray(model.minmax),
+                        setnos=np.asarray(model.setnos), mean=mean, bounds=bounds)
+    print('ref_pickle', os.path.getsize(os.path.join(GOLD, 'ref_model.fokl')), 'bytes; terms', model.mtx.shape)
+
+
 CASES = dict(isotherm_gp=case_isotherm_gp, isotherm_qmax=case_isotherm_qmax,
              cfg2_default=lambda: case_cfg2(False), cfg2_changed=lambda: case_cfg2(True),
              cfg1_sigmoid=case_cfg1_sigmoid, way3_bernoulli=case_way3_bernoulli,
              way3_cubic=case_way3_cubic, two_way_cubic=case_two_way_cubic, m1_cubic=case_m1,
-             basis_values=case_basis_values, bss_derivatives=case_bss_derivatives, evaluate=case_evaluate, clean=case_clean, constructor=case_constructor)
+             basis_values=case_basis_values, bss_derivatives=case_bss_derivatives, evaluate=case_evaluate, clean=case_clean, constructor=case_constructor, ref_pickle=case_ref_pickle)
 
 if __name__ == '__main__':
     todo = sys.argv[1:] or list(CASES)

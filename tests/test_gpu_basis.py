@@ -213,3 +213,21 @@ def test_evaluate_and_coverage3_against_reference_golden(name, phis_cubic, phis_
         close(cm, g[name + '_cov_mean'])
         close(cb, g[name + '_cov_bounds'])
         assert abs(float(rmse) - float(g[name + '_cov_rmse'])) < 1e-9 * scale
+
+
+@pytest.mark.gpu
+def test_model_saved_by_the_reference_predicts_the_same():
+    """tests/golden/ref_model.fokl was trained, evaluated and pickled by the unmodified reference; loaded here, the
+    device `evaluate` must return the reference's own mean and bounds (rtol 1e-9 of the output scale)."""
+    import os
+    import warnings
+    from FoKL import FoKLRoutines as FR
+    from conftest import GOLD
+    g = np.load(os.path.join(GOLD, 'ref_model_expect.npz'))
+    model = FR.load(os.path.join(GOLD, 'ref_model.fokl'))
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        mean, bounds = model.evaluate(ReturnBounds=1)
+    scale = np.max(np.abs(g['mean']))
+    assert np.max(np.abs(mean - g['mean'])) < 1e-9 * scale
+    assert np.max(np.abs(bounds - g['bounds'])) < 1e-9 * scale

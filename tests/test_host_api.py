@@ -221,3 +221,39 @@ def test_constructor_state_equals_the_reference():
     for case in want:
         assert got[case] == want[case], (case, {k: (got[case].get(k), want[case].get(k)) for k in
                                                set(got[case]) | set(want[case]) if got[case].get(k) != want[case].get(k)})
+
+
+def test_loads_a_model_saved_by_the_reference():
+    """`FoKLRoutines.load` on tests/golden/ref_model.fokl -- trained and pickled by the unmodified reference
+    (oracle/gen_golden.py) -- gives a model of this package's FoKL class with the reference's attributes."""
+    from conftest import GOLD
+    g = np.load(os.path.join(GOLD, 'ref_model_expect.npz'))
+    model = FoKLRoutines.load(os.path.join(GOLD, 'ref_model.fokl'))
+    assert type(model) is FoKLRoutines.FoKL and model.kernel == 'Bernoulli Polynomials'
+    for key in ('betas', 'mtx', 'evs', 'setnos'):
+        assert np.array_equal(np.asarray(getattr(model, key)), g[key]), key
+    assert np.array_equal(np.asarray(model.inputs), g['inputs']) and np.array_equal(np.asarray(model.data), g['data'])
+    assert np.array_equal(np.asarray(model.minmax, dtype=np.float64), g['minmax'])
+    assert model.draws == 40 and model.burnin == 40 and len(model.phis) == 20
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/src'), reason='the reference is only present in the build container')
+def test_reference_loads_a_model_saved_here(tmp_path, phis_bern):
+    """The other direction of the save/load layout: a model pickled by this package (attributes set by hand -- no GPU
+    here) is loaded by the unmodified reference's `load` as its own FoKL class, attributes intact."""
+    import subprocess
+    import sys
+    from conftest import ROOT
+    model = FoKLRoutines.FoKL(kernel=1, draws=7, burnin=3, UserWarnings=False, ConsoleOutput=False)
+    model.betas = np.arange(21.0).reshape(7, 3)
+    model.mtx = np.array([[1.0, 0.0], [0.0, 2.0]])
+    model.evs = np.array([-1.0, -2.0])
+    model.inputs, model.data, model.minmax = np.random.rand(5, 2), np.random.rand(5, 1), [[0.0, 1.0], [0.0, 1.0]]
+    path = model.save(str(tmp_path / 'mine'))
+    code = ("import sys, numpy as np; sys.path.insert(0, %r); import ref_harness; FR = ref_harness.load_reference(); "
+            "m = FR.load(%r); assert type(m).__module__ == 'FoKL.FoKLRoutines' and m.__class__ is FR.FoKL; "
+            "assert m.betas.shape == (7, 3) and m.draws == 7 and m.kernel == 'Bernoulli Polynomials'; "
+            "assert np.array_equal(m.mtx, [[1.0, 0.0], [0.0, 2.0]]) and len(m.phis) == 20; print('ok')"
+            % (os.path.join(ROOT, 'oracle'), path))
+    out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and out.stdout.strip().endswith('ok'), out.stderr[-1500:]

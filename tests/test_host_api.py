@@ -257,3 +257,13 @@ def test_reference_loads_a_model_saved_here(tmp_path, phis_bern):
             % (os.path.join(ROOT, 'oracle'), path))
     out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0 and out.stdout.strip().endswith('ok'), out.stderr[-1500:]
+
+
+def test_bernoulli_table_equals_the_reference_table(bern_table):
+    """getKernels.bernoulli() -- the only phis table upstream ships -- against the reference's own loader output
+    (tests/golden/bernoulli_table.npy, SURVEY section 8c KAT 4): same structure, same bits."""
+    phis = getKernels.bernoulli()
+    assert len(phis) == bern_table.shape[0] == 20
+    for n, row in enumerate(phis):
+        assert len(row) == n + 2
+        assert np.array_equal(np.asarray(row, dtype=np.float64), bern_table[n, :n + 2])

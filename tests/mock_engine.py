@@ -40,9 +40,18 @@ class MockEngine:
         self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
         return t.numpy()
 
+    # forward_select's parity mode indexes engine.G / engine.Xty as torch tensors (Engine keeps them in HBM)
+    @property
+    def G(self):
+        return torch.from_numpy(self._G)
+
+    @property
+    def Xty(self):
+        return torch.from_numpy(self._Xty)
+
     def _gram(self):
-        self.G = self._sum(self.X.T @ self.X)
-        self.Xty = self._sum(self.X.T @ self.y)
+        self._G = np.ascontiguousarray(self._sum(self.X.T @ self.X))
+        self._Xty = np.ascontiguousarray(self._sum(self.X.T @ self.y))
         self.P = self.X.shape[1]
 
     # ---- K1 / K2 / compaction ----------------------------------------------------------------------------------
@@ -61,16 +70,16 @@ class MockEngine:
         if len(keep) == self.P:
             return
         self.X = self.X[:, keep]
-        self.G = self.G[np.ix_(keep, keep)].copy()
-        self.Xty = self.Xty[keep].copy()
+        self._G = self._G[np.ix_(keep, keep)].copy()
+        self._Xty = self._Xty[keep].copy()
         self.P = len(keep)
 
     def truncate(self, p):
         """Drop the columns from p on (roll-back of a speculative append)."""
         self.calls.append(('truncate', p))
         self.X = self.X[:, :p]
-        self.G = self.G[:p, :p].copy()
-        self.Xty = self.Xty[:p].copy()
+        self._G = self._G[:p, :p].copy()
+        self._Xty = self._Xty[:p].copy()
         self.P = p
 
     # ---- K3 / K4 ----------------------------------------------------------------------------------------------
@@ -80,8 +89,12 @@ class MockEngine:
 
     def evaluate(self, col_sets, hyp, rng_mode=_lib.RNG_NONE, run_chain=None, seed=0, stream_ids=None, variates=None,
                  sign_fix=None, want_betas=False, want_eig=False, refine_tol=1e-7, gram=None):
-        G, Xty = gram if gram is not None else (self.G, self.Xty)
+        G, Xty = gram if gram is not None else (self._G, self._Xty)
         self.calls.append(('evaluate', [len(s) for s in col_sets]))
+        if variates is not None and torch.is_tensor(variates):
+            variates = variates.numpy()
+        if sign_fix is not None and torch.is_tensor(sign_fix):
+            sign_fix = sign_fix.numpy()
         n_cand = len(col_sets)
         p = np.array([len(s) for s in col_sets], dtype=np.int64)
         D = int(hyp['draws'])
@@ -91,11 +104,22 @@ class MockEngine:
         res.vec_off = np.concatenate([[0], np.cumsum(p)[:-1]]).astype(np.int64)
         res.mat_off = np.concatenate([[0], np.cumsum(p * p)[:-1]]).astype(np.int64)
         ev = np.zeros(n_cand)
-        stats, betas, betahat = [], [], []
+        stats, betas, betahat, qs, lambs = [], [], [], [], []
         for c, cols in enumerate(col_sets):
             chain = rng_mode != _lib.RNG_NONE and (run_chain is None or bool(run_chain[c]))
+            pc = len(cols)
+            var_c = sf_c = None
+            if chain and rng_mode == _lib.RNG_INJECTED:
+                # packed like the C ABI: candidate c at D * (vec_off[c] + 2 c), D rows of [z_0 .. z_{p-1}, g1, g2]
+                o = D * (int(res.vec_off[c]) + 2 * c)
+                var_c = np.asarray(variates).reshape(-1)[o:o + D * (pc + 2)].reshape(D, pc + 2)
+                if sign_fix is not None:
+                    sf_c = np.asarray(sign_fix).reshape(-1)[int(res.vec_off[c]):int(res.vec_off[c]) + pc]
             r = emu.candidate(G, Xty, np.asarray(cols, dtype=np.int32), hyp, rng_mode=rng_mode if chain else 0,
-                              seed=int(seed), stream=int(stream_ids[c]) if stream_ids is not None else 0)
+                              seed=int(seed), stream=int(stream_ids[c]) if stream_ids is not None else 0,
+                              variates=var_c, sign_fix=sf_c)
+            qs.append(r['Q'].T.reshape(-1))             # row r of the p x p block = eigenvector r, like the device
+            lambs.append(r['lamb'])
             ev[c] = r['ev']
             betahat.append(r['betahat'])
             b = r['betas'] if chain else np.zeros((D, len(cols)))
@@ -107,7 +131,9 @@ class MockEngine:
         res.stats = torch.from_numpy(np.concatenate(stats))
         res.betas = torch.from_numpy(np.concatenate(betas))
         res.betahat = torch.from_numpy(np.concatenate(betahat))
-        res.sigs = res.taus = res.lamb = res.Q = None
+        res.sigs = res.taus = None
+        res.lamb = torch.from_numpy(np.concatenate(lambs)) if want_eig else None
+        res.Q = torch.from_numpy(np.concatenate(qs)) if want_eig else None
         self._refine(res, col_sets, refine_tol, gram)
         return res
 
@@ -145,13 +171,13 @@ class MockEngine:
         return Handle()
 
     def gram_state(self):
-        return (self.G, self.Xty)
+        return (self._G, self._Xty)
 
     refine_mask = Engine.refine_mask
 
     def kill_loop(self, cols, cand_pos, bv0, bv1, hyp, threshav, threshstda, threshstdb, icpt, evmin, aic_adj, start):
         self.calls.append(('kill_loop', len(cand_pos)))
-        return emu.kill_loop(self.G, self.Xty, cols, cand_pos, bv0, bv1, hyp, threshav=threshav, threshstda=threshstda,
+        return emu.kill_loop(self._G, self._Xty, cols, cand_pos, bv0, bv1, hyp, threshav=threshav, threshstda=threshstda,
                              threshstdb=threshstdb, icpt=icpt, evmin=evmin, aic_adj=aic_adj, start=start)
 
     def kill_loop_launch(self, *args):

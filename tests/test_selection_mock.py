@@ -103,3 +103,36 @@ def test_interpolating_model_takes_the_literal_path(phis_cubic):
         assert np.array_equal(fast['mtx'], other['mtx']) and np.array_equal(fast['evs'], other['evs'])
         assert np.array_equal(fast['betas'], other['betas']) and fast['n_gibbs'] == other['n_gibbs']
     assert any(c[0] == 'refine' for c in eng_f.calls) and not any(c[0] == 'kill_loop' for c in eng_f.calls)
+
+
+def _digest():
+    import hashlib
+    st = np.random.get_state()
+    return hashlib.sha256(st[1].tobytes() + bytes(str((st[2], st[3], repr(st[4]))), 'ascii')).hexdigest()
+
+
+@pytest.mark.parametrize('n,m,seed,way3,aic', [(120, 2, 3, False, False), (150, 3, 4, True, False), (100, 2, 5, False, True)])
+def test_parity_mode_equals_the_oracle_fit(phis_cubic, n, m, seed, way3, aic):
+    """The whole host loop in parity mode (numpy variates injected in the reference's order, eigenvector signs aligned
+    with LAPACK) on the stand-in engine against the oracle's `fit` -- which is pinned to the unmodified reference: same
+    term matrix, same number of `gibbs` calls, same RNG end state, BIC trace and draws to rtol 1e-9 / 1e-7."""
+    x, y = _data(n, m, seed)
+    D = 60
+    a, atau = 4.0, 4.0
+    b, btau = fo.default_b_btau(y, a, atau)
+    np.random.seed(seed)
+    want = fo.fit(x, y, phis_cubic, kernel=fo.CUBIC, a=a, b=b, atau=atau, btau=btau, tolerance=3, burnin=D // 2,
+                  draws=D // 2, way3=way3, aic=aic)
+    want_digest = _digest()
+    eng = MockEngine(x, y, phis_cubic, fo.CUBIC)
+    hy = dict(a=a, b=b, atau=atau, btau=btau, tolerance=3, total_draws=D, gimmie=False, way3=way3, threshav=0.05,
+              threshstda=0.5, threshstdb=2.0, aic=aic)
+    np.random.seed(seed)
+    got = _selection.forward_select(eng, hy, m, len(phis_cubic), console=False, rng='numpy')
+    assert np.array_equal(got['mtx'], want.mtx)
+    assert got['n_gibbs'] == want.n_gibbs and _digest() == want_digest
+    assert np.allclose(got['evs'], want.evs, rtol=1e-9, atol=0)
+    full = np.asarray(want.betas_full)
+    assert got['betas'].shape == full.shape
+    if full.shape[1] < n // 3:       # the draws of a nearly saturated model (p ~ N) hinge on degenerate eigen-directions
+        assert np.allclose(got['betas'], full, rtol=1e-7, atol=1e-7 * np.max(np.abs(full)))

@@ -531,6 +531,8 @@ class Engine:
         t = None
         if side:
             ctx = self._side()
+            with torch.cuda.stream(self.side_stream):
+                t = self._tic()
         else:
             t = self._tic()
         rc = self.lib.fokl_candidates_eval(
@@ -541,7 +543,10 @@ class Engine:
         if rc != 0:
             msg = self.lib.fokl_last_error(ctx)
             raise RuntimeError("libfokl_b200 error %d: %s" % (rc, msg.decode() if msg else ''))
-        if not side:
+        if side:
+            with torch.cuda.stream(self.side_stream):
+                self._toc(t, 'side_batch', cands=n_cand, pmax=int(p.max()), psum=int(p.sum()))
+        else:
             self._toc(t, 'candidates_chain' if chain_any else 'candidates_bic', cands=n_cand, pmax=int(p.max()))
         self.gibbs_launch_batches += 1
         res = CandidateResult()

@@ -12,7 +12,7 @@ SO_PATH = os.path.join(CSRC, 'libfokl_b200.so')
 if os.environ.get('FOKL_B200_LIB'):        # kernel-variant experiments (tools/): another build of the same sources
     SO_PATH = os.path.abspath(os.environ['FOKL_B200_LIB'])
 SOURCES = ['ctx.cu', 'basis.cu', 'gram.cu', 'candidates.cu']
-HEADERS = ['fokl_ctx.cuh', 'fokl_math.cuh', 'cand_math.cuh', 'gram_plan.h']
+HEADERS = ['fokl_ctx.cuh', 'fokl_math.cuh', 'cand_math.cuh', 'gram_plan.h', 'eigbig.cuh', 'killbig.cuh']
 
 ABI_VERSION = 1
 KERNEL_CUBIC, KERNEL_BERNOULLI = 0, 1

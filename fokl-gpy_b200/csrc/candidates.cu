@@ -8,6 +8,8 @@
 #include "fokl_ctx.cuh"
 #include <stdlib.h>
 #include "cand_math.cuh"
+#include "eigbig.cuh"
+#include "killbig.cuh"
 #include <cooperative_groups.h>
 #include <algorithm>
 #include <queue>
@@ -115,8 +117,8 @@ __global__ void __launch_bounds__(kCholThreads) cand_chol_kernel(const CholParam
     extern __shared__ __align__(16) double sh[];
     const Team t = make_team();
     const CandMeta m = P.meta[blockIdx.x];
-    if (m.pad) {                       // too large for the cluster eigensolver: straight to the fallback kernel
-        if (t.tid == 0) P.info[blockIdx.x] = 4;
+    if (m.pad) {                       // too large for the cluster eigensolver: blocked solver (2) or fallback kernel (1)
+        if (t.tid == 0) P.info[blockIdx.x] = (m.pad == 2) ? 8 : 4;
         return;
     }
     const int p = m.p;
@@ -464,6 +466,40 @@ __global__ void __launch_bounds__(kEigJThreads, 1) cand_eigj_kernel(const EigJPa
     }
 }
 
+// betahat + BIC of the candidates factorised by the blocked eigensolver (eigbig.cuh), one CTA each
+struct OlsParams {
+    const double *G;
+    int64_t ldg;
+    const double *Xty;
+    const int32_t *col_sets;
+    const CandMeta *meta;
+    const int32_t *list;
+    CandConst k;
+    double *scratch, *ct, *lamb, *Q, *betahat, *ev;
+    int32_t *info;
+    const int32_t *sweeps;
+};
+
+__global__ void __launch_bounds__(1024) cand_ols_kernel(const OlsParams P)
+{
+    __shared__ double red[2 * 3 * 32];
+    const Team t = make_team();
+    const int cand = P.list[blockIdx.x];
+    const int st = P.sweeps[cand];
+    if (st < 0) {                      // Gram not positive definite: the two-matrix fallback kernel takes the model
+        if (t.tid == 0) P.info[cand] = 2;
+        return;
+    }
+    const CandMeta cm = P.meta[cand];
+    const int32_t *idx = P.col_sets + cm.set_off;
+    double ev = fokl::ols_and_bic(t, P.G, P.ldg, P.Xty, idx, cm.p, P.lamb + cm.vec_off, P.Q + cm.mat_off, P.k,
+                                  P.ct + cm.vec_off, P.betahat + cm.vec_off, P.scratch + cm.vec_off, red);
+    if (t.tid == 0) {
+        P.ev[cand] = ev;
+        P.info[cand] = (st << 8) | (st >= eigb::kMaxSweeps ? 16 : 0);
+    }
+}
+
 struct ChainParams {
     const CandMeta *meta;
     const int32_t *chain_list;
@@ -771,6 +807,11 @@ extern "C" int fokl_candidates_eval(fokl_ctx *ctx, const double *G, int64_t ldg,
     }
     int force_cs = 0;                    // tuning knob for tools/eig_batch_diag.py: force the eigensolver's cluster size
     if (const char *e = getenv("FOKL_EIGJ_CS")) force_cs = atoi(e);
+    // models at least this wide go to the blocked DMMA eigensolver (eigbig.cuh) instead of the cluster solver
+    int eigb_min_p = 64 * kEigJMaxNV + 1;
+    if (const char *e = getenv("FOKL_EIGB_MIN_P")) eigb_min_p = std::max(2, atoi(e));
+    eigb_min_p = std::min(eigb_min_p, 64 * kEigJMaxNV + 1);
+    std::vector<int32_t> big_list;
     if (force_cs != 1 && force_cs != 2 && force_cs != 4 && force_cs != 8 && force_cs != 16) force_cs = 0;
     std::vector<CandMeta> meta(n_cand);
     std::vector<int32_t> chain_list;
@@ -785,15 +826,19 @@ extern "C" int fokl_candidates_eval(fokl_ctx *ctx, const double *G, int64_t ldg,
         m.p = p; m.set_off = set_offsets[c]; m.pad = 0;
         m.vec_off = vec; m.mat_off = mat;
         // cluster size of the Jacobi eigensolver: the smallest whose column buffers fit in shared memory; raised below
-        {
+        if (p >= eigb_min_p) {
+            m.pad = 2;                                                     // blocked one-sided Jacobi on the tensor pipe
+            big_list.push_back(c);
+        } else {
             int cs = force_cs > 0 ? force_cs : 1;
             while (cs <= kEigJMaxCluster && eigj_smem_bytes(p, cs) > smem_cap) cs *= 2;
-            if (cs > ctx->max_cluster || p > 64 * kEigJMaxNV) m.pad = 1;   // too large: two-matrix Jacobi in global memory
+            if (cs > ctx->max_cluster) { m.pad = 2; big_list.push_back(c); }   // no cluster of that size on this device
             else eig_class[c] = cs;
         }
+        // W | V workspace of the two-matrix fallback (Gram not positive definite): only models of the cluster class
         const bool in_smem = (2 * (int64_t)p * p <= smem_wv_cap);
         m.wv_off = wv;
-        if (!in_smem) wv += 2 * (int64_t)p * p;
+        if (!in_smem && m.pad != 2) wv += 2 * (int64_t)p * p;
         const bool chain = rng_mode != FOKL_RNG_NONE && (!run_chain || run_chain[c]);
         m.chain_idx = chain ? (int32_t)chain_list.size() : -1;
         m.gam_off = gam;
@@ -843,6 +888,38 @@ extern "C" int fokl_candidates_eval(fokl_ctx *ctx, const double *G, int64_t ldg,
         }
     }
 
+    // ---- plan of the blocked eigensolver (models too wide for a cluster) -------------------------------------
+    const int n_big = (int)big_list.size();
+    const int sm_budget_b = (ctx->sm_budget > 0 && ctx->sm_budget < ctx->num_sms) ? ctx->sm_budget : ctx->num_sms;
+    std::vector<eigb::Job> jobs;
+    int64_t wbig = 0;
+    int eigb_team = 1, eigb_teams = 0, eigb_nb_max = 2;
+    if (n_big > 0) {
+        std::sort(big_list.begin(), big_list.end(), [&](int x, int y) { return meta[x].p > meta[y].p || (meta[x].p == meta[y].p && x < y); });
+        for (int c : big_list) {
+            eigb::Job J;
+            J.cand = c; J.p = meta[c].p; J.ld = (meta[c].p + 15) & ~15;
+            J.nb = (meta[c].p + eigb::kB - 1) / eigb::kB; J.nb += J.nb & 1;
+            J.set_off = meta[c].set_off; J.pad = 0;
+            J.w_off = wv + wbig; J.vec_off = meta[c].vec_off; J.mat_off = meta[c].mat_off;
+            meta[c].wv_off = J.w_off;                  // the not-positive-definite fallback reuses the area as W | V
+            wbig += 2 * (int64_t)J.ld * J.nb * eigb::kB;
+            eigb_nb_max = std::max(eigb_nb_max, (int)J.nb);
+            jobs.push_back(J);
+        }
+        int occ = 0;
+        FOKL_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, eigb::eigb_kernel, eigb::kThreads, eigb::kSmemBytes));
+        if (occ < 1) FOKL_FAIL(ctx, FOKL_ECUDA, "candidates_eval: blocked eigensolver does not fit an SM");
+        const int resident = occ * sm_budget_b;
+        // teams: as many models in flight as keep their W matrices L2-resident (~96 MB), one CTA per block pair at most
+        const int pairs_max = jobs[0].nb / 2;
+        const int64_t w_bytes = (int64_t)jobs[0].ld * jobs[0].nb * eigb::kB * (int64_t)sizeof(double);
+        int in_flight = (int)std::max<int64_t>(1, std::min<int64_t>(n_big, (96ll << 20) / std::max<int64_t>(w_bytes, 1)));
+        if (const char *e = getenv("FOKL_EIGB_TEAM")) eigb_team = std::max(1, atoi(e));
+        else eigb_team = std::max(1, std::min(pairs_max, resident / in_flight));
+        eigb_team = std::min(eigb_team, resident);
+        eigb_teams = std::max(1, std::min(n_big, resident / eigb_team));
+    }
     // ---- metadata upload ---------------------------------------------------------------------------------
     std::vector<int32_t> eig_list;                 // candidates grouped by cluster size
     int class_begin[6] = {0, 0, 0, 0, 0, 0};       // cs = 1, 2, 4, 8, 16
@@ -855,7 +932,8 @@ extern "C" int fokl_candidates_eval(fokl_ctx *ctx, const double *G, int64_t ldg,
     class_begin[5] = (int)eig_list.size();
     for (int c = 0; c < n_cand; ++c) any_fallback = any_fallback || meta[c].pad;
     size_t meta_bytes = 64 + (size_t)total_p * sizeof(int32_t) + (size_t)n_cand * sizeof(CandMeta) +
-                        (size_t)(n_chain + 1) * sizeof(int32_t) + (size_t)(n_cand + 1) * sizeof(int32_t) + 96;
+                        (size_t)(n_chain + 1) * sizeof(int32_t) + (size_t)(n_cand + 1) * sizeof(int32_t) + 96 +
+                        (size_t)(big_list.size() + 1) * (sizeof(eigb::Job) + sizeof(int32_t)) + 64;
     char *dmeta = (char *)fokl_scratch(ctx, fokl_ctx::B_META, meta_bytes);
     if (!dmeta) return FOKL_ENOMEM;
     std::vector<char> hmeta(meta_bytes, 0);
@@ -864,6 +942,12 @@ extern "C" int fokl_candidates_eval(fokl_ctx *ctx, const double *G, int64_t ldg,
     CandMeta *d_meta = carve<CandMeta>(dcur, n_cand);
     int32_t *d_chain = carve<int32_t>(dcur, n_chain + 1);
     int32_t *d_eig_list = carve<int32_t>(dcur, n_cand + 1);
+    int32_t *d_big_list = carve<int32_t>(dcur, n_big + 1);
+    eigb::Job *d_jobs = carve<eigb::Job>(dcur, n_big + 1);
+    if (n_big) {
+        memcpy(hmeta.data() + ((char *)d_big_list - dmeta), big_list.data(), (size_t)n_big * sizeof(int32_t));
+        memcpy(hmeta.data() + ((char *)d_jobs - dmeta), jobs.data(), (size_t)n_big * sizeof(eigb::Job));
+    }
     if (!eig_list.empty())
         memcpy(hmeta.data() + ((char *)d_eig_list - dmeta), eig_list.data(), eig_list.size() * sizeof(int32_t));
     memcpy(hmeta.data() + ((char *)d_sets - dmeta), col_sets, (size_t)total_p * sizeof(int32_t));
@@ -873,8 +957,8 @@ extern "C" int fokl_candidates_eval(fokl_ctx *ctx, const double *G, int64_t ldg,
 
     // ---- workspaces --------------------------------------------------------------------------------------
     double *d_wv = nullptr;
-    if (wv > 0) {
-        d_wv = (double *)fokl_scratch(ctx, fokl_ctx::B_CAND_A, (size_t)wv * sizeof(double));
+    if (wv + wbig > 0) {
+        d_wv = (double *)fokl_scratch(ctx, fokl_ctx::B_CAND_A, (size_t)(wv + wbig) * sizeof(double));
         if (!d_wv) return FOKL_ENOMEM;
     }
     size_t b_bytes = 512 + (size_t)vec * (6 * sizeof(double) + sizeof(int32_t)) + (size_t)n_cand * 64 * sizeof(double) +
@@ -995,6 +1079,37 @@ extern "C" int fokl_candidates_eval(fokl_ctx *ctx, const double *G, int64_t ldg,
             rc = fokl_aux_join(ctx, i);
             if (rc) return rc;
         }
+    }
+    if (n_big > 0) {
+        // Cholesky + blocked one-sided Jacobi (eigbig.cuh): one cooperative launch, teams of CTAs fetch models from a
+        // dispenser
+        const int vstride = (eigb_nb_max + 31) & ~31;
+        const size_t sync_ints = (size_t)eigb_teams * (2 + eigb::kFlagStride + vstride) + 32 + (size_t)n_cand;
+        int *d_sync = (int *)fokl_scratch(ctx, fokl_ctx::B_MISC, sync_ints * sizeof(int));
+        if (!d_sync) return FOKL_ENOMEM;
+        FOKL_CUDA(ctx, cudaMemsetAsync(d_sync, 0, sync_ints * sizeof(int), ctx->stream));
+        eigb::Params E;
+        E.G = G; E.ldg = ldg; E.col_sets = d_sets; E.jobs = d_jobs; E.n_jobs = n_big; E.team = eigb_team;
+        E.W = d_wv; E.lam_raw = d_lam_all; E.lamb = d_lamb; E.Q = d_Q;
+        E.bar = reinterpret_cast<unsigned *>(d_sync);
+        E.slot = d_sync + eigb_teams;
+        E.next = d_sync + 2 * eigb_teams;
+        E.flags = d_sync + 2 * eigb_teams + 32;
+        E.ver = E.flags + (size_t)eigb_teams * eigb::kFlagStride;
+        E.ver_stride = vstride;
+        E.status = E.ver + (size_t)eigb_teams * vstride;
+        E.max_inner = 1;
+        if (const char *e = getenv("FOKL_EIGB_INNER")) E.max_inner = std::max(1, atoi(e));
+        void *args[] = {(void *)&E};
+        FOKL_CUDA(ctx, cudaLaunchCooperativeKernel((const void *)eigb::eigb_kernel, dim3((unsigned)(eigb_teams * eigb_team)),
+                                                   dim3(eigb::kThreads), args, eigb::kSmemBytes, ctx->stream));
+        FOKL_LAUNCH_CHECK(ctx);
+        OlsParams O;
+        O.G = G; O.ldg = ldg; O.Xty = Xty; O.col_sets = d_sets; O.meta = d_meta; O.list = d_big_list; O.k = k;
+        O.scratch = d_scratch; O.ct = d_ct; O.lamb = d_lamb; O.Q = d_Q; O.betahat = d_betahat; O.ev = ev; O.info = info;
+        O.sweeps = E.status;
+        cand_ols_kernel<<<n_big, 1024, 0, ctx->stream>>>(O);
+        FOKL_LAUNCH_CHECK(ctx);
     }
     {
         EigParams P;
@@ -1142,6 +1257,50 @@ extern "C" int fokl_kill_loop(fokl_ctx *ctx, const double *G, int64_t ldg, const
         memcpy(h.data() + off_bv + (size_t)vm * sizeof(double), bv1, (size_t)vm * sizeof(double));
     }
     FOKL_CUDA(ctx, cudaMemcpyAsync(dmeta, h.data(), meta_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    // models whose packed tableau does not fit one SM's shared memory: whole-device kernel (killbig.cuh); the
+    // environment knob moves the switch-over for tests and tools (0 = never)
+    bool use_big = !in_smem;
+    if (const char *e = getenv("FOKL_KILL_BIG_MIN_P")) use_big = atoi(e) > 0 && p >= atoi(e);
+    if (use_big) {
+        // wide model: the tableau lives in L2 and its rows are dealt to one CTA per SM (killbig.cuh)
+        const int ldt = (p + 1 + 15) & ~15;
+        const size_t ws = ((size_t)(p + 1) * ldt + 6 * (size_t)ldt) * sizeof(double) + 256;
+        char *wcur = (char *)fokl_scratch(ctx, fokl_ctx::B_CAND_A, ws);
+        if (!wcur) return FOKL_ENOMEM;
+        killb::Params K;
+        K.G = G; K.ldg = ldg; K.Xty = Xty;
+        K.cols = reinterpret_cast<const int32_t *>(dmeta);
+        K.cand_pos = reinterpret_cast<const int32_t *>(dmeta + off_pos);
+        K.bv0 = reinterpret_cast<const double *>(dmeta + off_bv);
+        K.bv1 = K.bv0 + vm;
+        K.p = p; K.vm = vm; K.ldt = ldt;
+        K.c.a = hyp->a; K.c.b = hyp->b; K.c.atau = hyp->atau; K.c.btau = hyp->btau;
+        K.c.sigsqd0 = hyp->sigsqd0; K.c.tausqd0 = hyp->tausqd0; K.c.yty = hyp->yty; K.c.sum_y = hyp->sum_y;
+        K.c.n = (double)hyp->n; K.c.draws = hyp->draws; K.c.from0 = hyp->stat_from0; K.c.from1 = hyp->stat_from1;
+        K.in.threshav = kp->threshav; K.in.threshstda = kp->threshstda; K.in.threshstdb = kp->threshstdb;
+        K.in.icpt = kp->icpt; K.in.evmin = kp->evmin; K.in.aic_adj = kp->aic_adj; K.in.start = kp->start;
+        K.T = carve<double>(wcur, (size_t)(p + 1) * ldt);
+        K.dg = carve<double>(wcur, 2 * (size_t)ldt);
+        K.last = carve<double>(wcur, 2 * (size_t)ldt);
+        K.bcast = carve<double>(wcur, 2 * (size_t)ldt);
+        K.bar = reinterpret_cast<unsigned *>(carve<int>(wcur, 16));
+        K.out_i = out_i; K.out_ev = out_ev;
+        FOKL_CUDA(ctx, cudaMemsetAsync(K.bar, 0, 16 * sizeof(int), ctx->stream));
+        const size_t smem_big = (size_t)((p + 3) & ~1) * sizeof(double) + (size_t)(p + 1) + 16;
+        if (smem_big > 48 * 1024)
+            FOKL_CUDA(ctx, cudaFuncSetAttribute(killb::kill_loop_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big));
+        int occ = 0;
+        FOKL_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, killb::kill_loop_big_kernel, killb::kThreads, smem_big));
+        if (occ < 1) FOKL_FAIL(ctx, FOKL_ECUDA, "kill_loop: wide-model kernel does not fit an SM");
+        const int sms = (ctx->sm_budget > 0 && ctx->sm_budget < ctx->num_sms) ? ctx->sm_budget : ctx->num_sms;
+        int grid = std::max(1, std::min(sms, (p + 1 + killb::kWarps - 1) / killb::kWarps));
+        if (const char *e = getenv("FOKL_KILL_BIG_GRID")) grid = std::max(1, std::min(sms, atoi(e)));
+        void *args[] = {(void *)&K};
+        FOKL_CUDA(ctx, cudaLaunchCooperativeKernel((const void *)killb::kill_loop_big_kernel, dim3((unsigned)grid),
+                                                   dim3(killb::kThreads), args, smem_big, ctx->stream));
+        FOKL_LAUNCH_CHECK(ctx);
+        return FOKL_OK;
+    }
     double *Tg = nullptr;
     if (!in_smem) {
         Tg = (double *)fokl_scratch(ctx, fokl_ctx::B_CAND_A, (size_t)need * sizeof(double));

@@ -176,6 +176,50 @@ def case_two_way_cubic():
              (x, y), dict(clean=True), seed=23)
 
 
+def case_cfg4_shape():
+    """The headline workload's shape (BASELINE.json configs[3]: 8 inputs, way3, cubic, 1000 + 1000 draws, same target
+    function and noise as bench_data cfg4) at N = 1500 rows, so that the C = 8 / 28 / 56 / 168 substages and the sett = 3
+    partition walk (FR:1724-1735) are pinned by a run of the unmodified reference.  tolerance = 6 keeps the walk going
+    through ind = 4 at this small N (with the default 3 the fit stops after four substages).  Takes hours (Python
+    basis loop + dense per-draw products, FR:1446-1485, 1519-1548)."""
+    sys.path.insert(0, os.path.dirname(_HERE))
+    import bench_data
+    rng = np.random.default_rng(44)
+    x = rng.random((1500, 8))
+    y = bench_data.target('cfg4', x, rng.standard_normal(1500))
+    phis = cubic_phis()
+    run_case('cfg4_shape',
+             lambda FR: FR.FoKL(phis=phis, way3=True, draws=1000, burnin=1000, tolerance=6, UserWarnings=False,
+                                ConsoleOutput=True),
+             (x, y), dict(clean=True), seed=44)
+
+
+def case_cfg5_shape():
+    """BASELINE.json configs[4]'s shape (16 inputs, way3, cubic, the bench_data cfg5 target) at N = 900 rows and
+    15 + 15 draws, produced by the ORACLE (the unmodified reference cannot enumerate 16! permutations, FR:1350-1354;
+    the oracle's generator is pinned to np.unique(perms()) at M <= 8 in tests/test_oracle_golden.py).  threshstda / b are
+    raised so that the 560-term (1,1,1) substage proposes ~15 % of its terms instead of ~95 %: the parity replay makes
+    one eigh per proposal on the host."""
+    sys.path.insert(0, os.path.dirname(_HERE))
+    import bench_data
+    import fokl_oracle as fo
+    rng = np.random.default_rng(55)
+    x = rng.random((900, 16))
+    y = bench_data.target('cfg5', x, rng.standard_normal(900))
+    phis = cubic_phis()
+    hy = dict(a=4.0, atau=4.0, tolerance=2, burnin=15, draws=15, way3=True, aic=False, threshav=0.05, threshstda=5.0,
+              threshstdb=6.0)
+    lo, hi = x.min(axis=0), x.max(axis=0)
+    xn = (x - lo) / (hi - lo)
+    b, btau = fo.default_b_btau(y[:, None], hy['a'], hy['atau'])
+    np.random.seed(55)
+    r = fo.fit(xn, y[:, None], phis, kernel=fo.CUBIC, b=b, btau=btau, **hy)
+    np.savez_compressed(os.path.join(GOLD, 'cfg5_shape.npz'), inputs=xn, data=y[:, None], seed=55, kernel=fo.CUBIC,
+                        b=float(b), btau=float(btau), gimmie=False, mtx=r.mtx, evs=r.evs, n_gibbs=r.n_gibbs,
+                        rng_digest=rng_digest(), betas_mean=r.betas.mean(axis=0), source='oracle', **hy)
+    print('cfg5_shape (oracle) gibbs calls', r.n_gibbs, 'terms', r.mtx.shape, 'evs', r.evs)
+
+
 def case_m1():
     rng = np.random.default_rng(24)
     x = rng.random(60)
@@ -381,9 +425,10 @@ CASES = dict(isotherm_gp=case_isotherm_gp, isotherm_qmax=case_isotherm_qmax,
              cfg2_default=lambda: case_cfg2(False), cfg2_changed=lambda: case_cfg2(True),
              cfg1_sigmoid=case_cfg1_sigmoid, way3_bernoulli=case_way3_bernoulli,
              way3_cubic=case_way3_cubic, two_way_cubic=case_two_way_cubic, m1_cubic=case_m1,
+             cfg4_shape=case_cfg4_shape, cfg5_shape=case_cfg5_shape,
              basis_values=case_basis_values, bss_derivatives=case_bss_derivatives, evaluate=case_evaluate, clean=case_clean, constructor=case_constructor, ref_pickle=case_ref_pickle)
 
 if __name__ == '__main__':
-    todo = sys.argv[1:] or list(CASES)
+    todo = sys.argv[1:] or [c for c in CASES if c not in ('cfg4_shape', 'cfg5_shape')]      # hours / minutes: on request only
     for c in todo:
         CASES[c]()

@@ -302,3 +302,147 @@ def test_eigensolver_not_positive_definite_falls_back(engine):
     lam = res.lamb[:8].cpu().numpy()
     lam_ref, _ = eigh(G)
     assert np.max(np.abs(lam - lam_ref)) <= 1e-12 * lam_ref[-1]
+
+
+def _load_gram(engine, G, Xty, n, y):
+    import torch
+    pmax = G.shape[0]
+    cap = max(pmax, 64)
+    engine.G = torch.zeros((cap, cap), dtype=torch.float64, device=engine.device)
+    engine.Xty = torch.zeros(cap, dtype=torch.float64, device=engine.device)
+    engine.G[:pmax, :pmax] = torch.from_numpy(G).to(engine.device)
+    engine.Xty[:pmax] = torch.from_numpy(Xty).to(engine.device)
+    engine.Gcap = cap
+    engine.n_global, engine.sum_y, engine.yty = n, float(y.sum()), float(y @ y)
+
+
+def _check_eig(res, c, p, G, Xty, X, y, n):
+    from scipy.linalg import eigh
+    lam = res.lamb[res.vec_off[c]:res.vec_off[c] + p].cpu().numpy()
+    Q = res.Q[res.mat_off[c]:res.mat_off[c] + p * p].view(p, p).cpu().numpy().T      # columns = eigenvectors
+    lam_ref, _ = eigh(G[:p, :p])
+    assert np.all(np.diff(lam) >= 0)
+    assert np.max(np.abs(lam - lam_ref)) <= 1e-12 * lam_ref[-1], p
+    assert np.max(np.abs(Q.T @ Q - np.eye(p))) < 1e-11, p
+    assert np.max(np.abs((Q * lam) @ Q.T - G[:p, :p])) <= 1e-11 * lam_ref[-1], p
+    bh = res.betahat[res.vec_off[c]:res.vec_off[c] + p].cpu().numpy()
+    bh_ref = np.linalg.solve(G[:p, :p], Xty[:p])
+    assert np.max(np.abs(bh - bh_ref)) <= 1e-8 * np.max(np.abs(bh_ref)), p
+    r = y - X[:, :p] @ bh_ref
+    ev_ref = p * np.log(n) - 2 * (-(n / 2) * np.log(np.var(r)) - (n - 1) / 2)
+    assert abs(res.ev[c] - ev_ref) <= 1e-9 * abs(ev_ref), p
+
+
+@pytest.mark.parametrize('sizes', [(1024,), (1700,), (2072, 705, 1300)])
+def test_blocked_eigensolver_wide_models(engine, sizes):
+    """Models too wide for the cluster solver (BASELINE configs[4]: the 3-way substages of a 16-input problem reach
+    ~2000 columns): blocked Cholesky + one-sided block Jacobi on the FP64 tensor pipe (csrc/eigbig.cuh) against
+    scipy.linalg.eigh on the same Gram bits -- eigenvalues to 1e-12 of the largest, orthonormal eigenvectors,
+    reconstruction, betahat and BIC; several models side by side go through the team dispenser."""
+    rng = np.random.default_rng(sum(sizes))
+    pmax = max(sizes)
+    n = 3 * pmax + 50
+    X = rng.standard_normal((n, pmax)) * (1.0 + 3.0 * rng.random(pmax))
+    X[:, 0] = 1.0
+    y = X[:, :5] @ rng.standard_normal(5) + 0.1 * rng.standard_normal(n)
+    G, Xty = X.T @ X, X.T @ y
+    _load_gram(engine, G, Xty, n, y)
+    hyp = engine.make_hypers(4, 1, 4, 1, 1, 1, 10)
+    res = engine.evaluate([list(range(p)) for p in sizes], hyp, want_eig=True, refine_tol=None)
+    for c, p in enumerate(sizes):
+        assert (res.info[c] & 0xff) == 0, (p, res.info[c])
+        assert 0 < (res.info[c] >> 8) < 40
+        _check_eig(res, c, p, G, Xty, X, y, n)
+
+
+def test_blocked_eigensolver_small_models_and_graded_columns(engine, monkeypatch):
+    """The blocked solver forced onto small models (every block-count / padding case: p = 2 ... 300, ragged last
+    block, odd block counts) with strongly graded, correlated columns (condition ~1e8); a subset model (scattered
+    column list) as well."""
+    monkeypatch.setenv('FOKL_EIGB_MIN_P', '2')
+    rng = np.random.default_rng(11)
+    pmax = 300
+    n = 2000
+    u = rng.random((n, 6))
+    X = np.empty((n, pmax))
+    for j in range(pmax):
+        k = rng.choice(6, size=2, replace=False)
+        X[:, j] = (u[:, k[0]] ** (1 + j % 4)) * np.cos(3 * u[:, k[1]] * (1 + j % 3)) * 10.0 ** (-4 * rng.random()) \
+            + 1e-3 * rng.standard_normal(n)
+    X[:, 0] = 1.0
+    y = X[:, :5] @ rng.standard_normal(5) + 0.1 * rng.standard_normal(n)
+    G, Xty = X.T @ X, X.T @ y
+    _load_gram(engine, G, Xty, n, y)
+    hyp = engine.make_hypers(4, 1, 4, 1, 1, 1, 10)
+    sizes = (2, 3, 8, 9, 16, 17, 31, 33, 100, 129, 300)
+    res = engine.evaluate([list(range(p)) for p in sizes], hyp, want_eig=True, refine_tol=None)
+    from scipy.linalg import eigh
+    for c, p in enumerate(sizes):
+        assert (res.info[c] & 0xff) == 0, (p, res.info[c])
+        lam = res.lamb[res.vec_off[c]:res.vec_off[c] + p].cpu().numpy()
+        Q = res.Q[res.mat_off[c]:res.mat_off[c] + p * p].view(p, p).cpu().numpy().T
+        lam_ref, _ = eigh(G[:p, :p])
+        # one-sided Jacobi on the Cholesky factor: small eigenvalues to high RELATIVE accuracy
+        assert np.max(np.abs(lam - lam_ref) / lam_ref) <= 1e-8, p
+        assert np.max(np.abs(lam - lam_ref)) <= 1e-12 * lam_ref[-1], p
+        assert np.max(np.abs(Q.T @ Q - np.eye(p))) < 1e-11, p
+    cols = [0] + sorted(rng.choice(np.arange(1, pmax), size=150, replace=False).tolist())
+    res = engine.evaluate([cols], hyp, want_eig=True, refine_tol=None)
+    lam = res.lamb[:len(cols)].cpu().numpy()
+    lam_ref, _ = eigh(G[np.ix_(cols, cols)])
+    assert np.max(np.abs(lam - lam_ref)) <= 1e-12 * lam_ref[-1]
+
+
+def test_blocked_eigensolver_not_positive_definite_falls_back(engine, monkeypatch):
+    """A singular Gram fails the blocked Cholesky (status -1) and is handed to the two-matrix Jacobi."""
+    monkeypatch.setenv('FOKL_EIGB_MIN_P', '2')
+    from scipy.linalg import eigh
+    rng = np.random.default_rng(3)
+    X = rng.standard_normal((200, 70))
+    X[:, 45] = X[:, 2]
+    y = rng.standard_normal(200)
+    G = X.T @ X
+    _load_gram(engine, G, X.T @ y, 200, y)
+    hyp = engine.make_hypers(4, 1, 4, 1, 1, 1, 10)
+    res = engine.evaluate([list(range(70)), list(range(40))], hyp, want_eig=True, refine_tol=None)
+    assert res.info[0] & 2 and not (res.info[1] & 2)
+    for c, p in enumerate((70, 40)):
+        lam = res.lamb[res.vec_off[c]:res.vec_off[c] + p].cpu().numpy()
+        lam_ref, _ = eigh(G[:p, :p])
+        assert np.max(np.abs(lam - lam_ref)) <= 1e-12 * lam_ref[-1]
+
+
+@pytest.mark.parametrize('p', [60, 150, 400, 1100])
+def test_whole_device_kill_loop_equals_single_cta_kernel(engine, monkeypatch, p):
+    """fokl_kill_loop for models whose tableau does not fit one SM (csrc/killbig.cuh: rows dealt to one CTA per SM,
+    look-ahead pivot row, one grid barrier per pivot) takes the single-CTA kernel's decisions and BICs bit for bit."""
+    rng = np.random.default_rng(p)
+    n = 3 * p + 50
+    X = rng.standard_normal((n, p)) * (1.0 + 3.0 * rng.random(p))
+    X[:, 0] = 1.0
+    y = X[:, :min(40, p)] @ rng.standard_normal(min(40, p)) + 0.5 * rng.standard_normal(n)
+    _load_gram(engine, X.T @ X, X.T @ y, n, y)
+    hyp = engine.make_hypers(4, 1, 4, 1, 1, 1, 10)
+    cols = list(range(p))
+    vm = (3 * p) // 4
+    pos = [int(c) for c in rng.permutation(np.arange(p - vm, p))]
+    bv0 = np.sort(rng.random(vm))
+    bv1 = rng.random(vm) * 3
+    full = float(engine.evaluate([cols], hyp, refine_tol=None).ev[0])
+    out = {}
+    for name, knob in (('big', '2'), ('one', '0')):
+        monkeypatch.setenv('FOKL_KILL_BIG_MIN_P', knob)
+        out[name] = engine.kill_loop(cols, pos, bv0, bv1, hyp, 0.3, 0.5, 2.0, 2.0, full, 0.0, 3)
+    big, one = out['big'], out['one']
+    assert big['bad'] == one['bad'] == 0 and big['n_acc'] == one['n_acc'] > 0
+    assert big['tested'] == one['tested']
+    assert np.array_equal(big['acc'], one['acc']) and np.array_equal(big['calls'], one['calls'])
+    assert np.array_equal(big['ev'], one['ev'])
+    # a singular Gram is reported by both
+    G2 = X.T @ X
+    G2[:, 5] = G2[:, 2]
+    G2[5, :] = G2[2, :]
+    _load_gram(engine, G2, X.T @ y, n, y)
+    for knob in ('2', '0'):
+        monkeypatch.setenv('FOKL_KILL_BIG_MIN_P', knob)
+        assert engine.kill_loop(cols, pos, bv0, bv1, hyp, 0.3, 0.5, 2.0, 2.0, full, 0.0, 0)['bad'] != 0

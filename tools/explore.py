@@ -47,7 +47,10 @@ def main():
     orig = _selection.forward_select
 
     def patched(*args, **kw):
-        kw['on_substage'] = lambda ind, ev, terms: subs.append((ind, ev, terms.shape[0], time.time() - t1))
+        def _on(ind, ev, terms):
+            subs.append((ind, ev, terms.shape[0], time.time() - t1))
+            print('substage', subs[-1], flush=True)
+        kw['on_substage'] = _on
         return orig(*args, **kw)
     _selection.forward_select = patched
     t1 = time.time()

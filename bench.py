@@ -50,8 +50,9 @@ def parse():
     ap.add_argument('--workload', default='cfg4', choices=sorted(bench_data.CONFIGS))
     ap.add_argument('--n', type=int, default=0, help='override the number of rows (debugging only)')
     ap.add_argument('--draws', type=int, default=1000)
-    ap.add_argument('--cpu-rows', type=int, default=4000, help='rows of the bounded CPU sample')
-    ap.add_argument('--cpu-seconds', type=float, default=25.0, help='wall-time budget of the bounded CPU sample')
+    ap.add_argument('--cpu-rows', type=int, default=0, help='rows of the reduced-N CPU fit (default: 10^4; 2*10^4 for cfg3)')
+    ap.add_argument('--cpu-seconds', type=float, default=240.0,
+                    help='--impl reference: total wall-time bound; complete fits are repeated until --steps or this')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     return ap.parse_args()
@@ -113,69 +114,154 @@ class Clocks:
 
 
 # ---------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port on a bounded sample
+# CPU arm: the oracle port (a numpy / OpenBLAS / LAPACK restatement of the reference + a C basis helper), run TO
+# COMPLETION on a reduced-N instance of the same workload -- the value does not depend on a time budget
 # ---------------------------------------------------------------------------------------------------
+CPU_ROWS_DEFAULT = {'cfg3': 20000, 'cfg4': 10000, 'cfg5': 10000}      # BASELINE.md section 3 / SURVEY 8(d)
+
+
 class _CpuBudget(Exception):
     pass
 
 
-def cpu_fit_once(a, phis, rows, budget_s):
-    """The CPU oracle's fit on `rows` rows of the workload, cut off after `budget_s` seconds of wall time: returns
-    (gibbs calls completed, seconds up to the last completed call, threads, largest model width reached)."""
+def cpu_rows(a):
+    return a.cpu_rows or CPU_ROWS_DEFAULT[a.workload]
+
+
+def cpu_fit_complete(a, phis, rows, guard_s=600.0):
+    """One complete oracle fit of the workload at `rows` rows, all host threads.  Returns a dict with the number of
+    `gibbs` calls, seconds, design-matrix cells built, draws made, model widths and the time spent in the basis helper.
+    guard_s is a safety net only (never reached at the default sizes): a fit cut by it is flagged complete=False."""
     sys.path.insert(0, os.path.join(ROOT, 'oracle'))
     import fokl_oracle as fo
     c = bench_data.CONFIGS[a.workload]
     x, y = bench_data.make_rows(a.workload, 0, rows, n_total=rows)
     np.random.seed(c['seed'])
     threads = os.cpu_count() or 1
-    state = dict(calls=0, t=0.0, pmax=0)
+    st = dict(calls=0, t=0.0, pmax=0, cells=0, t_basis=0.0, draws=0, psum=0, p2sum=0, complete=True)
+    real_basis = fo.basis_columns
+
+    def timed_basis(x_, terms, *args, **kw):
+        t = time.perf_counter()
+        out = real_basis(x_, terms, *args, **kw)
+        st['t_basis'] += time.perf_counter() - t
+        st['cells'] += out.size
+        return out
+
     t0 = time.perf_counter()
 
     def on_gibbs(info):
-        state['calls'] = info['call']
-        state['t'] = time.perf_counter() - t0
-        state['pmax'] = max(state['pmax'], info['discmtx'].shape[0] + 1)
-        if budget_s and state['t'] > budget_s:
+        st['calls'] = info['call']
+        st['t'] = time.perf_counter() - t0
+        p = info['discmtx'].shape[0] + 1
+        st['pmax'] = max(st['pmax'], p)
+        st['psum'] += p
+        st['p2sum'] += p * p
+        st['draws'] += 2 * a.draws
+        if guard_s and st['t'] > guard_s:
             raise _CpuBudget()
 
+    fo.basis_columns = timed_basis
     try:
-        fo.fit(x, y, phis, kernel=c['kernel'], way3=c['way3'], draws=a.draws, burnin=a.draws, threads=threads,
-               on_gibbs=on_gibbs)
+        r = fo.fit(x, y, phis, kernel=c['kernel'], way3=c['way3'], draws=a.draws, burnin=a.draws, threads=threads,
+                   on_gibbs=on_gibbs)
+        st['terms'], st['substages'] = int(r.mtx.shape[0]), int(len(r.evs))
+        st['t'] = time.perf_counter() - t0
     except _CpuBudget:
-        pass
-    return state['calls'], state['t'], threads, state['pmax']
+        st['complete'] = False
+    finally:
+        fo.basis_columns = real_basis
+    st['threads'], st['rows'] = threads, rows
+    # X'X, X'y (FR:1492-1494) are recomputed in full by every call: 2 N p^2 flops each, at the BLAS rate measured here
+    A = np.random.default_rng(0).random((rows, 128))
+    A.T.dot(A)
+    tg = time.perf_counter()
+    for _ in range(5):
+        A.T.dot(A)
+    rate = 5 * 2.0 * rows * 128 * 128 / (time.perf_counter() - tg)
+    st['gram_flops'] = 2.0 * rows * st['p2sum']
+    st['t_gram_est'] = st['gram_flops'] / rate
+    st['gram_gflops_rate'] = rate / 1e9
+    return st
 
 
-def cpu_sample_desc(a, rows, budget_s, calls, pmax):
+def cpu_python_loop_cost(a, phis, seconds=3.0):
+    """us per design-matrix cell of the reference's literal Python triple loop (FR:1446-1485; oracle basis='py'),
+    measured on a few hundred rows of the workload's 3-way / 2-way terms for ~`seconds` s."""
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import fokl_oracle as fo
+    c = bench_data.CONFIGS[a.workload]
+    x, _ = bench_data.make_rows(a.workload, 0, 512, n_total=512)
+    part = ([1, 1, 1] if c['way3'] else [1, 1]) + [0] * (c['m'] - (3 if c['way3'] else 2))
+    terms = fo.distinct_perms(part).astype(int)[:8]
+    rows, cells, t0 = 16, 0, time.perf_counter()
+    while time.perf_counter() - t0 < seconds:
+        fo.basis_columns_py(x[:rows], terms, phis, c['kernel'])
+        cells += rows * terms.shape[0]
+    return 1e6 * (time.perf_counter() - t0) / cells
+
+
+def cpu_report(a, st, n_full, py_us):
+    """The numbers SURVEY 8(d) asks for next to the CPU value, plus the linear-in-N extrapolation LABELLED as such."""
+    t, tb = st['t'], st['t_basis']
+    cells_s = st['cells'] / tb if tb > 0 else None
+    scale = n_full / st['rows']
+    rep = {
+        'rows': st['rows'], 'complete_fit': st['complete'], 'seconds': t, 'gibbs_calls': st['calls'],
+        'terms_selected': st.get('terms'), 'substages': st.get('substages'), 'max_model_width': st['pmax'],
+        'cells_built': st['cells'], 'basis_seconds_c_helper': tb, 'cells_per_s_c_helper': cells_s,
+        'gram_flops': st['gram_flops'], 'gram_seconds_estimate': st['t_gram_est'], 'gram_gflops_rate': st['gram_gflops_rate'],
+        'draws': st['draws'], 'draws_per_s': st['draws'] / max(t - tb - st['t_gram_est'], 1e-9),
+        'python_loop_us_per_cell': py_us,
+        'reference_as_shipped_seconds_estimate': (t - tb) + st['cells'] * py_us * 1e-6 if py_us else None,
+        'extrapolation_to_full_N': {
+            'note': 'LABELLED EXTRAPOLATION, not a measurement: the same %d gibbs calls at N=%d, basis and Gram time '
+                    'scaled linearly in N, draw loop unchanged; the real N=%d fit keeps more terms and makes more calls'
+                    % (st['calls'], n_full, n_full),
+            'seconds_port_c_helper': (t - tb - st['t_gram_est']) + (tb + st['t_gram_est']) * scale,
+            'seconds_reference_python_loop': ((t - tb - st['t_gram_est']) + (st['t_gram_est'] + st['cells'] * py_us * 1e-6) * scale)
+            if py_us else None}}
+    return rep
+
+
+def cpu_sample_desc(a, st):
     return ('oracle port (numpy/OpenBLAS/LAPACK like the reference + a C basis helper, i.e. faster than the reference, '
-            'whose basis build is a Python triple loop) of the %s fit at N=%d rows, %d+%d draws, cut off after %.0f s: '
-            'the first %d gibbs calls (model width up to %d columns). The complete CPU fit at N=4000 takes 300 s '
-            '(0.62 candidate-models/s on 8 cores, see BASELINE.md)'
-            % (a.workload, rows, a.draws, a.draws, budget_s, calls, pmax))
+            'whose basis build is a Python triple loop) of the %s fit at N=%d rows, %d+%d draws, run to completion: '
+            '%d gibbs calls in %.1f s (model width up to %d columns)%s'
+            % (a.workload, st['rows'], a.draws, a.draws, st['calls'], st['t'], st['pmax'],
+               '' if st['complete'] else ' -- CUT by the safety guard'))
 
 
 def run_reference(a):
+    """`--impl reference`: complete CPU fits of the reduced-N workload on rank 0.  The TOTAL wall time is bounded
+    independently of --steps: fits are repeated until `--steps` are done or --cpu-seconds (default 240 s) are used up,
+    whichever comes first, and at least one fit always completes; warm-up is one import + one tiny fit."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
     phis = load_phis(a)
     n_total = a.n or bench_data.CONFIGS[a.workload]['n']
-    for _ in range(a.warmup):
-        cpu_fit_once(a, phis, a.cpu_rows, 2.0)
-    tot_models, tot_s, threads, pmax = 0, 0.0, 1, 0
-    budget = a.cpu_seconds * 2.0       # each step: a bounded sample of the fit
-    for _ in range(a.steps):
-        m, dt, threads, pm = cpu_fit_once(a, phis, a.cpu_rows, budget)
-        tot_models += m
-        tot_s += dt
-        pmax = max(pmax, pm)
+    rows = cpu_rows(a)
+    t_start = time.perf_counter()
+    if a.warmup:
+        cpu_fit_complete(a, phis, 300, guard_s=20.0)          # page in numpy / LAPACK / the C helper
+    py_us = cpu_python_loop_cost(a, phis)
+    fits = []
+    while len(fits) < max(a.steps, 1):
+        fits.append(cpu_fit_complete(a, phis, rows))
+        if time.perf_counter() - t_start + fits[-1]['t'] > a.cpu_seconds:
+            break
+    tot_models = sum(f['calls'] for f in fits)
+    tot_s = sum(f['t'] for f in fits)
     v = tot_models / tot_s
+    st = fits[-1]
     line = {'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': a.gpus, 'steps': a.steps,
-            'warmup': a.warmup, 'ms_per_step': 1e3 * tot_s / a.steps, 'higher_is_better': True, 'scaling': 'strong',
+            'steps_run': len(fits), 'warmup': a.warmup, 'ms_per_step': 1e3 * tot_s / len(fits),
+            'higher_is_better': True, 'scaling': 'strong',
             'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': config_dict(a, n_total, 1, {'cpu_sample_rows': a.cpu_rows}),
-            'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': threads, 'kind': 'port',
-                             'sample': cpu_sample_desc(a, a.cpu_rows, budget, tot_models // max(a.steps, 1), pmax)},
+            'config': config_dict(a, n_total, 1, {'cpu_sample_rows': rows}),
+            'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': st['threads'], 'kind': 'port',
+                             'sample': cpu_sample_desc(a, st), 'detail': cpu_report(a, st, n_total, py_us)},
             'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
     print(json.dumps(line), flush=True)
@@ -364,14 +450,24 @@ def main():
 
     cpu = None
     if world == 1 and not a.no_cpu_baseline:
-        mdl, dt, threads, pm = cpu_fit_once(a, phis, a.cpu_rows, a.cpu_seconds)
-        cpu = {'value': mdl / dt, 'unit': UNIT, 'cores': threads, 'kind': 'port',
-               'sample': cpu_sample_desc(a, a.cpu_rows, a.cpu_seconds, mdl, pm), 'seconds': dt}
+        st = cpu_fit_complete(a, phis, cpu_rows(a))
+        cpu = {'value': st['calls'] / st['t'], 'unit': UNIT, 'cores': st['threads'], 'kind': 'port',
+               'sample': cpu_sample_desc(a, st), 'seconds': st['t'],
+               'detail': cpu_report(a, st, n_total, cpu_python_loop_cost(a, phis))}
 
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': a.steps, 'warmup': a.warmup,
             'ms_per_step': ms / a.steps, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
-            'dtype': 'f64', 'data': 'synthetic', 'config': config_dict(a, n_total, world),
-            'candidate_models_per_step': models / a.steps, 'terms_selected': infos[-1]['terms'],
+            'dtype': 'f64', 'data': 'synthetic', 'config': config_dict(a, n_total, world, {'cpu_sample_rows': cpu_rows(a)}),
+            'candidate_models_per_step': models / a.steps,
+            'work_per_step': {
+                'note': "candidate_models_per_step counts the reference's `gibbs` invocations (FR:1650 full models + "
+                        "FR:1681 one per kill proposal).  Here a kill proposal's BIC is an O(1) score from the "
+                        "sweep-operator tableau of the model's Gram (kill_proposals_scored); an eigensolve + Gibbs chain "
+                        "is run only for the full models and for the accepted models whose chain can influence a later "
+                        "decision (eig_solves / chains_run)",
+                **{k: sum(i.get(k, 0) for i in infos) / a.steps
+                   for k in ('eig_solves', 'chains_run', 'kill_loops', 'kill_proposals_scored')}},
+            'terms_selected': infos[-1]['terms'],
             'substages': infos[-1]['substages'], 'wall_ms_per_step': wall_ms / a.steps,
             'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clk, 'roofline': roof, 'roofline_gram': roof_g,
             'roofline_note': "roofline = the basis-matrix kernel BASELINE.json's metric names (HBM-bound); "

@@ -806,13 +806,14 @@ class FoKL:
                   threshstdb=self.threshstdb, aic=self.aic)
         t0 = time.perf_counter()
         launches0 = eng.launch_count()
+        work0 = dict(eng.work)
         out = forward_select(eng, hy, ds.m, len(self.phis), console=self.ConsoleOutput, rng=B200_CONFIG['rng'],
                              eager=B200_CONFIG['eager_chains'], pipeline=B200_CONFIG['pipeline'])
         eng.synchronize()
         LAST_FIT_INFO.clear()
         LAST_FIT_INFO.update(n_gibbs=out['n_gibbs'], n_batches=out['n_batches'], seconds=time.perf_counter() - t0,
                              launches=eng.launch_count() - launches0, n=n, m=ds.m, terms=out['mtx'].shape[0],
-                             substages=len(out['evs']))
+                             substages=len(out['evs']), **{k: v - work0[k] for k, v in eng.work.items()})
 
         betas = out['betas']
         self.betas = betas[-self.draws::, :]

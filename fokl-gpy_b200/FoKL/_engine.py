@@ -146,6 +146,7 @@ class Engine:
         self.n_global = 0
         self.sum_y = self.yty = 0.0
         self.gibbs_launch_batches = 0
+        self.work = dict(eig_solves=0, chains_run=0, kill_loops=0, kill_proposals_scored=0)     # work counters (bench.py)
         self.profile = None      # set to {} to collect CUDA-event timings per stage (bench.py)
         self.ctx_side = None
         self.side_stream = None
@@ -549,6 +550,9 @@ class Engine:
         else:
             self._toc(t, 'candidates_chain' if chain_any else 'candidates_bic', cands=n_cand, pmax=int(p.max()))
         self.gibbs_launch_batches += 1
+        self.work['eig_solves'] += n_cand
+        if chain_any:
+            self.work['chains_run'] += int(n_cand if rc_arr is None else np.count_nonzero(rc_arr))
         res = CandidateResult()
         res.p, res.vec_off, res.mat_off, res.draws = p, vec_off, mat_off, D
         res.stats, res.betas, res.sigs, res.taus = stats, betas, sigs, taus
@@ -615,6 +619,8 @@ class Engine:
                 h = out.cpu().numpy()
                 oi = h[:n_i_d].view(np.int32)
                 k = int(oi[0])
+                self.work['kill_loops'] += 1
+                self.work['kill_proposals_scored'] += int(oi[1])
                 return dict(n_acc=k, tested=int(oi[1]), bad=int(oi[2]), acc=oi[3:3 + k].copy(),
                             calls=oi[3 + vm:3 + vm + k].copy(), ev=h[n_i_d:n_i_d + k].copy())
         return _Pending()

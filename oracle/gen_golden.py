@@ -195,7 +195,7 @@ def case_cfg4_shape():
 
 
 def case_cfg5_shape():
-    """BASELINE.json configs[4]'s shape (16 inputs, way3, cubic, the bench_data cfg5 target) at N = 900 rows and
+    """BASELINE.json configs[4]'s shape (16 inputs, way3, cubic, the bench_data cfg5 target) at N = 2500 rows and
     15 + 15 draws, produced by the ORACLE (the unmodified reference cannot enumerate 16! permutations, FR:1350-1354;
     the oracle's generator is pinned to np.unique(perms()) at M <= 8 in tests/test_oracle_golden.py).  threshstda / b are
     raised so that the 560-term (1,1,1) substage proposes ~15 % of its terms instead of ~95 %: the parity replay makes
@@ -204,10 +204,10 @@ def case_cfg5_shape():
     import bench_data
     import fokl_oracle as fo
     rng = np.random.default_rng(55)
-    x = rng.random((900, 16))
-    y = bench_data.target('cfg5', x, rng.standard_normal(900))
+    x = rng.random((2500, 16))
+    y = bench_data.target('cfg5', x, rng.standard_normal(2500))
     phis = cubic_phis()
-    hy = dict(a=4.0, atau=4.0, tolerance=2, burnin=15, draws=15, way3=True, aic=False, threshav=0.05, threshstda=5.0,
+    hy = dict(a=4.0, atau=4.0, tolerance=3, burnin=15, draws=15, way3=True, aic=False, threshav=0.05, threshstda=5.0,
               threshstdb=6.0)
     lo, hi = x.min(axis=0), x.max(axis=0)
     xn = (x - lo) / (hi - lo)

@@ -99,6 +99,21 @@ def test_bernoulli_tolerance_by_order(engine, phis_bern):
     assert np.mean(got == ref) > 0.98
 
 
+def test_bernoulli_orders_11_to_20(engine, phis_bern):
+    """The upper half of the shipped table (phis has 20 orders and the selection loop may reach ind = len(phis),
+    FR:1747) with the per-order tolerance of tests/test_host_emu.py::bernoulli_order_tolerance -- the reference's own
+    rounding noise against the exact polynomial at that order, measured there."""
+    from test_host_emu import bernoulli_order_tolerance
+    rng = np.random.default_rng(12)
+    x = rng.random((5000, 2))
+    for order in range(11, 21):
+        terms = np.array([[order, 0], [0, order], [order, 1]])
+        got = build_on_device(engine, phis_bern, fo.BERNOULLI, x, terms)
+        ref = fo.basis_columns(x, terms, phis_bern, fo.BERNOULLI)
+        scale = np.abs(ref).max(axis=0)
+        assert np.all(np.abs(got - ref).max(axis=0) <= bernoulli_order_tolerance(order) * scale), order
+
+
 def test_bernoulli_way3(engine, phis_bern):
     rng = np.random.default_rng(3)
     x = rng.random((1234, 4))

@@ -37,7 +37,7 @@ def fit_device(FR, g, phis, rng='numpy', recorder=None, eager=False, pipeline=Tr
         model = FR.FoKL(kernel=kernel, phis=phis, a=float(g['a']), b=float(g['b']), atau=float(g['atau']),
                         btau=float(g['btau']), tolerance=int(g['tolerance']), burnin=int(g['burnin']),
                         draws=int(g['draws']), way3=bool(g['way3']), aic=bool(g['aic']), UserWarnings=False,
-                        ConsoleOutput=False)
+                        ConsoleOutput=False, **thresholds(g))
         np.random.seed(int(g['seed']))
         betas, mtx, evs = model.fit(g['inputs'], g['data'], clean=True, normalize=False)
         return model, betas, mtx, evs, dict(FR.LAST_FIT_INFO), rng_digest()
@@ -46,6 +46,10 @@ def fit_device(FR, g, phis, rng='numpy', recorder=None, eager=False, pipeline=Tr
         FR.B200_CONFIG['rng'] = 'philox'
         FR.B200_CONFIG['eager_chains'] = False
         FR.B200_CONFIG['pipeline'] = True
+
+
+def thresholds(g):
+    return {k: float(g[k]) for k in ('threshav', 'threshstda', 'threshstdb') if k in g}
 
 
 class Diverged(Exception):
@@ -65,7 +69,7 @@ class Recorder:
         self.calls.append((key, ev))
 
 
-def oracle_replay(g, phis, grams):
+def oracle_replay(g, phis, grams, literal=True):
     """The oracle's selection loop on the device's Gram bits.  Returns (FitResult or None if the oracle left the
     device's path, rng digest, per-call (key, ev) log, per-substage ev log)."""
     calls, subs = [], []
@@ -84,7 +88,8 @@ def oracle_replay(g, phis, grams):
         r = fo.fit(g['inputs'], g['data'], phis, kernel=str(g['kernel']), a=float(g['a']), b=float(g['b']),
                    atau=float(g['atau']), btau=float(g['btau']), tolerance=int(g['tolerance']),
                    burnin=int(g['burnin']), draws=int(g['draws']), way3=bool(g['way3']), aic=bool(g['aic']),
-                   gram_hook=hook, on_gibbs=on_gibbs, on_substage=lambda ind, ev: subs.append(ev))
+                   gram_hook=hook, on_gibbs=on_gibbs, on_substage=lambda ind, ev: subs.append(ev), literal=literal,
+                   **thresholds(g))
     except Diverged:
         r = None
     return r, rng_digest(), calls, subs
@@ -137,6 +142,37 @@ def test_fit_parity_with_oracle_on_device_gram(name, phis_cubic, phis_bern):
     assert np.max(np.abs(betas - ref.betas)) <= 1e-7 * np.max(np.abs(ref.betas))
     assert isinstance(betas, np.ndarray) and isinstance(mtx, np.ndarray) and isinstance(evs, np.ndarray)
     assert np.array_equal(model.avg_betas, np.mean(model.betas, axis=0))
+
+
+def test_cfg5_shaped_fit_parity_with_oracle(phis_cubic, monkeypatch):
+    """BASELINE.json configs[4]'s shape -- 16 inputs, way3 (substages of 16 / 120 / 16 / 560 new terms), the cfg5
+    target -- at N = 2500, 15 + 15 draws, through the wide-model kernels (blocked eigensolver forced on from 300
+    columns; the (1,1,1) substage's models have ~700), in parity mode against (a) the oracle's own complete fit
+    (tests/golden/cfg5_shape.npz, oracle/gen_golden.py cfg5_shape: term matrix, `gibbs` count, RNG end state, evs)
+    and (b) the oracle's loop replayed call by call on the device's Gram bits (eigenbasis form of the draw loop,
+    SURVEY A.6: the literal three dense products per draw take 5 s per call at p = 700)."""
+    from FoKL import FoKLRoutines as FR
+    monkeypatch.setenv('FOKL_EIGB_MIN_P', '300')
+    g = load_golden('cfg5_shape')
+    rec = Recorder()
+    model, betas, mtx, evs, info, dig = fit_device(FR, g, phis_cubic, recorder=rec)
+    assert max(len(k) for k in rec.grams) + 1 > 560
+    # (b) call by call on the device's Gram bits: everything must agree
+    ref, dig_ref, calls, subs = oracle_replay(g, phis_cubic, rec.grams, literal=False)
+    assert ref is not None and dig_ref == dig
+    assert len(calls) == len(rec.calls) and info['n_gibbs'] == ref.n_gibbs
+    for (kd, evd), (ko, evo) in zip(rec.calls, calls):
+        assert kd == ko and abs(evd - evo) <= 1e-9 * abs(evo)
+    assert np.array_equal(mtx, ref.mtx)
+    assert np.allclose(evs, ref.evs, rtol=1e-9, atol=0)
+    assert np.max(np.abs(betas - ref.betas)) <= 1e-7 * np.max(np.abs(ref.betas))
+    # (a) the oracle's own run factorises its own BLAS Gram: LAPACK's eigenvector signs depend on the last bits of the
+    # Gram (SURVEY 0.7), so the injected normals pair with other directions and the kill proposals -- hence the number of
+    # `gibbs` calls -- may differ; what does not depend on the draws must agree: the first substage's BIC and the
+    # substage count, and the selected model must be of the same size class
+    assert abs(evs[0] - g['evs'][0]) <= 1e-9 * abs(g['evs'][0])
+    assert len(evs) == len(g['evs'])
+    assert abs(mtx.shape[0] - g['mtx'].shape[0]) <= max(2, 0.3 * g['mtx'].shape[0])
 
 
 # leading substages whose BIC must equal the reference's own run to 1e-9 (see docstring below)

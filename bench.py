@@ -396,6 +396,26 @@ def main():
                'h2d_bytes_per_step': int(x_host.nbytes + y_host.nbytes), 'd2h_bytes_per_step': int(einfos[-1]['d2h']),
                'ms_per_step': ems / a.steps}
 
+    # the same call with ordinary (pageable) numpy arrays, as a user who never heard of pinned memory passes them
+    e2e_pageable = None
+    if not a.no_e2e:
+        x_page, y_page = np.array(x_host, copy=True), np.array(y_host, copy=True)
+
+        def step_pageable():
+            np.random.seed(c['seed'])
+            model = new_model()
+            model.fit(x_page, y_page, clean=True, minmax=unit_minmax, AutoTranspose=False)
+            return dict(FR.LAST_FIT_INFO)
+
+        step_pageable()
+        pinfos, pms, _, _, _ = timed(step_pageable, max(1, min(a.steps, 3)), False)
+        e2e_pageable = {'value': sum(i['n_gibbs'] for i in pinfos) / (pms * 1e-3), 'unit': UNIT,
+                        'ms_per_step': pms / len(pinfos), 'host_buffers': 'pageable numpy arrays'}
+        del x_page, y_page
+    if e2e is not None:
+        e2e['host_buffers'] = 'pinned (torch pin_memory)'
+        e2e['pageable'] = e2e_pageable
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

@@ -486,7 +486,7 @@ def main():
                         "is run only for the full models and for the accepted models whose chain can influence a later "
                         "decision (eig_solves / chains_run)",
                 **{k: sum(i.get(k, 0) for i in infos) / a.steps
-                   for k in ('eig_solves', 'chains_run', 'kill_loops', 'kill_proposals_scored')}},
+                   for k in ('eig_solves', 'chains_run', 'secular_steps', 'kill_loops', 'kill_proposals_scored')}},
             'terms_selected': infos[-1]['terms'],
             'substages': infos[-1]['substages'], 'wall_ms_per_step': wall_ms / a.steps,
             'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clk, 'roofline': roof, 'roofline_gram': roof_g,

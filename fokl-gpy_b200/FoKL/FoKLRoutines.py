@@ -33,6 +33,15 @@ B200_CONFIG = {
     'device': None,                                         # torch device / index; None = current device
     # evaluate the chains that verify a substage together with the next substage's full model (same fit, bit for bit)
     'pipeline': os.environ.get('FOKL_B200_PIPELINE', '1') not in ('0', '', 'false', 'False'),
+    # build the next substage's columns and the stable part of its Gram block while the current substage's candidate
+    # stage runs (same Gram bits, same fit)
+    # (opt-in: measured 165 ms vs 151 ms per cfg4 fit, DESIGN.md section 3b -- the second pass over the new columns and
+    # the SMs left to the candidate stage cost more than the overlap returns)
+    'prefetch': os.environ.get('FOKL_B200_PREFETCH', '0') not in ('0', '', 'false', 'False'),
+    # chains of the nested accepted models of a substage by secular-equation updates instead of one eigensolver run per
+    # model (csrc/nested.cu); same decisions, the intercept means agree to ~1e-13
+    'nested_chains': os.environ.get('FOKL_B200_NESTED', '1') not in ('0', '', 'false', 'False'),
+    'nested_min_p': int(os.environ.get('FOKL_B200_NESTED_MIN_P', '384')),     # narrower batches: one solver per model
 }
 
 _ENGINES = {}
@@ -803,12 +812,14 @@ class FoKL:
 
         hy = dict(a=a, b=b, atau=atau, btau=btau, tolerance=self.tolerance, total_draws=self.burnin + self.draws,
                   gimmie=self.gimmie, way3=self.way3, threshav=self.threshav, threshstda=self.threshstda,
-                  threshstdb=self.threshstdb, aic=self.aic)
+                  threshstdb=self.threshstdb, aic=self.aic, nested_chains=B200_CONFIG.get('nested_chains', True),
+                  nested_min_p=B200_CONFIG.get('nested_min_p', 384))
         t0 = time.perf_counter()
         launches0 = eng.launch_count()
         work0 = dict(eng.work)
         out = forward_select(eng, hy, ds.m, len(self.phis), console=self.ConsoleOutput, rng=B200_CONFIG['rng'],
-                             eager=B200_CONFIG['eager_chains'], pipeline=B200_CONFIG['pipeline'])
+                             eager=B200_CONFIG['eager_chains'], pipeline=B200_CONFIG['pipeline'],
+                             prefetch=B200_CONFIG.get('prefetch', False))
         eng.synchronize()
         LAST_FIT_INFO.clear()
         LAST_FIT_INFO.update(n_gibbs=out['n_gibbs'], n_batches=out['n_batches'], seconds=time.perf_counter() - t0,

@@ -146,10 +146,17 @@ class Engine:
         self.n_global = 0
         self.sum_y = self.yty = 0.0
         self.gibbs_launch_batches = 0
-        self.work = dict(eig_solves=0, chains_run=0, kill_loops=0, kill_proposals_scored=0)     # work counters (bench.py)
+        self.work = dict(eig_solves=0, chains_run=0, kill_loops=0, kill_proposals_scored=0, secular_steps=0)     # work counters (bench.py)
         self.profile = None      # set to {} to collect CUDA-event timings per stage (bench.py)
         self.ctx_side = None
         self.side_stream = None
+        # build-ahead of the next substage's columns (prefetch_terms): its own context / stream, and the physical layout
+        # of X while a block sits above a gap: logical column j lives at j (j < P_base) or j + gap (j >= P_base)
+        self.ctx_pf = None
+        self.pf_stream = None
+        self.pf = None
+        self.gap = 0
+        self.P_base = 0
 
     # ------------------------------------------------------------------------------------------------
     def release(self):
@@ -162,6 +169,9 @@ class Engine:
         if getattr(self, 'ctx_side', None) is not None and self.ctx_side:
             self.lib.fokl_ctx_destroy(self.ctx_side)
             self.ctx_side = None
+        if getattr(self, 'ctx_pf', None) is not None and self.ctx_pf:
+            self.lib.fokl_ctx_destroy(self.ctx_pf)
+            self.ctx_pf = None
         if getattr(self, 'ctx', None) is not None and self.ctx:
             self.lib.fokl_ctx_destroy(self.ctx)
             self.ctx = None
@@ -182,6 +192,14 @@ class Engine:
 
     def synchronize(self):
         self._ck(self.lib.fokl_ctx_synchronize(self.ctx))
+        if self.ctx_pf is not None:
+            rc = self.lib.fokl_ctx_synchronize(self.ctx_pf)      # also reports a range error of a build-ahead basis launch
+            if rc != 0:
+                msg = self.lib.fokl_last_error(self.ctx_pf)
+                msg = msg.decode() if msg else ''
+                if rc == _lib.ERANGE:
+                    raise ValueError(msg)
+                raise RuntimeError("libfokl_b200 error %d: %s" % (rc, msg))
 
     def launch_count(self):
         n = int(self.lib.fokl_launch_count(self.ctx))
@@ -241,6 +259,7 @@ class Engine:
             self.kernel_id = _lib.KERNEL_BERNOULLI
         else:
             raise ValueError("The kernel %r is not currently supported." % (kernel,))
+        self._pf_tab_key = None          # the build-ahead context uploads its own copy on next use
         self.n_orders = tab.shape[0]
         self._phis_tab, self._phis_kernel = tab, kernel
         self._phis_key = key
@@ -305,6 +324,8 @@ class Engine:
             self.Pcap = 0
             self.X = None
             self._ensure_columns(64 if n * 64 * 8 < (4 << 30) else 16)
+        self.drop_prefetch()
+        self.gap = self.P_base = 0
         self._ck(self.lib.fokl_fill_ones(self.ctx, self.X.data_ptr(), n))
         self.Xfull[0].copy_(ds.y)
         self.P = 0
@@ -346,7 +367,8 @@ class Engine:
         if Xn is None:
             raise MemoryError("design matrix of %d columns x %d rows does not fit in device memory" % (need, self.ds.n))
         if self.X is not None and self.P > 0:
-            Xn[:self.P + 1].copy_(self.Xfull[:self.P + 1])      # y row + the columns built so far
+            end = self.P + self.gap + 1                          # y row + the columns built so far (incl. a block above a gap)
+            Xn[:end].copy_(self.Xfull[:end])
         self.Xfull = Xn
         self.X = Xn[1:]
         self.Pcap = new_cap
@@ -388,14 +410,176 @@ class Engine:
                                             self.Xty.data_ptr()))
         self.P = p_old + c
 
-    def append_terms(self, terms):
-        """K1 + K2 for `terms` (C x M integer orders): appends C columns to X, extends G / Xty."""
+    # ---- build-ahead of a substage's columns ------------------------------------------------------------------------
+    # The candidate stage of substage s (one cluster eigensolver, one 2000-draw chain, the kill loop) leaves the device
+    # almost idle, and the columns of substage s + 1 do not depend on its outcome: only the NEW columns of s can be
+    # deleted (FR:1660), so the first p_stable = p_old(s) columns are final.  prefetch_terms() therefore runs K1 and the
+    # (old[0, p_stable) | new | y) x new part of K2 for s + 1 on a second context / stream while s is being decided;
+    # append_terms(.., p_stable) later adds the small cross block new x (survivors of s) and scatters everything.  The
+    # new block is written ABOVE the columns s may still delete (a gap in X, closed by the next compaction).  Every
+    # append that names p_stable is computed by this same two-part scheme whether or not it was started ahead of time,
+    # so the Gram bits -- and with them the whole fit -- do not depend on the timing.
+    def _pf_ctx(self):
+        torch = self.torch
+        if self.ctx_pf is None:
+            self.pf_stream = torch.cuda.Stream(device=self.device)
+            ctx = ctypes.c_void_p()
+            rc = self.lib.fokl_ctx_create(ctypes.byref(ctx), self.dev_index, ctypes.c_void_p(self.pf_stream.cuda_stream))
+            if rc != 0:
+                raise RuntimeError("fokl_ctx_create (build-ahead context) failed with code %d" % rc)
+            self.ctx_pf = ctx
+            sms = torch.cuda.get_device_properties(self.device).multi_processor_count
+            # its Gram kernel leaves these SMs to the candidate stage it runs next to (one 16-CTA cluster + single CTAs)
+            self.lib.fokl_ctx_set_sm_budget(ctx, max(sms - 20, sms // 2))
+            self.lib.fokl_ctx_set_high_priority(self.ctx, 1)
+            self._pf_tab_key = None
+        key = (id(self._phis_tab), self._phis_kernel)
+        if self._pf_tab_key != key:
+            tab = self._phis_tab
+            fn = self.lib.fokl_set_phis_cubic if self._phis_kernel == CUBIC else self.lib.fokl_set_phis_bernoulli
+            rc = fn(self.ctx_pf, tab.ctypes.data, tab.shape[0], tab.shape[1])
+            if rc != 0:
+                raise RuntimeError("build-ahead context: basis table upload failed with code %d" % rc)
+            self._pf_tab_key = key
+        return self.ctx_pf
+
+    def _ck_pf(self, rc):
+        if rc != 0:
+            msg = self.lib.fokl_last_error(self.ctx_pf)
+            raise RuntimeError("libfokl_b200 error %d (build-ahead context): %s" % (rc, msg.decode() if msg else ''))
+
+    def drop_prefetch(self):
+        """Forget a build-ahead block (roll-back, end of the fit): wait for its kernels first -- what follows may
+        overwrite the columns they read or write."""
+        if self.pf is not None:
+            self.pf_stream.synchronize()
+            self.pf = None
+
+    def phys_cols(self, cols):
+        cols = np.asarray(cols, dtype=np.int32)
+        if self.gap == 0:
+            return np.ascontiguousarray(cols)
+        return np.ascontiguousarray(np.where(cols >= self.P_base, cols + self.gap, cols).astype(np.int32))
+
+    def prefetch_terms(self, terms, p_stable, after=None, wait_eig=False):
+        """Start K1 + the first part of K2 for `terms` on the build-ahead stream.  p_stable: the leading columns of the
+        model that no pending decision can delete.  after: an event on the main stream the build must wait for (default:
+        everything enqueued so far).  wait_eig: also wait for the eigensolver launches of the candidate batches enqueued
+        last on the main and the side context -- their clusters need whole groups of free SMs, which the Gram kernel's
+        long-lived thread blocks would deny them."""
+        torch = self.torch
+        terms = np.ascontiguousarray(terms, dtype=np.int16)
+        c, m = terms.shape
+        if m != self.ds.m:
+            raise ValueError("term width does not match the number of inputs")
+        if c == 0 or p_stable < 1 or p_stable > (self.P_base if self.gap else self.P):
+            return None
+        self.drop_prefetch()
+        ctx = self._pf_ctx()
+        # position: below the current block if the gap has room above the columns that may survive, else above it
+        lo = self.P
+        if self.gap > 0 and lo + c <= self.P_base + self.gap:
+            b0 = lo
+        else:
+            b0 = self.P + self.gap
+        cap0 = self.Pcap
+        try:
+            self._ensure_columns(b0 + c)
+        except MemoryError:
+            return None
+        n = self.ds.n
+        block_a = torch.empty(((p_stable + c + 1) * c,), dtype=torch.float64, device=self.device)
+        if after is None or self.Pcap != cap0:       # a re-allocation copied X on the main stream just now
+            after = self.mark()
+        self.pf_stream.wait_event(after)
+        if wait_eig:
+            self._ck_pf(self.lib.fokl_ctx_wait_eig(ctx, self.ctx))
+            if self.ctx_side is not None:
+                self._ck_pf(self.lib.fokl_ctx_wait_eig(ctx, self.ctx_side))
+        with torch.cuda.stream(self.pf_stream):
+            t = self._tic()
+            self._ck_pf(self.lib.fokl_basis_build(ctx, self.kernel_id, self.ds.x.data_ptr(), n, self.ds.ldx, m,
+                                                 terms.ctypes.data, c, self.X[b0].data_ptr(), self.ld))
+            self._toc(t, 'basis', bytes=8.0 * n * (m + c), cells=float(n) * c)
+            t = self._tic()
+            self._ck_pf(self.lib.fokl_gram_update_ex(ctx, self.X.data_ptr(), self.ld, n, p_stable, c, b0, 0,
+                                                    self.Xfull.data_ptr(), block_a.data_ptr()))
+            self._toc(t, 'gram', flops=2.0 * n * (p_stable * c + c * (c + 1) / 2 + c), bytes=8.0 * n * (p_stable + c + 1),
+                      cols=p_stable + c + 1)
+            done = torch.cuda.Event()
+            done.record(self.pf_stream)
+        self.pf = dict(terms=terms, p_stable=int(p_stable), b0=int(b0), c=int(c), block=block_a, done=done)
+        return self.pf
+
+    def _close_gap(self):
+        """Move the block above the gap down so that the model is one contiguous run of columns again."""
+        if self.gap == 0:
+            return
+        keep = self.phys_cols(np.arange(self.P, dtype=np.int32))
+        t = self._tic()
+        self._ck(self.lib.fokl_columns_compact(self.ctx, self.X.data_ptr(), self.ld, self.ds.n, keep.ctypes.data, self.P))
+        self._toc(t, 'compact')
+        self.gap = 0
+        self.P_base = self.P
+
+    def _append_split(self, terms, p_stable):
+        """append_terms through the two-part scheme (see above): commit the matching build-ahead block, or build it now."""
+        torch = self.torch
+        c = terms.shape[0]
+        pf = self.pf
+        if pf is None or pf['p_stable'] != p_stable or pf['c'] != c or not np.array_equal(pf['terms'], terms):
+            self.drop_prefetch()
+            self._close_gap()
+            pf = self.prefetch_terms(terms, p_stable)
+            if pf is None:
+                raise MemoryError("design matrix does not fit in device memory")
+        self.pf = None
+        main = torch.cuda.current_stream(self.device)
+        main.wait_event(pf['done'])
+        self._close_gap()                      # the previous substage kept all its columns: no compaction closed the gap
+        p_old, n, b0 = self.P, self.ds.n, pf['b0']
+        k = p_old - p_stable
+        self._ensure_gram(p_old + c)
+        need = (p_old + c + 1) * c
+        if self.block is None or self.block.numel() < need:
+            self.block = torch.empty((int(need * 1.5) + 64,), dtype=torch.float64, device=self.device)
+        blk = self.block[:need].view(p_old + c + 1, c)
+        a = pf['block'].view(p_stable + c + 1, c)
+        blk[:p_stable].copy_(a[:p_stable])
+        blk[p_old:].copy_(a[p_stable:])
+        if k > 0:
+            # cross block: new columns x the columns that survived the previous substage (X base shifted to p_stable)
+            bb = torch.empty(((k + c + 1) * c,), dtype=torch.float64, device=self.device)
+            t = self._tic()
+            self._ck(self.lib.fokl_gram_update_ex(self.ctx, self.X[p_stable].data_ptr(), self.ld, n, k, c, b0 - p_stable,
+                                                  _lib.GRAM_CROSS_ONLY, self.Xfull.data_ptr(), bb.data_ptr()))
+            self._toc(t, 'gram', flops=2.0 * n * k * c, bytes=8.0 * n * (k + c), cols=k + c)
+            blk[p_stable:p_old].copy_(bb.view(k + c + 1, c)[:k])
+        a.record_stream(main)
+        if self.dist is not None:
+            t = self._tic()
+            self._allreduce(self.block[:need])
+            self._toc(t, 'allreduce', bytes=8.0 * need)
+        self._ck(self.lib.fokl_gram_scatter(self.ctx, self.block.data_ptr(), p_old, c, self.G.data_ptr(), self.Gcap,
+                                            self.Xty.data_ptr()))
+        self.P_base, self.gap = p_old, b0 - p_old
+        self.P = p_old + c
+
+    def append_terms(self, terms, p_stable=None):
+        """K1 + K2 for `terms` (C x M integer orders): appends C columns to X, extends G / Xty.  p_stable (optional):
+        number of leading columns that were already final when the previous substage began -- selects the two-part
+        scheme that prefetch_terms() can start ahead of time."""
         terms = np.ascontiguousarray(terms, dtype=np.int16)
         c, m = terms.shape
         if m != self.ds.m:
             raise ValueError("term width does not match the number of inputs")
         if c == 0:
             return
+        if p_stable is not None and 1 <= p_stable <= self.P:
+            self._append_split(terms, int(p_stable))
+            return
+        self.drop_prefetch()
+        self._close_gap()
         self._ensure_columns(self.P + c)
         t = self._tic()
         self._ck(self.lib.fokl_basis_build(self.ctx, self.kernel_id, self.ds.x.data_ptr(), self.ds.n, self.ds.ldx, m,
@@ -409,9 +593,12 @@ class Engine:
         p_new = len(keep)
         if p_new == self.P:
             return
+        src = self.phys_cols(keep)              # where the kept columns live (a block may sit above a gap)
         t = self._tic()
-        self._ck(self.lib.fokl_columns_compact(self.ctx, self.X.data_ptr(), self.ld, self.ds.n, keep.ctypes.data, p_new))
+        self._ck(self.lib.fokl_columns_compact(self.ctx, self.X.data_ptr(), self.ld, self.ds.n, src.ctypes.data, p_new))
         self._toc(t, 'compact')
+        self.gap = 0
+        self.P_base = p_new
         self._ck(self.lib.fokl_gram_compact(self.ctx, self.G.data_ptr(), self.Gcap, self.Xty.data_ptr(),
                                             keep.ctypes.data, p_new, self.G2.data_ptr(), self.Gcap, self.Xty2.data_ptr()))
         self.G, self.G2 = self.G2, self.G
@@ -462,7 +649,14 @@ class Engine:
 
     def truncate(self, p):
         """Forget the columns from p on (roll-back of a speculative append_terms)."""
-        self.P = int(p)
+        self.drop_prefetch()
+        p = int(p)
+        if self.gap > 0 and p > self.P_base:
+            self._close_gap()
+        elif self.gap > 0:
+            self.gap = 0
+        self.P = p
+        self.P_base = min(self.P_base, p)
 
     def mark(self):
         """An event on the main stream: evaluate_launch(side=True, after=mark) then orders the side batch after the work
@@ -559,6 +753,93 @@ class Engine:
         res.betahat, res.lamb, res.Q = betahat, lamb, Q
         return PendingCandidates(self, res, ev, info, col_sets, side, (G, Xty, var_t, sf_t))
 
+    # ---- chains of nested models (csrc/nested.cu) ---------------------------------------------------------------------
+    def nested_chains_launch(self, col_sets, hyp, seed, stream_ids, gram=None, side=False, after=None):
+        """Intercept statistics of the chains of NESTED models: col_sets[i + 1] is col_sets[i] minus one or more columns
+        (col_sets[i][0] = the intercept column).  One eigensolver run (the first model), then one secular-equation step +
+        one GEMM per removed column, then all chains in one launch.  Returns a handle; finish() -> dict(mean0 = per model
+        the mean of the intercept's draws over rows stat_from0 .., ok = False if a step met equal eigenvalues or a chain
+        saw bstar < 0 -- evaluate the models with evaluate_launch then)."""
+        torch = self.torch
+        G, Xty, ldg = gram if gram is not None else (self.G, self.Xty, self.Gcap)
+        head = np.ascontiguousarray(col_sets[0], dtype=np.int32)
+        p0 = len(head)
+        pend = self.evaluate_launch([head], hyp, rng_mode=_lib.RNG_NONE, want_eig=True, gram=(G, Xty, ldg), side=side,
+                                    after=after)
+        ctx = self._side() if side else self.ctx
+        n_models = len(col_sets)
+        widths = np.array([len(c) for c in col_sets], dtype=np.int32)
+        offs = np.zeros(n_models, dtype=np.int64)
+        offs[1:] = np.cumsum(widths.astype(np.int64))[:-1]
+        total = int(widths.sum())
+        pos_of = {int(c): e for e, c in enumerate(head)}
+        with (torch.cuda.stream(self.side_stream) if side else contextlib.nullcontext()):
+            f64 = dict(dtype=torch.float64, device=self.device)
+            lam_all, ct_all, q0_all = torch.empty(total, **f64), torch.empty(total, **f64), torch.empty(total, **f64)
+            status = torch.zeros(1, dtype=torch.int32, device=self.device)
+            xty = Xty.index_select(0, torch.as_tensor(head.astype(np.int64), device=self.device)).clone()
+            lam = pend.res.lamb
+            Qs = pend.res.Q.view(p0, p0)              # rows = eigenvectors, columns = the head model's columns
+            work = torch.empty(4 * p0 + 8, **f64)
+            t = self._tic()
+            steps = 0
+            prev = set(int(c) for c in head)
+            for i, cols in enumerate(col_sets):
+                if i > 0:
+                    cur = set(int(c) for c in cols)
+                    for col in sorted(prev - cur):
+                        m = pos_of[col]
+                        p = lam.numel()
+                        u = Qs[:, m].contiguous()
+                        mu = torch.empty(p - 1, **f64)
+                        zt = torch.empty((p - 1, p), **f64)
+                        rc = self.lib.fokl_secular_step(ctx, lam.data_ptr(), u.data_ptr(), p, mu.data_ptr(), zt.data_ptr(), p,
+                                                        work.data_ptr(), status.data_ptr())
+                        if rc != 0:
+                            msg = self.lib.fokl_last_error(ctx)
+                            raise RuntimeError("libfokl_b200 error %d: %s" % (rc, msg.decode() if msg else ''))
+                        Qs = torch.matmul(zt, Qs)       # plain FP64 GEMM (cuBLAS): Q_new = Z' Q
+                        lam = mu
+                        xty[m] = 0.0                    # the removed variable: its components are zero to rounding
+                        steps += 1
+                    prev = cur
+                o, w = int(offs[i]), int(widths[i])
+                lam_all[o:o + w].copy_(lam)
+                torch.mv(Qs, xty, out=ct_all[o:o + w])
+                q0_all[o:o + w].copy_(Qs[:, 0])
+            p_dev = torch.from_numpy(widths).to(self.device)
+            off_dev = torch.from_numpy(offs).to(self.device)
+            sid_dev = torch.from_numpy(np.ascontiguousarray(stream_ids, dtype=np.uint64).view(np.int64)).to(self.device)
+            mean0 = torch.empty(n_models, **f64)
+            info = torch.zeros(n_models, dtype=torch.int32, device=self.device)
+            rc = self.lib.fokl_chain_icpt(ctx, n_models, p_dev.data_ptr(), off_dev.data_ptr(), sid_dev.data_ptr(),
+                                          lam_all.data_ptr(), ct_all.data_ptr(), q0_all.data_ptr(), ctypes.byref(hyp),
+                                          ctypes.c_uint64(int(seed)), mean0.data_ptr(), info.data_ptr())
+            if rc != 0:
+                msg = self.lib.fokl_last_error(ctx)
+                raise RuntimeError("libfokl_b200 error %d: %s" % (rc, msg.decode() if msg else ''))
+            self._toc(t, 'nested_chains', cands=n_models, steps=steps, pmax=int(p0))
+        self.work['eig_solves'] += 0            # (the head's solve was counted by evaluate_launch)
+        self.work['chains_run'] += n_models
+        self.work['secular_steps'] = self.work.get('secular_steps', 0) + steps
+        eng = self
+        keep = (lam_all, ct_all, q0_all, p_dev, off_dev, sid_dev, xty, work, pend)
+
+        class _Pending:
+            def finish(_self):
+                with (torch.cuda.stream(eng.side_stream) if side else contextlib.nullcontext()):
+                    st = int(status.cpu().item())
+                    m0 = mean0.cpu().numpy()
+                    inf = info.cpu().numpy()
+                if side:
+                    main_stream = torch.cuda.current_stream(eng.device)
+                    main_stream.wait_stream(eng.side_stream)
+                    for tns in keep[:8] + (mean0, info, status):
+                        tns.record_stream(main_stream)
+                ok = st == 0 and not inf.any() and bool(np.all(np.isfinite(m0)))
+                return dict(mean0=m0, ok=ok, status=st)
+        return _Pending()
+
     def refine_mask(self, ev, p, refine_tol=1e-7):
         """Candidates whose Gram-only BIC is not trustworthy (non-finite, or a residual variance below refine_tol of
         var(y): catastrophic cancellation) and must be recomputed from an N-length residual pass."""
@@ -629,7 +910,7 @@ class Engine:
         """BIC of FR:1551-1554 from an explicit N-length residual pass over X (used when the Gram-only
         formula has lost too many digits to cancellation)."""
         torch = self.torch
-        cols = np.ascontiguousarray(cols, dtype=np.int32)
+        cols = self.phys_cols(cols)
         out = torch.zeros(2, dtype=torch.float64, device=self.device)
         self._ck(self.lib.fokl_residual_moments(self.ctx, self.X.data_ptr(), self.ld, self.ds.n, len(cols),
                                                 cols.ctypes.data, betahat_dev.data_ptr(), self.ds.y.data_ptr(),

@@ -11,13 +11,14 @@ CSRC = os.path.join(os.path.dirname(_HERE), 'csrc')
 SO_PATH = os.path.join(CSRC, 'libfokl_b200.so')
 if os.environ.get('FOKL_B200_LIB'):        # kernel-variant experiments (tools/): another build of the same sources
     SO_PATH = os.path.abspath(os.environ['FOKL_B200_LIB'])
-SOURCES = ['ctx.cu', 'basis.cu', 'gram.cu', 'candidates.cu']
+SOURCES = ['ctx.cu', 'basis.cu', 'gram.cu', 'candidates.cu', 'nested.cu']
 HEADERS = ['fokl_ctx.cuh', 'fokl_math.cuh', 'cand_math.cuh', 'gram_plan.h', 'eigbig.cuh', 'killbig.cuh']
 
 ABI_VERSION = 1
 KERNEL_CUBIC, KERNEL_BERNOULLI = 0, 1
 RNG_NONE, RNG_INJECTED, RNG_PHILOX = 0, 1, 2
 ERANGE = -4
+GRAM_CROSS_ONLY = 1
 
 _vp = ctypes.c_void_p
 _i64 = ctypes.c_int64
@@ -53,14 +54,19 @@ PROTOTYPES = {
     'fokl_basis_build': (_i32, [_vp, _i32, _vp, _i64, _i64, _i32, _vp, _i32, _vp, _i64]),
     'fokl_basis_build_deriv': (_i32, [_vp, _i32, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _i32, _vp, _i64]),
     'fokl_ctx_set_sm_budget': (_i32, [_vp, _i32]),
+    'fokl_ctx_set_high_priority': (_i32, [_vp, _i32]),
+    'fokl_ctx_wait_eig': (_i32, [_vp, _vp]),
     'fokl_fill_ones': (_i32, [_vp, _vp, _i64]),
     'fokl_gram_update': (_i32, [_vp, _vp, _i64, _i64, _i32, _i32, _vp, _vp]),
+    'fokl_gram_update_ex': (_i32, [_vp, _vp, _i64, _i64, _i32, _i32, _i32, _i32, _vp, _vp]),
     'fokl_y_moments': (_i32, [_vp, _vp, _i64, _vp]),
     'fokl_gram_scatter': (_i32, [_vp, _vp, _i32, _i32, _vp, _i64, _vp]),
     'fokl_gram_compact': (_i32, [_vp, _vp, _i64, _vp, _vp, _i32, _vp, _i64, _vp]),
     'fokl_columns_compact': (_i32, [_vp, _vp, _i64, _i64, _vp, _i32]),
     'fokl_candidates_eval': (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _i32, ctypes.POINTER(Hypers), _vp, _i32, _u64,
                                     _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'fokl_secular_step': (_i32, [_vp, _vp, _vp, _i32, _vp, _vp, _i64, _vp, _vp]),
+    'fokl_chain_icpt': (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(Hypers), _u64, _vp, _vp]),
     'fokl_kill_scores': (_i32, [_vp, _vp, _i64, _vp, _vp, _i32, _vp, _i32, ctypes.POINTER(Hypers), _vp, _vp]),
     'fokl_kill_loop': (_i32, [_vp, _vp, _i64, _vp, _vp, _i32, _vp, _vp, _vp, _i32, ctypes.POINTER(Hypers),
                               ctypes.POINTER(KillParams), _vp, _vp]),

@@ -110,13 +110,17 @@ class PhiloxVariates:
 
 
 def forward_select(engine, hy, m, n_phis, console=True, rng='philox', eager=False, on_substage=None,
-                   recorder=None, pipeline=None):
+                   recorder=None, pipeline=None, prefetch=False):
     """Run the selection loop on an Engine that has a dataset bound (engine.begin_fit).
 
     hy: dict with a, b, atau, btau, tolerance, total_draws, gimmie, way3, threshav, threshstda, threshstdb, aic.
     pipeline (default: on for the free-running fast path): evaluate the chains that verify substage s together with
     the full model of substage s + 1 (see the module docstring of the driver loop below); the result is bit-identical
     to pipeline=False.
+    prefetch (opt-in): build the columns and most of the Gram block of substage s + 1 on a second stream while the
+    candidate stage of s runs (Engine.prefetch_terms).  Every substage's block is then formed by the same two-part
+    scheme whether or not it was started ahead of time, so the fit does not depend on the timing (it differs from the
+    prefetch=False fit in the last bits of the Gram: another summation order).
     Returns dict(betas=(D x P) numpy of the chosen model, mtx, evs, n_gibbs, n_batches)."""
     torch = engine.torch
     n = engine.n_global
@@ -199,12 +203,28 @@ def forward_select(engine, hy, m, n_phis, console=True, rng='philox', eager=Fals
         return ind, first_partition(ind, m, sett)
 
     # ---- phase A: append the new terms' columns (K1 + K2) -----------------------------------------------------------
-    def open_substage(ind, part, terms_in):
+    can_split = bool(prefetch) and hasattr(engine, 'prefetch_terms')      # (the tests' CPU stand-in engine has none)
+
+    def open_substage(ind, part, terms_in, p_stable=None):
+        """p_stable: the model width when the PREVIOUS substage began -- its first p_stable columns were final from
+        then on, so the build of this substage may have been started ahead of time (see start_next)."""
         vecs = distinct_permutations(part)
         p_old = engine.P                     # columns of the model accepted so far (incl. intercept)
-        engine.append_terms(vecs)
-        return dict(ind=ind, part=list(part), vecs=vecs, vm=vecs.shape[0], p_old=p_old,
+        if can_split:
+            engine.append_terms(vecs, p_stable=p_stable)
+        else:
+            engine.append_terms(vecs)
+        return dict(ind=ind, part=list(part), vecs=vecs, vm=vecs.shape[0], p_old=p_old, p_stable=p_stable,
                     terms=np.concatenate([terms_in, vecs], axis=0), full=list(range(engine.P)))
+
+    def start_next(S, after):
+        """Build ahead: K1 + the stable part of K2 of the substage that follows S, next to S's candidate stage."""
+        if not can_split:
+            return
+        nxt = walk_next(S['ind'], S['part'])
+        if nxt is None:
+            return
+        engine.prefetch_terms(distinct_permutations(nxt[1]), S['p_old'], after=after, wait_eig=True)
 
     # ---- phase B: the full model (FR:1650), evaluated as (launch, finish) so that other work can ride along ------------
     def full_launch(S):
@@ -300,33 +320,100 @@ def forward_select(engine, hy, m, n_phis, console=True, rng='philox', eager=Fals
     # The models of a batch are independent: with several ranks each evaluates every world-th one (all ranks hold the
     # full Gram) and the two scalars per model that drive the loop are summed into place by one allreduce, so every
     # rank takes the same decisions.
+    # Nested path (csrc/nested.cu): the accepted models of a substage are nested (each is its predecessor minus one
+    # column), and all the loop reads from their chains is |mean intercept|.  A batch of wide models is therefore
+    # evaluated by ONE eigensolver run + one secular-equation step per deleted column instead of one eigensolver run per
+    # model; their BIC is the kill loop's own (the same Gram-only quantity).  The last accepted model -- whose draws the
+    # substage returns (FR:1690) -- always takes the ordinary path.
+    use_nested = (mode == _lib.RNG_PHILOX and hasattr(engine, 'nested_chains_launch') and
+                  bool(hy.get('nested_chains', True)))
+    # below ~400 columns a batch of cold models (cluster eigensolver, ~0.1 ms per model in a batch of 160) beats the
+    # sequential chain of updates (~0.15 ms per step + the head's solve): measured on cfg4 (widths <= 227)
+    nested_min_models, nested_min_p = int(hy.get('nested_min_models', 4)), int(hy.get('nested_min_p', 384))
+
+    def nested_ok(todo, idx):
+        if not use_nested or len(idx) < nested_min_models or len(todo[idx[0]]['cols']) < nested_min_p:
+            return False
+        if any('ev_dev' not in todo[i] for i in idx):
+            return False
+        ev = np.array([todo[i]['ev_dev'] - aic_adj * len(todo[i]['cols']) for i in idx])
+        pw = np.array([len(todo[i]['cols']) for i in idx])
+        return not bool(np.any(engine.refine_mask(ev, pw)))       # Gram-only BICs must be trustworthy (no residual pass here)
+
     def chains_launch(todo, which, gram=None, side=False, after=None):
+        """Returns a list of parts (kind, handle, indices) or None."""
         if not which:
             return None
-        cnt['batches'] += 1
-        return engine.evaluate_launch([todo[i]['cols'] for i in which], hyp, rng_mode=mode,
-                                      run_chain=np.ones(len(which), dtype=np.uint8), seed=seed,
-                                      stream_ids=np.asarray([todo[i]['stream'] for i in which], dtype=np.uint64),
-                                      want_betas=True, gram=gram, side=side, after=after)
+        parts = []
+        cold = list(which)
+        last = len(todo) - 1
+        nest = [i for i in which if i != last]
+        if nested_ok(todo, nest):
+            cnt['batches'] += 1
+            h = engine.nested_chains_launch([todo[i]['cols'] for i in nest], hyp, seed,
+                                            np.asarray([todo[i]['stream'] for i in nest], dtype=np.uint64), gram=gram,
+                                            side=side, after=after)
+            parts.append(('nested', h, nest, gram))
+            cold = [i for i in which if i == last]
+        if cold:
+            cnt['batches'] += 1
+            h = engine.evaluate_launch([todo[i]['cols'] for i in cold], hyp, rng_mode=mode,
+                                       run_chain=np.ones(len(cold), dtype=np.uint8), seed=seed,
+                                       stream_ids=np.asarray([todo[i]['stream'] for i in cold], dtype=np.uint64),
+                                       want_betas=True, gram=gram, side=side, after=after)
+            parts.append(('cold', h, cold, gram))
+        return parts
 
-    def chains_collect(todo, which, handle, vals, refine):
+    def chains_collect(todo, which, parts, vals, refine):
         """Fill vals[i] = (|mean intercept|, BIC) and todo[i]['rr' / 'slot'] for the models `which`; returns True if a
         model's Gram-only BIC is not trustworthy and refine is off (see Engine.refine_mask)."""
-        if handle is None:
+        if parts is None:
             return False
-        rr = handle.finish(1e-7 if refine else None)
-        stats_h = getattr(rr, 'stats_host', None)      # one read-back for the whole batch
-        if stats_h is None:
-            stats_h = rr.stats.cpu().numpy()
-        for slot, i in enumerate(which):
-            # mean(beters[h0:, 0]) of this model: row 2, column 0 of its 3 x p statistics block
-            vals[i, 0] = abs(float(stats_h[3 * rr.vec_off[slot] + 2 * rr.p[slot]]))
-            vals[i, 1] = float(rr.ev[slot]) + aic_adj * len(todo[i]['cols'])
-            todo[i]['rr'], todo[i]['slot'] = rr, slot
-        return (not refine) and bool(np.any(engine.refine_mask(rr.ev, rr.p)))
+        need = False
+        for kind, handle, idx, gram in parts:
+            if kind == 'nested':
+                r = handle.finish()
+                if r['ok']:
+                    for slot, i in enumerate(idx):
+                        vals[i, 0] = abs(float(r['mean0'][slot]))
+                        vals[i, 1] = float(todo[i]['ev_dev'])
+                        todo[i]['rr'], todo[i]['slot'] = None, None
+                    continue
+                # equal eigenvalues met on the way (or a failed chain): the ordinary path, now
+                cnt['batches'] += 1
+                handle = engine.evaluate_launch([todo[i]['cols'] for i in idx], hyp, rng_mode=mode,
+                                                run_chain=np.ones(len(idx), dtype=np.uint8), seed=seed,
+                                                stream_ids=np.asarray([todo[i]['stream'] for i in idx], dtype=np.uint64),
+                                                want_betas=True, gram=gram)
+            rr = handle.finish(1e-7 if refine else None)
+            stats_h = getattr(rr, 'stats_host', None)      # one read-back for the whole batch
+            if stats_h is None:
+                stats_h = rr.stats.cpu().numpy()
+            for slot, i in enumerate(idx):
+                # mean(beters[h0:, 0]) of this model: row 2, column 0 of its 3 x p statistics block
+                vals[i, 0] = abs(float(stats_h[3 * rr.vec_off[slot] + 2 * rr.p[slot]]))
+                vals[i, 1] = float(rr.ev[slot]) + aic_adj * len(todo[i]['cols'])
+                todo[i]['rr'], todo[i]['slot'] = rr, slot
+            need = need or ((not refine) and bool(np.any(engine.refine_mask(rr.ev, rr.p))))
+        return need
+
+    def share_of(todo):
+        """(indices this rank evaluates, owner rank of every index or None).  Wide nested batches are cut into one
+        contiguous run per rank (a run costs one eigensolver + its steps); otherwise models are dealt round-robin."""
+        n_t = len(todo)
+        if world == 1:
+            return list(range(n_t)), None
+        if nested_ok(todo, list(range(n_t - 1))) and n_t - 1 >= world * nested_min_models:
+            w = np.array([float(len(rd['cols'])) ** 2 for rd in todo[:-1]])
+            cum = np.cumsum(w) / w.sum()
+            owners = np.minimum((cum * world - 1e-9).astype(np.int64), world - 1)
+            owners = np.concatenate([owners, [world - 1]])
+        else:
+            owners = np.arange(n_t) % world
+        return [i for i in range(n_t) if owners[i] == engine.rank], owners
 
     def my_share(todo):
-        return list(range(engine.rank, len(todo), world)) if world > 1 else list(range(len(todo)))
+        return share_of(todo)[0]
 
     def chains_reduce(todo, vals, need_refine):
         """All ranks: sum the per-model scalars into place; returns True if any rank flagged a model for refinement."""
@@ -335,8 +422,9 @@ def forward_select(engine, hy, m, n_phis, console=True, rng='philox', eager=Fals
             t = torch.from_numpy(vals).to(engine.device)
             engine._allreduce(t)
             vals[:] = t.cpu().numpy()
+            owners = share_of(todo)[1]
             for i, rd in enumerate(todo):
-                rd['owner'] = i % world
+                rd['owner'] = int(owners[i])
             need_refine = vals[len(todo), 0] > 0
         return bool(need_refine)
 
@@ -583,7 +671,7 @@ def forward_select(engine, hy, m, n_phis, console=True, rng='philox', eager=Fals
     carry = None            # dict(S=previous substage, gen=its generator, todo, gram=its Gram before compaction, cnt0)
     while True:
         # ---- B(s) [+ chains of s - 1] ----
-        mark = engine.mark() if carry is not None else None
+        mark = engine.mark() if (carry is not None or can_split) else None
         handle = full_launch(S)
         if carry is not None:
             # the side batch's stream waits for what the main stream held at `mark` (K1 + K2 of s, which it must not
@@ -591,6 +679,7 @@ def forward_select(engine, hy, m, n_phis, console=True, rng='philox', eager=Fals
             # the batch's many clusters fill the device around it
             todo, vals, mine = carry['todo'], np.zeros((len(carry['todo']) + 1, 2)), my_share(carry['todo'])
             side = chains_launch(todo, mine, gram=carry['gram'], side=True, after=mark)
+        start_next(S, mark)          # after both launches: the build waits for their eigensolver kernels
         full_finish(S, handle)
         # C(s) starts here: its kill-loop launch is enqueued before the host turns to the chains of s - 1, so the
         # collection / checks / bookkeeping of s - 1 (and any wait for a long side batch) run while that kernel does
@@ -614,7 +703,10 @@ def forward_select(engine, hy, m, n_phis, console=True, rng='philox', eager=Fals
                 # (what was started for substage s, including its kill loop, is dropped)
                 assert req_prev[0] == 'rollback'
                 engine.truncate(prev['p_old'])
-                engine.append_terms(prev['vecs'])
+                if can_split:
+                    engine.append_terms(prev['vecs'], p_stable=prev['p_stable'])
+                else:
+                    engine.append_terms(prev['vecs'])
                 cnt['calls'], cnt['gibbs'] = carry['cnt0']['calls'], carry['cnt0']['gibbs']
                 terms = prev['terms']
                 req_prev, outcome = step_gen(gen, 'done')
@@ -626,7 +718,7 @@ def forward_select(engine, hy, m, n_phis, console=True, rng='philox', eager=Fals
                 step = walk_next(S['ind'], S['part'])
                 if finished or step is None:
                     break
-                S = open_substage(step[0], step[1], terms)
+                S = open_substage(step[0], step[1], terms, p_stable=S['p_old'])
                 continue
             carry = None
             saved = dict(cnt)
@@ -660,14 +752,16 @@ def forward_select(engine, hy, m, n_phis, console=True, rng='philox', eager=Fals
                 terms = S['terms_final']
                 cnt['calls'], cnt['gibbs'] = outlook['calls'], outlook['gibbs']
                 carry = dict(S=S, gen=gen_s, todo=todo, gram=gram, cnt0=cnt0)
-                S = open_substage(step[0], step[1], terms)
+                S = open_substage(step[0], step[1], terms, p_stable=S['p_old'])
                 continue
             outcome = drive(gen_s, request, S)
         finished = close_substage(S, outcome, compacted=False)
         if finished or step is None:
             break
-        S = open_substage(step[0], step[1], terms)
+        S = open_substage(step[0], step[1], terms, p_stable=S['p_old'])
 
+    if can_split:
+        engine.drop_prefetch()          # a build started for a substage that never opens
     chosen = last if hy['gimmie'] else best
     betas = chosen[0].cpu().numpy()
     return dict(betas=betas, mtx=chosen[1].astype(np.float64), evs=np.array(evs, dtype=np.float64),

@@ -779,6 +779,8 @@ extern "C" int fokl_candidates_eval(fokl_ctx *ctx, const double *G, int64_t ldg,
     if (rng_mode != FOKL_RNG_NONE && hyp->draws < 1) FOKL_FAIL(ctx, FOKL_EINVAL, "candidates_eval: draws < 1");
     int rc = fokl_bind_device(ctx);
     if (rc) return rc;
+    fokl_hp_scope hp(ctx);
+    if (hp.rc) return hp.rc;
 
     const int D = hyp->draws;
     const size_t smem_cap = ctx->smem_optin ? ctx->smem_optin : 48 * 1024;
@@ -1135,6 +1137,11 @@ extern "C" int fokl_candidates_eval(fokl_ctx *ctx, const double *G, int64_t ldg,
         FOKL_LAUNCH_CHECK(ctx);
     }
     (void)any_fallback;
+    // every eigensolver launch of this call is enqueued: a Gram build on another context that must not take the SMs
+    // away from the cluster launches waits for this point (fokl_ctx_wait_eig)
+    if (!ctx->ev_eig) FOKL_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_eig, cudaEventDisableTiming));
+    FOKL_CUDA(ctx, cudaEventRecord(ctx->ev_eig, ctx->stream));
+    ctx->ev_eig_set = true;
     if (n_chain == 0) return FOKL_OK;
 
     // ---- chain -------------------------------------------------------------------------------------------------
@@ -1185,6 +1192,8 @@ extern "C" int fokl_kill_scores(fokl_ctx *ctx, const double *G, int64_t ldg, con
         if (props[a] < 1 || props[a] >= p) FOKL_FAIL(ctx, FOKL_EINVAL, "kill_scores: proposal position out of range");
     int rc = fokl_bind_device(ctx);
     if (rc) return rc;
+    fokl_hp_scope hp(ctx);
+    if (hp.rc) return hp.rc;
     const size_t smem_cap = ctx->smem_optin ? ctx->smem_optin : 48 * 1024;
     const int header = 2 * 3 * (kKillThreads / 32) + 2;
     const int smem_l_cap = (int)(smem_cap / sizeof(double)) - header;
@@ -1235,6 +1244,8 @@ extern "C" int fokl_kill_loop(fokl_ctx *ctx, const double *G, int64_t ldg, const
         if (cand_pos[i] < 1 || cand_pos[i] >= p) FOKL_FAIL(ctx, FOKL_EINVAL, "kill_loop: candidate position out of range");
     int rc = fokl_bind_device(ctx);
     if (rc) return rc;
+    fokl_hp_scope hp(ctx);
+    if (hp.rc) return hp.rc;
     const size_t smem_cap = ctx->smem_optin ? ctx->smem_optin : 48 * 1024;
     const int head = 2 + ((p + 2) & ~1);                         // flags + pivot-row copy
     const int smem_t_cap = (int)(smem_cap / sizeof(double)) - head;

@@ -46,7 +46,9 @@ cudaStream_t fokl_aux_fork(fokl_ctx *ctx, int i)
 {
     if (i < 0 || i >= fokl_ctx::kAux || !ctx->ev_fork) return nullptr;
     if (!ctx->aux[i]) {
-        if (cudaStreamCreateWithFlags(&ctx->aux[i], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        int least = 0, greatest = 0;
+        if (ctx->hp_on) cudaDeviceGetStreamPriorityRange(&least, &greatest);
+        if (cudaStreamCreateWithPriority(&ctx->aux[i], cudaStreamNonBlocking, ctx->hp_on ? greatest : 0) != cudaSuccess) return nullptr;
         if (cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
     }
     if (cudaStreamWaitEvent(ctx->aux[i], ctx->ev_fork, 0) != cudaSuccess) return nullptr;
@@ -58,6 +60,52 @@ int fokl_aux_join(fokl_ctx *ctx, int i)
     if (i < 0 || i >= fokl_ctx::kAux || !ctx->aux[i]) FOKL_FAIL(ctx, FOKL_ESTATE, "aux stream join without fork");
     FOKL_CUDA(ctx, cudaEventRecord(ctx->ev_join[i], ctx->aux[i]));
     FOKL_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join[i], 0));
+    return FOKL_OK;
+}
+
+fokl_hp_scope::fokl_hp_scope(fokl_ctx *c) : ctx(c)
+{
+    if (!ctx || !ctx->hp_on) return;
+    auto fail = [&](cudaError_t e, const char *what) {
+        ctx->err = std::string("high-priority scope: ") + what + " -> " + cudaGetErrorString(e);
+        rc = FOKL_ECUDA;
+    };
+    cudaError_t e;
+    if (!ctx->hp_stream) {
+        int least = 0, greatest = 0;
+        if ((e = cudaDeviceGetStreamPriorityRange(&least, &greatest)) != cudaSuccess) { fail(e, "priority range"); return; }
+        if ((e = cudaStreamCreateWithPriority(&ctx->hp_stream, cudaStreamNonBlocking, greatest)) != cudaSuccess)
+            { fail(e, "stream create"); return; }
+        if ((e = cudaEventCreateWithFlags(&ctx->ev_hp_in, cudaEventDisableTiming)) != cudaSuccess) { fail(e, "event create"); return; }
+        if ((e = cudaEventCreateWithFlags(&ctx->ev_hp_out, cudaEventDisableTiming)) != cudaSuccess) { fail(e, "event create"); return; }
+    }
+    if ((e = cudaEventRecord(ctx->ev_hp_in, ctx->stream)) != cudaSuccess) { fail(e, "event record"); return; }
+    if ((e = cudaStreamWaitEvent(ctx->hp_stream, ctx->ev_hp_in, 0)) != cudaSuccess) { fail(e, "stream wait"); return; }
+    saved = ctx->stream;
+    ctx->stream = ctx->hp_stream;
+    active = true;
+}
+
+fokl_hp_scope::~fokl_hp_scope()
+{
+    if (!active) return;
+    ctx->stream = saved;
+    if (cudaEventRecord(ctx->ev_hp_out, ctx->hp_stream) == cudaSuccess) cudaStreamWaitEvent(saved, ctx->ev_hp_out, 0);
+}
+
+extern "C" int fokl_ctx_wait_eig(fokl_ctx *waiter, fokl_ctx *src)
+{
+    FOKL_CHECK_CTX(waiter);
+    FOKL_CHECK_CTX(src);
+    if (!src->ev_eig_set) return FOKL_OK;
+    FOKL_CUDA(waiter, cudaStreamWaitEvent(waiter->stream, src->ev_eig, 0));
+    return FOKL_OK;
+}
+
+extern "C" int fokl_ctx_set_high_priority(fokl_ctx *ctx, int on)
+{
+    FOKL_CHECK_CTX(ctx);
+    ctx->hp_on = on != 0;
     return FOKL_OK;
 }
 
@@ -103,6 +151,10 @@ extern "C" int fokl_ctx_destroy(fokl_ctx *ctx)
         if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
     }
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->hp_stream) { cudaStreamSynchronize(ctx->hp_stream); cudaStreamDestroy(ctx->hp_stream); }
+    if (ctx->ev_eig) cudaEventDestroy(ctx->ev_eig);
+    if (ctx->ev_hp_in) cudaEventDestroy(ctx->ev_hp_in);
+    if (ctx->ev_hp_out) cudaEventDestroy(ctx->ev_hp_out);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return FOKL_OK;

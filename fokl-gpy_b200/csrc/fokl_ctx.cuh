@@ -40,6 +40,16 @@ struct fokl_ctx {
     cudaEvent_t ev_fork = nullptr;
     cudaEvent_t ev_join[kAux] = {nullptr, nullptr, nullptr};
 
+    // optional high-priority stream for the latency-bound candidate stage (fokl_ctx_set_high_priority): its kernels are
+    // dispatched ahead of the pending CTAs of bandwidth- / tensor-bound kernels that another context runs next to them
+    bool hp_on = false;
+    cudaStream_t hp_stream = nullptr;
+    cudaEvent_t ev_hp_in = nullptr, ev_hp_out = nullptr;
+
+    // recorded by fokl_candidates_eval right after its eigensolver launches (fokl_ctx_wait_eig)
+    cudaEvent_t ev_eig = nullptr;
+    bool ev_eig_set = false;
+
     // growable scratch buffers, indexed by purpose
     enum { B_META = 0, B_BASIS, B_GRAM, B_CAND_A, B_CAND_B, B_CAND_C, B_CAND_D, B_MISC, B_COUNT };
     fokl_buf bufs[B_COUNT];
@@ -72,6 +82,19 @@ int fokl_fork_point(fokl_ctx *ctx);
 cudaStream_t fokl_aux_fork(fokl_ctx *ctx, int i);
 // Join: make ctx->stream wait for everything enqueued on aux stream `i`.
 int fokl_aux_join(fokl_ctx *ctx, int i);
+
+// Scope guard: inside it ctx->stream is the context's high-priority stream (if enabled), ordered after everything
+// enqueued on the caller's stream so far; on exit the caller's stream is ordered after the scope's work.
+struct fokl_hp_scope {
+    fokl_ctx *ctx;
+    cudaStream_t saved = nullptr;
+    bool active = false;
+    int rc = FOKL_OK;
+    explicit fokl_hp_scope(fokl_ctx *c);
+    ~fokl_hp_scope();
+    fokl_hp_scope(const fokl_hp_scope &) = delete;
+    fokl_hp_scope &operator=(const fokl_hp_scope &) = delete;
+};
 
 static inline int fokl_bind_device(fokl_ctx *ctx)
 {

@@ -748,12 +748,21 @@ bool encode_gram_map(CUtensorMap *map, const double *base, int64_t ld, int64_t n
 extern "C" int fokl_gram_update(fokl_ctx *ctx, const double *X, int64_t ld, int64_t n, int p_old, int c,
                                 const double *y, double *block)
 {
+    return fokl_gram_update_ex(ctx, X, ld, n, p_old, c, p_old, 0, y, block);
+}
+
+extern "C" int fokl_gram_update_ex(fokl_ctx *ctx, const double *X, int64_t ld, int64_t n, int p_old, int c, int new_col0,
+                                   int flags, const double *y, double *block)
+{
     FOKL_CHECK_CTX(ctx);
-    if (!X || !y || !block || n < 1 || p_old < 0 || c < 1 || ld < n)
+    if (!X || !y || !block || n < 1 || p_old < 0 || c < 1 || ld < n || new_col0 < p_old)
         FOKL_FAIL(ctx, FOKL_EINVAL, "gram_update: bad argument");
+    const int gap = new_col0 - p_old;
+    const bool cross_only = (flags & FOKL_GRAM_CROSS_ONLY) != 0;
     if ((ld % 2) != 0 || ((uintptr_t)X % 16) != 0 || ((uintptr_t)y % 16) != 0)
         FOKL_FAIL(ctx, FOKL_EINVAL, "gram_update: X and y must be 16-byte aligned and ld even");
     if (p_old + c + 1 > 65000) FOKL_FAIL(ctx, FOKL_EINVAL, "gram_update: more than 65000 columns");
+    if (cross_only && p_old < 1) FOKL_FAIL(ctx, FOKL_EINVAL, "gram_update: cross-only block without old columns");
     int rc = fokl_bind_device(ctx);
     if (rc) return rc;
     const int p = p_old + c;
@@ -794,7 +803,7 @@ extern "C" int fokl_gram_update(fokl_ctx *ctx, const double *X, int64_t ld, int6
         return (size_t)st * (kb_ / 16) * slots * 128 + 2 * kMaxStagesTma * sizeof(uint64_t) + 1024;
     };
     if (use_mb || use_tma) {
-        plan = fokl::gram_make_plan(p_old, c, cap, warps);
+        plan = fokl::gram_make_plan(p_old, c, cap, warps, gap, cross_only);
         if (plan.tiles.empty() || plan.max_slots > cap) FOKL_FAIL(ctx, FOKL_ESTATE, "gram_update: empty or oversized plan");
     }
     if (use_mb) {
@@ -818,7 +827,7 @@ extern "C" int fokl_gram_update(fokl_ctx *ctx, const double *X, int64_t ld, int6
     }
     if (!use_mb && !use_tma) {
         warps = 16;
-        plan = fokl::gram_make_plan(p_old, c, cap, warps);
+        plan = fokl::gram_make_plan(p_old, c, cap, warps, gap, cross_only);
         if (plan.tiles.empty() || plan.max_slots > cap) FOKL_FAIL(ctx, FOKL_ESTATE, "gram_update: empty or oversized plan");
         // deepest slab that fits (fewer CTA-wide barriers per row), giving up one ring stage for it if necessary
         kb = 0;
@@ -847,7 +856,10 @@ extern "C" int fokl_gram_update(fokl_ctx *ctx, const double *X, int64_t ld, int6
 
     // row splits: about one resident CTA slot each
     const int64_t chunks = (n + kb - 1) / kb;
-    const int slots_total = ctx->num_sms * ctas_per_sm;
+    // a context with an SM budget (fokl_ctx_set_sm_budget) leaves the other SMs to the latency-bound kernels of the
+    // candidate stage it runs next to
+    const int sms_use = (ctx->sm_budget > 0 && ctx->sm_budget < ctx->num_sms) ? ctx->sm_budget : ctx->num_sms;
+    const int slots_total = sms_use * ctas_per_sm;
     int64_t want = std::max<int64_t>(1, slots_total / n_tiles);
     if (n_tiles > slots_total) want = 1;
     int nsplit = (int)std::max<int64_t>(1, std::min<int64_t>(want, chunks));
@@ -879,7 +891,7 @@ extern "C" int fokl_gram_update(fokl_ctx *ctx, const double *X, int64_t ld, int6
     FOKL_CUDA(ctx, cudaMemsetAsync(block, 0, (size_t)(p + 1) * c * sizeof(double), ctx->stream));
 
     GramParams P;
-    P.X = X; P.y = y; P.ld = ld; P.n = n; P.p = p;
+    P.X = X; P.y = y; P.ld = ld; P.n = n; P.p = p + gap;      // slot source P.p marks y (physical indices, gram_plan.h)
     P.kb = kb; P.kb_shift = kb_shift; P.stages = stages; P.max_slots = plan.max_slots;
     P.rows_per_split = rows_per_split;
     P.tiles = reinterpret_cast<const GramTileMeta *>(buf + off_tiles);
@@ -892,7 +904,7 @@ extern "C" int fokl_gram_update(fokl_ctx *ctx, const double *X, int64_t ld, int6
     if (use_tma) {
         GramTmaMaps maps;
         for (int k = 0; k < fokl::kGramBoxKinds; ++k)
-            if (!encode_gram_map(&maps.m[k], y, ld, n, p + 1, fokl::kGramBoxCols[k]))
+            if (!encode_gram_map(&maps.m[k], y, ld, n, p + gap + 1, fokl::kGramBoxCols[k]))
                 FOKL_FAIL(ctx, FOKL_ECUDA, "gram_update: cuTensorMapEncodeTiled failed");
         FOKL_CUDA(ctx, cudaFuncSetAttribute(gram_kernel_tma<15>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
         gram_kernel_tma<15><<<dim3(n_tiles, nsplit), 16 * 32, smem, ctx->stream>>>(

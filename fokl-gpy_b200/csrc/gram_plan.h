@@ -191,11 +191,18 @@ inline void gram_plan_place(GramPlan &pl, int warps, int kchunks, int mode = 0)
 }
 
 // max_slots_cap: most staged columns a tile may have (shared-memory budget), multiple of 16 and >= 32.
-inline GramPlan gram_make_plan(int p_old, int c, int max_slots_cap, int warps = kGramMaxWarps)
+// gap: the new columns are not stored right behind the old ones but `gap` columns further up (X columns
+// p_old + gap .. p_old + gap + c - 1: a block that was built ahead of time, while the columns in between were still
+// candidates of the previous substage); slot_src and the boxes then hold these PHYSICAL column indices and y is marked
+// by p_old + c + gap, while slot_arow / slot_bcol keep the logical output indices.  cross_only: only the
+// (old | y) x new fragments (the new x new part was formed by an earlier call).
+inline GramPlan gram_make_plan(int p_old, int c, int max_slots_cap, int warps = kGramMaxWarps, int gap = 0,
+                               bool cross_only = false)
 {
     const int kTileBlocks = gram_tile_blocks(warps);
     GramPlan pl;
     const int p = p_old + c;
+    auto phys = [&](int src) { return src < 0 ? -1 : (src >= p_old ? src + gap : src); };    // y (= p) -> p + gap
     const int fb = (c + 7) / 8;                      // fragment rows/cols of the new columns
     const int fo = (p_old + 1 + 7) / 8;              // fragment rows of old columns + y
     const int fa = fb + fo;                          // A-list length in fragments
@@ -204,7 +211,7 @@ inline GramPlan gram_make_plan(int p_old, int c, int max_slots_cap, int warps = 
         int o = e - fb * 8;                          // y first: [y | X_old] is one run of the engine's [y | X] buffer
         return o == 0 ? p : (o <= p_old ? o - 1 : -1);
     };
-    auto frag_needed = [&](int i, int j) { return i >= fb || i <= j; };
+    auto frag_needed = [&](int i, int j) { return i >= fb || (!cross_only && i <= j); };
     const int ba = (fa + 1) / 2, bb = (fb + 1) / 2;  // block rows / cols (a block = fragment pair)
     auto block_needed = [&](int ib, int jb) {
         for (int di = 0; di < 2; ++di)
@@ -265,8 +272,8 @@ inline GramPlan gram_make_plan(int p_old, int c, int max_slots_cap, int warps = 
             for (int r = 0; r < 8; ++r) {
                 int e = f * 8 + r;
                 int src = f < fa ? alist_src(e) : -1;
-                pl.slot_src.push_back(src);
-                pl.slot_arow.push_back(src < 0 ? -1 : src);             // output row index = X column index (y -> p)
+                pl.slot_src.push_back(phys(src));
+                pl.slot_arow.push_back(src < 0 ? -1 : src);             // output row index = logical column index (y -> p)
                 pl.slot_bcol.push_back((src >= p_old && src < p) ? src - p_old : -1);
             }
         std::vector<GramBlockMeta> full_blk, part_blk;
@@ -291,7 +298,7 @@ inline GramPlan gram_make_plan(int p_old, int c, int max_slots_cap, int warps = 
         // boxes: runs of 8-slot groups that are consecutive in [y | X], cut greedily into the largest box kinds
         tm.box_off = (int32_t)pl.boxes.size();
         {
-            auto xcol = [&](int src) { return src == p ? 0 : src + 1; };
+            auto xcol = [&](int src) { return src == p + gap ? 0 : src + 1; };     // physical index -> column of [y | X]
             const int n_grp = tm.n_slots / 8;
             int g = 0;
             while (g < n_grp) {

@@ -58,6 +58,15 @@ int64_t fokl_launch_count(fokl_ctx *ctx);
  * whose batches run next to another context's work (the pipelined selection loop) is given the device minus the
  * other's share, so that the two together still fit in one wave. */
 int fokl_ctx_set_sm_budget(fokl_ctx *ctx, int sms);
+/* on != 0: the candidate stage of this context (fokl_candidates_eval, fokl_kill_loop, fokl_kill_scores) is enqueued on
+ * a high-priority stream of the context, ordered after the context's stream on entry and before it on exit (same
+ * semantics for the caller), so that its small, latency-bound kernels are dispatched ahead of the pending thread
+ * blocks of a basis / Gram build that another context runs at the same time. */
+int fokl_ctx_set_high_priority(fokl_ctx *ctx, int on);
+/* make everything enqueued on `waiter` from now on wait until the eigensolver kernels of the most recent
+ * fokl_candidates_eval on `src` have finished (no-op if there was none).  Used to start a basis / Gram build on a second
+ * context only once the cluster launches of the candidate stage -- which need whole groups of free SMs -- are through. */
+int fokl_ctx_wait_eig(fokl_ctx *waiter, fokl_ctx *src);
 
 /* ---- basis tables: replaces getKernels.sp500()/bernoulli() output consumed at FR:1480-1482 ----
  * cubic:     tab (host) [n_orders][n_piece][4]  -- phis[s][k][piece] transposed to (s, piece, k)
@@ -95,6 +104,16 @@ int fokl_fill_ones(fokl_ctx *ctx, double *col, int64_t n);
  * 8 x 8 fragments lying entirely there are skipped and read back as 0; fokl_gram_scatter mirrors the upper triangle. */
 int fokl_gram_update(fokl_ctx *ctx, const double *X, int64_t ld, int64_t n, int p_old, int c,
                      const double *y, double *block);
+
+/* The same block for new columns that are NOT stored right behind the old ones: the new block occupies X columns
+ * [new_col0, new_col0 + c), new_col0 >= p_old (it was built ahead of time -- while the previous substage's candidate
+ * stage was still running -- above the columns that substage may yet delete); the output block keeps the layout above
+ * ((p_old + c + 1) x c, logical row order old | new | y).  flags: FOKL_GRAM_CROSS_ONLY = only the (old | y) x new rows
+ * (rows of the new x new part are left zero: an earlier call formed them).  A context with an SM budget
+ * (fokl_ctx_set_sm_budget) sizes the grid for that many SMs. */
+#define FOKL_GRAM_CROSS_ONLY 1
+int fokl_gram_update_ex(fokl_ctx *ctx, const double *X, int64_t ld, int64_t n, int p_old, int c, int new_col0,
+                        int flags, const double *y, double *block);
 
 /* moments of y: out (dev, 3 doubles) = { n, sum y, sum y^2 } (dtd, FR:1374). */
 int fokl_y_moments(fokl_ctx *ctx, const double *y, int64_t n, double *out);
@@ -151,6 +170,24 @@ int fokl_candidates_eval(fokl_ctx *ctx, const double *G, int64_t ldg, const doub
                          const uint64_t *stream_ids, const double *variates, const double *sign_fix,
                          double *ev, double *betahat, double *lamb, double *Q, double *betas,
                          double *sigs, double *taus, double *stats, int32_t *info);
+
+/* ---- chains of nested models (csrc/nested.cu) ------------------------------------------------------------------------
+ * The accepted models of one kill loop (FR:1669-1690) are nested: each is its predecessor with one column removed, and
+ * the selection loop needs, from the chain of each (FR:1690), only the posterior mean of the intercept (FR:1671).
+ * fokl_secular_step carries a spectral decomposition from a model to the next: lam (dev, p ascending eigenvalues),
+ * u (dev, p: the components of the p eigenvectors on the variable being removed) -> mu (dev, p - 1 ascending eigenvalues
+ * of the compressed matrix) and zt (dev, (p - 1) x ldz row-major: row i = new eigenvector i in the old eigenbasis), so
+ * that Q_new = zt Q (rows = eigenvectors) by a plain GEMM.  work: dev, 4 p doubles.  status (dev int, OR-ed, caller
+ * zeroes it): 1 = two equal eigenvalues (the step is not valid: fall back to fokl_candidates_eval), 2 = non-finite input.
+ * fokl_chain_icpt runs the eigenbasis draw loop (FR:1519-1548) of n_models models side by side from their
+ * (lam, ct = Q'X'y, q0 = intercept components of the eigenvectors), packed at off[i] (dev int64) with widths p[i] (dev
+ * int32), Philox streams stream_ids[i] (dev) -- the variates fokl_candidates_eval would use -- and returns
+ * mean0[i] = mean over draws stat_from0 .. of the intercept's draw, info[i] = 1 if bstar < 0 was seen. */
+int fokl_secular_step(fokl_ctx *ctx, const double *lam, const double *u, int p, double *mu, double *zt, int64_t ldz,
+                      double *work, int32_t *status);
+int fokl_chain_icpt(fokl_ctx *ctx, int n_models, const int32_t *p, const int64_t *off, const uint64_t *stream_ids,
+                    const double *lam, const double *ct, const double *q0, const fokl_hypers *hyp, uint64_t seed,
+                    double *mean0, int32_t *info);
 
 /* BIC of every single-column deletion of one model, from ONE Cholesky factorisation of its Gram
  * (SSE_{-q} = SSE + betahat_q^2 / (A^-1)_qq): what the kill loop FR:1669-1690 asks of `gibbs` for all its

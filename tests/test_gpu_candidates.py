@@ -446,3 +446,52 @@ def test_whole_device_kill_loop_equals_single_cta_kernel(engine, monkeypatch, p)
     for knob in ('2', '0'):
         monkeypatch.setenv('FOKL_KILL_BIG_MIN_P', knob)
         assert engine.kill_loop(cols, pos, bv0, bv1, hyp, 0.3, 0.5, 2.0, 2.0, full, 0.0, 0)['bad'] != 0
+
+
+@pytest.mark.parametrize('p0,n_models,kind', [(40, 12, 'gauss'), (300, 25, 'graded'), (900, 30, 'gauss')])
+def test_nested_chains_match_one_eigensolver_per_model(engine, p0, n_models, kind):
+    """csrc/nested.cu: the spectral decomposition of a model carried to its sub-models by secular-equation steps
+    (bisection on the offset from the nearer pole, Gu / Eisenstat weights) + the intercept-only chains: the posterior
+    mean of the intercept of every nested model equals the ordinary path's (one eigensolver + chain + betas + column
+    statistics per model, same Philox streams) to 1e-10; the eigenvalues of a step equal scipy's."""
+    import torch
+    from scipy.linalg import eigh
+    rng = np.random.default_rng(p0)
+    n = 4 * p0 + 50
+    X = rng.standard_normal((n, p0)) * (1.0 + 3.0 * rng.random(p0))
+    if kind == 'graded':
+        X = X * 10.0 ** (-3 * rng.random(p0)) + 0.3 * X[:, [1]]
+    X[:, 0] = 1.0
+    y = 2.0 + X[:, 1:6] @ rng.standard_normal(5) + 0.3 * rng.standard_normal(n)
+    G, Xty = X.T @ X, X.T @ y
+    _load_gram(engine, G, Xty, n, y)
+    hyp = engine.make_hypers(4, 1, 4, 1, 1, 1, 400)
+    drop = rng.permutation(np.arange(1, p0))[:2 * n_models]
+    sets = [np.array([c for c in range(p0) if c not in set(drop[:2 * k + 1].tolist())], dtype=np.int32)
+            for k in range(n_models)]                       # one, then two more columns removed per model
+    ids = np.arange(7, 7 + n_models, dtype=np.uint64)
+    got = engine.nested_chains_launch(sets, hyp, 99, ids).finish()
+    assert got['ok'] and got['status'] == 0
+    cold = engine.evaluate(sets, hyp, rng_mode=_lib.RNG_PHILOX, seed=99, stream_ids=ids, refine_tol=None)
+    st = cold.stats.cpu().numpy()
+    want = np.array([st[3 * cold.vec_off[c] + 2 * cold.p[c]] for c in range(n_models)])
+    assert np.max(np.abs(got['mean0'] - want) / np.abs(want)) < 1e-10
+    # one step against LAPACK: eigenvalues of the compressed matrix, orthonormal rows, and Z' Q diagonalises it
+    lam, Q = eigh(G)
+    m = int(drop[0])
+    f64 = dict(dtype=torch.float64, device=engine.device)
+    lam_d, u_d = torch.from_numpy(lam).to(engine.device), torch.from_numpy(np.ascontiguousarray(Q[m, :])).to(engine.device)
+    mu, zt = torch.empty(p0 - 1, **f64), torch.empty((p0 - 1, p0), **f64)
+    work, status = torch.empty(4 * p0, **f64), torch.zeros(1, dtype=torch.int32, device=engine.device)
+    engine._ck(engine.lib.fokl_secular_step(engine.ctx, lam_d.data_ptr(), u_d.data_ptr(), p0, mu.data_ptr(), zt.data_ptr(),
+                                            p0, work.data_ptr(), status.data_ptr()))
+    keep = [c for c in range(p0) if c != m]
+    mu_ref = eigh(G[np.ix_(keep, keep)], eigvals_only=True)
+    assert int(status.item()) == 0
+    assert np.max(np.abs(mu.cpu().numpy() - mu_ref)) <= 1e-12 * mu_ref[-1]
+    Z = zt.cpu().numpy()
+    assert np.max(np.abs(Z @ Z.T - np.eye(p0 - 1))) < 1e-11
+    Qn = Z @ Q.T                                            # rows = new eigenvectors over the p0 variables
+    assert np.max(np.abs(Qn[:, m])) < 1e-11                 # no component on the removed variable
+    Qk = Qn[:, keep]
+    assert np.max(np.abs(Qk @ G[np.ix_(keep, keep)] @ Qk.T - np.diag(mu_ref))) <= 1e-10 * mu_ref[-1]

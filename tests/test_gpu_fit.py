@@ -300,3 +300,57 @@ def test_clean_on_device_equals_host_clean(phis_cubic, tmp_path):
     path = md3.save(str(tmp_path / 'dev'))
     again = FR.load(path)
     assert np.array_equal(again.inputs, mh.inputs)
+
+
+def test_build_ahead_gives_the_same_fit(phis_cubic):
+    """B200_CONFIG['prefetch'] (opt-in): the next substage's columns and the stable part of its Gram block are built on
+    a second stream while the current substage's candidate stage runs.  Every substage's block is formed by the same
+    two-part scheme whether or not it was started ahead of time, so with prefetch on the fit is identical bit for bit
+    with the chain pipeline on, off, or forced (which exercises the roll-back rebuild); against prefetch off (one Gram
+    pass, another summation order) the terms are identical and the BIC trace agrees to 1e-9."""
+    from FoKL import FoKLRoutines as FR
+    rng = np.random.default_rng(31)
+    x = rng.random((6000, 4))
+    y = np.sin(2 * np.pi * x[:, 0]) + x[:, 1] * x[:, 2] + x[:, 0] * x[:, 2] * x[:, 3] + 0.05 * rng.standard_normal(6000)
+    fits = {}
+    for prefetch in (True, False):
+        for pipeline in (True, False, 'always'):
+            FR.B200_CONFIG['prefetch'], FR.B200_CONFIG['pipeline'] = prefetch, pipeline
+            try:
+                np.random.seed(7)
+                model = FR.FoKL(phis=phis_cubic, way3=True, draws=200, burnin=200, UserWarnings=False, ConsoleOutput=False)
+                fits[(prefetch, pipeline)] = model.fit(x, y, clean=True)
+            finally:
+                FR.B200_CONFIG['prefetch'], FR.B200_CONFIG['pipeline'] = False, True
+    for prefetch in (True, False):
+        base = fits[(prefetch, False)]
+        assert base[1].shape[0] >= 3
+        for pipeline in (True, 'always'):
+            assert all(np.array_equal(u, v) for u, v in zip(fits[(prefetch, pipeline)], base)), (prefetch, pipeline)
+    on, off = fits[(True, False)], fits[(False, False)]
+    assert np.array_equal(on[1], off[1])
+    assert np.allclose(on[2], off[2], rtol=1e-9, atol=0)
+
+
+def test_nested_chains_give_the_same_fit(phis_cubic):
+    """B200_CONFIG['nested_chains']: the chains of a substage's accepted models (nested: each is its predecessor minus
+    one column) through secular-equation updates of ONE eigendecomposition (csrc/nested.cu) instead of one eigensolver
+    run per model.  The intercept means agree to ~1e-13, so every decision -- hence terms, BIC trace and the returned
+    draws (always from the ordinary path) -- is identical."""
+    from FoKL import FoKLRoutines as FR
+    rng = np.random.default_rng(41)
+    x = rng.random((4000, 6))
+    y = np.sin(2 * np.pi * x[:, 0]) + x[:, 1] * x[:, 2] + x[:, 3] * x[:, 4] * x[:, 5] + 0.05 * rng.standard_normal(4000)
+    fits, work = {}, {}
+    for nested in (True, False):
+        FR.B200_CONFIG['nested_chains'], FR.B200_CONFIG['nested_min_p'] = nested, 12     # (default: wide batches only)
+        try:
+            np.random.seed(9)
+            model = FR.FoKL(phis=phis_cubic, way3=True, draws=150, burnin=150, UserWarnings=False, ConsoleOutput=False)
+            fits[nested] = model.fit(x, y, clean=True)
+            work[nested] = dict(FR.LAST_FIT_INFO)
+        finally:
+            FR.B200_CONFIG['nested_chains'], FR.B200_CONFIG['nested_min_p'] = True, 384
+    assert work[True]['secular_steps'] > 0 and work[False]['secular_steps'] == 0
+    assert work[True]['eig_solves'] < work[False]['eig_solves']
+    assert all(np.array_equal(u, v) for u, v in zip(fits[True], fits[False]))

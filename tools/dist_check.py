@@ -21,7 +21,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--single', action='store_true')
     ap.add_argument('--cfg', default='cfg4')
-    ap.add_argument('--n', type=int, default=1_000_000)
+    ap.add_argument('--n', '--rows', dest='n', type=int, default=1_000_000)   # use --rows under torchrun (its own parser claims --n*)
     ap.add_argument('--draws', type=int, default=500)
     a = ap.parse_args()
     import torch

@@ -346,7 +346,10 @@ def test_nested_chains_give_the_same_fit(phis_cubic):
         FR.B200_CONFIG['nested_chains'], FR.B200_CONFIG['nested_min_p'] = nested, 12     # (default: wide batches only)
         try:
             np.random.seed(9)
-            model = FR.FoKL(phis=phis_cubic, way3=True, draws=150, burnin=150, UserWarnings=False, ConsoleOutput=False)
+            # thresholds that make every kill proposal depend on the intercept threshold (FR:1671), so that the chain
+            # of every accepted model matters and whole runs of nested models are evaluated
+            model = FR.FoKL(phis=phis_cubic, way3=True, draws=150, burnin=150, threshstda=0.1, threshstdb=1e6,
+                            threshav=0.2, UserWarnings=False, ConsoleOutput=False)
             fits[nested] = model.fit(x, y, clean=True)
             work[nested] = dict(FR.LAST_FIT_INFO)
         finally:

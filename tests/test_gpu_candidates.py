@@ -495,3 +495,19 @@ def test_nested_chains_match_one_eigensolver_per_model(engine, p0, n_models, kin
     assert np.max(np.abs(Qn[:, m])) < 1e-11                 # no component on the removed variable
     Qk = Qn[:, keep]
     assert np.max(np.abs(Qk @ G[np.ix_(keep, keep)] @ Qk.T - np.diag(mu_ref))) <= 1e-10 * mu_ref[-1]
+
+
+def test_nested_chains_report_equal_eigenvalues(engine):
+    """Two exactly equal eigenvalues leave no interval for a root of the secular equation: the step must say so
+    (status 1, ok False) -- the selection loop then evaluates the batch by the ordinary path."""
+    n, p0 = 1000, 12
+    G = np.diag([float(n)] + [3.0] * (p0 - 1))          # orthogonal columns of equal norm: an 11-fold eigenvalue
+    Xty = np.arange(1, p0 + 1, dtype=np.float64)
+    y = np.zeros(n)
+    y[0] = 30.0
+    _load_gram(engine, G, Xty, n, y)
+    engine.sum_y, engine.yty = 1.0, 900.0
+    hyp = engine.make_hypers(4, 1, 4, 1, 1, 1, 50)
+    sets = [np.array([c for c in range(p0) if c not in (3, 5, 7, 9)[:k + 1]], dtype=np.int32) for k in range(4)]
+    got = engine.nested_chains_launch(sets, hyp, 1, np.arange(4, dtype=np.uint64)).finish()
+    assert not got['ok'] and (got['status'] & 1)

@@ -357,3 +357,60 @@ def test_nested_chains_give_the_same_fit(phis_cubic):
     assert work[True]['secular_steps'] > 0 and work[False]['secular_steps'] == 0
     assert work[True]['eig_solves'] < work[False]['eig_solves']
     assert all(np.array_equal(u, v) for u, v in zip(fits[True], fits[False]))
+
+
+class _StopAfter(Exception):
+    pass
+
+
+def test_cfg4_shaped_fit_parity_prefix(phis_cubic):
+    """The headline workload's SHAPE -- 8 inputs, way3, cubic, 1000 + 1000 draws, substages of C = 8 / 28 / 8 / 56 / 56 /
+    8 / 168 new terms and the sett = 3 partition walk (FR:1724-1735) -- on the inputs of tests/golden/cfg4_shape.npz (a
+    run of the unmodified reference: 503 `gibbs` calls), in parity mode, call by call against the oracle's loop replayed
+    on the device's Gram bits, for the first 130 calls (into the first 168-term substage; the oracle's eigenbasis form
+    costs 0.3 s per call on the host, the literal dense form 5 s).  Then the leading BIC trace against the reference's
+    own run: the first four substages do not depend on LAPACK's eigenvector signs.  (The reference ITSELF does not
+    reproduce its later substages on this fixture from run to run -- N = 1500 rows under up to 270 columns: a last-bit
+    change of X'X flips eigenvector signs; two runs of the unmodified reference in the same container
+    part ways at call 61)"""
+    from FoKL import FoKLRoutines as FR
+    g = load_golden('cfg4_shape')
+    limit = 130
+
+    class Rec(Recorder):
+        def on_result(self, key, ev):
+            Recorder.on_result(self, key, ev)
+            if len(self.calls) >= limit:
+                raise _StopAfter()
+
+    rec = Rec()
+    with pytest.raises(_StopAfter):
+        fit_device(FR, g, phis_cubic, recorder=rec)
+    assert len(rec.calls) == limit and max(len(k) for k in rec.grams) + 1 > 200
+    calls, subs = [], []
+
+    def hook(discmtx):
+        key = tuple(map(tuple, np.asarray(discmtx, dtype=np.int64)))
+        if key not in rec.grams:
+            raise Diverged()
+        return rec.grams[key]
+
+    def on_gibbs(d):
+        calls.append((tuple(map(tuple, np.asarray(d['discmtx'], dtype=np.int64))), float(d['ev'])))
+        if len(calls) >= limit:
+            raise _StopAfter()
+
+    np.random.seed(int(g['seed']))
+    with pytest.raises(_StopAfter):
+        fo.fit(g['inputs'], g['data'], phis_cubic, kernel=str(g['kernel']), a=float(g['a']), b=float(g['b']),
+               atau=float(g['atau']), btau=float(g['btau']), tolerance=int(g['tolerance']), burnin=int(g['burnin']),
+               draws=int(g['draws']), way3=True, aic=False, gram_hook=hook, on_gibbs=on_gibbs,
+               on_substage=lambda ind, ev: subs.append(ev), literal=False)
+    assert len(calls) == limit
+    for (kd, evd), (ko, evo) in zip(rec.calls, calls):
+        assert kd == ko and abs(evd - evo) <= 1e-9 * abs(evo)
+    # the reference's own run: substage BICs that do not depend on the draws' pairing with eigenvector signs
+    assert len(subs) >= 4
+    assert np.allclose(subs[:4], g['evs'][:4], rtol=1e-9, atol=0)
+    sizes = [len(k) + 1 for k, _ in rec.calls]
+    assert sizes[:60] == [int(v) for v in g['gram_sizes'][:60]]

@@ -435,12 +435,15 @@ def main():
 
     # DRAM traffic per launch from the committed `ncu --set full` capture of this same command (tools/ncu_traffic.py
     # over the .ncu-rep of one cfg4 fit); a number taken under the profiler is evidence, not a timing
-    traffic = {}
-    try:
-        with open(os.path.join(ROOT, 'profiles', 'r01_ncu_traffic.json')) as f:
-            traffic = json.load(f)
-    except Exception:
-        pass
+    traffic, traffic_src = {}, None
+    for name in ('r02_ncu_traffic.json', 'r01_ncu_traffic.json'):      # newest capture first (tools/gpu_final_r2.sh)
+        try:
+            with open(os.path.join(ROOT, 'profiles', name)) as f:
+                traffic = json.load(f)
+            traffic_src = 'profiles/' + name + (' @ ' + traffic['_commit'] if '_commit' in traffic else '')
+            break
+        except Exception:
+            continue
 
     def traffic_of(kernel):
         t = traffic.get(kernel)
@@ -455,7 +458,8 @@ def main():
     if b['calls']:
         ach = b['bytes'] / (b['ms'] * 1e-3) / 1e9
         roof = {'kernel': 'basis_kernel (K1)', 'bound': 'hbm', 'achieved': ach, 'peak': hbm_peak, 'unit': 'GB/s',
-                'frac': ach / hbm_peak, 'traffic': traffic_of('basis_kernel'), 'peak_source': hbm_src,
+                'frac': ach / hbm_peak, 'traffic': traffic_of('basis_kernel'), 'traffic_source': traffic_src,
+                'peak_source': hbm_src,
                 'launches': b['calls'],
                 'avg_launch_ms': b['ms'] / b['calls'], 'bytes_per_launch': b['bytes'] / b['calls'],
                 'share_of_step': shares.get('basis')}

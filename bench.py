@@ -446,10 +446,12 @@ def main():
             continue
 
     def traffic_of(kernel):
-        t = traffic.get(kernel)
-        if not t or a.workload != 'cfg4' or a.n or world != 1:
+        if a.workload != 'cfg4' or a.n or world != 1:
             return None
-        return t['traffic_bytes_per_launch']
+        parts = [v for k, v in traffic.items() if isinstance(v, dict) and k.startswith(kernel)]
+        if not parts:
+            return None
+        return sum(v['dram_read_bytes'] + v['dram_write_bytes'] for v in parts) / sum(v['launches'] for v in parts)
 
     tot_ms = ms
     shares = {k: v['ms'] / tot_ms for k, v in prof.items()}

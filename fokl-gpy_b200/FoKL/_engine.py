@@ -754,18 +754,33 @@ class Engine:
         return PendingCandidates(self, res, ev, info, col_sets, side, (G, Xty, var_t, sf_t))
 
     # ---- chains of nested models (csrc/nested.cu) ---------------------------------------------------------------------
-    def nested_chains_launch(self, col_sets, hyp, seed, stream_ids, gram=None, side=False, after=None):
+    def nested_chains_launch(self, col_sets, hyp, seed, stream_ids, gram=None, side=False, after=None, head=None):
         """Intercept statistics of the chains of NESTED models: col_sets[i + 1] is col_sets[i] minus one or more columns
         (col_sets[i][0] = the intercept column).  One eigensolver run (the first model), then one secular-equation step +
         one GEMM per removed column, then all chains in one launch.  Returns a handle; finish() -> dict(mean0 = per model
         the mean of the intercept's draws over rows stat_from0 .., ok = False if a step met equal eigenvalues or a chain
-        saw bstar < 0 -- evaluate the models with evaluate_launch then)."""
+        saw bstar < 0 -- evaluate the models with evaluate_launch then).
+        head (optional): (columns, lamb, Q) of a super-model of col_sets[0] that is already decomposed on the same Gram
+        (the substage's full model): the run starts from it instead of a cold solve of col_sets[0]."""
         torch = self.torch
         G, Xty, ldg = gram if gram is not None else (self.G, self.Xty, self.Gcap)
-        head = np.ascontiguousarray(col_sets[0], dtype=np.int32)
+        pend = None
+        if head is not None:
+            head_cols, lam0, Q0 = head
+            head_cols = np.ascontiguousarray(head_cols, dtype=np.int32)
+            if side:
+                self._side()
+                if after is not None:
+                    self.side_stream.wait_event(after)
+                else:
+                    self.side_stream.wait_stream(torch.cuda.current_stream(self.device))
+        else:
+            head_cols = np.ascontiguousarray(col_sets[0], dtype=np.int32)
+            pend = self.evaluate_launch([head_cols], hyp, rng_mode=_lib.RNG_NONE, want_eig=True, gram=(G, Xty, ldg),
+                                        side=side, after=after)
+            lam0, Q0 = pend.res.lamb, pend.res.Q
+        head = head_cols
         p0 = len(head)
-        pend = self.evaluate_launch([head], hyp, rng_mode=_lib.RNG_NONE, want_eig=True, gram=(G, Xty, ldg), side=side,
-                                    after=after)
         ctx = self._side() if side else self.ctx
         n_models = len(col_sets)
         widths = np.array([len(c) for c in col_sets], dtype=np.int32)
@@ -778,14 +793,14 @@ class Engine:
             lam_all, ct_all, q0_all = torch.empty(total, **f64), torch.empty(total, **f64), torch.empty(total, **f64)
             status = torch.zeros(1, dtype=torch.int32, device=self.device)
             xty = Xty.index_select(0, torch.as_tensor(head.astype(np.int64), device=self.device)).clone()
-            lam = pend.res.lamb
-            Qs = pend.res.Q.view(p0, p0)              # rows = eigenvectors, columns = the head model's columns
+            lam = lam0[:p0]
+            Qs = Q0[:p0 * p0].view(p0, p0)            # rows = eigenvectors, columns = the head model's columns
             work = torch.empty(4 * p0 + 8, **f64)
             t = self._tic()
             steps = 0
             prev = set(int(c) for c in head)
             for i, cols in enumerate(col_sets):
-                if i > 0:
+                if i > 0 or pend is None:
                     cur = set(int(c) for c in cols)
                     for col in sorted(prev - cur):
                         m = pos_of[col]

@@ -234,8 +234,11 @@ def forward_select(engine, hy, m, n_phis, console=True, rng='philox', eager=Fals
         if literal:
             return None
         cnt['batches'] += 1
+        # a wide full model keeps its eigendecomposition: the nested chains of its accepted sub-models start from it
+        S['keep_eig'] = bool(use_nested and len(S['full']) >= nested_min_p)
         return engine.evaluate_launch([S['full']], hyp, rng_mode=mode, run_chain=np.ones(1, dtype=np.uint8), seed=seed,
-                                      stream_ids=np.asarray([S['full_id']], dtype=np.uint64), want_betas=True)
+                                      stream_ids=np.asarray([S['full_id']], dtype=np.uint64), want_betas=True,
+                                      want_eig=S['keep_eig'])
 
     def full_finish(S, handle):
         nonlocal terms
@@ -246,6 +249,8 @@ def forward_select(engine, hy, m, n_phis, console=True, rng='philox', eager=Fals
             res = run([full], [chain_arg], [S['full_id']])
         else:
             res = handle.finish(1e-7)
+            if S.get('keep_eig') and not (int(res.info[0]) & 6):
+                S['head'] = (np.asarray(full, dtype=np.int32), res.lamb, res.Q)
         S['ev'] = float(res.ev[0]) + aic_adj * (S['terms'].shape[0] + 1)
         # a (nearly) interpolating full model: its BIC came from the residual pass because the Gram-only form has lost
         # its digits to cancellation (Engine.refine_mask) -- the device kill loop scores with the same Gram-only form,
@@ -331,6 +336,8 @@ def forward_select(engine, hy, m, n_phis, console=True, rng='philox', eager=Fals
     # sequential chain of updates (~0.15 ms per step + the head's solve): measured on cfg4 (widths <= 227)
     nested_min_models, nested_min_p = int(hy.get('nested_min_models', 4)), int(hy.get('nested_min_p', 384))
 
+    nested_head_max_steps = int(hy.get('nested_head_max_steps', 96))
+
     def nested_ok(todo, idx):
         if not use_nested or len(idx) < nested_min_models or len(todo[idx[0]]['cols']) < nested_min_p:
             return False
@@ -350,9 +357,12 @@ def forward_select(engine, hy, m, n_phis, console=True, rng='philox', eager=Fals
         nest = [i for i in which if i != last]
         if nested_ok(todo, nest):
             cnt['batches'] += 1
+            head = todo[nest[0]].get('head')
+            if head is not None and len(head[0]) - len(todo[nest[0]]['cols']) > nested_head_max_steps:
+                head = None          # too many steps from the full model to this run's first model: cold solve instead
             h = engine.nested_chains_launch([todo[i]['cols'] for i in nest], hyp, seed,
                                             np.asarray([todo[i]['stream'] for i in nest], dtype=np.uint64), gram=gram,
-                                            side=side, after=after)
+                                            side=side, after=after, head=head)
             parts.append(('nested', h, nest, gram))
             cold = [i for i in which if i == last]
         if cold:
@@ -504,6 +514,7 @@ def forward_select(engine, hy, m, n_phis, console=True, rng='philox', eager=Fals
                     cuts = np.cumsum(len(model) - 1 - np.arange(n_acc))[:-1]
                     for k_, cols_k in enumerate(np.split(flat_cols, cuts)):
                         rounds.append(dict(i=int(r['acc'][k_]), cols=cols_k, stream=state['calls'] + int(r['calls'][k_]),
+                                           head=S.get('head'),
                                            gibbs_after=state['gibbs'] + int(r['calls'][k_]),
                                            ev_dev=float(r['ev'][k_]), icpt_used=state['icpt']))
                 state['calls'] += r['tested']

@@ -12,7 +12,8 @@ Differences that are deliberate and documented:
     (so `np.random.seed` still makes `fit` reproducible).  `B200_CONFIG['rng'] = 'numpy'` (or env
     FOKL_B200_RNG=numpy) injects the legacy numpy variates in the reference's exact order instead;
   * `relats_in` with exclusions raises, as it does upstream (FR:1631 is broken);
-  * `update=True` (fitupdate, FR:1850-2583), `bss_derivatives` and `to_pyomo` are outside the hot path.
+  * `update=True` (fitupdate, FR:1850-2583) and `to_pyomo` are not built and raise (DESIGN.md section 7);
+    `bss_derivatives`, `evaluate` and `coverage3` run on the device like `fit`.
 """
 import copy
 import math

@@ -12,6 +12,8 @@ The fast path is exact: a proposal's outcome depends only on the kill set accept
 on the draws of the last accepted model (FR:1670-1690).  `forward_select` drives these phases as a software pipeline
 (the batch of C(s) next to B(s + 1)); see the comment above its driver loop.
 """
+import os
+
 import numpy as np
 
 from . import _lib
@@ -390,6 +392,9 @@ def forward_select(engine, hy, m, n_phis, console=True, rng='philox', eager=Fals
                         todo[i]['rr'], todo[i]['slot'] = None, None
                     continue
                 # equal eigenvalues met on the way (or a failed chain): the ordinary path, now
+                if os.environ.get('FOKL_B200_DEBUG'):
+                    print('nested run not ok: status', r['status'], 'models', len(idx), 'widths', len(todo[idx[0]]['cols']),
+                          '..', len(todo[idx[-1]]['cols']), 'finite', bool(np.all(np.isfinite(r['mean0']))), flush=True)
                 cnt['batches'] += 1
                 handle = engine.evaluate_launch([todo[i]['cols'] for i in idx], hyp, rng_mode=mode,
                                                 run_chain=np.ones(len(idx), dtype=np.uint8), seed=seed,

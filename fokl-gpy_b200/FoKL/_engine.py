@@ -802,6 +802,8 @@ class Engine:
             for i, cols in enumerate(col_sets):
                 if i > 0 or pend is None:
                     cur = set(int(c) for c in cols)
+                    if not cur <= prev:
+                        raise ValueError("nested_chains_launch: model %d is not a subset of its predecessor" % i)
                     for col in sorted(prev - cur):
                         m = pos_of[col]
                         p = lam.numel()

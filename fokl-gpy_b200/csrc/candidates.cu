@@ -905,7 +905,7 @@ extern "C" int fokl_candidates_eval(fokl_ctx *ctx, const double *G, int64_t ldg,
             J.set_off = meta[c].set_off; J.pad = 0;
             J.w_off = wv + wbig; J.vec_off = meta[c].vec_off; J.mat_off = meta[c].mat_off;
             meta[c].wv_off = J.w_off;                  // the not-positive-definite fallback reuses the area as W | V
-            wbig += 2 * (int64_t)J.ld * J.nb * eigb::kB;
+            wbig += 2 * (int64_t)J.ld * J.nb * eigb::kB + (((int64_t)J.p / 2 + 16) & ~(int64_t)15);   // W (+ the fallback's V) + the column order (int32)
             eigb_nb_max = std::max(eigb_nb_max, (int)J.nb);
             jobs.push_back(J);
         }
@@ -1102,6 +1102,8 @@ extern "C" int fokl_candidates_eval(fokl_ctx *ctx, const double *G, int64_t ldg,
         E.status = E.ver + (size_t)eigb_teams * vstride;
         E.max_inner = 1;
         if (const char *e = getenv("FOKL_EIGB_INNER")) E.max_inner = std::max(1, atoi(e));
+        E.sort_diag = 1;
+        if (const char *e = getenv("FOKL_EIGB_SORT")) E.sort_diag = atoi(e) != 0;
         void *args[] = {(void *)&E};
         FOKL_CUDA(ctx, cudaLaunchCooperativeKernel((const void *)eigb::eigb_kernel, dim3((unsigned)(eigb_teams * eigb_team)),
                                                    dim3(eigb::kThreads), args, eigb::kSmemBytes, ctx->stream));

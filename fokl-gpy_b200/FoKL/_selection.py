@@ -640,7 +640,8 @@ def forward_select(engine, hy, m, n_phis, console=True, rng='philox', eager=Fals
         else:
             terms_s = S['terms']
             if killed:
-                keep = [c for c in S['full'] if c not in set(killed)]
+                kset = set(killed)
+                keep = [c for c in S['full'] if c not in kset]
                 engine.compact(keep)
                 terms_s = np.delete(terms_s, [c - 1 for c in killed], axis=0)
             terms = terms_s
@@ -762,7 +763,8 @@ def forward_select(engine, hy, m, n_phis, console=True, rng='philox', eager=Fals
                 gram = engine.gram_state()
                 cnt0 = dict(cnt)
                 killed = outlook['killed']
-                keep = [c for c in S['full'] if c not in set(killed)]
+                kset = set(killed)
+                keep = [c for c in S['full'] if c not in kset]
                 engine.compact(keep)
                 S['terms_final'] = np.delete(S['terms'], [c - 1 for c in killed], axis=0)
                 terms = S['terms_final']

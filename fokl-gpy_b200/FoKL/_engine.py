@@ -797,7 +797,7 @@ class Engine:
             Qs = Q0[:p0 * p0].view(p0, p0)            # rows = eigenvectors, columns = the head model's columns
             work = torch.empty(4 * p0 + 8, **f64)
             t = self._tic()
-            steps = 0
+            steps = dead = 0
             prev = set(int(c) for c in head)
             for i, cols in enumerate(col_sets):
                 if i > 0 or pend is None:
@@ -819,11 +819,22 @@ class Engine:
                         lam = mu
                         xty[m] = 0.0                    # the removed variable: its components are zero to rounding
                         steps += 1
+                        dead += 1
+                        del pos_of[col]
+                        if dead >= 64 and dead * 8 >= Qs.shape[1]:
+                            # drop the removed variables' (zero) columns so that the GEMM shrinks with the model
+                            live = sorted(pos_of.values())
+                            sel = torch.as_tensor(np.asarray(live, dtype=np.int64), device=self.device)
+                            Qs = Qs.index_select(1, sel)
+                            xty = xty.index_select(0, sel)
+                            remap = {old: new for new, old in enumerate(live)}
+                            pos_of = {c: remap[e] for c, e in pos_of.items()}
+                            dead = 0
                     prev = cur
                 o, w = int(offs[i]), int(widths[i])
                 lam_all[o:o + w].copy_(lam)
                 torch.mv(Qs, xty, out=ct_all[o:o + w])
-                q0_all[o:o + w].copy_(Qs[:, 0])
+                q0_all[o:o + w].copy_(Qs[:, pos_of[int(head[0])]])       # the intercept column
             p_dev = torch.from_numpy(widths).to(self.device)
             off_dev = torch.from_numpy(offs).to(self.device)
             sid_dev = torch.from_numpy(np.ascontiguousarray(stream_ids, dtype=np.uint64).view(np.int64)).to(self.device)

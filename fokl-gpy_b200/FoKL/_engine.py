@@ -797,44 +797,52 @@ class Engine:
             Qs = Q0[:p0 * p0].view(p0, p0)            # rows = eigenvectors, columns = the head model's columns
             work = torch.empty(4 * p0 + 8, **f64)
             t = self._tic()
-            steps = dead = 0
-            prev = set(int(c) for c in head)
+            # the deletions of the whole run are known: only the intercept's column of Q, the columns of the variables
+            # still to be removed (their rows give u) and the vector Q'X'y have to be carried from model to model
+            dels, prev = [], set(int(c) for c in head)
             for i, cols in enumerate(col_sets):
                 if i > 0 or pend is None:
                     cur = set(int(c) for c in cols)
                     if not cur <= prev:
                         raise ValueError("nested_chains_launch: model %d is not a subset of its predecessor" % i)
-                    for col in sorted(prev - cur):
-                        m = pos_of[col]
-                        p = lam.numel()
-                        u = Qs[:, m].contiguous()
-                        mu = torch.empty(p - 1, **f64)
-                        zt = torch.empty((p - 1, p), **f64)
-                        rc = self.lib.fokl_secular_step(ctx, lam.data_ptr(), u.data_ptr(), p, mu.data_ptr(), zt.data_ptr(), p,
-                                                        work.data_ptr(), status.data_ptr())
-                        if rc != 0:
-                            msg = self.lib.fokl_last_error(ctx)
-                            raise RuntimeError("libfokl_b200 error %d: %s" % (rc, msg.decode() if msg else ''))
-                        Qs = torch.matmul(zt, Qs)       # plain FP64 GEMM (cuBLAS): Q_new = Z' Q
-                        lam = mu
-                        xty[m] = 0.0                    # the removed variable: its components are zero to rounding
-                        steps += 1
-                        dead += 1
-                        del pos_of[col]
-                        if dead >= 64 and dead * 8 >= Qs.shape[1]:
-                            # drop the removed variables' (zero) columns so that the GEMM shrinks with the model
-                            live = sorted(pos_of.values())
-                            sel = torch.as_tensor(np.asarray(live, dtype=np.int64), device=self.device)
-                            Qs = Qs.index_select(1, sel)
-                            xty = xty.index_select(0, sel)
-                            remap = {old: new for new, old in enumerate(live)}
-                            pos_of = {c: remap[e] for c, e in pos_of.items()}
-                            dead = 0
+                    dels.append([pos_of[c] for c in sorted(prev - cur)])
                     prev = cur
+                else:
+                    dels.append([])
+            order = [m for d in dels for m in d]
+            need = torch.as_tensor(np.asarray([pos_of[int(head[0])]] + order, dtype=np.int64), device=self.device)
+            R = Qs.index_select(1, need).contiguous()            # p x (1 + remaining deletions)
+            ct = torch.mv(Qs, xty)
+            steps = used = 0
+            col_of = {m: 1 + j for j, m in enumerate(order)}     # column of R holding variable m
+            for i in range(n_models):
+                for m in dels[i]:
+                    p = lam.numel()
+                    u = R[:, col_of[m]].contiguous()
+                    mu = torch.empty(p - 1, **f64)
+                    zt = torch.empty((p - 1, p), **f64)
+                    rc = self.lib.fokl_secular_step(ctx, lam.data_ptr(), u.data_ptr(), p, mu.data_ptr(), zt.data_ptr(), p,
+                                                    work.data_ptr(), status.data_ptr())
+                    if rc != 0:
+                        msg = self.lib.fokl_last_error(ctx)
+                        raise RuntimeError("libfokl_b200 error %d: %s" % (rc, msg.decode() if msg else ''))
+                    # Q_new = Z' Q on the carried columns (plain FP64 GEMM, cuBLAS) and Q_new' X'y = Z' (Q'X'y - (X'y)_m u):
+                    # the new eigenvectors have no component on the removed variable
+                    ct = torch.mv(zt, ct - xty[m] * u)
+                    R = torch.matmul(zt, R)
+                    lam = mu
+                    steps += 1
+                    used += 1
+                    if used >= 64 and used * 4 >= R.shape[1]:
+                        # drop the columns of the variables already removed: the GEMM shrinks with the work left
+                        keep = [0] + [col_of[mm] for mm in order[steps:]]
+                        R = R.index_select(1, torch.as_tensor(np.asarray(keep, dtype=np.int64), device=self.device))
+                        col_of = {mm: 1 + j for j, mm in enumerate(order[steps:])}
+                        used = 0
                 o, w = int(offs[i]), int(widths[i])
                 lam_all[o:o + w].copy_(lam)
-                torch.mv(Qs, xty, out=ct_all[o:o + w])
-                q0_all[o:o + w].copy_(Qs[:, pos_of[int(head[0])]])       # the intercept column
+                ct_all[o:o + w].copy_(ct)
+                q0_all[o:o + w].copy_(R[:, 0])
             p_dev = torch.from_numpy(widths).to(self.device)
             off_dev = torch.from_numpy(offs).to(self.device)
             sid_dev = torch.from_numpy(np.ascontiguousarray(stream_ids, dtype=np.uint64).view(np.int64)).to(self.device)

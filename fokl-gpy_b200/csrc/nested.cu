@@ -13,9 +13,9 @@
 //   its eigenvectors, in the old eigenbasis, z_i ~ (diag(lam) - mu_i)^-1 u, so Q_new = Q Z with row m dropped.
 //
 // fokl_secular_step does one such step in three kernels:
-//   (1) roots: one warp per root; bisection on the IEEE bit pattern of the offset delta from the nearer pole (the
-//       offset, not mu itself, is the unknown: lam_j - mu_i is then accurate to a few ulp however close root and pole
-//       are); 62 halvings reach the last bit whatever the magnitude of the offset;
+//   (1) roots: one warp per root; the unknown is the offset delta from the nearer pole, not mu itself (lam_j - mu_i is
+//       then accurate to a few ulp however close root and pole are).  Bisection on the IEEE bit pattern of |delta|
+//       (26 halvings settle the exponent and 15 bits whatever the magnitude), then safeguarded Newton steps;
 //   (2) Gu / Eisenstat weights: uhat_j^2 = prod_i (mu_i - lam_j) / prod_{l != j} (lam_l - lam_j) -- the vector for which
 //       the computed roots are the EXACT roots; eigenvectors built from uhat are orthogonal to working precision
 //       (built from u they are not when roots crowd a pole);
@@ -28,6 +28,8 @@
 #include "fokl_ctx.cuh"
 #include "cand_math.cuh"
 #include <math.h>
+#include <stdlib.h>
+#include <algorithm>
 #include <string.h>
 #include <vector>
 
@@ -60,7 +62,7 @@ __device__ __forceinline__ double secular_f(const double *lam, const double *u2,
 // status bits: 1 = two equal eigenvalues (no interval for a root), 2 = non-finite input
 __global__ void __launch_bounds__(kSecThreads) secular_roots_kernel(const double *__restrict__ lam, const double *__restrict__ u,
                                                                     int p, double *__restrict__ u2, double *__restrict__ delta,
-                                                                    int32_t *__restrict__ anchor, int32_t *status)
+                                                                    int32_t *__restrict__ anchor, int32_t *status, int n_bisect)
 {
     // u2 is filled by the first pass of every warp's own use below?  No: a separate tiny loop keeps the kernel simple --
     // every CTA squares the whole vector into shared memory.
@@ -93,16 +95,42 @@ __global__ void __launch_bounds__(kSecThreads) secular_roots_kernel(const double
         // bisection on |delta| in (0, bound]: f is increasing in mu.  left: f(0+) = -inf, f(bound) > 0; right
         // (delta = -t): f(t = 0+) = +inf, f(t = bound) <= 0.
         const double bound = left ? half : g - half;
+        // 26 halvings of the bit pattern settle the exponent (<= 11 steps) and >= 15 leading bits of |delta|; safeguarded
+        // Newton steps on the bracket then reach the rounding floor of f quadratically (3 - 4 evaluations instead of 36
+        // more halvings; a step that leaves the bracket is replaced by its midpoint)
         unsigned long long blo = 0ull, bhi = (unsigned long long)__double_as_longlong(bound);
-        for (int it = 0; it < 64 && bhi - blo > 1ull; ++it) {
+        for (int it = 0; it < n_bisect && bhi - blo > 1ull; ++it) {
             const unsigned long long bm = blo + ((bhi - blo) >> 1);
             const double t = __longlong_as_double((long long)bm);
             const double f = secular_f(lam_s, u2_s, p, la, left ? t : -t, lane);
             const bool root_below = left ? (f > 0.0) : (f < 0.0);       // the root's |delta| is below t
             if (root_below) bhi = bm; else blo = bm;
         }
+        double tlo = __longlong_as_double((long long)blo), thi = __longlong_as_double((long long)bhi);
+        double t = thi;
+        if (bhi - blo > 1ull) {
+            t = 0.5 * (tlo + thi);
+            for (int it = 0; it < 12; ++it) {
+                const double dl = left ? t : -t;
+                double f = 0.0, fp = 0.0;
+                for (int j = lane; j < p; j += 32) {
+                    const double r = 1.0 / ((lam_s[j] - la) - dl);
+                    const double ur = u2_s[j] * r;
+                    f += ur;
+                    fp = fma(ur, r, fp);
+                }
+                f = warp_sum(f);
+                fp = warp_sum(fp);                                        // d f / d delta > 0
+                const bool root_below = left ? (f > 0.0) : (f < 0.0);
+                if (root_below) thi = t; else tlo = t;
+                double tn = left ? t - f / fp : t + f / fp;               // |delta| = t: d f / d t = +-fp
+                if (fabs(tn - t) <= 4.5e-16 * t) { t = tn < tlo ? tlo : (tn > thi ? thi : tn); break; }   // converged
+                if (!(tn >= tlo && tn <= thi)) tn = 0.5 * (tlo + thi);
+                t = tn;
+                if (!(thi > tlo)) break;
+            }
+        }
         if (lane == 0) {
-            const double t = __longlong_as_double((long long)bhi);
             delta[i] = left ? t : -t;
             anchor[i] = a;
         }
@@ -250,7 +278,10 @@ extern "C" int fokl_secular_step(fokl_ctx *ctx, const double *lam, const double 
     const size_t smem = 2 * (size_t)p * sizeof(double);
     if (smem > 48 * 1024)
         FOKL_CUDA(ctx, cudaFuncSetAttribute(secular_roots_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    secular_roots_kernel<<<grid, kSecThreads, smem, ctx->stream>>>(lam, u, p, u2, delta, anchor, status);
+    // FOKL_SECULAR_BISECT=64: pure bisection to the last bit (tools / tests)
+    int n_bisect = 26;
+    if (const char *e = getenv("FOKL_SECULAR_BISECT")) n_bisect = std::max(8, std::min(64, atoi(e)));
+    secular_roots_kernel<<<grid, kSecThreads, smem, ctx->stream>>>(lam, u, p, u2, delta, anchor, status, n_bisect);
     FOKL_LAUNCH_CHECK(ctx);
     secular_uhat_kernel<<<grid, kSecThreads, 0, ctx->stream>>>(lam, u, delta, anchor, p, uhat);
     FOKL_LAUNCH_CHECK(ctx);

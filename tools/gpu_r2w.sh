@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+( timeout 900 python -m pytest tests/test_gpu_fit.py tests/test_gpu_candidates.py -m gpu -x -q -k "nested or cfg5" 2>&1 | tail -4 ) > gpurun_out/r2w_pytest.log; cat gpurun_out/r2w_pytest.log
+( timeout 300 python tools/nested_check.py 2072 200 gauss 2>&1 | grep -v Warn ) > gpurun_out/r2w_nested.log; cat gpurun_out/r2w_nested.log
+( timeout 600 python bench.py --workload cfg5 --steps 3 --warmup 2 --no-cpu-baseline --no-e2e 2>&1 | tail -1 ) > gpurun_out/r2w_bench_cfg5.log
+echo cfg5; grep -o '"ms_per_step": [0-9.]*' gpurun_out/r2w_bench_cfg5.log | head -1; grep -o '"stage_ms_per_step": {[^}]*}' gpurun_out/r2w_bench_cfg5.log

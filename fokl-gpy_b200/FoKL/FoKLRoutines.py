@@ -42,7 +42,7 @@ B200_CONFIG = {
     # chains of the nested accepted models of a substage by secular-equation updates instead of one eigensolver run per
     # model (csrc/nested.cu); same decisions, the intercept means agree to ~1e-13
     'nested_chains': os.environ.get('FOKL_B200_NESTED', '1') not in ('0', '', 'false', 'False'),
-    'nested_min_p': int(os.environ.get('FOKL_B200_NESTED_MIN_P', '384')),     # narrower batches: one solver per model
+    'nested_min_p': int(os.environ.get('FOKL_B200_NESTED_MIN_P', '256')),     # narrower batches: one solver per model
 }
 
 _ENGINES = {}
@@ -814,7 +814,7 @@ class FoKL:
         hy = dict(a=a, b=b, atau=atau, btau=btau, tolerance=self.tolerance, total_draws=self.burnin + self.draws,
                   gimmie=self.gimmie, way3=self.way3, threshav=self.threshav, threshstda=self.threshstda,
                   threshstdb=self.threshstdb, aic=self.aic, nested_chains=B200_CONFIG.get('nested_chains', True),
-                  nested_min_p=B200_CONFIG.get('nested_min_p', 384))
+                  nested_min_p=B200_CONFIG.get('nested_min_p', 256))
         t0 = time.perf_counter()
         launches0 = eng.launch_count()
         work0 = dict(eng.work)

@@ -334,9 +334,10 @@ def forward_select(engine, hy, m, n_phis, console=True, rng='philox', eager=Fals
     # substage returns (FR:1690) -- always takes the ordinary path.
     use_nested = (mode == _lib.RNG_PHILOX and hasattr(engine, 'nested_chains_launch') and
                   bool(hy.get('nested_chains', True)))
-    # below ~400 columns a batch of cold models (cluster eigensolver, ~0.1 ms per model in a batch of 160) beats the
-    # sequential chain of updates (~0.15 ms per step + the head's solve): measured on cfg4 (widths <= 227)
-    nested_min_models, nested_min_p = int(hy.get('nested_min_models', 4)), int(hy.get('nested_min_p', 384))
+    # below ~250 columns a batch of cold models (cluster eigensolver, ~0.1 ms per model in a batch of 160) beats the
+    # sequential chain of updates (~0.1 ms per step + the head's solve): measured on cfg4 (widths <= 227: 151 ms per
+    # fit without, 188 ms with) and cfg5 (0.90 s per fit with 256 or 160, 0.95 s with 384)
+    nested_min_models, nested_min_p = int(hy.get('nested_min_models', 4)), int(hy.get('nested_min_p', 256))
 
     nested_head_max_steps = int(hy.get('nested_head_max_steps', 96))
 

@@ -353,7 +353,7 @@ def test_nested_chains_give_the_same_fit(phis_cubic):
             fits[nested] = model.fit(x, y, clean=True)
             work[nested] = dict(FR.LAST_FIT_INFO)
         finally:
-            FR.B200_CONFIG['nested_chains'], FR.B200_CONFIG['nested_min_p'] = True, 384
+            FR.B200_CONFIG['nested_chains'], FR.B200_CONFIG['nested_min_p'] = True, 256
     assert work[True]['secular_steps'] > 0 and work[False]['secular_steps'] == 0
     assert work[True]['eig_solves'] < work[False]['eig_solves']
     assert all(np.array_equal(u, v) for u, v in zip(fits[True], fits[False]))

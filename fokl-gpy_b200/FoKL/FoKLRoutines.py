@@ -12,7 +12,8 @@ Differences that are deliberate and documented:
     (so `np.random.seed` still makes `fit` reproducible).  `B200_CONFIG['rng'] = 'numpy'` (or env
     FOKL_B200_RNG=numpy) injects the legacy numpy variates in the reference's exact order instead;
   * `relats_in` with exclusions raises, as it does upstream (FR:1631 is broken);
-  * `update=True` (fitupdate, FR:1850-2583) and `to_pyomo` are not built and raise (DESIGN.md section 7);
+  * `update=True` (fitupdate, FR:1850-2583) runs on the device too (FoKL/_update.py, csrc/update.cu);
+  * `to_pyomo` is not built and raises (DESIGN.md section 7);
     `bss_derivatives`, `evaluate` and `coverage3` run on the device like `fit`.
 """
 import copy
@@ -770,9 +771,6 @@ class FoKL:
             if np.asarray(inputs).dtype != np.float64 or np.asarray(data).dtype != np.float64:
                 raise NotImplementedError("the B200 build supports clean(bit=64) datasets only (float64)")
 
-        if self.update == True:  # noqa: E712
-            raise NotImplementedError("update=True (fitupdate, reference FR:1850-2583) is outside the B200 hot path")
-
         # relats_in: only "exclude nothing" works upstream (np.zeros(a, b) at FR:1631 raises otherwise)
         relats_in = self.relats_in
         if np.logical_not(all([isinstance(index, int) for index in relats_in])):
@@ -810,6 +808,10 @@ class FoKL:
             if btau is None:
                 btau = (np.abs(data_mean) / sigmasq) * (atau + 1)
                 self.btau = btau
+
+        if self.update == True:  # noqa: E712   (FR:1365-1367)
+            self.betas, self.mtx, self.evs = self._fitupdate_device(eng, ds)
+            return self.betas, self.mtx, self.evs
 
         hy = dict(a=a, b=b, atau=atau, btau=btau, tolerance=self.tolerance, total_draws=self.burnin + self.draws,
                   gimmie=self.gimmie, way3=self.way3, threshav=self.threshav, threshstda=self.threshstda,
@@ -1013,7 +1015,37 @@ class FoKL:
         return dy
 
     def fitupdate(self, inputs, data):
-        raise NotImplementedError("fitupdate (reference FR:1850-2583) is outside the B200 hot path")
+        """Update fit (FR:1850-2583) on already-normalised `inputs` / `data`: the first call (model not `built`) selects
+        and samples a model from scratch with the evidence taken as the maximum log-likelihood over the draws; later
+        calls use the previous draws (rows `burn` .. -1) as a Gaussian prior on the old coefficients and test further
+        terms next to them.  Returns (betas, mtx, evs) with the reference's types (all burnin + draws rows of betas)."""
+        eng = _engine()
+        eng.set_phis(self.phis, self.kernel)
+        inputs, data = self._format(inputs, data)
+        ds = eng.upload(inputs, data)
+        eng.begin_fit(ds)
+        return self._fitupdate_device(eng, ds)
+
+    def _fitupdate_device(self, eng, ds):
+        from ._update import model_prior, update_select
+        # relats_in: FR:2459-2478 only handles "exclude nothing" (the same np.zeros(a, b) defect as FR:1631)
+        if len(self.relats_in) != 0:
+            raise TypeError("relats_in with excluded terms is not supported (it raises upstream as well)")
+        prior = model_prior(self.betas, self.burn) if self.built else None             # FR:1939-1948
+        hy = dict(a=self.a, b=self.b, atau=self.atau, btau=self.btau, tolerance=self.tolerance,
+                  total_draws=self.burnin + self.draws, gimmie=self.gimmie, aic=self.aic, sigsqd0=self.sigsqd0)
+        t0 = time.perf_counter()
+        launches0 = eng.launch_count()
+        out = update_select(eng, hy, ds.m, len(self.phis), prior=prior, console=self.ConsoleOutput,
+                            rng=B200_CONFIG['rng'])
+        eng.synchronize()
+        if out['built']:
+            self.built = True                                                            # FR:2565
+        LAST_FIT_INFO.clear()
+        LAST_FIT_INFO.update(n_gibbs=out['n_gibbs'], n_batches=out['n_gibbs'], seconds=time.perf_counter() - t0,
+                             launches=eng.launch_count() - launches0, n=eng.n_global, m=ds.m,
+                             terms=out['mtx'].shape[0], substages=len(out['evs']))
+        return out['betas'], out['mtx'], out['evs']
 
     def save(self, filename=None, directory=None):
         """Pickle the model to '<filename>.fokl'; returns the path (FR:1807-1846)."""

@@ -942,6 +942,33 @@ class Engine:
                             calls=oi[3 + vm:3 + vm + k].copy(), ev=h[n_i_d:n_i_d + k].copy())
         return _Pending()
 
+    # ---- update fits (FoKL/_update.py, csrc/update.cu) ---------------------------------------------------------------
+    def sym_eigh(self, A):
+        """(lam ascending, Q with eigenvectors as columns) of a symmetric positive definite p x p device matrix, by the
+        library's own eigensolver (fokl_candidates_eval without a chain, the matrix passed in place of the Gram)."""
+        torch = self.torch
+        A = A.contiguous()
+        p = int(A.shape[0])
+        hyp = self.make_hypers(1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1)
+        dummy = torch.zeros(p, dtype=torch.float64, device=self.device)
+        res = self.evaluate_launch([list(range(p))], hyp, want_eig=True, gram=(A, dummy, p)).finish(None)
+        return res.lamb[:p].clone(), res.Q[:p * p].view(p, p).t().contiguous()
+
+    def residual_sse(self, p, betahat_dev):
+        """|y - X[:, :p] betahat|^2 over all rows of all ranks (FR:2083), by an N-length pass."""
+        torch = self.torch
+        cols = self.phys_cols(list(range(int(p))))
+        out = torch.zeros(2, dtype=torch.float64, device=self.device)
+        bh = betahat_dev.contiguous()
+        self._ck(self.lib.fokl_residual_moments(self.ctx, self.X.data_ptr(), self.ld, self.ds.n, len(cols),
+                                                cols.ctypes.data, bh.data_ptr(), self.ds.y.data_ptr(), out.data_ptr()))
+        self._allreduce(out)
+        return float(out[1].item())
+
+    def update_chain(self, spec, arrays, rng_mode, seed=0, stream_id=0, variates=None):
+        from ._update import engine_update_chain
+        return engine_update_chain(self, spec, arrays, rng_mode, seed=seed, stream_id=stream_id, variates=variates)
+
     def residual_bic(self, cols, betahat_dev):
         """BIC of FR:1551-1554 from an explicit N-length residual pass over X (used when the Gram-only
         formula has lost too many digits to cancellation)."""

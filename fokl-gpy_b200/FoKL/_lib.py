@@ -11,8 +11,8 @@ CSRC = os.path.join(os.path.dirname(_HERE), 'csrc')
 SO_PATH = os.path.join(CSRC, 'libfokl_b200.so')
 if os.environ.get('FOKL_B200_LIB'):        # kernel-variant experiments (tools/): another build of the same sources
     SO_PATH = os.path.abspath(os.environ['FOKL_B200_LIB'])
-SOURCES = ['ctx.cu', 'basis.cu', 'gram.cu', 'candidates.cu', 'nested.cu']
-HEADERS = ['fokl_ctx.cuh', 'fokl_math.cuh', 'cand_math.cuh', 'gram_plan.h', 'eigbig.cuh', 'killbig.cuh']
+SOURCES = ['ctx.cu', 'basis.cu', 'gram.cu', 'candidates.cu', 'nested.cu', 'update.cu']
+HEADERS = ['fokl_ctx.cuh', 'fokl_math.cuh', 'cand_math.cuh', 'gram_plan.h', 'eigbig.cuh', 'killbig.cuh', 'update_math.cuh']
 
 ABI_VERSION = 1
 KERNEL_CUBIC, KERNEL_BERNOULLI = 0, 1
@@ -42,6 +42,14 @@ class KillParams(ctypes.Structure):
                 ('start', ctypes.c_int32), ('reserved', ctypes.c_int32)]
 
 
+class UpdateModel(ctypes.Structure):
+    """struct fokl_update_model (include/fokl_b200.h)."""
+    _fields_ = [('mode', ctypes.c_int32), ('po', ctypes.c_int32), ('pn', ctypes.c_int32), ('draws', ctypes.c_int32),
+                ('a_star', ctypes.c_double), ('atau_star', ctypes.c_double), ('b', ctypes.c_double),
+                ('btau', ctypes.c_double), ('sigsqd0', ctypes.c_double), ('yty', ctypes.c_double),
+                ('squerr', ctypes.c_double), ('n', ctypes.c_int64)]
+
+
 PROTOTYPES = {
     'fokl_abi_version': (_i32, []),
     'fokl_ctx_create': (_i32, [ctypes.POINTER(_vp), _i32, _vp]),
@@ -67,6 +75,8 @@ PROTOTYPES = {
                                     _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'fokl_secular_step': (_i32, [_vp, _vp, _vp, _i32, _vp, _vp, _i64, _vp, _vp]),
     'fokl_chain_icpt': (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(Hypers), _u64, _vp, _vp]),
+    'fokl_update_chain': (_i32, [_vp, ctypes.POINTER(UpdateModel), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32,
+                                 _u64, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'fokl_kill_scores': (_i32, [_vp, _vp, _i64, _vp, _vp, _i32, _vp, _i32, ctypes.POINTER(Hypers), _vp, _vp]),
     'fokl_kill_loop': (_i32, [_vp, _vp, _i64, _vp, _vp, _i32, _vp, _vp, _vp, _i32, ctypes.POINTER(Hypers),
                               ctypes.POINTER(KillParams), _vp, _vp]),

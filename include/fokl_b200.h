@@ -189,6 +189,36 @@ int fokl_chain_icpt(fokl_ctx *ctx, int n_models, const int32_t *p, const int64_t
                     const double *lam, const double *ct, const double *q0, const fokl_hypers *hyp, uint64_t seed,
                     double *mean0, int32_t *info);
 
+/* ---- update fits: `fitupdate` / update=True (FR:1850-2583; entered from `fit` at FR:1365-1367) -------------------------
+ * The draw loops of the three-case sampler gibbs_Xin_update (FR:2057-2430) in spectral coordinates (csrc/update_math.cuh):
+ *   mode 1 (FR:2062-2147, first fit of an update model): pn = p, po = 0; lam_n = eigenvalues of X'X, c_n = Q'X'y,
+ *          squerr = |y - X betahat|^2.  gam_n[d] = Q' betas[d].
+ *   mode 2 (FR:2150-2264, same terms as the prior model): po = p, pn = 0; with Sigma_old^-1 = L L' and
+ *          L^-1 X'X L^-T = V D V', T = L^-T V:  lam_o = D, c_o = T'X'y, m_o = T^-1 mu_old.  betas[d] = T gam_o[d].
+ *          (One generalised eigendecomposition replaces the reference's eigh + inv per draw, FR:2197-2203: same
+ *          conditional law at every draw, another square root of its covariance.)
+ *   mode 3 (FR:2267-2426, new terms): lam_o, Q_o = eigh(Xo'Xo + Sigma_old^-1) (FR:2296), lam_n, Q_n = eigh(Xn'Xn)
+ *          (FR:2312); c_o = Q_o'(Xo'y + Sigma_old^-1 mu_old), t_o = Q_o'Xo'y, m_o = Q_o'mu_old, c_n = Q_n'Xn'y,
+ *          M = Q_o'Xo'Xn Q_n (po x pn row-major), Mt = M' (pn x po row-major), K = Q_o'Xo'Xo Q_o, W = Q_o'Sigma_old^-1 Q_o
+ *          (po x po row-major).  betas[d] = [Q_o gam_o[d], Q_n gam_n[d]].
+ * All arrays dev.  rng_mode FOKL_RNG_INJECTED: variates = draws rows of [z (po), z (pn), G1, G2] in the order the
+ * reference consumes them; FOKL_RNG_PHILOX: stream `stream_id` of `seed`.  Outputs: gam_o (draws x po), gam_n
+ * (draws x pn), sigs, taus, lik (draws each; ev = (mmtx + 1) log n - 2 max(lik), FR:2143 / 2257 / 2419, host side),
+ * info (1 int): 1 if bstar < 0 was seen (FR:2128).                                                                  */
+typedef struct fokl_update_model {
+    int32_t mode, po, pn, draws;
+    double a_star, atau_star;  /* gamma shapes (FR:2086-2087 / 2176-2177 / 2327-2328)            */
+    double b, btau;            /* FR:1926-1929                                                  */
+    double sigsqd0;            /* chain start (FR:1936); tausqd starts at 1 / sigsqd0 (FR:2067) */
+    double yty, squerr;
+    int64_t n;
+} fokl_update_model;
+int fokl_update_chain(fokl_ctx *ctx, const fokl_update_model *mdl, const double *lam_o, const double *c_o,
+                      const double *t_o, const double *m_o, const double *lam_n, const double *c_n, const double *M,
+                      const double *Mt, const double *K, const double *W, int rng_mode, uint64_t seed,
+                      uint64_t stream_id, const double *variates, double *gam_o, double *gam_n, double *sigs,
+                      double *taus, double *lik, int32_t *info);
+
 /* BIC of every single-column deletion of one model, from ONE Cholesky factorisation of its Gram
  * (SSE_{-q} = SSE + betahat_q^2 / (A^-1)_qq): what the kill loop FR:1669-1690 asks of `gibbs` for all its
  * proposals at once.  cols (host, p entries, cols[0] = intercept) selects the model in G; props (host, k positions

@@ -421,12 +421,82 @@ def case_ref_pickle():
     print('ref_pickle', os.path.getsize(os.path.join(GOLD, 'ref_model.fokl')), 'bytes; terms', model.mtx.shape)
 
 
+def _update_surface(x):
+    """The example's sigmoid surface (examples/sigmoid/updateSig.py:22-24) on scattered points."""
+    return 1 / ((1 + np.exp(-5 * x[:, 0] + 2.5)) * (1 + np.exp(-5 * x[:, 1] + 2.5)))
+
+
+def run_update_case(name, kernel, m, n_batch, n_fits, draws, burnin, burn, seed, hypers, noise=0.01, gimmie=False, drift=0.0):
+    """`update=True` (FR:1365-1367 -> fitupdate FR:1850-2583) the way examples/sigmoid/updateSig.py:64-118 drives it:
+    clean with a fixed minmax, fit the first batch (case 1), then set model.data / model.inputs to the next batch and
+    fit again (cases 2 / 3).  Stores every fit's inputs and outputs."""
+    import warnings
+    FR = ref_harness.load_reference()
+    rng = np.random.default_rng(seed)
+    x = rng.random((n_batch * n_fits, m))
+    if m == 2:
+        y = _update_surface(x)
+    else:
+        y = _update_surface(x) + 0.3 * np.sin(3 * x[:, 2]) * x[:, 0]
+    batch = np.repeat(np.arange(n_fits), n_batch)
+    y = y + drift * batch * np.sin(6 * x[:, 0]) * x[:, 1]        # later batches carry structure the first fit never saw
+    y = (y + noise * rng.standard_normal(len(y)))[:, None]
+    kw = dict(UserWarnings=False, ConsoleOutput=False, draws=draws, burnin=burnin, **hypers)
+    if kernel == 0:
+        kw['phis'] = cubic_phis()
+    else:
+        kw['kernel'] = 1
+    out = dict(x=x, y=y, kernel=kernel, n_batch=n_batch, n_fits=n_fits, draws=draws, burnin=burnin, burn=burn, seed=seed,
+               gimmie=gimmie, **{k: v for k, v in hypers.items()})
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        np.random.seed(seed)
+        model = FR.FoKL(**kw)
+        model.update = True
+        model.built = False
+        model.burn = burn
+        model.gimmie = gimmie
+        import io
+        import contextlib
+        for f in range(n_fits):
+            lo, hi = f * n_batch, (f + 1) * n_batch
+            buf = io.StringIO()
+            with contextlib.redirect_stdout(buf):
+                if f == 0:
+                    model.clean(x[lo:hi], y[lo:hi], minmax=[[0, 1]] * m)
+                else:
+                    model.data = y[lo:hi]
+                    model.inputs = model.clean(x[lo:hi])
+                betas, mtx, evs = model.fit()
+            out['inputs_%d' % f] = np.asarray(model.inputs, dtype=np.float64)
+            out['betas_%d' % f] = np.asarray(betas)
+            out['mtx_%d' % f] = np.asarray(mtx, dtype=np.float64)
+            out['evs_%d' % f] = np.asarray(evs, dtype=np.float64)
+            out['built_%d' % f] = bool(model.built)
+            out['rng_digest_%d' % f] = rng_digest()
+            out['stdout_%d' % f] = buf.getvalue()
+            print(name, 'fit', f, 'betas', np.shape(betas), type(betas).__name__, 'terms', np.shape(mtx), 'evs',
+                  np.shape(evs), 'built', model.built, 'cases', buf.getvalue().count('same'), buf.getvalue().count('new'))
+    np.savez_compressed(os.path.join(GOLD, name + '.npz'), **out)
+
+
+def case_update_cubic():
+    run_update_case('update_cubic', 0, 2, 500, 3, draws=300, burnin=0, burn=100, seed=77,
+                    hypers=dict(sigsqd0=0.009, a=9, b=0.01, atau=3, btau=4000, tolerance=3), drift=0.15)
+
+
+def case_update_bernoulli():
+    run_update_case('update_bernoulli', 1, 3, 400, 3, draws=250, burnin=50, burn=120, seed=78,
+                    hypers=dict(sigsqd0=0.02, a=9, b=0.01, atau=3, btau=4000, tolerance=2, aic=True), gimmie=True)
+
+
 CASES = dict(isotherm_gp=case_isotherm_gp, isotherm_qmax=case_isotherm_qmax,
              cfg2_default=lambda: case_cfg2(False), cfg2_changed=lambda: case_cfg2(True),
              cfg1_sigmoid=case_cfg1_sigmoid, way3_bernoulli=case_way3_bernoulli,
              way3_cubic=case_way3_cubic, two_way_cubic=case_two_way_cubic, m1_cubic=case_m1,
              cfg4_shape=case_cfg4_shape, cfg5_shape=case_cfg5_shape,
-             basis_values=case_basis_values, bss_derivatives=case_bss_derivatives, evaluate=case_evaluate, clean=case_clean, constructor=case_constructor, ref_pickle=case_ref_pickle)
+             basis_values=case_basis_values, bss_derivatives=case_bss_derivatives, evaluate=case_evaluate, clean=case_clean, constructor=case_constructor, ref_pickle=case_ref_pickle,
+             update_cubic=case_update_cubic, update_bernoulli=case_update_bernoulli)
 
 if __name__ == '__main__':
     todo = sys.argv[1:] or [c for c in CASES if c not in ('cfg4_shape', 'cfg5_shape')]      # hours / minutes: on request only

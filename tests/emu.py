@@ -20,7 +20,7 @@ class EmuHypers(ctypes.Structure):
 
 
 def _newest_dep():
-    deps = [_SRC] + [os.path.join(_CSRC, f) for f in ('fokl_math.cuh', 'cand_math.cuh', 'gram_plan.h')]
+    deps = [_SRC] + [os.path.join(_CSRC, f) for f in ('fokl_math.cuh', 'cand_math.cuh', 'gram_plan.h', 'update_math.cuh')]
     return max(os.path.getmtime(d) for d in deps)
 
 
@@ -57,6 +57,8 @@ def lib():
     L.emu_philox_gammas.restype = None
     L.emu_gram_plan.argtypes = [_vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp]
     L.emu_gram_plan.restype = _i32
+    L.emu_update_chain.argtypes = [_vp] * 13 + [_u64, _u64] + [_vp] * 5
+    L.emu_update_chain.restype = _i32
     _lib = L
     return L
 
@@ -180,3 +182,29 @@ def gram_plan(A, p_old, c, cap=352, warps=16, kchunks=1, mode=1):
                              stats.ctypes.data)
     return rc, out, cover, dict(n_tiles=int(stats[0]), max_slots=int(stats[1]), blocks=int(stats[2]),
                                 max_positions_per_tile=int(stats[3]), max_ksplit=int(stats[4]))
+
+
+def update_chain(mode, po, pn, draws, astar, atau_star, b, btau, sigsqd0, yty, squerr, n, arrays, variates=None, seed=0,
+                 stream=0):
+    """csrc/update_math.cuh update_chain on one host thread.  arrays: dict with the keys of fokl_update_chain
+    (lam_o, c_o, t_o, m_o, lam_n, c_n, M, Mt, K, W; missing = not used by the mode)."""
+    mdl = np.array([mode, po, pn, draws], dtype=np.int32)
+    par = np.array([astar, atau_star, b, btau, sigsqd0, yty, squerr, n], dtype=np.float64)
+    keep = []
+
+    def ptr(k):
+        v = arrays.get(k)
+        if v is None:
+            return None
+        v = np.ascontiguousarray(v, dtype=np.float64)
+        keep.append(v)
+        return v.ctypes.data
+    var = None if variates is None else np.ascontiguousarray(variates, dtype=np.float64)
+    gam_o = np.zeros((draws, max(po, 1)))
+    gam_n = np.zeros((draws, max(pn, 1)))
+    sigs, taus, lik = np.zeros(draws), np.zeros(draws), np.zeros(draws)
+    bad = lib().emu_update_chain(mdl.ctypes.data, par.ctypes.data, ptr('lam_o'), ptr('c_o'), ptr('t_o'), ptr('m_o'),
+                                 ptr('lam_n'), ptr('c_n'), ptr('M'), ptr('Mt'), ptr('K'), ptr('W'),
+                                 None if var is None else var.ctypes.data, seed, stream, gam_o.ctypes.data,
+                                 gam_n.ctypes.data, sigs.ctypes.data, taus.ctypes.data, lik.ctypes.data)
+    return dict(gam_o=gam_o[:, :po], gam_n=gam_n[:, :pn], sigs=sigs, taus=taus, lik=lik, bad=bad)

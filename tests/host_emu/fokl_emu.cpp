@@ -8,6 +8,7 @@
 #include <cstring>
 #include <vector>
 #include "../../fokl-gpy_b200/csrc/cand_math.cuh"
+#include "../../fokl-gpy_b200/csrc/update_math.cuh"
 
 using namespace fokl;
 
@@ -208,6 +209,30 @@ void emu_philox_gammas(uint64_t seed, uint64_t stream, int draws, double shape, 
     g.k0 = (uint32_t)seed; g.k1 = (uint32_t)(seed >> 32);
     for (int d = 0; d < draws; ++d)
         out[d] = philox_gamma(g, (uint32_t)stream, (uint32_t)(stream >> 32) & 0x7fffffffu, d, 0u, shape);
+}
+
+// The update sampler (csrc/update_math.cuh) with one host thread.  mdl: [mode, po, pn, draws] ints; par: [astar,
+// atau_star, b, btau, sigsqd0, yty, squerr, n].  variates: injected table or null (Philox seed / stream).
+int emu_update_chain(const int32_t *mdl, const double *par, const double *lam_o, const double *c_o, const double *t_o,
+                     const double *m_o, const double *lam_n, const double *c_n, const double *M, const double *Mt,
+                     const double *K, const double *W, const double *variates, uint64_t seed, uint64_t stream,
+                     double *gam_o, double *gam_n, double *sigs, double *taus, double *lik)
+{
+    Team t;
+    t.tid = 0; t.nthr = 1; t.lane = 0; t.nlane = 1; t.warp = 0; t.nwarp = 1;
+    UpdModel m;
+    m.mode = mdl[0]; m.po = mdl[1]; m.pn = mdl[2]; m.draws = mdl[3];
+    m.astar = par[0]; m.atau_star = par[1]; m.b = par[2]; m.btau = par[3]; m.sigsqd0 = par[4]; m.yty = par[5];
+    m.squerr = par[6]; m.n = par[7];
+    UpdArrays A;
+    A.lam_o = lam_o; A.c_o = c_o; A.t_o = t_o; A.m_o = m_o; A.lam_n = lam_n; A.c_n = c_n; A.M = M; A.Mt = Mt; A.K = K; A.W = W;
+    UpdVariates V;
+    V.table = variates;
+    V.g.k0 = (uint32_t)seed; V.g.k1 = (uint32_t)(seed >> 32);
+    V.s_lo = (uint32_t)stream; V.s_hi = (uint32_t)(stream >> 32) & 0x7fffffffu;
+    V.w = m.po + m.pn; V.astar = m.astar; V.atau_star = m.atau_star;
+    std::vector<double> sh(update_scratch_doubles(m.po, m.pn, 1));
+    return update_chain(t, m, A, V, gam_o, gam_n, sigs, taus, lik, sh.data());
 }
 
 }  // extern "C"

@@ -156,6 +156,29 @@ class MockEngine:
             lik = -(n / 2) * np.log(siglik) - (n - 1) / 2
         return len(cols) * np.log(n) - 2 * lik
 
+    # ---- update fits (FoKL/_update.py) -------------------------------------------------------------------------------
+    def sym_eigh(self, A):
+        A = np.ascontiguousarray(A.numpy(), dtype=np.float64)
+        p = A.shape[0]
+        r = emu.candidate(A, np.zeros(p), np.arange(p, dtype=np.int32),
+                          dict(a=1.0, b=1.0, atau=1.0, btau=1.0, sigsqd0=1.0, tausqd0=1.0, yty=1.0, sum_y=0.0, n=10, draws=1))
+        self.calls.append(('sym_eigh', p))
+        return torch.from_numpy(r['lamb'].copy()), torch.from_numpy(np.ascontiguousarray(r['Q']))
+
+    def residual_sse(self, p, betahat):
+        r = self.y - self.X[:, :p] @ betahat.numpy()
+        return float(self._sum(np.array([r @ r]))[0])
+
+    def update_chain(self, spec, arrays, rng_mode, seed=0, stream_id=0, variates=None):
+        self.calls.append(('update_chain', (spec['mode'], spec['po'], spec['pn'])))
+        arr = {k: v.numpy() for k, v in arrays.items()}
+        r = emu.update_chain(spec['mode'], spec['po'], spec['pn'], spec['draws'], spec['a_star'], spec['atau_star'],
+                             spec['b'], spec['btau'], spec['sigsqd0'], spec['yty'], spec['squerr'], spec['n'], arr,
+                             variates=variates if rng_mode == _lib.RNG_INJECTED else None, seed=seed, stream=stream_id)
+        return dict(gam_o=torch.from_numpy(r['gam_o'].copy()), gam_n=torch.from_numpy(r['gam_n'].copy()),
+                    sigs=torch.from_numpy(r['sigs']), taus=torch.from_numpy(r['taus']), lik=torch.from_numpy(r['lik']),
+                    bad=r['bad'])
+
     def mark(self):
         return None
 

@@ -108,8 +108,10 @@ def test_fit_fails_loudly_without_a_gpu(phis_cubic):
 
 def test_out_of_scope_entry_points_say_so(phis_cubic):
     m = FoKLRoutines.FoKL(phis=phis_cubic, UserWarnings=False)
-    with pytest.raises(NotImplementedError):
-        m.fitupdate(None, None)
+    with pytest.raises(ImportError):
+        m.to_pyomo(None, None)
+    with pytest.raises(RuntimeError):          # fitupdate is a device path now: without a CUDA device it fails loudly
+        m.fitupdate(np.random.rand(8, 2), np.random.rand(8))
     # bss_derivatives: keyword handling mirrors FR:626-740 and fails before any device work
     m.mtx, m.minmax, m.draws = np.array([[1.0, 0.0], [1.0, 2.0]]), [[0, 1], [0, 1]], 2
     with pytest.raises(ValueError, match="does not align"):

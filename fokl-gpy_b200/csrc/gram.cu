@@ -70,6 +70,10 @@ __device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, do
 template <unsigned BIT>
 __device__ __forceinline__ void dmma_m8n8k4_if(double &c0, double &c1, double a, double b, unsigned on)
 {
+#ifdef FOKL_GRAM_MASK_BRANCH
+    if (on & BIT) dmma_m8n8k4(c0, c1, a, b);
+    return;
+#endif
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
@@ -291,7 +295,11 @@ __device__ __forceinline__ void gram_consume_tma(const GramParams &P, const Gram
         a_off[b] = (bm.a_slot + frag_r) * 16 + lane_off;
         b_off[b] = (bm.b_slot + frag_r) * 16 + lane_off;
         ph0[b] = bm.phase;
+#ifdef FOKL_GRAM_MASK_BRANCH
+        msk[b] = __reduce_or_sync(0xffffffffu, (unsigned)bm.mask);      // (a value the compiler knows to be warp-uniform)
+#else
         msk[b] = bm.mask;
+#endif
     }
     double acc[NB][4][2];
 #pragma unroll
@@ -797,6 +805,8 @@ extern "C" int fokl_gram_update_ex(fokl_ctx *ctx, const double *X, int64_t ld, i
     const bool can_tma = (y + ld == X) && (ld % 16) == 0 && tensor_map_encoder() != nullptr;
     bool use_tma = can_tma && env_kernel && !strcmp(env_kernel, "tma");
     bool use_mb = !use_tma && !(env_kernel && !strcmp(env_kernel, "cpasync"));
+    // FOKL_GRAM_WARPS = 12 / 15: force the consumer-warp count of the tensor-map kernel (tuning knob)
+    const int env_warps = getenv("FOKL_GRAM_WARPS") ? atoi(getenv("FOKL_GRAM_WARPS")) : 0;
     int warps = 15, kb = 0, stages = 0;
     fokl::GramPlan plan;
     auto smem_need_tma = [&](int slots, int kb_, int st) {
@@ -814,6 +824,15 @@ extern "C" int fokl_gram_update_ex(fokl_ctx *ctx, const double *X, int64_t ld, i
                 if (smem_need(plan.max_slots, cand_kb, st) <= smem_cap) { kb = cand_kb; stages = st; break; }
         }
         if (kb == 0 && !env_kernel) { use_mb = false; use_tma = can_tma; }       // wide tile: tensor-map ring, else cp.async
+    }
+    if (use_tma && env_warps != 15) {
+        // 12 consumer warps (three per sub-partition next to the producer) when the tiles then need no more of them:
+        // the same blocks on fewer, evenly loaded warps (C = 168 over 29 old rows: 44 blocks per tile, 14.6 -> 13.8 ms)
+        fokl::GramPlan p12 = fokl::gram_make_plan(p_old, c, cap, 12, gap, cross_only);
+        if (!p12.tiles.empty() && p12.max_slots <= cap && (p12.tiles.size() <= plan.tiles.size() || env_warps == 12)) {
+            warps = 12;
+            plan = p12;
+        }
     }
     if (use_tma) {
         // deepest slab that leaves a ring of >= 4 stages
@@ -906,9 +925,15 @@ extern "C" int fokl_gram_update_ex(fokl_ctx *ctx, const double *X, int64_t ld, i
         for (int k = 0; k < fokl::kGramBoxKinds; ++k)
             if (!encode_gram_map(&maps.m[k], y, ld, n, p + gap + 1, fokl::kGramBoxCols[k]))
                 FOKL_FAIL(ctx, FOKL_ECUDA, "gram_update: cuTensorMapEncodeTiled failed");
-        FOKL_CUDA(ctx, cudaFuncSetAttribute(gram_kernel_tma<15>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
-        gram_kernel_tma<15><<<dim3(n_tiles, nsplit), 16 * 32, smem, ctx->stream>>>(
-            P, maps, reinterpret_cast<const fokl::GramBoxMeta *>(buf + off_box));
+        if (warps == 12) {
+            FOKL_CUDA(ctx, cudaFuncSetAttribute(gram_kernel_tma<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
+            gram_kernel_tma<12><<<dim3(n_tiles, nsplit), 13 * 32, smem, ctx->stream>>>(
+                P, maps, reinterpret_cast<const fokl::GramBoxMeta *>(buf + off_box));
+        } else {
+            FOKL_CUDA(ctx, cudaFuncSetAttribute(gram_kernel_tma<15>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
+            gram_kernel_tma<15><<<dim3(n_tiles, nsplit), 16 * 32, smem, ctx->stream>>>(
+                P, maps, reinterpret_cast<const fokl::GramBoxMeta *>(buf + off_box));
+        }
     } else if (!use_mb) {
         FOKL_CUDA(ctx, cudaFuncSetAttribute(gram_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
         gram_kernel<16><<<dim3(n_tiles, nsplit), 512, smem, ctx->stream>>>(P);

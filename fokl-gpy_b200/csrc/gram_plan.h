@@ -23,7 +23,13 @@ namespace fokl {
 
 constexpr int kGramBlocksPerWarp = 4;   // 2 x 2-fragment blocks per warp (4 * 4 * 2 = 32 accumulator doubles per lane)
 constexpr int kGramMaxWarps = 16;       // warps per CTA: 16 (one CTA per SM) or 8 (two CTAs per SM)
-inline int gram_tile_blocks(int warps) { return warps * kGramBlocksPerWarp; }
+// (Measured and dropped, profiles/r02_gram_round2.txt: a fifth block for the three consumer warps that share their SM
+// sub-partition with the producer warp, dealt so that the four sub-partitions carry equal block counts -- the 40
+// accumulators leave no registers for loads in flight under the 128-register cap of a 16-warp CTA, those warps become
+// the slowest of every stage and the ring makes everybody wait for them: C = 168 launches 18.5 -> 19.8 ms.)
+inline int gram_warp_cap(int, int) { return kGramBlocksPerWarp; }
+inline int gram_tile_cap(int warps) { return warps * kGramBlocksPerWarp; }       // most blocks (work items) of a tile
+inline int gram_tile_blocks(int warps) { return warps * kGramBlocksPerWarp; }    // positions per tile (workspace stride)
 constexpr int kGramRect = 8;            // rectangles of 8 x 8 blocks = 128 x 128 outputs
 
 struct GramTileMeta {
@@ -98,16 +104,17 @@ inline GramPlacement gram_place_items(const std::vector<int> &weight, int r, int
     pc.pos.assign(n_items, -1);
     if (mode == 1) {
         // sequential deal: the items in list order (blocks with skipped fragments come first) fill warp 0's positions,
-        // then warp 1's, ...
+        // then warp 1's, ...  Cost: a skipped fragment keeps its issue slot, so a sub-partition's load is counted in
+        // items (4 slots each), not in needed fragments.
         int next = 0, max_cnt = 0;
         int sl[4] = {0, 0, 0, 0};
         for (int w = 0; w < warps; ++w) {
             int cnt = 0;
-            for (int q = w; q < n_items; q += warps) { pc.pos[next] = q; sl[w & 3] += weight[next / r]; ++next; ++cnt; }
+            for (int q = w; q < n_items; q += warps) { pc.pos[next] = q; ++sl[w & 3]; ++next; ++cnt; }
             max_cnt = std::max(max_cnt, cnt);
         }
         pc.n_pos = n_items;
-        pc.cost = std::max(100.0 * max_cnt, 16.0 * std::max(std::max(sl[0], sl[1]), std::max(sl[2], sl[3]))) / r;
+        pc.cost = std::max(100.0 * max_cnt, 64.0 * std::max(std::max(sl[0], sl[1]), std::max(sl[2], sl[3]))) / r;
         return pc;
     }
     std::vector<int> order(n_items);
@@ -127,7 +134,7 @@ inline GramPlacement gram_place_items(const std::vector<int> &weight, int r, int
         // an untouched or unpredicated warp under the even deal (spread, not packed), then to any unpredicated one.
         int best = -1, best_cls = 9;
         for (int w = 0; w < warps; ++w) {
-            if (wcnt[w] >= kGramBlocksPerWarp) continue;
+            if (wcnt[w] >= gram_warp_cap(warps, w)) continue;
             int cls;
             if (part) cls = (wmasked[w] && wcnt[w] < per) ? 0 : (wcnt[w] == 0 ? 1 : (wmasked[w] ? 2 : 3));
             else cls = (!wmasked[w] && wcnt[w] < per) ? 0 : (!wmasked[w] ? 1 : 2);
@@ -156,7 +163,7 @@ inline GramPlacement gram_place_items(const std::vector<int> &weight, int r, int
 // admissible ksplit).  Call once per plan.
 inline void gram_plan_place(GramPlan &pl, int warps, int kchunks, int mode = 0)
 {
-    const int cap = gram_tile_blocks(warps);
+    const int cap = gram_tile_cap(warps);
     std::vector<GramBlockMeta> out;
     for (GramTileMeta &tm : pl.tiles) {
         std::vector<GramBlockMeta> base;
@@ -197,21 +204,34 @@ inline void gram_plan_place(GramPlan &pl, int warps, int kchunks, int mode = 0)
 // by p_old + c + gap, while slot_arow / slot_bcol keep the logical output indices.  cross_only: only the
 // (old | y) x new fragments (the new x new part was formed by an earlier call).
 inline GramPlan gram_make_plan(int p_old, int c, int max_slots_cap, int warps = kGramMaxWarps, int gap = 0,
-                               bool cross_only = false)
+                               bool cross_only = false, int pad_mode = -1)
 {
-    const int kTileBlocks = gram_tile_blocks(warps);
+    if (pad_mode < 0) {
+        // pad_mode: an all-padding fragment row between an odd number of new fragment rows and the old ones (see
+        // below) -- whichever of the two layouts needs fewer blocks
+        if (((c + 7) / 8) % 2 == 0) return gram_make_plan(p_old, c, max_slots_cap, warps, gap, cross_only, 0);
+        GramPlan a = gram_make_plan(p_old, c, max_slots_cap, warps, gap, cross_only, 0);
+        GramPlan b = gram_make_plan(p_old, c, max_slots_cap, warps, gap, cross_only, 1);
+        return b.blocks.size() < a.blocks.size() ? b : a;
+    }
+    const int kTileBlocks = gram_tile_cap(warps);
     GramPlan pl;
     const int p = p_old + c;
     auto phys = [&](int src) { return src < 0 ? -1 : (src >= p_old ? src + gap : src); };    // y (= p) -> p + gap
     const int fb = (c + 7) / 8;                      // fragment rows/cols of the new columns
     const int fo = (p_old + 1 + 7) / 8;              // fragment rows of old columns + y
-    const int fa = fb + fo;                          // A-list length in fragments
+    // pad_mode 1: the old rows start on an even fragment row (one all-padding fragment row after an odd number of new
+    // ones), so that no 2 x 2 block straddles the new and the old part.  With an even number of old fragment rows the
+    // straddling block row costs a whole extra row of half-empty blocks (C = 168 over 59 old rows: 120 blocks instead
+    // of 110); with an odd number it pairs the last new with the first old fragment row and is the better layout.
+    const int fbp = fb + (pad_mode ? (fb & 1) : 0);
+    const int fa = fbp + fo;                         // A-list length in fragments
     auto alist_src = [&](int e) -> int {             // A-list entry -> X column (p = y, -1 = pad)
-        if (e < fb * 8) return e < c ? p_old + e : -1;
-        int o = e - fb * 8;                          // y first: [y | X_old] is one run of the engine's [y | X] buffer
+        if (e < fbp * 8) return e < c ? p_old + e : -1;
+        int o = e - fbp * 8;                         // y first: [y | X_old] is one run of the engine's [y | X] buffer
         return o == 0 ? p : (o <= p_old ? o - 1 : -1);
     };
-    auto frag_needed = [&](int i, int j) { return i >= fb || (!cross_only && i <= j); };
+    auto frag_needed = [&](int i, int j) { return i >= fbp || (i < fb && !cross_only && i <= j); };
     const int ba = (fa + 1) / 2, bb = (fb + 1) / 2;  // block rows / cols (a block = fragment pair)
     auto block_needed = [&](int ib, int jb) {
         for (int di = 0; di < 2; ++di)
@@ -302,9 +322,12 @@ inline GramPlan gram_make_plan(int p_old, int c, int max_slots_cap, int warps = 
             const int n_grp = tm.n_slots / 8;
             int g = 0;
             while (g < n_grp) {
+                if (pl.slot_src[tm.slot_off + 8 * g] < 0) { ++g; continue; }       // all-padding fragment row: never read
                 const int x0 = xcol(pl.slot_src[tm.slot_off + 8 * g]);
                 int len = 1;
-                while (g + len < n_grp && xcol(pl.slot_src[tm.slot_off + 8 * (g + len)]) == x0 + 8 * len) ++len;
+                while (g + len < n_grp && pl.slot_src[tm.slot_off + 8 * (g + len)] >= 0 &&
+                       xcol(pl.slot_src[tm.slot_off + 8 * (g + len)]) == x0 + 8 * len)
+                    ++len;
                 int done = 0;
                 while (done < len) {
                     int kind = kGramBoxKinds - 1;

@@ -261,11 +261,14 @@ extern "C" int emu_gram_plan(const double *A, int64_t n, int p_old, int c, int m
         // positions of a warp are filled from its first one (the kernel stops at the first hole)
         for (int w = 0; w < warps; ++w) {
             bool hole = false;
+            int owned = 0;
             for (int q = w; q < tm.n_blk; q += warps) {
                 const bool h = pl.blocks[tm.blk_off + q].mask == 0;
                 if (hole && !h) return -6;
                 hole = hole || h;
+                owned += h ? 0 : 1;
             }
+            if (owned > gram_warp_cap(warps, w)) return -8;
         }
         // gram_kernel: every item accumulates its own chunks; gram_reduce_kernel: the head walks the chain
         std::vector<double> part((size_t)tm.n_blk * 256, 0.0);

@@ -240,10 +240,11 @@ def test_gram_work_plan_covers_the_block_exactly_once(p_old, c, cap, warps, kchu
 
 def test_gram_k_split_fills_the_cta():
     """A narrow substage (8 new columns against 50 old ones: 4 blocks) is split over the 16-row chunks of a slab so
-    that every warp of the CTA has work; a wide one (168 new columns) is left alone."""
+    that more warps of the CTA have work (two items per block: one per SM sub-partition and block -- measured faster
+    than four, profiles/r02_gram_round2.txt); a wide one (168 new columns) is left alone."""
     A = np.random.default_rng(0).standard_normal((300, 50 + 8 + 1))
     rc, _, _, st = emu.gram_plan(A, 50, 8, 352, 16, 16)
-    assert rc == 0 and st['max_ksplit'] >= 4 and st['max_positions_per_tile'] >= 16
+    assert rc == 0 and st['max_ksplit'] >= 2 and st['max_positions_per_tile'] >= 8
     A = np.random.default_rng(0).standard_normal((40, 50 + 168 + 1))
     rc, _, _, st = emu.gram_plan(A, 50, 168, 352, 16, 4)
     assert rc == 0 and st['max_ksplit'] == 1

@@ -32,7 +32,7 @@ def main():
     X, y = full[1:], full[0]           # [y | X]: the engine's layout (tensor-map TMA kernel unless a knob says otherwise)
     block = torch.empty(((pmax + 1) * max(c for _, c in shapes) + 64,), dtype=torch.float64, device='cuda')
     variants = a.variants.split(';')
-    knobs = ('FOKL_GRAM_KERNEL', 'FOKL_GRAM_KB', 'FOKL_GRAM_STAGES', 'FOKL_GRAM_PLACE')
+    knobs = ('FOKL_GRAM_KERNEL', 'FOKL_GRAM_KB', 'FOKL_GRAM_STAGES', 'FOKL_GRAM_PLACE', 'FOKL_GRAM_WARPS')
     print('%-10s' % 'P_old,C', ' '.join('%-34s' % v[:34] for v in variants))
     for p_old, c in shapes:
         flops = 2.0 * n * (p_old * c + c * (c + 1) / 2 + c)
@@ -46,6 +46,7 @@ def main():
                     k, val = kv.split('=')
                     os.environ[k] = val
             best = 1e9
+            times = []
             err = 0.0
             try:
                 for r in range(a.reps + 1):
@@ -56,6 +57,7 @@ def main():
                     torch.cuda.synchronize()
                     if r:
                         best = min(best, e0.elapsed_time(e1))
+                        times.append(e0.elapsed_time(e1))
                 out = block[:(p_old + c + 1) * c].view(p_old + c + 1, c).clone()
                 if ref is None:
                     ref = out
@@ -64,7 +66,7 @@ def main():
                     m = torch.ones_like(out, dtype=torch.bool)
                     m[p_old:p_old + c] = torch.triu(torch.ones((c, c), dtype=torch.bool, device='cuda'))
                     err = float(((out - ref).abs() * m).max() / ref.abs().max())
-                cells.append('%7.3f ms %5.1f TF/s %.0e' % (best, flops / best / 1e9, err))
+                cells.append('%7.3f/%7.3f ms %5.1f TF/s %.0e' % (best, float(np.median(times)), flops / best / 1e9, err))
             except Exception as ex:  # noqa: BLE001
                 cells.append('ERR ' + str(ex)[:28])
         print('%-10s' % ('%d,%d' % (p_old, c)), ' '.join('%-34s' % s for s in cells), flush=True)

@@ -147,20 +147,35 @@ __device__ __forceinline__ void bulk_g2s(void *smem, const void *gmem, unsigned 
 
 // Consumer side of the mbarrier ring for a warp that owns NB work items (positions q = warp + 16 b): wait for a slab,
 // issue its DMMAs, hand the stage back.  No CTA-wide barrier: warps drift up to stages - 1 slabs apart.
-template <int WARPS, int NB, bool MASKED>
+// FLEX: 0 = every block of the warp is a full regular 2 x 2 block (four operand loads per four DMMAs); 1 = the warp's first
+// block is a loose / masked one (one operand pair per fragment, predicated DMMAs), the others are full regular blocks;
+// 2 = every block takes the loose form.  The plan (gram_plan.h) puts at most one loose block on a warp whenever the
+// tile has no more of them than busy warps, so the extra loads are spread evenly.
+template <int WARPS, int NB, int FLEX>
 __device__ __forceinline__ void gram_consume(const GramParams &P, const GramTileMeta &tm, const double *stages, size_t stage_doubles,
                                              int stride, uint64_t *full, uint64_t *empty, int nk, int lane, int warp, double *out)
 {
     constexpr int kGramWarps = WARPS;
-    int a_off[NB], b_off[NB];
-    unsigned msk[NB];
+    constexpr int NF = FLEX == 2 ? NB : (FLEX == 1 ? 1 : 0);        // blocks 0 .. NF - 1: loose form
+    constexpr int NFA = NF > 0 ? NF : 1, NR = NB - NF, NRA = NR > 0 ? NR : 1;
+    int a_off[NRA], b_off[NRA];
+    int la_off[NFA][4], lb_off[NFA][4];
+    unsigned msk[NFA];
     const int frag_r = lane >> 2, frag_k = lane & 3;
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
         const GramBlockMeta bm = P.blocks[tm.blk_off + warp + kGramWarps * b];
-        a_off[b] = (bm.a_slot + frag_r) * stride + frag_k + 16 * bm.phase;     // this item's first 16-row chunk
-        b_off[b] = (bm.b_slot + frag_r) * stride + frag_k + 16 * bm.phase;
-        msk[b] = bm.mask;
+        if (b < NF) {
+            msk[b] = bm.mask;
+#pragma unroll
+            for (int f = 0; f < 4; ++f) {
+                la_off[b][f] = (bm.la[f] + frag_r) * stride + frag_k + 16 * bm.phase;     // this item's first 16-row chunk
+                lb_off[b][f] = (bm.lb[f] + frag_r) * stride + frag_k + 16 * bm.phase;
+            }
+        } else {
+            a_off[b - NF] = (bm.a_slot + frag_r) * stride + frag_k + 16 * bm.phase;
+            b_off[b - NF] = (bm.b_slot + frag_r) * stride + frag_k + 16 * bm.phase;
+        }
     }
     double acc[NB][4][2];
 #pragma unroll
@@ -179,25 +194,28 @@ __device__ __forceinline__ void gram_consume(const GramParams &P, const GramTile
         for (int k0 = 0; k0 < P.kb; k0 += kstep) {
 #pragma unroll
             for (int kk = 0; kk < 16; kk += 4) {
-                double a0[NB], a1[NB], b0[NB], b1[NB];
+                double a0[NRA], a1[NRA], b0[NRA], b1[NRA];
 #pragma unroll
-                for (int b = 0; b < NB; ++b) {
+                for (int b = 0; b < NR; ++b) {
                     const double *pa = S + a_off[b] + k0 + kk, *pb = S + b_off[b] + k0 + kk;
                     a0[b] = pa[0]; a1[b] = pa[half]; b0[b] = pb[0]; b1[b] = pb[half];
                 }
 #pragma unroll
-                for (int b = 0; b < NB; ++b) {
-                    if (MASKED) {
-                        dmma_m8n8k4_if<1u>(acc[b][0][0], acc[b][0][1], a0[b], b0[b], msk[b]);
-                        dmma_m8n8k4_if<2u>(acc[b][1][0], acc[b][1][1], a0[b], b1[b], msk[b]);
-                        dmma_m8n8k4_if<4u>(acc[b][2][0], acc[b][2][1], a1[b], b0[b], msk[b]);
-                        dmma_m8n8k4_if<8u>(acc[b][3][0], acc[b][3][1], a1[b], b1[b], msk[b]);
-                    } else {
-                        dmma_m8n8k4(acc[b][0][0], acc[b][0][1], a0[b], b0[b]);
-                        dmma_m8n8k4(acc[b][1][0], acc[b][1][1], a0[b], b1[b]);
-                        dmma_m8n8k4(acc[b][2][0], acc[b][2][1], a1[b], b0[b]);
-                        dmma_m8n8k4(acc[b][3][0], acc[b][3][1], a1[b], b1[b]);
-                    }
+                for (int b = 0; b < NF; ++b) {
+                    double av[4], bv[4];
+#pragma unroll
+                    for (int f = 0; f < 4; ++f) { av[f] = S[la_off[b][f] + k0 + kk]; bv[f] = S[lb_off[b][f] + k0 + kk]; }
+                    dmma_m8n8k4_if<1u>(acc[b][0][0], acc[b][0][1], av[0], bv[0], msk[b]);
+                    dmma_m8n8k4_if<2u>(acc[b][1][0], acc[b][1][1], av[1], bv[1], msk[b]);
+                    dmma_m8n8k4_if<4u>(acc[b][2][0], acc[b][2][1], av[2], bv[2], msk[b]);
+                    dmma_m8n8k4_if<8u>(acc[b][3][0], acc[b][3][1], av[3], bv[3], msk[b]);
+                }
+#pragma unroll
+                for (int b = 0; b < NR; ++b) {
+                    dmma_m8n8k4(acc[NF + b][0][0], acc[NF + b][0][1], a0[b], b0[b]);
+                    dmma_m8n8k4(acc[NF + b][1][0], acc[NF + b][1][1], a0[b], b1[b]);
+                    dmma_m8n8k4(acc[NF + b][2][0], acc[NF + b][2][1], a1[b], b0[b]);
+                    dmma_m8n8k4(acc[NF + b][3][0], acc[NF + b][3][1], a1[b], b1[b]);
                 }
             }
         }
@@ -278,28 +296,35 @@ struct GramTmaMaps {
     CUtensorMap m[fokl::kGramBoxKinds];
 };
 
-template <int WARPS, int NB, bool MASKED>
+template <int WARPS, int NB, int FLEX>
 __device__ __forceinline__ void gram_consume_tma(const GramParams &P, const GramTileMeta &tm, const double *stages, size_t stage_doubles,
                                                  uint64_t *full, uint64_t *empty, int nk, int lane, int warp, double *out)
 {
     constexpr int kGramWarps = WARPS;
+    constexpr int NF = FLEX == 2 ? NB : (FLEX == 1 ? 1 : 0);        // blocks 0 .. NF - 1: loose form (see gram_consume)
+    constexpr int NFA = NF > 0 ? NF : 1, NR = NB - NF, NRA = NR > 0 ? NR : 1;
     const int frag_r = lane >> 2, frag_k = lane & 3;
     // lane constants of the swizzled address: unit = (t + 4 h) ^ r with h = frag_k >> 1; element within the unit = frag_k & 1
     const int lane_off = 8 * ((frag_k >> 1) ^ (frag_r >> 2)) + (frag_k & 1);
     const int r3 = frag_r & 3;
-    int a_off[NB], b_off[NB], ph0[NB];
-    unsigned msk[NB];
+    int a_off[NRA], b_off[NRA], ph0[NB];
+    int la_off[NFA][4], lb_off[NFA][4];
+    unsigned msk[NFA];
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
         const GramBlockMeta bm = P.blocks[tm.blk_off + warp + kGramWarps * b];
-        a_off[b] = (bm.a_slot + frag_r) * 16 + lane_off;
-        b_off[b] = (bm.b_slot + frag_r) * 16 + lane_off;
         ph0[b] = bm.phase;
-#ifdef FOKL_GRAM_MASK_BRANCH
-        msk[b] = __reduce_or_sync(0xffffffffu, (unsigned)bm.mask);      // (a value the compiler knows to be warp-uniform)
-#else
-        msk[b] = bm.mask;
-#endif
+        if (b < NF) {
+            msk[b] = bm.mask;
+#pragma unroll
+            for (int f = 0; f < 4; ++f) {
+                la_off[b][f] = (bm.la[f] + frag_r) * 16 + lane_off;
+                lb_off[b][f] = (bm.lb[f] + frag_r) * 16 + lane_off;
+            }
+        } else {
+            a_off[b - NF] = (bm.a_slot + frag_r) * 16 + lane_off;
+            b_off[b - NF] = (bm.b_slot + frag_r) * 16 + lane_off;
+        }
     }
     double acc[NB][4][2];
 #pragma unroll
@@ -320,26 +345,30 @@ __device__ __forceinline__ void gram_consume_tma(const GramParams &P, const Gram
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
                 const int toff = 2 * (t ^ r3);
-                double a0[NB], a1[NB], b0[NB], b1[NB];
+                double a0[NRA], a1[NRA], b0[NRA], b1[NRA];
 #pragma unroll
-                for (int b = 0; b < NB; ++b) {
-                    const double *base = S + (c0 + ph0[b]) * chunk_doubles + toff;
+                for (int b = 0; b < NR; ++b) {
+                    const double *base = S + (c0 + ph0[NF + b]) * chunk_doubles + toff;
                     const double *pa = base + a_off[b], *pb = base + b_off[b];
                     a0[b] = pa[0]; a1[b] = pa[half]; b0[b] = pb[0]; b1[b] = pb[half];
                 }
 #pragma unroll
-                for (int b = 0; b < NB; ++b) {
-                    if (MASKED) {
-                        dmma_m8n8k4_if<1u>(acc[b][0][0], acc[b][0][1], a0[b], b0[b], msk[b]);
-                        dmma_m8n8k4_if<2u>(acc[b][1][0], acc[b][1][1], a0[b], b1[b], msk[b]);
-                        dmma_m8n8k4_if<4u>(acc[b][2][0], acc[b][2][1], a1[b], b0[b], msk[b]);
-                        dmma_m8n8k4_if<8u>(acc[b][3][0], acc[b][3][1], a1[b], b1[b], msk[b]);
-                    } else {
-                        dmma_m8n8k4(acc[b][0][0], acc[b][0][1], a0[b], b0[b]);
-                        dmma_m8n8k4(acc[b][1][0], acc[b][1][1], a0[b], b1[b]);
-                        dmma_m8n8k4(acc[b][2][0], acc[b][2][1], a1[b], b0[b]);
-                        dmma_m8n8k4(acc[b][3][0], acc[b][3][1], a1[b], b1[b]);
-                    }
+                for (int b = 0; b < NF; ++b) {
+                    const double *base = S + (c0 + ph0[b]) * chunk_doubles + toff;
+                    double av[4], bv[4];
+#pragma unroll
+                    for (int f = 0; f < 4; ++f) { av[f] = base[la_off[b][f]]; bv[f] = base[lb_off[b][f]]; }
+                    dmma_m8n8k4_if<1u>(acc[b][0][0], acc[b][0][1], av[0], bv[0], msk[b]);
+                    dmma_m8n8k4_if<2u>(acc[b][1][0], acc[b][1][1], av[1], bv[1], msk[b]);
+                    dmma_m8n8k4_if<4u>(acc[b][2][0], acc[b][2][1], av[2], bv[2], msk[b]);
+                    dmma_m8n8k4_if<8u>(acc[b][3][0], acc[b][3][1], av[3], bv[3], msk[b]);
+                }
+#pragma unroll
+                for (int b = 0; b < NR; ++b) {
+                    dmma_m8n8k4(acc[NF + b][0][0], acc[NF + b][0][1], a0[b], b0[b]);
+                    dmma_m8n8k4(acc[NF + b][1][0], acc[NF + b][1][1], a0[b], b1[b]);
+                    dmma_m8n8k4(acc[NF + b][2][0], acc[NF + b][2][1], a1[b], b0[b]);
+                    dmma_m8n8k4(acc[NF + b][3][0], acc[NF + b][3][1], a1[b], b1[b]);
                 }
             }
         }
@@ -377,15 +406,15 @@ gram_kernel_tma(const GramParams P, const __grid_constant__ GramTmaMaps maps, co
     const int nk = n_hi > n_lo ? (int)((n_hi - n_lo + P.kb - 1) / P.kb) : 0;
 
     int nb = 0;
-    bool partial = false;
+    int flex = 0;            // 0: all blocks full and regular, 1: the first one loose / masked, 2: any
     if (warp < kGramWarps) {
         for (int b = 0; b < kGramBlocksPerWarp; ++b) {
             const int q = warp + kGramWarps * b;
             if (q >= tm.n_blk) break;
-            const unsigned mk = P.blocks[tm.blk_off + q].mask;
-            if (mk == 0u) break;
+            const GramBlockMeta bq = P.blocks[tm.blk_off + q];
+            if (bq.mask == 0u) break;
             nb = b + 1;
-            partial |= mk != 15u;
+            if (bq.loose != 0 || bq.mask != 15u) flex = b == 0 ? (flex > 1 ? flex : 1) : 2;     // see gram_consume
         }
     }
     const int active = __syncthreads_count(lane == 0 && nb > 0);   // consumer warps that own work (and release stages)
@@ -429,8 +458,9 @@ gram_kernel_tma(const GramParams P, const __grid_constant__ GramTmaMaps maps, co
     }
     double *out = P.part + ((size_t)blockIdx.y * P.n_tiles + blockIdx.x) * (size_t)(P.tile_blocks * 256);
 #define FOKL_ROWS(NB)                                                                                                  \
-    if (partial) gram_consume_tma<WARPS, NB, true>(P, tm, stages, stage_doubles, full, empty, nk, lane, warp, out);     \
-    else gram_consume_tma<WARPS, NB, false>(P, tm, stages, stage_doubles, full, empty, nk, lane, warp, out);            \
+    if (flex == 0) gram_consume_tma<WARPS, NB, 0>(P, tm, stages, stage_doubles, full, empty, nk, lane, warp, out);      \
+    else if (flex == 1) gram_consume_tma<WARPS, NB, 1>(P, tm, stages, stage_doubles, full, empty, nk, lane, warp, out); \
+    else gram_consume_tma<WARPS, NB, 2>(P, tm, stages, stage_doubles, full, empty, nk, lane, warp, out);                \
     break;
     switch (nb) {
     case 0: break;
@@ -615,15 +645,15 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) gram_kernel_mb(const Gram
 
     // work items of this warp: positions q = warp + 16 b < n_blk, filled from b = 0 (mask 0 = hole)
     int nb = 0;
-    bool partial = false;
+    int flex = 0;            // 0: all blocks full and regular, 1: the first one loose / masked, 2: any
     if (warp < kGramWarps) {
         for (int b = 0; b < kGramBlocksPerWarp; ++b) {
             const int q = warp + kGramWarps * b;
             if (q >= tm.n_blk) break;
-            const unsigned mk = P.blocks[tm.blk_off + q].mask;
-            if (mk == 0u) break;
+            const GramBlockMeta bq = P.blocks[tm.blk_off + q];
+            if (bq.mask == 0u) break;
             nb = b + 1;
-            partial |= mk != 15u;
+            if (bq.loose != 0 || bq.mask != 15u) flex = b == 0 ? (flex > 1 ? flex : 1) : 2;     // see gram_consume
         }
     }
     // runs of staged columns (at most n_slots / 2 of them fit the table: a run of one slot next to padding at worst);
@@ -666,8 +696,9 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) gram_kernel_mb(const Gram
     }
     double *out = P.part + ((size_t)blockIdx.y * P.n_tiles + blockIdx.x) * (size_t)(P.tile_blocks * 256);
 #define FOKL_ROWS(NB)                                                                                                          \
-    if (partial) gram_consume<WARPS, NB, true>(P, tm, stages, stage_doubles, stride, full, empty, nk, lane, warp, out);         \
-    else gram_consume<WARPS, NB, false>(P, tm, stages, stage_doubles, stride, full, empty, nk, lane, warp, out);                \
+    if (flex == 0) gram_consume<WARPS, NB, 0>(P, tm, stages, stage_doubles, stride, full, empty, nk, lane, warp, out);          \
+    else if (flex == 1) gram_consume<WARPS, NB, 1>(P, tm, stages, stage_doubles, stride, full, empty, nk, lane, warp, out);     \
+    else gram_consume<WARPS, NB, 2>(P, tm, stages, stage_doubles, stride, full, empty, nk, lane, warp, out);                    \
     break;
     switch (nb) {
     case 0: break;
@@ -693,8 +724,8 @@ __global__ void gram_reduce_kernel(const double *__restrict__ part, int nsplit, 
         const int q = e >> 8, f = (e >> 6) & 3, idx = e & 63;
         const GramBlockMeta bm = blocks[tm.blk_off + q];
         if (bm.phase != 0 || !(bm.mask >> f & 1u)) continue;   // not the head item of a block / fragment not computed
-        const int arow = slot_arow[tm.slot_off + bm.a_slot + 8 * (f >> 1) + (idx >> 3)];
-        const int bcol = slot_bcol[tm.slot_off + bm.b_slot + 8 * (f & 1) + (idx & 7)];
+        const int arow = slot_arow[tm.slot_off + bm.la[f] + (idx >> 3)];
+        const int bcol = slot_bcol[tm.slot_off + bm.lb[f] + (idx & 7)];
         if (arow < 0 || bcol < 0) continue;
         double s = 0.0;
         for (int qq = q; qq >= 0; qq = blocks[tm.blk_off + qq].next) {      // the block's items in phase order
@@ -825,11 +856,12 @@ extern "C" int fokl_gram_update_ex(fokl_ctx *ctx, const double *X, int64_t ld, i
         }
         if (kb == 0 && !env_kernel) { use_mb = false; use_tma = can_tma; }       // wide tile: tensor-map ring, else cp.async
     }
-    if (use_tma && env_warps != 15) {
-        // 12 consumer warps (three per sub-partition next to the producer) when the tiles then need no more of them:
-        // the same blocks on fewer, evenly loaded warps (C = 168 over 29 old rows: 44 blocks per tile, 14.6 -> 13.8 ms)
+    if (use_tma && env_warps == 12) {
+        // 12 consumer warps (three per sub-partition next to the producer): a tuning knob since the placement deals the
+        // work items evenly over the sub-partitions (gram_plan.h, mode 2) -- 15 warps are then as fast or faster on every
+        // shape of the cfg4 fit (profiles/r02_gram_round2.txt)
         fokl::GramPlan p12 = fokl::gram_make_plan(p_old, c, cap, 12, gap, cross_only);
-        if (!p12.tiles.empty() && p12.max_slots <= cap && (p12.tiles.size() <= plan.tiles.size() || env_warps == 12)) {
+        if (!p12.tiles.empty() && p12.max_slots <= cap) {
             warps = 12;
             plan = p12;
         }
@@ -846,7 +878,7 @@ extern "C" int fokl_gram_update_ex(fokl_ctx *ctx, const double *X, int64_t ld, i
     }
     if (!use_mb && !use_tma) {
         warps = 16;
-        plan = fokl::gram_make_plan(p_old, c, cap, warps, gap, cross_only);
+        plan = fokl::gram_make_plan(p_old, c, cap, warps, gap, cross_only, -1, false);    // (this kernel has no loose-block form)
         if (plan.tiles.empty() || plan.max_slots > cap) FOKL_FAIL(ctx, FOKL_ESTATE, "gram_update: empty or oversized plan");
         // deepest slab that fits (fewer CTA-wide barriers per row), giving up one ring stage for it if necessary
         kb = 0;
@@ -867,11 +899,13 @@ extern "C" int fokl_gram_update_ex(fokl_ctx *ctx, const double *X, int64_t ld, i
     const int kTileBlocks = fokl::gram_tile_blocks(warps);
     int kb_shift = 0;
     while ((2 << kb_shift) < kb) ++kb_shift;
-    // placement: 1 = sequential deal (the default: 4 - 6 % faster than the balanced deal on the wide tiles and within
-    // 2 % elsewhere, profiles/r01_gram_ksplit.txt), 0 = balanced deal
-    const int place_mode = getenv("FOKL_GRAM_PLACE") ? atoi(getenv("FOKL_GRAM_PLACE")) : 1;
+    // placement (gram_plan.h): 2 = even deal over the SM sub-partitions with at most one loose block per warp (the
+    // default), 1 = sequential deal, 0 = balanced by needed fragments
+    const int place_mode = getenv("FOKL_GRAM_PLACE") ? atoi(getenv("FOKL_GRAM_PLACE")) : 2;
     // k-split of tiles with few blocks (gram_plan.h); the cp.async kernel works whole slabs per item
-    fokl::gram_plan_place(plan, warps, (use_mb || use_tma) ? kb / 16 : 1, place_mode);
+    // FOKL_GRAM_KSPLIT: force the k-split (largest admissible power of two <= the value; tuning knob)
+    const int force_r = getenv("FOKL_GRAM_KSPLIT") ? atoi(getenv("FOKL_GRAM_KSPLIT")) : 0;
+    fokl::gram_plan_place(plan, warps, (use_mb || use_tma) ? kb / 16 : 1, place_mode, force_r);
 
     // row splits: about one resident CTA slot each
     const int64_t chunks = (n + kb - 1) / kb;

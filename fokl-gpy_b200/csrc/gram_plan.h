@@ -53,10 +53,17 @@ struct GramBoxMeta {
 
 // One work item = one 2 x 2-fragment block restricted to the 16-row chunks  phase, phase + ksplit, ...  of every slab.
 struct GramBlockMeta {
-    uint16_t a_slot, b_slot;            // first of 16 consecutive tile-local slots on the row / column side
-    uint8_t mask;                       // bit f = fragment (f >> 1, f & 1) of the block is needed
+    uint16_t a_slot, b_slot;            // regular block: first of 16 consecutive tile-local slots on the row / column side
+    uint8_t mask;                       // bit f = fragment f of the block is needed
     uint8_t phase;                      // 0 .. ksplit - 1; the phase-0 item is the head of its block's item chain
     int16_t next;                       // tile-local position of the block's next item, -1 = last
+    // Fragment f of the block = rows: slots la[f] .. la[f] + 7, columns: slots lb[f] .. lb[f] + 7.  A regular block is
+    // the 2 x 2 arrangement la[f] = a_slot + 8 (f >> 1), lb[f] = b_slot + 8 (f & 1) (four operand loads per four DMMAs).
+    // A LOOSE block (loose = 1) packs four unrelated fragments -- the needed fragments of what would otherwise be
+    // half-empty diagonal / edge blocks, whose skipped fragments would still cost their DMMA issue slots (eight operand
+    // loads per four DMMAs, but no wasted slot).
+    uint16_t la[4], lb[4];
+    uint16_t loose, pad;
 };
 
 struct GramPlan {
@@ -96,12 +103,59 @@ struct GramPlacement {
 
 inline int gram_popcount4(unsigned m) { return (int)((m & 1u) + (m >> 1 & 1u) + (m >> 2 & 1u) + (m >> 3 & 1u)); }
 
-inline GramPlacement gram_place_items(const std::vector<int> &weight, int r, int warps, int mode = 0)
+inline GramPlacement gram_place_items(const std::vector<int> &weight, int r, int warps, int mode = 0,
+                                      const std::vector<int> *flex = nullptr)
 {
     const int nb = (int)weight.size(), n_items = nb * r;
     const int per = (n_items + warps - 1) / warps;                 // items per warp when dealt evenly
     GramPlacement pc;
     pc.pos.assign(n_items, -1);
+    if (mode == 2) {
+        // even deal over the SM sub-partitions (warp w issues on sub-partition w & 3, whose tensor pipe is the shared
+        // resource): an item goes to the sub-partition with the fewest items, inside it to the warp with the fewest.
+        // Loose / masked items (flex) take the FIRST position of a warp, one per warp, so that every warp runs the
+        // one-loose-block form at most; when the tile has more of them than busy warps the items are dealt in list
+        // order (loose first) and the first warps take the all-loose form.
+        std::vector<int> cnt(warps, 0);
+        int sl[4] = {0, 0, 0, 0};
+        for (int i = 0; i < n_items; ++i) {
+            int best = -1;
+            for (int w = 0; w < warps; ++w) {
+                if (cnt[w] >= gram_warp_cap(warps, w)) continue;
+                if (best < 0) { best = w; continue; }
+                const int a = sl[w & 3], b = sl[best & 3];
+                if (a != b ? a < b : cnt[w] < cnt[best]) best = w;
+            }
+            ++cnt[best];
+            ++sl[best & 3];
+        }
+        int busy = 0, max_cnt = 0;
+        for (int w = 0; w < warps; ++w) { busy += cnt[w] > 0; max_cnt = std::max(max_cnt, cnt[w]); }
+        std::vector<int> flex_items, full_items;
+        for (int it = 0; it < n_items; ++it) ((flex && (*flex)[it / r]) ? flex_items : full_items).push_back(it);
+        std::vector<int> used(warps, 0);
+        size_t nf = 0;
+        double all_loose_penalty = 1.0;
+        if ((int)flex_items.size() <= busy) {
+            for (int w = 0; w < warps && nf < flex_items.size(); ++w)
+                if (cnt[w] > 0) { pc.pos[flex_items[nf++]] = w; used[w] = 1; }
+        } else {
+            full_items.insert(full_items.begin(), flex_items.begin(), flex_items.end());
+            // warps whose blocks all take the loose form are the slowest of every slab (twice the operand loads):
+            // 14 old + 56 new columns, 1.83 ms unsplit against 2.37 ms split in four (profiles/r02_gram_round2.txt)
+            all_loose_penalty = 1.3;
+        }
+        size_t nx = 0;
+        for (int w = 0; w < warps; ++w)
+            for (int b = used[w]; b < cnt[w]; ++b) {
+                pc.pos[full_items[nx++]] = w + warps * b;
+                pc.n_pos = std::max(pc.n_pos, w + warps * b + 1);
+            }
+        for (int w = 0; w < warps; ++w)
+            if (used[w]) pc.n_pos = std::max(pc.n_pos, w + 1);
+        pc.cost = all_loose_penalty * std::max(100.0 * max_cnt, 64.0 * std::max(std::max(sl[0], sl[1]), std::max(sl[2], sl[3]))) / r;
+        return pc;
+    }
     if (mode == 1) {
         // sequential deal: the items in list order (blocks with skipped fragments come first) fill warp 0's positions,
         // then warp 1's, ...  Cost: a skipped fragment keeps its issue slot, so a sub-partition's load is counted in
@@ -161,26 +215,32 @@ inline GramPlacement gram_place_items(const std::vector<int> &weight, int r, int
 
 // Place the blocks of every tile of a fresh plan for slabs of `kchunks` 16-row chunks (KB / 16 = the largest
 // admissible ksplit).  Call once per plan.
-inline void gram_plan_place(GramPlan &pl, int warps, int kchunks, int mode = 0)
+inline void gram_plan_place(GramPlan &pl, int warps, int kchunks, int mode = 0, int force_r = 0)
 {
     const int cap = gram_tile_cap(warps);
     std::vector<GramBlockMeta> out;
     for (GramTileMeta &tm : pl.tiles) {
         std::vector<GramBlockMeta> base;
-        std::vector<int> weight;
+        std::vector<int> weight, flex;
         for (int q = 0; q < tm.n_blk; ++q) {
             const GramBlockMeta &bm = pl.blocks[tm.blk_off + q];
-            if (bm.phase == 0 && bm.mask != 0) { base.push_back(bm); weight.push_back(gram_popcount4(bm.mask)); }
+            if (bm.phase == 0 && bm.mask != 0) {
+                base.push_back(bm);
+                weight.push_back(gram_popcount4(bm.mask));
+                flex.push_back(bm.loose != 0 || bm.mask != 15u);
+            }
         }
         const int nb = (int)base.size();
         GramPlacement best;
         int best_r = 0;
         for (int r = 1; r <= kchunks && nb * r <= cap; r *= 2) {
-            GramPlacement pc = gram_place_items(weight, r, warps, mode);
-            if (best_r == 0 || pc.cost < best.cost * 0.999) { best = pc; best_r = r; }
+            GramPlacement pc = gram_place_items(weight, r, warps, mode, &flex);
+            if (best_r == 0 || (force_r ? r <= force_r : pc.cost < best.cost * 0.999)) { best = pc; best_r = r; }
         }
         GramBlockMeta hole;
         hole.a_slot = hole.b_slot = 0; hole.mask = 0; hole.phase = 0; hole.next = -1;
+        for (int f = 0; f < 4; ++f) hole.la[f] = hole.lb[f] = 0;
+        hole.loose = 0; hole.pad = 0;
         std::vector<GramBlockMeta> placed(best.n_pos, hole);
         for (int g = 0; g < nb; ++g)
             for (int f = 0; f < best_r; ++f) {
@@ -204,15 +264,21 @@ inline void gram_plan_place(GramPlan &pl, int warps, int kchunks, int mode = 0)
 // by p_old + c + gap, while slot_arow / slot_bcol keep the logical output indices.  cross_only: only the
 // (old | y) x new fragments (the new x new part was formed by an earlier call).
 inline GramPlan gram_make_plan(int p_old, int c, int max_slots_cap, int warps = kGramMaxWarps, int gap = 0,
-                               bool cross_only = false, int pad_mode = -1)
+                               bool cross_only = false, int pad_mode = -1, bool allow_loose = true)
 {
     if (pad_mode < 0) {
         // pad_mode: an all-padding fragment row between an odd number of new fragment rows and the old ones (see
         // below) -- whichever of the two layouts needs fewer blocks
-        if (((c + 7) / 8) % 2 == 0) return gram_make_plan(p_old, c, max_slots_cap, warps, gap, cross_only, 0);
-        GramPlan a = gram_make_plan(p_old, c, max_slots_cap, warps, gap, cross_only, 0);
-        GramPlan b = gram_make_plan(p_old, c, max_slots_cap, warps, gap, cross_only, 1);
-        return b.blocks.size() < a.blocks.size() ? b : a;
+        if (((c + 7) / 8) % 2 == 0) return gram_make_plan(p_old, c, max_slots_cap, warps, gap, cross_only, 0, allow_loose);
+        GramPlan a = gram_make_plan(p_old, c, max_slots_cap, warps, gap, cross_only, 0, allow_loose);
+        GramPlan b = gram_make_plan(p_old, c, max_slots_cap, warps, gap, cross_only, 1, allow_loose);
+        auto n_loose = [](const GramPlan &pl) {
+            size_t k = 0;
+            for (const GramBlockMeta &bm : pl.blocks) k += bm.loose;
+            return k;
+        };
+        if (b.blocks.size() != a.blocks.size()) return b.blocks.size() < a.blocks.size() ? b : a;
+        return n_loose(b) < n_loose(a) ? b : a;
     }
     const int kTileBlocks = gram_tile_cap(warps);
     GramPlan pl;
@@ -249,13 +315,36 @@ inline GramPlan gram_make_plan(int p_old, int c, int max_slots_cap, int warps = 
                 for (int jb = rj; jb < std::min(rj + kGramRect, bb); ++jb)
                     if (block_needed(ib, jb)) order.push_back({ib, jb});
     const int total = (int)order.size();
-    const int n_tiles_min = (total + kTileBlocks - 1) / kTileBlocks;
-    const int target = n_tiles_min ? (total + n_tiles_min - 1) / n_tiles_min : 0;
-
+    // work items once the half-empty blocks are repacked into loose blocks (estimate for the whole block: every tile
+    // rounds its own loose fragments up to a multiple of four, so the tile count is raised until every tile fits)
+    int full_total = 0, part_frags = 0;
+    std::vector<int> order_q(order.size(), 0);      // needed fragments of every block of the walk
+    for (size_t o = 0; o < order.size(); ++o) {
+        const auto &ob = order[o];
+        int cntf = 0;
+        for (int f = 0; f < 4; ++f) {
+            int i = 2 * ob.first + (f >> 1), j = 2 * ob.second + (f & 1);
+            if (i < fa && j < fb && frag_needed(i, j)) ++cntf;
+        }
+        order_q[o] = allow_loose ? cntf : 4;         // (predicated form: a half-empty block still costs a whole item)
+        if (cntf == 4) ++full_total;
+        else part_frags += cntf;
+    }
+    long total_q = 0;
+    for (int q : order_q) total_q += q;
+    const int items_est = allow_loose ? full_total + (part_frags + 3) / 4 : total;
     std::vector<int> frag_local(fa + 1, -1);         // A-list fragment row -> tile-local fragment index
+  for (int n_tiles_try = std::max(1, (items_est + kTileBlocks - 1) / kTileBlocks);; ++n_tiles_try) {
+    pl = GramPlan();
+    // tiles of equal WORK: a tile ends where the needed fragments walked so far are nearest to its share (the blocks with
+    // skipped fragments are repacked four fragments to an item, so items ~ needed fragments / 4)
+    const double target_q = (double)total_q / n_tiles_try;
+    long cum_q = 0;
+    int tile_idx = 0;
+    bool fits = true;
     size_t pos = 0;
     while (pos < order.size()) {
-        // grow a tile: up to `target` blocks while the slot union stays under the cap
+        // grow a tile up to its share of the work while the slot union stays under the cap
         std::vector<int> used;                       // A-list fragment rows touched (as row or column operand)
         std::fill(frag_local.begin(), frag_local.end(), -1);
         auto touch_count = [&](int ib, int jb) {
@@ -270,16 +359,19 @@ inline GramPlan gram_make_plan(int p_old, int c, int max_slots_cap, int warps = 
         };
         size_t first = pos;
         int n_blk = 0;
-        while (pos < order.size() && n_blk < target) {
+        while (pos < order.size()) {
+            if (n_blk > 0 && tile_idx + 1 < n_tiles_try && cum_q + 0.5 * order_q[pos] > (tile_idx + 1) * target_q) break;
             int ib = order[pos].first, jb = order[pos].second;
             int add = touch_count(ib, jb);
             if (n_blk > 0 && ((int)used.size() + add) * 8 > max_slots_cap) break;
             int fr[4] = {2 * ib, 2 * ib + 1, 2 * jb, 2 * jb + 1};
             for (int q = 0; q < 4; ++q)
                 if (frag_local[fr[q]] < 0) { frag_local[fr[q]] = 1; used.push_back(fr[q]); }
+            cum_q += order_q[pos];
             ++pos;
             ++n_blk;
         }
+        ++tile_idx;
         std::sort(used.begin(), used.end());
         // both fragment rows of a block are always touched together, so they stay adjacent after sorting
         for (size_t u = 0; u < used.size(); ++u) frag_local[used[u]] = (int)u;
@@ -308,10 +400,55 @@ inline GramPlan gram_make_plan(int p_old, int c, int max_slots_cap, int warps = 
                 int i = 2 * order[q].first + (f >> 1), j = 2 * order[q].second + (f & 1);
                 if (i < fa && j < fb && frag_needed(i, j)) bm.mask |= (uint8_t)(1u << f);
             }
+            bm.loose = 0;
+            bm.pad = 0;
             (bm.mask == 15u ? full_blk : part_blk).push_back(bm);
         }
-        // blocks with skipped fragments first (see gram_plan_place)
-        pl.blocks.insert(pl.blocks.end(), part_blk.begin(), part_blk.end());
+        for (GramBlockMeta &bm : full_blk) {
+            for (int f = 0; f < 4; ++f) {
+                bm.la[f] = (uint16_t)(bm.a_slot + 8 * (f >> 1));
+                bm.lb[f] = (uint16_t)(bm.b_slot + 8 * (f & 1));
+            }
+            bm.loose = 0;
+            bm.pad = 0;
+        }
+        // the needed fragments of the half-empty blocks, repacked four to a loose block
+        std::vector<GramBlockMeta> loose_blk;
+        if (!allow_loose) {
+            // predicated form (the cp.async kernel): the half-empty blocks stay 2 x 2 blocks with skipped fragments
+            for (GramBlockMeta &bm : part_blk)
+                for (int f = 0; f < 4; ++f) {
+                    bm.la[f] = (uint16_t)(bm.a_slot + 8 * (f >> 1));
+                    bm.lb[f] = (uint16_t)(bm.b_slot + 8 * (f & 1));
+                }
+            loose_blk = part_blk;
+        } else {
+            std::vector<std::pair<uint16_t, uint16_t>> lf;
+            for (const GramBlockMeta &bm : part_blk)
+                for (int f = 0; f < 4; ++f)
+                    if (bm.mask >> f & 1u)
+                        lf.push_back({(uint16_t)(bm.a_slot + 8 * (f >> 1)), (uint16_t)(bm.b_slot + 8 * (f & 1))});
+            for (size_t g = 0; g < lf.size(); g += 4) {
+                GramBlockMeta bm;
+                bm.a_slot = lf[g].first;
+                bm.b_slot = lf[g].second;
+                bm.mask = 0;
+                bm.phase = 0;
+                bm.next = -1;
+                bm.loose = 1;
+                bm.pad = 0;
+                for (int f = 0; f < 4; ++f) {
+                    const bool have = g + f < lf.size();
+                    bm.la[f] = have ? lf[g + f].first : lf[g].first;
+                    bm.lb[f] = have ? lf[g + f].second : lf[g].second;
+                    if (have) bm.mask |= (uint8_t)(1u << f);
+                }
+                loose_blk.push_back(bm);
+            }
+        }
+        tm.n_blk = (int32_t)(loose_blk.size() + full_blk.size());
+        // loose blocks first: as few warps as possible run the eight-load form (see gram_plan_place)
+        pl.blocks.insert(pl.blocks.end(), loose_blk.begin(), loose_blk.end());
         pl.blocks.insert(pl.blocks.end(), full_blk.begin(), full_blk.end());
         tm.ksplit = 1;
         tm.pad = 0;
@@ -346,7 +483,10 @@ inline GramPlan gram_make_plan(int p_old, int c, int max_slots_cap, int warps = 
         tm.n_box = (int32_t)pl.boxes.size() - tm.box_off;
         pl.tiles.push_back(tm);
         pl.max_slots = std::max(pl.max_slots, (int)tm.n_slots);
+        fits = fits && tm.n_blk <= kTileBlocks;
     }
+    if (fits || n_tiles_try >= total) break;
+  }
     return pl;      // blocks still in list order, one item each: the caller runs gram_plan_place() once
 }
 

@@ -275,15 +275,19 @@ extern "C" int emu_gram_plan(const double *A, int64_t n, int p_old, int c, int m
         for (int q = 0; q < tm.n_blk; ++q) {
             const GramBlockMeta bm = pl.blocks[tm.blk_off + q];
             if (bm.mask == 0) continue;
-            if (bm.a_slot + 16 > tm.n_slots || bm.b_slot + 16 > tm.n_slots) return -2;
+            for (int f = 0; f < 4; ++f)
+                if (bm.la[f] + 8 > tm.n_slots || bm.lb[f] + 8 > tm.n_slots) return -2;
+            if (!bm.loose)
+                for (int f = 0; f < 4; ++f)
+                    if (bm.la[f] != bm.a_slot + 8 * (f >> 1) || bm.lb[f] != bm.b_slot + 8 * (f & 1)) return -9;
             if (bm.mask > 15 || bm.phase >= tm.ksplit) return -4;
             if (bm.next >= tm.n_blk || (bm.next >= 0 && pl.blocks[tm.blk_off + bm.next].phase != bm.phase + 1)) return -7;
             if ((bm.next < 0) != (bm.phase == tm.ksplit - 1)) return -7;
             for (int f = 0; f < 4; ++f)
                 for (int idx = 0; idx < 64; ++idx) {
                     if (!(bm.mask >> f & 1)) continue;
-                    const int ca = pl.slot_src[tm.slot_off + bm.a_slot + 8 * (f >> 1) + (idx >> 3)];
-                    const int cb = pl.slot_src[tm.slot_off + bm.b_slot + 8 * (f & 1) + (idx & 7)];
+                    const int ca = pl.slot_src[tm.slot_off + bm.la[f] + (idx >> 3)];
+                    const int cb = pl.slot_src[tm.slot_off + bm.lb[f] + (idx & 7)];
                     if (ca < 0 || cb < 0) continue;
                     double s = 0.0;
                     for (int64_t i = 0; i < n; ++i)
@@ -298,8 +302,8 @@ extern "C" int emu_gram_plan(const double *A, int64_t n, int p_old, int c, int m
             for (int f = 0; f < 4; ++f)
                 for (int idx = 0; idx < 64; ++idx) {
                     if (!(bm.mask >> f & 1)) continue;
-                    const int sa = tm.slot_off + bm.a_slot + 8 * (f >> 1) + (idx >> 3);
-                    const int sb = tm.slot_off + bm.b_slot + 8 * (f & 1) + (idx & 7);
+                    const int sa = tm.slot_off + bm.la[f] + (idx >> 3);
+                    const int sb = tm.slot_off + bm.lb[f] + (idx & 7);
                     const int arow = pl.slot_arow[sa], bcol = pl.slot_bcol[sb];
                     if (arow < 0 || bcol < 0) continue;
                     const int ca = pl.slot_src[sa], cb = pl.slot_src[sb];

@@ -212,7 +212,8 @@ def test_kill_loop_matches_sequential_oracle_loop(phis_cubic, aic, packed):
                          packed=packed)['bad'] == 1
 
 
-@pytest.mark.parametrize('warps,kchunks,mode', [(16, 1, 1), (15, 4, 1), (15, 16, 1), (15, 8, 0), (16, 16, 0), (8, 8, 1)])
+@pytest.mark.parametrize('warps,kchunks,mode', [(16, 1, 1), (15, 4, 1), (15, 16, 1), (15, 8, 0), (16, 16, 0), (8, 8, 1), (15, 1, 2), (12, 1, 2), (15, 16, 2),
+                                               (12, 4, 2)])
 @pytest.mark.parametrize('p_old,c,cap', [(1, 1, 352), (1, 8, 352), (9, 28, 352), (37, 56, 352), (50, 168, 352),
                                           (71, 168, 352), (3, 5, 32), (130, 40, 64), (20, 300, 128), (400, 17, 352)])
 def test_gram_work_plan_covers_the_block_exactly_once(p_old, c, cap, warps, kchunks, mode):
@@ -235,7 +236,8 @@ def test_gram_work_plan_covers_the_block_exactly_once(p_old, c, cap, warps, kchu
     assert st['max_positions_per_tile'] <= 4 * warps and st['max_slots'] <= cap and st['max_ksplit'] <= kchunks
     # balanced: no tile is much smaller than the largest unless the slot cap forced a cut
     if p_old + c + 32 <= cap:
-        assert st['n_tiles'] == -(-st['blocks'] // (4 * warps))
+        # (every tile rounds its loose fragments up to whole blocks, which can cost one tile more than the quotient)
+        assert -(-st['blocks'] // (4 * warps)) <= st['n_tiles'] <= -(-st['blocks'] // (4 * warps)) + 1
 
 
 def test_gram_k_split_fills_the_cta():

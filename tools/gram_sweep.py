@@ -32,7 +32,7 @@ def main():
     X, y = full[1:], full[0]           # [y | X]: the engine's layout (tensor-map TMA kernel unless a knob says otherwise)
     block = torch.empty(((pmax + 1) * max(c for _, c in shapes) + 64,), dtype=torch.float64, device='cuda')
     variants = a.variants.split(';')
-    knobs = ('FOKL_GRAM_KERNEL', 'FOKL_GRAM_KB', 'FOKL_GRAM_STAGES', 'FOKL_GRAM_PLACE', 'FOKL_GRAM_WARPS')
+    knobs = ('FOKL_GRAM_KERNEL', 'FOKL_GRAM_KB', 'FOKL_GRAM_STAGES', 'FOKL_GRAM_PLACE', 'FOKL_GRAM_WARPS', 'FOKL_GRAM_KSPLIT')
     print('%-10s' % 'P_old,C', ' '.join('%-34s' % v[:34] for v in variants))
     for p_old, c in shapes:
         flops = 2.0 * n * (p_old * c + c * (c + 1) / 2 + c)

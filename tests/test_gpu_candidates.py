@@ -402,6 +402,9 @@ def test_blocked_eigensolver_not_positive_definite_falls_back(engine, monkeypatc
     X[:, 45] = X[:, 2]
     y = rng.standard_normal(200)
     G = X.T @ X
+    # (an exactly duplicated column leaves a pivot of +-1 ulp, which may pass the factorisation: make the matrix
+    # indefinite beyond rounding so that the fall-back is what runs)
+    G[45, 45] *= 1.0 - 1e-6
     _load_gram(engine, G, X.T @ y, 200, y)
     hyp = engine.make_hypers(4, 1, 4, 1, 1, 1, 10)
     res = engine.evaluate([list(range(70)), list(range(40))], hyp, want_eig=True, refine_tol=None)

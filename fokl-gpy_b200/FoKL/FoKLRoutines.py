@@ -44,6 +44,9 @@ B200_CONFIG = {
     # model (csrc/nested.cu); same decisions, the intercept means agree to ~1e-13
     'nested_chains': os.environ.get('FOKL_B200_NESTED', '1') not in ('0', '', 'false', 'False'),
     'nested_min_p': int(os.environ.get('FOKL_B200_NESTED_MIN_P', '256')),     # narrower batches: one solver per model
+    # a substage's kill loop starts from the full model's eigendecomposition (tableau = -A^-1 formed by the whole
+    # device) instead of sweeping its p pivots one after the other; same decisions, BICs agree to ~1e-12
+    'kill_from_eig': os.environ.get('FOKL_B200_KILL_FROM_EIG', '1') not in ('0', '', 'false', 'False'),
 }
 
 _ENGINES = {}
@@ -816,7 +819,8 @@ class FoKL:
         hy = dict(a=a, b=b, atau=atau, btau=btau, tolerance=self.tolerance, total_draws=self.burnin + self.draws,
                   gimmie=self.gimmie, way3=self.way3, threshav=self.threshav, threshstda=self.threshstda,
                   threshstdb=self.threshstdb, aic=self.aic, nested_chains=B200_CONFIG.get('nested_chains', True),
-                  nested_min_p=B200_CONFIG.get('nested_min_p', 256))
+                  nested_min_p=B200_CONFIG.get('nested_min_p', 256),
+                  kill_from_eig=B200_CONFIG.get('kill_from_eig', True))
         t0 = time.perf_counter()
         launches0 = eng.launch_count()
         work0 = dict(eng.work)

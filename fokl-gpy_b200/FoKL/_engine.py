@@ -107,6 +107,8 @@ class PendingCandidates:
 
 
 class Engine:
+    kill_from_eig = True      # kill_loop_launch(eig=...) is available (the selection loop asks before using it)
+
     def __init__(self, device=None, group=None):
         import torch
         self.torch = torch
@@ -305,8 +307,9 @@ class Engine:
         if getattr(self, '_bounce', None) is None:
             self._bounce = [torch.empty(chunk, dtype=torch.float64).pin_memory() for _ in range(2)]
             self._bounce_pool = ThreadPoolExecutor(max_workers=max(2, min(8, (os.cpu_count() or 4) // 2)))
+            self._bounce_events = [None, None]
         pool, nthr = self._bounce_pool, self._bounce_pool._max_workers
-        events = [None, None]
+        events = self._bounce_events          # (kept across calls: the next array reuses the buffers of this one)
         for k, lo in enumerate(range(0, flat.shape[0], chunk)):
             hi = min(lo + chunk, flat.shape[0])
             b = k & 1
@@ -946,8 +949,11 @@ class Engine:
                                      aic_adj, start).finish()
 
     def kill_loop_launch(self, cols, cand_pos, bv0, bv1, hyp, threshav, threshstda, threshstdb, icpt, evmin, aic_adj,
-                         start):
-        """Enqueue fokl_kill_loop; the returned handle's finish() reads the result back (host work can go in between)."""
+                         start, eig=None):
+        """Enqueue fokl_kill_loop; the returned handle's finish() reads the result back (host work can go in between).
+        eig (optional): (lamb, Q) device tensors of the eigendecomposition of G[cols][cols] as evaluate_launch(...,
+        want_eig=True) returns them for exactly this column list -- the loop's tableau is then formed from it by the
+        whole device instead of by len(cols) sequential pivots."""
         torch = self.torch
         cols = np.ascontiguousarray(cols, dtype=np.int32)
         cand_pos = np.ascontiguousarray(cand_pos, dtype=np.int32)
@@ -955,7 +961,8 @@ class Engine:
         bv1 = np.ascontiguousarray(bv1, dtype=np.float64)
         vm = len(cand_pos)
         kp = _lib.KillParams(float(threshav), float(threshstda), float(threshstdb), float(icpt), float(evmin),
-                             float(aic_adj), int(start), 0)
+                             float(aic_adj), int(start), 0, None if eig is None else eig[0].data_ptr(),
+                             None if eig is None else eig[1].data_ptr())
         # one output buffer: [3 + 2 vm] int32 viewed in the first doubles, then vm doubles
         n_i = 3 + 2 * vm
         n_i_d = (n_i + 1) // 2

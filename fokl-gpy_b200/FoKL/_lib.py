@@ -14,7 +14,7 @@ if os.environ.get('FOKL_B200_LIB'):        # kernel-variant experiments (tools/)
 SOURCES = ['ctx.cu', 'basis.cu', 'gram.cu', 'candidates.cu', 'nested.cu', 'update.cu']
 HEADERS = ['fokl_ctx.cuh', 'fokl_math.cuh', 'cand_math.cuh', 'gram_plan.h', 'eigbig.cuh', 'killbig.cuh', 'update_math.cuh']
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 KERNEL_CUBIC, KERNEL_BERNOULLI = 0, 1
 RNG_NONE, RNG_INJECTED, RNG_PHILOX = 0, 1, 2
 ERANGE = -4
@@ -39,7 +39,8 @@ class KillParams(ctypes.Structure):
     """struct fokl_kill_params (include/fokl_b200.h)."""
     _fields_ = [('threshav', ctypes.c_double), ('threshstda', ctypes.c_double), ('threshstdb', ctypes.c_double),
                 ('icpt', ctypes.c_double), ('evmin', ctypes.c_double), ('aic_adj', ctypes.c_double),
-                ('start', ctypes.c_int32), ('reserved', ctypes.c_int32)]
+                ('start', ctypes.c_int32), ('reserved', ctypes.c_int32), ('lamb', ctypes.c_void_p),
+                ('Qt', ctypes.c_void_p)]
 
 
 class UpdateModel(ctypes.Structure):

@@ -145,6 +145,9 @@ def forward_select(engine, hy, m, n_phis, console=True, rng='philox', eager=Fals
     pipeline = False if (literal or not pipeline) else pipeline      # True, or 'always' (tests: speculate even when
     #                                                                   the stopping rule is predicted to fire)
     world = engine.world if engine.dist is not None else 1
+    # the kill loop of a substage starts from the full model's eigendecomposition (fokl_kill_params.lamb / Qt) unless
+    # switched off (tests, tools); the tests' CPU stand-in engine has no such path
+    kill_from_eig = bool(hy.get('kill_from_eig', True)) and not literal and getattr(engine, 'kill_from_eig', False)
 
     # selection state (FR:1590-1604)
     terms = np.zeros((0, m), dtype=np.int64)     # damtx: row j <-> column j + 1 of X
@@ -238,9 +241,10 @@ def forward_select(engine, hy, m, n_phis, console=True, rng='philox', eager=Fals
         cnt['batches'] += 1
         # a wide full model keeps its eigendecomposition: the nested chains of its accepted sub-models start from it
         S['keep_eig'] = bool(use_nested and len(S['full']) >= nested_min_p)
+        # ... and every full model hands it to its kill loop, whose tableau is then formed from it (Engine.kill_loop_launch)
         return engine.evaluate_launch([S['full']], hyp, rng_mode=mode, run_chain=np.ones(1, dtype=np.uint8), seed=seed,
                                       stream_ids=np.asarray([S['full_id']], dtype=np.uint64), want_betas=True,
-                                      want_eig=S['keep_eig'])
+                                      want_eig=bool(S['keep_eig'] or kill_from_eig))
 
     def full_finish(S, handle):
         nonlocal terms
@@ -253,6 +257,8 @@ def forward_select(engine, hy, m, n_phis, console=True, rng='philox', eager=Fals
             res = handle.finish(1e-7)
             if S.get('keep_eig') and not (int(res.info[0]) & 6):
                 S['head'] = (np.asarray(full, dtype=np.int32), res.lamb, res.Q)
+            if kill_from_eig and res.lamb is not None and not (int(res.info[0]) & 6):
+                S['eig'] = (res.lamb, res.Q)
         S['ev'] = float(res.ev[0]) + aic_adj * (S['terms'].shape[0] + 1)
         # a (nearly) interpolating full model: its BIC came from the residual pass because the Gram-only form has lost
         # its digits to cancellation (Engine.refine_mask) -- the device kill loop scores with the same Gram-only form,
@@ -607,6 +613,10 @@ def forward_select(engine, hy, m, n_phis, console=True, rng='philox', eager=Fals
 
     def kill_launch(S, request):
         _, model, pos, icpt_now, evmin_now, start = request
+        if S.get('eig') is not None and len(model) == len(S['full']):
+            # the loop starts from the full model, whose eigendecomposition is at hand
+            return engine.kill_loop_launch(model, pos, S['bv0'], S['bv1'], hyp, hy['threshav'], hy['threshstda'],
+                                           hy['threshstdb'], icpt_now, evmin_now, aic_adj, start, eig=S['eig'])
         return engine.kill_loop_launch(model, pos, S['bv0'], S['bv1'], hyp, hy['threshav'], hy['threshstda'],
                                        hy['threshstdb'], icpt_now, evmin_now, aic_adj, start)
 

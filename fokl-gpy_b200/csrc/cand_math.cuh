@@ -826,16 +826,21 @@ template <bool PACKED>
 FOKL_HD int kill_loop_t(const Team &t, const double *G, int64_t ldg, const double *Xty, const int *idx, int p,
                       const int *cand_pos, const double *bv0, const double *bv1, int vm, const CandConst &c,
                       const KillLoopIn &in, double *T, int *out_i, double *out_ev, int *sh /* 4 shared ints */,
-                      double *rowbuf /* p + 1 shared doubles */)
+                      double *rowbuf /* p + 1 shared doubles */, const double *T0 = nullptr, int ldt0 = 0)
 {
     const int ld = p + 1;
     const double ybar = c.sum_y / c.n;
     const int64_t row0 = (int64_t)idx[0] * ldg;
+    // T0 (optional): the tableau as it is AFTER the p forward sweeps, formed from the model's eigendecomposition by
+    // kill_tableau_kernel ((p + 1) x ldt0, symmetric; the entry behind it is 1.0 if it may be used, see there) -- the p
+    // sequential pivots, two thirds of this kernel's time on a 226-column model, are then not run.
+    const bool pre = T0 != nullptr && T0[(int64_t)ld * ldt0] > 0.5;
     for (int e = t.tid; e < ld * ld; e += t.nthr) {
         int j = e / ld, i = e - j * ld;
         if (PACKED && i < j) continue;
         double v;
-        if (i < p && j < p) v = G[(int64_t)idx[i] * ldg + idx[j]];
+        if (pre) v = T0[(int64_t)i * ldt0 + j];
+        else if (i < p && j < p) v = G[(int64_t)idx[i] * ldg + idx[j]];
         else if (i == p && j == p) v = c.yty - c.n * ybar * ybar;
         else {
             int q = i < p ? i : j;
@@ -846,7 +851,7 @@ FOKL_HD int kill_loop_t(const Team &t, const double *G, int64_t ldg, const doubl
     if (t.tid == 0) { sh[0] = 0; sh[1] = 0; sh[2] = 0; sh[3] = 0; }
     t.sync();
     int bad = 0;
-    for (int k = 0; k < p; ++k) {
+    for (int k = 0; k < p && !pre; ++k) {
         const double d = T[PACKED ? tri_index(k, k) : (int64_t)k * ld + k];
         if (!(d > 1e-11 * G[(int64_t)idx[k] * ldg + idx[k]])) { bad = 1; break; }   // not numerically positive definite
         t.sync();
@@ -907,10 +912,10 @@ FOKL_HD int kill_loop_t(const Team &t, const double *G, int64_t ldg, const doubl
 FOKL_HD int kill_loop(const Team &t, const double *G, int64_t ldg, const double *Xty, const int *idx, int p,
                       const int *cand_pos, const double *bv0, const double *bv1, int vm, const CandConst &c,
                       const KillLoopIn &in, double *T, int *out_i, double *out_ev, int *sh /* 4 shared ints */,
-                      double *rowbuf /* p + 1 shared doubles */, bool packed = false)
+                      double *rowbuf /* p + 1 shared doubles */, bool packed = false, const double *T0 = nullptr, int ldt0 = 0)
 {
-    return packed ? kill_loop_t<true>(t, G, ldg, Xty, idx, p, cand_pos, bv0, bv1, vm, c, in, T, out_i, out_ev, sh, rowbuf)
-                  : kill_loop_t<false>(t, G, ldg, Xty, idx, p, cand_pos, bv0, bv1, vm, c, in, T, out_i, out_ev, sh, rowbuf);
+    return packed ? kill_loop_t<true>(t, G, ldg, Xty, idx, p, cand_pos, bv0, bv1, vm, c, in, T, out_i, out_ev, sh, rowbuf, T0, ldt0)
+                  : kill_loop_t<false>(t, G, ldg, Xty, idx, p, cand_pos, bv0, bv1, vm, c, in, T, out_i, out_ev, sh, rowbuf, T0, ldt0);
 }
 
 }  // namespace fokl

@@ -744,6 +744,8 @@ struct KillLoopParams {
     int32_t *out_i;
     double *out_ev;
     int smem_doubles;
+    const double *T0;        // tableau after the forward sweeps (kill_tableau_kernel) or null
+    int ldt0;
 };
 
 __global__ void __launch_bounds__(kKillThreads) kill_loop_kernel(const KillLoopParams P)
@@ -756,7 +758,115 @@ __global__ void __launch_bounds__(kKillThreads) kill_loop_kernel(const KillLoopP
     const bool packed = P.smem_doubles > 0;
     double *T = packed ? (sh + 2 + ((P.p + 2) & ~1)) : P.T_global;
     fokl::kill_loop(t, P.G, P.ldg, P.Xty, P.cols, P.p, P.cand_pos, P.bv0, P.bv1, P.vm, P.c, P.in, T, P.out_i, P.out_ev,
-                    shi, rowbuf, packed);
+                    shi, rowbuf, packed, P.T0, P.ldt0);
+}
+
+// ---- the kill loop's tableau AFTER its p forward sweeps, from the model's eigendecomposition -------------------------------
+// Sweeping all p pivots of [A b; b' c] gives [-A^-1  A^-1 b; b' A^-1  c - b' A^-1 b].  When the model is the substage's
+// full model its eigendecomposition A = Q Lam Q' has just been computed (FR:1499), so the block is a plain
+// symmetric product, A^-1 = (Q Lam^-1/2)(Q Lam^-1/2)', that every SM can work on -- instead of p strictly sequential
+// rank-one updates by one CTA (or p grid barriers for a wide model).  b, c: centred like fokl::kill_loop_t.
+// Usable flag (T0[(p + 1) ldt]): 1.0 iff lam_min > 1e-10 max_k A_kk -- then every pivot of the sequential form would
+// have passed its own test (pivot >= lam_min), so both forms take the same path; otherwise the kill kernels run the
+// sequential sweeps with their own positive-definiteness test as before.
+struct KillTabParams {
+    const double *G;
+    int64_t ldg;
+    const double *Xty;
+    const int32_t *cols;
+    int p, ldt;
+    const double *lamb, *Qt;     // eigenvalues ascending; Qt[k * p + i] = component i of eigenvector k
+    double ybar, cc;             // mean of y; yty - n ybar^2
+    double *w;                   // p doubles: (Q' b)_k / lam_k
+    double *T0;                  // (p + 1) x ldt, + the flag
+};
+
+__global__ void __launch_bounds__(256) kill_w_kernel(const KillTabParams P)
+{
+    const int lane = threadIdx.x & 31, k = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (k >= P.p) return;
+    const int64_t row0 = (int64_t)P.cols[0] * P.ldg;
+    const double *q = P.Qt + (int64_t)k * P.p;
+    double s = 0.0;
+    for (int i = lane; i < P.p; i += 32) s = fma(q[i], P.Xty[P.cols[i]] - P.ybar * P.G[row0 + P.cols[i]], s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) P.w[k] = s / P.lamb[k];
+}
+
+constexpr int kTabTile = 32;
+__global__ void __launch_bounds__(256) kill_tableau_kernel(const KillTabParams P)
+{
+    __shared__ double As[kTabTile][kTabTile + 1], Bs[kTabTile][kTabTile + 1];
+    __shared__ double red[8];
+    const int p = P.p, ldt = P.ldt, tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+    const int nt = (p + kTabTile - 1) / kTabTile;
+    const int n_tiles = nt * (nt + 1) / 2;
+    if ((int)blockIdx.x == n_tiles) {
+        // last row / column: betahat = Q w; corner: c - sum w_k^2 lam_k; the usable flag
+        for (int j = tid; j < p; j += 256) {
+            double b = 0.0;
+            for (int k = 0; k < p; ++k) b = fma(P.Qt[(int64_t)k * p + j], P.w[k], b);
+            P.T0[(int64_t)p * ldt + j] = b;
+            P.T0[(int64_t)j * ldt + p] = b;
+        }
+        double s = 0.0, dmax = 0.0;
+        for (int k = tid; k < p; k += 256) {
+            s = fma(P.w[k] * P.w[k], P.lamb[k], s);
+            dmax = fmax(dmax, P.G[(int64_t)P.cols[k] * P.ldg + P.cols[k]]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            s += __shfl_xor_sync(0xffffffffu, s, o);
+            dmax = fmax(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+        }
+        __shared__ double red2[8];
+        if (tx == 0) { red[ty] = s; red2[ty] = dmax; }
+        __syncthreads();
+        if (tid == 0) {
+            double st = 0.0, dm = 0.0;
+            for (int q = 0; q < 8; ++q) { st += red[q]; dm = fmax(dm, red2[q]); }
+            const double sse = P.cc - st;
+            P.T0[(int64_t)p * ldt + p] = sse;
+            const double l0 = P.lamb[0];
+            const bool ok = l0 > 1e-10 * dm && sse == sse && fabs(sse) < 1.79e308;
+            P.T0[(int64_t)(p + 1) * ldt] = ok ? 1.0 : 0.0;
+        }
+        return;
+    }
+    // tile (bi >= bj) of -A^-1 from the linear tile index
+    int bi = (int)((sqrt(8.0 * (double)blockIdx.x + 1.0) - 1.0) * 0.5);
+    while (bi * (bi + 1) / 2 > (int)blockIdx.x) --bi;
+    while ((bi + 1) * (bi + 2) / 2 <= (int)blockIdx.x) ++bi;
+    const int bj = (int)blockIdx.x - bi * (bi + 1) / 2;
+    const int i0 = bi * kTabTile, j0 = bj * kTabTile;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int k0 = 0; k0 < p; k0 += kTabTile) {
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            const int kk = ty + 8 * m, k = k0 + kk;
+            const bool kin = k < p;
+            const double il = kin ? 1.0 / P.lamb[k] : 0.0;
+            As[kk][tx] = (kin && i0 + tx < p) ? P.Qt[(int64_t)k * p + i0 + tx] * il : 0.0;
+            Bs[kk][tx] = (kin && j0 + tx < p) ? P.Qt[(int64_t)k * p + j0 + tx] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int kk = 0; kk < kTabTile; ++kk) {
+            const double b = Bs[kk][tx];
+#pragma unroll
+            for (int m = 0; m < 4; ++m) acc[m] = fma(As[kk][ty + 8 * m], b, acc[m]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        const int i = i0 + ty + 8 * m, j = j0 + tx;
+        if (i < p && j < p && i >= j) {                 // (diagonal tiles: one writer per symmetric pair)
+            P.T0[(int64_t)i * ldt + j] = -acc[m];
+            P.T0[(int64_t)j * ldt + i] = -acc[m];
+        }
+    }
 }
 
 template <typename T>
@@ -1281,10 +1391,28 @@ extern "C" int fokl_kill_loop(fokl_ctx *ctx, const double *G, int64_t ldg, const
     // environment knob moves the switch-over for tests and tools (0 = never)
     bool use_big = !in_smem;
     if (const char *e = getenv("FOKL_KILL_BIG_MIN_P")) use_big = atoi(e) > 0 && p >= atoi(e);
+    // the model's eigendecomposition, if the caller has it: the tableau after the forward sweeps is formed from it
+    // by every SM (kill_tableau_kernel) and the kill kernels start at their first round
+    const bool from_eig = kp->lamb != nullptr && kp->Qt != nullptr && !getenv("FOKL_KILL_NO_EIG");
+    const int ldt = (p + 1 + 15) & ~15;
+    auto launch_tableau = [&](double *T0, double *w) -> int {
+        KillTabParams K;
+        K.G = G; K.ldg = ldg; K.Xty = Xty;
+        K.cols = reinterpret_cast<const int32_t *>(dmeta);
+        K.p = p; K.ldt = ldt; K.lamb = kp->lamb; K.Qt = kp->Qt;
+        K.ybar = hyp->sum_y / (double)hyp->n;
+        K.cc = hyp->yty - (double)hyp->n * K.ybar * K.ybar;
+        K.w = w; K.T0 = T0;
+        kill_w_kernel<<<(p + 7) / 8, 256, 0, ctx->stream>>>(K);
+        FOKL_LAUNCH_CHECK(ctx);
+        const int nt = (p + kTabTile - 1) / kTabTile;
+        kill_tableau_kernel<<<nt * (nt + 1) / 2 + 1, 256, 0, ctx->stream>>>(K);
+        FOKL_LAUNCH_CHECK(ctx);
+        return FOKL_OK;
+    };
     if (use_big) {
         // wide model: the tableau lives in L2 and its rows are dealt to one CTA per SM (killbig.cuh)
-        const int ldt = (p + 1 + 15) & ~15;
-        const size_t ws = ((size_t)(p + 1) * ldt + 6 * (size_t)ldt) * sizeof(double) + 256;
+        const size_t ws = ((size_t)(p + 2) * ldt + 7 * (size_t)ldt) * sizeof(double) + 256;
         char *wcur = (char *)fokl_scratch(ctx, fokl_ctx::B_CAND_A, ws);
         if (!wcur) return FOKL_ENOMEM;
         killb::Params K;
@@ -1299,7 +1427,12 @@ extern "C" int fokl_kill_loop(fokl_ctx *ctx, const double *G, int64_t ldg, const
         K.c.n = (double)hyp->n; K.c.draws = hyp->draws; K.c.from0 = hyp->stat_from0; K.c.from1 = hyp->stat_from1;
         K.in.threshav = kp->threshav; K.in.threshstda = kp->threshstda; K.in.threshstdb = kp->threshstdb;
         K.in.icpt = kp->icpt; K.in.evmin = kp->evmin; K.in.aic_adj = kp->aic_adj; K.in.start = kp->start;
-        K.T = carve<double>(wcur, (size_t)(p + 1) * ldt);
+        K.T = carve<double>(wcur, (size_t)(p + 2) * ldt);
+        K.pre = from_eig ? 1 : 0;
+        if (from_eig) {
+            rc = launch_tableau(K.T, carve<double>(wcur, (size_t)ldt));
+            if (rc) return rc;
+        }
         K.dg = carve<double>(wcur, 2 * (size_t)ldt);
         K.last = carve<double>(wcur, 2 * (size_t)ldt);
         K.bcast = carve<double>(wcur, 2 * (size_t)ldt);
@@ -1339,6 +1472,15 @@ extern "C" int fokl_kill_loop(fokl_ctx *ctx, const double *G, int64_t ldg, const
     P.in.threshav = kp->threshav; P.in.threshstda = kp->threshstda; P.in.threshstdb = kp->threshstdb;
     P.in.icpt = kp->icpt; P.in.evmin = kp->evmin; P.in.aic_adj = kp->aic_adj; P.in.start = kp->start;
     P.T_global = Tg; P.out_i = out_i; P.out_ev = out_ev;
+    P.T0 = nullptr; P.ldt0 = ldt;
+    if (from_eig) {
+        char *tcur = (char *)fokl_scratch(ctx, fokl_ctx::B_CAND_B, ((size_t)(p + 2) * ldt + (size_t)ldt) * sizeof(double) + 256);
+        if (!tcur) return FOKL_ENOMEM;
+        double *T0 = carve<double>(tcur, (size_t)(p + 2) * ldt);
+        rc = launch_tableau(T0, carve<double>(tcur, (size_t)ldt));
+        if (rc) return rc;
+        P.T0 = T0;
+    }
     P.smem_doubles = in_smem ? (int)need : 0;
     size_t smem = (size_t)(head + (in_smem ? need : 0)) * sizeof(double);
     FOKL_CUDA(ctx, cudaFuncSetAttribute(kill_loop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));

@@ -32,7 +32,8 @@ struct Params {
     int p, vm, ldt;
     fokl::CandConst c;
     fokl::KillLoopIn in;
-    double *T;           // [p + 1][ldt]
+    double *T;           // [p + 1][ldt] (+ one row: entry [p + 1][0] = 1.0 if pre != 0 and the tableau is usable)
+    int pre;             // != 0: T already holds the tableau after the p forward sweeps (kill_tableau_kernel)
     double *dg;          // [2][ldt] diagonal of T (buffer r & 1 is read in kill round r)
     double *last;        // [2][ldt] last row of T, likewise
     double *bcast;       // [2][ldt] forward sweeps: the next pivot row
@@ -90,7 +91,16 @@ __global__ void __launch_bounds__(kThreads, 1) kill_loop_big_kernel(const Params
     double *T = P.T;
 
     // ---- tableau [G x; x' yty] (centred like fokl::kill_loop_t), rows dealt round-robin ------------------------------------
-    for (int j = cta + nc * warp; j < ld; j += nc * kWarps) {
+    // (pre: the swept tableau was formed from the model's eigendecomposition -- only the diagonal and the last row of
+    // the first kill round are copied out, the p pivots with one grid barrier each are not run)
+    const bool pre = P.pre != 0 && __ldcg(T + (int64_t)ld * ldt) > 0.5;
+    if (pre) {
+        for (int i = cta * kThreads + tid; i < ld; i += nc * kThreads) {
+            P.dg[i] = __ldcg(T + (int64_t)i * ldt + i);
+            P.last[i] = __ldcg(T + (int64_t)p * ldt + i);
+        }
+    }
+    for (int j = cta + nc * warp; j < ld && !pre; j += nc * kWarps) {
         double *Tj = T + (int64_t)j * ldt;
         for (int i = lane; i < ld; i += 32) {
             double v;
@@ -109,7 +119,7 @@ __global__ void __launch_bounds__(kThreads, 1) kill_loop_big_kernel(const Params
 
     // ---- forward sweeps -----------------------------------------------------------------------------------------------------
     int bad = 0;
-    for (int k = 0; k < p; ++k) {
+    for (int k = 0; k < p && !pre; ++k) {
         const double *src = P.bcast + (size_t)(k & 1) * ldt;
         for (int i = tid; i < ld; i += kThreads) rowbuf[i] = __ldcg(src + i);
         __syncthreads();

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define FOKL_ABI_VERSION 1
+#define FOKL_ABI_VERSION 2
 
 #define FOKL_OK 0
 #define FOKL_EINVAL (-1)   /* bad argument                                  */
@@ -244,6 +244,12 @@ typedef struct fokl_kill_params {
     double aic_adj;                            /* (2 - ln n) if aic else 0, per model column       */
     int32_t start;                             /* first candidate index to consider                */
     int32_t reserved;
+    /* Optional (both or neither; dev): the eigendecomposition of the model's Gram G[cols][cols] as fokl_candidates_eval
+     * returns it (lamb ascending, Qt[k * p + i] = component i of eigenvector k).  The tableau the loop starts from is
+     * then formed from it by the whole device instead of by p sequential pivots; an ill-conditioned model
+     * (lamb[0] <= 1e-10 max diag) takes the sequential form regardless. */
+    const double *lamb;
+    const double *Qt;
 } fokl_kill_params;
 int fokl_kill_loop(fokl_ctx *ctx, const double *G, int64_t ldg, const double *Xty, const int32_t *cols, int p,
                    const int32_t *cand_pos, const double *bv0, const double *bv1, int vm, const fokl_hypers *hyp,

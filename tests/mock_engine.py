@@ -203,7 +203,7 @@ class MockEngine:
         return emu.kill_loop(self._G, self._Xty, cols, cand_pos, bv0, bv1, hyp, threshav=threshav, threshstda=threshstda,
                              threshstdb=threshstdb, icpt=icpt, evmin=evmin, aic_adj=aic_adj, start=start)
 
-    def kill_loop_launch(self, *args):
+    def kill_loop_launch(self, *args, **kw):
         r = self.kill_loop(*args)
         self.calls.append(('kill_launch', 0))
 

@@ -451,6 +451,53 @@ def test_whole_device_kill_loop_equals_single_cta_kernel(engine, monkeypatch, p)
         assert engine.kill_loop(cols, pos, bv0, bv1, hyp, 0.3, 0.5, 2.0, 2.0, full, 0.0, 0)['bad'] != 0
 
 
+@pytest.mark.parametrize('p,big', [(60, '0'), (100, '0'), (226, '0'), (150, '2'), (700, '2')])
+def test_kill_loop_from_eigendecomposition_equals_sequential_pivots(engine, monkeypatch, p, big):
+    """fokl_kill_params.lamb / Qt: the tableau the loop starts from is formed from the model's eigendecomposition
+    (csrc/candidates.cu kill_tableau_kernel) instead of by p sequential pivots -- same decisions, BICs to 1e-9; an
+    ill-conditioned model takes the sequential form (and reports a singular Gram as before)."""
+    rng = np.random.default_rng(100 + p)
+    n = 3 * p + 50
+    X = rng.standard_normal((n, p)) * (1.0 + 3.0 * rng.random(p))
+    X[:, 0] = 1.0
+    y = X[:, :min(40, p)] @ rng.standard_normal(min(40, p)) + 0.5 * rng.standard_normal(n)
+    _load_gram(engine, X.T @ X, X.T @ y, n, y)
+    hyp = engine.make_hypers(4, 1, 4, 1, 1, 1, 10)
+    cols = list(range(p))
+    vm = (3 * p) // 4
+    pos = [int(c) for c in rng.permutation(np.arange(p - vm, p))]
+    bv0 = np.sort(rng.random(vm))
+    bv1 = rng.random(vm) * 3
+    res = engine.evaluate([cols], hyp, want_eig=True, refine_tol=None)
+    full = float(res.ev[0])
+    monkeypatch.setenv('FOKL_KILL_BIG_MIN_P', big)
+    seq = engine.kill_loop(cols, pos, bv0, bv1, hyp, 0.3, 0.5, 2.0, 2.0, full, 0.0, 1)
+    eig = engine.kill_loop_launch(cols, pos, bv0, bv1, hyp, 0.3, 0.5, 2.0, 2.0, full, 0.0, 1,
+                                  eig=(res.lamb, res.Q)).finish()
+    assert seq['bad'] == eig['bad'] == 0 and seq['n_acc'] == eig['n_acc'] > 0
+    assert seq['tested'] == eig['tested']
+    assert np.array_equal(seq['acc'], eig['acc']) and np.array_equal(seq['calls'], eig['calls'])
+    # (north_star: BIC within rtol 1e-9 of the reference's float64 path)
+    assert np.allclose(seq['ev'], eig['ev'], rtol=1e-9, atol=0), np.max(np.abs(seq['ev'] - eig['ev']) / np.abs(seq['ev']))
+    # the environment switch really selects the sequential form (bit-identical to it)
+    monkeypatch.setenv('FOKL_KILL_NO_EIG', '1')
+    off = engine.kill_loop_launch(cols, pos, bv0, bv1, hyp, 0.3, 0.5, 2.0, 2.0, full, 0.0, 1,
+                                  eig=(res.lamb, res.Q)).finish()
+    assert np.array_equal(off['ev'], seq['ev'])
+    monkeypatch.delenv('FOKL_KILL_NO_EIG')
+    # nearly singular model: lam_min <= 1e-10 max diag -> the sequential form runs, flags the Gram as it did before
+    X2 = X.copy()
+    X2[:, 5] = X2[:, 2] * (1.0 + 1e-9)
+    _load_gram(engine, X2.T @ X2, X2.T @ y, n, y)
+    res2 = engine.evaluate([cols], hyp, want_eig=True, refine_tol=None)
+    seq2 = engine.kill_loop(cols, pos, bv0, bv1, hyp, 0.3, 0.5, 2.0, 2.0, full, 0.0, 0)
+    if res2.lamb is not None and not (int(res2.info[0]) & 6):
+        eig2 = engine.kill_loop_launch(cols, pos, bv0, bv1, hyp, 0.3, 0.5, 2.0, 2.0, full, 0.0, 0,
+                                       eig=(res2.lamb, res2.Q)).finish()
+        assert eig2['bad'] == seq2['bad'] and eig2['n_acc'] == seq2['n_acc']
+        assert np.array_equal(eig2['ev'], seq2['ev'])
+
+
 @pytest.mark.parametrize('p0,n_models,kind', [(40, 12, 'gauss'), (300, 25, 'graded'), (900, 30, 'gauss')])
 def test_nested_chains_match_one_eigensolver_per_model(engine, p0, n_models, kind):
     """csrc/nested.cu: the spectral decomposition of a model carried to its sub-models by secular-equation steps

@@ -678,7 +678,12 @@ class Engine:
             self.ctx_side = ctx
             # its batches run next to the main context's full-model evaluation (one cluster of up to 16 CTAs)
             sms = self.torch.cuda.get_device_properties(self.device).multi_processor_count
-            self.lib.fokl_ctx_set_sm_budget(ctx, max(sms - 16, 16))
+            self.lib.fokl_ctx_set_sm_budget(ctx, max(sms - int(os.environ.get('FOKL_B200_SIDE_RESERVE', '16')), 16))
+            # ... and the main context's candidate stage (the full model: one cluster, latency-bound, on the critical path)
+            # goes to a high-priority stream so that its CTAs are placed ahead of the batch's: cfg4 full models
+            # 34.0 -> 30.6 ms per fit next to the side batches (gpurun_out/r4l, profiles/r02_bench_lines.txt)
+            if os.environ.get('FOKL_B200_MAIN_HP', '1') not in ('0', ''):
+                self.lib.fokl_ctx_set_high_priority(self.ctx, 1)
         return self.ctx_side
 
     def gram_state(self):

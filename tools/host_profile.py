@@ -64,6 +64,10 @@ def main():
             k[1] += g
         busy += s.elapsed_time(e)
         prev_end, prev_name = e, name
+    print('timeline (ms from the first event; side_batch runs on the side stream):')
+    for name, s_, e_, extra in ev:
+        print('%9.3f  %-18s %8.3f ms  %s' % (t0.elapsed_time(s_), name, s_.elapsed_time(e_),
+                                            ' '.join('%s=%s' % kv for kv in extra.items() if kv[0] in ('cands', 'pmax', 'cols'))))
     print('main-stream stages busy %.1f ms; gaps between them:' % busy)
     for key, (cnt, tot) in sorted(gaps.items(), key=lambda kv: -kv[1][1]):
         print('   %-40s %3d x  %7.3f ms total  %6.3f avg' % (key, cnt, tot, tot / cnt))

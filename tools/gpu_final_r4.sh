@@ -4,7 +4,7 @@
 mkdir -p gpurun_out
 cp tools/.commit gpurun_out/f4_commit.txt 2>/dev/null
 ( timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2 ) > gpurun_out/f4_smoke.log; cat gpurun_out/f4_smoke.log
-( timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -4 ) > gpurun_out/f4_pytest.log; cat gpurun_out/f4_pytest.log
+( timeout 1200 python -m pytest tests -m gpu -q 2>&1 | tail -4 ) > gpurun_out/f4_pytest.log; cat gpurun_out/f4_pytest.log
 ( timeout 900 python bench.py 2>&1 | tail -1 ) > gpurun_out/f4_bench.log
 ( timeout 600 python bench.py --impl reference --steps 3 --warmup 1 2>&1 | tail -1 ) > gpurun_out/f4_bench_reference.log
 ( timeout 600 python bench.py --workload cfg5 --steps 3 --warmup 2 --no-cpu-baseline 2>&1 | tail -1 ) > gpurun_out/f4_bench_cfg5.log

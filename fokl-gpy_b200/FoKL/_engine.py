@@ -74,6 +74,13 @@ class PendingCandidates:
         self.engine, self.res, self.ev, self.info = engine, res, ev, info
         self.col_sets, self.side, self.keep_alive = col_sets, side, keep_alive
 
+    def _unpack(self, h):
+        res, n = self.res, len(self.col_sets)
+        n_i = (n + 1) // 2
+        res.ev = h[:n].copy()
+        res.info = h[n:n + n_i].view(np.int32)[:n].copy()
+        res.stats_host = h[n + n_i:] if res.stats is not None else None
+
     def finish(self, refine_tol=None):
         """Synchronise and return the CandidateResult.  refine_tol > 0: near-interpolating / degenerate fits are
         recomputed from an N-length residual pass over the *current* X (FR:1551), so the models must still be there."""
@@ -83,18 +90,14 @@ class PendingCandidates:
             # read back on the side stream itself: the main stream may hold later work (the next kill loop) that these
             # copies must not queue behind; afterwards the main stream may touch the batch's tensors
             with eng.torch.cuda.stream(eng.side_stream):
-                res.ev = self.ev.cpu().numpy()
-                res.info = self.info.cpu().numpy()
-                if res.stats is not None:
-                    res.stats_host = res.stats.cpu().numpy()
+                self._unpack(self.pack.cpu().numpy())
             main_stream = eng.torch.cuda.current_stream(eng.device)
             main_stream.wait_stream(eng.side_stream)
-            for tns in (res.stats, res.betas, res.sigs, res.taus, res.betahat, res.lamb, res.Q, self.ev, self.info):
+            for tns in (self.pack, res.betas, res.sigs, res.taus, res.betahat, res.lamb, res.Q):
                 if tns is not None:
                     tns.record_stream(main_stream)      # allocated on the side stream's pool, read on the main stream
         else:
-            res.ev = self.ev.cpu().numpy()
-            res.info = self.info.cpu().numpy()
+            self._unpack(self.pack.cpu().numpy())
         res.refined = np.zeros(len(res.ev), dtype=bool)
         if refine_tol is not None and refine_tol > 0:
             bad = eng.refine_mask(res.ev, res.p, refine_tol)
@@ -216,6 +219,24 @@ class Engine:
     def _allreduce(self, t):
         if self.dist is not None:
             self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+
+    def ctl_allreduce(self, arr):
+        """Sum a small host array over the ranks and return it (host).  Control traffic of the selection loop (two
+        scalars per verified model): it travels on its OWN communicator and on the side stream, so it neither queues
+        behind the Gram block's allreduce -- which waits for the K2 kernel the main stream is running -- nor orders
+        the main stream after it."""
+        torch = self.torch
+        if self.dist is None:
+            return arr
+        if getattr(self, '_ctl_group', None) is None:
+            ranks = None if self.group is None else self.dist.get_process_group_ranks(self.group)
+            self._ctl_group = self.dist.new_group(ranks=ranks)
+        self._side()
+        with torch.cuda.stream(self.side_stream):
+            t = torch.from_numpy(np.ascontiguousarray(arr)).to(self.device)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self._ctl_group)
+            out = t.cpu().numpy()
+        return out
 
     # ---- optional per-stage timing with CUDA events on the launching stream ------------------------
     def _tic(self):
@@ -686,6 +707,11 @@ class Engine:
                 self.lib.fokl_ctx_set_high_priority(self.ctx, 1)
         return self.ctx_side
 
+    def join_side(self):
+        """Order the main stream after everything the side context's stream holds (no host synchronisation)."""
+        if getattr(self, 'ctx_side', None) is not None:
+            self.torch.cuda.current_stream(self.device).wait_stream(self.side_stream)
+
     def gram_state(self):
         """(G, Xty, ldg) of the current model as tensor references: stays valid (for reading) across the next
         append_terms / one compact, which write to other buffers or to rows / columns beyond the current P."""
@@ -738,11 +764,14 @@ class Engine:
             total_p = int(p.sum())
             D = int(hyp.draws)
             f64 = dict(dtype=torch.float64, device=self.device)
-            ev = torch.empty(n_cand, **f64)
-            info = torch.zeros(n_cand, dtype=torch.int32, device=self.device)
-            betahat = torch.empty(total_p, **f64)
             chain_any = rng_mode != _lib.RNG_NONE and (run_chain is None or bool(np.any(run_chain)))
-            stats = torch.zeros(3 * total_p, **f64) if chain_any else None
+            # ev | info | stats share one buffer: one read-back in finish() instead of three
+            n_i = (n_cand + 1) // 2
+            pack = torch.zeros(n_cand + n_i + (3 * total_p if chain_any else 0), **f64)
+            ev = pack[:n_cand]
+            info = pack[n_cand:n_cand + n_i].view(torch.int32)[:n_cand]
+            betahat = torch.empty(total_p, **f64)
+            stats = pack[n_cand + n_i:] if chain_any else None
             betas = torch.empty(D * total_p, **f64) if (chain_any and want_betas) else None
             sigs = torch.empty(D * n_cand, **f64) if (chain_any and want_betas) else None
             taus = torch.empty(D * n_cand, **f64) if (chain_any and want_betas) else None
@@ -795,7 +824,9 @@ class Engine:
         res.p, res.vec_off, res.mat_off, res.draws = p, vec_off, mat_off, D
         res.stats, res.betas, res.sigs, res.taus = stats, betas, sigs, taus
         res.betahat, res.lamb, res.Q = betahat, lamb, Q
-        return PendingCandidates(self, res, ev, info, col_sets, side, (G, Xty, var_t, sf_t))
+        pend = PendingCandidates(self, res, ev, info, col_sets, side, (G, Xty, var_t, sf_t))
+        pend.pack = pack
+        return pend
 
     # ---- chains of nested models (csrc/nested.cu) ---------------------------------------------------------------------
     def nested_chains_launch(self, col_sets, hyp, seed, stream_ids, gram=None, side=False, after=None, head=None):

@@ -264,7 +264,8 @@ def forward_select(engine, hy, m, n_phis, console=True, rng='philox', eager=Fals
         # its digits to cancellation (Engine.refine_mask) -- the device kill loop scores with the same Gram-only form,
         # so this substage takes the literal path
         S['refined'] = bool(getattr(res, 'refined', np.zeros(1, dtype=bool))[0])
-        st = res.stats_of(0).cpu().numpy()
+        st = getattr(res, 'stats_host', None)          # (read back with the BIC in one copy)
+        st = res.stats_of(0).cpu().numpy() if st is None else st[:3 * len(full)].reshape(3, len(full))
         S['betas'] = res.betas_of(0)
         new_cols = np.arange(S['p_old'], S['p_old'] + S['vm'])
         with np.errstate(all='ignore'):
@@ -441,9 +442,12 @@ def forward_select(engine, hy, m, n_phis, console=True, rng='philox', eager=Fals
         """All ranks: sum the per-model scalars into place; returns True if any rank flagged a model for refinement."""
         if world > 1:
             vals[len(todo), 0] = float(need_refine)
-            t = torch.from_numpy(vals).to(engine.device)
-            engine._allreduce(t)
-            vals[:] = t.cpu().numpy()
+            if hasattr(engine, 'ctl_allreduce'):
+                vals[:] = engine.ctl_allreduce(vals)
+            else:                                   # (the tests' CPU stand-in engine)
+                t = torch.from_numpy(vals).to(engine.device)
+                engine._allreduce(t)
+                vals[:] = t.cpu().numpy()
             owners = share_of(todo)[1]
             for i, rd in enumerate(todo):
                 rd['owner'] = int(owners[i])
@@ -680,9 +684,22 @@ def forward_select(engine, hy, m, n_phis, console=True, rng='philox', eager=Fals
             evs.append(ev)
         return False
 
-    def will_finish(ev_outlook):
-        """The stopping rule of FR:1701-1721 applied to a BIC that is not final yet (a prediction only)."""
-        return bool(evs) and not (ev_outlook < np.min(evs)) and greater >= tolerance
+    def will_finish(ev_outlook, pending=None):
+        """The stopping rule of FR:1701-1721 applied to a BIC that is not final yet (a prediction only).  pending: the
+        predicted BIC of the previous substage when that one has not been closed yet (it is applied first)."""
+        evs_s, g = list(evs), greater
+        if pending is not None:
+            if evs_s:
+                if pending < np.min(evs_s):
+                    g = 1
+                elif g < tolerance:
+                    g += 1
+                else:
+                    return True              # the fit is predicted to end with the previous substage
+            else:
+                g += 1
+            evs_s.append(pending)
+        return bool(evs_s) and not (ev_outlook < np.min(evs_s)) and g >= tolerance
 
     # ---- driver ------------------------------------------------------------------------------------------------------------
     # Sequential form, per substage s:  A(s) append -> B(s) full model -> C(s) kill loop [-> chains of the accepted
@@ -696,7 +713,7 @@ def forward_select(engine, hy, m, n_phis, console=True, rng='philox', eager=Fals
     # both forms draw the same variates and give bit-identical fits.
     step = (1, first_partition(1, m, sett))
     S = open_substage(step[0], step[1], terms)
-    carry = None            # dict(S=previous substage, gen=its generator, todo, gram=its Gram before compaction, cnt0)
+    carry = None            # dict(S=previous substage, gen=its generator, todo, gram=its Gram before compaction, cnt0, ev)
     while True:
         # ---- B(s) [+ chains of s - 1] ----
         mark = engine.mark() if (carry is not None or can_split) else None
@@ -705,22 +722,47 @@ def forward_select(engine, hy, m, n_phis, console=True, rng='philox', eager=Fals
             # the side batch's stream waits for what the main stream held at `mark` (K1 + K2 of s, which it must not
             # share the SMs with), not for the full model just enqueued -- whose single cluster is launched first so that
             # the batch's many clusters fill the device around it
-            todo, vals, mine = carry['todo'], np.zeros((len(carry['todo']) + 1, 2)), my_share(carry['todo'])
-            side = chains_launch(todo, mine, gram=carry['gram'], side=True, after=mark)
+            todo_prev, vals, mine = carry['todo'], np.zeros((len(carry['todo']) + 1, 2)), my_share(carry['todo'])
+            side = chains_launch(todo_prev, mine, gram=carry['gram'], side=True, after=mark)
         start_next(S, mark)          # after both launches: the build waits for their eigensolver kernels
         full_finish(S, handle)
-        # C(s) starts here: its kill-loop launch is enqueued before the host turns to the chains of s - 1, so the
-        # collection / checks / bookkeeping of s - 1 (and any wait for a long side batch) run while that kernel does
-        gen_s = request = outcome_s = pending_kill = None
+        # ---- C(s): the kill loop ----
+        gen_s = request = outcome_s = None
         if not (literal or S['refined']):
             gen_s = kill_fast(S)
             request, outcome_s = step_gen(gen_s, first=True)
-            if request is not None and request[0] == 'kill':
-                pending_kill = kill_launch(S, request)
+            while request is not None and request[0] == 'kill':
+                request, outcome_s = step_gen(gen_s, kill_launch(S, request).finish())
+        step = walk_next(S['ind'], S['part'])
+        # ---- D(s) + A(s + 1), speculatively, BEFORE the host turns to the chains of s - 1: the device goes straight
+        # from the kill loop to the compaction and the next substage's columns, and the collection / checks /
+        # bookkeeping of s - 1 (read-backs, an allreduce with several ranks) run while those kernels do.  The stopping
+        # rule is predicted with the previous substage's predicted BIC, which is almost always its true one.
+        spec = None
+        if gen_s is not None and request is not None:
+            _, todo, outlook = request
+            if pipeline and step is not None and outlook is not None and \
+                    (pipeline == 'always' or not will_finish(outlook['ev'], None if carry is None else carry['ev'])):
+                if carry is not None and hasattr(engine, 'join_side'):
+                    engine.join_side()           # the chains of s - 1 read the Gram buffer this compaction writes to
+                gram = engine.gram_state()
+                cnt0 = dict(cnt)
+                killed = outlook['killed']
+                kset = set(killed)
+                keep = [c for c in S['full'] if c not in kset]
+                engine.compact(keep)
+                S['terms_final'] = np.delete(S['terms'], [c - 1 for c in killed], axis=0)
+                terms_before = terms
+                terms = S['terms_final']
+                cnt_spec = dict(calls=outlook['calls'], gibbs=outlook['gibbs'])
+                spec = dict(carry=dict(S=S, gen=gen_s, todo=todo, gram=gram, cnt0=cnt0, ev=outlook['ev']),
+                            S_next=open_substage(step[0], step[1], terms, p_stable=S['p_old']), cnt=cnt_spec)
+                terms = terms_before             # (restored: the bookkeeping of s - 1 below runs in its own state)
+        # ---- the chains of s - 1: collect, check, close ----
         if carry is not None:
-            need = chains_collect(todo, mine, side, vals, refine=False)
-            need = chains_reduce(todo, vals, need)
-            for i, rd in enumerate(todo):
+            need = chains_collect(todo_prev, mine, side, vals, refine=False)
+            need = chains_reduce(todo_prev, vals, need)
+            for i, rd in enumerate(todo_prev):
                 rd['icpt_true'], rd['ev_true'] = float(vals[i, 0]), float(vals[i, 1])
                 if need:
                     rd['unrefined'] = True
@@ -728,7 +770,8 @@ def forward_select(engine, hy, m, n_phis, console=True, rng='philox', eager=Fals
             req_prev, outcome = step_gen(gen, 'speculated')
             if outcome is None:
                 # a check failed: rebuild substage s - 1 as it was before the speculation and finish it synchronously
-                # (what was started for substage s, including its kill loop, is dropped)
+                # (what was started for substage s -- its full model, kill loop, compaction, the columns of s + 1 -- is
+                # dropped)
                 assert req_prev[0] == 'rollback'
                 engine.truncate(prev['p_old'])
                 if can_split:
@@ -753,37 +796,20 @@ def forward_select(engine, hy, m, n_phis, console=True, rng='philox', eager=Fals
             finished = close_substage(prev, outcome, compacted=True)
             cnt.update(calls=saved['calls'], gibbs=saved['gibbs'])      # the speculative substage's counters stand
             if finished:
-                engine.truncate(S['p_old'])                              # drop the speculative columns of s
+                engine.truncate(S['p_old'])                              # drop the speculative columns of s (and s + 1)
                 cnt['calls'], cnt['gibbs'] = outcome['calls'], outcome['gibbs']
                 break
-        # ---- C(s), continued ----
+        if spec is not None:
+            carry, S, terms = spec['carry'], spec['S_next'], spec['carry']['S']['terms_final']
+            cnt['calls'], cnt['gibbs'] = spec['cnt']['calls'], spec['cnt']['gibbs']
+            continue
+        # ---- C(s) / D(s), synchronous forms ----
         if gen_s is None:
             outcome = kill_literal(S, parity=(mode == _lib.RNG_INJECTED))
         else:
             outcome = outcome_s
-            if pending_kill is not None:
-                request, outcome = step_gen(gen_s, pending_kill.finish())
-            while request is not None and request[0] == 'kill':
-                request, outcome = step_gen(gen_s, kill_launch(S, request).finish())
-        step = walk_next(S['ind'], S['part'])
-        if request is not None:
-            _, todo, outlook = request
-            if pipeline and step is not None and outlook is not None and \
-                    (pipeline == 'always' or not will_finish(outlook['ev'])):
-                # speculate on `outlook`: D(s) without its bookkeeping, then A(s + 1)
-                gram = engine.gram_state()
-                cnt0 = dict(cnt)
-                killed = outlook['killed']
-                kset = set(killed)
-                keep = [c for c in S['full'] if c not in kset]
-                engine.compact(keep)
-                S['terms_final'] = np.delete(S['terms'], [c - 1 for c in killed], axis=0)
-                terms = S['terms_final']
-                cnt['calls'], cnt['gibbs'] = outlook['calls'], outlook['gibbs']
-                carry = dict(S=S, gen=gen_s, todo=todo, gram=gram, cnt0=cnt0)
-                S = open_substage(step[0], step[1], terms, p_stable=S['p_old'])
-                continue
-            outcome = drive(gen_s, request, S)
+            if request is not None:
+                outcome = drive(gen_s, request, S)
         finished = close_substage(S, outcome, compacted=False)
         if finished or step is None:
             break

@@ -147,7 +147,7 @@ class Engine:
         self.ds = None
         self.X = self.Xfull = None
         self.P = 0
-        self.G = self.Xty = self.G2 = self.Xty2 = None
+        self.G = self.Xty = self.G2 = self.Xty2 = self.G3 = self.Xty3 = None
         self.block = None
         self.n_global = 0
         self.sum_y = self.yty = 0.0
@@ -444,8 +444,8 @@ class Engine:
             G[:self.P, :self.P].copy_(self.G[:self.P, :self.P])
             Xty[:self.P].copy_(self.Xty[:self.P])
         self.G, self.Xty = G, Xty
-        self.G2 = torch.zeros_like(G)
-        self.Xty2 = torch.zeros_like(Xty)
+        self.G2, self.G3 = torch.zeros_like(G), torch.zeros_like(G)
+        self.Xty2, self.Xty3 = torch.zeros_like(Xty), torch.zeros_like(Xty)
         self.Gcap = cap
 
     def _append_built(self, c):
@@ -661,8 +661,11 @@ class Engine:
         self.P_base = p_new
         self._ck(self.lib.fokl_gram_compact(self.ctx, self.G.data_ptr(), self.Gcap, self.Xty.data_ptr(),
                                             keep.ctypes.data, p_new, self.G2.data_ptr(), self.Gcap, self.Xty2.data_ptr()))
-        self.G, self.G2 = self.G2, self.G
-        self.Xty, self.Xty2 = self.Xty2, self.Xty
+        # three buffers in rotation: the Gram a compaction starts from stays intact across the NEXT compaction as well,
+        # so the chains that verify substage s - 1 on the side stream (they index the Gram as it was before the
+        # compaction of s - 1) may still be running when the compaction of s is enqueued
+        self.G, self.G2, self.G3 = self.G2, self.G3, self.G
+        self.Xty, self.Xty2, self.Xty3 = self.Xty2, self.Xty3, self.Xty
         self.P = p_new
 
     # ------------------------------------------------------------------------------------------------
@@ -714,7 +717,7 @@ class Engine:
 
     def gram_state(self):
         """(G, Xty, ldg) of the current model as tensor references: stays valid (for reading) across the next
-        append_terms / one compact, which write to other buffers or to rows / columns beyond the current P."""
+        append_terms calls and TWO compactions, which write to other buffers or to rows / columns beyond the current P."""
         return (self.G, self.Xty, self.Gcap)
 
     def truncate(self, p):

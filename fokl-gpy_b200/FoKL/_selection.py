@@ -743,8 +743,8 @@ def forward_select(engine, hy, m, n_phis, console=True, rng='philox', eager=Fals
             _, todo, outlook = request
             if pipeline and step is not None and outlook is not None and \
                     (pipeline == 'always' or not will_finish(outlook['ev'], None if carry is None else carry['ev'])):
-                if carry is not None and hasattr(engine, 'join_side'):
-                    engine.join_side()           # the chains of s - 1 read the Gram buffer this compaction writes to
+                # (the chains of s - 1 may still be reading the Gram as it was two compactions ago: Engine.compact
+                # rotates three buffers, so this compaction does not write to it)
                 gram = engine.gram_state()
                 cnt0 = dict(cnt)
                 killed = outlook['killed']

@@ -454,12 +454,14 @@ def forward_select(engine, hy, m, n_phis, console=True, rng='philox', eager=Fals
             need_refine = vals[len(todo), 0] > 0
         return bool(need_refine)
 
-    def chains_now(todo):
-        """Synchronous form: evaluate `todo` on the current Gram (X still holds every column: refinement possible)."""
+    def chains_now(todo, launched=None):
+        """Synchronous form: evaluate `todo` on the current Gram (X still holds every column: refinement possible).
+        launched: (indices, parts) of a chains_launch(todo, indices) made earlier for exactly this list."""
         vals = np.zeros((len(todo) + 1, 2))
-        mine = my_share(todo)
+        mine = my_share(todo) if launched is None else launched[0]
+        first = chains_launch(todo, mine) if launched is None else launched[1]
         if world > 1:
-            need = chains_collect(todo, mine, chains_launch(todo, mine), vals, refine=False)
+            need = chains_collect(todo, mine, first, vals, refine=False)
             if chains_reduce(todo, vals, need):
                 # some model needs the N-length residual pass (a collective): evaluate the batch replicated
                 vals = np.zeros((len(todo) + 1, 2))
@@ -468,7 +470,7 @@ def forward_select(engine, hy, m, n_phis, console=True, rng='philox', eager=Fals
                 for rd in todo:
                     rd['owner'] = -1
         else:
-            chains_collect(todo, mine, chains_launch(todo, mine), vals, refine=True)
+            chains_collect(todo, mine, first, vals, refine=True)
         for i, rd in enumerate(todo):
             rd['icpt_true'], rd['ev_true'] = float(vals[i, 0]), float(vals[i, 1])
 
@@ -631,14 +633,19 @@ def forward_select(engine, hy, m, n_phis, console=True, rng='philox', eager=Fals
         except StopIteration as stop:
             return None, stop.value
 
-    def drive(gen, request, S):
-        """Answer a kill_fast generator synchronously until it returns its outcome."""
+    def drive(gen, request, S, pre=None):
+        """Answer a kill_fast generator synchronously until it returns its outcome.  pre: (todo, indices, parts) of a
+        chains_launch already made for the pending request."""
         while True:
             if request[0] == 'kill':
                 answer = kill_launch(S, request).finish()
             else:
                 assert request[0] == 'chains', request[0]
-                chains_now(request[1])
+                if pre is not None and request[1] is pre[0]:
+                    chains_now(request[1], launched=pre[1:])
+                else:
+                    chains_now(request[1])
+                pre = None
                 answer = 'done'
             request, outcome = step_gen(gen, answer)
             if request is None:
@@ -758,6 +765,12 @@ def forward_select(engine, hy, m, n_phis, console=True, rng='philox', eager=Fals
                 spec = dict(carry=dict(S=S, gen=gen_s, todo=todo, gram=gram, cnt0=cnt0, ev=outlook['ev']),
                             S_next=open_substage(step[0], step[1], terms, p_stable=S['p_old']), cnt=cnt_spec)
                 terms = terms_before             # (restored: the bookkeeping of s - 1 below runs in its own state)
+        # no speculation (the fit is expected to end here, or this is the last substage of the walk): the chains that
+        # verify s are at least ENQUEUED before the host waits for those of s - 1
+        pre = None
+        if spec is None and carry is not None and gen_s is not None and request is not None and request[0] == 'chains':
+            idx_s = my_share(request[1])
+            pre = (request[1], idx_s, chains_launch(request[1], idx_s))
         # ---- the chains of s - 1: collect, check, close ----
         if carry is not None:
             need = chains_collect(todo_prev, mine, side, vals, refine=False)
@@ -809,7 +822,7 @@ def forward_select(engine, hy, m, n_phis, console=True, rng='philox', eager=Fals
         else:
             outcome = outcome_s
             if request is not None:
-                outcome = drive(gen_s, request, S)
+                outcome = drive(gen_s, request, S, pre=pre)
         finished = close_substage(S, outcome, compacted=False)
         if finished or step is None:
             break

@@ -177,11 +177,12 @@ def gram_plan(A, p_old, c, cap=352, warps=16, kchunks=1, mode=1):
     assert p1 == p_old + c + 1
     out = np.full((p1, c), np.nan)
     cover = np.zeros((p1, c), dtype=np.int32)
-    stats = np.zeros(5, dtype=np.int32)
+    stats = np.zeros(7, dtype=np.int32)
     rc = lib().emu_gram_plan(A.ctypes.data, n, p_old, c, cap, warps, kchunks, mode, out.ctypes.data, cover.ctypes.data,
                              stats.ctypes.data)
     return rc, out, cover, dict(n_tiles=int(stats[0]), max_slots=int(stats[1]), blocks=int(stats[2]),
-                                max_positions_per_tile=int(stats[3]), max_ksplit=int(stats[4]))
+                                max_positions_per_tile=int(stats[3]), max_ksplit=int(stats[4]), sp_spread=int(stats[5]),
+                                flex_late=int(stats[6]))
 
 
 def update_chain(mode, po, pn, draws, astar, atau_star, b, btau, sigsqd0, yty, squerr, n, arrays, variates=None, seed=0,

@@ -242,7 +242,7 @@ int emu_update_chain(const int32_t *mdl, const double *par, const double *lam_o,
 // pre-filled by the caller; cover (same shape, int) counts how many times each entry was written.
 #include "../../fokl-gpy_b200/csrc/gram_plan.h"
 extern "C" int emu_gram_plan(const double *A, int64_t n, int p_old, int c, int max_slots_cap, int warps, int kchunks, int mode, double *out,
-                             int32_t *cover, int32_t *stats /* n_tiles, max_slots, total_blocks, max_positions_per_tile, max_ksplit */)
+                             int32_t *cover, int32_t *stats /* n_tiles, max_slots, total_blocks, max_positions_per_tile, max_ksplit, sp_spread, flex_late */)
 {
     const int p = p_old + c;
     GramPlan pl = gram_make_plan(p_old, c, max_slots_cap, warps);
@@ -253,6 +253,8 @@ extern "C" int emu_gram_plan(const double *A, int64_t n, int p_old, int c, int m
     stats[2] = 0;
     stats[3] = 0;
     stats[4] = 0;
+    stats[5] = 0;       // largest spread of items over the sub-partitions that still have room
+    stats[6] = 0;       // loose / masked items placed behind a warp's first position although every busy warp could take one
     for (const GramTileMeta &tm : pl.tiles) {
         if (tm.n_blk > stats[3]) stats[3] = tm.n_blk;
         if (tm.ksplit > stats[4]) stats[4] = tm.ksplit;
@@ -269,6 +271,30 @@ extern "C" int emu_gram_plan(const double *A, int64_t n, int p_old, int c, int m
                 owned += h ? 0 : 1;
             }
             if (owned > gram_warp_cap(warps, w)) return -8;
+        }
+        // placement statistics: items per SM sub-partition (warp & 3), loose / masked items outside a warp's first position
+        {
+            int sl[4] = {0, 0, 0, 0}, busy = 0, flex_total = 0, flex_late = 0;
+            for (int w = 0; w < warps; ++w) {
+                int owned = 0;
+                for (int q = w, b = 0; q < tm.n_blk; q += warps, ++b) {
+                    const GramBlockMeta &bm = pl.blocks[tm.blk_off + q];
+                    if (bm.mask == 0) break;
+                    ++owned;
+                    if (bm.loose || bm.mask != 15) { ++flex_total; flex_late += b > 0; }
+                }
+                sl[w & 3] += owned;
+                busy += owned > 0;
+            }
+            int mx = 0, mn = 1 << 30;
+            for (int q = 0; q < 4; ++q) {
+                int cap_q = 0;
+                for (int w = q; w < warps; w += 4) cap_q += gram_warp_cap(warps, w);
+                mx = sl[q] > mx ? sl[q] : mx;
+                if (sl[q] < cap_q) mn = sl[q] < mn ? sl[q] : mn;       // a full sub-partition cannot take more
+            }
+            if (mn != (1 << 30) && mx - mn > stats[5]) stats[5] = mx - mn;
+            if (flex_total <= busy) stats[6] += flex_late;
         }
         // gram_kernel: every item accumulates its own chunks; gram_reduce_kernel: the head walks the chain
         std::vector<double> part((size_t)tm.n_blk * 256, 0.0);

@@ -240,6 +240,21 @@ def test_gram_work_plan_covers_the_block_exactly_once(p_old, c, cap, warps, kchu
         assert -(-st['blocks'] // (4 * warps)) <= st['n_tiles'] <= -(-st['blocks'] // (4 * warps)) + 1
 
 
+@pytest.mark.parametrize('p_old,c', [(28, 168), (51, 168), (58, 168), (64, 56), (37, 56), (14, 56), (8, 28), (400, 1680)])
+@pytest.mark.parametrize('warps', [15, 12])
+def test_gram_placement_is_even_over_the_sub_partitions(p_old, c, warps):
+    """Placement mode 2 (the K2 default): the work items of a tile are dealt evenly over the four SM sub-partitions
+    (warp & 3) -- the tensor pipe of a sub-partition is the shared resource -- and a loose / masked item sits in its
+    warp's FIRST position whenever the tile has no more of them than busy warps (kernel form FLEX = 1: one 8-load item per
+    warp at most)."""
+    rng = np.random.default_rng(p_old + c)
+    A = rng.random((40, p_old + c + 1))
+    rc, out, cover, st = emu.gram_plan(A, p_old, c, cap=240, warps=warps, kchunks=1, mode=2)
+    assert rc == 0
+    assert st['sp_spread'] <= 1, st
+    assert st['flex_late'] == 0, st
+
+
 def test_gram_k_split_fills_the_cta():
     """A narrow substage (8 new columns against 50 old ones: 4 blocks) is split over the 16-row chunks of a slab so
     that more warps of the CTA have work (two items per block: one per SM sub-partition and block -- measured faster

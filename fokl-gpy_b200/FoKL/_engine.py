@@ -710,11 +710,6 @@ class Engine:
                 self.lib.fokl_ctx_set_high_priority(self.ctx, 1)
         return self.ctx_side
 
-    def join_side(self):
-        """Order the main stream after everything the side context's stream holds (no host synchronisation)."""
-        if getattr(self, 'ctx_side', None) is not None:
-            self.torch.cuda.current_stream(self.device).wait_stream(self.side_stream)
-
     def gram_state(self):
         """(G, Xty, ldg) of the current model as tensor references: stays valid (for reading) across the next
         append_terms calls and TWO compactions, which write to other buffers or to rows / columns beyond the current P."""

@@ -524,17 +524,24 @@ def forward_select(engine, hy, m, n_phis, console=True, rng='philox', eager=Fals
                 n_acc = int(r['n_acc'])
                 if n_acc:
                     # column lists of the n_acc nested models in one shot: model k = alive minus the first k + 1 kills
+                    # (this runs between the kill kernel and the compaction, i.e. on the device's critical path: one
+                    # comparison matrix, no per-model numpy calls)
                     kcols = cand_cols[np.asarray(r['acc'][:n_acc], dtype=np.int64)]
-                    member = np.repeat(alive[None, :], n_acc, axis=0)
-                    rr_, cc_ = np.tril_indices(n_acc)
-                    member[rr_, kcols[cc_]] = False
+                    when = np.full(len(full), n_acc, dtype=np.int32)       # kill number of every column (never: n_acc)
+                    when[kcols] = np.arange(n_acc, dtype=np.int32)
+                    member = (when[None, :] > np.arange(n_acc, dtype=np.int32)[:, None]) & alive[None, :]
                     flat_cols = np.nonzero(member)[1].astype(np.int32)
-                    cuts = np.cumsum(len(model) - 1 - np.arange(n_acc))[:-1]
-                    for k_, cols_k in enumerate(np.split(flat_cols, cuts)):
-                        rounds.append(dict(i=int(r['acc'][k_]), cols=cols_k, stream=state['calls'] + int(r['calls'][k_]),
-                                           head=S.get('head'),
-                                           gibbs_after=state['gibbs'] + int(r['calls'][k_]),
-                                           ev_dev=float(r['ev'][k_]), icpt_used=state['icpt']))
+                    ends = np.cumsum(len(model) - 1 - np.arange(n_acc)).tolist()
+                    acc_l = np.asarray(r['acc'][:n_acc]).tolist()
+                    calls_l = np.asarray(r['calls'][:n_acc]).tolist()
+                    ev_l = np.asarray(r['ev'][:n_acc], dtype=np.float64).tolist()
+                    lo_ = 0
+                    for k_ in range(n_acc):
+                        rounds.append(dict(i=int(acc_l[k_]), cols=flat_cols[lo_:ends[k_]],
+                                           stream=state['calls'] + int(calls_l[k_]), head=S.get('head'),
+                                           gibbs_after=state['gibbs'] + int(calls_l[k_]),
+                                           ev_dev=float(ev_l[k_]), icpt_used=state['icpt']))
+                        lo_ = ends[k_]
                 state['calls'] += r['tested']
                 state['gibbs'] += r['tested']
                 state['killed'] = state['killed'] + [int(cand_cols[int(i)]) for i in r['acc']]

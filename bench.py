@@ -436,7 +436,7 @@ def main():
     # DRAM traffic per launch from the committed `ncu --set full` capture of this same command (tools/ncu_traffic.py
     # over the .ncu-rep of one cfg4 fit); a number taken under the profiler is evidence, not a timing
     traffic, traffic_src = {}, None
-    for name in ('r02_ncu_traffic.json', 'r01_ncu_traffic.json'):      # newest capture first (tools/gpu_final_r2.sh)
+    for name in ('r02_ncu_traffic.json', 'r01_ncu_traffic.json'):      # newest capture first (tools/gpurun/gpu_final_r2.sh)
         try:
             with open(os.path.join(ROOT, 'profiles', name)) as f:
                 traffic = json.load(f)

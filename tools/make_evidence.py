@@ -1,4 +1,4 @@
-"""Turn the raw outputs of tools/gpu_final_r4.sh (gpurun_out/<prefix>_*) into the committed evidence under profiles/:
+"""Turn the raw outputs of tools/gpurun/gpu_final_r4.sh (gpurun_out/<prefix>_*) into the committed evidence under profiles/:
 launch list summary, per-launch DRAM traffic table + JSON (what bench.py's roofline.traffic quotes, with the commit hash),
 `ncu --set full` summary of the Gram capture, pytest / smoke output.   usage: python tools/make_evidence.py f4 r02"""
 import csv
@@ -30,7 +30,7 @@ def main(prefix, rnd):
         launch_summary.main(os.path.join(go, prefix + '_launches.csv'))
     with open(os.path.join(pr, rnd + '_launches_final.txt'), 'w') as f:
         f.write('# ncu --metrics gpu__time_duration.sum --clock-control none of `python bench.py --steps 1 --warmup 1 --no-e2e '
-                '--no-cpu-baseline` (two cfg4 fits), commit %s (tools/gpu_final_r4.sh); times under ncu are serialised and '
+                '--no-cpu-baseline` (two cfg4 fits), commit %s (tools/gpurun/gpu_final_r4.sh); times under ncu are serialised and '
                 'cold-cache: shares, not absolutes\n' % commit)
         f.write(buf.getvalue())
     # traffic
@@ -49,7 +49,7 @@ def main(prefix, rnd):
     out = {'_commit': commit,
            '_command': 'ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none '
                        '-k regex:"basis_kernel|gram_kernel" python bench.py --steps 1 --warmup 0 --no-e2e --no-cpu-baseline '
-                       '(tools/gpu_final_r4.sh): the first cfg4 fit of the process'}
+                       '(tools/gpurun/gpu_final_r4.sh): the first cfg4 fit of the process'}
     with open(os.path.join(pr, rnd + '_ncu_traffic_launches.txt'), 'w') as f:
         f.write('# per-launch DRAM traffic of every K1 / K2 launch of one cfg4 fit (commit %s); times under ncu are cold-cache '
                 'and serialised\n' % commit)
@@ -81,7 +81,7 @@ def main(prefix, rnd):
         ncu_stalls.main(tmp)
     with open(os.path.join(pr, rnd + '_ncu_gram.txt'), 'w') as f:
         f.write('# ncu --set full --clock-control none of the 12th Gram launch of a cfg4 fit (C = 168 new columns, the widest '
-                'model), commit %s (tools/gpu_final_r4.sh)\n' % commit)
+                'model), commit %s (tools/gpurun/gpu_final_r4.sh)\n' % commit)
         f.write(buf.getvalue())
     with open(os.path.join(pr, rnd + '_pytest_gpu.txt'), 'w') as f:
         f.write('# python -c "import __graft_entry__ as g; g.smoke()" and python -m pytest tests -m gpu -q on a B200, commit %s\n' % commit)

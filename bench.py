@@ -162,6 +162,12 @@ def cpu_fit_complete(a, phis, rows, guard_s=600.0):
             raise _CpuBudget()
 
     fo.basis_columns = timed_basis
+    # all host threads for BLAS / LAPACK whatever the launcher exported: torchrun sets OMP_NUM_THREADS=1 for its workers,
+    # which would make this arm single-threaded at N > 1 and multi-threaded at N = 1
+    import scipy.linalg  # noqa: F401  (loads scipy's OpenBLAS so that the limit below covers it too)
+    import threadpoolctl
+    limits = threadpoolctl.threadpool_limits(limits=threads)
+    st['blas_threads'] = sorted({int(d['num_threads']) for d in threadpoolctl.threadpool_info()}) or [1]
     try:
         r = fo.fit(x, y, phis, kernel=c['kernel'], way3=c['way3'], draws=a.draws, burnin=a.draws, threads=threads,
                    on_gibbs=on_gibbs)
@@ -182,6 +188,7 @@ def cpu_fit_complete(a, phis, rows, guard_s=600.0):
     st['gram_flops'] = 2.0 * rows * st['p2sum']
     st['t_gram_est'] = st['gram_flops'] / rate
     st['gram_gflops_rate'] = rate / 1e9
+    limits.restore_original_limits()
     return st
 
 
@@ -208,6 +215,7 @@ def cpu_report(a, st, n_full, py_us):
     scale = n_full / st['rows']
     rep = {
         'rows': st['rows'], 'complete_fit': st['complete'], 'seconds': t, 'gibbs_calls': st['calls'],
+        'blas_threads': st.get('blas_threads'),
         'terms_selected': st.get('terms'), 'substages': st.get('substages'), 'max_model_width': st['pmax'],
         'cells_built': st['cells'], 'basis_seconds_c_helper': tb, 'cells_per_s_c_helper': cells_s,
         'gram_flops': st['gram_flops'], 'gram_seconds_estimate': st['t_gram_est'], 'gram_gflops_rate': st['gram_gflops_rate'],

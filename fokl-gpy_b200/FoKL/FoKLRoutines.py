@@ -768,6 +768,10 @@ class FoKL:
                 warnings.warn("If not calling 'clean' prior to 'fit' or within the argument of 'fit', then this is the "
                               "likely source of any subsequent errors. To troubleshoot, simply include 'clean=True' "
                               "within the argument of 'fit'.", category=UserWarning)
+                if np.ndim(data) != 2:
+                    # upstream goes on with the raw arguments and fails on `dtd[0][0]` of a scalar data'data (FR:1374-1378)
+                    raise IndexError("'data' must be an [n x 1] array when 'clean' was never performed on this model "
+                                     "(invalid index to scalar variable upstream); include 'clean=True'.")
                 inputs, data = self._format(inputs, data)
             self.inputs = inputs
             self.data = data

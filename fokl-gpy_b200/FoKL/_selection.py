@@ -659,6 +659,16 @@ def forward_select(engine, hy, m, n_phis, console=True, rng='philox', eager=Fals
                 return outcome
 
     # ---- phase D: drop the accepted kills (FR:1691-1695) and the bookkeeping of FR:1701-1721 ----------------------------
+    def same_model_bic(ev, n_killed, S, prev_ev):
+        """When EVERY new term of a substage is killed (FR:1673-1692) the surviving model is the previous substage's
+        model, and upstream its BIC is the previous value bit for bit (same X, same arithmetic: the reference's traces
+        hold exact ties only, never near-ties) -- a non-improvement under the strict `ev < min(evs)` of FR:1702.  Here
+        the same model's BIC may come from another route (tableau score, another eigensolver batch, a secular update)
+        and differ in the last bits, which would turn the tie into a coin toss: carry the previous value over."""
+        if prev_ev is not None and S['vm'] > 0 and n_killed == S['vm']:
+            return prev_ev
+        return ev
+
     def close_substage(S, outcome, compacted):
         """Returns True when the fit is finished.  compacted: the engine and `terms` already reflect outcome['killed']
         (the driver speculated on it)."""
@@ -675,7 +685,7 @@ def forward_select(engine, hy, m, n_phis, console=True, rng='philox', eager=Fals
                 terms_s = np.delete(terms_s, [c - 1 for c in killed], axis=0)
             terms = terms_s
         cnt['calls'], cnt['gibbs'] = outcome['calls'], outcome['gibbs']
-        ev = outcome['evmin']
+        ev = same_model_bic(outcome['evmin'], len(killed), S, evs[-1] if evs else None)
         last = (outcome['betas'], terms_s.copy())
         if console:
             print([S['ind'], float(ev)])
@@ -755,6 +765,9 @@ def forward_select(engine, hy, m, n_phis, console=True, rng='philox', eager=Fals
         spec = None
         if gen_s is not None and request is not None:
             _, todo, outlook = request
+            if outlook is not None:
+                prev_ev = carry['ev'] if carry is not None else (evs[-1] if evs else None)
+                outlook = dict(outlook, ev=same_model_bic(outlook['ev'], len(outlook['killed']), S, prev_ev))
             if pipeline and step is not None and outlook is not None and \
                     (pipeline == 'always' or not will_finish(outlook['ev'], None if carry is None else carry['ev'])):
                 # (the chains of s - 1 may still be reading the Gram as it was two compactions ago: Engine.compact

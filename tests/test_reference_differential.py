@@ -48,3 +48,50 @@ def test_host_api_outcomes_equal_the_reference(tmp_path):
         elif want['warnings'] != got['warnings']:
             bad.append((name, 'warnings', want['warnings'], got['warnings']))
     assert not bad, '\n'.join('%s [%s]\n  reference: %.300r\n  here:      %.300r' % b for b in bad)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_SRC), reason='the reference is only present in the build container')
+def test_small_fits_with_unusual_hypers_equal_the_live_reference(tmp_path, monkeypatch):
+    """24 small whole fits (Bernoulli and cubic kernels, raw inputs, clean=True) with the hyper-parameters the golden fixtures do not
+    reach -- gimmie, aic, tolerance 1 / 5, loose / tight kill thresholds, strong / weak priors, hyper-parameters passed
+    to `fit`, odd draw counts, burnin = 0, minmax + pillow, a random train split, five inputs, way3 with two inputs (which
+    upstream cannot run: IndexError at FR:1725, and neither can this package) -- on the live unmodified reference and,
+    through the public API in parity mode, on the CPU stand-in engine: normalised inputs, b / btau, train split, term
+    matrix, BIC trace (1e-9) and the numpy RNG end state must be the reference's."""
+    sys.path.insert(0, os.path.join(ROOT, 'tests', 'diff'))
+    import fit_cases
+    from FoKL import FoKLRoutines as FR
+    from test_public_api_stand_in import StandInEngine
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(ROOT, 'oracle', '_stubs'), REF_SRC]))
+    out = str(tmp_path / 'ref_fits.pkl')
+    r = subprocess.run([sys.executable, os.path.join(ROOT, 'tests', 'diff', 'fit_cases.py'), out], env=env,
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-3000:]
+    with open(out, 'rb') as f:
+        ref = pickle.load(f)
+    assert ref['file'].startswith(REF_SRC)
+    eng = StandInEngine()
+    monkeypatch.setattr(FR, '_engine', lambda device=None: eng)
+    monkeypatch.setitem(FR.B200_CONFIG, 'rng', 'numpy')
+    bad = []
+    for name in fit_cases.CASES:
+        want, got = ref['fits'][name], fit_cases.run_case(FR, name)
+        if 'raised' in want or 'raised' in got:          # a fit the reference cannot finish fails here in the same way
+            if want.get('raised') != got.get('raised'):
+                bad.append((name, 'raised', want.get('raised'), got.get('raised')))
+            continue
+        for key in ('inputs', 'data', 'minmax', 'mtx'):
+            if not np.array_equal(want[key], got[key]):
+                bad.append((name, key))
+        if (want['trainlog'] is None) != (got['trainlog'] is None) or (
+                want['trainlog'] is not None and not np.array_equal(want['trainlog'], got['trainlog'])):
+            bad.append((name, 'trainlog'))
+        if want['b'] != got['b'] or want['btau'] != got['btau']:
+            bad.append((name, 'b/btau'))
+        if want['evs'].shape != got['evs'].shape or not np.allclose(want['evs'], got['evs'], rtol=1e-9, atol=0):
+            bad.append((name, 'evs', want['evs'], got['evs']))
+        if want['betas_shape'] != got['betas_shape']:
+            bad.append((name, 'betas shape', want['betas_shape'], got['betas_shape']))
+        if want['digest'] != got['digest']:
+            bad.append((name, 'rng end state'))
+    assert not bad, bad

@@ -37,6 +37,11 @@ CASES = {
 }
 
 
+if __import__('os').environ.get('FOKL_DIFF_CASES'):          # exploratory runs: another case list, same format
+    with open(__import__('os').environ['FOKL_DIFF_CASES'], 'rb') as _f:
+        CASES = pickle.load(_f)
+
+
 def cubic_phis():
     import os
     here = os.path.dirname(os.path.abspath(__file__))

@@ -401,6 +401,128 @@ def cases():
     def process_kwargs_bad_default_raises(FR, rng):
         return FR._process_kwargs(3, {'b': 3})
 
+    # ---- evaluate / coverage3 on a hand-made model (FR:851-1200); on this package the device product is replaced ----
+    def _fitted(FR, rng, kernel=1, m=2, rows=60):
+        if hasattr(FR, 'eng_predict'):                 # this package: numpy stand-in for K1 + fokl_predict_draws
+            import fokl_oracle as fo
+
+            def predict(eng, phis, kern, normputs, terms, betas_sel):
+                k = fo.CUBIC if kern == 'Cubic Splines' else fo.BERNOULLI
+                x = np.asarray(normputs, dtype=np.float64)
+                X = np.hstack([np.ones((x.shape[0], 1)), fo.basis_columns(x, np.asarray(terms, dtype=np.int64), phis, k)])
+                return X @ np.asarray(betas_sel, dtype=np.float64).T
+            FR.eng_predict = predict
+            FR._engine = lambda device=None: None
+        model = _model(FR, draws=50)
+        x = rng.random((25, m))
+        model.clean(x * 4 - 1, rng.standard_normal(25), _setattr=True)
+        model.mtx = np.array([[1, 0], [0, 2], [1, 1], [3, 0]], dtype=np.float64)[:, :m]
+        model.betas = rng.standard_normal((rows, 5))
+        return model
+
+    def _pred(out):
+        if isinstance(out, tuple):
+            return [np.asarray(o).tolist() if not isinstance(o, list) else o for o in out]
+        return np.asarray(out).tolist()
+
+    @case
+    def evaluate_defaults(FR, rng):
+        np.random.seed(3)
+        m = _fitted(FR, rng)
+        return _pred(m.evaluate()), np.asarray(m.setnos).tolist()
+
+    @case
+    def evaluate_bounds_and_draws(FR, rng):
+        np.random.seed(4)
+        m = _fitted(FR, rng)
+        return _pred(m.evaluate(m.inputs, draws=45, ReturnBounds=1)), _pred(m.evaluate(m.inputs, draws=45, ReturnBounds='yes'))
+
+    @case
+    def evaluate_few_draws_with_bounds_warns(FR, rng):
+        np.random.seed(5)
+        m = _fitted(FR, rng)
+        m.UserWarnings = True
+        return _pred(m.evaluate(m.inputs, draws=45, ReturnBounds=0)), _pred(m.evaluate(rng.random((4, 2)), draws=45))
+
+    @case
+    def evaluate_one_draw(FR, rng):
+        np.random.seed(6)
+        m = _fitted(FR, rng)
+        return _pred(m.evaluate(m.inputs, draws=1))
+
+    @case
+    def evaluate_raw_inputs_clean(FR, rng):
+        np.random.seed(7)
+        m = _fitted(FR, rng)
+        return _pred(m.evaluate(rng.random((6, 2)) * 4 - 1, clean=True)), _pred(m.evaluate(rng.random(2) * 4 - 1, clean=True,
+                                                                                           SingleInstance=True))
+
+    @case
+    def evaluate_clean_on_default_inputs_warns(FR, rng):
+        np.random.seed(8)
+        m = _fitted(FR, rng)
+        return _pred(m.evaluate(clean=True))
+
+    @case
+    def evaluate_user_betas_and_mtx(FR, rng):
+        np.random.seed(9)
+        m = _fitted(FR, rng)
+        b = rng.standard_normal((70, 3))
+        return _pred(m.evaluate(rng.random((5, 2)), betas=b, mtx=[[1, 0], [0, 1]], draws=50))
+
+    @case
+    def evaluate_mtx_single_row(FR, rng):
+        np.random.seed(10)
+        m = _fitted(FR, rng)
+        return _pred(m.evaluate(rng.random((5, 2)), betas=rng.standard_normal((60, 2)), mtx=[2, 1]))
+
+    @case
+    def evaluate_one_input_mtx_int(FR, rng):
+        np.random.seed(11)
+        m = _fitted(FR, rng, m=1)
+        return _pred(m.evaluate(rng.random((5, 1)), betas=rng.standard_normal((60, 2)), mtx=3))
+
+    @case
+    def evaluate_out_of_range_inputs(FR, rng):
+        np.random.seed(12)
+        m = _fitted(FR, rng)
+        return _pred(m.evaluate(np.array([[1.5, 0.2], [-0.1, 0.5]])))
+
+    @case
+    def evaluate_too_many_draws_raises(FR, rng):
+        m = _fitted(FR, rng)
+        return m.evaluate(m.inputs, betas=m.betas[:20], draws=30)
+
+    @case
+    def coverage3_defaults(FR, rng):
+        np.random.seed(13)
+        m = _fitted(FR, rng)
+        return _pred(m.coverage3())
+
+    @case
+    def coverage3_no_bounds(FR, rng):
+        np.random.seed(14)
+        m = _fitted(FR, rng)
+        return _pred(m.coverage3(ReturnBounds=False, draws=30))
+
+    @case
+    def coverage3_inputs_without_data_warns(FR, rng):
+        np.random.seed(15)
+        m = _fitted(FR, rng)
+        m.UserWarnings = True
+        return _pred(m.coverage3(inputs=rng.random((7, 2))))
+
+    @case
+    def coverage3_user_inputs_and_data(FR, rng):
+        np.random.seed(16)
+        m = _fitted(FR, rng)
+        return _pred(m.coverage3(inputs=rng.random((7, 2)), data=rng.standard_normal(7), draws=40))
+
+    @case
+    def coverage3_unknown_keyword_raises(FR, rng):
+        m = _fitted(FR, rng)
+        return m.coverage3(colour='red')
+
     return c
 
 

@@ -1,5 +1,6 @@
-"""Differential test of the host-only API: ~40 calls (`clean` with every keyword and input container, train split,
-`evaluate_basis`, constructor / `clear` / `save` / `load`, the error paths) run on the UNMODIFIED reference and on this
+"""Differential test of the host-only API: ~70 calls (`clean` with every keyword and input container, train split,
+`evaluate_basis`, constructor / `clear` / `save` / `load`, `evaluate` / `coverage3` on a hand-made model with the device
+product replaced by numpy, the error paths) run on the UNMODIFIED reference and on this
 package, outcome by outcome -- returned values bit-identical, same attributes, same exception type, same warning
 texts.  The reference lives only in the build container (/root/reference); elsewhere the test is skipped."""
 import os
@@ -24,26 +25,33 @@ def _run(pythonpath, out):
         return pickle.load(f)
 
 
-def _same(a, b):
+def _same(a, b, tol=0.0):
     if isinstance(a, (list, tuple)) and isinstance(b, (list, tuple)):
-        return len(a) == len(b) and all(_same(u, v) for u, v in zip(a, b))
+        return len(a) == len(b) and all(_same(u, v, tol) for u, v in zip(a, b))
     if isinstance(a, dict) and isinstance(b, dict):
-        return a.keys() == b.keys() and all(_same(a[k], b[k]) for k in a)
+        return a.keys() == b.keys() and all(_same(a[k], b[k], tol) for k in a)
     if isinstance(a, float) and isinstance(b, float):
-        return a == b or (np.isnan(a) and np.isnan(b))
+        return a == b or (np.isnan(a) and np.isnan(b)) or abs(a - b) <= tol * max(1.0, abs(a), abs(b))
     return type(a) is type(b) and a == b
+
+
+def _tolerance(name):
+    """Predictions are a sum over the model's columns (FR:950-968): another summation order moves the last bits, and the
+    device product itself is held to 1e-9 by the `-m gpu` tests.  Everything else must be bit-identical."""
+    predicts = name.startswith(('evaluate_', 'coverage3_')) and not name.startswith('evaluate_basis')
+    return 1e-12 if predicts else 0.0
 
 
 @pytest.mark.skipif(not os.path.isdir(REF_SRC), reason='the reference is only present in the build container')
 def test_host_api_outcomes_equal_the_reference(tmp_path):
     ref = _run([os.path.join(ROOT, 'oracle', '_stubs'), REF_SRC], str(tmp_path / 'ref.pkl'))
-    mine = _run([os.path.join(ROOT, 'fokl-gpy_b200')], str(tmp_path / 'mine.pkl'))
+    mine = _run([os.path.join(ROOT, 'fokl-gpy_b200'), os.path.join(ROOT, 'oracle')], str(tmp_path / 'mine.pkl'))
     assert ref['file'].startswith(REF_SRC) and mine['file'].startswith(ROOT)
-    assert ref['outcomes'].keys() == mine['outcomes'].keys() and len(ref['outcomes']) >= 40
+    assert ref['outcomes'].keys() == mine['outcomes'].keys() and len(ref['outcomes']) >= 70
     bad = []
     for name, want in ref['outcomes'].items():
         got = mine['outcomes'][name]
-        if not _same(want['result'], got['result']):
+        if not _same(want['result'], got['result'], _tolerance(name)):
             bad.append((name, 'result', want['result'], got['result']))
         elif want['warnings'] != got['warnings']:
             bad.append((name, 'warnings', want['warnings'], got['warnings']))

@@ -970,28 +970,13 @@ class FoKL:
                     d_rows.append(dr)
         dy = np.zeros([N, M, 2, draws])
         bsel = np.ascontiguousarray(betas[-draws:, :], dtype=np.float64)
+        if t_rows and bsel.shape[0] != draws:
+            # upstream fails here as well: `betas[-draws:, b + 1] * phi` does not broadcast into dy's draws axis (FR:789)
+            raise ValueError(f"operands could not be broadcast together with shapes ({draws},) ({bsel.shape[0]},): "
+                             f"'betas' holds fewer than draws={draws} rows.")
         if t_rows:
-            import torch
-            eng = _engine()
-            eng.set_phis(phis, kernel)
-            x64 = np.ascontiguousarray(inputs, dtype=np.float64)
-            ds = eng.upload(x64, np.zeros(N))
-            t16 = np.ascontiguousarray(np.concatenate(t_rows, axis=0), dtype=np.int16)
-            d8 = np.ascontiguousarray(np.concatenate(d_rows, axis=0), dtype=np.uint8)
-            dv = np.ascontiguousarray(divisors, dtype=np.float64)
-            X = torch.empty((t16.shape[0], ds.ldx), dtype=torch.float64, device=eng.device)
-            eng._ck(eng.lib.fokl_basis_build_deriv(eng.ctx, eng.kernel_id, ds.x.data_ptr(), N, ds.ldx, M,
-                                                   t16.ctypes.data, d8.ctypes.data, dv.ctypes.data, t16.shape[0],
-                                                   X.data_ptr(), ds.ldx))
-            eng.synchronize()       # surfaces the out-of-range flag (inputs outside [0, 1]) as ValueError
-            for m, di, idx, off in pairs:
-                if not len(idx):
-                    continue
-                b = torch.from_numpy(np.ascontiguousarray(bsel[:, idx + 1])).to(eng.device)
-                out = torch.empty((N, draws), dtype=torch.float64, device=eng.device)
-                eng._ck(eng.lib.fokl_predict_draws(eng.ctx, X[off].data_ptr(), ds.ldx, N, len(idx), b.data_ptr(), draws,
-                                                   out.data_ptr()))
-                dy[:, m, di, :] = out.cpu().numpy()
+            eng_derivative_draws(_engine(), phis, kernel, inputs, np.concatenate(t_rows, axis=0),
+                                 np.concatenate(d_rows, axis=0), divisors, pairs, bsel, dy)
 
         if not current['IndividualDraws'] and draws > 1:
             dy = np.mean(dy, axis=3)[:, :, :, np.newaxis]
@@ -1067,6 +1052,33 @@ class FoKL:
             pickle.dump(self, file)
         time.sleep(1)  # so that the next saved model is guaranteed a different default filename
         return filepath
+
+
+def eng_derivative_draws(eng, phis, kernel, inputs, term_rows, deriv_rows, divisors, pairs, bsel, dy):
+    """dy[:, m, di, :] = (derivative design columns of the terms idx that contain input m) @ bsel[:, idx + 1]' for every
+    (m, di, idx, off) of `pairs`, on the device: one fokl_basis_build_deriv over all rows of term_rows / deriv_rows (the
+    columns of a pair start at row `off`), one fokl_predict_draws per pair (FR:727-795)."""
+    import torch
+    N, M, draws = np.shape(inputs)[0], np.shape(term_rows)[1], dy.shape[3]
+    eng.set_phis(phis, kernel)
+    x64 = np.ascontiguousarray(inputs, dtype=np.float64)
+    ds = eng.upload(x64, np.zeros(N))
+    t16 = np.ascontiguousarray(term_rows, dtype=np.int16)
+    d8 = np.ascontiguousarray(deriv_rows, dtype=np.uint8)
+    dv = np.ascontiguousarray(divisors, dtype=np.float64)
+    X = torch.empty((t16.shape[0], ds.ldx), dtype=torch.float64, device=eng.device)
+    eng._ck(eng.lib.fokl_basis_build_deriv(eng.ctx, eng.kernel_id, ds.x.data_ptr(), N, ds.ldx, M,
+                                           t16.ctypes.data, d8.ctypes.data, dv.ctypes.data, t16.shape[0],
+                                           X.data_ptr(), ds.ldx))
+    eng.synchronize()       # surfaces the out-of-range flag (inputs outside [0, 1]) as ValueError
+    for m, di, idx, off in pairs:
+        if not len(idx):
+            continue
+        b = torch.from_numpy(np.ascontiguousarray(bsel[:, idx + 1])).to(eng.device)
+        out = torch.empty((N, draws), dtype=torch.float64, device=eng.device)
+        eng._ck(eng.lib.fokl_predict_draws(eng.ctx, X[off].data_ptr(), ds.ldx, N, len(idx), b.data_ptr(), draws,
+                                           out.data_ptr()))
+        dy[:, m, di, :] = out.cpu().numpy()
 
 
 def eng_predict(eng, phis, kernel, normputs, terms, betas_sel):

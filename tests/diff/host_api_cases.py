@@ -523,6 +523,145 @@ def cases():
         m = _fitted(FR, rng)
         return m.coverage3(colour='red')
 
+    # ---- bss_derivatives (FR:594-805) on a hand-made model; on this package through the host "device" -----------------
+    def _deriv_model(FR, rng, kernel=1, m=3):
+        if hasattr(FR, 'eng_derivative_draws'):
+            from fake_device import FakeDeviceEngine
+            eng = FakeDeviceEngine()
+            FR._engine = lambda device=None: eng
+        model = _model(FR, draws=5) if kernel == 1 else FR.FoKL(phis=_cubic(), UserWarnings=False, ConsoleOutput=False, draws=5)
+        x = rng.random((11, m))
+        x[0, 0], x[1, m - 1] = 0.0, 1.0
+        mtx = np.array([[1, 0, 0], [0, 2, 0], [0, 0, 3], [1, 1, 0], [2, 0, 1], [1, 2, 1]], dtype=np.float64)[:, :m]
+        mtx = mtx[np.any(mtx != 0, axis=1)]
+        betas = rng.standard_normal((7, mtx.shape[0] + 1))
+        minmax = [[-1.0, 3.0], [0.0, 1.0], [10.0, 10.7]][:m]
+        model.mtx, model.minmax, model.betas, model.inputs = mtx, minmax, betas, x
+        return model, dict(inputs=x, betas=betas, mtx=mtx, minmax=minmax, draws=5)
+
+    def _cubic():
+        import os
+        import spline_table
+        here = os.path.dirname(os.path.abspath(__file__))
+        return spline_table.to_phis(np.load(os.path.join(here, '..', 'golden', 'phis_cubic_48.npy')))
+
+    def _arr(out):
+        if out is None:
+            return None
+        if isinstance(out, tuple):
+            return [np.asarray(o).tolist() for o in out]
+        return np.asarray(out).tolist()
+
+    @case
+    def derivs_defaults_from_attributes(FR, rng):
+        m, kw = _deriv_model(FR, rng)
+        return _arr(m.bss_derivatives())
+
+    @case
+    def derivs_d1_index_d2_true(FR, rng):
+        m, kw = _deriv_model(FR, rng)
+        return _arr(m.bss_derivatives(d1=1, d2=True, **kw))
+
+    @case
+    def derivs_d1_strings(FR, rng):
+        m, kw = _deriv_model(FR, rng)
+        return _arr(m.bss_derivatives(d1='on', d2='off', **kw)), _arr(m.bss_derivatives(d1='off', d2='on', **kw))
+
+    @case
+    def derivs_list_of_one(FR, rng):
+        m, kw = _deriv_model(FR, rng)
+        return _arr(m.bss_derivatives(d1=[2], d2=[0], **kw))
+
+    @case
+    def derivs_bad_list_length_raises(FR, rng):
+        m, kw = _deriv_model(FR, rng)
+        return m.bss_derivatives(d1=[1, 0], **kw)
+
+    @case
+    def derivs_bad_type_raises(FR, rng):
+        m, kw = _deriv_model(FR, rng)
+        return m.bss_derivatives(d1=1.5, **kw)
+
+    @case
+    def derivs_none_requested_warns(FR, rng):
+        m, kw = _deriv_model(FR, rng)
+        m.UserWarnings = True
+        return _arr(m.bss_derivatives(d1=False, d2=False, **kw))
+
+    @case
+    def derivs_betas_transposed_and_list(FR, rng):
+        m, kw = _deriv_model(FR, rng)
+        kw['betas'] = kw['betas'].T.tolist()
+        return _arr(m.bss_derivatives(**kw))
+
+    @case
+    def derivs_betas_wrong_shape_raises(FR, rng):
+        m, kw = _deriv_model(FR, rng)
+        kw['betas'] = kw['betas'][:, :3]
+        return m.bss_derivatives(**kw)
+
+    @case
+    def derivs_individual_draws_full_array(FR, rng):
+        m, kw = _deriv_model(FR, rng)
+        return _arr(m.bss_derivatives(d1=True, d2=[1, 0, 1], IndividualDraws='yes', ReturnFullArray=1, **kw))
+
+    @case
+    def derivs_one_draw(FR, rng):
+        m, kw = _deriv_model(FR, rng)
+        kw['draws'] = 1
+        return _arr(m.bss_derivatives(IndividualDraws=True, **kw))
+
+    @case
+    def derivs_one_input_vector(FR, rng):
+        m, kw = _deriv_model(FR, rng, m=1)
+        kw['inputs'] = kw['inputs'][:, 0]
+        kw['minmax'] = [-1.0, 3.0]
+        return _arr(m.bss_derivatives(d2=0, **kw))
+
+    @case
+    def derivs_mtx_int(FR, rng):
+        m, kw = _deriv_model(FR, rng, m=1)
+        kw['mtx'], kw['betas'] = 2, kw['betas'][:, :2]
+        return _arr(m.bss_derivatives(**kw))
+
+    @case
+    def derivs_return_basis(FR, rng):
+        m, kw = _deriv_model(FR, rng)
+        return _arr(m.bss_derivatives(d1=[0, 1, 0], ReturnBasis=True, **kw))
+
+    @case
+    def derivs_cubic_kernel(FR, rng):
+        m, kw = _deriv_model(FR, rng, kernel=0)
+        return _arr(m.bss_derivatives(d1=True, d2=True, **kw))
+
+    @case
+    def derivs_cubic_return_basis(FR, rng):
+        m, kw = _deriv_model(FR, rng, kernel=0)
+        return _arr(m.bss_derivatives(d1=2, ReturnBasis=True, **kw))
+
+    @case
+    def derivs_kernel_by_index(FR, rng):
+        m, kw = _deriv_model(FR, rng)
+        return _arr(m.bss_derivatives(kernel=1, **kw))
+
+    @case
+    def derivs_unsupported_kernel_raises(FR, rng):
+        m, kw = _deriv_model(FR, rng)
+        return m.bss_derivatives(kernel='Wavelets', **kw)
+
+    @case
+    def derivs_inputs_outside_unit_interval_warn(FR, rng):
+        m, kw = _deriv_model(FR, rng)
+        m.UserWarnings = True
+        kw['inputs'] = kw['inputs'] * 1.0
+        kw['inputs'][3, 1] = 1.0 + 1e-9
+        return _arr(m.bss_derivatives(**kw))
+
+    @case
+    def derivs_unknown_keyword_raises(FR, rng):
+        m, kw = _deriv_model(FR, rng)
+        return m.bss_derivatives(order=2, **kw)
+
     return c
 
 

@@ -38,19 +38,35 @@ def _same(a, b, tol=0.0):
 def _tolerance(name):
     """Predictions are a sum over the model's columns (FR:950-968): another summation order moves the last bits, and the
     device product itself is held to 1e-9 by the `-m gpu` tests.  Everything else must be bit-identical."""
-    predicts = name.startswith(('evaluate_', 'coverage3_')) and not name.startswith('evaluate_basis')
+    predicts = name.startswith(('evaluate_', 'coverage3_', 'derivs_')) and not name.startswith('evaluate_basis')
     return 1e-12 if predicts else 0.0
+
+
+# Deliberate, documented departures: calls on which upstream dies of an internal bug and this package answers.
+DEPARTURES = {
+    # FR:728-777 branch on `kernel == self.kernels[0] / [1]` only: an integer kernel (accepted everywhere else, FR:829-832)
+    # or an unknown name leaves `basis` undefined -> UnboundLocalError.  Here the index is resolved and an unknown kernel
+    # raises the ValueError that `evaluate_basis` raises for it.
+    'derivs_kernel_by_index': (('raised', 'UnboundLocalError'), 'ok'),
+    'derivs_unsupported_kernel_raises': (('raised', 'UnboundLocalError'), ('raised', 'ValueError')),
+}
 
 
 @pytest.mark.skipif(not os.path.isdir(REF_SRC), reason='the reference is only present in the build container')
 def test_host_api_outcomes_equal_the_reference(tmp_path):
-    ref = _run([os.path.join(ROOT, 'oracle', '_stubs'), REF_SRC], str(tmp_path / 'ref.pkl'))
-    mine = _run([os.path.join(ROOT, 'fokl-gpy_b200'), os.path.join(ROOT, 'oracle')], str(tmp_path / 'mine.pkl'))
+    ref = _run([os.path.join(ROOT, 'oracle', '_stubs'), REF_SRC, os.path.join(ROOT, 'oracle')], str(tmp_path / 'ref.pkl'))
+    mine = _run([os.path.join(ROOT, 'fokl-gpy_b200'), os.path.join(ROOT, 'oracle'), os.path.join(ROOT, 'tests')],
+                str(tmp_path / 'mine.pkl'))
     assert ref['file'].startswith(REF_SRC) and mine['file'].startswith(ROOT)
-    assert ref['outcomes'].keys() == mine['outcomes'].keys() and len(ref['outcomes']) >= 70
+    assert ref['outcomes'].keys() == mine['outcomes'].keys() and len(ref['outcomes']) >= 90
     bad = []
     for name, want in ref['outcomes'].items():
         got = mine['outcomes'][name]
+        if name in DEPARTURES:
+            ref_side, my_side = DEPARTURES[name]
+            assert want['result'] == ref_side, (name, 'upstream changed', want['result'])
+            assert got['result'] == my_side or (my_side == 'ok' and got['result'][0] == 'ok'), (name, got['result'])
+            continue
         if not _same(want['result'], got['result'], _tolerance(name)):
             bad.append((name, 'result', want['result'], got['result']))
         elif want['warnings'] != got['warnings']:

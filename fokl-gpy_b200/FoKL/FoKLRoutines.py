@@ -14,7 +14,10 @@ Differences that are deliberate and documented:
   * `relats_in` with exclusions raises, as it does upstream (FR:1631 is broken);
   * `update=True` (fitupdate, FR:1850-2583) runs on the device too (FoKL/_update.py, csrc/update.cu);
   * `to_pyomo` is not built and raises (DESIGN.md section 7);
-    `bss_derivatives`, `evaluate` and `coverage3` run on the device like `fit`.
+    `bss_derivatives`, `evaluate` and `coverage3` run on the device like `fit`;
+  * `bss_derivatives(kernel=<int>)` resolves the index and an unknown kernel name raises ValueError -- upstream both die
+    of an UnboundLocalError (FR:728-777).  Every other host-side call is held to the live reference outcome by outcome
+    (values, exception types, warning texts) by tests/test_reference_differential.py.
 """
 import copy
 import math

@@ -159,3 +159,71 @@ def test_shards_are_independent_of_world_size():
                        for k in range(world)])
         assert np.array_equal(np.concatenate(xs), full_x)
         assert np.array_equal(np.concatenate(ys), full_y)
+
+
+def _public_api_worker(rank, world, port, out_dir):
+    import types
+
+    import torch.distributed as dist
+    for p in (os.path.join(ROOT, 'fokl-gpy_b200'), os.path.join(ROOT, 'oracle'), os.path.join(ROOT, 'tests'), ROOT):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        import spline_table
+        from FoKL import FoKLRoutines as FR
+        from mock_engine import MockEngine
+        from test_public_api_stand_in import StandInEngine
+        from test_selection_mock import synthetic
+
+        class ShardedStandIn(StandInEngine):
+            def begin_fit(self, ds):
+                MockEngine.__init__(self, ds.x, ds.y, self._phis_arg, self._kernel_arg, dist=dist)
+
+        eng = ShardedStandIn()
+        FR._engine = lambda device=None: eng
+        phis = spline_table.to_phis(np.load(os.path.join(ROOT, 'tests', 'golden', 'phis_cubic_48.npy')))
+        x, y = synthetic(333, 3, 12)
+        raw = 5.0 * x - 2.0                               # un-normalised: the bounds must come from all ranks
+        per = -(-len(y) // world)
+        lo, hi = rank * per, min((rank + 1) * per, len(y))
+        np.random.seed(70 + rank)
+        model = FR.FoKL(phis=phis, way3=True, draws=40, burnin=40, UserWarnings=False, ConsoleOutput=False)
+        betas, mtx, evs = model.fit(raw[lo:hi], y[lo:hi], clean=True)
+        np.savez(os.path.join(out_dir, 'api_rank%d.npz' % rank), betas=betas, mtx=mtx, evs=evs, b=model.b, btau=model.btau,
+                 minmax=np.asarray(model.minmax), rows=np.asarray(model.inputs).shape[0], n=eng.n_global)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_fit_through_the_public_api(tmp_path, phis_cubic, monkeypatch):
+    """`FoKL.fit(raw_row_shard, data_shard, clean=True)` on two gloo ranks (stand-in engine): `clean` normalises every
+    shard with the GLOBAL per-column bounds (MIN / MAX allreduce), the b / btau defaults come from the all-reduced data
+    moments (FR:1322-1348 on the whole dataset), and both ranks return the single-rank fit of the whole dataset."""
+    import torch.multiprocessing as mp
+    from FoKL import FoKLRoutines as FR
+    from test_public_api_stand_in import StandInEngine
+    from test_selection_mock import synthetic
+    world = 2
+    port = 33500 + (os.getpid() % 2000)
+    mp.spawn(_public_api_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    r = [np.load(os.path.join(str(tmp_path), 'api_rank%d.npz' % k)) for k in range(world)]
+    x, y = synthetic(333, 3, 12)
+    raw = 5.0 * x - 2.0
+    eng = StandInEngine()
+    monkeypatch.setattr(FR, '_engine', lambda device=None: eng)
+    np.random.seed(70)
+    model = FR.FoKL(phis=phis_cubic, way3=True, draws=40, burnin=40, UserWarnings=False, ConsoleOutput=False)
+    betas, mtx, evs = model.fit(raw, y, clean=True)
+    assert int(r[0]['rows']) + int(r[1]['rows']) == 333 and int(r[0]['n']) == int(r[1]['n']) == 333
+    for k in range(world):
+        assert np.array_equal(r[k]['minmax'], np.asarray(model.minmax))
+        assert np.isclose(float(r[k]['b']), model.b, rtol=1e-12) and np.isclose(float(r[k]['btau']), model.btau, rtol=1e-12)
+        assert np.array_equal(r[k]['mtx'], mtx)
+        assert np.allclose(r[k]['evs'], evs, rtol=1e-9, atol=0)
+        assert r[k]['betas'].shape == betas.shape
+    for key in ('betas', 'mtx', 'evs', 'b', 'btau'):
+        assert np.array_equal(r[0][key], r[1][key]), key

@@ -118,6 +118,15 @@ def _process_kwargs(default, user):
     raise ValueError("Input 'default' must be a dictionary or list.")
 
 
+def _set_attributes(self, attrs):
+    """Set the items of the dictionary `attrs` as attributes of `self` (FR:93-100)."""
+    if isinstance(attrs, dict):
+        for key, value in attrs.items():
+            setattr(self, key, value)
+    else:
+        warnings.warn("Input must be a Python dictionary.")
+
+
 def _merge_dicts(d1, d2):
     d = d1.copy()
     d.update(d2)

@@ -70,6 +70,15 @@ def sp500(**kwargs):
     for kw in kwargs:
         if kw not in ('Smooth', 'Save'):
             raise ValueError(f"Unexpected keyword argument: {kw}")
+    smooth, save = kwargs.get('Smooth', 0), kwargs.get('Save', 0)
+    if save == 1 and smooth == 0:
+        warnings.warn("The spline coefficients were not save because they were not requested to be smoothed.",
+                      category=UserWarning)
+    if smooth:
+        # GK:10-218 is a development tool that re-smooths the end pieces of the (already smoothed) shipped table; it is
+        # not on the fit path (SURVEY 8a row a1 = the loader, GK:245-255) and is not rebuilt here
+        raise NotImplementedError("sp500(Smooth=1) (getKernels.smooth_coefficients, a development option upstream) is "
+                                  "not part of the B200 build; the table is returned as stored with Smooth=0.")
     upstream = os.path.join(_KDIR, UPSTREAM_SPLINE_FILE)
     if os.path.exists(upstream):
         raw = np.loadtxt(upstream, delimiter=',', dtype=np.double)
@@ -90,9 +99,30 @@ def sp500(**kwargs):
     return _to_phis(table)
 
 
-def bernoulli(file='orthogonal_Bn_scaled.npy'):
-    """Return coefficients of the scaled orthonormal Bernoulli polynomials (20 polynomials)."""
+def smooth_coefficients(phis):
+    """Upstream's end-piece smoothing of a spline table (GK:10-218): a development tool, not rebuilt (see sp500)."""
+    raise NotImplementedError("getKernels.smooth_coefficients is a development option upstream and is not part of the "
+                              "B200 build.")
+
+
+def bss_anova(n=500):
+    """Development helper kept for interface parity (GK:270-305): writes the square roots of the eigenvalues of the
+    n x n BSS-ANOVA kernel matrix, largest first, to 'BSS-ANOVA__sqrt-eigvals__K-500x500.txt' in the working directory
+    (upstream used them to scale the orthonormal Bernoulli polynomials) and returns None."""
+    x = np.linspace(0.0, 1.0, n)
+    xi, xj = np.meshgrid(x, x)
+    k = _b1(xi) * _b1(xj) + _b2(xi) * _b2(xj) - _b4(np.abs(xi - xj)) / 24
+    lam = np.linalg.eigvalsh(k)
+    np.savetxt("BSS-ANOVA__sqrt-eigvals__K-500x500.txt", np.flip(np.sqrt(lam)), delimiter=",")
+
+
+def bernoulli(file='orthogonal_Bn_scaled.txt'):
+    """Return coefficients of the scaled orthonormal Bernoulli polynomials (20 polynomials; GK:308-326).  The table ships
+    as kernels/orthogonal_Bn_scaled.npy -- the float64 values `np.loadtxt` reads from upstream's text file -- and is used
+    when the named text file is not present next to it."""
     path = os.path.join(_KDIR, file)
+    if not os.path.exists(path) and os.path.exists(os.path.splitext(path)[0] + '.npy'):
+        path = os.path.splitext(path)[0] + '.npy'
     if path.endswith('.npy'):
         coeffs = np.load(path)
     else:

@@ -662,6 +662,40 @@ def cases():
         m, kw = _deriv_model(FR, rng)
         return m.bss_derivatives(order=2, **kw)
 
+    # ---- getKernels / module helpers --------------------------------------------------------------------------------
+    @case
+    def getkernels_bernoulli_default_and_named(FR, rng):
+        from FoKL import getKernels
+        a, b = getKernels.bernoulli(), getKernels.bernoulli('orthogonal_Bn_scaled.txt')
+        return [list(map(float, r)) for r in a], [len(r) for r in b], a == b
+
+    @case
+    def getkernels_sp500_unknown_keyword_raises(FR, rng):
+        from FoKL import getKernels
+        return getKernels.sp500(Smoothing=1)
+
+    @case
+    def getkernels_bss_anova_writes_the_eigenvalue_file(FR, rng):
+        import os
+        import tempfile
+        from FoKL import getKernels
+        cwd = os.getcwd()
+        os.chdir(tempfile.mkdtemp())
+        try:
+            out = getKernels.bss_anova(n=60)
+            vals = np.loadtxt("BSS-ANOVA__sqrt-eigvals__K-500x500.txt", delimiter=",")
+        finally:
+            os.chdir(cwd)
+        return out, len(vals), [round(float(v), 9) for v in vals[:12]]
+
+    @case
+    def set_attributes_helper(FR, rng):
+        m = _model(FR)
+        FR._set_attributes(m, {'alpha': 1, 'beta': [2]})
+        m.UserWarnings = True
+        FR._set_attributes(m, ['not', 'a', 'dict'])
+        return m.alpha, m.beta
+
     return c
 
 

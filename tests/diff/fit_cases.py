@@ -2,6 +2,7 @@
 reference first on sys.path) and on this package (imported by tests/test_reference_differential.py, which runs them on
 the CPU stand-in engine).  TEST INFRASTRUCTURE."""
 import hashlib
+import os
 import pickle
 import sys
 
@@ -37,13 +38,12 @@ CASES = {
 }
 
 
-if __import__('os').environ.get('FOKL_DIFF_CASES'):          # exploratory runs: another case list, same format
-    with open(__import__('os').environ['FOKL_DIFF_CASES'], 'rb') as _f:
+if os.environ.get('FOKL_DIFF_CASES'):          # exploratory runs (tools/diff_fuzz.py): another case list, same format
+    with open(os.environ['FOKL_DIFF_CASES'], 'rb') as _f:
         CASES = pickle.load(_f)
 
 
 def cubic_phis():
-    import os
     here = os.path.dirname(os.path.abspath(__file__))
     sys.path.insert(0, os.path.join(here, '..', '..', 'oracle'))
     import spline_table

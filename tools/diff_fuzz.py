@@ -1,15 +1,15 @@
 """Exploration script (not part of the product; build container only): random small whole fits on the LIVE unmodified
 reference (/root/reference, subprocess) and, through this package's public API in parity mode, on the CPU stand-in engine
 (tests/mock_engine.py).  Reports every case whose normalised inputs, b / btau, term matrix, BIC trace (1e-9) or numpy RNG
-end state differ, with the width of the model at the first differing substage: a difference that starts at a substage
-whose model has p >= n columns is the reference's own 1 / Lamb noise on a singular Gram ("rank-deficient
-rounds are reported, not parity-checked"); anything earlier is a bug.
+end state differ, with the width and the conditioning of the model at the first differing substage.  A difference that
+starts where the model has p >= n columns, or where lambda_min / lambda_max of its Gram is below 1e-12, is the
+reference's own unclamped 1 / Lamb on a singular Gram (FR:1502; SURVEY 8d: "rank-deficient rounds are reported, not
+parity-checked"); anything earlier is a bug.
 
     python tools/diff_fuzz.py <seed> <n_cases>          # ~13 min for 60 cases on 8 cores
 
-Result of `python tools/diff_fuzz.py 1 60` at the end of round 2: 53 of 60 identical; the other 7 agree up to the first
-substage with p >= n (profiles/r02_diff_fuzz.txt).  The fixed list tests/diff/fit_cases.py (24 cases, all well posed) is
-what the test suite runs."""
+Results at the end of round 2 (profiles/r02_diff_fuzz.txt): 190 random fits, 175 identical, 15 part from the reference at
+a singular Gram, 0 bugs.  The fixed list tests/diff/fit_cases.py (24 cases, all well posed) is what the test suite runs."""
 import os
 import pickle
 import subprocess
@@ -81,15 +81,20 @@ def main():
     eng = StandInEngine()
     FR._engine = lambda device=None: eng
     FR.B200_CONFIG['rng'] = 'numpy'
-    real_select, widths = sel.forward_select, []
+    real_select, widths, rconds = sel.forward_select, [], []
 
     def select(*a, **k):
-        k['on_substage'] = lambda ind, ev, terms: widths.append(terms.shape[0] + 1)
+        def on_substage(ind, ev, terms):
+            widths.append(terms.shape[0] + 1)
+            w = np.linalg.eigvalsh(eng._G)                    # Gram of the model the substage ends with
+            rconds.append(float(w[0] / w[-1]))
+        k['on_substage'] = on_substage
         return real_select(*a, **k)
     sel.forward_select = select
     n_bad = n_sat = 0
     for name, cfg in fit_cases.CASES.items():
         del widths[:]
+        del rconds[:]
         want, got = ref[name], fit_cases.run_case(FR, name)
         why = []
         if 'raised' in want or 'raised' in got:
@@ -111,11 +116,14 @@ def main():
                     abs(got['evs'][k] - want['evs'][k]) <= 1e-9 * abs(want['evs'][k]):
                 k += 1
         n_rows = int(np.asarray(got.get('inputs', np.zeros((cfg[0], 1)))).shape[0])
-        saturated = k < len(widths) and widths[k] >= n_rows
+        # singular for the reference's unclamped 1 / Lamb (FR:1502): p >= n, or lambda_min / lambda_max of a model on the way
+        # there below 1e-12 (the substage's own candidates, which hold more columns, are worse conditioned still)
+        saturated = k < len(widths) and (widths[k] >= n_rows or min(rconds[max(0, k - 1):k + 1]) < 1e-12)
         n_sat += saturated
         n_bad += not saturated
         print('%s %s\n   differs in %s; BIC traces agree for %d substages; model width at the first differing one: %s of n = %d'
-              ' rows -> %s' % (name, cfg, why, k, widths[k] if k < len(widths) else '?', n_rows,
+              ' rows, lambda_min / lambda_max %.1e -> %s' % (name, cfg, why, k, widths[k] if k < len(widths) else '?', n_rows,
+                               rconds[k] if k < len(rconds) else float('nan'),
                                'singular Gram (not parity-checkable)' if saturated else 'BUG'), flush=True)
     print('cases %d: identical %d, differ from a saturated substage on %d, BUGS %d'
           % (len(fit_cases.CASES), len(fit_cases.CASES) - n_bad - n_sat, n_sat, n_bad))

@@ -119,3 +119,48 @@ def test_small_fits_with_unusual_hypers_equal_the_live_reference(tmp_path, monke
         if want['digest'] != got['digest']:
             bad.append((name, 'rng end state'))
     assert not bad, bad
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_SRC), reason='the reference is only present in the build container')
+def test_oracle_equals_the_live_reference_on_the_small_fits(tmp_path, phis_cubic, phis_bern):
+    """The checker itself: oracle/fokl_oracle.py `fit` on the reference's own cleaned train set and resolved
+    hyper-parameters, for the same 24 configurations -- term matrix, numpy RNG end state and returned draws identical,
+    BIC trace 1e-10 (same container, same BLAS: in practice bit for bit).  Widens the pin of tests/test_oracle_golden.py
+    (7 stored runs) to gimmie, aic, tolerance 1 - 5, kill thresholds, priors, odd draw counts, burnin 0, 1 - 5 inputs."""
+    sys.path.insert(0, os.path.join(ROOT, 'tests', 'diff'))
+    import fit_cases
+    import fokl_oracle as fo
+    from FoKL.FoKLRoutines import _str_to_bool
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(ROOT, 'oracle', '_stubs'), REF_SRC]))
+    out = str(tmp_path / 'ref_fits.pkl')
+    r = subprocess.run([sys.executable, os.path.join(ROOT, 'tests', 'diff', 'fit_cases.py'), out], env=env,
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-3000:]
+    with open(out, 'rb') as f:
+        ref = pickle.load(f)['fits']
+    checked = 0
+    for name, (n, m, seed, ckw, fkw) in fit_cases.CASES.items():
+        want = ref[name]
+        if 'raised' in want:
+            continue
+        hy = dict(a=4, atau=4, tolerance=3, burnin=30, draws=30, gimmie=False, way3=False, threshav=0.05, threshstda=0.5,
+                  threshstdb=2, aic=False)
+        hy.update({k: v for k, v in {**ckw, **fkw}.items() if k in hy})
+        for k in ('gimmie', 'way3', 'aic'):
+            hy[k] = _str_to_bool(hy[k])
+        cubic = bool(ckw.get('cubic'))
+        x, y = want['inputs'], want['data']      # (after `fit`, model.inputs / model.data are the TRAIN set, FR:1316-1317)
+        np.random.seed(seed)
+        if want['trainlog'] is not None:        # the reference drew the train split from the same stream first (FR:509-530)
+            from FoKL import FoKLRoutines as FR
+            FR.FoKL(kernel=1, UserWarnings=False).generate_trainlog(fkw['train'], len(want['trainlog']))
+        got = fo.fit(x, y, phis_cubic if cubic else phis_bern, kernel=fo.CUBIC if cubic else fo.BERNOULLI, b=want['b'],
+                     btau=want['btau'], **hy)
+        assert np.array_equal(got.mtx, want['mtx']), name
+        assert np.allclose(got.evs, want['evs'], rtol=1e-10, atol=0), name
+        assert fit_cases.digest() == want['digest'], name
+        assert got.betas.shape == want['betas_shape'], name
+        if np.array_equal(got.evs, want['evs']):
+            assert np.array_equal(got.betas, want['betas']), name
+        checked += 1
+    assert checked >= 23

@@ -128,7 +128,13 @@ class _Sampler:
         elif case == 2:
             # Sigma_old^-1 = L L',  L^-1 G L^-T = V D V',  T = L^-T V:  T'G T = D,  T' Sigma_old^-1 T = I
             sinv = self.prior['sinv']
-            L = torch.linalg.cholesky(0.5 * (sinv + sinv.t()))
+            try:
+                L = torch.linalg.cholesky(0.5 * (sinv + sinv.t()))
+            except torch.linalg.LinAlgError as exc:
+                # a prior covariance estimated from fewer draws than coefficients is singular: upstream's inv(Sigma_old)
+                # (FR:2171) is then inf / nan / indefinite and its `eigh` refuses it with this ValueError
+                raise ValueError("array must not contain infs or NaNs (the covariance of the previous draws is "
+                                 "singular: keep more draws than the model has coefficients)") from exc
             Li = torch.linalg.solve_triangular(L, torch.eye(p, dtype=torch.float64, device=e.device), upper=False)
             C = Li.mm(G).mm(Li.t())
             C = 0.5 * (C + C.t())

@@ -164,3 +164,47 @@ def test_oracle_equals_the_live_reference_on_the_small_fits(tmp_path, phis_cubic
             assert np.array_equal(got.betas, want['betas']), name
         checked += 1
     assert checked >= 23
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_SRC), reason='the reference is only present in the build container')
+def test_update_flows_equal_the_live_reference(tmp_path, monkeypatch):
+    """Five update flows (`update = True`; `clean` with a fixed minmax, `fit()`, next batch, `fit()` -- the way
+    examples/sigmoid/updateSig.py drives it) with both kernels, aic, gimmie, tolerance 1 / 2, on the live reference and
+    through the public API on the stand-in engine.  First fit (case 1 of FR:2060-2140): term matrix, evidence trace
+    (1e-6) and numpy RNG end state.  Second fit (cases 2 / 3, from the previous draws as prior): term matrix, `built`,
+    the returned types (np.matrix, as upstream) and the RNG end state -- i.e. every decision; the evidence values
+    themselves are maxima of a likelihood over the draws and agree within Monte-Carlo error only (tests/test_update.py).
+    A prior estimated from fewer draws than coefficients fails with ValueError on both sides."""
+    diff_dir = os.path.join(ROOT, 'tests', 'diff')
+    sys.path.insert(0, diff_dir)
+    import update_cases
+    from FoKL import FoKLRoutines as FR
+    from test_public_api_stand_in import StandInEngine
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(ROOT, 'oracle', '_stubs'), REF_SRC,
+                                                       os.path.join(ROOT, 'oracle'), diff_dir]))
+    out = str(tmp_path / 'ref_updates.pkl')
+    r = subprocess.run([sys.executable, os.path.join(diff_dir, 'update_cases.py'), out], env=env, capture_output=True,
+                       text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-3000:]
+    with open(out, 'rb') as f:
+        ref = pickle.load(f)
+    assert ref['file'].startswith(REF_SRC)
+    eng = StandInEngine()
+    monkeypatch.setattr(FR, '_engine', lambda device=None: eng)
+    monkeypatch.setitem(FR.B200_CONFIG, 'rng', 'numpy')
+    n_raised = 0
+    for name in update_cases.CASES:
+        want, got = ref['fits'][name], update_cases.run_case(FR, name)
+        assert len(want) == len(got), name
+        for f, (w, g) in enumerate(zip(want, got)):
+            if 'raised' in w or 'raised' in g:
+                assert w.get('raised') == g.get('raised'), (name, f, w.get('raised'), g.get('raised'))
+                n_raised += 1
+                continue
+            assert np.array_equal(w['mtx'], g['mtx']), (name, f)
+            assert w['built'] == g['built'] and w['betas_type'] == g['betas_type'] and w['betas_shape'] == g['betas_shape']
+            assert w['digest'] == g['digest'], (name, f)
+            assert w['evs'].shape == g['evs'].shape
+            if f == 0:
+                assert np.allclose(w['evs'], g['evs'], rtol=1e-6, atol=0), (name, w['evs'], g['evs'])
+    assert n_raised == 1

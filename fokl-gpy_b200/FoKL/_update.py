@@ -73,6 +73,8 @@ class _Sampler:
             mu_old, sigma_old = prior
             mu = np.asarray(mu_old, dtype=np.float64).reshape(-1)
             sinv = np.linalg.inv(np.asarray(sigma_old, dtype=np.float64))           # FR:2171, 2291
+            if not np.all(np.isfinite(sinv)):
+                raise ValueError("array must not contain infs or NaNs")             # what upstream's eigh says (FR:2296)
             self.prior = dict(p=len(mu), mu=self._dev(mu), sinv=self._dev(sinv), sinv_host=sinv)
 
     def _dev(self, a):

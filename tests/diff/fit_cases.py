@@ -35,6 +35,11 @@ CASES = {
     'cubic_gimmie_loose': (90, 2, 22, dict(cubic=True, gimmie=True, threshstda=0.2, threshav=0.3), dict()),
     'way3_m5': (130, 5, 23, dict(way3=True), dict()),
     'two_way_m5_tol2': (130, 5, 24, dict(tolerance=2), dict()),
+    # containers and call sequences of the public API
+    'inputs_as_list_of_columns': (90, 2, 25, dict(container='list'), dict()),
+    'pandas_frame_and_series': (90, 3, 26, dict(container='pandas'), dict()),
+    'refit_same_model_on_other_data': (80, 2, 27, dict(container='refit'), dict()),
+    'clean_first_then_fit_without_arguments': (80, 2, 28, dict(container='preclean'), dict(pillow=0.1)),
 }
 
 
@@ -72,10 +77,24 @@ def run_case(FR, name):
     x, y = data(n, m, seed)
     ckw = dict(dict(draws=30, burnin=30), **ckw)
     kern = dict(phis=cubic_phis()) if ckw.pop('cubic', False) else dict(kernel=1)
+    container = ckw.pop('container', None)
     np.random.seed(seed)
     model = FR.FoKL(UserWarnings=False, ConsoleOutput=False, **kern, **ckw)
     try:
-        betas, mtx, evs = model.fit(x, y, clean=True, **fkw)
+        if container == 'list':
+            betas, mtx, evs = model.fit([x[:, k] for k in range(m)], list(y), clean=True, **fkw)
+        elif container == 'pandas':
+            import pandas as pd
+            frame = pd.DataFrame({'c%d' % k: x[:, k] for k in range(m)})
+            betas, mtx, evs = model.fit(frame, pd.Series(y), clean=True, **fkw)
+        elif container == 'refit':
+            model.fit(x[:40], y[:40], clean=True, **fkw)
+            betas, mtx, evs = model.fit(x[40:], y[40:], clean=True, **fkw)
+        elif container == 'preclean':
+            model.clean(x, y, _setattr=True, **fkw)
+            betas, mtx, evs = model.fit()
+        else:
+            betas, mtx, evs = model.fit(x, y, clean=True, **fkw)
     except Exception as exc:  # noqa: BLE001 -- a fit the reference cannot finish: the exception type is the outcome
         return dict(raised=type(exc).__name__)
     return dict(betas_shape=tuple(betas.shape), mtx=np.asarray(mtx, dtype=np.float64), evs=np.asarray(evs, dtype=np.float64),

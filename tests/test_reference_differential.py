@@ -125,7 +125,7 @@ def test_small_fits_with_unusual_hypers_equal_the_live_reference(tmp_path, monke
 @pytest.mark.skipif(not os.path.isdir(REF_SRC), reason='the reference is only present in the build container')
 def test_oracle_equals_the_live_reference_on_the_small_fits(tmp_path, phis_cubic, phis_bern):
     """The checker itself: oracle/fokl_oracle.py `fit` on the reference's own cleaned train set and resolved
-    hyper-parameters, for the same 24 configurations -- term matrix, numpy RNG end state and returned draws identical,
+    hyper-parameters, for the same configurations -- term matrix, numpy RNG end state and returned draws identical,
     BIC trace 1e-10 (same container, same BLAS: in practice bit for bit).  Widens the pin of tests/test_oracle_golden.py
     (7 stored runs) to gimmie, aic, tolerance 1 - 5, kill thresholds, priors, odd draw counts, burnin 0, 1 - 5 inputs."""
     sys.path.insert(0, os.path.join(ROOT, 'tests', 'diff'))

@@ -9,7 +9,7 @@ parity-checked"); anything earlier is a bug.
     python tools/diff_fuzz.py <seed> <n_cases>          # ~13 min for 60 cases on 8 cores
 
 Results at the end of round 2 (profiles/r02_diff_fuzz.txt): 190 random fits, 175 identical, 15 part from the reference at
-a singular Gram, 0 bugs.  The fixed list tests/diff/fit_cases.py (24 cases, all well posed) is what the test suite runs."""
+a singular Gram, 0 bugs.  The fixed list tests/diff/fit_cases.py (28 cases, all well posed) is what the test suite runs."""
 import os
 import pickle
 import subprocess

@@ -136,3 +136,35 @@ def test_parity_mode_equals_the_oracle_fit(phis_cubic, n, m, seed, way3, aic):
     assert got['betas'].shape == full.shape
     if full.shape[1] < n // 3:       # the draws of a nearly saturated model (p ~ N) hinge on degenerate eigen-directions
         assert np.allclose(got['betas'], full, rtol=1e-7, atol=1e-7 * np.max(np.abs(full)))
+
+
+def test_the_host_loops_call_only_what_the_real_engine_defines():
+    """Guard against drift between tests/mock_engine.py and FoKL._engine.Engine: every `engine.<name>` the host loops
+    (FoKL/_selection.py, FoKL/_update.py, FoKL/FoKLRoutines.py) touch must exist on the real Engine (or be probed with hasattr / getattr there),
+    and the keyword names the loops pass must be parameters of the real method -- so a loop that runs on the stand-in
+    cannot be calling something the device engine does not have."""
+    import ast
+    import inspect
+    import os
+    from FoKL import FoKLRoutines, _engine, _selection, _update
+    real = _engine.Engine
+    init_src = inspect.getsource(real)
+    real_attrs = {n for n, _ in inspect.getmembers(real)} | set(__import__('re').findall(r'self\.([A-Za-z_]\w*)\s*=', init_src))
+    for mod in (_selection, _update, FoKLRoutines):
+        tree = ast.parse(inspect.getsource(mod))
+        src = inspect.getsource(mod)
+        for node in ast.walk(tree):
+            if isinstance(node, ast.Attribute) and isinstance(node.value, ast.Name) and node.value.id in ('engine', 'e', 'eng'):
+                name = node.attr
+                if name in real_attrs:
+                    continue
+                probed = ("hasattr(engine, '%s')" % name in src) or ("getattr(engine, '%s'" % name in src)
+                assert probed, '%s uses engine.%s, which FoKL._engine.Engine does not define' % (os.path.basename(mod.__file__), name)
+            if isinstance(node, ast.Call) and isinstance(node.func, ast.Attribute) and isinstance(node.func.value, ast.Name) \
+                    and node.func.value.id in ('engine', 'e', 'eng') and hasattr(real, node.func.attr):
+                params = inspect.signature(getattr(real, node.func.attr)).parameters
+                if any(p.kind == p.VAR_KEYWORD for p in params.values()):
+                    continue
+                for kw in node.keywords:
+                    if kw.arg is not None:
+                        assert kw.arg in params, 'Engine.%s has no keyword %r' % (node.func.attr, kw.arg)

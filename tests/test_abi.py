@@ -42,3 +42,24 @@ def test_product_code_never_imports_the_oracle():
             if f.endswith(('.py', '.cu', '.cuh')):
                 src = open(os.path.join(base, f)).read()
                 assert 'fokl_oracle' not in src and 'import emu' not in src, f
+
+
+def test_every_call_site_passes_the_number_of_arguments_the_prototype_declares():
+    """Static check of the ctypes call sites in FoKL/_engine.py, FoKL/FoKLRoutines.py and FoKL/_update.py: each
+    `...lib.fokl_xxx(a, b, ...)` passes exactly as many positional arguments as `_lib.PROTOTYPES['fokl_xxx']` (=
+    include/fokl_b200.h) declares -- ctypes would only say so at run time, on a GPU box."""
+    import ast
+    import inspect
+    from FoKL import FoKLRoutines, _engine, _lib, _update
+    seen = set()
+    for mod in (_engine, FoKLRoutines, _update):
+        for node in ast.walk(ast.parse(inspect.getsource(mod))):
+            if isinstance(node, ast.Call) and isinstance(node.func, ast.Attribute) and node.func.attr.startswith('fokl_') \
+                    and isinstance(node.func.value, ast.Attribute) and node.func.value.attr == 'lib':
+                name = node.func.attr
+                assert name in _lib.PROTOTYPES, name
+                assert not node.keywords and not any(isinstance(a, ast.Starred) for a in node.args), name
+                assert len(node.args) == len(_lib.PROTOTYPES[name][1]), (mod.__name__, name, node.lineno, len(node.args),
+                                                                        len(_lib.PROTOTYPES[name][1]))
+                seen.add(name)
+    assert len(seen) >= 20, sorted(seen)
